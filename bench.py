@@ -1,0 +1,500 @@
+#!/usr/bin/env python
+"""Benchmark of the U + Q95 sliding-window scoring path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one chromosome-scale batch:
+packed genotypes (resident in HBM) -> per-window N(Variants), U, Q95 and the
+candidate position lists.  Default workload = BASELINE.json configs[1]:
+synthetic 1000G-scale chr1, 6 M biallelic sites x 2504 diploid individuals
+(ref 1500 / tgt 1000 / src 4), win-len 50 kb, step 10 kb, U(w=0.01, x=0.5,
+y "=1") + Q(w=0.01, q=0.95, y "=1"), ancestral alleles available.
+
+`value`  : windows/s, whole job (all ranks), inputs resident in HBM, CUDA events.
+`e2e`    : same metric through the host-buffer C-ABI call (pinned HOST buffers
+           in, HOST results out; H2D/D2H inside the timed region).
+`roofline`: the genotype pass (K1) against the measured HBM copy bandwidth.
+`cpu_baseline`: the CPU oracle (numpy restatement of the reference) on a
+           bounded sample of the same workload, all host cores.
+
+Multi-GPU (torchrun): every rank scores its own chromosome-scale shard (weak
+scaling, no data-path collective); time = max over ranks.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(
+    name="synthetic-1000G-chr1",
+    n_sites=6_000_000,
+    n_ind=(1500, 1000, 4),  # ref / tgt / src, diploid
+    ploidy=(2, 2, 2),
+    mean_gap=41.5,  # GRCh37 chr1 249 250 621 bp / 6e6 sites
+    win_len=50_000,
+    win_step=10_000,
+    w=0.01,
+    x=0.5,
+    y=("=", 1.0),
+    quantile=0.95,
+    anc=True,
+    seed=20261018 + 2,
+)
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------
+# clocks during the timed region (pynvml; falls back to nvidia-smi once)
+# --------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.period = period_s
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _once(self):
+        nv = self.nv
+        try:
+            self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            try:
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for bit, name in self.REASONS.items():
+                if mask & bit and name != "gpu_idle":
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._once()
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is None:
+            return
+        self._stop.clear()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        if self.nv is None or self._thread is None:
+            return
+        self._once()
+        self._stop.set()
+        self._thread.join()
+        self._thread = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {
+            "sm_mhz": float(np.median(self.samples)),
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# --------------------------------------------------------------------------
+# workload construction
+# --------------------------------------------------------------------------
+def make_positions(n_sites: int, mean_gap: float, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    gaps = rng.geometric(1.0 / mean_gap, size=n_sites).astype(np.int64)
+    pos = np.cumsum(gaps)
+    assert pos[-1] < 2**31 - 1
+    return pos.astype(np.int32)
+
+
+def make_windows(pos: np.ndarray, win_len: int, win_step: int):
+    from sai_b200.windows import split_genome
+
+    wins = split_genome([int(pos[0]), int(pos[-1])], win_len, win_step)
+    ws = np.array([w[0] for w in wins], dtype=np.int64)
+    we = np.array([w[1] for w in wins], dtype=np.int64)
+    return ws, we
+
+
+def make_job_for(wl):
+    from sai_b200.scoring import make_job
+
+    return make_job(
+        0, 1, [2], wl["anc"],
+        u=dict(w=wl["w"], x=wl["x"], y_list=[wl["y"]]),
+        q=dict(w=wl["w"], quantile=wl["quantile"], y_list=[wl["y"]]),
+    )
+
+
+def algorithmic_bytes(wl, n_windows: int) -> int:
+    """S x (sum_pops N_pop x 2 bit / 8 + 4) + W x 20."""
+    per_site = sum(wl["n_ind"]) * 2 / 8 + 4
+    return int(wl["n_sites"] * per_site + n_windows * 20)
+
+
+# --------------------------------------------------------------------------
+# CPU baseline: the oracle on a bounded sample, all host cores
+# --------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_chunk(args):
+    import sai_oracle as orc
+
+    start, end = args
+    d = _CPU
+    pos = d["pos"]
+    lo, hi = np.searchsorted(pos, start, "left"), np.searchsorted(pos, end, "right")
+    sub = lambda m: {k: orc.PopData(pos[lo:hi], v[lo:hi]) for k, v in m.items()}  # region read
+    items = orc.score_chunk("1", start, end, d["win_len"], d["win_step"], sub(d["ref"]), sub(d["tgt"]), sub(d["src"]),
+                            d["pc"], d["sc"], d["anc"])
+    return len(items)
+
+
+def cpu_reference_setup(wl, sample_sites: int, seed: int):
+    """Decodes `sample_sites` of the synthetic workload (generated by the same
+    device generator, so the CPU and GPU arms see the same data model) into the
+    int64 matrices the reference holds."""
+    import ctypes as C
+
+    import torch
+
+    from sai_b200 import _cabi
+    from sai_b200.configs import PloidyConfig, StatConfig
+    from sai_b200.encode import PackedGenotypes, make_layout, unpack_population
+    from sai_b200.scoring import synth_fill
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    lay = make_layout(list(wl["n_ind"]), list(wl["ploidy"]), [2, 2, 2])
+    nbytes = int(_cabi.load().sai_packed_bytes(C.byref(lay), sample_sites))
+    d_packed = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    synth_fill(lay, d_packed, sample_sites, [0, 1, 2], seed, 0.0)
+    pos = make_positions(wl["n_sites"], wl["mean_gap"], seed)[:sample_sites]
+    pg = PackedGenotypes(lay, sample_sites, pos, d_packed.cpu().numpy())
+    del d_packed
+    mats = [unpack_population(pg, p).astype(np.int64) for p in range(3)]  # int64, as the reference holds them
+    op, y = wl["y"]
+    ystr = f"{op}{y}"
+    _CPU.update(
+        pos=pos, ref={"REF": mats[0]}, tgt={"TGT": mats[1]}, src={"SRC": mats[2]},
+        win_len=wl["win_len"], win_step=wl["win_step"], anc=wl["anc"],
+        pc=PloidyConfig({"ref": {"REF": 2}, "tgt": {"TGT": 2}, "src": {"SRC": 2}}),
+        sc=StatConfig({"U": {"ref": {"REF": wl["w"]}, "tgt": {"TGT": wl["x"]}, "src": {"SRC": ystr}},
+                       "Q": {"ref": {"REF": wl["w"]}, "tgt": {"TGT": wl["quantile"]}, "src": {"SRC": ystr}}}),
+    )
+    from sai_b200.windows import split_genome
+
+    wins = split_genome([int(pos[0]), int(pos[-1])], wl["win_len"], wl["win_step"])
+    # only windows fully inside the sample
+    return [w for w in wins if w[1] <= int(pos[-1])]
+
+
+def cpu_reference_run(wins, n_windows: int, nproc: int, pool):
+    """Scores the first `n_windows` windows of the sample, split into
+    contiguous window ranges like ChunkGenerator._split_windows_ranges
+    (8 chunks per worker, sai/sai.py:91), mapped over a process pool like
+    sai.multiprocessing.mp_pool.  Returns (windows, seconds)."""
+    from sai_b200.windows import split_windows_ranges
+
+    use = wins[:n_windows]
+    chunks = split_windows_ranges(use, max(1, min(len(use), nproc * 8)))
+    t0 = time.perf_counter()
+    done = sum(pool.map(_cpu_chunk, chunks)) if pool is not None else sum(map(_cpu_chunk, chunks))
+    return done, time.perf_counter() - t0
+
+
+def cpu_pool(nproc: int):
+    import multiprocessing as mp
+
+    if nproc <= 1:
+        return None
+    return mp.get_context("fork").Pool(nproc)
+
+
+# --------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sites", type=int, default=WORKLOAD["n_sites"], help="override the number of sites (debug)")
+    ap.add_argument("--variant", type=int, default=0, help="K1 variant (0 = carry-save popcount, 2 = direct popcount)")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--cpu-sample-sites", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debug)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    wl = dict(WORKLOAD)
+    wl["n_sites"] = args.sites
+    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        return reference_arm(args, wl, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    from sai_b200 import _cabi
+    from sai_b200.encode import PackedGenotypes, make_layout
+    from sai_b200.scoring import DeviceScorer, HostEngine, synth_fill
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- build the shard of this rank (untimed) ----
+    seed = wl["seed"] + 1000 * rank
+    lay = make_layout(list(wl["n_ind"]), list(wl["ploidy"]), [2, 2, 2])
+    S = wl["n_sites"]
+    packed_bytes = int(_cabi.load().sai_packed_bytes(C.byref(lay), S))
+    d_packed = torch.empty(packed_bytes, dtype=torch.uint8, device="cuda")
+    synth_fill(lay, d_packed, S, [0, 1, 2], seed, 0.0)
+    pos = make_positions(S, wl["mean_gap"], seed)
+    ws, we = make_windows(pos, wl["win_len"], wl["win_step"])
+    W = int(ws.shape[0])
+    d_pos, d_ws, d_we = torch.from_numpy(pos).cuda(), torch.from_numpy(ws).cuda(), torch.from_numpy(we).cuda()
+    job = make_job_for(wl)
+    sc = DeviceScorer(lay, S, W, 1, cap_u=max(4 * W, 1 << 16), cap_q=max(16 * W, 1 << 18))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        sc.step(d_packed, d_pos, d_ws, d_we, [job], args.variant)
+    torch.cuda.synchronize()
+    res = sc.results()  # also checks the candidate capacity
+    u_total, q_finite = int(res.u.sum()), int(np.isfinite(res.q).sum())
+
+    # ---- timed region: K steps, inputs resident in HBM (3.8 GB per step >> 126 MB L2) ----
+    K = args.steps
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k1a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    k1b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ev0.record()
+    for i in range(K):
+        k1a[i].record()
+        sc.site_flags(d_packed, [job], args.variant)
+        k1b[i].record()
+        sc.window_stats(d_pos, d_ws, d_we, [job])
+    ev1.record()
+    barrier()
+    clocks.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(k1a, k1b)]))
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / K
+    value = world * W / (ms_per_step / 1e3)
+
+    # ---- e2e: pinned HOST buffers -> C-ABI host engine -> HOST results ----
+    h_packed = torch.empty(packed_bytes, dtype=torch.uint8, pin_memory=True)
+    h_packed.copy_(d_packed)
+    torch.cuda.synchronize()
+    del d_packed
+    torch.cuda.empty_cache()
+    pg = PackedGenotypes(lay, S, pos, h_packed.numpy())
+    eng = HostEngine(local)
+    Ke = args.e2e_steps if args.e2e_steps is not None else max(3, min(K, 10))
+    r2 = eng.score_arrays(pg, ws, we, [job])  # warm-up (allocates device buffers)
+    same = bool(np.array_equal(r2.u, res.u) and np.array_equal(r2.q, res.q, equal_nan=True))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        r2 = eng.score_arrays(pg, ws, we, [job])
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = world * W / (t_e2e / Ke)
+    h2d = packed_bytes + pos.nbytes + ws.nbytes + we.nbytes
+    d2h = int(r2.nsnps.nbytes + r2.u.nbytes + r2.q.nbytes + r2.u_off.nbytes + r2.q_off.nbytes
+              + 4 * (int(r2.u_off[0, -1]) + int(r2.q_off[0, -1])))
+    eng.close()
+
+    # ---- roofline of the dominant kernel (K1) ----
+    peak, peak_src = measured_peaks()
+    alg = algorithmic_bytes(wl, W)
+    achieved = alg / (k1_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("n_sites") == S:
+            traffic = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        sample_sites = args.cpu_sample_sites or min(S, 240_000)
+        wins = cpu_reference_setup(wl, sample_sites, seed)
+        pool = cpu_pool(cores)
+        n_w = min(len(wins), max(8, 4 * cores))
+        done, secs = cpu_reference_run(wins, n_w, cores, pool)
+        if pool is not None:
+            pool.close()
+        cpu = {
+            "value": done / secs, "unit": "windows/s", "cores": cores, "kind": "port",
+            "sample": f"first {done} windows ({sample_sites} sites decoded to int64) of the same workload, "
+                      f"oracle/sai_oracle.py over a {cores}-process fork pool, 8 window-range chunks per worker",
+            "seconds": secs,
+        }
+
+    if rank == 0:
+        out = {
+            "metric": "u_q95_windows_per_sec",
+            "value": value,
+            "unit": "windows/s",
+            "n_gpus": world,
+            "steps": K,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "u32 bit-planes (popcount) + f64 frequency compares",
+            "data": "synthetic (device-generated, counter-based RNG)",
+            "config": {
+                "workload": f"{wl['name']}: {S} sites x {sum(wl['n_ind'])} diploid (ref {wl['n_ind'][0]}/tgt {wl['n_ind'][1]}/src {wl['n_ind'][2]}), "
+                            f"win {wl['win_len']}/{wl['win_step']}, U(w={wl['w']},x={wl['x']},y={wl['y'][0]}{wl['y'][1]}) + Q{int(wl['quantile'] * 100)}",
+                "windows_per_gpu": W,
+                "sharding": "one chromosome-scale shard per GPU, no data-path collective",
+                "l2": f"inputs ({packed_bytes / 1e9:.2f} GB per step) larger than L2 (126 MB); no explicit flush",
+                "k1_variant": args.variant,
+            },
+            "genotype_gbps": world * alg / (ms_per_step / 1e3) / 1e9,
+            "roofline": {
+                "bound": "hbm", "kernel": "k_site (genotype pass, fused site conditions)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "k1_ms": k1_ms, "algorithmic_bytes": alg,
+            },
+            "cpu_baseline": cpu,
+            "e2e": {
+                "value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": Ke, "ms_per_step": 1e3 * t_e2e / Ke, "matches_device_path": same,
+            },
+            "gpu_launches": 4 * K,
+            "clocks": clocks.summary(),
+            "check": {"u_total": u_total, "windows_with_q": q_finite},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(args, wl, rank, world):
+    """The reference's CPU implementation of the path, timed on the host cores.
+    The reference is pure Python and /root/reference does not exist on the GPU
+    box, so this runs the oracle port (oracle/sai_oracle.py, a numpy restatement
+    pinned against the reference's outputs) over all host cores, the way the
+    reference's own mp_pool + _split_windows_ranges would."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    S = wl["n_sites"]
+    sample_sites = args.cpu_sample_sites or min(S, 240_000)
+    wins = cpu_reference_setup(wl, sample_sites, wl["seed"])
+    pool = cpu_pool(cores)
+    # calibrate: one short run, then size a step to fit the whole run in ~3 minutes
+    n0 = min(len(wins), max(8, cores))
+    done, secs = cpu_reference_run(wins, n0, cores, pool)
+    rate = done / secs
+    budget = 150.0 / (args.steps + args.warmup)
+    n_w = int(max(n0, min(len(wins), rate * min(budget, 15.0))))
+    for _ in range(args.warmup):
+        cpu_reference_run(wins, n_w, cores, pool)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        d, _s = cpu_reference_run(wins, n_w, cores, pool)
+        total += d
+    elapsed = time.perf_counter() - t0
+    if pool is not None:
+        pool.close()
+    value = total / elapsed
+    sample = (f"{n_w} windows per step ({sample_sites} sites decoded to int64) of the same workload, "
+              f"oracle/sai_oracle.py over a {cores}-process fork pool, 8 window-range chunks per worker")
+    out = {
+        "impl": "reference",
+        "metric": "u_q95_windows_per_sec",
+        "value": value,
+        "unit": "windows/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "int64 allele sums + f64 (numpy)",
+        "data": "synthetic (same device generator, decoded to int64 on the host)",
+        "config": {"workload": f"{wl['name']}: bounded sample of {S} sites x {sum(wl['n_ind'])} diploid, "
+                               f"win {wl['win_len']}/{wl['win_step']}, U + Q{int(wl['quantile'] * 100)}"},
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,242 @@
+/*
+ * sai_b200.h -- C ABI of the B200-native U / Q sliding-window scoring path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  A
+ * reference-side binding (ctypes) calls these from the
+ * reference's batched entry point `ChunkPreprocessor.run(chr_name, start, end)`
+ * (sai/preprocessors/chunk_preprocessor.py:105-147), replacing the per-window
+ * Python loop
+ *     WindowGenerator._window_generator   sai/generators/window_generator.py:150-247
+ *     FeaturePreprocessor.run             sai/preprocessors/feature_preprocessor.py:63-191
+ *     UStatistic.compute                  sai/stats/u_statistic.py:37-99
+ *     QStatistic.compute                  sai/stats/q_statistic.py:37-104
+ *     compute_matching_loci / calc_freq   sai/stats/stat_utils.py:55-168 / :26-52
+ * The reference has no FFI of its own (pure Python + numpy); every entry point
+ * below names the reference interface it replaces.
+ *
+ * All functions return 0 on success or a negative SAI_E_* code; device entry
+ * points are stream-ordered and never synchronise the host.  `stream` is a
+ * cudaStream_t passed as void* (0 = legacy default stream).
+ *
+ * ---------------------------------------------------------------------------
+ * Packed genotype layout ("tiled bit-planes")
+ * ---------------------------------------------------------------------------
+ * Input encoding replaced: per-population int64 matrices of per-individual
+ * allele sums, `reshape_genotypes(is_phased=False)` sai/utils/utils.py:405-410.
+ *
+ *  - An individual's value v (sum of its alleles; any v < 0 = missing call) is
+ *    stored in `bits` = B bit-planes as the binary code of v; the all-ones code
+ *    (2^B - 1) means missing.  B = 2 covers haploid/diploid data (0,1,2,missing).
+ *  - 32 individuals of one population form a *group*: B consecutive 32-bit
+ *    words (plane 0 .. plane B-1), bit i of a word = individual 32*g + i.
+ *    Unused individuals of the last group are coded missing.
+ *  - The words of a population (groups * B of them) are laid out in 8-byte
+ *    *pairs* (padded with one zero word when odd).  A site's column is the
+ *    concatenation of its populations' pairs: `pairs_per_site` pairs.
+ *  - Sites are grouped in *tiles* of 32.  A tile is stored as
+ *        pair_t tile[pairs_per_site][32 sites]          (8-byte elements)
+ *    so that the 32 lanes of a warp read 256 contiguous bytes per pair index
+ *    and each lane owns one site.  Tiles are contiguous:
+ *        byte offset(tile T, pair p, site s) = ((T*pairs_per_site + p)*32 + s)*8
+ *    Sites beyond n_sites in the last tile are coded all-missing.
+ */
+#ifndef SAI_B200_H
+#define SAI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAI_MAX_POPS 16  /* populations in one packed matrix          */
+#define SAI_MAX_SRC 8    /* source populations of one job             */
+#define SAI_MAX_JOBS 8   /* (ref,tgt) jobs fused into one genotype pass */
+#define SAI_TILE_SITES 32
+
+enum {
+  SAI_OK = 0,
+  SAI_E_ARG = -1,      /* invalid argument (maps to the reference's ValueError) */
+  SAI_E_CUDA = -2,     /* CUDA runtime error; see sai_last_error()              */
+  SAI_E_DOMAIN = -3,   /* genotype value does not fit the bit-planes            */
+  SAI_E_CAPACITY = -4, /* candidate buffers too small; totals were written      */
+  SAI_E_NOMEM = -5
+};
+
+/* comparator of a source population, `"=", "<", ">", "<=", ">="`
+ * (sai/stats/stat_utils.py:133-139, parsed at sai/configs/stat_config.py:159-207) */
+enum { SAI_OP_EQ = 0, SAI_OP_LT = 1, SAI_OP_GT = 2, SAI_OP_LE = 3, SAI_OP_GE = 4 };
+
+typedef struct {
+  int32_t n_samples; /* individuals in the population                     */
+  int32_t ploidy;    /* configured ploidy: frequency denominator factor   */
+  int32_t bits;      /* bit-planes B (2..4)                               */
+  int32_t pair_off;  /* first pair of this population in a site column    */
+  int32_t n_pairs;   /* pairs owned by this population                    */
+  int32_t n_groups;  /* ceil(n_samples / 32)                              */
+} sai_pop_layout;
+
+typedef struct {
+  int32_t n_pops;
+  int32_t pairs_per_site;
+  sai_pop_layout pop[SAI_MAX_POPS];
+} sai_layout;
+
+/* One condition block = the arguments of compute_matching_loci
+ * (sai/stats/stat_utils.py:55-63) that are not genotypes. */
+typedef struct {
+  double w;                      /* ref_freq < w                               */
+  double y[SAI_MAX_SRC];         /* thresholds, one per source population      */
+  double one_minus_y[SAI_MAX_SRC]; /* host-computed Python-float `1 - y`
+                                    (stat_utils.py:149)                       */
+  int32_t op[SAI_MAX_SRC];       /* SAI_OP_*                                   */
+  int32_t enabled;               /* 0: statistic not requested                 */
+  int32_t pad_;
+} sai_cond;
+
+/* One job = one (ref_pop, tgt_pop, src_combination) of the population product
+ * (sai/generators/window_generator.py:164-166) with the U and Q parameters
+ * FeaturePreprocessor.run hands to the statistic classes
+ * (sai/preprocessors/feature_preprocessor.py:163-186). */
+typedef struct {
+  int32_t ref_pop;               /* index into sai_layout.pop                  */
+  int32_t tgt_pop;
+  int32_t n_src;
+  int32_t src_pop[SAI_MAX_SRC];
+  int32_t anc_allele_available;  /* 0: also try 1-y and invert (stat_utils.py:146-160) */
+  sai_cond u;                    /* UStatistic: w, y_list                      */
+  double x;                      /* UStatistic: tgt_freq > x  (u_statistic.py:92) */
+  sai_cond q;                    /* QStatistic: w, y_list                      */
+  double quantile;               /* QStatistic: quantile (q_statistic.py:100)  */
+} sai_job;
+
+/* ---- library ------------------------------------------------------------ */
+const char* sai_version(void);
+const char* sai_last_error(void); /* thread-local message of the last failure */
+
+/* ---- layout / host encode (replaces reshape_genotypes, utils.py:405-410) -- */
+/* Fills offsets for `n_pops` populations; bits[i] <= 0 selects the smallest B
+ * that holds 0..ploidy plus the missing code. */
+int sai_layout_init(sai_layout* lay, int32_t n_pops, const int32_t* n_samples,
+                    const int32_t* ploidy, const int32_t* bits);
+/* bits needed for values 0..max_value plus the missing code */
+int32_t sai_bits_for_max_value(int32_t max_value);
+int64_t sai_num_tiles(int64_t n_sites);
+uint64_t sai_packed_bytes(const sai_layout* lay, int64_t n_sites);
+
+/* Packs population `pop` of sites [0, n_sites) from a row-major int8 matrix of
+ * per-individual allele sums (`gt[site*row_stride + individual]`, negative =
+ * missing) into `packed` (host memory, sai_packed_bytes() long, all
+ * populations share it).  Call once per population.  Returns SAI_E_DOMAIN if a
+ * value exceeds the population's bit-planes.  `n_threads` <= 0: hardware
+ * concurrency. */
+int sai_pack_i8(const sai_layout* lay, int32_t pop, const int8_t* gt,
+                int64_t n_sites, int64_t row_stride, uint8_t* packed,
+                int32_t n_threads);
+/* Inverse of sai_pack_i8 for sites [site0, site0+n): missing decodes to -1. */
+int sai_unpack_i8(const sai_layout* lay, int32_t pop, const uint8_t* packed,
+                  int64_t n_sites_total, int64_t site0, int64_t n, int8_t* gt,
+                  int64_t row_stride);
+
+/* ---- K1: site counts (replaces calc_freq's passes, stat_utils.py:45-49) --- */
+/* For tiles [tile0, tile0+n_tiles): per population p and site s
+ *     num[p*stride + s]    = sum of called values      (stat_utils.py:48)
+ *     called[p*stride + s] = number of called individuals (stat_utils.py:46)
+ * d_packed points at tile 0.  variant: 0 = LDG path, 1 = TMA bulk-copy ring. */
+int sai_site_counts(const sai_layout* lay, const void* d_packed, int64_t tile0,
+                    int64_t n_tiles, int32_t* d_num, int32_t* d_called,
+                    int64_t stride, int32_t variant, void* stream);
+
+/* ---- K1 fused: counts + per-site U/Q conditions in one genotype pass ------ */
+/* Per job j and tile T writes the 32-bit masks
+ *     d_mask_u[j*n_tiles_total + T], d_mask_q[j*n_tiles_total + T]
+ * (bit s = site 32*T+s satisfies the U resp. Q condition: stat_utils.py:166,
+ * u_statistic.py:92) and, for Q-flagged sites, the (possibly inverted) target
+ * frequency d_qval[j*qval_stride + site] (q_statistic.py:92).  Optionally also
+ * stores the counts (d_num/d_called may be NULL). */
+int sai_site_flags(const sai_layout* lay, const void* d_packed, int64_t tile0,
+                   int64_t n_tiles, int64_t n_tiles_total, const sai_job* jobs,
+                   int32_t n_jobs, uint32_t* d_mask_u, uint32_t* d_mask_q,
+                   double* d_qval, int64_t qval_stride, int32_t* d_num,
+                   int32_t* d_called, int64_t count_stride, int32_t variant,
+                   void* stream);
+
+/* Same outputs computed from cached counts (threshold sweeps never re-read the
+ * genotypes). */
+int sai_flags_from_counts(const sai_layout* lay, const int32_t* d_num,
+                          const int32_t* d_called, int64_t count_stride,
+                          int64_t n_sites, const sai_job* jobs, int32_t n_jobs,
+                          uint32_t* d_mask_u, uint32_t* d_mask_q, double* d_qval,
+                          int64_t qval_stride, void* stream);
+
+/* ---- K2..K6: windows ------------------------------------------------------ */
+/* Per job j and window i (inclusive [win_start[i], win_end[i]],
+ * window_generator.py:173-174) over sorted unique positions d_pos[n_sites]:
+ *     nsnps[j*W+i]  number of sites in the window   (feature_preprocessor.py:127)
+ *     u[j*W+i]      U count                          (u_statistic.py:94-96)
+ *     q[j*W+i]      Q value, NaN if no site matches  (q_statistic.py:96-100)
+ *     u_off/q_off[j*(W+1) + i]   CSR offsets of the candidate position lists
+ *                                (u_statistic.py:95, q_statistic.py:101)
+ *     u_cand / q_cand            positions, per job at j*cap_u / j*cap_q
+ * Candidate lists longer than the capacity are clipped; offsets are always
+ * complete so the caller can re-run sai_window_stats with larger buffers. */
+int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
+                     const int64_t* d_win_end, int64_t n_windows, const sai_job* jobs,
+                     int32_t n_jobs, const uint32_t* d_mask_u, const uint32_t* d_mask_q,
+                     const double* d_qval, int64_t qval_stride, int32_t* d_nsnps,
+                     int64_t* d_u, double* d_q, int64_t* d_u_off, int64_t* d_q_off,
+                     int32_t* d_u_cand, int64_t cap_u, int32_t* d_q_cand, int64_t cap_q,
+                     void* stream);
+
+/* Re-runs only the candidate fill (K6) after sai_window_stats, e.g. with larger
+ * buffers; d_q holds the per-window Q values written by sai_window_stats. */
+int sai_fill_candidates(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
+                        const int64_t* d_win_end, int64_t n_windows, int32_t n_jobs,
+                        const uint32_t* d_mask_u, const uint32_t* d_mask_q,
+                        const double* d_qval, int64_t qval_stride, const double* d_q,
+                        const int64_t* d_u_off, const int64_t* d_q_off, int32_t* d_u_cand,
+                        int64_t cap_u, int32_t* d_q_cand, int64_t cap_q, void* stream);
+
+/* ---- host-buffer engine (replaces ChunkPreprocessor.run's inner loop) ----- */
+typedef struct sai_engine sai_engine;
+int sai_engine_create(int32_t device, sai_engine** out);
+void sai_engine_destroy(sai_engine* e);
+
+typedef struct {
+  int32_t* nsnps; /* [n_jobs*W]      */
+  int64_t* u;     /* [n_jobs*W]      */
+  double* q;      /* [n_jobs*W]      */
+  int64_t* u_off; /* [n_jobs*(W+1)]  */
+  int64_t* q_off; /* [n_jobs*(W+1)]  */
+  int32_t* u_cand; /* [n_jobs*cap_u] */
+  int32_t* q_cand; /* [n_jobs*cap_q] */
+  int64_t cap_u, cap_q;
+} sai_host_results;
+
+/* HOST pointers in, HOST results out: copies the packed tiles to the GPU in
+ * slices that overlap with the genotype pass, runs the window kernels, copies
+ * the results back and synchronises.  Returns SAI_E_CAPACITY (results other
+ * than the clipped candidate lists are valid) when cap_u / cap_q were too
+ * small. */
+int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* packed,
+                          const int32_t* pos, int64_t n_sites, const int64_t* win_start,
+                          const int64_t* win_end, int64_t n_windows, const sai_job* jobs,
+                          int32_t n_jobs, sai_host_results* out);
+
+/* After SAI_E_CAPACITY: re-runs only the candidate fill with larger host
+ * buffers; out->u_off / out->q_off must still hold the offsets returned by the
+ * failed sai_engine_score_host call. */
+int sai_engine_fetch_candidates(sai_engine* e, sai_host_results* out);
+
+/* ---- synthetic genotypes (bench / tests only) ---------------------------- */
+/* Fills tiles [tile0, tile0+n_tiles) of a packed matrix directly on the device
+ * with the synthetic model of DESIGN.md (counter-based RNG, reproducible from
+ * `seed`).  role[p]: 0 = ref-like, 1 = tgt-like, 2 = src-like population. */
+int sai_synth_fill(const sai_layout* lay, void* d_packed, int64_t tile0, int64_t n_tiles,
+                   int64_t n_sites, const int32_t* role, uint64_t seed,
+                   double missing_rate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAI_B200_H */

@@ -1,0 +1,130 @@
+"""Host-side encoding: per-individual allele-sum matrices -> tiled bit-planes.
+
+Replaces the reference's in-memory representation -- one int64 matrix
+``(sites, individuals)`` per population produced by
+``reshape_genotypes(is_phased=False)`` (sai/utils/utils.py:405-410) -- by the
+packed layout of ``include/sai_b200.h`` (2 bits per individual for ploidy <= 2).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+
+
+class PopData:
+    """Positions + per-individual allele sums of one population (the two
+    fields of the reference's ``ChromosomeData`` the scoring path reads,
+    sai/utils/genomic_dataclasses.py:25-46)."""
+
+    __slots__ = ("POS", "GT")
+
+    def __init__(self, POS, GT):
+        self.POS = np.asarray(POS)
+        self.GT = np.asarray(GT)
+
+
+def make_layout(n_samples: Sequence[int], ploidy: Sequence[int], bits: Optional[Sequence[int]] = None):
+    lib = _cabi.load()
+    n = len(n_samples)
+    if n != len(ploidy):
+        raise ValueError("n_samples and ploidy must have the same length")
+    if n > _cabi.MAX_POPS:
+        raise ValueError(f"at most {_cabi.MAX_POPS} populations per packed matrix")
+    for p in ploidy:
+        if not isinstance(p, (int, np.integer)) or isinstance(p, bool) or p <= 0:
+            raise ValueError("ploidy must be a positive integer.")
+    lay = _cabi.Layout()
+    ns = (C.c_int32 * n)(*[int(x) for x in n_samples])
+    pl = (C.c_int32 * n)(*[int(x) for x in ploidy])
+    bt = (C.c_int32 * n)(*[int(x) for x in (bits if bits is not None else [0] * n)])
+    _cabi.check(lib.sai_layout_init(C.byref(lay), n, ns, pl, bt))
+    return lay
+
+
+@dataclass
+class PackedGenotypes:
+    layout: "_cabi.Layout"
+    n_sites: int
+    pos: np.ndarray  # int32, sorted, unique
+    packed: np.ndarray  # uint8, host
+    pop_names: list = field(default_factory=list)
+
+    @property
+    def n_tiles(self) -> int:
+        return (self.n_sites + _cabi.TILE_SITES - 1) // _cabi.TILE_SITES
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.packed.nbytes)
+
+
+def _as_i8(gt: np.ndarray) -> np.ndarray:
+    gt = np.asarray(gt)
+    if gt.ndim != 2:
+        raise ValueError("genotype matrix must be 2-D (sites x individuals)")
+    if gt.dtype == np.int8 and gt.flags.c_contiguous:
+        return gt
+    # negative = missing (any negative value, sai/stats/stat_utils.py:45); large
+    # values are clipped to 127 and rejected by the packer's domain check
+    return np.ascontiguousarray(np.clip(gt, -1, 127).astype(np.int8))
+
+
+def bits_for(gt: np.ndarray, ploidy: int) -> int:
+    vmax = int(gt.max()) if gt.size else 0
+    return int(_cabi.load().sai_bits_for_max_value(max(int(ploidy), vmax)))
+
+
+def pack_populations(
+    gts: Sequence[np.ndarray],
+    ploidy: Sequence[int],
+    pos: np.ndarray,
+    pop_names: Optional[Sequence[str]] = None,
+    bits: Optional[Sequence[int]] = None,
+    n_threads: int = 0,
+    out: Optional[np.ndarray] = None,
+) -> PackedGenotypes:
+    """Packs one matrix per population (all over the same ``pos``)."""
+    lib = _cabi.load()
+    mats = [_as_i8(g) for g in gts]
+    pos = np.ascontiguousarray(np.asarray(pos), dtype=np.int32)
+    n_sites = int(pos.shape[0])
+    for m in mats:
+        if m.shape[0] != n_sites:
+            raise ValueError("every population must have one row per position")
+    if bits is None:
+        bits = [bits_for(m, p) for m, p in zip(mats, ploidy)]
+    lay = make_layout([m.shape[1] for m in mats], ploidy, bits)
+    nbytes = int(lib.sai_packed_bytes(C.byref(lay), n_sites))
+    if out is None:
+        out = np.empty(max(nbytes, 1), dtype=np.uint8)
+    elif out.nbytes < nbytes or out.dtype != np.uint8:
+        raise ValueError("output buffer too small")
+    for i, m in enumerate(mats):
+        _cabi.check(
+            lib.sai_pack_i8(
+                C.byref(lay), i, m.ctypes.data, n_sites, m.shape[1], out.ctypes.data, n_threads
+            )
+        )
+    return PackedGenotypes(lay, n_sites, pos, out[:nbytes] if nbytes else out[:0], list(pop_names or []))
+
+
+def unpack_population(pg: PackedGenotypes, pop: int, site0: int = 0, n: Optional[int] = None) -> np.ndarray:
+    """Decodes population ``pop`` back to int8 allele sums (missing = -1)."""
+    lib = _cabi.load()
+    if n is None:
+        n = pg.n_sites - site0
+    ns = pg.layout.pop[pop].n_samples
+    out = np.empty((n, ns), dtype=np.int8)
+    if n:
+        _cabi.check(
+            lib.sai_unpack_i8(
+                C.byref(pg.layout), pop, pg.packed.ctypes.data, pg.n_sites, site0, n, out.ctypes.data, ns
+            )
+        )
+    return out

@@ -1,0 +1,240 @@
+"""GPU-backed mirrors of the reference's batched entry points.
+
+``ChunkPreprocessor`` has the constructor and ``run(chr_name, start, end)`` /
+``process_items(items)`` contract of the reference class
+(sai/preprocessors/chunk_preprocessor.py:38-147) and returns item dicts with
+the schema of ``FeaturePreprocessor.run``
+(sai/preprocessors/feature_preprocessor.py:119-191), in the reference's order
+(population product outermost, windows innermost,
+sai/generators/window_generator.py:164-167) -- but the per-window Python loop
+is replaced by one call into the CUDA library per chunk.
+"""
+
+from __future__ import annotations
+
+from itertools import combinations, product
+from pathlib import Path
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _cabi
+from .encode import PopData, pack_populations
+from .scoring import HostEngine, make_job
+from .windows import chunk_windows, split_genome
+
+
+def _same_positions(members: list[PopData]) -> bool:
+    first = members[0].POS
+    return all(m.POS.shape == first.shape and np.array_equal(m.POS, first) for m in members[1:])
+
+
+def _common_rows(members: list[PopData]) -> tuple[np.ndarray, list[np.ndarray]]:
+    """Positions present in every member (window_generator.py:193-197) and each
+    member's genotype rows at those positions (:217-231)."""
+    if _same_positions(members):
+        return members[0].POS, [m.GT for m in members]
+    common = members[0].POS
+    for m in members[1:]:
+        common = np.intersect1d(common, m.POS)
+    return common, [m.GT.compress(np.isin(m.POS, common), axis=0) for m in members]
+
+
+def score_populations(
+    chr_name: str,
+    windows_by_tgt: dict[str, list[tuple[int, int]]],
+    ref_data: dict[str, PopData],
+    tgt_data: dict[str, PopData],
+    src_data: dict[str, PopData],
+    ploidy_config,
+    stat_config,
+    anc_allele_available: bool,
+    engine: HostEngine,
+    out_data: Optional[dict[str, PopData]] = None,
+    num_src: Optional[int] = None,
+) -> list[dict[str, Any]]:
+    """Item dicts for every (ref, tgt, src-combination, outgroup) x window."""
+    stats = [s for s in stat_config.root.keys() if s in ("U", "Q")]
+    num_src = len(src_data) if num_src is None else num_src
+    src_combos = list(combinations(src_data.keys(), num_src))
+    outs = list(out_data.keys()) if out_data else [None]
+    src_ploidies = ploidy_config.get_ploidy("src")
+    items: list[dict[str, Any]] = []
+
+    for ref_pop, tgt_pop, src_comb, out_pop in product(ref_data, tgt_data, src_combos, outs):
+        windows = windows_by_tgt[tgt_pop]
+        members = [ref_data[ref_pop], tgt_data[tgt_pop]] + [src_data[s] for s in src_comb]
+        if out_pop is not None:
+            members.append(out_data[out_pop])
+        pos, rows = _common_rows(members)
+        n_src = len(src_comb)
+        # positional zip of src genotypes / y_list / ploidies, exactly as
+        # feature_preprocessor.py:160,168-170 and stat_utils.py:116-119 do
+        ploidy = [ploidy_config.get_ploidy("ref", ref_pop), ploidy_config.get_ploidy("tgt", tgt_pop)]
+        ploidy += list(src_ploidies[:n_src])
+        if len(ploidy) != 2 + n_src:
+            raise ValueError("The length of src_gts_list and src ploidies must match.")
+        specs = {}
+        for s in stats:
+            prm = stat_config.get_parameters(s)
+            spec = {"w": prm["ref"][ref_pop], "y_list": list(prm["src"].values())}
+            spec["x" if s == "U" else "quantile"] = prm["tgt"][tgt_pop]
+            specs[s] = spec
+        job = make_job(0, 1, list(range(2, 2 + n_src)), anc_allele_available, specs.get("U"), specs.get("Q"))
+        pg = pack_populations(rows[: 2 + n_src], ploidy, pos)
+        res = engine.score(pg, windows, [job]) if stats else None
+        pos_dtype = np.asarray(pos).dtype
+        for i, (start, end) in enumerate(windows):
+            nsnps = int(res.nsnps[0, i]) if res is not None else int(
+                np.count_nonzero((pos >= start) & (pos <= end))
+            )
+            item = {
+                "chr_name": chr_name,
+                "start": start,
+                "end": end,
+                "ref_pop": ref_pop,
+                "tgt_pop": tgt_pop,
+                "src_pop_list": src_comb,
+                "out_pop": "NA" if out_pop is None else out_pop,
+                "nsnps": nsnps,
+                "cdd_pos": {},
+            }
+            for s in stats:
+                if nsnps == 0:  # empty window: feature_preprocessor.py:131-144
+                    item[s] = np.nan
+                    item["cdd_pos"][s] = np.array([])
+                elif s == "U":
+                    item[s] = int(res.u[0, i])
+                    item["cdd_pos"][s] = res.u_positions(0, i).astype(pos_dtype)
+                else:
+                    qv = res.q[0, i]
+                    if np.isnan(qv):  # q_statistic.py:96-98
+                        item[s] = np.nan
+                        item["cdd_pos"][s] = np.array([])
+                    else:
+                        item[s] = np.float64(qv)
+                        item["cdd_pos"][s] = res.q_positions(0, i).astype(pos_dtype)
+            items.append(item)
+    return items
+
+
+def write_items(output_file: str, items: list[dict[str, Any]], stat_config) -> None:
+    """Appends score rows and ``.U.log`` / ``.Q.log`` rows with the reference's
+    text layout (feature_preprocessor.py:193-258)."""
+    names = [s for s in stat_config.root.keys() if s in ("U", "Q") or stat_config.root[s] is True]
+    with open(output_file, "a") as f:
+        for it in items:
+            parts = []
+            for s in names:
+                v = it.get(s)
+                if isinstance(v, list) and len(v) == len(it["src_pop_list"]):
+                    parts.extend("" if x is None else str(x) for x in v)
+                else:
+                    if isinstance(v, list):
+                        v = v[0] if v else ""
+                    parts.append("" if v is None else str(v))
+            f.write(
+                f"{it['chr_name']}\t{it['start']}\t{it['end']}\t{it['ref_pop']}\t{it['tgt_pop']}\t"
+                f"{','.join(it['src_pop_list'])}\t{it['out_pop']}\t{it['nsnps']}\t" + "\t".join(parts) + "\n"
+            )
+    for key in ("U", "Q"):
+        if key not in stat_config.root:
+            continue
+        with open(Path(output_file).with_suffix(f".{key}.log"), "a") as f:
+            for it in items:
+                c = it["cdd_pos"][key]
+                txt = "NA" if c.size == 0 else ",".join(f"{it['chr_name']}:{p}" for p in c)
+                f.write(f"{it['chr_name']}\t{it['start']}\t{it['end']}\t{txt}\n")
+
+
+class ChunkPreprocessor:
+    """Drop-in for ``sai.preprocessors.ChunkPreprocessor`` on the U/Q path."""
+
+    def __init__(
+        self,
+        vcf_file: str,
+        ref_ind_file: str,
+        tgt_ind_file: str,
+        src_ind_file: str,
+        out_ind_file: Optional[str],
+        win_len: int,
+        win_step: int,
+        output_file: str,
+        ploidy_config,
+        stat_config,
+        anc_allele_file: Optional[str] = None,
+        num_src: int = 1,
+        device: int = 0,
+    ):
+        from .vcf import parse_ind_file
+
+        self.vcf_file = vcf_file
+        self.ref_ind_file = ref_ind_file
+        self.tgt_ind_file = tgt_ind_file
+        self.src_ind_file = src_ind_file
+        self.out_ind_file = out_ind_file
+        self.win_len = win_len
+        self.win_step = win_step
+        self.output_file = output_file
+        self.ploidy_config = ploidy_config
+        self.stat_config = stat_config
+        self.anc_allele_file = anc_allele_file
+        self.num_src = len(parse_ind_file(src_ind_file).keys())
+        self.anc_allele_available = anc_allele_file is not None
+        self.engine = HostEngine(device)  # picklable; CUDA context created in run()
+
+    def run(self, chr_name: str, start: int, end: int) -> list[dict[str, Any]]:
+        from .vcf import read_data
+
+        if self.win_len <= 0:
+            raise ValueError("`win_len` must be greater than 0.")
+        if self.win_step < 0:
+            raise ValueError("`win_step` must be non-negative.")
+        groups = read_data(
+            vcf_file=self.vcf_file,
+            chr_name=chr_name,
+            ploidy_config=self.ploidy_config,
+            ref_ind_file=self.ref_ind_file,
+            tgt_ind_file=self.tgt_ind_file,
+            src_ind_file=self.src_ind_file,
+            out_ind_file=self.out_ind_file,
+            anc_allele_file=self.anc_allele_file,
+            start=start,
+            end=end,
+        )
+        ref_data, ref_samples = groups["ref"]
+        tgt_data, tgt_samples = groups["tgt"]
+        src_data, src_samples = groups["src"]
+        out_data, _ = groups["outgroup"]
+        if start is None and end is None:
+            windows = {t: split_genome(tgt_data[t].POS, self.win_len, self.win_step) for t in tgt_samples}
+        else:
+            wins = chunk_windows(start, end, self.win_len, self.win_step)
+            windows = {t: wins for t in tgt_samples}
+        if ref_data is None or tgt_data is None or src_data is None:
+            return self._empty_items(chr_name, windows, ref_samples, tgt_samples, src_samples)
+        return score_populations(
+            chr_name, windows, ref_data, tgt_data, src_data, self.ploidy_config, self.stat_config,
+            self.anc_allele_available, self.engine, out_data=out_data, num_src=self.num_src,
+        )
+
+    def _empty_items(self, chr_name, windows, ref_samples, tgt_samples, src_samples):
+        # no data in the region: window_generator.py:249-289 + feature_preprocessor.py:131-144
+        stats = [s for s in self.stat_config.root.keys() if s in ("U", "Q")]
+        items = []
+        for ref_pop, tgt_pop, src_comb in product(
+            ref_samples, tgt_samples, list(combinations(src_samples.keys(), self.num_src))
+        ):
+            for start, end in windows[tgt_pop]:
+                it = {
+                    "chr_name": chr_name, "start": start, "end": end, "ref_pop": ref_pop, "tgt_pop": tgt_pop,
+                    "src_pop_list": src_comb, "out_pop": "NA", "nsnps": 0, "cdd_pos": {},
+                }
+                for s in stats:
+                    it[s] = np.nan
+                    it["cdd_pos"][s] = np.array([])
+                items.append(it)
+        return items
+
+    def process_items(self, items: list[dict[str, Any]]) -> None:
+        write_items(self.output_file, items, self.stat_config)

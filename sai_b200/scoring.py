@@ -1,0 +1,332 @@
+"""Python host layer over the C ABI: jobs, the host-buffer engine and the
+device-resident scorer.
+
+Nothing here computes a statistic on the CPU -- every number comes from the
+CUDA kernels behind ``libsai_b200.so``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from .encode import PackedGenotypes
+
+
+# --------------------------------------------------------------------------
+# jobs
+# --------------------------------------------------------------------------
+def _fill_cond(cond: "_cabi.Cond", w: float, y_list: Sequence[tuple[str, float]]) -> None:
+    # same checks, same messages as compute_matching_loci (stat_utils.py:99-108)
+    if not (0 <= w <= 1):
+        raise ValueError("Parameters w must be within the range [0, 1].")
+    for op, y in y_list:
+        if not (0 <= y <= 1):
+            raise ValueError(f"Invalid value in y_list: {y}. within the range [0, 1].")
+        if op not in _cabi.OPS:
+            raise ValueError(
+                f"Invalid operator in y_list: {op}. Must be '=', '<', '>', '<=', or '>='."
+            )
+    cond.w = float(w)
+    for k, (op, y) in enumerate(y_list):
+        cond.y[k] = float(y)
+        cond.one_minus_y[k] = 1 - y  # Python float arithmetic, as stat_utils.py:149
+        cond.op[k] = _cabi.OPS[op]
+    cond.enabled = 1
+
+
+def make_job(
+    ref_pop: int,
+    tgt_pop: int,
+    src_pops: Sequence[int],
+    anc_allele_available: bool,
+    u: Optional[dict] = None,
+    q: Optional[dict] = None,
+) -> "_cabi.Job":
+    """``u = {"w", "x", "y_list"}``, ``q = {"w", "quantile", "y_list"}`` -- the
+    keyword arguments ``UStatistic.compute`` / ``QStatistic.compute`` receive
+    (sai/preprocessors/feature_preprocessor.py:163-186)."""
+    if len(src_pops) > _cabi.MAX_SRC:
+        raise ValueError(f"at most {_cabi.MAX_SRC} source populations")
+    job = _cabi.Job()
+    job.ref_pop, job.tgt_pop, job.n_src = int(ref_pop), int(tgt_pop), len(src_pops)
+    for k, s in enumerate(src_pops):
+        job.src_pop[k] = int(s)
+    job.anc_allele_available = 1 if anc_allele_available else 0
+    for name, spec in (("u", u), ("q", q)):
+        if spec is None:
+            continue
+        if len(spec["y_list"]) != len(src_pops):
+            raise ValueError("The length of src_gts_list and y_list must match.")
+        _fill_cond(getattr(job, name), spec["w"], spec["y_list"])
+    if u is not None:
+        job.x = float(u["x"])
+    if q is not None:
+        qq = float(q["quantile"])
+        if not (0 <= qq <= 1):
+            raise ValueError("Quantiles must be in the range [0, 1]")
+        job.quantile = qq
+    return job
+
+
+def _job_array(jobs: Sequence["_cabi.Job"]):
+    if not 1 <= len(jobs) <= _cabi.MAX_JOBS:
+        raise ValueError(f"between 1 and {_cabi.MAX_JOBS} jobs per call")
+    return (_cabi.Job * len(jobs))(*jobs)
+
+
+# --------------------------------------------------------------------------
+# results
+# --------------------------------------------------------------------------
+@dataclass
+class WindowResults:
+    """Per job ``j`` and window ``i``; candidate lists in CSR form."""
+
+    nsnps: np.ndarray  # int32 [J, W]
+    u: np.ndarray  # int64 [J, W]
+    q: np.ndarray  # float64 [J, W], NaN where no site matches
+    u_off: np.ndarray  # int64 [J, W+1]
+    q_off: np.ndarray
+    u_cand: np.ndarray  # int32 [J, cap_u] positions
+    q_cand: np.ndarray
+
+    def u_positions(self, j: int, i: int) -> np.ndarray:
+        return self.u_cand[j, self.u_off[j, i] : self.u_off[j, i + 1]]
+
+    def q_positions(self, j: int, i: int) -> np.ndarray:
+        return self.q_cand[j, self.q_off[j, i] : self.q_off[j, i + 1]]
+
+
+# --------------------------------------------------------------------------
+# host-buffer engine (HOST pointers in, HOST results out)
+# --------------------------------------------------------------------------
+class HostEngine:
+    """One per GPU / worker process.  Created lazily so that an object holding
+    it can be pickled to worker processes before any CUDA context exists
+    (the reference pickles its preprocessor, sai/multiprocessing/mp_manager.py:153-164)."""
+
+    def __init__(self, device: int = 0):
+        self.device = int(device)
+        self._h = None
+
+    def _handle(self):
+        if self._h is None:
+            h = C.c_void_p()
+            _cabi.check(_cabi.load().sai_engine_create(self.device, C.byref(h)))
+            self._h = h
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            _cabi.load().sai_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __getstate__(self):
+        return {"device": self.device}
+
+    def __setstate__(self, st):
+        self.device = st["device"]
+        self._h = None
+
+    def score(
+        self,
+        pg: PackedGenotypes,
+        windows: Sequence[tuple[int, int]],
+        jobs: Sequence["_cabi.Job"],
+        cap_u: Optional[int] = None,
+        cap_q: Optional[int] = None,
+    ) -> WindowResults:
+        ws = np.ascontiguousarray([w[0] for w in windows], dtype=np.int64)
+        we = np.ascontiguousarray([w[1] for w in windows], dtype=np.int64)
+        return self.score_arrays(pg, ws, we, jobs, cap_u, cap_q)
+
+    def score_arrays(self, pg, ws, we, jobs, cap_u=None, cap_q=None) -> WindowResults:
+        lib = _cabi.load()
+        J, W = len(jobs), int(ws.shape[0])
+        cap_u = max(1, 4 * W + 1024) if cap_u is None else int(cap_u)
+        cap_q = max(1, 4 * W + 1024) if cap_q is None else int(cap_q)
+        jarr = _job_array(jobs)
+        nsnps = np.zeros((J, W), dtype=np.int32)
+        u = np.zeros((J, W), dtype=np.int64)
+        q = np.full((J, W), np.nan, dtype=np.float64)
+        u_off = np.zeros((J, W + 1), dtype=np.int64)
+        q_off = np.zeros((J, W + 1), dtype=np.int64)
+        u_cand = np.zeros((J, cap_u), dtype=np.int32)
+        q_cand = np.zeros((J, cap_q), dtype=np.int32)
+
+        def results():
+            r = _cabi.HostResults()
+            r.nsnps, r.u, r.q = nsnps.ctypes.data, u.ctypes.data, q.ctypes.data
+            r.u_off, r.q_off = u_off.ctypes.data, q_off.ctypes.data
+            r.u_cand, r.q_cand = u_cand.ctypes.data, q_cand.ctypes.data
+            r.cap_u, r.cap_q = u_cand.shape[1], q_cand.shape[1]
+            return r
+
+        pos = np.ascontiguousarray(pg.pos, dtype=np.int32)
+        res = results()
+        rc = lib.sai_engine_score_host(
+            self._handle(),
+            C.byref(pg.layout),
+            pg.packed.ctypes.data if pg.packed.size else None,
+            pos.ctypes.data if pos.size else None,
+            pg.n_sites,
+            ws.ctypes.data if W else None,
+            we.ctypes.data if W else None,
+            W,
+            jarr,
+            J,
+            C.byref(res),
+        )
+        if rc == _cabi.E_CAPACITY:
+            u_cand = np.zeros((J, max(1, int(u_off[:, W].max()))), dtype=np.int32)
+            q_cand = np.zeros((J, max(1, int(q_off[:, W].max()))), dtype=np.int32)
+            res = results()
+            rc = lib.sai_engine_fetch_candidates(self._handle(), C.byref(res))
+        _cabi.check(rc)
+        return WindowResults(nsnps, u, q, u_off, q_off, u_cand, q_cand)
+
+
+# --------------------------------------------------------------------------
+# device-resident scorer (torch tensors own the memory; C ABI gets raw pointers)
+# --------------------------------------------------------------------------
+class DeviceScorer:
+    """Runs the kernels on data already resident in HBM, on torch's current
+    stream.  torch is used for allocation and streams only."""
+
+    def __init__(self, layout, n_sites: int, n_windows: int, n_jobs: int, device=None, cap_u=None, cap_q=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("sai_b200 needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.lib = _cabi.load()
+        self.layout = layout
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_sites, self.W, self.J = int(n_sites), int(n_windows), int(n_jobs)
+        self.n_tiles = (self.n_sites + _cabi.TILE_SITES - 1) // _cabi.TILE_SITES
+        self.stride = self.n_tiles * _cabi.TILE_SITES
+        d = self.device
+        J, W = self.J, self.W
+        self.mask_u = torch.zeros((J, max(1, self.n_tiles)), dtype=torch.int32, device=d)
+        self.mask_q = torch.zeros((J, max(1, self.n_tiles)), dtype=torch.int32, device=d)
+        self.qval = torch.zeros((J, max(1, self.stride)), dtype=torch.float64, device=d)
+        self.nsnps = torch.zeros((J, W), dtype=torch.int32, device=d)
+        self.u = torch.zeros((J, W), dtype=torch.int64, device=d)
+        self.q = torch.zeros((J, W), dtype=torch.float64, device=d)
+        self.u_off = torch.zeros((J, W + 1), dtype=torch.int64, device=d)
+        self.q_off = torch.zeros((J, W + 1), dtype=torch.int64, device=d)
+        self.cap_u = max(1, 4 * W + 1024) if cap_u is None else int(cap_u)
+        self.cap_q = max(1, 4 * W + 1024) if cap_q is None else int(cap_q)
+        self.u_cand = torch.zeros((J, self.cap_u), dtype=torch.int32, device=d)
+        self.q_cand = torch.zeros((J, self.cap_q), dtype=torch.int32, device=d)
+        self.num = None
+        self.called = None
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def site_counts(self, d_packed, variant: int = 0):
+        """K1 alone: returns ``(num, called)`` int32 tensors ``[n_pops, stride]``."""
+        torch = self.torch
+        n_pops = self.layout.n_pops
+        if self.num is None:
+            self.num = torch.zeros((n_pops, max(1, self.stride)), dtype=torch.int32, device=self.device)
+            self.called = torch.zeros_like(self.num)
+        _cabi.check(
+            self.lib.sai_site_counts(
+                C.byref(self.layout), d_packed.data_ptr(), 0, self.n_tiles, self.num.data_ptr(),
+                self.called.data_ptr(), self.stride, variant, self._stream(),
+            )
+        )
+        return self.num, self.called
+
+    def site_flags(self, d_packed, jobs, variant: int = 0, with_counts: bool = False, tile0: int = 0, n_tiles=None):
+        """K1 fused: genotype pass + site conditions for ``jobs``."""
+        jarr = _job_array(jobs)
+        num = called = None
+        if with_counts:
+            if self.num is None:
+                torch = self.torch
+                self.num = torch.zeros((self.layout.n_pops, max(1, self.stride)), dtype=torch.int32, device=self.device)
+                self.called = torch.zeros_like(self.num)
+            num, called = self.num.data_ptr(), self.called.data_ptr()
+        _cabi.check(
+            self.lib.sai_site_flags(
+                C.byref(self.layout), d_packed.data_ptr(), tile0, self.n_tiles - tile0 if n_tiles is None else n_tiles,
+                self.n_tiles, jarr, len(jobs), self.mask_u.data_ptr(), self.mask_q.data_ptr(),
+                self.qval.data_ptr(), self.qval.shape[1], num, called, self.stride if with_counts else 0,
+                variant, self._stream(),
+            )
+        )
+
+    def flags_from_counts(self, jobs):
+        """Site conditions from the cached counts (threshold sweeps)."""
+        if self.num is None:
+            raise RuntimeError("site_counts() has not been run")
+        jarr = _job_array(jobs)
+        _cabi.check(
+            self.lib.sai_flags_from_counts(
+                C.byref(self.layout), self.num.data_ptr(), self.called.data_ptr(), self.stride, self.n_sites,
+                jarr, len(jobs), self.mask_u.data_ptr(), self.mask_q.data_ptr(), self.qval.data_ptr(),
+                self.qval.shape[1], self._stream(),
+            )
+        )
+
+    def window_stats(self, d_pos, d_ws, d_we, jobs):
+        jarr = _job_array(jobs)
+        _cabi.check(
+            self.lib.sai_window_stats(
+                d_pos.data_ptr(), self.n_sites, d_ws.data_ptr(), d_we.data_ptr(), self.W, jarr, len(jobs),
+                self.mask_u.data_ptr(), self.mask_q.data_ptr(), self.qval.data_ptr(), self.qval.shape[1],
+                self.nsnps.data_ptr(), self.u.data_ptr(), self.q.data_ptr(), self.u_off.data_ptr(),
+                self.q_off.data_ptr(), self.u_cand.data_ptr(), self.cap_u, self.q_cand.data_ptr(), self.cap_q,
+                self._stream(),
+            )
+        )
+
+    def step(self, d_packed, d_pos, d_ws, d_we, jobs, variant: int = 0):
+        """One pass of the hot path over device-resident inputs (4 launches)."""
+        self.site_flags(d_packed, jobs, variant)
+        self.window_stats(d_pos, d_ws, d_we, jobs)
+
+    def results(self) -> WindowResults:
+        """Copies the results to the host (synchronises); grows the candidate
+        buffers and re-fills them if they were too small."""
+        torch = self.torch
+        u_off, q_off = self.u_off.cpu().numpy(), self.q_off.cpu().numpy()
+        need_u = int(u_off[:, self.W].max()) if self.J else 0
+        need_q = int(q_off[:, self.W].max()) if self.J else 0
+        if need_u > self.cap_u or need_q > self.cap_q:
+            raise _cabi.SaiError(
+                f"candidate capacity too small (need cap_u>={need_u}, cap_q>={need_q}); "
+                "construct DeviceScorer with larger cap_u/cap_q"
+            )
+        return WindowResults(
+            self.nsnps.cpu().numpy(), self.u.cpu().numpy(), self.q.cpu().numpy(), u_off, q_off,
+            self.u_cand.cpu().numpy(), self.q_cand.cpu().numpy(),
+        )
+
+
+def synth_fill(layout, d_packed, n_sites: int, roles: Sequence[int], seed: int, missing_rate: float = 0.0,
+               tile0: int = 0, n_tiles: Optional[int] = None, stream=None):
+    """Bench/test helper: synthetic packed genotypes generated on the device."""
+    import torch
+
+    lib = _cabi.load()
+    nt = (n_sites + _cabi.TILE_SITES - 1) // _cabi.TILE_SITES
+    role = (C.c_int32 * len(roles))(*[int(r) for r in roles])
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream)
+    _cabi.check(
+        lib.sai_synth_fill(C.byref(layout), d_packed.data_ptr(), tile0, nt - tile0 if n_tiles is None else n_tiles,
+                           n_sites, role, seed, float(missing_rate), st)
+    )

@@ -1,0 +1,188 @@
+"""CPU-only checks of the C-ABI library and the host logic (no compute calls)."""
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "sai_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sai_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sai_b200 import _cabi
+
+    lib = _cabi.load()
+    declared = _declared_functions()
+    assert len(declared) >= 18
+    assert sorted(_cabi.SYMBOLS) == declared  # the ctypes table mirrors the header
+    for name in declared:
+        assert hasattr(lib, name), name
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(_cabi.lib_path())], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", nm), name
+    assert b"sm_100a" in lib.sai_version()
+
+
+def test_struct_sizes_match_header():
+    from sai_b200 import _cabi
+
+    assert C.sizeof(_cabi.PopLayout) == 24
+    assert C.sizeof(_cabi.Layout) == 8 + 24 * _cabi.MAX_POPS
+    assert C.sizeof(_cabi.Cond) == 8 + 8 * 8 + 8 * 8 + 4 * 8 + 8
+    assert C.sizeof(_cabi.Job) == 4 * 3 + 4 * 8 + 4 + 2 * C.sizeof(_cabi.Cond) + 16
+    assert C.sizeof(_cabi.HostResults) == 9 * 8
+
+
+def test_layout_and_bits():
+    from sai_b200 import _cabi
+    from sai_b200.encode import make_layout
+
+    lib = _cabi.load()
+    assert [lib.sai_bits_for_max_value(v) for v in (1, 2, 3, 4, 6, 7, 14)] == [2, 2, 3, 3, 3, 4, 4]
+    lay = make_layout([1500, 1000, 4], [2, 2, 2])
+    assert [(lay.pop[i].n_groups, lay.pop[i].n_pairs, lay.pop[i].pair_off) for i in range(3)] == [(47, 47, 0), (32, 32, 47), (1, 1, 79)]
+    assert lay.pairs_per_site == 80
+    assert lib.sai_packed_bytes(C.byref(lay), 6_000_000) == 187_500 * 80 * 256
+    assert lib.sai_num_tiles(33) == 2
+    lay3 = make_layout([33, 5], [4, 3])
+    assert (lay3.pop[0].bits, lay3.pop[0].n_pairs, lay3.pop[1].bits, lay3.pop[1].n_pairs) == (3, 3, 3, 2)
+    with pytest.raises(ValueError, match="ploidy must be a positive integer"):
+        make_layout([3], [0])
+    with pytest.raises(ValueError):
+        make_layout([3] * 17, [2] * 17)
+
+
+@pytest.mark.parametrize("n_sites", [0, 1, 31, 32, 33, 1000])
+def test_pack_unpack_roundtrip(n_sites):
+    from sai_b200.encode import pack_populations, unpack_population
+
+    rng = np.random.default_rng(n_sites)
+    mats = [rng.integers(-2, 3, size=(n_sites, 70)).astype(np.int8), rng.integers(-1, 2, size=(n_sites, 1)).astype(np.int64),
+            rng.integers(-1, 5, size=(n_sites, 33)).astype(np.int8), rng.integers(0, 9, size=(n_sites, 64)).astype(np.int8)]
+    pg = pack_populations(mats, [2, 1, 4, 8], np.arange(n_sites))
+    assert [pg.layout.pop[i].bits for i in range(4)] == [2, 2, 3, 4]
+    for i, m in enumerate(mats):
+        assert np.array_equal(unpack_population(pg, i), np.where(m < 0, -1, m).astype(np.int8))
+    if n_sites > 40:
+        assert np.array_equal(unpack_population(pg, 2, 35, 4), np.where(mats[2][35:39] < 0, -1, mats[2][35:39]))
+
+
+def test_pack_rejects_out_of_domain():
+    from sai_b200.encode import pack_populations
+
+    g = np.array([[0, 1, 3]], dtype=np.int8)
+    with pytest.raises(ValueError, match="does not fit"):
+        pack_populations([g], [2], np.arange(1), bits=[2])
+    pack_populations([g], [2], np.arange(1))  # auto: 3 bit-planes
+
+
+def test_job_validation_messages():
+    from sai_b200.scoring import make_job
+
+    with pytest.raises(ValueError, match=r"Parameters w must be within the range \[0, 1\]."):
+        make_job(0, 1, [2], True, u=dict(w=-0.1, x=0.5, y_list=[("=", 1.0)]))
+    with pytest.raises(ValueError, match="Invalid value in y_list"):
+        make_job(0, 1, [2], True, q=dict(w=0.1, quantile=0.5, y_list=[("=", 1.1)]))
+    with pytest.raises(ValueError, match="Invalid operator in y_list"):
+        make_job(0, 1, [2], True, q=dict(w=0.1, quantile=0.5, y_list=[("==", 1.0)]))
+    with pytest.raises(ValueError, match="The length of src_gts_list and y_list must match"):
+        make_job(0, 1, [2, 3], True, q=dict(w=0.1, quantile=0.5, y_list=[("=", 1.0)]))
+    j = make_job(0, 1, [2], False, u=dict(w=0.1, x=0.5, y_list=[("=", 0.8)]))
+    assert j.u.one_minus_y[0] == 1 - 0.8 == 0.19999999999999996 and j.q.enabled == 0
+
+
+def test_windows_match_oracle():
+    import sai_oracle as orc
+    from sai_b200 import windows as W
+
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        first = int(rng.integers(0, 10**6))
+        last = first + int(rng.integers(0, 10**6))
+        step = int(rng.integers(1, 60000))
+        size = step + int(rng.integers(0, 100000))
+        start = None if rng.random() < 0.5 else int(rng.integers(0, first + 2))
+        a, b = W.split_genome([first, last], size, step, start), orc.split_genome([first, last], size, step, start)
+        assert a == b
+        n = int(rng.integers(1, 9))
+        assert W.split_windows_ranges(a, n) == orc.split_windows_ranges(b, n)
+        for (s, e) in W.split_windows_ranges(a, n):
+            pass
+    wins = W.split_genome([2309, 48989], 10000, 5000)
+    assert W.split_windows_ranges(wins, 2) == [(1, 30000), (25001, 55000)]  # reference test_chunk_generator.py:39
+    # every shard re-derives exactly its own windows, in order (the halo is win_len - step)
+    for n in (1, 2, 3, 4, 8):
+        parts = [W.chunk_windows(s, e, 10000, 5000) for s, e in W.split_windows_ranges(wins, n)]
+        assert [w for p in parts for w in p] == wins
+    with pytest.raises(ValueError, match="`step_size` cannot be greater than `window_size`"):
+        W.split_genome([1, 2], 20, 25)
+    with pytest.raises(ValueError, match="`pos` array must not be empty"):
+        W.split_genome([], 30, 10)
+    with pytest.raises(ValueError, match="must be positive integers"):
+        W.split_genome([1], 0, 0)
+
+
+def test_config_mirror():
+    from sai_b200.configs import PloidyConfig, StatConfig, parse_comparator
+
+    assert parse_comparator("=1", "U", "src") == ("=", 1.0)
+    assert parse_comparator(">=0.2", "U", "src") == (">=", 0.2)
+    assert parse_comparator("<0.5", "Q", "src") == ("<", 0.5)
+    with pytest.raises(ValueError, match="must contain a valid comparator"):
+        parse_comparator("0.5", "U", "src")
+    with pytest.raises(ValueError, match="between 0 and 1"):
+        parse_comparator("=1.5", "U", "src")
+    sc = StatConfig({"U": {"ref": {"A": 0.3}, "tgt": {"B": 0.5}, "src": {"C": "=1", "D": "<=0.25"}}, "fd": True})
+    assert list(sc.get_parameters("U")["src"].values()) == [("=", 1.0), ("<=", 0.25)]
+    with pytest.raises(ValueError, match="not supported"):
+        StatConfig({"Z": True})
+    with pytest.raises(ValueError, match="exactly the keys"):
+        StatConfig({"U": {"ref": {"A": 0.3}}})
+    pc = PloidyConfig({"ref": {"A": 2}, "tgt": {"B": 4}, "src": {"C": 1, "D": 2}})
+    assert pc.get_ploidy("src") == [1, 2] and pc.get_ploidy("tgt", "B") == 4 and pc.get_ploidy("outgroup") is None
+    with pytest.raises(ValueError, match="positive integer"):
+        PloidyConfig({"ref": {"A": 0}, "tgt": {"B": 4}, "src": {"C": 1}})
+    with pytest.raises(KeyError):
+        pc.get_ploidy("ref", "nope")
+
+
+def test_vcf_ingest_semantics(tmp_path):
+    """numbers={'GT': ploidy} padding / truncation, '.' alleles, region filter,
+    ancestral-allele filter and flip (sai/utils/utils.py:78-186, 492-555)."""
+    from sai_b200.configs import PloidyConfig
+    from sai_b200.vcf import read_data
+
+    vcf = tmp_path / "t.vcf"
+    vcf.write_text(
+        "##fileformat=VCFv4.1\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\tc\n"
+        "1\t10\t.\tA\tT\t.\t.\t.\tGT\t0|1\t1/1\t.|.\n"
+        "1\t20\t.\tA\tT\t.\t.\t.\tGT:DP\t1|.:3\t0|0|1|1:4\t1:2\n"
+        "1\t30\t.\tG\tC\t.\t.\t.\tGT\t0|0\t0|1\t1|1\n"
+        "1\t40\t.\tG\tC\t.\t.\t.\tGT\t0|0\t0|1\t1|1\n"
+        "2\t10\t.\tA\tT\t.\t.\t.\tGT\t1|1\t1|1\t1|1\n"
+    )
+    for g, pops in (("ref", "R a"), ("tgt", "T b"), ("src", "S c")):
+        (tmp_path / f"{g}.list").write_text(pops.replace(" ", "\t") + "\n")
+    anc = tmp_path / "anc.bed"
+    anc.write_text("1\t9\t10\tA\n1\t19\t20\tT\n1\t29\t30\tN\n2\t9\t10\tA\n")  # pos 30: neither REF nor ALT; pos 40: absent
+    lists = [str(tmp_path / f"{g}.list") for g in ("ref", "tgt", "src")]
+    pc = PloidyConfig({"ref": {"R": 2}, "tgt": {"T": 4}, "src": {"S": 2}})
+    d = read_data(str(vcf), "1", pc, *lists, None, None)
+    assert d["ref"][0]["R"].POS.tolist() == [10, 20, 30, 40] and d["outgroup"] == (None, None)
+    assert d["ref"][0]["R"].GT[:, 0].tolist() == [1, 0, 0, 0]  # "1|." -> 1 + (-1) = 0: called (SURVEY hard part 4)
+    assert d["tgt"][0]["T"].GT[:, 0].tolist() == [0, 2, -1, -1]  # diploid read as ploidy 4: padded with -1
+    assert d["src"][0]["S"].GT[:, 0].tolist() == [-2, 0, 2, 2]  # ".|." -> -2; haploid "1" -> 1 + (-1)
+    d = read_data(str(vcf), "1", pc, *lists, None, str(anc), start=5, end=35)
+    assert d["ref"][0]["R"].POS.tolist() == [10, 20]  # 30 removed (anc not REF/ALT), 40 outside region
+    assert d["ref"][0]["R"].GT[:, 0].tolist() == [1, 2]  # pos 20 flipped: alleles (1,-1) -> (0,2)
+    assert d["src"][0]["S"].GT[:, 0].tolist() == [-2, 2]  # flipped haploid "1": (1,-1) -> (0, 2)
+    assert read_data(str(vcf), "3", pc, *lists, None, None)["ref"][0] is None

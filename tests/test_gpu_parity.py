@@ -1,0 +1,455 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle
+and against the reference-generated golden fixtures.
+
+Bars: U, N(Variants), candidate position lists bit-exact; Q bit-exact on every
+fixture (the contract is |dQ| <= 1e-12 absolute, NaN <-> NaN -- asserted as
+well so a regression shows which bar broke)."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sai_oracle as orc
+import synth
+from helpers import GOLDEN, SimplePloidy, SimpleStats, check_items, load_pipe_case, pipe_case_names, vcf_case_names
+
+pytestmark = pytest.mark.gpu
+
+Q_TOL = 1e-12  # absolute tolerance stated by BASELINE.json's north_star
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from sai_b200.scoring import HostEngine
+
+    e = HostEngine(0)
+    yield e
+    e.close()
+
+
+def _pop(pos, m):
+    from sai_b200.encode import PopData
+
+    return PopData(pos, m)
+
+
+# ---------------------------------------------------------------- stat-class level
+from test_oracle_golden import Q_KATS, U_KATS  # noqa: E402  (the reference's KATs)
+
+
+@pytest.mark.parametrize("case", U_KATS)
+def test_u_kat_gpu(case):
+    from sai_b200.stats import STAT_REGISTRY
+
+    ref, tgt, srcs, pl, w, x, y_list, anc, exp_u, exp_pos = case
+    stat = STAT_REGISTRY.get("U")(ref_gts=np.array(ref), tgt_gts=np.array(tgt), src_gts_list=[np.array(s) for s in srcs],
+                                  ref_ploidy=pl[0], tgt_ploidy=pl[1], src_ploidy_list=pl[2:])
+    res = stat.compute(pos=np.arange(len(ref)), w=w, x=x, y_list=y_list, anc_allele_available=anc)
+    assert res["name"] == "U" and res["value"] == exp_u
+    assert np.array_equal(res["cdd_pos"], np.array(exp_pos))
+
+
+@pytest.mark.parametrize("case", Q_KATS)
+def test_q_kat_gpu(case):
+    from sai_b200.stats import STAT_REGISTRY
+
+    ref, tgt, srcs, pl, w, y_list, q, anc, exp_q, exp_pos = case
+    stat = STAT_REGISTRY.get("Q")(ref_gts=np.array(ref), tgt_gts=np.array(tgt), src_gts_list=[np.array(s) for s in srcs],
+                                  ref_ploidy=pl[0], tgt_ploidy=pl[1], src_ploidy_list=pl[2:])
+    res = stat.compute(pos=np.arange(len(ref)), w=w, y_list=y_list, quantile=q, anc_allele_available=anc)
+    assert res["name"] == "Q"
+    if np.isnan(exp_q):
+        assert np.isnan(res["value"])
+    else:
+        assert np.isclose(res["value"], exp_q)
+    assert np.array_equal(res["cdd_pos"], np.array(exp_pos))
+
+
+def test_q_edge_case_exact_gpu():
+    from sai_b200.stats import QStatistic
+
+    c = Q_KATS[4]
+    res = QStatistic(ref_gts=np.array(c[0]), tgt_gts=np.array(c[1]), src_gts_list=[np.array(c[2][0])], ref_ploidy=1,
+                     tgt_ploidy=1, src_ploidy_list=[1]).compute(
+        pos=np.arange(3), w=0.95, y_list=[("=", 1.0)], quantile=0.95, anc_allele_available=False)
+    assert float(res["value"]) == 0.9666666666666667
+
+
+def test_stat_errors_gpu():
+    from sai_b200.stats import QStatistic, UStatistic
+
+    z = np.zeros((2, 2), int)
+    kw = dict(ref_gts=z, tgt_gts=z, src_gts_list=[z], ref_ploidy=2, tgt_ploidy=2, src_ploidy_list=[2])
+    with pytest.raises(ValueError, match="Missing required argument"):
+        UStatistic(**kw).compute(pos=np.arange(2), w=0.5, x=0.5, y_list=[("=", 0)])
+    with pytest.raises(ValueError, match="Missing required argument"):
+        QStatistic(**kw).compute(pos=np.arange(2), w=0.5, quantile=0.95, anc_allele_available=False)
+    with pytest.raises(ValueError, match=r"Parameters w must be within the range \[0, 1\]."):
+        UStatistic(**kw).compute(pos=np.arange(2), w=1.1, x=0.5, y_list=[("=", 0)], anc_allele_available=True)
+    with pytest.raises(ValueError, match="Invalid value in y_list"):
+        UStatistic(**kw).compute(pos=np.arange(2), w=0.1, x=0.5, y_list=[("=", 1.5)], anc_allele_available=True)
+    with pytest.raises(ValueError, match="Invalid operator in y_list"):
+        UStatistic(**kw).compute(pos=np.arange(2), w=0.1, x=0.5, y_list=[("!", 0.5)], anc_allele_available=True)
+    with pytest.raises(ValueError, match="The length of src_gts_list and y_list must match"):
+        UStatistic(**kw).compute(pos=np.arange(2), w=0.1, x=0.5, y_list=[("=", 0.5)] * 2, anc_allele_available=True)
+    with pytest.raises(ValueError, match="ploidy must be a positive integer"):
+        UStatistic(**{**kw, "ref_ploidy": 0}).compute(pos=np.arange(2), w=0.1, x=0.5, y_list=[("=", 0.5)], anc_allele_available=True)
+
+
+def test_stat_cases_gpu():
+    """400 random cases whose expected outputs came from the reference's own
+    UStatistic / QStatistic (tests/golden/make_golden.py)."""
+    from sai_b200.stats import QStatistic, UStatistic
+
+    meta = json.load(open(os.path.join(GOLDEN, "stat_cases.json")))
+    arrs = np.load(os.path.join(GOLDEN, "stat_cases.npz"))
+    for c, m in enumerate(meta):
+        mats = [arrs[f"c{c}_g{k}"] for k in range(2 + m["n_src"])]
+        pos = arrs[f"c{c}_pos"]
+        y_list = [tuple(y) for y in m["y_list"]]
+        pl = m["ploidy"]
+        kw = dict(ref_gts=mats[0], tgt_gts=mats[1], src_gts_list=mats[2:], ref_ploidy=pl[0], tgt_ploidy=pl[1], src_ploidy_list=pl[2:])
+        ru = UStatistic(**kw).compute(pos=pos, w=m["w"], x=m["x"], y_list=y_list, anc_allele_available=m["anc"])
+        rq = QStatistic(**kw).compute(pos=pos, w=m["w"], quantile=m["q"], y_list=y_list, anc_allele_available=m["anc"])
+        assert ru["value"] == m["U"], c
+        assert [int(p) for p in ru["cdd_pos"]] == m["U_pos"], c
+        if m["Q"] == "nan":
+            assert np.isnan(rq["value"]), c
+        else:
+            assert abs(float(rq["value"]) - float.fromhex(m["Q"])) <= Q_TOL, c
+            assert float(rq["value"]).hex() == m["Q"], c
+        assert [int(p) for p in rq["cdd_pos"]] == m["Q_pos"], c
+
+
+# ---------------------------------------------------------------- pipeline level
+@pytest.mark.parametrize("name", pipe_case_names())
+def test_pipeline_golden_gpu(name, engine, tmp_path):
+    from sai_b200.preprocessors import score_populations, write_items
+    from sai_b200.windows import chunk_windows
+
+    case, pos, data = load_pipe_case(name)
+    wins = chunk_windows(case["start"], case["end"], case["win_len"], case["win_step"])
+    mk = lambda d: {p: _pop(pos, m) for p, m in d.items()}
+    stats = SimpleStats(case["stats"])
+    items = score_populations(case["chr_name"], {t: wins for t in data["tgt"]}, mk(data["ref"]), mk(data["tgt"]),
+                              mk(data["src"]), SimplePloidy(case["ploidies"]), stats, case["anc"], engine)
+    check_items(items, case["items"], q_tol=Q_TOL)
+    check_items(items, case["items"], q_tol=0.0)  # and bit-exact, so the TSV text is identical
+    out = tmp_path / "scores.tsv"
+    write_items(str(out), items, stats)
+    assert out.read_text() == case["text"]["tsv"]
+    for key in ("U", "Q"):
+        if key in case["text"]:
+            assert (tmp_path / f"scores.{key}.log").read_text() == case["text"][key]
+
+
+@pytest.mark.parametrize("name", vcf_case_names())
+def test_vcf_fixture_gpu(name, tmp_path):
+    """VCF file -> ChunkPreprocessor.run -> process_items, against the outputs
+    of the reference pipeline on the same records."""
+    from sai_b200.preprocessors import ChunkPreprocessor
+
+    case = json.load(open(os.path.join(GOLDEN, f"vcf_{name}.json")))
+    stats = SimpleStats(case["stats"])
+    out = tmp_path / "scores.tsv"
+    pre = ChunkPreprocessor(
+        vcf_file=os.path.join(GOLDEN, case["vcf"]),
+        ref_ind_file=os.path.join(GOLDEN, f"vcf_{name}.ref.list"),
+        tgt_ind_file=os.path.join(GOLDEN, f"vcf_{name}.tgt.list"),
+        src_ind_file=os.path.join(GOLDEN, f"vcf_{name}.src.list"),
+        out_ind_file=None, win_len=case["win_len"], win_step=case["win_step"], output_file=str(out),
+        ploidy_config=SimplePloidy(case["ploidies"]), stat_config=stats,
+        anc_allele_file=os.path.join(GOLDEN, f"vcf_{name}.anc.bed") if case["anc"] else None)
+    items = pre.run(case["chr_name"], case["start"], case["end"])
+    check_items(items, case["items"], q_tol=0.0)
+    pre.process_items(items)
+    assert out.read_text() == case["text"]["tsv"]
+    if name == "example_q":
+        assert float(items[0]["Q"]) == 0.9  # reference tests/test_sai.py:63
+    if name == "example_u":
+        assert items[0]["U"] == 3  # reference tests/preprocessors/test_feature_preprocessor.py:223
+    if name == "mixed_ploidy":
+        assert [it["U"] for it in items] == [0, 1]  # reference tests/test_sai.py:150-151
+
+
+# ---------------------------------------------------------------- K1 alone
+@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("shape", [(1, [1, 1, 1]), (33, [5, 40, 2]), (1000, [257, 96, 3]), (4097, [1500, 1000, 4])])
+def test_site_counts_vs_oracle(variant, shape):
+    import torch
+
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import DeviceScorer
+
+    n_sites, n_ind = shape
+    rng = np.random.default_rng(n_sites)
+    ploidy = [2, 1, 4]
+    mats = []
+    for n, p in zip(n_ind, ploidy):
+        g = rng.integers(0, p + 1, size=(n_sites, n)).astype(np.int8)
+        g[rng.random(g.shape) < 0.1] = -1
+        g[rng.random(n_sites) < 0.05] = -2  # whole population missing at some sites
+        mats.append(g)
+    pg = pack_populations(mats, ploidy, np.arange(n_sites))
+    sc = DeviceScorer(pg.layout, n_sites, 0, 1)
+    d_packed = torch.from_numpy(pg.packed).cuda()
+    num, called = sc.site_counts(d_packed, variant)
+    num, called = num.cpu().numpy(), called.cpu().numpy()
+    for i, g in enumerate(mats):
+        en, ec = orc.site_counts(g)
+        assert np.array_equal(num[i, :n_sites], en), (i, variant)
+        assert np.array_equal(called[i, :n_sites], ec), (i, variant)
+        assert not called[i, n_sites:].any()  # padding sites are all-missing
+
+
+# ---------------------------------------------------------------- randomized differential
+def _random_case(seed, n_sites, anc, missing, stats, pops, gap=60.0, win=(20000, 5000)):
+    pos, mats = synth.make_populations(seed, n_sites, pops, mean_gap=gap, introgressed=0.02, missing=missing,
+                                       src_all_missing=0.002 if missing else 0.0)
+    ploidies = {g: {p: pops[g][p][1] for p in pops[g]} for g in pops}
+    end = int(pos[-1]) // win[1] * win[1] + win[0]
+    return pos, mats, ploidies, (1, end), win
+
+
+@pytest.mark.parametrize("seed, anc, missing", [(11, True, 0.0), (12, False, 0.01), (13, False, 0.2), (14, True, 0.05)])
+def test_differential_vs_oracle(seed, anc, missing, engine):
+    from sai_b200.preprocessors import score_populations
+    from sai_b200.windows import chunk_windows
+
+    pops = {"ref": {"R": (300, 2)}, "tgt": {"T": (200, 2)}, "src": {"N": (2, 2), "D": (1, 2)}}
+    stats = {"U": {"ref": {"R": 0.02}, "tgt": {"T": 0.3}, "src": {"N": "=1", "D": ">=0.5"}},
+             "Q": {"ref": {"R": 0.1}, "tgt": {"T": 0.95}, "src": {"N": ">=0.5", "D": "=1"}}}
+    pos, mats, ploidies, (start, end), win = _random_case(seed, 20000, anc, missing, stats, pops)
+    sc, pc = SimpleStats(stats), SimplePloidy(ploidies)
+    wins = chunk_windows(start, end, *win)
+    got = score_populations("7", {"T": wins}, {p: _pop(pos, m) for p, m in mats["ref"].items()},
+                            {p: _pop(pos, m) for p, m in mats["tgt"].items()},
+                            {p: _pop(pos, m) for p, m in mats["src"].items()}, pc, sc, anc, engine)
+    mk = lambda d: {p: orc.PopData(pos, m.astype(np.int64)) for p, m in d.items()}
+    exp = orc.score_chunk("7", start, end, win[0], win[1], mk(mats["ref"]), mk(mats["tgt"]), mk(mats["src"]), pc, sc, anc)
+    assert len(got) == len(exp) == len(wins)
+    n_q = 0
+    for g, e in zip(got, exp):
+        assert (g["start"], g["end"], g["nsnps"]) == (e["start"], e["end"], e["nsnps"])
+        for s in ("U", "Q"):
+            if isinstance(e[s], float) and np.isnan(e[s]):
+                assert np.isnan(g[s])
+            elif s == "U":
+                assert g[s] == e[s]
+            else:
+                n_q += 1
+                assert abs(float(g[s]) - float(e[s])) <= Q_TOL
+                assert float(g[s]) == float(e[s])
+            assert np.array_equal(np.asarray(g["cdd_pos"][s]), np.asarray(e["cdd_pos"][s]))
+    assert n_q > 10
+
+
+def test_large_window_selection_paths(engine):
+    """Windows with > 32 and > 1024 flagged sites exercise the shared-memory
+    radix select and the unbuffered (global) select."""
+    from sai_b200.preprocessors import score_populations
+
+    pops = {"ref": {"R": (37, 2)}, "tgt": {"T": (211, 2)}, "src": {"S": (1, 2)}}
+    stats = {"U": {"ref": {"R": 1.0}, "tgt": {"T": 0.0}, "src": {"S": ">=0"}},
+             "Q": {"ref": {"R": 1.0}, "tgt": {"T": 0.95}, "src": {"S": ">=0"}}}
+    pos, mats = synth.make_populations(21, 9000, pops, mean_gap=10.0, missing=0.15)
+    wins = [(1, 400), (1, 3000), (1, 20000), (1, int(pos[-1])), (5000, 60000), (int(pos[-1]) + 5, int(pos[-1]) + 50)]
+    ploidies = {g: {p: pops[g][p][1] for p in pops[g]} for g in pops}
+    sc, pc = SimpleStats(stats), SimplePloidy(ploidies)
+    for anc in (True, False):
+        got = score_populations("1", {"T": wins}, {"R": _pop(pos, mats["ref"]["R"])}, {"T": _pop(pos, mats["tgt"]["T"])},
+                                {"S": _pop(pos, mats["src"]["S"])}, pc, sc, anc, engine)
+        for it, (s, e) in zip(got, wins):
+            keep = (pos >= s) & (pos <= e)
+            if not keep.any():
+                assert it["nsnps"] == 0 and np.isnan(it["U"]) and np.isnan(it["Q"])
+                continue
+            sub = lambda m: m[keep].astype(np.int64)
+            eu = orc.u_statistic(sub(mats["ref"]["R"]), sub(mats["tgt"]["T"]), [sub(mats["src"]["S"])], 2, 2, [2],
+                                 pos=pos[keep], w=1.0, x=0.0, y_list=[(">=", 0.0)], anc_allele_available=anc)
+            eq = orc.q_statistic(sub(mats["ref"]["R"]), sub(mats["tgt"]["T"]), [sub(mats["src"]["S"])], 2, 2, [2],
+                                 pos=pos[keep], w=1.0, quantile=0.95, y_list=[(">=", 0.0)], anc_allele_available=anc)
+            assert it["nsnps"] == int(keep.sum())
+            assert it["U"] == eu["value"] and np.array_equal(it["cdd_pos"]["U"], eu["cdd_pos"])
+            assert float(it["Q"]) == float(eq["value"])
+            assert np.array_equal(it["cdd_pos"]["Q"], eq["cdd_pos"])
+    assert max(it["nsnps"] for it in got) > 1024
+
+
+# ---------------------------------------------------------------- device-resident path == host-buffer path
+def test_device_scorer_matches_engine_and_cached_counts(engine):
+    import torch
+
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import DeviceScorer, make_job
+    from sai_b200.windows import split_genome
+
+    pops = {"ref": {"R": (150, 2)}, "tgt": {"T1": (90, 2), "T2": (70, 1)}, "src": {"S": (3, 2)}}
+    pos, mats = synth.make_populations(31, 30000, pops, mean_gap=50.0, introgressed=0.02, missing=0.02)
+    gts = [mats["ref"]["R"], mats["tgt"]["T1"], mats["tgt"]["T2"], mats["src"]["S"]]
+    pg = pack_populations(gts, [2, 2, 1, 2], pos)
+    wins = split_genome(pos, 50000, 10000)
+    jobs = [
+        make_job(0, 1, [3], True, u=dict(w=0.05, x=0.2, y_list=[("=", 1.0)]), q=dict(w=0.05, quantile=0.95, y_list=[("=", 1.0)])),
+        make_job(0, 2, [3], False, u=dict(w=0.3, x=0.1, y_list=[(">=", 0.5)]), q=dict(w=0.5, quantile=0.5, y_list=[("<", 0.5)])),
+    ]
+    ref = engine.score(pg, wins, jobs)
+    d_packed = torch.from_numpy(pg.packed).cuda()
+    d_pos = torch.from_numpy(pg.pos).cuda()
+    d_ws = torch.tensor([w[0] for w in wins], dtype=torch.int64, device="cuda")
+    d_we = torch.tensor([w[1] for w in wins], dtype=torch.int64, device="cuda")
+    for mode in ("fused", "counts", "simple"):
+        sc = DeviceScorer(pg.layout, pg.n_sites, len(wins), len(jobs))
+        if mode == "fused":
+            sc.step(d_packed, d_pos, d_ws, d_we, jobs)
+        elif mode == "simple":
+            sc.step(d_packed, d_pos, d_ws, d_we, jobs, variant=2)
+        else:
+            sc.site_counts(d_packed)
+            sc.flags_from_counts(jobs)
+            sc.window_stats(d_pos, d_ws, d_we, jobs)
+        got = sc.results()
+        assert np.array_equal(got.nsnps, ref.nsnps) and np.array_equal(got.u, ref.u), mode
+        assert np.array_equal(got.q, ref.q, equal_nan=True), mode
+        assert np.array_equal(got.u_off, ref.u_off) and np.array_equal(got.q_off, ref.q_off), mode
+        for j in range(len(jobs)):
+            nu, nq = int(ref.u_off[j, -1]), int(ref.q_off[j, -1])
+            assert np.array_equal(got.u_cand[j, :nu], ref.u_cand[j, :nu]), mode
+            assert np.array_equal(got.q_cand[j, :nq], ref.q_cand[j, :nq]), mode
+    assert ref.u.sum() > 0 and np.isfinite(ref.q).sum() > 10
+
+
+def test_candidate_capacity_retry(engine):
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import make_job
+
+    rng = np.random.default_rng(5)
+    n = 5000
+    gts = [np.zeros((n, 8), np.int8), rng.integers(1, 3, size=(n, 8)).astype(np.int8), np.full((n, 1), 2, np.int8)]
+    pg = pack_populations(gts, [2, 2, 2], np.arange(1, n + 1))
+    job = make_job(0, 1, [2], True, u=dict(w=0.5, x=0.1, y_list=[("=", 1.0)]), q=dict(w=0.5, quantile=0.0, y_list=[("=", 1.0)]))
+    wins = [(1, n), (1, n // 2)]
+    res = engine.score(pg, wins, [job], cap_u=10, cap_q=10)  # far too small: every site is a candidate
+    assert res.u[0].tolist() == [n, n // 2]
+    assert np.array_equal(res.u_positions(0, 0), np.arange(1, n + 1))
+    assert np.array_equal(res.q_positions(0, 1), np.arange(1, n // 2 + 1))
+
+
+# ---------------------------------------------------------------- synthetic generator + full-size properties
+def _synth_setup(n_sites, n_ind=(1500, 1000, 4), missing=0.0, seed=20261019):
+    import torch
+
+    from sai_b200.encode import make_layout
+    from sai_b200.scoring import synth_fill
+    from sai_b200 import _cabi
+    import ctypes as C
+
+    lay = make_layout(list(n_ind), [2, 2, 2], [2, 2, 2])
+    nbytes = int(_cabi.load().sai_packed_bytes(C.byref(lay), n_sites))
+    d_packed = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    synth_fill(lay, d_packed, n_sites, [0, 1, 2], seed, missing)
+    return lay, d_packed
+
+
+def test_synthetic_subrange_vs_oracle():
+    """Decodes slices of the device-generated matrix and checks the GPU results
+    of the windows inside them against the oracle."""
+    import torch
+
+    from sai_b200.encode import PackedGenotypes, unpack_population
+    from sai_b200.scoring import DeviceScorer, make_job
+
+    n_sites = 64 * 1024
+    for missing in (0.0, 0.01):
+        lay, d_packed = _synth_setup(n_sites, (300, 200, 4), missing)
+        pos = (np.arange(n_sites, dtype=np.int64) * 40 + 17).astype(np.int32)
+        wins = [(s, s + 49999) for s in range(1, int(pos[-1]), 10000)]
+        anc = missing == 0.0
+        job = make_job(0, 1, [2], anc, u=dict(w=0.01, x=0.5, y_list=[("=", 1.0)]), q=dict(w=0.01, quantile=0.95, y_list=[("=", 1.0)]))
+        sc = DeviceScorer(lay, n_sites, len(wins), 1)
+        d_pos = torch.from_numpy(pos).cuda()
+        d_ws = torch.tensor([w[0] for w in wins], dtype=torch.int64, device="cuda")
+        d_we = torch.tensor([w[1] for w in wins], dtype=torch.int64, device="cuda")
+        sc.step(d_packed, d_pos, d_ws, d_we, [job])
+        got = sc.results()
+        pg = PackedGenotypes(lay, n_sites, pos, d_packed.cpu().numpy())
+        mats = [unpack_population(pg, p).astype(np.int64) for p in range(3)]
+        assert got.u.sum() > 0
+        for i in range(0, len(wins), 7):
+            s, e = wins[i]
+            keep = (pos >= s) & (pos <= e)
+            eu = orc.u_statistic(mats[0][keep], mats[1][keep], [mats[2][keep]], 2, 2, [2], pos=pos[keep], w=0.01, x=0.5,
+                                 y_list=[("=", 1.0)], anc_allele_available=anc)
+            eq = orc.q_statistic(mats[0][keep], mats[1][keep], [mats[2][keep]], 2, 2, [2], pos=pos[keep], w=0.01,
+                                 quantile=0.95, y_list=[("=", 1.0)], anc_allele_available=anc)
+            assert got.nsnps[0, i] == keep.sum()
+            assert got.u[0, i] == eu["value"]
+            assert np.array_equal(got.u_positions(0, i), eu["cdd_pos"])
+            assert (np.isnan(got.q[0, i]) and np.isnan(eq["value"])) or got.q[0, i] == float(eq["value"])
+            assert np.array_equal(got.q_positions(0, i), np.asarray(eq["cdd_pos"], dtype=np.int32))
+
+
+def test_full_size_properties():
+    """BASELINE config 2 shape (6 M sites x 2504 diploid individuals): size-
+    independent properties -- disjoint windows tile the genome (sum of U ==
+    number of U-flagged sites == number of U candidates, sum of N(Variants) ==
+    sites), overlapping 50 kb windows equal the sum of their five 10 kb parts,
+    re-running is bit-identical, and a decoded slice matches the oracle."""
+    import torch
+
+    from sai_b200.encode import PackedGenotypes, unpack_population
+    from sai_b200.scoring import DeviceScorer, make_job
+
+    n_sites = 6_000_000
+    lay, d_packed = _synth_setup(n_sites)
+    rng = np.random.default_rng(3)
+    pos = np.cumsum(rng.geometric(1 / 41.5, size=n_sites)).astype(np.int32)
+    d_pos = torch.from_numpy(pos).cuda()
+    job = make_job(0, 1, [2], True, u=dict(w=0.01, x=0.5, y_list=[("=", 1.0)]), q=dict(w=0.01, quantile=0.95, y_list=[("=", 1.0)]))
+    last = int(pos[-1])
+    small = [(s, s + 9999) for s in range(1, last + 1, 10000)]
+    big = [(s, s + 49999) for s in range(1, last + 1, 10000)]
+
+    def run(wins):
+        sc = DeviceScorer(lay, n_sites, len(wins), 1, cap_u=400_000, cap_q=2_000_000)
+        d_ws = torch.tensor([w[0] for w in wins], dtype=torch.int64, device="cuda")
+        d_we = torch.tensor([w[1] for w in wins], dtype=torch.int64, device="cuda")
+        sc.step(d_packed, d_pos, d_ws, d_we, [job])
+        return sc, sc.results()
+
+    sc_s, rs = run(small)
+    flagged_u = int(sum(bin(int(x) & 0xFFFFFFFF).count("1") for x in sc_s.mask_u.cpu().numpy().ravel()))
+    assert int(rs.nsnps.sum()) == n_sites
+    assert int(rs.u.sum()) == flagged_u == int(rs.u_off[0, -1]) and flagged_u > 1000
+    assert np.all(np.diff(rs.u_cand[0, :flagged_u]) > 0)  # candidates come out in genome order
+    _, rb = run(big)
+    k = len(small)
+    cs = np.concatenate([[0], np.cumsum(rs.u[0])])
+    cn = np.concatenate([[0], np.cumsum(rs.nsnps[0].astype(np.int64))])
+    hi = np.minimum(np.arange(k) + 5, k)
+    assert np.array_equal(rb.u[0], cs[hi] - cs[np.arange(k)])
+    assert np.array_equal(rb.nsnps[0], cn[hi] - cn[np.arange(k)])
+    _, rb2 = run(big)
+    assert np.array_equal(rb.q, rb2.q, equal_nan=True) and np.array_equal(rb.u, rb2.u)
+    # decoded slice vs oracle
+    t0, nt = 100_000, 256
+    pps = lay.pairs_per_site
+    sl = d_packed[t0 * pps * 256 : (t0 + nt) * pps * 256].cpu().numpy()
+    sub_pos = pos[t0 * 32 : (t0 + nt) * 32]
+    pg = PackedGenotypes(lay, nt * 32, sub_pos, sl)
+    mats = [unpack_population(pg, p).astype(np.int64) for p in range(3)]
+    checked = 0
+    for i, (s, e) in enumerate(big):
+        if s < sub_pos[0] or e > sub_pos[-1]:
+            continue
+        keep = (sub_pos >= s) & (sub_pos <= e)
+        eu = orc.u_statistic(mats[0][keep], mats[1][keep], [mats[2][keep]], 2, 2, [2], pos=sub_pos[keep], w=0.01, x=0.5,
+                             y_list=[("=", 1.0)], anc_allele_available=True)
+        eq = orc.q_statistic(mats[0][keep], mats[1][keep], [mats[2][keep]], 2, 2, [2], pos=sub_pos[keep], w=0.01,
+                             quantile=0.95, y_list=[("=", 1.0)], anc_allele_available=True)
+        assert rb.u[0, i] == eu["value"] and rb.nsnps[0, i] == keep.sum()
+        assert (np.isnan(rb.q[0, i]) and np.isnan(eq["value"])) or rb.q[0, i] == float(eq["value"])
+        checked += 1
+    assert checked >= 10
