@@ -169,33 +169,28 @@ int sai_flags_from_counts(const sai_layout* lay, const int32_t* d_num,
                           uint32_t* d_mask_u, uint32_t* d_mask_q, double* d_qval,
                           int64_t qval_stride, void* stream);
 
-/* ---- K2..K6: windows ------------------------------------------------------ */
+/* ---- K4: windows (one launch) --------------------------------------------- */
 /* Per job j and window i (inclusive [win_start[i], win_end[i]],
  * window_generator.py:173-174) over sorted unique positions d_pos[n_sites]:
- *     nsnps[j*W+i]  number of sites in the window   (feature_preprocessor.py:127)
- *     u[j*W+i]      U count                          (u_statistic.py:94-96)
- *     q[j*W+i]      Q value, NaN if no site matches  (q_statistic.py:96-100)
- *     u_off/q_off[j*(W+1) + i]   CSR offsets of the candidate position lists
- *                                (u_statistic.py:95, q_statistic.py:101)
- *     u_cand / q_cand            positions, per job at j*cap_u / j*cap_q
- * Candidate lists longer than the capacity are clipped; offsets are always
- * complete so the caller can re-run sai_window_stats with larger buffers. */
+ *     nsnps[j*W+i]    number of sites in the window   (feature_preprocessor.py:127)
+ *     u[j*W+i]        U count                          (u_statistic.py:94-96)
+ *     q[j*W+i]        Q value, NaN if no site matches  (q_statistic.py:96-100)
+ *     q_cnt[j*W+i]    number of Q candidate positions  (q_statistic.py:101)
+ *     u_start/q_start[j*W+i]  where the window's candidate positions start in
+ *                     d_u_cand + j*cap_u / d_q_cand + j*cap_q; a window's list
+ *                     is contiguous and in genome order (u[..] resp. q_cnt[..]
+ *                     entries); the order of windows inside the buffer is
+ *                     arbitrary (space is reserved with one atomic per window)
+ *     totals[j*2+0/1] candidates of job j (U / Q).  Lists that do not fit
+ *                     cap_u / cap_q are clipped: call again with larger buffers
+ *                     when a total exceeds its capacity. */
 int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
                      const int64_t* d_win_end, int64_t n_windows, const sai_job* jobs,
                      int32_t n_jobs, const uint32_t* d_mask_u, const uint32_t* d_mask_q,
                      const double* d_qval, int64_t qval_stride, int32_t* d_nsnps,
-                     int64_t* d_u, double* d_q, int64_t* d_u_off, int64_t* d_q_off,
-                     int32_t* d_u_cand, int64_t cap_u, int32_t* d_q_cand, int64_t cap_q,
-                     void* stream);
-
-/* Re-runs only the candidate fill (K6) after sai_window_stats, e.g. with larger
- * buffers; d_q holds the per-window Q values written by sai_window_stats. */
-int sai_fill_candidates(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
-                        const int64_t* d_win_end, int64_t n_windows, int32_t n_jobs,
-                        const uint32_t* d_mask_u, const uint32_t* d_mask_q,
-                        const double* d_qval, int64_t qval_stride, const double* d_q,
-                        const int64_t* d_u_off, const int64_t* d_q_off, int32_t* d_u_cand,
-                        int64_t cap_u, int32_t* d_q_cand, int64_t cap_q, void* stream);
+                     int64_t* d_u, double* d_q, int32_t* d_q_cnt, int64_t* d_u_start,
+                     int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand, int64_t cap_u,
+                     int32_t* d_q_cand, int64_t cap_q, void* stream);
 
 /* ---- host-buffer engine (replaces ChunkPreprocessor.run's inner loop) ----- */
 typedef struct sai_engine sai_engine;
@@ -203,30 +198,31 @@ int sai_engine_create(int32_t device, sai_engine** out);
 void sai_engine_destroy(sai_engine* e);
 
 typedef struct {
-  int32_t* nsnps; /* [n_jobs*W]      */
-  int64_t* u;     /* [n_jobs*W]      */
-  double* q;      /* [n_jobs*W]      */
-  int64_t* u_off; /* [n_jobs*(W+1)]  */
-  int64_t* q_off; /* [n_jobs*(W+1)]  */
-  int32_t* u_cand; /* [n_jobs*cap_u] */
-  int32_t* q_cand; /* [n_jobs*cap_q] */
+  int32_t* nsnps;   /* [n_jobs*W]     */
+  int64_t* u;       /* [n_jobs*W]     */
+  double* q;        /* [n_jobs*W]     */
+  int32_t* q_cnt;   /* [n_jobs*W]     */
+  int64_t* u_start; /* [n_jobs*W]     */
+  int64_t* q_start; /* [n_jobs*W]     */
+  int64_t* totals;  /* [n_jobs*2]     */
+  int32_t* u_cand;  /* [n_jobs*cap_u] */
+  int32_t* q_cand;  /* [n_jobs*cap_q] */
   int64_t cap_u, cap_q;
 } sai_host_results;
 
 /* HOST pointers in, HOST results out: copies the packed tiles to the GPU in
- * slices that overlap with the genotype pass, runs the window kernels, copies
- * the results back and synchronises.  Returns SAI_E_CAPACITY (results other
- * than the clipped candidate lists are valid) when cap_u / cap_q were too
- * small. */
+ * slices that overlap with the genotype pass, runs the window kernel, copies
+ * the results back and synchronises.  Returns SAI_E_CAPACITY (everything but
+ * the candidate lists is valid, totals say what is needed) when cap_u / cap_q
+ * were too small. */
 int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* packed,
                           const int32_t* pos, int64_t n_sites, const int64_t* win_start,
                           const int64_t* win_end, int64_t n_windows, const sai_job* jobs,
                           int32_t n_jobs, sai_host_results* out);
 
-/* After SAI_E_CAPACITY: re-runs only the candidate fill with larger host
- * buffers; out->u_off / out->q_off must still hold the offsets returned by the
- * failed sai_engine_score_host call. */
-int sai_engine_fetch_candidates(sai_engine* e, sai_host_results* out);
+/* After SAI_E_CAPACITY: re-runs only the window kernel on the flags still
+ * resident on the device, with the (larger) buffers of `out`. */
+int sai_engine_rescore_windows(sai_engine* e, sai_host_results* out);
 
 /* ---- synthetic genotypes (bench / tests only) ---------------------------- */
 /* Fills tiles [tile0, tile0+n_tiles) of a packed matrix directly on the device

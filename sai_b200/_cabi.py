@@ -69,8 +69,10 @@ class HostResults(C.Structure):
         ("nsnps", C.c_void_p),
         ("u", C.c_void_p),
         ("q", C.c_void_p),
-        ("u_off", C.c_void_p),
-        ("q_off", C.c_void_p),
+        ("q_cnt", C.c_void_p),
+        ("u_start", C.c_void_p),
+        ("q_start", C.c_void_p),
+        ("totals", C.c_void_p),
         ("u_cand", C.c_void_p),
         ("q_cand", C.c_void_p),
         ("cap_u", C.c_int64),
@@ -100,11 +102,7 @@ SYMBOLS = {
     "sai_flags_from_counts": (C.c_int, [_LAY, _P, _P, _I64, _I64, _JOB, _I32, _P, _P, _P, _I64, _P]),
     "sai_window_stats": (
         C.c_int,
-        [_P, _I64, _P, _P, _I64, _JOB, _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _P],
-    ),
-    "sai_fill_candidates": (
-        C.c_int,
-        [_P, _I64, _P, _P, _I64, _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _I64, _P],
+        [_P, _I64, _P, _P, _I64, _JOB, _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _P],
     ),
     "sai_engine_create": (C.c_int, [_I32, C.POINTER(_P)]),
     "sai_engine_destroy": (None, [_P]),
@@ -112,7 +110,7 @@ SYMBOLS = {
         C.c_int,
         [_P, _LAY, _P, _P, _I64, _P, _P, _I64, _JOB, _I32, C.POINTER(HostResults)],
     ),
-    "sai_engine_fetch_candidates": (C.c_int, [_P, C.POINTER(HostResults)]),
+    "sai_engine_rescore_windows": (C.c_int, [_P, C.POINTER(HostResults)]),
     "sai_synth_fill": (C.c_int, [_LAY, _P, _I64, _I64, _I64, _P, _U64, C.c_double, _P]),
 }
 

@@ -21,10 +21,10 @@ struct sai_engine {
     size_t cap = 0;
   };
   Buf packed, pos, win, mask, qval, res, cand;
-  // state of the last call (for sai_engine_fetch_candidates)
+  // state of the last call (for sai_engine_rescore_windows)
   int64_t n_sites = 0, W = 0;
   int32_t n_jobs = 0;
-  int64_t cap_u = 0, cap_q = 0;
+  sai_job jobs[SAI_MAX_JOBS];
 };
 
 namespace sai {
@@ -47,18 +47,89 @@ static int grow(sai_engine::Buf& b, size_t bytes) {
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct ResLayout {
-  size_t nsnps, u, q, u_off, q_off, total;
+  size_t nsnps, u, q, q_cnt, u_start, q_start, totals, total;
 };
 static ResLayout res_layout(int64_t W, int n_jobs) {
   ResLayout r{};
   size_t at = 0;
-  r.nsnps = at, at += align256(sizeof(int32_t) * n_jobs * W);
-  r.u = at, at += align256(sizeof(int64_t) * n_jobs * W);
-  r.q = at, at += align256(sizeof(double) * n_jobs * W);
-  r.u_off = at, at += align256(sizeof(int64_t) * n_jobs * (W + 1));
-  r.q_off = at, at += align256(sizeof(int64_t) * n_jobs * (W + 1));
+  const size_t n = (size_t)n_jobs * (size_t)W;
+  r.nsnps = at, at += align256(sizeof(int32_t) * n);
+  r.u = at, at += align256(sizeof(int64_t) * n);
+  r.q = at, at += align256(sizeof(double) * n);
+  r.q_cnt = at, at += align256(sizeof(int32_t) * n);
+  r.u_start = at, at += align256(sizeof(int64_t) * n);
+  r.q_start = at, at += align256(sizeof(int64_t) * n);
+  r.totals = at, at += align256(sizeof(int64_t) * 2 * n_jobs);
   r.total = at;
   return r;
+}
+
+// Window kernel on the device-resident flags + results back to the host.
+static int run_windows(sai_engine* e, sai_host_results* out) {
+  const int64_t W = e->W;
+  const int n_jobs = e->n_jobs;
+  const int64_t n_tiles = sai_num_tiles(e->n_sites);
+  const int64_t stride = n_tiles * kTile;
+  const ResLayout rl = res_layout(W, n_jobs);
+  const size_t cu = align256(sizeof(int32_t) * (size_t)n_jobs * out->cap_u);
+  const size_t cq = align256(sizeof(int32_t) * (size_t)n_jobs * out->cap_q);
+  if (int rc = grow(e->cand, cu + cq + 256)) return rc;
+  char* res = static_cast<char*>(e->res.p);
+  const uint32_t* d_mask_u = static_cast<const uint32_t*>(e->mask.p);
+  const uint32_t* d_mask_q = d_mask_u + (size_t)n_jobs * n_tiles;
+  const int64_t* d_ws = static_cast<const int64_t*>(e->win.p);
+  int32_t* d_uc = static_cast<int32_t*>(e->cand.p);
+  int32_t* d_qc = reinterpret_cast<int32_t*>(static_cast<char*>(e->cand.p) + cu);
+  cudaStream_t st = e->s_comp;
+  if (int rc = sai_window_stats(
+          static_cast<const int32_t*>(e->pos.p), e->n_sites, d_ws, d_ws + W, W, e->jobs, n_jobs,
+          d_mask_u, d_mask_q, static_cast<const double*>(e->qval.p), stride,
+          reinterpret_cast<int32_t*>(res + rl.nsnps), reinterpret_cast<int64_t*>(res + rl.u),
+          reinterpret_cast<double*>(res + rl.q), reinterpret_cast<int32_t*>(res + rl.q_cnt),
+          reinterpret_cast<int64_t*>(res + rl.u_start), reinterpret_cast<int64_t*>(res + rl.q_start),
+          reinterpret_cast<int64_t*>(res + rl.totals), d_uc, out->cap_u, d_qc, out->cap_q, st))
+    return rc;
+  const size_t n = (size_t)n_jobs * (size_t)W;
+  if (n > 0) {
+    SAI_CUDA_CHECK(cudaMemcpyAsync(out->nsnps, res + rl.nsnps, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    SAI_CUDA_CHECK(cudaMemcpyAsync(out->u, res + rl.u, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+    SAI_CUDA_CHECK(cudaMemcpyAsync(out->q, res + rl.q, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    SAI_CUDA_CHECK(cudaMemcpyAsync(out->q_cnt, res + rl.q_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    SAI_CUDA_CHECK(cudaMemcpyAsync(out->u_start, res + rl.u_start, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+    SAI_CUDA_CHECK(cudaMemcpyAsync(out->q_start, res + rl.q_start, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+  }
+  SAI_CUDA_CHECK(cudaMemcpyAsync(out->totals, res + rl.totals, sizeof(int64_t) * 2 * n_jobs, cudaMemcpyDeviceToHost, st));
+  SAI_CUDA_CHECK(cudaStreamSynchronize(st));
+  bool fits = true;
+  for (int j = 0; j < n_jobs; ++j) {
+    const int64_t tu = out->totals[2 * j], tq = out->totals[2 * j + 1];
+    if (tu > out->cap_u || tq > out->cap_q) {
+      fits = false;
+      continue;
+    }
+    if (tu > 0)
+      SAI_CUDA_CHECK(cudaMemcpyAsync(out->u_cand + (size_t)j * out->cap_u, d_uc + (size_t)j * out->cap_u,
+                                     sizeof(int32_t) * tu, cudaMemcpyDeviceToHost, st));
+    if (tq > 0)
+      SAI_CUDA_CHECK(cudaMemcpyAsync(out->q_cand + (size_t)j * out->cap_q, d_qc + (size_t)j * out->cap_q,
+                                     sizeof(int32_t) * tq, cudaMemcpyDeviceToHost, st));
+  }
+  SAI_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (!fits) {
+    set_error("candidate capacity too small (see totals)");
+    return SAI_E_CAPACITY;
+  }
+  return SAI_OK;
+}
+
+static int check_results(const sai_host_results* out) {
+  SAI_REQUIRE(out && out->nsnps && out->u && out->q && out->q_cnt && out->u_start && out->q_start &&
+                  out->totals,
+              "NULL result pointer");
+  SAI_REQUIRE(out->cap_u >= 0 && out->cap_q >= 0 && (out->cap_u == 0 || out->u_cand) &&
+                  (out->cap_q == 0 || out->q_cand),
+              "bad candidate buffers");
+  return SAI_OK;
 }
 
 }  // namespace sai
@@ -89,83 +160,23 @@ void sai_engine_destroy(sai_engine* e) {
   delete e;
 }
 
-static int fetch_candidates(sai_engine* e, sai_host_results* out, bool refill) {
-  const int64_t W = e->W;
-  const int n_jobs = e->n_jobs;
-  const ResLayout rl = res_layout(W, n_jobs);
-  char* res = static_cast<char*>(e->res.p);
-  // totals per job = last offset
-  int64_t need_u = 0, need_q = 0;
-  for (int j = 0; j < n_jobs; ++j) {
-    need_u = std::max(need_u, out->u_off[(size_t)j * (W + 1) + W]);
-    need_q = std::max(need_q, out->q_off[(size_t)j * (W + 1) + W]);
-  }
-  if (need_u > out->cap_u || need_q > out->cap_q) {
-    set_error("candidate capacity too small: need cap_u >= %lld, cap_q >= %lld", (long long)need_u,
-              (long long)need_q);
-    return SAI_E_CAPACITY;
-  }
-  if (refill) {
-    const size_t cu = align256(sizeof(int32_t) * (size_t)n_jobs * out->cap_u);
-    const size_t cq = align256(sizeof(int32_t) * (size_t)n_jobs * out->cap_q);
-    if (int rc = grow(e->cand, cu + cq + 256)) return rc;
-    int32_t* d_uc = static_cast<int32_t*>(e->cand.p);
-    int32_t* d_qc = reinterpret_cast<int32_t*>(static_cast<char*>(e->cand.p) + cu);
-    const int64_t n_tiles = sai_num_tiles(e->n_sites);
-    uint32_t* d_mask_u = static_cast<uint32_t*>(e->mask.p);
-    uint32_t* d_mask_q = d_mask_u + (size_t)n_jobs * n_tiles;
-    const int64_t* d_ws = static_cast<const int64_t*>(e->win.p);
-    if (int rc = sai_fill_candidates(
-            static_cast<const int32_t*>(e->pos.p), e->n_sites, d_ws, d_ws + W, W, n_jobs, d_mask_u,
-            d_mask_q, static_cast<const double*>(e->qval.p), n_tiles * kTile,
-            reinterpret_cast<const double*>(res + rl.q),
-            reinterpret_cast<const int64_t*>(res + rl.u_off),
-            reinterpret_cast<const int64_t*>(res + rl.q_off), d_uc, out->cap_u, d_qc, out->cap_q,
-            e->s_comp))
-      return rc;
-    e->cap_u = out->cap_u;
-    e->cap_q = out->cap_q;
-  }
-  const size_t cu = align256(sizeof(int32_t) * (size_t)n_jobs * e->cap_u);
-  const int32_t* d_uc = static_cast<const int32_t*>(e->cand.p);
-  const int32_t* d_qc = reinterpret_cast<const int32_t*>(static_cast<const char*>(e->cand.p) + cu);
-  for (int j = 0; j < n_jobs; ++j) {
-    const int64_t tu = out->u_off[(size_t)j * (W + 1) + W], tq = out->q_off[(size_t)j * (W + 1) + W];
-    if (tu > 0)
-      SAI_CUDA_CHECK(cudaMemcpyAsync(out->u_cand + (size_t)j * out->cap_u,
-                                     d_uc + (size_t)j * e->cap_u, sizeof(int32_t) * tu,
-                                     cudaMemcpyDeviceToHost, e->s_comp));
-    if (tq > 0)
-      SAI_CUDA_CHECK(cudaMemcpyAsync(out->q_cand + (size_t)j * out->cap_q,
-                                     d_qc + (size_t)j * e->cap_q, sizeof(int32_t) * tq,
-                                     cudaMemcpyDeviceToHost, e->s_comp));
-  }
-  SAI_CUDA_CHECK(cudaStreamSynchronize(e->s_comp));
-  return SAI_OK;
-}
-
 int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* packed,
                           const int32_t* pos, int64_t n_sites, const int64_t* win_start,
                           const int64_t* win_end, int64_t n_windows, const sai_job* jobs,
                           int32_t n_jobs, sai_host_results* out) {
-  SAI_REQUIRE(e && out, "NULL argument");
+  SAI_REQUIRE(e, "NULL engine");
   if (int rc = validate_layout(lay)) return rc;
   if (int rc = validate_jobs(lay, jobs, n_jobs)) return rc;
   SAI_REQUIRE(n_sites >= 0 && n_windows >= 0, "negative size");
   SAI_REQUIRE(n_sites == 0 || (packed && pos), "NULL input");
   SAI_REQUIRE(n_windows == 0 || (win_start && win_end), "NULL windows");
-  SAI_REQUIRE(out->nsnps && out->u && out->q && out->u_off && out->q_off, "NULL result pointer");
-  SAI_REQUIRE(out->cap_u >= 0 && out->cap_q >= 0 && (out->cap_u == 0 || out->u_cand) &&
-                  (out->cap_q == 0 || out->q_cand),
-              "bad candidate buffers");
+  if (int rc = check_results(out)) return rc;
   SAI_CUDA_CHECK(cudaSetDevice(e->device));
   const int64_t W = n_windows;
   const int64_t n_tiles = sai_num_tiles(n_sites);
   const int64_t stride = n_tiles * kTile;
   const size_t packed_bytes = sai_packed_bytes(lay, n_sites);
   const ResLayout rl = res_layout(W, n_jobs);
-  const size_t cu = align256(sizeof(int32_t) * (size_t)n_jobs * out->cap_u);
-  const size_t cq = align256(sizeof(int32_t) * (size_t)n_jobs * out->cap_q);
 
   if (int rc = grow(e->packed, packed_bytes + 256)) return rc;
   if (int rc = grow(e->pos, sizeof(int32_t) * (size_t)stride + 256)) return rc;
@@ -173,27 +184,23 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
   if (int rc = grow(e->mask, sizeof(uint32_t) * 2 * (size_t)n_jobs * n_tiles + 256)) return rc;
   if (int rc = grow(e->qval, sizeof(double) * (size_t)n_jobs * stride + 256)) return rc;
   if (int rc = grow(e->res, rl.total + 256)) return rc;
-  if (int rc = grow(e->cand, cu + cq + 256)) return rc;
   e->n_sites = n_sites;
   e->W = W;
   e->n_jobs = n_jobs;
-  e->cap_u = out->cap_u;
-  e->cap_q = out->cap_q;
+  for (int j = 0; j < n_jobs; ++j) e->jobs[j] = jobs[j];
 
   uint32_t* d_mask_u = static_cast<uint32_t*>(e->mask.p);
   uint32_t* d_mask_q = d_mask_u + (size_t)n_jobs * n_tiles;
   double* d_qval = static_cast<double*>(e->qval.p);
   int32_t* d_pos = static_cast<int32_t*>(e->pos.p);
   int64_t* d_ws = static_cast<int64_t*>(e->win.p);
-  int64_t* d_we = d_ws + W;
-  char* res = static_cast<char*>(e->res.p);
 
   // small inputs first
   if (n_sites > 0)
     SAI_CUDA_CHECK(cudaMemcpyAsync(d_pos, pos, sizeof(int32_t) * n_sites, cudaMemcpyHostToDevice, e->s_copy));
   if (W > 0) {
     SAI_CUDA_CHECK(cudaMemcpyAsync(d_ws, win_start, sizeof(int64_t) * W, cudaMemcpyHostToDevice, e->s_copy));
-    SAI_CUDA_CHECK(cudaMemcpyAsync(d_we, win_end, sizeof(int64_t) * W, cudaMemcpyHostToDevice, e->s_copy));
+    SAI_CUDA_CHECK(cudaMemcpyAsync(d_ws + W, win_end, sizeof(int64_t) * W, cudaMemcpyHostToDevice, e->s_copy));
   }
   // sliced H2D of the packed tiles, K1 per slice as soon as it has landed
   const size_t tile_bytes = (size_t)lay->pairs_per_site * kTile * 8;
@@ -217,34 +224,14 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
   }
   SAI_CUDA_CHECK(cudaEventRecord(e->ev[n_slices], e->s_copy));
   SAI_CUDA_CHECK(cudaStreamWaitEvent(e->s_comp, e->ev[n_slices], 0));
-
-  int32_t* d_uc = static_cast<int32_t*>(e->cand.p);
-  int32_t* d_qc = reinterpret_cast<int32_t*>(static_cast<char*>(e->cand.p) + cu);
-  if (int rc = sai_window_stats(d_pos, n_sites, d_ws, d_we, W, jobs, n_jobs, d_mask_u, d_mask_q,
-                                d_qval, stride, reinterpret_cast<int32_t*>(res + rl.nsnps),
-                                reinterpret_cast<int64_t*>(res + rl.u),
-                                reinterpret_cast<double*>(res + rl.q),
-                                reinterpret_cast<int64_t*>(res + rl.u_off),
-                                reinterpret_cast<int64_t*>(res + rl.q_off), d_uc, out->cap_u, d_qc,
-                                out->cap_q, e->s_comp))
-    return rc;
-  if (W > 0) {
-    SAI_CUDA_CHECK(cudaMemcpyAsync(out->nsnps, res + rl.nsnps, sizeof(int32_t) * n_jobs * W, cudaMemcpyDeviceToHost, e->s_comp));
-    SAI_CUDA_CHECK(cudaMemcpyAsync(out->u, res + rl.u, sizeof(int64_t) * n_jobs * W, cudaMemcpyDeviceToHost, e->s_comp));
-    SAI_CUDA_CHECK(cudaMemcpyAsync(out->q, res + rl.q, sizeof(double) * n_jobs * W, cudaMemcpyDeviceToHost, e->s_comp));
-  }
-  SAI_CUDA_CHECK(cudaMemcpyAsync(out->u_off, res + rl.u_off, sizeof(int64_t) * n_jobs * (W + 1), cudaMemcpyDeviceToHost, e->s_comp));
-  SAI_CUDA_CHECK(cudaMemcpyAsync(out->q_off, res + rl.q_off, sizeof(int64_t) * n_jobs * (W + 1), cudaMemcpyDeviceToHost, e->s_comp));
-  SAI_CUDA_CHECK(cudaStreamSynchronize(e->s_comp));
-  return fetch_candidates(e, out, /*refill=*/false);
+  return run_windows(e, out);
 }
 
-/* After SAI_E_CAPACITY: re-run only the candidate fill with larger host buffers
- * (out->u_off / q_off must still hold the offsets of the failed call). */
-int sai_engine_fetch_candidates(sai_engine* e, sai_host_results* out) {
-  SAI_REQUIRE(e && out && out->u_off && out->q_off, "NULL argument");
+int sai_engine_rescore_windows(sai_engine* e, sai_host_results* out) {
+  SAI_REQUIRE(e && e->n_jobs > 0, "no previous sai_engine_score_host call");
+  if (int rc = check_results(out)) return rc;
   SAI_CUDA_CHECK(cudaSetDevice(e->device));
-  return fetch_candidates(e, out, /*refill=*/true);
+  return run_windows(e, out);
 }
 
 }  // extern "C"

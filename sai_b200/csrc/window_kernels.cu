@@ -1,8 +1,8 @@
-// K4..K6: per-window U, N(Variants), exact Q and the candidate position lists.
+// K4: per-window U, N(Variants), exact Q and the candidate position lists (one launch).
 //
 // One warp owns one (job, window).  A window [start, end] (inclusive,
 // sai/generators/window_generator.py:173-174) maps to the site range [lo, hi)
-// by binary search on the sorted positions; its U count is the popcount of the
+// by a cooperative 32-ary search on the sorted positions; its U count is the popcount of the
 // tile masks over that range (sai/stats/u_statistic.py:94-96) and Q is the
 // numpy 'linear' quantile of the flagged sites' target frequencies
 // (sai/stats/q_statistic.py:96-101; numpy/lib/_function_base_impl.py _lerp).
@@ -35,24 +35,47 @@ struct WinParams {
   int32_t* nsnps;
   int64_t* u;
   double* q;
-  int64_t* u_off;  // [J][W+1]; K4 stores counts, K5 scans in place
-  int64_t* q_off;
+  int32_t* q_cnt;
+  int64_t* u_start;  // [J][W] first candidate of the window inside the job's u_cand
+  int64_t* q_start;
+  unsigned long long* totals;  // [J][2] candidates reserved so far (U, Q)
   int32_t* u_cand;
   int64_t cap_u;
   int32_t* q_cand;
   int64_t cap_q;
 };
 
-__device__ __forceinline__ int64_t lower_bound_pos(const int32_t* pos, int64_t n, int64_t key) {
-  int64_t lo = 0, hi = n;  // first index with pos >= key
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if ((int64_t)__ldg(pos + mid) < key)
-      lo = mid + 1;
-    else
-      hi = mid;
+// Cooperative 32-ary lower bounds of two keys at once: first index whose
+// position is >= key.  Each round probes 32 evenly spaced positions per key, so
+// a 6 M-site chromosome needs 5 dependent rounds instead of 2 x 23 binary steps.
+__device__ __forceinline__ void warp_lower_bound2(const int32_t* __restrict__ pos, int64_t n,
+                                                  int64_t key_a, int64_t key_b, int lane,
+                                                  int64_t& out_a, int64_t& out_b) {
+  int64_t lo_a = 0, hi_a = n, lo_b = 0, hi_b = n;  // answer in [lo, hi]
+  while (hi_a > lo_a || hi_b > lo_b) {
+    const int64_t na = hi_a - lo_a, nb = hi_b - lo_b;
+    const int64_t sa = na > 32 ? (na + 31) / 32 : 1, sb = nb > 32 ? (nb + 31) / 32 : 1;
+    const int64_t ia = lo_a + (lane + 1) * sa - 1, ib = lo_b + (lane + 1) * sb - 1;
+    const bool pa = ia < hi_a && (int64_t)__ldg(pos + ia) < key_a;
+    const bool pb = ib < hi_b && (int64_t)__ldg(pos + ib) < key_b;
+    const int ca = __popc(__ballot_sync(0xffffffffu, pa));  // sorted => the true lanes are a prefix
+    const int cb = __popc(__ballot_sync(0xffffffffu, pb));
+    if (na > 0) {
+      // probes 0..ca-1 are < key, probe ca (if it exists) is >= key
+      const int64_t nhi = lo_a + (int64_t)(ca + 1) * sa - 1;
+      lo_a += (int64_t)ca * sa;
+      if (nhi < hi_a) hi_a = nhi;
+      if (lo_a > hi_a) lo_a = hi_a;
+    }
+    if (nb > 0) {
+      const int64_t nhi = lo_b + (int64_t)(cb + 1) * sb - 1;
+      lo_b += (int64_t)cb * sb;
+      if (nhi < hi_b) hi_b = nhi;
+      if (lo_b > hi_b) lo_b = hi_b;
+    }
   }
-  return lo;
+  out_a = lo_a;
+  out_b = lo_b;
 }
 
 __device__ __forceinline__ int warp_sum(int v) {
@@ -259,11 +282,12 @@ __global__ void __launch_bounds__(kWinWarps * 32) k_window_stats(const __grid_co
        item += (int64_t)gridDim.x * kWinWarps) {
     const int j = (int)(item / P.W);
     const int64_t i = item - (int64_t)j * P.W;
-    const int64_t lo = lower_bound_pos(P.pos, P.n_sites, P.ws[i]);
-    const int64_t hi = lower_bound_pos(P.pos, P.n_sites, P.we[i] + 1);
+    int64_t lo, hi;
+    warp_lower_bound2(P.pos, P.n_sites, P.ws[i], P.we[i] + 1, lane, lo, hi);
     const uint32_t* mu = P.mask_u + (size_t)j * P.n_tiles;
     const uint32_t* mq = P.mask_q + (size_t)j * P.n_tiles;
     const double* qv = P.qval + (size_t)j * P.qval_stride;
+    const bool want_u = P.u_enabled[j] != 0, want_q = P.q_enabled[j] != 0;
     int u_cnt = 0, q_n = 0;
     int64_t T0 = 0, T1 = -1;
     if (hi > lo) {
@@ -275,8 +299,8 @@ __global__ void __launch_bounds__(kWinWarps * 32) k_window_stats(const __grid_co
         uint32_t a = 0, b = 0;
         if (T <= T1) {
           const uint32_t rm = range_mask(T, lo, hi);
-          a = __ldg(mu + T) & rm;
-          b = __ldg(mq + T) & rm;
+          if (want_u) a = __ldg(mu + T) & rm;
+          if (want_q) b = __ldg(mq + T) & rm;
         }
         u_cnt += __popc(a);
         const int c = __popc(b);
@@ -297,7 +321,7 @@ __global__ void __launch_bounds__(kWinWarps * 32) k_window_stats(const __grid_co
     }
     double qres = CUDART_NAN;
     int q_cand = 0;
-    if (P.q_enabled[j] && q_n > 0) {
+    if (q_n > 0) {
       const double qq = P.quantile[j];
       if (q_n <= 32) {
         const unsigned long long key = lane < q_n ? s_buf[warp][lane] : ~0ull;
@@ -315,94 +339,37 @@ __global__ void __launch_bounds__(kWinWarps * 32) k_window_stats(const __grid_co
       }
     }
     __syncwarp();
+    // reserve this window's slices of the candidate buffers (one atomic each)
+    unsigned long long ub = 0, qb = 0;
     if (lane == 0) {
+      if (u_cnt > 0) ub = atomicAdd(P.totals + 2 * j, (unsigned long long)u_cnt);
+      if (q_cand > 0) qb = atomicAdd(P.totals + 2 * j + 1, (unsigned long long)q_cand);
       P.nsnps[item] = (int32_t)(hi - lo);
-      P.u[item] = P.u_enabled[j] ? u_cnt : 0;
+      P.u[item] = u_cnt;
       P.q[item] = qres;
-      P.u_off[(size_t)j * (P.W + 1) + i] = P.u_enabled[j] ? u_cnt : 0;
-      P.q_off[(size_t)j * (P.W + 1) + i] = q_cand;
-      if (i == P.W - 1) {
-        P.u_off[(size_t)j * (P.W + 1) + P.W] = 0;
-        P.q_off[(size_t)j * (P.W + 1) + P.W] = 0;
-      }
+      P.q_cnt[item] = q_cand;
+      P.u_start[item] = (int64_t)ub;
+      P.q_start[item] = (int64_t)qb;
     }
-  }
-}
-
-// K5: in-place exclusive scan of the per-window candidate counts -> CSR offsets.
-// One block per (job, statistic); chunks of blockDim with a running carry.
-__global__ void __launch_bounds__(1024) k_scan_offsets(int64_t* u_off, int64_t* q_off, int64_t W) {
-  __shared__ long long s_warp[32];
-  __shared__ long long s_total;
-  __shared__ long long s_carry;
-  int64_t* a = (blockIdx.y == 0 ? u_off : q_off) + (size_t)blockIdx.x * (W + 1);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (int64_t base = 0; base <= W; base += blockDim.x) {
-    const int64_t idx = base + threadIdx.x;
-    const long long v = idx <= W ? a[idx] : 0;
-    long long x = v;  // inclusive scan inside the warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      const long long w = s_warp[lane];
-      long long xx = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long y = __shfl_up_sync(0xffffffffu, xx, o);
-        if (lane >= o) xx += y;
-      }
-      s_warp[lane] = xx - w;  // exclusive offset of each warp
-      if (lane == 31) s_total = xx;
-    }
-    __syncthreads();
-    if (idx <= W) a[idx] = s_carry + s_warp[warp] + (x - v);
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry += s_total;
-    __syncthreads();
-  }
-}
-
-// K6: candidate positions (u_statistic.py:95, q_statistic.py:101) in site order.
-__global__ void __launch_bounds__(kWinWarps * 32) k_fill_candidates(const __grid_constant__ WinParams P) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t total = (int64_t)P.n_jobs * P.W;
-  for (int64_t item = (int64_t)blockIdx.x * kWinWarps + warp; item < total;
-       item += (int64_t)gridDim.x * kWinWarps) {
-    const int j = (int)(item / P.W);
-    const int64_t i = item - (int64_t)j * P.W;
-    const int64_t u0 = P.u_off[(size_t)j * (P.W + 1) + i], u1 = P.u_off[(size_t)j * (P.W + 1) + i + 1];
-    const int64_t q0 = P.q_off[(size_t)j * (P.W + 1) + i], q1 = P.q_off[(size_t)j * (P.W + 1) + i + 1];
-    if (u1 == u0 && q1 == q0) continue;
-    const int64_t lo = lower_bound_pos(P.pos, P.n_sites, P.ws[i]);
-    const int64_t hi = lower_bound_pos(P.pos, P.n_sites, P.we[i] + 1);
-    if (hi <= lo) continue;
-    const uint32_t* mu = P.mask_u + (size_t)j * P.n_tiles;
-    const uint32_t* mq = P.mask_q + (size_t)j * P.n_tiles;
-    const double* qv = P.qval + (size_t)j * P.qval_stride;
-    const double thr = P.q[item];
+    if (u_cnt == 0 && q_cand == 0) continue;
+    ub = shfl64(ub, 0);
+    qb = shfl64(qb, 0);
+    // second walk: candidate positions in site order (u_statistic.py:95, q_statistic.py:101)
     int32_t* uc = P.u_cand + (size_t)j * P.cap_u;
     int32_t* qc = P.q_cand + (size_t)j * P.cap_q;
-    const int64_t T0 = lo / kTile, T1 = (hi - 1) / kTile;
-    int64_t uw = u0, qw = q0;
+    int64_t uw = (int64_t)ub, qw = (int64_t)qb;
     for (int64_t Tb = T0; Tb <= T1; Tb += 32) {
       const int64_t T = Tb + lane;
       uint32_t a = 0, b = 0;
       if (T <= T1) {
         const uint32_t rm = range_mask(T, lo, hi);
-        if (u1 > u0) a = __ldg(mu + T) & rm;
-        if (q1 > q0) {
+        if (u_cnt > 0) a = __ldg(mu + T) & rm;
+        if (q_cand > 0) {
           uint32_t m = __ldg(mq + T) & rm;
           while (m) {
             const int bit = __ffs(m) - 1;
             m &= m - 1;
-            if (__ldg(qv + T * kTile + bit) >= thr) b |= 1u << bit;
+            if (__ldg(qv + T * kTile + bit) >= qres) b |= 1u << bit;
           }
         }
       }
@@ -427,28 +394,6 @@ __global__ void __launch_bounds__(kWinWarps * 32) k_fill_candidates(const __grid
   }
 }
 
-static int fill_params(WinParams& P, const int32_t* d_pos, int64_t n_sites, const int64_t* ws,
-                       const int64_t* we, int64_t W, int32_t n_jobs, const uint32_t* mask_u,
-                       const uint32_t* mask_q, const double* qval, int64_t qval_stride) {
-  SAI_REQUIRE(d_pos && ws && we && mask_u && mask_q && qval, "NULL device pointer");
-  SAI_REQUIRE(n_sites >= 0 && n_sites < (1ll << 31), "n_sites out of range");
-  SAI_REQUIRE(W >= 0, "negative window count");
-  SAI_REQUIRE(n_jobs >= 1 && n_jobs <= SAI_MAX_JOBS, "n_jobs %d outside [1,%d]", n_jobs, SAI_MAX_JOBS);
-  SAI_REQUIRE(qval_stride >= n_sites, "qval_stride too small");
-  P.pos = d_pos;
-  P.n_sites = n_sites;
-  P.n_tiles = sai_num_tiles(n_sites);
-  P.ws = ws;
-  P.we = we;
-  P.W = W;
-  P.n_jobs = n_jobs;
-  P.mask_u = mask_u;
-  P.mask_q = mask_q;
-  P.qval = qval;
-  P.qval_stride = qval_stride;
-  return SAI_OK;
-}
-
 static int win_grid(int64_t items) {
   const int64_t want = (items + kWinWarps - 1) / kWinWarps;
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -459,21 +404,32 @@ static int win_grid(int64_t items) {
 
 using namespace sai;
 
-extern "C" {
-
-int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
-                     const int64_t* d_win_end, int64_t n_windows, const sai_job* jobs,
-                     int32_t n_jobs, const uint32_t* d_mask_u, const uint32_t* d_mask_q,
-                     const double* d_qval, int64_t qval_stride, int32_t* d_nsnps, int64_t* d_u,
-                     double* d_q, int64_t* d_u_off, int64_t* d_q_off, int32_t* d_u_cand,
-                     int64_t cap_u, int32_t* d_q_cand, int64_t cap_q, void* stream) {
-  WinParams P{};
-  if (int rc = fill_params(P, d_pos, n_sites, d_win_start, d_win_end, n_windows, n_jobs, d_mask_u,
-                           d_mask_q, d_qval, qval_stride))
-    return rc;
-  SAI_REQUIRE(jobs && d_nsnps && d_u && d_q && d_u_off && d_q_off, "NULL device pointer");
+extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
+                                const int64_t* d_win_end, int64_t n_windows, const sai_job* jobs,
+                                int32_t n_jobs, const uint32_t* d_mask_u, const uint32_t* d_mask_q,
+                                const double* d_qval, int64_t qval_stride, int32_t* d_nsnps,
+                                int64_t* d_u, double* d_q, int32_t* d_q_cnt, int64_t* d_u_start,
+                                int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand,
+                                int64_t cap_u, int32_t* d_q_cand, int64_t cap_q, void* stream) {
+  SAI_REQUIRE(d_pos && d_mask_u && d_mask_q && d_qval && d_totals, "NULL device pointer");
+  SAI_REQUIRE(n_sites >= 0 && n_sites < (1ll << 31), "n_sites out of range");
+  SAI_REQUIRE(n_windows >= 0, "negative window count");
+  SAI_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= SAI_MAX_JOBS, "n_jobs %d outside [1,%d]", n_jobs,
+              SAI_MAX_JOBS);
+  SAI_REQUIRE(qval_stride >= n_sites, "qval_stride too small");
+  SAI_REQUIRE(n_windows == 0 || (d_win_start && d_win_end && d_nsnps && d_u && d_q && d_q_cnt &&
+                                 d_u_start && d_q_start),
+              "NULL device pointer");
   SAI_REQUIRE(cap_u >= 0 && cap_q >= 0 && (cap_u == 0 || d_u_cand) && (cap_q == 0 || d_q_cand),
               "bad candidate buffers");
+  WinParams P{};
+  P.pos = d_pos;
+  P.n_sites = n_sites;
+  P.n_tiles = sai_num_tiles(n_sites);
+  P.ws = d_win_start;
+  P.we = d_win_end;
+  P.W = n_windows;
+  P.n_jobs = n_jobs;
   for (int j = 0; j < n_jobs; ++j) {
     P.u_enabled[j] = jobs[j].u.enabled;
     P.q_enabled[j] = jobs[j].q.enabled;
@@ -482,58 +438,25 @@ int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win
       SAI_REQUIRE(jobs[j].quantile >= 0.0 && jobs[j].quantile <= 1.0,
                   "Quantiles must be in the range [0, 1]");
   }
+  P.mask_u = d_mask_u;
+  P.mask_q = d_mask_q;
+  P.qval = d_qval;
+  P.qval_stride = qval_stride;
   P.nsnps = d_nsnps;
   P.u = d_u;
   P.q = d_q;
-  P.u_off = d_u_off;
-  P.q_off = d_q_off;
+  P.q_cnt = d_q_cnt;
+  P.u_start = d_u_start;
+  P.q_start = d_q_start;
+  P.totals = reinterpret_cast<unsigned long long*>(d_totals);
   P.u_cand = d_u_cand;
   P.cap_u = cap_u;
   P.q_cand = d_q_cand;
   P.cap_q = cap_q;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (n_windows == 0) {
-    SAI_CUDA_CHECK(cudaMemsetAsync(d_u_off, 0, sizeof(int64_t) * n_jobs, st));
-    SAI_CUDA_CHECK(cudaMemsetAsync(d_q_off, 0, sizeof(int64_t) * n_jobs, st));
-    return SAI_OK;
-  }
-  const int grid = win_grid((int64_t)n_jobs * n_windows);
-  k_window_stats<<<grid, kWinWarps * 32, 0, st>>>(P);
-  SAI_CUDA_CHECK(cudaGetLastError());
-  k_scan_offsets<<<dim3(n_jobs, 2), 1024, 0, st>>>(d_u_off, d_q_off, n_windows);
-  SAI_CUDA_CHECK(cudaGetLastError());
-  if (cap_u > 0 || cap_q > 0) {
-    k_fill_candidates<<<grid, kWinWarps * 32, 0, st>>>(P);
-    SAI_CUDA_CHECK(cudaGetLastError());
-  }
-  return SAI_OK;
-}
-
-int sai_fill_candidates(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
-                        const int64_t* d_win_end, int64_t n_windows, int32_t n_jobs,
-                        const uint32_t* d_mask_u, const uint32_t* d_mask_q, const double* d_qval,
-                        int64_t qval_stride, const double* d_q, const int64_t* d_u_off,
-                        const int64_t* d_q_off, int32_t* d_u_cand, int64_t cap_u,
-                        int32_t* d_q_cand, int64_t cap_q, void* stream) {
-  WinParams P{};
-  if (int rc = fill_params(P, d_pos, n_sites, d_win_start, d_win_end, n_windows, n_jobs, d_mask_u,
-                           d_mask_q, d_qval, qval_stride))
-    return rc;
-  SAI_REQUIRE(d_q && d_u_off && d_q_off, "NULL device pointer");
-  SAI_REQUIRE(cap_u >= 0 && cap_q >= 0 && (cap_u == 0 || d_u_cand) && (cap_q == 0 || d_q_cand),
-              "bad candidate buffers");
+  SAI_CUDA_CHECK(cudaMemsetAsync(d_totals, 0, sizeof(int64_t) * 2 * n_jobs, st));
   if (n_windows == 0) return SAI_OK;
-  P.q = const_cast<double*>(d_q);
-  P.u_off = const_cast<int64_t*>(d_u_off);
-  P.q_off = const_cast<int64_t*>(d_q_off);
-  P.u_cand = d_u_cand;
-  P.cap_u = cap_u;
-  P.q_cand = d_q_cand;
-  P.cap_q = cap_q;
-  const int grid = win_grid((int64_t)n_jobs * n_windows);
-  k_fill_candidates<<<grid, kWinWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  k_window_stats<<<win_grid((int64_t)n_jobs * n_windows), kWinWarps * 32, 0, st>>>(P);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }
-
-}  // extern "C"

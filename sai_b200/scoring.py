@@ -84,21 +84,27 @@ def _job_array(jobs: Sequence["_cabi.Job"]):
 # --------------------------------------------------------------------------
 @dataclass
 class WindowResults:
-    """Per job ``j`` and window ``i``; candidate lists in CSR form."""
+    """Per job ``j`` and window ``i``.  A window's candidate positions are the
+    ``u[j, i]`` (resp. ``q_cnt[j, i]``) entries of ``u_cand[j]`` (``q_cand[j]``)
+    starting at ``u_start[j, i]`` (``q_start[j, i]``), in genome order."""
 
     nsnps: np.ndarray  # int32 [J, W]
     u: np.ndarray  # int64 [J, W]
     q: np.ndarray  # float64 [J, W], NaN where no site matches
-    u_off: np.ndarray  # int64 [J, W+1]
-    q_off: np.ndarray
+    q_cnt: np.ndarray  # int32 [J, W]
+    u_start: np.ndarray  # int64 [J, W]
+    q_start: np.ndarray  # int64 [J, W]
+    totals: np.ndarray  # int64 [J, 2]
     u_cand: np.ndarray  # int32 [J, cap_u] positions
     q_cand: np.ndarray
 
     def u_positions(self, j: int, i: int) -> np.ndarray:
-        return self.u_cand[j, self.u_off[j, i] : self.u_off[j, i + 1]]
+        s = int(self.u_start[j, i])
+        return self.u_cand[j, s : s + int(self.u[j, i])]
 
     def q_positions(self, j: int, i: int) -> np.ndarray:
-        return self.q_cand[j, self.q_off[j, i] : self.q_off[j, i + 1]]
+        s = int(self.q_start[j, i])
+        return self.q_cand[j, s : s + int(self.q_cnt[j, i])]
 
 
 # --------------------------------------------------------------------------
@@ -156,24 +162,27 @@ class HostEngine:
         cap_u = max(1, 4 * W + 1024) if cap_u is None else int(cap_u)
         cap_q = max(1, 4 * W + 1024) if cap_q is None else int(cap_q)
         jarr = _job_array(jobs)
-        nsnps = np.zeros((J, W), dtype=np.int32)
-        u = np.zeros((J, W), dtype=np.int64)
-        q = np.full((J, W), np.nan, dtype=np.float64)
-        u_off = np.zeros((J, W + 1), dtype=np.int64)
-        q_off = np.zeros((J, W + 1), dtype=np.int64)
-        u_cand = np.zeros((J, cap_u), dtype=np.int32)
-        q_cand = np.zeros((J, cap_q), dtype=np.int32)
+        r = WindowResults(
+            nsnps=np.zeros((J, W), dtype=np.int32),
+            u=np.zeros((J, W), dtype=np.int64),
+            q=np.full((J, W), np.nan, dtype=np.float64),
+            q_cnt=np.zeros((J, W), dtype=np.int32),
+            u_start=np.zeros((J, W), dtype=np.int64),
+            q_start=np.zeros((J, W), dtype=np.int64),
+            totals=np.zeros((J, 2), dtype=np.int64),
+            u_cand=np.zeros((J, cap_u), dtype=np.int32),
+            q_cand=np.zeros((J, cap_q), dtype=np.int32),
+        )
 
-        def results():
-            r = _cabi.HostResults()
-            r.nsnps, r.u, r.q = nsnps.ctypes.data, u.ctypes.data, q.ctypes.data
-            r.u_off, r.q_off = u_off.ctypes.data, q_off.ctypes.data
-            r.u_cand, r.q_cand = u_cand.ctypes.data, q_cand.ctypes.data
-            r.cap_u, r.cap_q = u_cand.shape[1], q_cand.shape[1]
-            return r
+        def c_results():
+            h = _cabi.HostResults()
+            for name in ("nsnps", "u", "q", "q_cnt", "u_start", "q_start", "totals", "u_cand", "q_cand"):
+                setattr(h, name, getattr(r, name).ctypes.data)
+            h.cap_u, h.cap_q = r.u_cand.shape[1], r.q_cand.shape[1]
+            return h
 
         pos = np.ascontiguousarray(pg.pos, dtype=np.int32)
-        res = results()
+        res = c_results()
         rc = lib.sai_engine_score_host(
             self._handle(),
             C.byref(pg.layout),
@@ -187,13 +196,13 @@ class HostEngine:
             J,
             C.byref(res),
         )
-        if rc == _cabi.E_CAPACITY:
-            u_cand = np.zeros((J, max(1, int(u_off[:, W].max()))), dtype=np.int32)
-            q_cand = np.zeros((J, max(1, int(q_off[:, W].max()))), dtype=np.int32)
-            res = results()
-            rc = lib.sai_engine_fetch_candidates(self._handle(), C.byref(res))
+        if rc == _cabi.E_CAPACITY:  # totals say what is needed: re-run the window kernel only
+            r.u_cand = np.zeros((J, max(1, int(r.totals[:, 0].max()))), dtype=np.int32)
+            r.q_cand = np.zeros((J, max(1, int(r.totals[:, 1].max()))), dtype=np.int32)
+            res = c_results()
+            rc = lib.sai_engine_rescore_windows(self._handle(), C.byref(res))
         _cabi.check(rc)
-        return WindowResults(nsnps, u, q, u_off, q_off, u_cand, q_cand)
+        return r
 
 
 # --------------------------------------------------------------------------
@@ -223,8 +232,10 @@ class DeviceScorer:
         self.nsnps = torch.zeros((J, W), dtype=torch.int32, device=d)
         self.u = torch.zeros((J, W), dtype=torch.int64, device=d)
         self.q = torch.zeros((J, W), dtype=torch.float64, device=d)
-        self.u_off = torch.zeros((J, W + 1), dtype=torch.int64, device=d)
-        self.q_off = torch.zeros((J, W + 1), dtype=torch.int64, device=d)
+        self.q_cnt = torch.zeros((J, W), dtype=torch.int32, device=d)
+        self.u_start = torch.zeros((J, W), dtype=torch.int64, device=d)
+        self.q_start = torch.zeros((J, W), dtype=torch.int64, device=d)
+        self.totals = torch.zeros((J, 2), dtype=torch.int64, device=d)
         self.cap_u = max(1, 4 * W + 1024) if cap_u is None else int(cap_u)
         self.cap_q = max(1, 4 * W + 1024) if cap_q is None else int(cap_q)
         self.u_cand = torch.zeros((J, self.cap_u), dtype=torch.int32, device=d)
@@ -284,35 +295,44 @@ class DeviceScorer:
 
     def window_stats(self, d_pos, d_ws, d_we, jobs):
         jarr = _job_array(jobs)
+        self._last = (d_pos, d_ws, d_we, jobs)
         _cabi.check(
             self.lib.sai_window_stats(
                 d_pos.data_ptr(), self.n_sites, d_ws.data_ptr(), d_we.data_ptr(), self.W, jarr, len(jobs),
                 self.mask_u.data_ptr(), self.mask_q.data_ptr(), self.qval.data_ptr(), self.qval.shape[1],
-                self.nsnps.data_ptr(), self.u.data_ptr(), self.q.data_ptr(), self.u_off.data_ptr(),
-                self.q_off.data_ptr(), self.u_cand.data_ptr(), self.cap_u, self.q_cand.data_ptr(), self.cap_q,
-                self._stream(),
+                self.nsnps.data_ptr(), self.u.data_ptr(), self.q.data_ptr(), self.q_cnt.data_ptr(),
+                self.u_start.data_ptr(), self.q_start.data_ptr(), self.totals.data_ptr(),
+                self.u_cand.data_ptr(), self.cap_u, self.q_cand.data_ptr(), self.cap_q, self._stream(),
             )
         )
 
     def step(self, d_packed, d_pos, d_ws, d_we, jobs, variant: int = 0):
-        """One pass of the hot path over device-resident inputs (4 launches)."""
+        """One pass of the hot path over device-resident inputs: the genotype
+        pass and the window kernel (2 launches + one 16-byte memset)."""
         self.site_flags(d_packed, jobs, variant)
         self.window_stats(d_pos, d_ws, d_we, jobs)
+        self._last = (d_pos, d_ws, d_we, jobs)
 
     def results(self) -> WindowResults:
-        """Copies the results to the host (synchronises); grows the candidate
-        buffers and re-fills them if they were too small."""
+        """Copies the results to the host (synchronises).  If the candidate
+        buffers were too small they are grown and the window kernel is re-run
+        on the flags still resident on the device."""
         torch = self.torch
-        u_off, q_off = self.u_off.cpu().numpy(), self.q_off.cpu().numpy()
-        need_u = int(u_off[:, self.W].max()) if self.J else 0
-        need_q = int(q_off[:, self.W].max()) if self.J else 0
+        totals = self.totals.cpu().numpy()
+        need_u, need_q = (int(totals[:, 0].max()), int(totals[:, 1].max())) if self.J else (0, 0)
         if need_u > self.cap_u or need_q > self.cap_q:
-            raise _cabi.SaiError(
-                f"candidate capacity too small (need cap_u>={need_u}, cap_q>={need_q}); "
-                "construct DeviceScorer with larger cap_u/cap_q"
-            )
+            if getattr(self, "_last", None) is None:
+                raise _cabi.SaiError(
+                    f"candidate capacity too small (need cap_u>={need_u}, cap_q>={need_q})"
+                )
+            self.cap_u, self.cap_q = max(self.cap_u, need_u), max(self.cap_q, need_q)
+            self.u_cand = torch.zeros((self.J, self.cap_u), dtype=torch.int32, device=self.device)
+            self.q_cand = torch.zeros((self.J, self.cap_q), dtype=torch.int32, device=self.device)
+            self.window_stats(*self._last)
+            totals = self.totals.cpu().numpy()
         return WindowResults(
-            self.nsnps.cpu().numpy(), self.u.cpu().numpy(), self.q.cpu().numpy(), u_off, q_off,
+            self.nsnps.cpu().numpy(), self.u.cpu().numpy(), self.q.cpu().numpy(), self.q_cnt.cpu().numpy(),
+            self.u_start.cpu().numpy(), self.q_start.cpu().numpy(), totals,
             self.u_cand.cpu().numpy(), self.q_cand.cpu().numpy(),
         )
 

@@ -313,11 +313,11 @@ def test_device_scorer_matches_engine_and_cached_counts(engine):
         got = sc.results()
         assert np.array_equal(got.nsnps, ref.nsnps) and np.array_equal(got.u, ref.u), mode
         assert np.array_equal(got.q, ref.q, equal_nan=True), mode
-        assert np.array_equal(got.u_off, ref.u_off) and np.array_equal(got.q_off, ref.q_off), mode
+        assert np.array_equal(got.q_cnt, ref.q_cnt) and np.array_equal(got.totals, ref.totals), mode
         for j in range(len(jobs)):
-            nu, nq = int(ref.u_off[j, -1]), int(ref.q_off[j, -1])
-            assert np.array_equal(got.u_cand[j, :nu], ref.u_cand[j, :nu]), mode
-            assert np.array_equal(got.q_cand[j, :nq], ref.q_cand[j, :nq]), mode
+            for i in range(len(wins)):
+                assert np.array_equal(got.u_positions(j, i), ref.u_positions(j, i)), mode
+                assert np.array_equal(got.q_positions(j, i), ref.q_positions(j, i)), mode
     assert ref.u.sum() > 0 and np.isfinite(ref.q).sum() > 10
 
 
@@ -420,10 +420,14 @@ def test_full_size_properties():
         return sc, sc.results()
 
     sc_s, rs = run(small)
-    flagged_u = int(sum(bin(int(x) & 0xFFFFFFFF).count("1") for x in sc_s.mask_u.cpu().numpy().ravel()))
+    flagged_u = int(np.unpackbits(sc_s.mask_u.cpu().numpy().view(np.uint8)).sum())
     assert int(rs.nsnps.sum()) == n_sites
-    assert int(rs.u.sum()) == flagged_u == int(rs.u_off[0, -1]) and flagged_u > 1000
-    assert np.all(np.diff(rs.u_cand[0, :flagged_u]) > 0)  # candidates come out in genome order
+    assert int(rs.u.sum()) == flagged_u == int(rs.totals[0, 0]) and flagged_u > 1000
+    # disjoint windows: every U candidate appears exactly once, each window's list in genome order
+    allc = np.sort(rs.u_cand[0, :flagged_u])
+    assert np.all(np.diff(allc) > 0)
+    for i in np.flatnonzero(rs.u[0] > 1)[:200]:
+        assert np.all(np.diff(rs.u_positions(0, i)) > 0)
     _, rb = run(big)
     k = len(small)
     cs = np.concatenate([[0], np.cumsum(rs.u[0])])
