@@ -344,30 +344,35 @@ def main():
     value = world * W / (ms_per_step / 1e3)
 
     # ---- e2e: pinned HOST buffers -> C-ABI host engine -> HOST results ----
-    h_packed = torch.empty(packed_bytes, dtype=torch.uint8, pin_memory=True)
-    h_packed.copy_(d_packed)
-    torch.cuda.synchronize()
-    del d_packed
-    torch.cuda.empty_cache()
-    pg = PackedGenotypes(lay, S, pos, h_packed.numpy())
-    eng = HostEngine(local)
     Ke = args.e2e_steps if args.e2e_steps is not None else max(3, min(K, 10))
-    r2 = eng.score_arrays(pg, ws, we, [job])  # warm-up (allocates device buffers)
-    same = bool(np.array_equal(r2.u, res.u) and np.array_equal(r2.q, res.q, equal_nan=True))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        r2 = eng.score_arrays(pg, ws, we, [job])
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_value = world * W / (t_e2e / Ke)
-    h2d = packed_bytes + pos.nbytes + ws.nbytes + we.nbytes
-    d2h = int(r2.nsnps.nbytes + r2.u.nbytes + r2.q.nbytes + r2.q_cnt.nbytes + r2.u_start.nbytes + r2.q_start.nbytes
-              + r2.totals.nbytes + 4 * int(r2.totals.sum()))
-    eng.close()
+    e2e = None
+    if Ke > 0:
+        h_packed = torch.empty(packed_bytes, dtype=torch.uint8, pin_memory=True)
+        h_packed.copy_(d_packed)
+        torch.cuda.synchronize()
+        del d_packed
+        torch.cuda.empty_cache()
+        pg = PackedGenotypes(lay, S, pos, h_packed.numpy())
+        eng = HostEngine(local)
+        r2 = eng.score_arrays(pg, ws, we, [job])  # warm-up (allocates device buffers)
+        same = bool(np.array_equal(r2.u, res.u) and np.array_equal(r2.q, res.q, equal_nan=True))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            r2 = eng.score_arrays(pg, ws, we, [job])
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        h2d = packed_bytes + pos.nbytes + ws.nbytes + we.nbytes
+        d2h = int(r2.nsnps.nbytes + r2.u.nbytes + r2.q.nbytes + r2.q_cnt.nbytes + r2.u_start.nbytes + r2.q_start.nbytes
+                  + r2.totals.nbytes + 4 * int(r2.totals.sum()))
+        eng.close()
+        e2e = {
+            "value": world * W / (t_e2e / Ke), "unit": "windows/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": Ke, "ms_per_step": 1e3 * t_e2e / Ke, "matches_device_path": same,
+        }
 
     # ---- roofline of the dominant kernel (K1) ----
     peak, peak_src = measured_peaks()
@@ -429,10 +434,7 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "k1_ms": k1_ms, "algorithmic_bytes": alg,
             },
             "cpu_baseline": cpu,
-            "e2e": {
-                "value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": Ke, "ms_per_step": 1e3 * t_e2e / Ke, "matches_device_path": same,
-            },
+            "e2e": e2e,
             "gpu_launches": 2 * K,
             "clocks": clocks.summary(),
             "check": {"u_total": u_total, "windows_with_q": q_finite},

@@ -14,7 +14,9 @@
 
 namespace sai {
 
-// streaming 8-byte load: read-only path, do not allocate in L1
+// streaming 8-byte load: read-only path, do not allocate in L1.  (An L2
+// evict-first cache hint was measured: it made the window kernel 14 us faster
+// but this kernel 80 us slower -- profiles/round1_notes.md.)
 __device__ __forceinline__ uint2 ld_stream(const uint2* p) {
   uint2 r;
   asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));

@@ -2,12 +2,15 @@
 //
 // One warp owns one (job, window).  A window [start, end] (inclusive,
 // sai/generators/window_generator.py:173-174) maps to the site range [lo, hi)
-// by a cooperative 32-ary search on the sorted positions; its U count is the popcount of the
-// tile masks over that range (sai/stats/u_statistic.py:94-96) and Q is the
-// numpy 'linear' quantile of the flagged sites' target frequencies
+// by a cooperative 32-ary search on the sorted positions; its U count is the
+// popcount of the tile masks over that range (sai/stats/u_statistic.py:94-96)
+// and Q is the numpy 'linear' quantile of the flagged sites' target frequencies
 // (sai/stats/q_statistic.py:96-101; numpy/lib/_function_base_impl.py _lerp).
 // Order statistics are selected exactly on the float64 bit patterns (all
 // values are non-negative, so unsigned order == numeric order).
+//
+// The kernel is issue-bound (see profiles/), so all site / tile indices are
+// 32-bit (n_sites < 2^31 is checked on the host) and warp sums use REDUX.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -15,15 +18,16 @@
 namespace sai {
 
 constexpr int kWinWarps = 4;
-constexpr int kBufCap = 1024;  // doubles buffered in shared memory per warp
+constexpr int kBufCap = 256;    // doubles buffered in shared memory per warp (more: global walk)
+constexpr int kMaskCache = 64;  // tiles whose masks stay in shared memory between the two walks
 
 struct WinParams {
   const int32_t* pos;
-  int64_t n_sites;
-  int64_t n_tiles;
+  int32_t n_sites;
+  int32_t n_tiles;
   const int64_t* ws;
   const int64_t* we;
-  int64_t W;
+  int32_t W;
   int32_t n_jobs;
   int32_t u_enabled[SAI_MAX_JOBS];
   int32_t q_enabled[SAI_MAX_JOBS];
@@ -45,32 +49,41 @@ struct WinParams {
   int64_t cap_q;
 };
 
+__device__ __forceinline__ int clamp_key(int64_t k) {
+  return k > 2147483647ll ? 2147483647 : (k < -2147483647ll ? -2147483647 : (int)k);
+}
+
 // Cooperative 32-ary lower bounds of two keys at once: first index whose
 // position is >= key.  Each round probes 32 evenly spaced positions per key, so
 // a 6 M-site chromosome needs 5 dependent rounds instead of 2 x 23 binary steps.
-__device__ __forceinline__ void warp_lower_bound2(const int32_t* __restrict__ pos, int64_t n,
+__device__ __forceinline__ void warp_lower_bound2(const int32_t* __restrict__ pos, int n,
                                                   int64_t key_a, int64_t key_b, int lane,
-                                                  int64_t& out_a, int64_t& out_b) {
-  int64_t lo_a = 0, hi_a = n, lo_b = 0, hi_b = n;  // answer in [lo, hi]
+                                                  int& out_a, int& out_b) {
+  // positions are int32: clamp the keys so that the comparisons can be 32-bit
+  const int ka = clamp_key(key_a), kb = clamp_key(key_b);
+  // a key beyond INT32_MAX is above every position
+  int lo_a = key_a > 2147483647ll ? n : 0, hi_a = n;  // answer in [lo, hi]
+  int lo_b = key_b > 2147483647ll ? n : 0, hi_b = n;
   while (hi_a > lo_a || hi_b > lo_b) {
-    const int64_t na = hi_a - lo_a, nb = hi_b - lo_b;
-    const int64_t sa = na > 32 ? (na + 31) / 32 : 1, sb = nb > 32 ? (nb + 31) / 32 : 1;
-    const int64_t ia = lo_a + (lane + 1) * sa - 1, ib = lo_b + (lane + 1) * sb - 1;
-    const bool pa = ia < hi_a && (int64_t)__ldg(pos + ia) < key_a;
-    const bool pb = ib < hi_b && (int64_t)__ldg(pos + ib) < key_b;
+    const int na = hi_a - lo_a, nb = hi_b - lo_b;
+    const int sa = na > 32 ? (na + 31) >> 5 : 1, sb = nb > 32 ? (nb + 31) >> 5 : 1;
+    const unsigned ia = (unsigned)lo_a + (unsigned)(lane + 1) * (unsigned)sa - 1u;
+    const unsigned ib = (unsigned)lo_b + (unsigned)(lane + 1) * (unsigned)sb - 1u;
+    const bool pa = ia < (unsigned)hi_a && __ldg(pos + ia) < ka;
+    const bool pb = ib < (unsigned)hi_b && __ldg(pos + ib) < kb;
     const int ca = __popc(__ballot_sync(0xffffffffu, pa));  // sorted => the true lanes are a prefix
     const int cb = __popc(__ballot_sync(0xffffffffu, pb));
     if (na > 0) {
       // probes 0..ca-1 are < key, probe ca (if it exists) is >= key
-      const int64_t nhi = lo_a + (int64_t)(ca + 1) * sa - 1;
-      lo_a += (int64_t)ca * sa;
-      if (nhi < hi_a) hi_a = nhi;
+      const unsigned nhi = (unsigned)lo_a + (unsigned)(ca + 1) * (unsigned)sa - 1u;
+      lo_a += ca * sa;
+      if (nhi < (unsigned)hi_a) hi_a = (int)nhi;
       if (lo_a > hi_a) lo_a = hi_a;
     }
     if (nb > 0) {
-      const int64_t nhi = lo_b + (int64_t)(cb + 1) * sb - 1;
-      lo_b += (int64_t)cb * sb;
-      if (nhi < hi_b) hi_b = nhi;
+      const unsigned nhi = (unsigned)lo_b + (unsigned)(cb + 1) * (unsigned)sb - 1u;
+      lo_b += cb * sb;
+      if (nhi < (unsigned)hi_b) hi_b = (int)nhi;
       if (lo_b > hi_b) lo_b = hi_b;
     }
   }
@@ -78,11 +91,7 @@ __device__ __forceinline__ void warp_lower_bound2(const int32_t* __restrict__ po
   out_b = lo_b;
 }
 
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 __device__ __forceinline__ int warp_excl_scan(int v, int lane) {
   int x = v;
 #pragma unroll
@@ -107,11 +116,11 @@ __device__ __forceinline__ unsigned long long warp_min64(unsigned long long v) {
 }
 
 // Site range of a window restricted to tile T: mask of the bits inside [lo, hi).
-__device__ __forceinline__ uint32_t range_mask(int64_t T, int64_t lo, int64_t hi) {
-  const int64_t base = T * kTile;
+__device__ __forceinline__ uint32_t range_mask(int T, int lo, int hi) {
+  const int base = T * kTile;
   uint32_t m = 0xffffffffu;
-  if (lo > base) m &= 0xffffffffu << (int)(lo - base);
-  if (hi < base + kTile) m &= 0xffffffffu >> (int)(base + kTile - hi);
+  if (lo > base) m <<= (lo - base);
+  if (hi < base + kTile) m &= 0xffffffffu >> (base + kTile - hi);
   return m;
 }
 
@@ -120,16 +129,16 @@ __device__ __forceinline__ uint32_t range_mask(int64_t T, int64_t lo, int64_t hi
 struct MaskSource {
   const uint32_t* mask;  // job's mask_q
   const double* qval;    // job's qval
-  int64_t lo, hi, T0, T1;
+  int lo, hi, T0, T1;
   int lane;
   template <typename F>
   __device__ __forceinline__ void for_each(F f) const {
-    for (int64_t T = T0 + lane; T <= T1; T += 32) {
+    for (int T = T0 + lane; T <= T1; T += 32) {
       uint32_t m = __ldg(mask + T) & range_mask(T, lo, hi);
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
-        f((unsigned long long)__double_as_longlong(__ldg(qval + T * kTile + b)));
+        f((unsigned long long)__double_as_longlong(__ldg(qval + (size_t)T * kTile + b)));
       }
     }
   }
@@ -273,47 +282,58 @@ __device__ double warp_quantile_small(unsigned long long key, int n, double q, i
   return lerp_numpy(a, b, g);
 }
 
-__global__ void __launch_bounds__(kWinWarps * 32) k_window_stats(const __grid_constant__ WinParams P) {
+// grid: x = window groups (kWinWarps windows per block, grid-stride), y = job
+__global__ void __launch_bounds__(kWinWarps * 32, 8) k_window_stats(const __grid_constant__ WinParams P) {
   __shared__ unsigned long long s_buf[kWinWarps][kBufCap];
-  __shared__ int s_hist[kWinWarps][256];
+  __shared__ int s_hist[kWinWarps][256];  // 14.3 KB per block in total -> 16 blocks per SM
+  __shared__ uint32_t s_mu[kWinWarps][kMaskCache], s_mq[kWinWarps][kMaskCache];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t total = (int64_t)P.n_jobs * P.W;
-  for (int64_t item = (int64_t)blockIdx.x * kWinWarps + warp; item < total;
-       item += (int64_t)gridDim.x * kWinWarps) {
-    const int j = (int)(item / P.W);
-    const int64_t i = item - (int64_t)j * P.W;
-    int64_t lo, hi;
+  const int j = blockIdx.y;
+  const uint32_t* __restrict__ mu = P.mask_u + (size_t)j * P.n_tiles;
+  const uint32_t* __restrict__ mq = P.mask_q + (size_t)j * P.n_tiles;
+  const double* __restrict__ qv = P.qval + (size_t)j * P.qval_stride;
+  const bool want_u = P.u_enabled[j] != 0, want_q = P.q_enabled[j] != 0;
+  const double qq = P.quantile[j];
+  int32_t* __restrict__ uc = P.u_cand + (size_t)j * P.cap_u;
+  int32_t* __restrict__ qc = P.q_cand + (size_t)j * P.cap_q;
+  unsigned long long* buf = s_buf[warp];
+  uint32_t* cmu = s_mu[warp];
+  uint32_t* cmq = s_mq[warp];
+
+  for (int i = blockIdx.x * kWinWarps + warp; i < P.W; i += gridDim.x * kWinWarps) {
+    const size_t item = (size_t)j * P.W + i;
+    int lo, hi;
     warp_lower_bound2(P.pos, P.n_sites, P.ws[i], P.we[i] + 1, lane, lo, hi);
-    const uint32_t* mu = P.mask_u + (size_t)j * P.n_tiles;
-    const uint32_t* mq = P.mask_q + (size_t)j * P.n_tiles;
-    const double* qv = P.qval + (size_t)j * P.qval_stride;
-    const bool want_u = P.u_enabled[j] != 0, want_q = P.q_enabled[j] != 0;
     int u_cnt = 0, q_n = 0;
-    int64_t T0 = 0, T1 = -1;
+    int T0 = 0, T1 = -1;
     if (hi > lo) {
-      T0 = lo / kTile;
-      T1 = (hi - 1) / kTile;
-      unsigned long long* buf = s_buf[warp];
-      for (int64_t Tb = T0; Tb <= T1; Tb += 32) {
-        const int64_t T = Tb + lane;
+      T0 = lo >> 5;
+      T1 = (hi - 1) >> 5;
+      for (int Tb = T0; Tb <= T1; Tb += 32) {
+        const int T = Tb + lane;
         uint32_t a = 0, b = 0;
         if (T <= T1) {
           const uint32_t rm = range_mask(T, lo, hi);
           if (want_u) a = __ldg(mu + T) & rm;
           if (want_q) b = __ldg(mq + T) & rm;
+          if (T - T0 < kMaskCache) {
+            cmu[T - T0] = a;
+            cmq[T - T0] = b;
+          }
         }
         u_cnt += __popc(a);
-        const int c = __popc(b);
-        const int off = q_n + warp_excl_scan(c, lane);
-        q_n += warp_sum(c);
-        // gather this lane's flagged values into the warp buffer (site order)
-        int w = off;
-        while (b) {
-          const int bit = __ffs(b) - 1;
-          b &= b - 1;
-          if (w < kBufCap)
-            buf[w] = (unsigned long long)__double_as_longlong(__ldg(qv + T * kTile + bit));
-          ++w;
+        if (__any_sync(0xffffffffu, b != 0)) {
+          const int c = __popc(b);
+          int w = q_n + warp_excl_scan(c, lane);
+          q_n += warp_sum(c);
+          // gather this lane's flagged values into the warp buffer (site order)
+          while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1;
+            if (w < kBufCap)
+              buf[w] = (unsigned long long)__double_as_longlong(__ldg(qv + (size_t)T * kTile + bit));
+            ++w;
+          }
         }
       }
       u_cnt = warp_sum(u_cnt);
@@ -322,14 +342,13 @@ __global__ void __launch_bounds__(kWinWarps * 32) k_window_stats(const __grid_co
     double qres = CUDART_NAN;
     int q_cand = 0;
     if (q_n > 0) {
-      const double qq = P.quantile[j];
       if (q_n <= 32) {
-        const unsigned long long key = lane < q_n ? s_buf[warp][lane] : ~0ull;
+        const unsigned long long key = lane < q_n ? buf[lane] : ~0ull;
         qres = warp_quantile_small(key, q_n, qq, lane);
         const bool ge = lane < q_n && __longlong_as_double((long long)key) >= qres;
         q_cand = __popc(__ballot_sync(0xffffffffu, ge));
       } else if (q_n <= kBufCap) {
-        BufSource src{s_buf[warp], q_n, lane};
+        BufSource src{buf, q_n, lane};
         qres = warp_quantile(src, q_n, qq, s_hist[warp], lane);
         q_cand = warp_count_ge(src, qres);
       } else {
@@ -338,66 +357,68 @@ __global__ void __launch_bounds__(kWinWarps * 32) k_window_stats(const __grid_co
         q_cand = warp_count_ge(src, qres);
       }
     }
-    __syncwarp();
     // reserve this window's slices of the candidate buffers (one atomic each)
     unsigned long long ub = 0, qb = 0;
     if (lane == 0) {
       if (u_cnt > 0) ub = atomicAdd(P.totals + 2 * j, (unsigned long long)u_cnt);
       if (q_cand > 0) qb = atomicAdd(P.totals + 2 * j + 1, (unsigned long long)q_cand);
-      P.nsnps[item] = (int32_t)(hi - lo);
+      P.nsnps[item] = hi - lo;
       P.u[item] = u_cnt;
       P.q[item] = qres;
       P.q_cnt[item] = q_cand;
       P.u_start[item] = (int64_t)ub;
       P.q_start[item] = (int64_t)qb;
     }
-    if (u_cnt == 0 && q_cand == 0) continue;
-    ub = shfl64(ub, 0);
-    qb = shfl64(qb, 0);
-    // second walk: candidate positions in site order (u_statistic.py:95, q_statistic.py:101)
-    int32_t* uc = P.u_cand + (size_t)j * P.cap_u;
-    int32_t* qc = P.q_cand + (size_t)j * P.cap_q;
-    int64_t uw = (int64_t)ub, qw = (int64_t)qb;
-    for (int64_t Tb = T0; Tb <= T1; Tb += 32) {
-      const int64_t T = Tb + lane;
-      uint32_t a = 0, b = 0;
-      if (T <= T1) {
-        const uint32_t rm = range_mask(T, lo, hi);
-        if (u_cnt > 0) a = __ldg(mu + T) & rm;
-        if (q_cand > 0) {
-          uint32_t m = __ldg(mq + T) & rm;
+    if (u_cnt > 0 || q_cand > 0) {
+      ub = shfl64(ub, 0);
+      qb = shfl64(qb, 0);
+      // second walk: candidate positions in site order (u_statistic.py:95, q_statistic.py:101)
+      long long uw = (long long)ub, qw = (long long)qb;
+      for (int Tb = T0; Tb <= T1; Tb += 32) {
+        const int T = Tb + lane;
+        uint32_t a = 0, b = 0;
+        if (T <= T1) {
+          uint32_t m;
+          if (T - T0 < kMaskCache) {
+            a = cmu[T - T0];
+            m = cmq[T - T0];
+          } else {
+            const uint32_t rm = range_mask(T, lo, hi);
+            a = want_u ? (__ldg(mu + T) & rm) : 0u;
+            m = want_q ? (__ldg(mq + T) & rm) : 0u;
+          }
           while (m) {
             const int bit = __ffs(m) - 1;
             m &= m - 1;
-            if (__ldg(qv + T * kTile + bit) >= qres) b |= 1u << bit;
+            if (__ldg(qv + (size_t)T * kTile + bit) >= qres) b |= 1u << bit;
+          }
+        }
+        if (__any_sync(0xffffffffu, a != 0)) {
+          const int ca = __popc(a);
+          long long wa = uw + warp_excl_scan(ca, lane);
+          uw += warp_sum(ca);
+          while (a) {
+            const int bit = __ffs(a) - 1;
+            a &= a - 1;
+            if (wa < P.cap_u) uc[wa] = __ldg(P.pos + T * kTile + bit);
+            ++wa;
+          }
+        }
+        if (__any_sync(0xffffffffu, b != 0)) {
+          const int cb = __popc(b);
+          long long wb = qw + warp_excl_scan(cb, lane);
+          qw += warp_sum(cb);
+          while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1;
+            if (wb < P.cap_q) qc[wb] = __ldg(P.pos + T * kTile + bit);
+            ++wb;
           }
         }
       }
-      const int ca = __popc(a), cb = __popc(b);
-      int64_t wa = uw + warp_excl_scan(ca, lane);
-      int64_t wb = qw + warp_excl_scan(cb, lane);
-      uw += warp_sum(ca);
-      qw += warp_sum(cb);
-      while (a) {
-        const int bit = __ffs(a) - 1;
-        a &= a - 1;
-        if (wa < P.cap_u) uc[wa] = __ldg(P.pos + T * kTile + bit);
-        ++wa;
-      }
-      while (b) {
-        const int bit = __ffs(b) - 1;
-        b &= b - 1;
-        if (wb < P.cap_q) qc[wb] = __ldg(P.pos + T * kTile + bit);
-        ++wb;
-      }
     }
+    __syncwarp();  // the shared buffers are reused by the next window
   }
-}
-
-static int win_grid(int64_t items) {
-  const int64_t want = (items + kWinWarps - 1) / kWinWarps;
-  const int64_t cap = (int64_t)sm_count() * 16;
-  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
 }  // namespace sai
@@ -412,8 +433,8 @@ extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int
                                 int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand,
                                 int64_t cap_u, int32_t* d_q_cand, int64_t cap_q, void* stream) {
   SAI_REQUIRE(d_pos && d_mask_u && d_mask_q && d_qval && d_totals, "NULL device pointer");
-  SAI_REQUIRE(n_sites >= 0 && n_sites < (1ll << 31), "n_sites out of range");
-  SAI_REQUIRE(n_windows >= 0, "negative window count");
+  SAI_REQUIRE(n_sites >= 0 && n_sites < (1ll << 31) - 64, "n_sites out of range");
+  SAI_REQUIRE(n_windows >= 0 && n_windows < (1ll << 31) - 1024, "window count out of range");
   SAI_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= SAI_MAX_JOBS, "n_jobs %d outside [1,%d]", n_jobs,
               SAI_MAX_JOBS);
   SAI_REQUIRE(qval_stride >= n_sites, "qval_stride too small");
@@ -424,11 +445,11 @@ extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int
               "bad candidate buffers");
   WinParams P{};
   P.pos = d_pos;
-  P.n_sites = n_sites;
-  P.n_tiles = sai_num_tiles(n_sites);
+  P.n_sites = (int32_t)n_sites;
+  P.n_tiles = (int32_t)sai_num_tiles(n_sites);
   P.ws = d_win_start;
   P.we = d_win_end;
-  P.W = n_windows;
+  P.W = (int32_t)n_windows;
   P.n_jobs = n_jobs;
   for (int j = 0; j < n_jobs; ++j) {
     P.u_enabled[j] = jobs[j].u.enabled;
@@ -456,7 +477,10 @@ extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SAI_CUDA_CHECK(cudaMemsetAsync(d_totals, 0, sizeof(int64_t) * 2 * n_jobs, st));
   if (n_windows == 0) return SAI_OK;
-  k_window_stats<<<win_grid((int64_t)n_jobs * n_windows), kWinWarps * 32, 0, st>>>(P);
+  const int64_t want = (n_windows + kWinWarps - 1) / kWinWarps;
+  const int64_t cap = (int64_t)sm_count() * 32;
+  const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_jobs);
+  k_window_stats<<<grid, kWinWarps * 32, 0, st>>>(P);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }
