@@ -1,0 +1,95 @@
+"""Top-level ``score`` with the signature and file outputs of the reference's
+``sai.sai.score`` (sai/sai.py:33-151), running the U/Q path on the GPU.
+
+Only U and Q are computed here (the hot path this package covers); a config
+that enables another statistic is rejected instead of silently writing
+partial rows.  In a reference-side integration ``score`` itself stays
+untouched and only the ``ChunkPreprocessor`` it constructs is swapped
+(INTEGRATION.md).
+"""
+
+from __future__ import annotations
+
+import os
+from pathlib import Path
+
+from .configs import load_config
+from .preprocessors import ChunkPreprocessor
+from .vcf import _open_text
+from .windows import split_genome, split_windows_ranges
+
+
+def chromosome_span(vcf_file: str, chr_name: str) -> tuple[int, int]:
+    """First and last POS of ``chr_name`` (what ``ChunkGenerator.__init__``
+    finds with pysam, sai/generators/chunk_generator.py:64-76)."""
+    first = last = None
+    with _open_text(vcf_file) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            tab = line.find("\t")
+            if line[:tab] != chr_name:
+                if first is not None:
+                    break
+                continue
+            p = int(line[tab + 1 : line.find("\t", tab + 1)])
+            if first is None:
+                first = p
+            last = p
+    if first is None:
+        raise ValueError(f"Chromosome {chr_name} not found in VCF.")
+    return first, last
+
+
+def score(
+    vcf_file: str,
+    chr_name: str,
+    win_len: int,
+    win_step: int,
+    anc_allele_file: str,
+    output_file: str,
+    config: str,
+    num_workers: int = 1,
+    device: int = 0,
+) -> None:
+    cfg = load_config(config)
+    stat_config, ploidy_config, pop_config = cfg.statistics, cfg.ploidies, cfg.populations
+    others = [s for s in stat_config.root if s not in ("U", "Q") and stat_config.root[s] is not False]
+    if others:
+        raise NotImplementedError(
+            f"sai_b200 covers the U and Q statistics only; the configuration also enables {others}."
+        )
+    first, last = chromosome_span(vcf_file, chr_name)
+    windows = split_genome([first, last], win_len, win_step)
+    # one chunk per worker slot, processed one after the other on this GPU
+    # (sai.py:92 fixes num_chunks=1; the multi-GPU driver is sai_b200.distributed)
+    chunks = split_windows_ranges(windows, max(1, int(num_workers)))
+    pre = ChunkPreprocessor(
+        vcf_file=vcf_file,
+        ref_ind_file=pop_config.get_population("ref"),
+        tgt_ind_file=pop_config.get_population("tgt"),
+        src_ind_file=pop_config.get_population("src"),
+        out_ind_file=pop_config.get_population("outgroup"),
+        win_len=win_len,
+        win_step=win_step,
+        output_file=output_file,
+        ploidy_config=ploidy_config,
+        stat_config=stat_config,
+        anc_allele_file=anc_allele_file,
+        device=device,
+    )
+    header = ["Chrom", "Start", "End", "Ref", "Tgt", "Src", "Outgroup", "N(Variants)"]
+    header += [s for s in stat_config.root if s in ("U", "Q")]
+    directory = os.path.dirname(output_file)
+    if directory:
+        os.makedirs(directory, exist_ok=True)
+    with open(output_file, "w") as f:
+        f.write("\t".join(header) + "\n")
+    for key in ("U", "Q"):
+        if key in stat_config.root:
+            with open(Path(output_file).with_suffix(f".{key}.log"), "w") as f:
+                f.write(f"Chrom\tStart\tEnd\t{key}_SNP\n")
+    items = []
+    for start, end in chunks:
+        items.extend(pre.run(chr_name, start, end))
+    pre.process_items(items)

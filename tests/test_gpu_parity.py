@@ -174,6 +174,62 @@ def test_vcf_fixture_gpu(name, tmp_path):
         assert [it["U"] for it in items] == [0, 1]  # reference tests/test_sai.py:150-151
 
 
+def test_score_entry_point_gpu(tmp_path):
+    """`score()` (signature of sai.sai.score): YAML config + VCF -> TSV + logs,
+    Q == 0.9 like the reference's tests/test_sai.py:45-63."""
+    import pandas as pd
+    import yaml
+
+    from sai_b200.score import score
+
+    case = json.load(open(os.path.join(GOLDEN, "vcf_example_q.json")))
+    cfg = tmp_path / "cfg.yaml"
+    cfg.write_text(yaml.safe_dump({
+        "statistics": case["stats"], "ploidies": case["ploidies"],
+        "populations": {g: os.path.join(GOLDEN, f"vcf_example_q.{g}.list") for g in ("ref", "tgt", "src")}}))
+    out = tmp_path / "sub" / "out.tsv"
+    score(os.path.join(GOLDEN, case["vcf"]), "21", 6666, 6666, None, str(out), str(cfg), 1)
+    df = pd.read_csv(out, sep="\t")
+    assert list(df.columns) == ["Chrom", "Start", "End", "Ref", "Tgt", "Src", "Outgroup", "N(Variants)", "Q"]
+    assert df["Q"].iloc[0] == 0.9
+    assert out.read_text().split("\n", 1)[1] == case["text"]["tsv"]
+    assert (tmp_path / "sub" / "out.Q.log").read_text() == "Chrom\tStart\tEnd\tQ_SNP\n" + case["text"]["Q"]
+    with pytest.raises(FileNotFoundError, match="not found"):
+        score(os.path.join(GOLDEN, case["vcf"]), "21", 6666, 6666, None, str(out), "config.yaml", 1)
+    with pytest.raises(ValueError, match="not found in VCF"):
+        score(os.path.join(GOLDEN, case["vcf"]), "7", 6666, 6666, None, str(out), str(cfg), 1)
+
+
+def test_sharded_equals_unsharded_gpu(engine):
+    """Window-range shards with their win_len - win_step halo (the multi-GPU
+    partition, chunk_generator.py:111-142) give exactly the unsharded rows."""
+    from sai_b200.preprocessors import score_populations
+    from sai_b200.windows import chunk_windows, split_genome, split_windows_ranges
+
+    pops = {"ref": {"R": (100, 2)}, "tgt": {"T": (80, 2)}, "src": {"S": (2, 2)}}
+    stats = SimpleStats({"U": {"ref": {"R": 0.05}, "tgt": {"T": 0.2}, "src": {"S": "=1"}},
+                         "Q": {"ref": {"R": 0.05}, "tgt": {"T": 0.9}, "src": {"S": "=1"}}})
+    pc = SimplePloidy({"ref": {"R": 2}, "tgt": {"T": 2}, "src": {"S": 2}})
+    pos, mats = synth.make_populations(41, 12000, pops, mean_gap=70.0, introgressed=0.02, missing=0.01)
+    wins = split_genome([int(pos[0]), int(pos[-1])], 50000, 10000)
+
+    def run(start, end):
+        keep = (pos >= start) & (pos <= end)  # region read of the shard
+        mk = lambda m: _pop(pos[keep], m[keep])
+        return score_populations("3", {"T": chunk_windows(start, end, 50000, 10000)}, {"R": mk(mats["ref"]["R"])},
+                                 {"T": mk(mats["tgt"]["T"])}, {"S": mk(mats["src"]["S"])}, pc, stats, True, engine)
+
+    whole = run(*split_windows_ranges(wins, 1)[0])
+    for n in (2, 3, 8):
+        parts = [it for s, e in split_windows_ranges(wins, n) for it in run(s, e)]
+        assert len(parts) == len(whole) == len(wins)
+        for a, b in zip(parts, whole):
+            assert (a["start"], a["end"], a["nsnps"], a["U"]) == (b["start"], b["end"], b["nsnps"], b["U"])
+            assert (np.isnan(a["Q"]) and np.isnan(b["Q"])) or a["Q"] == b["Q"]
+            assert np.array_equal(a["cdd_pos"]["U"], b["cdd_pos"]["U"]) and np.array_equal(a["cdd_pos"]["Q"], b["cdd_pos"]["Q"])
+    assert sum(it["U"] for it in whole) > 0
+
+
 # ---------------------------------------------------------------- K1 alone
 @pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("shape", [(1, [1, 1, 1]), (33, [5, 40, 2]), (1000, [257, 96, 3]), (4097, [1500, 1000, 4])])
