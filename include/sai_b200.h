@@ -142,7 +142,10 @@ int sai_unpack_i8(const sai_layout* lay, int32_t pop, const uint8_t* packed,
 /* For tiles [tile0, tile0+n_tiles): per population p and site s
  *     num[p*stride + s]    = sum of called values      (stat_utils.py:48)
  *     called[p*stride + s] = number of called individuals (stat_utils.py:46)
- * d_packed points at tile 0.  variant: 0 = LDG path, 1 = TMA bulk-copy ring. */
+ * d_packed points at tile 0.  variant (tuning / A-B knob, same results):
+ *   0 = carry-save popcount, 8 loads in flight per lane (default)
+ *   1 = carry-save popcount, 16 loads in flight per lane
+ *   2 = direct POPC per word (XU-pipe bound; kept as the baseline) */
 int sai_site_counts(const sai_layout* lay, const void* d_packed, int64_t tile0,
                     int64_t n_tiles, int32_t* d_num, int32_t* d_called,
                     int64_t stride, int32_t variant, void* stream);

@@ -63,13 +63,34 @@ struct SliceCounter {
 
 // B == 2 population: planes (a = bit0, b = bit1) of one group sit in one pair.
 //   num  = popc(a) + 2 popc(b) - 3 popc(a&b),   missing = popc(a&b)
-template <int SIMPLE>
+template <int MODE>
 __device__ __forceinline__ void count_b2(const uint2* __restrict__ col, int n_pairs, int& num,
                                          int& miss) {
   int p = 0;
   int acc_a = 0, acc_b = 0, acc_m = 0;
-  if (!SIMPLE) {
+  if (MODE != 2) {
     SliceCounter ca, cb, cm;
+    if (MODE == 1) {
+      // 16 loads in flight per lane
+      for (; p + 16 <= n_pairs; p += 16) {
+        uint2 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = ld_stream(col + (size_t)(p + i) * kTile);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t a[8], b[8], m[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            a[i] = v[8 * h + i].x;
+            b[i] = v[8 * h + i].y;
+            m[i] = v[8 * h + i].x & v[8 * h + i].y;
+          }
+          ca.add8(a);
+          cb.add8(b);
+          cm.add8(m);
+        }
+      }
+    }
     for (; p + 8 <= n_pairs; p += 8) {
       uint2 v[8];
 #pragma unroll
@@ -89,7 +110,7 @@ __device__ __forceinline__ void count_b2(const uint2* __restrict__ col, int n_pa
     acc_b = cb.total();
     acc_m = cm.total();
   }
-  // remainder (and the SIMPLE variant): direct popcounts
+  // remainder (and MODE 2): direct popcounts
 #pragma unroll 4
   for (; p < n_pairs; ++p) {
     uint2 v = ld_stream(col + (size_t)p * kTile);
@@ -140,8 +161,8 @@ struct SiteParams {
 
 constexpr int kSiteWarps = 8;
 
-template <int SIMPLE, bool FUSED>
-__global__ void __launch_bounds__(kSiteWarps * 32)
+template <int MODE, bool FUSED>
+__global__ void __launch_bounds__(kSiteWarps * 32, MODE == 1 ? 3 : 1)
     k_site(const __grid_constant__ SiteParams P, const __grid_constant__ JobBlock JB) {
   extern __shared__ int s_counts[];  // [warp][2][n_pops][32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(kSiteWarps * 32)
       const uint2* col = tile + (size_t)L.pair_off * kTile;
       int num, miss;
       if (L.bits == 2)
-        count_b2<SIMPLE>(col, L.n_pairs, num, miss);
+        count_b2<MODE>(col, L.n_pairs, num, miss);
       else
         count_generic(col, L.n_groups, L.bits, num, miss);
       const int called = L.n_groups * 32 - miss;
@@ -230,18 +251,18 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <int SIMPLE, bool FUSED>
+template <int MODE, bool FUSED>
 static int launch_site(const SiteParams& P, const JobBlock& JB, cudaStream_t st) {
   if (P.n_tiles == 0) return SAI_OK;
   const size_t smem = (size_t)kSiteWarps * 2 * P.lay.n_pops * kTile * sizeof(int);
   int occ = 0;
-  SAI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_site<SIMPLE, FUSED>,
+  SAI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_site<MODE, FUSED>,
                                                                kSiteWarps * 32, smem));
   if (occ < 1) occ = 1;
   int64_t want = (P.n_tiles + kSiteWarps - 1) / kSiteWarps;
   int64_t cap = (int64_t)sm_count() * occ;
   int grid = (int)(want < cap ? want : cap);
-  k_site<SIMPLE, FUSED><<<grid, kSiteWarps * 32, smem, st>>>(P, JB);
+  k_site<MODE, FUSED><<<grid, kSiteWarps * 32, smem, st>>>(P, JB);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }
@@ -269,7 +290,8 @@ int sai_site_counts(const sai_layout* lay, const void* d_packed, int64_t tile0, 
   P.count_stride = stride;
   JobBlock JB{};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (variant == 2) return launch_site<1, false>(P, JB, st);
+  if (variant == 2) return launch_site<2, false>(P, JB, st);
+  if (variant == 1) return launch_site<1, false>(P, JB, st);
   return launch_site<0, false>(P, JB, st);
 }
 
@@ -301,7 +323,8 @@ int sai_site_flags(const sai_layout* lay, const void* d_packed, int64_t tile0, i
   JB.n_jobs = n_jobs;
   for (int j = 0; j < n_jobs; ++j) JB.job[j] = jobs[j];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (variant == 2) return launch_site<1, true>(P, JB, st);
+  if (variant == 2) return launch_site<2, true>(P, JB, st);
+  if (variant == 1) return launch_site<1, true>(P, JB, st);
   return launch_site<0, true>(P, JB, st);
 }
 

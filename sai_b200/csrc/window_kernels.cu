@@ -12,6 +12,7 @@
 // The kernel is issue-bound (see profiles/), so all site / tile indices are
 // 32-bit (n_sites < 2^31 is checked on the host) and warp sums use REDUX.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -282,142 +283,377 @@ __device__ double warp_quantile_small(unsigned long long key, int n, double q, i
   return lerp_numpy(a, b, g);
 }
 
-// grid: x = window groups (kWinWarps windows per block, grid-stride), y = job
-__global__ void __launch_bounds__(kWinWarps * 32, 8) k_window_stats(const __grid_constant__ WinParams P) {
-  __shared__ unsigned long long s_buf[kWinWarps][kBufCap];
-  __shared__ int s_hist[kWinWarps][256];  // 14.3 KB per block in total -> 16 blocks per SM
-  __shared__ uint32_t s_mu[kWinWarps][kMaskCache], s_mq[kWinWarps][kMaskCache];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.y;
-  const uint32_t* __restrict__ mu = P.mask_u + (size_t)j * P.n_tiles;
-  const uint32_t* __restrict__ mq = P.mask_q + (size_t)j * P.n_tiles;
-  const double* __restrict__ qv = P.qval + (size_t)j * P.qval_stride;
-  const bool want_u = P.u_enabled[j] != 0, want_q = P.q_enabled[j] != 0;
-  const double qq = P.quantile[j];
-  int32_t* __restrict__ uc = P.u_cand + (size_t)j * P.cap_u;
-  int32_t* __restrict__ qc = P.q_cand + (size_t)j * P.cap_q;
-  unsigned long long* buf = s_buf[warp];
-  uint32_t* cmu = s_mu[warp];
-  uint32_t* cmq = s_mq[warp];
+// ---------------------------------------------------------------------------
+// Per-warp scratch.  The batched fast path and the generic path never use it at
+// the same time, so they share the bytes.
+// ---------------------------------------------------------------------------
+constexpr int kFastN = 32;   // flagged sites per window (U and Q each) on the fast path
+constexpr int kFastTiles = 64;
 
-  for (int i = blockIdx.x * kWinWarps + warp; i < P.W; i += gridDim.x * kWinWarps) {
-    const size_t item = (size_t)j * P.W + i;
-    int lo, hi;
-    warp_lower_bound2(P.pos, P.n_sites, P.ws[i], P.we[i] + 1, lane, lo, hi);
-    int u_cnt = 0, q_n = 0;
-    int T0 = 0, T1 = -1;
-    if (hi > lo) {
-      T0 = lo >> 5;
-      T1 = (hi - 1) >> 5;
-      for (int Tb = T0; Tb <= T1; Tb += 32) {
-        const int T = Tb + lane;
-        uint32_t a = 0, b = 0;
-        if (T <= T1) {
+template <int kBatch>
+struct FastScratch {
+  unsigned long long qv[kBatch][kFastN];  // flagged target frequencies (bit patterns)
+  int32_t qpos[kBatch][kFastN];           // their positions
+  int32_t upos[kBatch][kFastN];           // positions of the U-flagged sites
+};
+struct SlowScratch {
+  unsigned long long buf[kBufCap];
+  int hist[256];
+  uint32_t mu[kMaskCache], mq[kMaskCache];
+};
+template <int kBatch>
+union WarpScratch {
+  FastScratch<kBatch> f;
+  SlowScratch s;
+};
+
+struct JobView {
+  const uint32_t* __restrict__ mu;
+  const uint32_t* __restrict__ mq;
+  const double* __restrict__ qv;
+  int32_t* __restrict__ uc;
+  int32_t* __restrict__ qc;
+  bool want_u, want_q;
+  double qq;
+  int j;
+};
+
+// Generic path for one window whose site range [lo, hi) is known: any number of
+// tiles and of flagged sites.
+__device__ void window_generic(const WinParams& P, const JobView& J, SlowScratch& S, int i, int lo,
+                               int hi, int lane) {
+  const size_t item = (size_t)J.j * P.W + i;
+  int u_cnt = 0, q_n = 0;
+  int T0 = 0, T1 = -1;
+  if (hi > lo) {
+    T0 = lo >> 5;
+    T1 = (hi - 1) >> 5;
+    for (int Tb = T0; Tb <= T1; Tb += 32) {
+      const int T = Tb + lane;
+      uint32_t a = 0, b = 0;
+      if (T <= T1) {
+        const uint32_t rm = range_mask(T, lo, hi);
+        if (J.want_u) a = __ldg(J.mu + T) & rm;
+        if (J.want_q) b = __ldg(J.mq + T) & rm;
+        if (T - T0 < kMaskCache) {
+          S.mu[T - T0] = a;
+          S.mq[T - T0] = b;
+        }
+      }
+      u_cnt += __popc(a);
+      if (__any_sync(0xffffffffu, b != 0)) {
+        const int c = __popc(b);
+        int w = q_n + warp_excl_scan(c, lane);
+        q_n += warp_sum(c);
+        while (b) {
+          const int bit = __ffs(b) - 1;
+          b &= b - 1;
+          if (w < kBufCap)
+            S.buf[w] = (unsigned long long)__double_as_longlong(__ldg(J.qv + (size_t)T * kTile + bit));
+          ++w;
+        }
+      }
+    }
+    u_cnt = warp_sum(u_cnt);
+    __syncwarp();
+  }
+  double qres = CUDART_NAN;
+  int q_cand = 0;
+  if (q_n > 0) {
+    if (q_n <= 32) {
+      const unsigned long long key = lane < q_n ? S.buf[lane] : ~0ull;
+      qres = warp_quantile_small(key, q_n, J.qq, lane);
+      const bool ge = lane < q_n && __longlong_as_double((long long)key) >= qres;
+      q_cand = __popc(__ballot_sync(0xffffffffu, ge));
+    } else if (q_n <= kBufCap) {
+      BufSource src{S.buf, q_n, lane};
+      qres = warp_quantile(src, q_n, J.qq, S.hist, lane);
+      q_cand = warp_count_ge(src, qres);
+    } else {
+      MaskSource src{J.mq, J.qv, lo, hi, T0, T1, lane};
+      qres = warp_quantile(src, q_n, J.qq, S.hist, lane);
+      q_cand = warp_count_ge(src, qres);
+    }
+  }
+  // reserve this window's slices of the candidate buffers (one atomic each)
+  unsigned long long ub = 0, qb = 0;
+  if (lane == 0) {
+    if (u_cnt > 0) ub = atomicAdd(P.totals + 2 * J.j, (unsigned long long)u_cnt);
+    if (q_cand > 0) qb = atomicAdd(P.totals + 2 * J.j + 1, (unsigned long long)q_cand);
+    P.nsnps[item] = hi - lo;
+    P.u[item] = u_cnt;
+    P.q[item] = qres;
+    P.q_cnt[item] = q_cand;
+    P.u_start[item] = (int64_t)ub;
+    P.q_start[item] = (int64_t)qb;
+  }
+  if (u_cnt > 0 || q_cand > 0) {
+    ub = shfl64(ub, 0);
+    qb = shfl64(qb, 0);
+    // second walk: candidate positions in site order (u_statistic.py:95, q_statistic.py:101)
+    long long uw = (long long)ub, qw = (long long)qb;
+    for (int Tb = T0; Tb <= T1; Tb += 32) {
+      const int T = Tb + lane;
+      uint32_t a = 0, b = 0;
+      if (T <= T1) {
+        uint32_t m;
+        if (T - T0 < kMaskCache) {
+          a = S.mu[T - T0];
+          m = S.mq[T - T0];
+        } else {
           const uint32_t rm = range_mask(T, lo, hi);
-          if (want_u) a = __ldg(mu + T) & rm;
-          if (want_q) b = __ldg(mq + T) & rm;
-          if (T - T0 < kMaskCache) {
-            cmu[T - T0] = a;
-            cmq[T - T0] = b;
+          a = J.want_u ? (__ldg(J.mu + T) & rm) : 0u;
+          m = J.want_q ? (__ldg(J.mq + T) & rm) : 0u;
+        }
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          if (__ldg(J.qv + (size_t)T * kTile + bit) >= qres) b |= 1u << bit;
+        }
+      }
+      if (__any_sync(0xffffffffu, a != 0)) {
+        const int ca = __popc(a);
+        long long wa = uw + warp_excl_scan(ca, lane);
+        uw += warp_sum(ca);
+        while (a) {
+          const int bit = __ffs(a) - 1;
+          a &= a - 1;
+          if (wa < P.cap_u) J.uc[wa] = __ldg(P.pos + T * kTile + bit);
+          ++wa;
+        }
+      }
+      if (__any_sync(0xffffffffu, b != 0)) {
+        const int cb = __popc(b);
+        long long wb = qw + warp_excl_scan(cb, lane);
+        qw += warp_sum(cb);
+        while (b) {
+          const int bit = __ffs(b) - 1;
+          b &= b - 1;
+          if (wb < P.cap_q) J.qc[wb] = __ldg(P.pos + T * kTile + bit);
+          ++wb;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// 32-ary lower bounds of 2*kBatch keys at once (same invariant as a single
+// search: answer in [lo, hi]); every round has 2*kBatch loads in flight.
+template <int kBatch>
+__device__ __forceinline__ void warp_lower_bound_batch(const int32_t* __restrict__ pos, int n,
+                                                       const int64_t (&key)[2 * kBatch], int lane,
+                                                       int (&out)[2 * kBatch]) {
+  int lo[2 * kBatch], hi[2 * kBatch], k32[2 * kBatch];
+#pragma unroll
+  for (int t = 0; t < 2 * kBatch; ++t) {
+    k32[t] = clamp_key(key[t]);
+    lo[t] = key[t] > 2147483647ll ? n : 0;
+    hi[t] = n;
+  }
+  while (true) {
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < 2 * kBatch; ++t) any = any || (hi[t] > lo[t]);
+    if (!any) break;
+    bool pred[2 * kBatch];
+    int step[2 * kBatch];
+#pragma unroll
+    for (int t = 0; t < 2 * kBatch; ++t) {
+      const int nn = hi[t] - lo[t];
+      step[t] = nn > 32 ? (nn + 31) >> 5 : 1;
+      const unsigned idx = (unsigned)lo[t] + (unsigned)(lane + 1) * (unsigned)step[t] - 1u;
+      pred[t] = idx < (unsigned)hi[t] && __ldg(pos + idx) < k32[t];
+    }
+#pragma unroll
+    for (int t = 0; t < 2 * kBatch; ++t) {
+      const int c = __popc(__ballot_sync(0xffffffffu, pred[t]));
+      if (hi[t] > lo[t]) {
+        const unsigned nhi = (unsigned)lo[t] + (unsigned)(c + 1) * (unsigned)step[t] - 1u;
+        lo[t] += c * step[t];
+        if (nhi < (unsigned)hi[t]) hi[t] = (int)nhi;
+        if (lo[t] > hi[t]) lo[t] = hi[t];
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 2 * kBatch; ++t) out[t] = lo[t];
+}
+
+// grid: x = window batches (kWinWarps * kBatch windows per block, grid-stride), y = job.
+// Each warp works on kBatch consecutive windows at once so that every dependent
+// memory round trip (window bounds, searches, masks, flagged values, slice
+// reservation) is shared by kBatch windows; windows that do not fit the fast
+// path (> 64 tiles or > 32 flagged sites) fall through to window_generic.
+template <int kBatch, int kMinBlocks>
+__global__ void __launch_bounds__(kWinWarps * 32, kMinBlocks)
+    k_window_stats(const __grid_constant__ WinParams P) {
+  __shared__ WarpScratch<kBatch> s_scratch[kWinWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  JobView J;
+  J.j = blockIdx.y;
+  J.mu = P.mask_u + (size_t)J.j * P.n_tiles;
+  J.mq = P.mask_q + (size_t)J.j * P.n_tiles;
+  J.qv = P.qval + (size_t)J.j * P.qval_stride;
+  J.want_u = P.u_enabled[J.j] != 0;
+  J.want_q = P.q_enabled[J.j] != 0;
+  J.qq = P.quantile[J.j];
+  J.uc = P.u_cand + (size_t)J.j * P.cap_u;
+  J.qc = P.q_cand + (size_t)J.j * P.cap_q;
+  WarpScratch<kBatch>& SC = s_scratch[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (int i0 = (blockIdx.x * kWinWarps + warp) * kBatch; i0 < P.W; i0 += gridDim.x * kWinWarps * kBatch) {
+    // ---- A: window bounds as keys (one coalesced load for the whole batch) ----
+    int64_t key[2 * kBatch];
+    {
+      const int k = lane >> 1;  // lanes 0..2*kBatch-1: lane 2k -> start of window k, 2k+1 -> end+1
+      int64_t mine = 0;
+      if (lane < 2 * kBatch && i0 + k < P.W) mine = (lane & 1) ? P.we[i0 + k] + 1 : P.ws[i0 + k];
+#pragma unroll
+      for (int t = 0; t < 2 * kBatch; ++t) key[t] = (int64_t)shfl64((unsigned long long)mine, t);
+    }
+    // ---- B: all searches together ----
+    int bnd[2 * kBatch];
+    warp_lower_bound_batch<kBatch>(P.pos, P.n_sites, key, lane, bnd);
+
+    // ---- C: masks of all windows ----
+    uint32_t a[kBatch][2], b[kBatch][2];
+    int T0[kBatch];
+    bool valid[kBatch], fast[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      const int lo = bnd[2 * k], hi = bnd[2 * k + 1];
+      valid[k] = i0 + k < P.W;
+      T0[k] = lo >> 5;
+      const int T1 = hi > lo ? (hi - 1) >> 5 : T0[k] - 1;
+      fast[k] = valid[k] && (T1 - T0[k] + 1 <= kFastTiles);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int T = T0[k] + it * 32 + lane;
+        a[k][it] = b[k][it] = 0;
+        if (fast[k] && T <= T1) {
+          const uint32_t rm = range_mask(T, lo, hi);
+          if (J.want_u) a[k][it] = __ldg(J.mu + T) & rm;
+          if (J.want_q) b[k][it] = __ldg(J.mq + T) & rm;
+        }
+      }
+    }
+    int u_cnt[kBatch], q_n[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      u_cnt[k] = warp_sum(__popc(a[k][0]) + __popc(a[k][1]));
+      q_n[k] = warp_sum(__popc(b[k][0]) + __popc(b[k][1]));
+      fast[k] = fast[k] && u_cnt[k] <= kFastN && q_n[k] <= kFastN;
+    }
+
+    // ---- D: flagged values / positions into shared memory, loads issued before any store ----
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      if (!fast[k] || (u_cnt[k] == 0 && q_n[k] == 0)) continue;
+      int wq[2], wu[2];
+      {
+        const int c0 = __popc(b[k][0]), c1 = __popc(b[k][1]);
+        wq[0] = q_n[k] ? warp_excl_scan(c0, lane) : 0;
+        wq[1] = q_n[k] ? warp_sum(c0) + warp_excl_scan(c1, lane) : 0;
+        const int d0 = __popc(a[k][0]), d1 = __popc(a[k][1]);
+        wu[0] = u_cnt[k] ? warp_excl_scan(d0, lane) : 0;
+        wu[1] = u_cnt[k] ? warp_sum(d0) + warp_excl_scan(d1, lane) : 0;
+      }
+      unsigned long long vq[2] = {0ull, 0ull};
+      int pq[2] = {0, 0}, pu[2] = {0, 0};
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int site0 = (T0[k] + it * 32 + lane) * kTile;
+        if (b[k][it]) {
+          const int bit = __ffs(b[k][it]) - 1;
+          vq[it] = (unsigned long long)__double_as_longlong(__ldg(J.qv + (size_t)site0 + bit));
+          pq[it] = __ldg(P.pos + site0 + bit);
+        }
+        if (a[k][it]) pu[it] = __ldg(P.pos + site0 + __ffs(a[k][it]) - 1);
+      }
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int site0 = (T0[k] + it * 32 + lane) * kTile;
+        if (b[k][it]) {
+          SC.f.qv[k][wq[it]] = vq[it];
+          SC.f.qpos[k][wq[it]] = pq[it];
+          uint32_t m = b[k][it] & (b[k][it] - 1);  // further flagged sites of the same tile (rare)
+          int w = wq[it] + 1;
+          while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            SC.f.qv[k][w] = (unsigned long long)__double_as_longlong(__ldg(J.qv + (size_t)site0 + bit));
+            SC.f.qpos[k][w] = __ldg(P.pos + site0 + bit);
+            ++w;
           }
         }
-        u_cnt += __popc(a);
-        if (__any_sync(0xffffffffu, b != 0)) {
-          const int c = __popc(b);
-          int w = q_n + warp_excl_scan(c, lane);
-          q_n += warp_sum(c);
-          // gather this lane's flagged values into the warp buffer (site order)
-          while (b) {
-            const int bit = __ffs(b) - 1;
-            b &= b - 1;
-            if (w < kBufCap)
-              buf[w] = (unsigned long long)__double_as_longlong(__ldg(qv + (size_t)T * kTile + bit));
+        if (a[k][it]) {
+          SC.f.upos[k][wu[it]] = pu[it];
+          uint32_t m = a[k][it] & (a[k][it] - 1);
+          int w = wu[it] + 1;
+          while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            SC.f.upos[k][w] = __ldg(P.pos + site0 + bit);
             ++w;
           }
         }
       }
-      u_cnt = warp_sum(u_cnt);
-      __syncwarp();
     }
-    double qres = CUDART_NAN;
-    int q_cand = 0;
-    if (q_n > 0) {
-      if (q_n <= 32) {
-        const unsigned long long key = lane < q_n ? buf[lane] : ~0ull;
-        qres = warp_quantile_small(key, q_n, qq, lane);
-        const bool ge = lane < q_n && __longlong_as_double((long long)key) >= qres;
-        q_cand = __popc(__ballot_sync(0xffffffffu, ge));
-      } else if (q_n <= kBufCap) {
-        BufSource src{buf, q_n, lane};
-        qres = warp_quantile(src, q_n, qq, s_hist[warp], lane);
-        q_cand = warp_count_ge(src, qres);
-      } else {
-        MaskSource src{mq, qv, lo, hi, T0, T1, lane};
-        qres = warp_quantile(src, q_n, qq, s_hist[warp], lane);
-        q_cand = warp_count_ge(src, qres);
+    __syncwarp();
+
+    // ---- E: quantiles (n <= 32: one value per lane) ----
+    double qres[kBatch];
+    unsigned ge[kBatch];
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      qres[k] = CUDART_NAN;
+      ge[k] = 0;
+      if (fast[k] && q_n[k] > 0) {
+        const unsigned long long kv = lane < q_n[k] ? SC.f.qv[k][lane] : ~0ull;
+        qres[k] = warp_quantile_small(kv, q_n[k], J.qq, lane);
+        ge[k] = __ballot_sync(0xffffffffu, lane < q_n[k] && __longlong_as_double((long long)kv) >= qres[k]);
       }
     }
-    // reserve this window's slices of the candidate buffers (one atomic each)
-    unsigned long long ub = 0, qb = 0;
-    if (lane == 0) {
-      if (u_cnt > 0) ub = atomicAdd(P.totals + 2 * j, (unsigned long long)u_cnt);
-      if (q_cand > 0) qb = atomicAdd(P.totals + 2 * j + 1, (unsigned long long)q_cand);
-      P.nsnps[item] = hi - lo;
-      P.u[item] = u_cnt;
-      P.q[item] = qres;
-      P.q_cnt[item] = q_cand;
-      P.u_start[item] = (int64_t)ub;
-      P.q_start[item] = (int64_t)qb;
+    // ---- F: reserve the candidate slices of all fast windows with one atomic instruction ----
+    unsigned long long base = 0;
+    {
+      int want = 0;
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        if (lane == 2 * k && fast[k]) want = u_cnt[k];
+        if (lane == 2 * k + 1 && fast[k]) want = __popc(ge[k]);
+      }
+      if (want > 0) base = atomicAdd(P.totals + 2 * J.j + (lane & 1), (unsigned long long)want);
     }
-    if (u_cnt > 0 || q_cand > 0) {
-      ub = shfl64(ub, 0);
-      qb = shfl64(qb, 0);
-      // second walk: candidate positions in site order (u_statistic.py:95, q_statistic.py:101)
-      long long uw = (long long)ub, qw = (long long)qb;
-      for (int Tb = T0; Tb <= T1; Tb += 32) {
-        const int T = Tb + lane;
-        uint32_t a = 0, b = 0;
-        if (T <= T1) {
-          uint32_t m;
-          if (T - T0 < kMaskCache) {
-            a = cmu[T - T0];
-            m = cmq[T - T0];
-          } else {
-            const uint32_t rm = range_mask(T, lo, hi);
-            a = want_u ? (__ldg(mu + T) & rm) : 0u;
-            m = want_q ? (__ldg(mq + T) & rm) : 0u;
-          }
-          while (m) {
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            if (__ldg(qv + (size_t)T * kTile + bit) >= qres) b |= 1u << bit;
-          }
-        }
-        if (__any_sync(0xffffffffu, a != 0)) {
-          const int ca = __popc(a);
-          long long wa = uw + warp_excl_scan(ca, lane);
-          uw += warp_sum(ca);
-          while (a) {
-            const int bit = __ffs(a) - 1;
-            a &= a - 1;
-            if (wa < P.cap_u) uc[wa] = __ldg(P.pos + T * kTile + bit);
-            ++wa;
-          }
-        }
-        if (__any_sync(0xffffffffu, b != 0)) {
-          const int cb = __popc(b);
-          long long wb = qw + warp_excl_scan(cb, lane);
-          qw += warp_sum(cb);
-          while (b) {
-            const int bit = __ffs(b) - 1;
-            b &= b - 1;
-            if (wb < P.cap_q) qc[wb] = __ldg(P.pos + T * kTile + bit);
-            ++wb;
-          }
-        }
+    // ---- G: results and candidate positions ----
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      if (!fast[k]) continue;
+      const long long ub = (long long)shfl64(base, 2 * k), qb = (long long)shfl64(base, 2 * k + 1);
+      const int qc_n = __popc(ge[k]);
+      if (lane == 0) {
+        const size_t item = (size_t)J.j * P.W + i0 + k;
+        P.nsnps[item] = bnd[2 * k + 1] - bnd[2 * k];
+        P.u[item] = u_cnt[k];
+        P.q[item] = qres[k];
+        P.q_cnt[item] = qc_n;
+        P.u_start[item] = ub;
+        P.q_start[item] = qb;
+      }
+      if (lane < u_cnt[k] && ub + lane < P.cap_u) J.uc[ub + lane] = SC.f.upos[k][lane];
+      if ((ge[k] >> lane) & 1u) {
+        const long long w = qb + __popc(ge[k] & lt_mask);
+        if (w < P.cap_q) J.qc[w] = SC.f.qpos[k][lane];
       }
     }
-    __syncwarp();  // the shared buffers are reused by the next window
+    __syncwarp();
+    // ---- windows that need the generic path ----
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      if (valid[k] && !fast[k]) window_generic(P, J, SC.s, i0 + k, bnd[2 * k], bnd[2 * k + 1], lane);
+    }
   }
 }
 
@@ -477,10 +713,29 @@ extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SAI_CUDA_CHECK(cudaMemsetAsync(d_totals, 0, sizeof(int64_t) * 2 * n_jobs, st));
   if (n_windows == 0) return SAI_OK;
-  const int64_t want = (n_windows + kWinWarps - 1) / kWinWarps;
+  static const int batch = [] {
+    const char* e = getenv("SAI_WIN_BATCH");  // tuning knob: windows per warp (1, 2 or 4)
+    const int b = e ? atoi(e) : 1;
+    return (b == 2 || b == 4) ? b : 1;
+  }();
+  const int64_t per_block = kWinWarps * batch;
+  const int64_t want = (n_windows + per_block - 1) / per_block;
   const int64_t cap = (int64_t)sm_count() * 32;
   const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_jobs);
-  k_window_stats<<<grid, kWinWarps * 32, 0, st>>>(P);
+  static const int minb = [] {
+    const char* e = getenv("SAI_WIN_MINB");
+    return e ? atoi(e) : 12;
+  }();
+  if (batch == 1 && minb == 10)
+    k_window_stats<1, 10><<<grid, kWinWarps * 32, 0, st>>>(P);
+  else if (batch == 1 && minb == 12)
+    k_window_stats<1, 12><<<grid, kWinWarps * 32, 0, st>>>(P);
+  else if (batch == 1)
+    k_window_stats<1, 8><<<grid, kWinWarps * 32, 0, st>>>(P);
+  else if (batch == 2)
+    k_window_stats<2, 6><<<grid, kWinWarps * 32, 0, st>>>(P);
+  else
+    k_window_stats<4, 4><<<grid, kWinWarps * 32, 0, st>>>(P);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }

@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""BASELINE.json configs 3-5 on the GPU (parity-test cases, not bench lines).
+
+    python tools/run_configs.py --config 3            # two sources, haploid + diploid, missing, both anc modes
+    python tools/run_configs.py --config 5            # threshold / window sweep on a 20k-sample cohort (cached counts)
+    torchrun --nproc-per-node N tools/run_configs.py --config 4   # 22 autosomes, 80 M sites, sharded by window range
+                                                                  # + genome-wide `sai outlier` thresholds
+
+Every run spot-checks GPU results against the CPU oracle on decoded slices of
+the device-generated data and prints one JSON summary line (rank 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import torch  # noqa: E402
+
+import sai_oracle as orc  # noqa: E402
+from sai_b200 import _cabi  # noqa: E402
+from sai_b200.encode import PackedGenotypes, make_layout, unpack_population  # noqa: E402
+from sai_b200.scoring import DeviceScorer, make_job, synth_fill  # noqa: E402
+from sai_b200.windows import split_genome, split_windows_ranges  # noqa: E402
+
+# hg19 autosome lengths (Mb, rounded) -- proportions for config 4
+HG19_MB = [249, 243, 198, 191, 181, 171, 159, 146, 141, 136, 135, 134, 115, 107, 103, 90, 81, 78, 59, 63, 48, 51]
+
+
+def positions(n_sites, mean_gap, seed):
+    rng = np.random.default_rng(seed)
+    return np.cumsum(rng.geometric(1.0 / mean_gap, size=n_sites).astype(np.int64)).astype(np.int32)
+
+
+def device_matrix(lay, n_sites, roles, seed, missing):
+    nbytes = int(_cabi.load().sai_packed_bytes(C.byref(lay), n_sites))
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    synth_fill(lay, d, n_sites, roles, seed, missing)
+    return d
+
+
+def decode_slice(lay, d_packed, pos, tile0, n_tiles):
+    pps = lay.pairs_per_site
+    sl = d_packed[tile0 * pps * 256 : (tile0 + n_tiles) * pps * 256].cpu().numpy()
+    sub_pos = pos[tile0 * 32 : (tile0 + n_tiles) * 32]
+    pg = PackedGenotypes(lay, len(sub_pos), sub_pos, sl)
+    return sub_pos, [unpack_population(pg, p).astype(np.int64) for p in range(lay.n_pops)]
+
+
+def check_windows(res, j, wins, sub_pos, mats, ploidy, src_idx, u_kw, q_kw, anc, max_checks=12):
+    """Oracle comparison for the windows that lie inside the decoded slice."""
+    n = 0
+    for i, (s, e) in enumerate(wins):
+        if s < sub_pos[0] or e > sub_pos[-1]:
+            continue
+        keep = (sub_pos >= s) & (sub_pos <= e)
+        args = (mats[0][keep], mats[1][keep], [mats[k][keep] for k in src_idx], ploidy[0], ploidy[1], [ploidy[k] for k in src_idx])
+        eu = orc.u_statistic(*args, pos=sub_pos[keep], anc_allele_available=anc, **u_kw)
+        eq = orc.q_statistic(*args, pos=sub_pos[keep], anc_allele_available=anc, **q_kw)
+        assert res.nsnps[j, i] == keep.sum(), (i, res.nsnps[j, i], keep.sum())
+        assert res.u[j, i] == eu["value"], (i, res.u[j, i], eu["value"])
+        assert np.array_equal(res.u_positions(j, i), eu["cdd_pos"]), i
+        if np.isnan(eq["value"]):
+            assert np.isnan(res.q[j, i]), i
+        else:
+            assert res.q[j, i] == float(eq["value"]), (i, res.q[j, i], float(eq["value"]))
+        assert np.array_equal(res.q_positions(j, i), np.asarray(eq["cdd_pos"], dtype=np.int32)), i
+        n += 1
+        if n >= max_checks:
+            break
+    return n
+
+
+def dev_windows(wins):
+    ws = torch.tensor([w[0] for w in wins], dtype=torch.int64, device="cuda")
+    we = torch.tensor([w[1] for w in wins], dtype=torch.int64, device="cuda")
+    return ws, we
+
+
+def timed(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+# --------------------------------------------------------------------------
+def config3(args):
+    """Two source populations with joint y thresholds, haploid and diploid, with missing genotypes."""
+    S = args.sites or 1_000_000
+    out = {"config": 3, "n_sites": S, "cases": []}
+    y_sets = [[("=", 1.0), ("=", 1.0)], [("=", 1.0), ("=", 0.0)], [("=", 0.0), ("=", 1.0)], [(">=", 0.5), ("<=", 0.5)]]
+    for ploidy, n_src in ((2, (2, 2)), (1, (1, 1))):
+        lay = make_layout([1500, 1000, n_src[0], n_src[1]], [ploidy] * 4, [2] * 4)
+        d_packed = device_matrix(lay, S, [0, 1, 2, 2], 20261018 + 3 + ploidy, 0.002)
+        pos = positions(S, 41.5, 3)
+        d_pos = torch.from_numpy(pos).cuda()
+        wins = split_genome([int(pos[0]), int(pos[-1])], 50_000, 10_000)
+        d_ws, d_we = dev_windows(wins)
+        sub_pos, mats = decode_slice(lay, d_packed, pos, 5000, 192)
+        for anc in (True, False):
+            jobs, kws = [], []
+            for ys in y_sets:
+                u_kw = dict(w=0.05, x=0.2, y_list=ys)
+                q_kw = dict(w=0.05, quantile=0.95, y_list=ys)
+                jobs.append(make_job(0, 1, [2, 3], anc, u=u_kw, q=q_kw))
+                kws.append((u_kw, q_kw))
+            sc = DeviceScorer(lay, S, len(wins), len(jobs), cap_u=1 << 20, cap_q=1 << 20)
+            ms = timed(lambda: sc.step(d_packed, d_pos, d_ws, d_we, jobs))
+            res = sc.results()
+            checked = sum(check_windows(res, j, wins, sub_pos, mats, [ploidy] * 4, [2, 3], *kws[j], anc) for j in range(len(jobs)))
+            out["cases"].append(dict(ploidy=ploidy, anc=anc, jobs=len(jobs), ms_per_pass=ms, windows=len(wins),
+                                     u_sum=[int(x) for x in res.u.sum(1)], q_windows=[int(np.isfinite(r).sum()) for r in res.q],
+                                     oracle_windows_checked=checked))
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------
+def config5(args):
+    """Threshold / window sweep on a 20 000-sample cohort: one genotype pass caches (num, called); every parameter
+    set re-derives the site masks from the cache."""
+    S = args.sites or 1_000_000
+    n_ind = [12_000, 7_996, 4]
+    lay = make_layout(n_ind, [2, 2, 2], [2, 2, 2])
+    d_packed = device_matrix(lay, S, [0, 1, 2], 20261018 + 5, 0.0)
+    pos = positions(S, 41.5, 5)
+    d_pos = torch.from_numpy(pos).cuda()
+    grid_w, grid_x, grid_y = [0.01, 0.05, 0.1, 0.2, 0.5], [0.0, 0.01], [0.5, 1.0]
+    grid_win = [(L, st) for L in (10_000, 50_000, 100_000) for st in (5_000, 10_000, 50_000) if st <= L]
+    max_w = max(len(split_genome([int(pos[0]), int(pos[-1])], L, st)) for L, st in grid_win)
+    sc = DeviceScorer(lay, S, max_w, 1, cap_u=1 << 22, cap_q=1 << 23)
+    t_counts = timed(lambda: sc.site_counts(d_packed), reps=3)
+    packed_bytes = d_packed.numel()
+    alg = S * (sum(n_ind) * 2 / 8 + 4)
+    sub_pos, mats = decode_slice(lay, d_packed, pos, 9000, 128)
+    n_sets, t_flags, t_win, checked = 0, 0.0, 0.0, 0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    u_total = 0
+    for (L, st) in grid_win:
+        wins = split_genome([int(pos[0]), int(pos[-1])], L, st)
+        d_ws, d_we = dev_windows(wins)
+        sc.W = len(wins)
+        for w in grid_w:
+            for x in grid_x:
+                for y in grid_y:
+                    u_kw = dict(w=w, x=x, y_list=[("=", y)])
+                    q_kw = dict(w=w, quantile=0.95, y_list=[("=", y)])
+                    job = make_job(0, 1, [2], True, u=u_kw, q=q_kw)
+                    ev[0].record()
+                    sc.flags_from_counts([job])
+                    ev[1].record()
+                    sc.window_stats(d_pos, d_ws, d_we, [job])
+                    ev[2].record()
+                    torch.cuda.synchronize()
+                    t_flags += ev[0].elapsed_time(ev[1])
+                    t_win += ev[1].elapsed_time(ev[2])
+                    n_sets += 1
+                    if n_sets % 9 == 1:
+                        res = sc.results()
+                        # results arrays are allocated for max_w windows; only the first len(wins) are live
+                        checked += check_windows(res, 0, wins, sub_pos, mats, [2, 2, 2], [2], u_kw, q_kw, True, max_checks=4)
+                        u_total += int(res.u[0, : len(wins)].sum())
+    print(json.dumps(dict(config=5, n_sites=S, n_samples=sum(n_ind), parameter_sets=n_sets,
+                          genotype_pass_ms=t_counts, genotype_pass_gbps_algorithmic=alg / t_counts / 1e6,
+                          genotype_pass_gbps_packed=packed_bytes / t_counts / 1e6,
+                          flags_from_counts_ms_per_set=t_flags / n_sets, window_stats_ms_per_set=t_win / n_sets,
+                          oracle_windows_checked=checked, u_total_checked_sets=u_total)))
+
+
+# --------------------------------------------------------------------------
+def config4(args):
+    """Whole genome: 22 autosomes (80 M sites by default) sharded by contiguous window ranges over the ranks, then
+    the genome-wide outlier thresholds with one all-gather per column."""
+    import torch.distributed as dist
+
+    from sai_b200.outlier import distributed_threshold, outlier_mask, threshold_from_values
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    total = args.sites or 80_000_000
+    n_ind = [1500, 1000, 4]
+    lay = make_layout(n_ind, [2, 2, 2], [2, 2, 2])
+    chrom_sites = [int(total * mb / sum(HG19_MB)) // 32 * 32 for mb in HG19_MB]
+    L, st = 50_000, 10_000
+    # the flattened (chromosome, window) list, split like _split_windows_ranges
+    chrom_pos = [positions(n, mb * 1e6 / n, 100 + c) for c, (n, mb) in enumerate(zip(chrom_sites, HG19_MB))]
+    chrom_wins = [split_genome([int(p[0]), int(p[-1])], L, st) for p in chrom_pos]
+    flat = [(c, w) for c, wins in enumerate(chrom_wins) for w in wins]
+    base, extra = divmod(len(flat), world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    mine = flat[lo:hi]
+    u_kw = dict(w=0.01, x=0.5, y_list=[("=", 1.0)])
+    q_kw = dict(w=0.01, quantile=0.95, y_list=[("=", 1.0)])
+    job = make_job(0, 1, [2], True, u=u_kw, q=q_kw)
+
+    # per chromosome piece of this rank: the sites of [first.start, last.end]
+    pieces = []
+    for c in sorted({c for c, _ in mine}):
+        wins = [w for cc, w in mine if cc == c]
+        pos = chrom_pos[c]
+        s_lo = int(np.searchsorted(pos, wins[0][0], "left")) // 32 * 32  # tile aligned: the generator is tile-addressed
+        s_hi = int(np.searchsorted(pos, wins[-1][1], "right"))
+        pieces.append((c, wins, s_lo, s_hi))
+    # generate every piece on the device (untimed), then time the scoring of all pieces
+    data = []
+    for c, wins, s_lo, s_hi in pieces:
+        n = s_hi - s_lo
+        nbytes = int(_cabi.load().sai_packed_bytes(C.byref(lay), n))
+        d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        # tile0 offsets the generator so that a site has the same genotypes whichever rank holds it
+        role = (C.c_int32 * 3)(0, 1, 2)
+        _cabi.check(_cabi.load().sai_synth_fill(C.byref(lay), d.data_ptr() - (s_lo // 32) * lay.pairs_per_site * 256,
+                                                s_lo // 32, (n + 31) // 32, chrom_sites[c], role, 777 + c, 0.0,
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        d_pos = torch.from_numpy(chrom_pos[c][s_lo:s_hi].copy()).cuda()
+        d_ws, d_we = dev_windows(wins)
+        sc = DeviceScorer(lay, n, len(wins), 1, cap_u=max(8 * len(wins), 1 << 16), cap_q=max(32 * len(wins), 1 << 18))
+        data.append((c, wins, d, d_pos, d_ws, d_we, sc, s_lo))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(2):  # first pass warms up
+        a.record()
+        for c, wins, d, d_pos, d_ws, d_we, sc, s_lo in data:
+            sc.step(d, d_pos, d_ws, d_we, [job])
+        b.record()
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    results = [(c, wins, sc.results()) for c, wins, d, d_pos, d_ws, d_we, sc, s_lo in data]
+    u_local = np.concatenate([r.u[0] for _, _, r in results]).astype(np.float64) if results else np.array([])
+    q_local = np.concatenate([r.q[0] for _, _, r in results]) if results else np.array([])
+    t0 = time.perf_counter()
+    thr_u = distributed_threshold(u_local, 0.99, "U")
+    thr_q = distributed_threshold(q_local, 0.99, "Q")
+    t_thr = time.perf_counter() - t0
+    n_out_u = int(outlier_mask(u_local, thr_u, "U").sum())
+    n_out_q = int(outlier_mask(q_local, thr_q, "Q").sum())
+    # oracle spot check on this rank's first piece
+    c, wins, d, d_pos, d_ws, d_we, sc, s_lo = data[0]
+    sub_pos, mats = decode_slice(lay, d, chrom_pos[c][s_lo:], 64, 128)
+    checked = check_windows(results[0][2], 0, wins, sub_pos, mats, [2, 2, 2], [2], u_kw, q_kw, True, max_checks=6)
+    gathered = [None] * world
+    summary = dict(rank=rank, windows=len(mine), sites=int(sum(dd[3].numel() for dd in data)),
+                   ms=ms, u_sum=float(u_local.sum()), q_windows=int(np.isfinite(q_local).sum()), outliers_u=n_out_u,
+                   outliers_q=n_out_q, oracle_windows_checked=checked,
+                   u_values=u_local.tolist() if args.dump else None, q_values=q_local.tolist() if args.dump else None)
+    if world > 1:
+        dist.all_gather_object(gathered, summary)
+    else:
+        gathered = [summary]
+    if rank == 0:
+        tot_w = sum(g["windows"] for g in gathered)
+        print(json.dumps(dict(config=4, n_gpus=world, total_sites=int(sum(chrom_sites)), total_windows=tot_w,
+                              max_rank_ms=float(t.item()), windows_per_s=tot_w / (float(t.item()) / 1e3),
+                              threshold_u_q99=thr_u, threshold_q_q99=thr_q, threshold_allgather_s=t_thr,
+                              outliers_u=sum(g["outliers_u"] for g in gathered), outliers_q=sum(g["outliers_q"] for g in gathered),
+                              u_sum=sum(g["u_sum"] for g in gathered), q_windows=sum(g["q_windows"] for g in gathered),
+                              per_rank=[{k: g[k] for k in ("rank", "windows", "sites", "ms", "oracle_windows_checked")} for g in gathered])))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, required=True, choices=[3, 4, 5])
+    ap.add_argument("--sites", type=int, default=None)
+    ap.add_argument("--dump", action="store_true")
+    a = ap.parse_args()
+    {3: config3, 4: config4, 5: config5}[a.config](a)
