@@ -138,6 +138,23 @@ int sai_unpack_i8(const sai_layout* lay, int32_t pop, const uint8_t* packed,
                   int64_t n_sites_total, int64_t site0, int64_t n, int8_t* gt,
                   int64_t row_stride);
 
+/* ---- host VCF ingest (replaces read_geno_data + check_anc_allele + flip_snps +
+ * reshape_genotypes(is_phased=False), sai/utils/utils.py:78-186, 492-555, 405-410) */
+/* One pass over VCF text (complete lines are consumed; *bytes_consumed tells
+ * where the next call has to start).  For every record of `chrom` with
+ * start <= POS <= end (no region filter when start > end) that survives the
+ * ancestral-allele table (n_anc == 0: no table; entries: sorted anc_pos[i] with
+ * the allele in anc_allele + 8*i, NUL padded) writes out_pos[row] and, for every
+ * requested output column o, out_gt[row*row_stride + o] = sum of the first
+ * sample_ploidy[o] alleles of VCF sample column sample_column[o] ("." and
+ * absent alleles = -1; flipped records: every allele a -> |a - 1|).
+ * Returns the number of rows written (<= rows_cap) or a negative SAI_E_* code. */
+int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* chrom, int64_t start,
+                         int64_t end, const int32_t* sample_column, const int32_t* sample_ploidy,
+                         int32_t n_out, const int32_t* anc_pos, const char* anc_allele,
+                         int64_t n_anc, int32_t* out_pos, int8_t* out_gt, int64_t row_stride,
+                         int64_t rows_cap, int64_t* bytes_consumed, int32_t n_threads);
+
 /* ---- K1: site counts (replaces calc_freq's passes, stat_utils.py:45-49) --- */
 /* For tiles [tile0, tile0+n_tiles): per population p and site s
  *     num[p*stride + s]    = sum of called values      (stat_utils.py:48)

@@ -154,34 +154,49 @@ int sai_pack_i8(const sai_layout* lay, int32_t pop, const int8_t* gt, int64_t n_
   n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n_tiles));
   std::atomic<int> domain_err{0};
 
+  // 8 individuals per 64-bit word: sign bit -> missing code, (code >> b) & 1 gathered
+  // with a multiply ("movemask") into 8 plane bits.
+  auto pack32 = [&](const int8_t* v, uint32_t* plane) -> bool {
+    bool bad = false;
+    const uint64_t ones = 0x0101010101010101ull;
+    for (int b = 0; b < B; ++b) plane[b] = 0;
+    for (int q = 0; q < 4; ++q) {
+      uint64_t x;
+      memcpy(&x, v + 8 * q, 8);
+      const uint64_t negm = ((x >> 7) & ones) * 0xffull;  // 0xff in every negative byte
+      const uint64_t val = x & ~negm;
+      // a called value must be < miss_code: byte + (128 - miss_code) sets bit 7 otherwise
+      bad |= (((val + ones * (uint64_t)(128 - miss_code)) | val) & (ones << 7)) != 0;
+      const uint64_t code = val | (negm & (ones * (uint64_t)miss_code));
+      for (int b = 0; b < B; ++b)
+        plane[b] |= (uint32_t)((((code >> b) & ones) * 0x0102040810204080ull) >> 56) << (8 * q);
+    }
+    return bad;
+  };
   auto work = [&](int64_t t0, int64_t t1) {
+    int8_t tail[32];
+    bool bad = false;
     for (int64_t T = t0; T < t1; ++T) {
       for (int s = 0; s < kTile; ++s) {
         const int64_t site = T * kTile + s;
         const int8_t* row = site < n_sites ? gt + site * row_stride : nullptr;
         for (int g = 0; g < L.n_groups; ++g) {
-          uint32_t plane[4] = {0, 0, 0, 0};
+          uint32_t plane[4];
           const int i0 = g * 32;
-          const int cnt = std::min(32, L.n_samples - i0);
-          for (int i = 0; i < 32; ++i) {
-            int code = miss_code;
-            if (row && i < cnt) {
-              int v = row[i0 + i];
-              if (v >= 0) {
-                if (v >= miss_code) {
-                  domain_err.store(1, std::memory_order_relaxed);
-                  v = miss_code;
-                }
-                code = v;
-              }
-            }
-            for (int b = 0; b < B; ++b) plane[b] |= (uint32_t)((code >> b) & 1) << i;
+          const int cnt = row ? std::min(32, L.n_samples - i0) : 0;
+          if (cnt == 32) {
+            bad |= pack32(row + i0, plane);
+          } else {
+            memset(tail, 0xff, sizeof(tail));  // -1: missing
+            if (cnt > 0) memcpy(tail, row + i0, cnt);
+            bad |= pack32(tail, plane);
           }
           for (int b = 0; b < B; ++b) *word_ptr(lay, L, packed, T, s, g * B + b) = plane[b];
         }
         if ((L.n_groups * B) & 1) *word_ptr(lay, L, packed, T, s, L.n_groups * B) = 0u;
       }
     }
+    if (bad) domain_err.store(1, std::memory_order_relaxed);
   };
   if (n_threads == 1) {
     work(0, n_tiles);

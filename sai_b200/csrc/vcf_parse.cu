@@ -1,0 +1,222 @@
+// Host-side VCF genotype parser (N2: ingest).  No device code in this file.
+//
+// Replaces, for the scoring path, the per-population `allel.read_vcf(...,
+// numbers={"GT": ploidy}, region=...)` calls of read_geno_data
+// (sai/utils/utils.py:78-186), the ancestral-allele filter / flip of
+// check_anc_allele + flip_snps (utils.py:492-555) and the allele sum of
+// reshape_genotypes(is_phased=False) (utils.py:405-410) by ONE pass over the
+// VCF text that writes, per kept record, the position and one int8 allele sum
+// per requested (sample column, ploidy) pair:
+//   * GT is cut or padded with missing (-1) to `ploidy` alleles, "." = -1;
+//   * without an ancestral-allele table every record of the region is kept;
+//     with one, records whose position is not in the table or whose ancestral
+//     allele is neither REF nor the first ALT are dropped, and where it equals
+//     ALT every allele a becomes |a - 1| (so a missing allele becomes 2);
+//   * the value written is the sum of the (possibly flipped) alleles.
+#include <string.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sai {
+
+struct KeptLine {
+  const char* samples;  // first character after the FORMAT column
+  int32_t gt_index;     // position of GT among the ':'-separated FORMAT keys
+  int32_t pos;
+  bool flip;
+};
+
+static inline const char* next_tab(const char* p, const char* end) {
+  const void* t = memchr(p, '\t', (size_t)(end - p));
+  return t ? static_cast<const char*>(t) : end;
+}
+
+// Parses the GT of the sample field starting at f (field ends at a tab or at
+// lend) into the allele sum (see file header); returns the end of the field.
+static inline const char* gt_sum(const char* f, const char* lend, int gt_index, int ploidy,
+                                 bool flip, int8_t* out) {
+  const char* p = f;
+  // skip to the GT sub-field
+  for (int k = 0; k < gt_index; ++k) {
+    while (p < lend && *p != ':' && *p != '\t') ++p;
+    if (p < lend && *p == ':') ++p;
+  }
+  int sum = 0, n = 0;
+  bool open = p < lend && *p != '\t' && *p != ':';  // still inside the GT sub-field
+  while (n < ploidy) {
+    int a = -1;
+    if (open) {
+      int v = 0;
+      bool digits = false, junk = false;
+      while (p < lend) {
+        const char c = *p;
+        if (c == '/' || c == '|' || c == ':' || c == '\t') break;
+        if (c >= '0' && c <= '9' && !junk) {
+          v = v * 10 + (c - '0');
+          digits = true;
+        } else {
+          junk = true;  // "." or anything else: missing
+        }
+        ++p;
+      }
+      if (digits && !junk) a = v;
+      if (p < lend && (*p == '/' || *p == '|'))
+        ++p;  // next allele token (possibly empty)
+      else
+        open = false;
+    }
+    if (flip) a = a > 0 ? a - 1 : 1 - a;  // |a - 1|
+    sum += a;
+    ++n;
+  }
+  *out = (int8_t)(sum < -128 ? -128 : (sum > 127 ? 127 : sum));
+  while (p < lend && *p != '\t') ++p;
+  return p;
+}
+
+}  // namespace sai
+
+using namespace sai;
+
+extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* chrom, int64_t start,
+                                    int64_t end, const int32_t* sample_column,
+                                    const int32_t* sample_ploidy, int32_t n_out,
+                                    const int32_t* anc_pos, const char* anc_allele, int64_t n_anc,
+                                    int32_t* out_pos, int8_t* out_gt, int64_t row_stride,
+                                    int64_t rows_cap, int64_t* bytes_consumed, int32_t n_threads) {
+  if (!text || len < 0 || !chrom || !sample_column || !sample_ploidy || n_out < 1 || !out_pos ||
+      !out_gt || row_stride < n_out || rows_cap < 0 || !bytes_consumed || (n_anc > 0 && (!anc_pos || !anc_allele))) {
+    set_error("sai_vcf_parse_gt: bad argument");
+    return SAI_E_ARG;
+  }
+  const size_t chrom_len = strlen(chrom);
+  const bool region = start <= end;
+  const char* const tend = text + len;
+  std::vector<KeptLine> kept;
+  // columns sorted so that every line is walked once, left to right
+  std::vector<int> order(n_out);
+  for (int i = 0; i < n_out; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return sample_column[a] < sample_column[b]; });
+  for (int i = 0; i < n_out; ++i)
+    if (sample_column[i] < 0 || sample_ploidy[i] < 1 || sample_ploidy[i] > 16) {
+      set_error("sai_vcf_parse_gt: bad sample column / ploidy");
+      return SAI_E_ARG;
+    }
+
+  // ---- pass 1 (serial, cheap): complete lines, record filter, flip decision ----
+  const char* p = text;
+  while (p < tend && (int64_t)kept.size() < rows_cap) {
+    const void* nl = memchr(p, '\n', (size_t)(tend - p));
+    if (!nl) break;  // incomplete last line: left for the next call
+    const char* lend = static_cast<const char*>(nl);
+    const char* line = p;
+    p = lend + 1;
+    if (lend > line && lend[-1] == '\r') --lend;
+    if (line == lend || *line == '#') continue;
+    const char* t0 = next_tab(line, lend);  // CHROM
+    if ((size_t)(t0 - line) != chrom_len || memcmp(line, chrom, chrom_len) != 0) continue;
+    const char* f = t0 + 1;
+    const char* t1 = next_tab(f, lend);  // POS
+    int64_t pos = 0;
+    for (const char* q = f; q < t1; ++q) pos = pos * 10 + (*q - '0');
+    if (region && (pos < start || pos > end)) continue;
+    const char* t2 = next_tab(t1 + 1, lend);  // ID
+    const char* ref = t2 + 1;
+    const char* t3 = next_tab(ref, lend);  // REF
+    const char* alt = t3 + 1;
+    const char* t4 = next_tab(alt, lend);  // ALT
+    const void* comma = memchr(alt, ',', (size_t)(t4 - alt));
+    const char* alt_end = comma ? static_cast<const char*>(comma) : t4;  // alt_number=1: first ALT
+    bool flip = false;
+    if (n_anc > 0) {
+      const int32_t* it = std::lower_bound(anc_pos, anc_pos + n_anc, (int32_t)pos);
+      if (it == anc_pos + n_anc || *it != (int32_t)pos) continue;  // no ancestral allele: dropped
+      const char* a = anc_allele + 8 * (it - anc_pos);
+      const size_t alen = strnlen(a, 8);
+      const bool is_ref = (size_t)(t3 - ref) == alen && memcmp(a, ref, alen) == 0;
+      const bool is_alt = (size_t)(alt_end - alt) == alen && memcmp(a, alt, alen) == 0;
+      if (!is_ref && !is_alt) continue;
+      flip = is_alt;  // utils.py:523-524
+    }
+    const char* t5 = next_tab(t4 + 1, lend);   // QUAL
+    const char* t6 = next_tab(t5 + 1, lend);   // FILTER
+    const char* t7 = next_tab(t6 + 1, lend);   // INFO
+    const char* fmt = t7 + 1;
+    const char* t8 = next_tab(fmt, lend);      // FORMAT
+    int gi = 0;
+    {
+      int k = 0;
+      const char* q = fmt;
+      bool found = false;
+      while (q < t8) {
+        const void* c = memchr(q, ':', (size_t)(t8 - q));
+        const char* ke = c ? static_cast<const char*>(c) : t8;
+        if (ke - q == 2 && q[0] == 'G' && q[1] == 'T') {
+          gi = k;
+          found = true;
+          break;
+        }
+        q = ke + 1;
+        ++k;
+      }
+      if (!found) gi = 0;
+    }
+    if (t8 >= lend) continue;  // no sample columns
+    kept.push_back(KeptLine{t8 + 1, gi, (int32_t)pos, flip});
+    (void)lend;
+  }
+  *bytes_consumed = (int64_t)(p - text);
+  const int64_t n_rows = (int64_t)kept.size();
+  if (n_rows == 0) return 0;
+
+  // ---- pass 2 (parallel over records): walk the sample columns ----
+  auto work = [&](int64_t r0, int64_t r1) {
+    for (int64_t r = r0; r < r1; ++r) {
+      const KeptLine& K = kept[r];
+      out_pos[r] = K.pos;
+      int8_t* row = out_gt + r * row_stride;
+      const void* nl = memchr(K.samples, '\n', (size_t)(tend - K.samples));
+      const char* lend = nl ? static_cast<const char*>(nl) : tend;
+      if (lend > K.samples && lend[-1] == '\r') --lend;
+      const char* f = K.samples;  // start of sample column `col`
+      int col = 0;
+      bool have = f < lend;  // a field exists at f
+      for (int oi = 0; oi < n_out; ++oi) {
+        const int o = order[oi];
+        const int want = sample_column[o];
+        while (col < want && have) {
+          while (f < lend && *f != '\t') ++f;
+          if (f < lend) {
+            ++f;
+            ++col;
+          } else {
+            have = false;
+          }
+        }
+        if (col != want || !have) {
+          row[o] = (int8_t)(-sample_ploidy[o]);  // column absent: all alleles missing
+          continue;
+        }
+        gt_sum(f, lend, K.gt_index, sample_ploidy[o], K.flip, &row[o]);  // f stays: a column may be requested twice
+      }
+    }
+  };
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<int64_t>(n_threads, n_rows);
+  if (n_threads <= 1) {
+    work(0, n_rows);
+  } else {
+    std::vector<std::thread> th;
+    const int64_t per = (n_rows + n_threads - 1) / n_threads;
+    for (int i = 0; i < n_threads; ++i) {
+      const int64_t a = i * per, b = std::min(n_rows, a + per);
+      if (a < b) th.emplace_back(work, a, b);
+    }
+    for (auto& t : th) t.join();
+  }
+  return n_rows;
+}

@@ -212,6 +212,92 @@ def load_population_group(
     return data, samples
 
 
+def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chunk_bytes=64 << 20):
+    """One pass of the native parser (``sai_vcf_parse_gt``) over the file.
+    ``requests`` = list of (sample_name, ploidy); returns ``(pos, gt)`` with one
+    int8 column per request, or ``None`` for the sample names line missing."""
+    import ctypes as C
+
+    from . import _cabi
+
+    lib = _cabi.load()
+    anc_pos = anc_buf = None
+    n_anc = 0
+    if anc is not None:
+        keys = sorted(anc)
+        if any(len(anc[k].encode()) > 7 for k in keys):
+            return None  # long alleles: use the Python reader
+        anc_pos = np.ascontiguousarray(keys, dtype=np.int32)
+        anc_buf = b"".join(anc[k].encode().ljust(8, b"\0") for k in keys)
+        n_anc = len(keys)
+    pos_parts, gt_parts = [], []
+    cols = ploidies = None
+    n_out = len(requests)
+    consumed = C.c_int64(0)
+    region = (start, end) if (start is not None and end is not None) else (1, 0)
+    opener = gzip.open if _is_gzip(vcf_file) else open
+    with opener(vcf_file, "rb") as f:
+        carry = b""
+        while True:
+            block = f.read(chunk_bytes)
+            data = carry + block
+            if not data:
+                break
+            if cols is None:
+                # header: find the #CHROM line to map sample names to columns
+                h = data.find(b"#CHROM")
+                if h < 0:
+                    if not block:
+                        break
+                    carry = data
+                    continue
+                he = data.find(b"\n", h)
+                if he < 0:
+                    if not block:
+                        break
+                    carry = data
+                    continue
+                names = data[h:he].decode().rstrip("\r").split("\t")[9:]
+                index = {n: i for i, n in enumerate(names)}
+                cols = np.ascontiguousarray([index[s] for s, _ in requests], dtype=np.int32)  # KeyError like list.index
+                ploidies = np.ascontiguousarray([p for _, p in requests], dtype=np.int32)
+                data = data[he + 1 :]
+            if not block and not data.endswith(b"\n"):
+                data += b"\n"  # last line without a newline
+            at = 0
+            while at < len(data):
+                cap = max(1024, min(1 << 20, (len(data) - at) // max(64, 2 * n_out) + 16))
+                out_pos = np.empty(cap, dtype=np.int32)
+                out_gt = np.empty((cap, n_out), dtype=np.int8)
+                n = lib.sai_vcf_parse_gt(
+                    C.c_char_p(data[at:]) if at else C.c_char_p(data), len(data) - at, chr_name.encode(), region[0], region[1],
+                    cols.ctypes.data, ploidies.ctypes.data, n_out,
+                    anc_pos.ctypes.data if n_anc else None, anc_buf if n_anc else None, n_anc,
+                    out_pos.ctypes.data, out_gt.ctypes.data, n_out, cap, C.byref(consumed), n_threads,
+                )
+                if n < 0:
+                    _cabi.check(int(n))
+                if n:
+                    pos_parts.append(out_pos[:n].copy())
+                    gt_parts.append(out_gt[:n].copy())
+                if consumed.value == 0:
+                    break
+                at += consumed.value
+            carry = data[at:]
+            if not block:
+                break
+    if cols is None:
+        return None
+    if not pos_parts:
+        return np.empty(0, dtype=np.int32), np.empty((0, n_out), dtype=np.int8)
+    return np.concatenate(pos_parts), np.concatenate(gt_parts)
+
+
+def _is_gzip(path: str) -> bool:
+    with open(path, "rb") as f:
+        return f.read(2) == b"\x1f\x8b"
+
+
 def read_data(
     vcf_file: str,
     chr_name: str,
@@ -223,17 +309,68 @@ def read_data(
     anc_allele_file: Optional[str],
     start: Optional[int] = None,
     end: Optional[int] = None,
+    native: bool = True,
 ):
     """``{"ref": (data, samples), "tgt": ..., "src": ..., "outgroup": ...}``
-    (sai/utils/utils.py:215-356 with the WindowGenerator's fixed flags)."""
-    region = VcfRegion(vcf_file, chr_name, start, end)
+    (sai/utils/utils.py:215-356 with the WindowGenerator's fixed flags:
+    ``is_phased=False``, no fixed-variant / missing filters).  ``native=True``
+    parses the file once for all populations with ``sai_vcf_parse_gt``;
+    ``native=False`` is the pure-Python reader kept as a cross-check."""
     anc = None
     if anc_allele_file:
         anc = read_anc_allele(anc_allele_file, chr_name, start, end)
-    out = {}
-    for group, ind_file in (("ref", ref_ind_file), ("tgt", tgt_ind_file), ("src", src_ind_file), ("outgroup", out_ind_file)):
+    groups = (("ref", ref_ind_file), ("tgt", tgt_ind_file), ("src", src_ind_file), ("outgroup", out_ind_file))
+    if not native:
+        region = VcfRegion(vcf_file, chr_name, start, end)
+        out = {}
+        for group, ind_file in groups:
+            if ind_file is None or (group == "outgroup" and group not in ploidy_config.root):
+                out[group] = (None, None)
+                continue
+            out[group] = load_population_group(region, ind_file, group, ploidy_config, anc)
+        return out
+
+    # plan: one output column per (population, sample) with the population's ploidy
+    plan, requests, out = [], [], {}
+    for group, ind_file in groups:
         if ind_file is None or (group == "outgroup" and group not in ploidy_config.root):
             out[group] = (None, None)
             continue
-        out[group] = load_population_group(region, ind_file, group, ploidy_config, anc)
+        samples = parse_ind_file(ind_file)
+        if group not in ploidy_config.root:
+            raise ValueError(f"Ploidy configuration missing group '{group}'.")
+        ploidies = ploidy_config.root[group]
+        for population in ploidies:
+            if population not in samples:
+                raise ValueError(
+                    f"Population '{population}' in ploidy_config[{group}] not found in sample file: {ind_file}"
+                )
+        pops = []
+        for population, names in samples.items():
+            if population not in ploidies:
+                warnings.warn(
+                    f"Population '{population}' found in sample file but not in ploidy_config[{group}]; skipping.",
+                    RuntimeWarning,
+                )
+                continue
+            a = len(requests)
+            requests += [(n, ploidies[population]) for n in names]
+            pops.append((population, a, len(requests)))
+        plan.append((group, samples, pops))
+    if not requests:
+        return out
+    try:
+        parsed = _native_read(vcf_file, chr_name, start, end, requests, anc)
+    except (KeyError, OSError) as e:
+        region = chr_name if start is None and end is None else f"{chr_name}:{start}-{end}"
+        raise ValueError(f"Failed to read VCF file {vcf_file} from {region}: {e}") from e
+    if parsed is None:
+        return read_data(vcf_file, chr_name, ploidy_config, ref_ind_file, tgt_ind_file, src_ind_file, out_ind_file,
+                         anc_allele_file, start, end, native=False)
+    pos, gt = parsed
+    for group, samples, pops in plan:
+        if pos.size == 0 or not pops:
+            out[group] = (None, samples)
+            continue
+        out[group] = ({p: PopData(pos.copy(), np.ascontiguousarray(gt[:, a:b])) for p, a, b in pops}, samples)
     return out

@@ -186,3 +186,68 @@ def test_vcf_ingest_semantics(tmp_path):
     assert d["ref"][0]["R"].GT[:, 0].tolist() == [1, 2]  # pos 20 flipped: alleles (1,-1) -> (0,2)
     assert d["src"][0]["S"].GT[:, 0].tolist() == [-2, 2]  # flipped haploid "1": (1,-1) -> (0, 2)
     assert read_data(str(vcf), "3", pc, *lists, None, None)["ref"][0] is None
+
+
+def _random_vcf(path, rng, n_sites, n_samples, crlf=False, final_newline=True):
+    lines = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n_samples))]
+    pos = np.sort(rng.choice(np.arange(1, 50 * n_sites), size=n_sites, replace=False))
+    bases = "ACGT"
+    recs = []
+    for p in pos:
+        chrom = "7" if rng.random() < 0.85 else "77"  # "77" must not match chromosome "7"
+        ref = bases[rng.integers(4)]
+        alt = bases[(bases.index(ref) + 1 + rng.integers(3)) % 4] + (",<DEL>" if rng.random() < 0.1 else "")
+        fmt = rng.choice(["GT", "GT:DP", "DP:GT:GQ"])
+        fields = []
+        for _ in range(n_samples):
+            pl = int(rng.choice([1, 2, 2, 2, 4]))
+            alleles = [("." if rng.random() < 0.08 else str(int(rng.integers(0, 3 if rng.random() < 0.05 else 2)))) for _ in range(pl)]
+            gt = alleles[0]
+            for a in alleles[1:]:
+                gt += ("|" if rng.random() < 0.5 else "/") + a
+            fields.append({"GT": gt, "GT:DP": gt + ":12", "DP:GT:GQ": "7:" + gt + ":30"}[fmt])
+        lines.append("\t".join([chrom, str(p), ".", ref, alt, ".", "PASS", "AA=x", fmt] + fields))
+        recs.append((chrom, int(p), ref, alt.split(",")[0]))
+    text = ("\r\n" if crlf else "\n").join(lines) + (("\r\n" if crlf else "\n") if final_newline else "")
+    open(path, "w", newline="").write(text)
+    return recs
+
+
+@pytest.mark.parametrize("crlf, final_newline", [(False, True), (True, True), (False, False)])
+def test_native_vcf_reader_matches_python_reader(tmp_path, crlf, final_newline):
+    """sai_vcf_parse_gt (one native pass for all populations) == the pure-Python
+    reader, with and without an ancestral-allele table and a region."""
+    from sai_b200.configs import PloidyConfig
+    from sai_b200.vcf import read_data
+
+    rng = np.random.default_rng(17)
+    vcf = tmp_path / "r.vcf"
+    recs = _random_vcf(vcf, rng, 400, 23, crlf, final_newline)
+    (tmp_path / "ref.list").write_text("".join(f"R1\ts{i}\n" for i in range(0, 9)) + "".join(f"R2\ts{i}\n" for i in range(5, 12)))
+    (tmp_path / "tgt.list").write_text("".join(f"T\ts{i}\n" for i in range(12, 20)))
+    (tmp_path / "src.list").write_text("S1\ts20\nS1\ts21\nS2\ts22\n")
+    anc = tmp_path / "anc.bed"
+    with open(anc, "w") as f:
+        for chrom, p, ref, alt in recs:
+            r = rng.random()
+            if r < 0.1:
+                continue  # no ancestral allele: record dropped
+            allele = ref if r < 0.5 else (alt if r < 0.9 else "N")
+            f.write(f"{chrom}\t{p - 1}\t{p}\t{allele}\n")
+    pc = PloidyConfig({"ref": {"R1": 2, "R2": 4}, "tgt": {"T": 2}, "src": {"S1": 1, "S2": 3}})
+    lists = [str(tmp_path / f"{g}.list") for g in ("ref", "tgt", "src")]
+    for anc_file in (None, str(anc)):
+        for region in ((None, None), (recs[40][1], recs[300][1])):
+            a = read_data(str(vcf), "7", pc, *lists, None, anc_file, start=region[0], end=region[1], native=True)
+            b = read_data(str(vcf), "7", pc, *lists, None, anc_file, start=region[0], end=region[1], native=False)
+            n_rows = None
+            for g in ("ref", "tgt", "src"):
+                assert list(a[g][0]) == list(b[g][0]) and a[g][1] == b[g][1]
+                for p in a[g][0]:
+                    assert np.array_equal(a[g][0][p].POS, b[g][0][p].POS), (g, p)
+                    assert np.array_equal(a[g][0][p].GT, b[g][0][p].GT), (g, p)
+                    n_rows = a[g][0][p].POS.size
+            assert n_rows and n_rows > 20
+    with pytest.raises(ValueError, match="Failed to read VCF"):
+        (tmp_path / "bad.list").write_text("R1\tnobody\nR2\ts1\n")
+        read_data(str(vcf), "7", pc, str(tmp_path / "bad.list"), lists[1], lists[2], None, None)
