@@ -212,6 +212,23 @@ int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win
                      int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand, int64_t cap_u,
                      int32_t* d_q_cand, int64_t cap_q, void* stream);
 
+/* ---- N3: site-pattern sums for Danc / Dplus / df / fd ------------------------ */
+/* From the cached counts of sai_site_counts: for every source population k and
+ * window i the seven sums d_sums[(k*W + i)*7 + t], t = abba, baba, baaa, abaa,
+ * bbaa, abba_d, baba_d (calc_pattern_sum, sai/stats/stat_utils.py:220-272; the
+ * _d sums use max(tgt, src), sai/stats/fd_statistic.py:78-81).  out_pop < 0 =
+ * no outgroup (frequency 0, stat_utils.py:212-213).  The statistics are
+ *   Danc  = (baaa - abaa) / (baaa + abaa)                 danc_statistic.py:74-80
+ *   Dplus = (abba - baba + baaa - abaa) / (abba + baba + baaa + abaa)   dplus_statistic.py:76-83
+ *   df    = (abba - baba) / (abba + baba + 2 bbaa)         df_statistic.py:75-81
+ *   fd    = (abba - baba) / (abba_d - baba_d)              fd_statistic.py:83-86
+ * (NaN when the denominator is 0), formed by the caller. */
+int sai_window_patterns(const sai_layout* lay, const int32_t* d_pos, int64_t n_sites,
+                        const int64_t* d_win_start, const int64_t* d_win_end, int64_t n_windows,
+                        const int32_t* d_num, const int32_t* d_called, int64_t count_stride,
+                        int32_t ref_pop, int32_t tgt_pop, int32_t out_pop, const int32_t* src_pops,
+                        int32_t n_src, double* d_sums, void* stream);
+
 /* ---- host-buffer engine (replaces ChunkPreprocessor.run's inner loop) ----- */
 typedef struct sai_engine sai_engine;
 int sai_engine_create(int32_t device, sai_engine** out);
@@ -243,6 +260,13 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
 /* After SAI_E_CAPACITY: re-runs only the window kernel on the flags still
  * resident on the device, with the (larger) buffers of `out`. */
 int sai_engine_rescore_windows(sai_engine* e, sai_host_results* out);
+
+/* Site-pattern sums (see sai_window_patterns) for the chunk of the last
+ * sai_engine_score_host call, whose packed tiles, positions and windows are
+ * still resident on the device: runs the counting genotype pass + the pattern
+ * kernel and copies sums[n_src][W][7] to the host. */
+int sai_engine_pattern_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, int32_t tgt_pop,
+                            int32_t out_pop, const int32_t* src_pops, int32_t n_src, double* sums);
 
 /* ---- synthetic genotypes (bench / tests only) ---------------------------- */
 /* Fills tiles [tile0, tile0+n_tiles) of a packed matrix directly on the device

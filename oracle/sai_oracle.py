@@ -224,6 +224,52 @@ def q_statistic(
 
 
 # --------------------------------------------------------------------------
+# N3  Danc / Dplus / df / fd      (sai/stats/stat_utils.py:171-272 and the four
+#     *_statistic.py classes)
+# --------------------------------------------------------------------------
+def pattern_sum(freqs, pattern: str) -> float:
+    """Sum over sites of the product of ``f`` ('b') or ``1 - f`` ('a') of
+    (ref, tgt, src, out), multiplied in that order starting from ones
+    (stat_utils.py:258-272)."""
+    if len(pattern) != 4:
+        raise ValueError("Pattern must be a four-character string.")
+    prod = np.ones_like(freqs[0])
+    for f, c in zip(freqs, pattern.lower()):
+        if c == "a":
+            prod = prod * (1 - f)
+        elif c == "b":
+            prod = prod * f
+        else:
+            raise ValueError(f"Invalid character '{c}' in pattern. Only 'a' and 'b' allowed.")
+    return float(np.sum(prod))
+
+
+def four_pop_statistics(ref_gts, tgt_gts, src_gts_list, ref_ploidy, tgt_ploidy, src_ploidy_list,
+                        out_gts=None, out_ploidy=None) -> dict[str, list[float]]:
+    """``{"Danc": [...], "Dplus": [...], "df": [...], "fd": [...]}``, one value per
+    source population (danc_statistic.py:62-83, dplus_statistic.py:63-86,
+    df_statistic.py:62-84, fd_statistic.py:63-89).  The outgroup frequency is
+    0 when there is no outgroup (stat_utils.py:212-213)."""
+    out = {"Danc": [], "Dplus": [], "df": [], "fd": []}
+    fr = site_frequency(ref_gts, ref_ploidy)
+    ft = site_frequency(tgt_gts, tgt_ploidy)
+    fo = np.zeros_like(fr) if out_gts is None else site_frequency(out_gts, out_ploidy)
+    ratio = lambda n, d: n / d if d != 0 else np.nan
+    for src, sp in zip(src_gts_list, src_ploidy_list):
+        fs = site_frequency(src, sp)
+        four = (fr, ft, fs, fo)
+        abba, baba = pattern_sum(four, "abba"), pattern_sum(four, "baba")
+        baaa, abaa, bbaa = pattern_sum(four, "baaa"), pattern_sum(four, "abaa"), pattern_sum(four, "bbaa")
+        dnr = np.maximum(ft, fs)
+        abba_d, baba_d = pattern_sum((fr, dnr, dnr, fo), "abba"), pattern_sum((fr, dnr, dnr, fo), "baba")
+        out["Danc"].append(ratio(baaa - abaa, baaa + abaa))
+        out["Dplus"].append(ratio(abba - baba + baaa - abaa, abba + baba + baaa + abaa))
+        out["df"].append(ratio(abba - baba, abba + baba + 2 * bbaa))
+        out["fd"].append(ratio(abba - baba, abba_d - baba_d))
+    return out
+
+
+# --------------------------------------------------------------------------
 # A5  window grid                  (sai/utils/utils.py:558-612)
 # --------------------------------------------------------------------------
 def split_genome(pos, window_size: int, step_size: int, start: Optional[int] = None):
@@ -335,8 +381,8 @@ def iter_windows(
 def window_item(win: dict, stat_config, anc_allele_available: bool) -> dict[str, Any]:
     """One output item for one window dict.  ``stat_config`` needs ``.root``
     (ordered mapping) and ``.get_parameters(name)``; ``win['ploidy_config']``
-    needs ``.get_ploidy(group, pop=None)``.  Only U and Q are computed here
-    (the other statistics are outside the hot path)."""
+    needs ``.get_ploidy(group, pop=None)``.  U, Q and the four site-pattern
+    statistics (Danc, Dplus, df, fd) are covered; DD is not."""
     item = {
         "chr_name": win["chr_name"],
         "start": win["start"],
@@ -349,10 +395,15 @@ def window_item(win: dict, stat_config, anc_allele_available: bool) -> dict[str,
         "cdd_pos": {},
     }
     stats = [s for s in stat_config.root.keys() if s in ("U", "Q")]
+    four = [s for s in stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd") and stat_config.root[s] is True]
+    n_src = len(win["src_pop_list"])
     if win["ref_gts"] is None or win["tgt_gts"] is None or win["src_gts_list"] is None:
-        for s in stats:
-            item[s] = np.nan
-            item["cdd_pos"][s] = np.array([])
+        for s in stat_config.root.keys():  # feature_preprocessor.py:137-144, in config order
+            if s in four:
+                item[s] = [np.nan] * n_src if n_src > 1 else np.nan
+            elif s in stats:
+                item[s] = np.nan
+                item["cdd_pos"][s] = np.array([])
         return item
     pc = win["ploidy_config"]
     pops = dict(
@@ -363,7 +414,16 @@ def window_item(win: dict, stat_config, anc_allele_available: bool) -> dict[str,
         tgt_ploidy=pc.get_ploidy("tgt", win["tgt_pop"]),
         src_ploidy_list=pc.get_ploidy("src"),
     )
-    for s in stats:
+    four_vals = None
+    if four:
+        four_vals = four_pop_statistics(**pops, out_gts=win["out_gts"],
+                                        out_ploidy=pc.get_ploidy("outgroup", win["out_pop"]) if win["out_pop"] is not None else None)
+    for s in stat_config.root.keys():
+        if s in four:
+            item[s] = four_vals[s]
+            continue
+        if s not in stats:
+            continue
         prm = stat_config.get_parameters(s)
         common = dict(
             pos=win["pos"],
@@ -392,6 +452,7 @@ def score_chunk(
     ploidy_config,
     stat_config,
     anc_allele_available: bool,
+    out_data: Optional[dict] = None,
 ) -> list[dict[str, Any]]:
     """What ``ChunkPreprocessor.run(chr_name, start, end)`` returns
     (sai/preprocessors/chunk_preprocessor.py:105-147) given in-memory
@@ -405,6 +466,7 @@ def score_chunk(
         {t: wins for t in tgt_data},
         num_src=len(src_data),
         ploidy_config=ploidy_config,
+        out_data=out_data,
     )
     return [window_item(w, stat_config, anc_allele_available) for w in gen]
 
@@ -418,7 +480,16 @@ def format_items(items: list[dict], stat_names: Sequence[str]):
     reference's exact text layout (``str(value)`` for every statistic)."""
     rows = []
     for it in items:
-        vals = "\t".join("" if it.get(s) is None else str(it.get(s)) for s in stat_names)
+        parts = []
+        for s in stat_names:
+            v = it.get(s)
+            if isinstance(v, list) and len(v) == len(it["src_pop_list"]):
+                parts.extend("" if x is None else str(x) for x in v)  # one column per source
+            else:
+                if isinstance(v, list):
+                    v = v[0] if v else ""
+                parts.append("" if v is None else str(v))
+        vals = "\t".join(parts)
         rows.append(
             f"{it['chr_name']}\t{it['start']}\t{it['end']}\t{it['ref_pop']}\t"
             f"{it['tgt_pop']}\t{','.join(it['src_pop_list'])}\t{it['out_pop']}\t"
@@ -437,9 +508,16 @@ def format_items(items: list[dict], stat_names: Sequence[str]):
     return rows, logs
 
 
-def score_header(stat_names: Sequence[str]) -> str:
+def score_header(stat_names: Sequence[str], src_pops: Sequence[str] = ()) -> str:
+    """Header of the score file (sai/sai.py:111-131): U and Q one column each,
+    the other statistics one column per source population when there are several."""
     cols = ["Chrom", "Start", "End", "Ref", "Tgt", "Src", "Outgroup", "N(Variants)"]
-    return "\t".join(cols + list(stat_names)) + "\n"
+    for s in stat_names:
+        if s in ("U", "Q") or len(src_pops) <= 1:
+            cols.append(s)
+        else:
+            cols.extend(f"{s}.{sp}" for sp in src_pops)
+    return "\t".join(cols) + "\n"
 
 
 # --------------------------------------------------------------------------

@@ -108,6 +108,11 @@ SYMBOLS = {
         C.c_int,
         [_P, _I64, _P, _P, _I64, _JOB, _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _P],
     ),
+    "sai_window_patterns": (
+        C.c_int,
+        [_LAY, _P, _I64, _P, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _P],
+    ),
+    "sai_engine_pattern_sums": (C.c_int, [_P, _LAY, _I32, _I32, _I32, _P, _I32, _P]),
     "sai_engine_create": (C.c_int, [_I32, C.POINTER(_P)]),
     "sai_engine_destroy": (None, [_P]),
     "sai_engine_score_host": (

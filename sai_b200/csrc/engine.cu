@@ -20,7 +20,7 @@ struct sai_engine {
     void* p = nullptr;
     size_t cap = 0;
   };
-  Buf packed, pos, win, mask, qval, res, cand;
+  Buf packed, pos, win, mask, qval, res, cand, counts, sums;
   // state of the last call (for sai_engine_rescore_windows)
   int64_t n_sites = 0, W = 0;
   int32_t n_jobs = 0;
@@ -152,7 +152,7 @@ int sai_engine_create(int32_t device, sai_engine** out) {
 void sai_engine_destroy(sai_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  for (auto* b : {&e->packed, &e->pos, &e->win, &e->mask, &e->qval, &e->res, &e->cand})
+  for (auto* b : {&e->packed, &e->pos, &e->win, &e->mask, &e->qval, &e->res, &e->cand, &e->counts, &e->sums})
     if (b->p) cudaFree(b->p);
   for (auto ev : e->ev) cudaEventDestroy(ev);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
@@ -225,6 +225,32 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
   SAI_CUDA_CHECK(cudaEventRecord(e->ev[n_slices], e->s_copy));
   SAI_CUDA_CHECK(cudaStreamWaitEvent(e->s_comp, e->ev[n_slices], 0));
   return run_windows(e, out);
+}
+
+int sai_engine_pattern_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, int32_t tgt_pop,
+                            int32_t out_pop, const int32_t* src_pops, int32_t n_src, double* sums) {
+  SAI_REQUIRE(e && e->n_jobs > 0, "no previous sai_engine_score_host call");
+  SAI_REQUIRE(sums && src_pops, "NULL argument");
+  if (int rc = validate_layout(lay)) return rc;
+  SAI_CUDA_CHECK(cudaSetDevice(e->device));
+  const int64_t n_tiles = sai_num_tiles(e->n_sites);
+  const int64_t stride = n_tiles * kTile;
+  const int64_t W = e->W;
+  if (W == 0 || n_src <= 0) return SAI_OK;
+  if (int rc = grow(e->counts, sizeof(int32_t) * 2 * (size_t)lay->n_pops * stride + 256)) return rc;
+  if (int rc = grow(e->sums, sizeof(double) * 7 * (size_t)n_src * W + 256)) return rc;
+  int32_t* d_num = static_cast<int32_t*>(e->counts.p);
+  int32_t* d_called = d_num + (size_t)lay->n_pops * stride;
+  if (int rc = sai_site_counts(lay, e->packed.p, 0, n_tiles, d_num, d_called, stride, 0, e->s_comp)) return rc;
+  const int64_t* d_ws = static_cast<const int64_t*>(e->win.p);
+  if (int rc = sai_window_patterns(lay, static_cast<const int32_t*>(e->pos.p), e->n_sites, d_ws, d_ws + W, W,
+                                   d_num, d_called, stride, ref_pop, tgt_pop, out_pop, src_pops, n_src,
+                                   static_cast<double*>(e->sums.p), e->s_comp))
+    return rc;
+  SAI_CUDA_CHECK(cudaMemcpyAsync(sums, e->sums.p, sizeof(double) * 7 * (size_t)n_src * W,
+                                 cudaMemcpyDeviceToHost, e->s_comp));
+  SAI_CUDA_CHECK(cudaStreamSynchronize(e->s_comp));
+  return SAI_OK;
 }
 
 int sai_engine_rescore_windows(sai_engine* e, sai_host_results* out) {

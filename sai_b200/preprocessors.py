@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _cabi
 from .encode import PopData, pack_populations
-from .scoring import HostEngine, make_job
+from .scoring import HostEngine, four_pop_values, make_job
 from .windows import chunk_windows, split_genome
 
 
@@ -55,6 +55,9 @@ def score_populations(
 ) -> list[dict[str, Any]]:
     """Item dicts for every (ref, tgt, src-combination, outgroup) x window."""
     stats = [s for s in stat_config.root.keys() if s in ("U", "Q")]
+    four = [s for s in stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd") and stat_config.root[s] is True]
+    if any(s == "DD" and stat_config.root[s] is True for s in stat_config.root.keys()):
+        raise NotImplementedError("the DD statistic is not covered by sai_b200")
     num_src = len(src_data) if num_src is None else num_src
     src_combos = list(combinations(src_data.keys(), num_src))
     outs = list(out_data.keys()) if out_data else [None]
@@ -81,8 +84,16 @@ def score_populations(
             spec["x" if s == "U" else "quantile"] = prm["tgt"][tgt_pop]
             specs[s] = spec
         job = make_job(0, 1, list(range(2, 2 + n_src)), anc_allele_available, specs.get("U"), specs.get("Q"))
-        pg = pack_populations(rows[: 2 + n_src], ploidy, pos)
-        res = engine.score(pg, windows, [job]) if stats else None
+        n_pack = 2 + n_src
+        if out_pop is not None and four:
+            ploidy.append(ploidy_config.get_ploidy("outgroup", out_pop))
+            n_pack += 1
+        pg = pack_populations(rows[:n_pack], ploidy[:n_pack], pos)
+        res = engine.score(pg, windows, [job]) if (stats or four) else None
+        four_vals = None
+        if four:
+            sums = engine.pattern_sums(pg, 0, 1, 2 + n_src if (out_pop is not None) else -1, list(range(2, 2 + n_src)))
+            four_vals = four_pop_values(sums)
         pos_dtype = np.asarray(pos).dtype
         for i, (start, end) in enumerate(windows):
             nsnps = int(res.nsnps[0, i]) if res is not None else int(
@@ -99,7 +110,15 @@ def score_populations(
                 "nsnps": nsnps,
                 "cdd_pos": {},
             }
-            for s in stats:
+            for s in stat_config.root.keys():
+                if s in four:
+                    if nsnps == 0:  # feature_preprocessor.py:137-141
+                        item[s] = [np.nan for _ in range(n_src)] if n_src > 1 else np.nan
+                    else:
+                        item[s] = [four_vals[s][k][i] for k in range(n_src)]
+                    continue
+                if s not in stats:
+                    continue
                 if nsnps == 0:  # empty window: feature_preprocessor.py:131-144
                     item[s] = np.nan
                     item["cdd_pos"][s] = np.array([])
@@ -221,6 +240,7 @@ class ChunkPreprocessor:
     def _empty_items(self, chr_name, windows, ref_samples, tgt_samples, src_samples):
         # no data in the region: window_generator.py:249-289 + feature_preprocessor.py:131-144
         stats = [s for s in self.stat_config.root.keys() if s in ("U", "Q")]
+        four = [s for s in self.stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd")]
         items = []
         for ref_pop, tgt_pop, src_comb in product(
             ref_samples, tgt_samples, list(combinations(src_samples.keys(), self.num_src))
@@ -230,6 +250,8 @@ class ChunkPreprocessor:
                     "chr_name": chr_name, "start": start, "end": end, "ref_pop": ref_pop, "tgt_pop": tgt_pop,
                     "src_pop_list": src_comb, "out_pop": "NA", "nsnps": 0, "cdd_pos": {},
                 }
+                for s in four:
+                    it[s] = [np.nan for _ in src_comb] if len(src_comb) > 1 else np.nan
                 for s in stats:
                     it[s] = np.nan
                     it["cdd_pos"][s] = np.array([])

@@ -1,9 +1,8 @@
 """Top-level ``score`` with the signature and file outputs of the reference's
 ``sai.sai.score`` (sai/sai.py:33-151), running the U/Q path on the GPU.
 
-Only U and Q are computed here (the hot path this package covers); a config
-that enables another statistic is rejected instead of silently writing
-partial rows.  In a reference-side integration ``score`` itself stays
+U, Q and the four site-pattern statistics (Danc, Dplus, df, fd) are computed;
+a config that enables DD is rejected instead of silently writing partial rows.  In a reference-side integration ``score`` itself stays
 untouched and only the ``ChunkPreprocessor`` it constructs is swapped
 (INTEGRATION.md).
 """
@@ -54,11 +53,17 @@ def score(
 ) -> None:
     cfg = load_config(config)
     stat_config, ploidy_config, pop_config = cfg.statistics, cfg.ploidies, cfg.populations
-    others = [s for s in stat_config.root if s not in ("U", "Q") and stat_config.root[s] is not False]
+    others = [s for s in stat_config.root if s not in ("U", "Q", "Danc", "Dplus", "df", "fd") and stat_config.root[s] is not False]
     if others:
         raise NotImplementedError(
-            f"sai_b200 covers the U and Q statistics only; the configuration also enables {others}."
+            f"sai_b200 covers U, Q, Danc, Dplus, df and fd; the configuration also enables {others}."
         )
+    if anc_allele_file is None:  # sai/sai.py:79-84
+        for stat_name in stat_config.root.keys():
+            if stat_name in ["fd", "df", "Danc", "Dplus"]:
+                raise ValueError(
+                    f"The {stat_name} statistic requires polarized data, please provide the ancestral allele information with `--anc-alleles`."
+                )
     first, last = chromosome_span(vcf_file, chr_name)
     windows = split_genome([first, last], win_len, win_step)
     # one chunk per worker slot, processed one after the other on this GPU
@@ -79,7 +84,14 @@ def score(
         device=device,
     )
     header = ["Chrom", "Start", "End", "Ref", "Tgt", "Src", "Outgroup", "N(Variants)"]
-    header += [s for s in stat_config.root if s in ("U", "Q")]
+    src_pops = list(ploidy_config.root["src"].keys())
+    for stat_name in stat_config.root.keys():  # sai/sai.py:122-129
+        if stat_name not in ("U", "Q") and stat_config.root[stat_name] is False:
+            continue
+        if stat_name in ("U", "Q") or len(src_pops) <= 1:
+            header.append(stat_name)
+        else:
+            header.extend(f"{stat_name}.{sp}" for sp in src_pops)
     directory = os.path.dirname(output_file)
     if directory:
         os.makedirs(directory, exist_ok=True)

@@ -159,6 +159,7 @@ class HostEngine:
     def score_arrays(self, pg, ws, we, jobs, cap_u=None, cap_q=None) -> WindowResults:
         lib = _cabi.load()
         J, W = len(jobs), int(ws.shape[0])
+        self._last_W = W
         cap_u = max(1, 4 * W + 1024) if cap_u is None else int(cap_u)
         cap_q = max(1, 4 * W + 1024) if cap_q is None else int(cap_q)
         jarr = _job_array(jobs)
@@ -203,6 +204,37 @@ class HostEngine:
             rc = lib.sai_engine_rescore_windows(self._handle(), C.byref(res))
         _cabi.check(rc)
         return r
+
+
+    def pattern_sums(self, pg: PackedGenotypes, ref_pop: int, tgt_pop: int, out_pop: int, src_pops: Sequence[int]) -> np.ndarray:
+        """Site-pattern sums ``[n_src, W, 7]`` (abba, baba, baaa, abaa, bbaa,
+        abba_d, baba_d) of the chunk scored by the last ``score`` call."""
+        lib = _cabi.load()
+        W = self._last_W
+        sums = np.zeros((len(src_pops), W, 7), dtype=np.float64)
+        src = (C.c_int32 * len(src_pops))(*[int(x) for x in src_pops])
+        _cabi.check(lib.sai_engine_pattern_sums(self._handle(), C.byref(pg.layout), int(ref_pop), int(tgt_pop),
+                                                int(out_pop), src, len(src_pops), sums.ctypes.data))
+        return sums
+
+
+def four_pop_values(sums: np.ndarray) -> dict:
+    """Danc / Dplus / df / fd per source population and window from the seven
+    pattern sums, with the reference's formulas and its ``denominator != 0``
+    rule (danc_statistic.py:74-80, dplus_statistic.py:76-83, df_statistic.py:75-81,
+    fd_statistic.py:83-86).  Returns ``{name: [n_src][W] Python floats}``."""
+    out = {"Danc": [], "Dplus": [], "df": [], "fd": []}
+    ratio = lambda n, d: n / d if d != 0 else float("nan")
+    for k in range(sums.shape[0]):
+        rows = {name: [] for name in out}
+        for abba, baba, baaa, abaa, bbaa, abba_d, baba_d in sums[k].tolist():
+            rows["Danc"].append(ratio(baaa - abaa, baaa + abaa))
+            rows["Dplus"].append(ratio(abba - baba + baaa - abaa, abba + baba + baaa + abaa))
+            rows["df"].append(ratio(abba - baba, abba + baba + 2 * bbaa))
+            rows["fd"].append(ratio(abba - baba, abba_d - baba_d))
+        for name in out:
+            out[name].append(rows[name])
+    return out
 
 
 # --------------------------------------------------------------------------

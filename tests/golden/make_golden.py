@@ -118,9 +118,11 @@ def run_reference_pipeline(chr_name, start, end, win_len, win_step, data, ploidi
     wg.num_src = len(data["src"])
     wg.ploidy_config = PloidyConfig(ploidies)
     mk = lambda d: {p: ChromosomeData(POS=np.asarray(pos), REF=None, ALT=None, GT=np.asarray(gt, dtype=np.int64)) for p, (pos, gt) in d.items()}
-    wg.ref_data, wg.tgt_data, wg.src_data, wg.out_data = mk(data["ref"]), mk(data["tgt"]), mk(data["src"]), None
+    wg.ref_data, wg.tgt_data, wg.src_data = mk(data["ref"]), mk(data["tgt"]), mk(data["src"])
+    wg.out_data = mk(data["outgroup"]) if data.get("outgroup") else None
     names = lambda d: {p: [f"{p}_{i}" for i in range(np.asarray(gt).shape[1])] for p, (pos, gt) in d.items()}
-    wg.ref_samples, wg.tgt_samples, wg.src_samples, wg.out_samples = names(data["ref"]), names(data["tgt"]), names(data["src"]), None
+    wg.ref_samples, wg.tgt_samples, wg.src_samples = names(data["ref"]), names(data["tgt"]), names(data["src"])
+    wg.out_samples = names(data["outgroup"]) if data.get("outgroup") else None
     wg.src_combinations = [tuple(data["src"].keys())]
     wg.tgt_windows = {
         t: split_genome(
@@ -150,6 +152,10 @@ def run_reference_pipeline(chr_name, start, end, win_len, win_step, data, ploidi
                 v = it[s]
                 e[s] = fhex(v) if (s == "Q" or v != v) else int(v)
                 e[s + "_pos"] = [int(p) for p in it["cdd_pos"][s]]
+        for s in ("Danc", "Dplus", "df", "fd"):
+            if s in it:
+                v = it[s]
+                e[s] = [fhex(x) for x in v] if isinstance(v, list) else fhex(v)
         exp.append(e)
     return exp, text
 
@@ -198,6 +204,21 @@ PIPE_CASES = {
         stats={"U": {"ref": {"R": 0.3}, "tgt": {"T": 0.2}, "src": {"S": "=1"}},
                "Q": {"ref": {"R": 0.3}, "tgt": {"T": 0.75}, "src": {"S": "=1"}}},
         anc=True),
+    "fourpop_two_src": dict(
+        seed=8, n_sites=2500, gap=120.0,
+        pops={"ref": {"AFR": (60, 2)}, "tgt": {"EUR": (40, 2)}, "src": {"NEA": (2, 2), "DEN": (1, 2)}},
+        synth=dict(missing=0.01, src_all_missing=0.004), win=(40000, 20000),
+        stats={"Danc": True, "Dplus": True, "df": True, "fd": True,
+               "U": {"ref": {"AFR": 0.05}, "tgt": {"EUR": 0.3}, "src": {"NEA": "=1", "DEN": "=1"}},
+               "Q": {"ref": {"AFR": 0.05}, "tgt": {"EUR": 0.95}, "src": {"NEA": "=1", "DEN": "=1"}}},
+        anc=True),
+    "fourpop_outgroup": dict(
+        seed=9, n_sites=2000, gap=100.0,
+        pops={"ref": {"R": (50, 2)}, "tgt": {"T": (30, 4)}, "src": {"S": (3, 1)}, "outgroup": {"O": (2, 2)}},
+        synth={}, win=(30000, 10000),
+        stats={"fd": True, "df": True, "Danc": True, "Dplus": False,
+               "U": {"ref": {"R": 0.1}, "tgt": {"T": 0.2}, "src": {"S": "=1"}}},
+        anc=True),
     "u_only_chunked": dict(
         seed=7, n_sites=1500, gap=100.0,
         pops={"ref": {"R": (64, 2)}, "tgt": {"T": (32, 2)}, "src": {"S": (2, 2)}},
@@ -219,7 +240,7 @@ def pipe_cases():
         else:
             start, end = 1, int(pos[-1]) // c["win"][1] * c["win"][1] + c["win"][0]
         data = {g: {p: (pos, m) for p, m in d.items()} for g, d in mats.items()}
-        ploidies = {g: {p: c["pops"][g][p][1] for p in c["pops"][g]} for g in ("ref", "tgt", "src")}
+        ploidies = {g: {p: c["pops"][g][p][1] for p in c["pops"][g]} for g in c["pops"]}
         exp, text = run_reference_pipeline("1", start, end, c["win"][0], c["win"][1], data, ploidies, c["stats"], c["anc"])
         arrays = {"pos": pos.astype(np.int32)}
         for g, d in mats.items():
@@ -270,6 +291,12 @@ VCF_CASES = {
                          ploidies={"ref": {"ref1": 2}, "tgt": {"tgt1": 4, "tgt2": 4}, "src": {"src1": 4, "src2": 4}},
                          stats={"U": {"ref": {"ref1": 0.3}, "tgt": {"tgt1": 0.8, "tgt2": 0.8}, "src": {"src1": "=1", "src2": "=1"}}},
                          win=(50000, 50000), anc="test.mixed.ploidy.data.anc.alleles", first_last=True),
+    # test_sai.py:92-110 -> fd, df, Danc, Dplus of tests/data/test.with.outgroup.res.tsv
+    "outgroup_stats": dict(vcf="test.with.outgroup.vcf.gz", chr="1", lists=("test.with.outgroup.ref.list", "test.with.outgroup.tgt.list", "test.with.outgroup.src.list"),
+                           out_list="test.with.outgroup.out.list",
+                           ploidies={"ref": {"ref": 2}, "tgt": {"tgt": 2}, "src": {"src": 2}, "outgroup": {"out": 2}},
+                           stats={"fd": True, "df": True, "Danc": True, "Dplus": True},
+                           win=(40000, 40000), anc="test.with.outgroup.anc.alleles", first_last=True),
     # realistic shape (SLiM, 1008 ref + 503 tgt + 1 src), goldens minted here
     "outgroup_shape": dict(vcf="test.with.outgroup.vcf.gz", chr="1", lists=("test.with.outgroup.ref.list", "test.with.outgroup.tgt.list", "test.with.outgroup.src.list"),
                            ploidies=None,
@@ -302,11 +329,15 @@ def vcf_cases():
         from sai_b200.windows import split_genome as my_split, split_windows_ranges
         wins = my_split([int(region.pos[0]), int(region.pos[-1])], c["win"][0], c["win"][1])
         start, end = split_windows_ranges(wins, 1)[0]
+        out_path = None
+        if c.get("out_list"):
+            out_path = _write_list(name, "outgroup", my_vcf.parse_ind_file(os.path.join(REF, "tests", "data", c["out_list"])))
         groups = my_vcf.read_data(
             os.path.join(HERE, dst_name), c["chr"], MyPloidy(ploidies),
-            *[_write_list(name, g, lists[g]) for g in ("ref", "tgt", "src")], None,
+            *[_write_list(name, g, lists[g]) for g in ("ref", "tgt", "src")], out_path,
             os.path.join(HERE, f"vcf_{name}.anc.bed") if c["anc"] else None, start=start, end=end)
-        data = {g: {p: (d.POS, d.GT.astype(np.int64)) for p, d in groups[g][0].items()} for g in ("ref", "tgt", "src")}
+        data = {g: {p: (d.POS, d.GT.astype(np.int64)) for p, d in groups[g][0].items()}
+                for g in ("ref", "tgt", "src", "outgroup") if groups[g][0] is not None}
         exp, text = run_reference_pipeline(c["chr"], start, end, c["win"][0], c["win"][1], data, ploidies, stats, c["anc"] is not None)
         with open(os.path.join(HERE, f"vcf_{name}.json"), "w") as f:
             json.dump(dict(vcf=dst_name, chr_name=c["chr"], start=start, end=end, win_len=c["win"][0], win_step=c["win"][1],

@@ -34,13 +34,15 @@ def load_pipe_case(name: str):
     case = json.load(open(os.path.join(GOLDEN, f"pipe_{name}.json")))
     arrs = np.load(os.path.join(GOLDEN, f"pipe_{name}.npz"))
     data = {"ref": {}, "tgt": {}, "src": {}}
+    if "outgroup" in case["ploidies"]:
+        data["outgroup"] = {}
     for g in data:
         for p in case["ploidies"][g]:
             data[g][p] = arrs[f"{g}__{p}"]
     return case, arrs["pos"], data
 
 
-def check_items(got: list[dict], exp: list[dict], q_tol: float = 0.0) -> None:
+def check_items(got: list[dict], exp: list[dict], q_tol: float = 0.0, four_tol: float = 0.0) -> None:
     """Item-by-item comparison with the reference's outputs: everything exact;
     Q bit-exact when ``q_tol == 0`` else within ``q_tol`` absolute."""
     assert len(got) == len(exp), (len(got), len(exp))
@@ -63,3 +65,18 @@ def check_items(got: list[dict], exp: list[dict], q_tol: float = 0.0) -> None:
                 else:
                     assert abs(float(g[s]) - want) <= q_tol, (n, float(g[s]), want)
             assert [int(p) for p in g["cdd_pos"][s]] == e[s + "_pos"], (n, s)
+        for s in ("Danc", "Dplus", "df", "fd"):
+            if s not in e:
+                assert s not in g, (n, s)
+                continue
+            gv = g[s] if isinstance(g[s], list) else [g[s]]
+            ev = e[s] if isinstance(e[s], list) else [e[s]]
+            assert isinstance(g[s], list) == isinstance(e[s], list) and len(gv) == len(ev), (n, s)
+            for a, b in zip(gv, ev):
+                if b == "nan":
+                    assert np.isnan(a), (n, s, a)
+                elif four_tol == 0.0:
+                    assert float(a).hex() == b, (n, s, float(a), float.fromhex(b))
+                else:
+                    want = float.fromhex(b)
+                    assert abs(float(a) - want) <= four_tol * max(1.0, abs(want)), (n, s, float(a), want)

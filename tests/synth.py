@@ -54,4 +54,9 @@ def make_populations(
         if src_all_missing > 0:
             g[rng.random(n_sites) < src_all_missing] = -2
         out["src"][name] = g
+    if "outgroup" in pops:  # drawn last so that the other populations do not depend on it
+        out["outgroup"] = {}
+        f_out = np.where(rng.random(n_sites) < 0.03, 1.0, f * 0.05)
+        for name, (n, p) in pops["outgroup"].items():
+            out["outgroup"][name] = population(rng, f_out, n, p, missing)
     return pos, out

@@ -204,9 +204,9 @@ def test_pipeline_against_reference_outputs(name):
     stats = SimpleStats(case["stats"])
     items = orc.score_chunk(case["chr_name"], case["start"], case["end"], case["win_len"], case["win_step"],
                             mk(data["ref"]), mk(data["tgt"]), mk(data["src"]), SimplePloidy(case["ploidies"]),
-                            stats, case["anc"])
+                            stats, case["anc"], out_data=mk(data["outgroup"]) if "outgroup" in data else None)
     check_items(items, case["items"])
-    rows, logs = orc.format_items(items, [s for s in case["stats"]])
+    rows, logs = orc.format_items(items, [s for s in case["stats"] if s in ("U", "Q") or case["stats"][s] is True])
     assert "".join(rows) == case["text"]["tsv"]
     for key in logs:
         assert "".join(logs[key]) == case["text"][key]
@@ -223,14 +223,20 @@ def test_vcf_fixtures_against_reference_outputs(name):
     case = json.load(open(os.path.join(GOLDEN, f"vcf_{name}.json")))
     pc = SimplePloidy(case["ploidies"])
     anc = os.path.join(GOLDEN, f"vcf_{name}.anc.bed") if case["anc"] else None
+    out_list = os.path.join(GOLDEN, f"vcf_{name}.outgroup.list")
     groups = V.read_data(os.path.join(GOLDEN, case["vcf"]), case["chr_name"], pc,
-                         *[os.path.join(GOLDEN, f"vcf_{name}.{g}.list") for g in ("ref", "tgt", "src")], None, anc,
-                         start=case["start"], end=case["end"])
+                         *[os.path.join(GOLDEN, f"vcf_{name}.{g}.list") for g in ("ref", "tgt", "src")],
+                         out_list if os.path.exists(out_list) else None, anc, start=case["start"], end=case["end"])
     mk = lambda d: {p: orc.PopData(x.POS, x.GT.astype(np.int64)) for p, x in d.items()}
     items = orc.score_chunk(case["chr_name"], case["start"], case["end"], case["win_len"], case["win_step"],
                             mk(groups["ref"][0]), mk(groups["tgt"][0]), mk(groups["src"][0]), pc,
-                            SimpleStats(case["stats"]), case["anc"])
+                            SimpleStats(case["stats"]), case["anc"],
+                            out_data=mk(groups["outgroup"][0]) if groups["outgroup"][0] is not None else None)
     check_items(items, case["items"])
+    if name == "outgroup_stats":  # the reference's stored golden, tests/data/test.with.outgroup.res.tsv (test_sai.py:92-110)
+        want = dict(fd=0.0012826844929596443, df=0.0012417913767941238, Danc=-0.12498082112760132, Dplus=-0.12149240420484364)
+        for k, v in want.items():
+            assert np.isclose(items[0][k][0], v) and items[0][k][0] == v
     if name == "example_q":
         assert float(items[0]["Q"]) == 0.9
     if name == "example_u":
