@@ -1,0 +1,185 @@
+"""Edge cases of the CUDA path (through the C ABI): empty and degenerate inputs,
+extreme coordinates, the capacity limits of the ABI, parameter extremes, and a
+hypothesis-driven differential test against the oracle."""
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+import sai_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from sai_b200.scoring import HostEngine
+
+    e = HostEngine(0)
+    yield e
+    e.close()
+
+
+def _score(engine, mats, ploidy, pos, wins, n_src, anc, u=None, q=None):
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import make_job
+
+    pg = pack_populations(mats, ploidy, pos)
+    job = make_job(0, 1, list(range(2, 2 + n_src)), anc, u, q)
+    return engine.score(pg, wins, [job])
+
+
+def _expect(mats, ploidy, pos, win, n_src, anc, u, q):
+    keep = (pos >= win[0]) & (pos <= win[1])
+    sub = [m[keep].astype(np.int64) for m in mats]
+    if not keep.any():
+        return 0, None, None
+    eu = orc.u_statistic(sub[0], sub[1], sub[2 : 2 + n_src], ploidy[0], ploidy[1], list(ploidy[2 : 2 + n_src]),
+                         pos=pos[keep], anc_allele_available=anc, **u)
+    eq = orc.q_statistic(sub[0], sub[1], sub[2 : 2 + n_src], ploidy[0], ploidy[1], list(ploidy[2 : 2 + n_src]),
+                         pos=pos[keep], anc_allele_available=anc, **q)
+    return int(keep.sum()), eu, eq
+
+
+def _compare(res, i, exp):
+    n, eu, eq = exp
+    assert res.nsnps[0, i] == n
+    if eu is None:
+        assert res.u[0, i] == 0 and np.isnan(res.q[0, i]) and res.q_cnt[0, i] == 0
+        return
+    assert res.u[0, i] == eu["value"]
+    assert np.array_equal(res.u_positions(0, i), eu["cdd_pos"])
+    if np.isnan(eq["value"]):
+        assert np.isnan(res.q[0, i])
+    else:
+        assert res.q[0, i] == float(eq["value"])
+    assert np.array_equal(res.q_positions(0, i), np.asarray(eq["cdd_pos"], dtype=np.int32))
+
+
+U = dict(w=0.5, x=0.2, y_list=[("=", 1.0)])
+Q = dict(w=0.5, quantile=0.95, y_list=[("=", 1.0)])
+
+
+def test_empty_inputs(engine):
+    z = [np.zeros((0, 3), np.int8), np.zeros((0, 2), np.int8), np.zeros((0, 1), np.int8)]
+    res = _score(engine, z, [2, 2, 2], np.zeros(0, np.int32), [(1, 100), (50, 60)], 1, True, U, Q)
+    assert res.nsnps.tolist() == [[0, 0]] and res.u.tolist() == [[0, 0]] and np.isnan(res.q).all()
+    rng = np.random.default_rng(0)
+    m = [rng.integers(0, 3, size=(5, 3)).astype(np.int8) for _ in range(3)]
+    res = _score(engine, m, [2, 2, 2], np.arange(1, 6), [], 1, True, U, Q)
+    assert res.nsnps.shape == (1, 0) and res.totals.tolist() == [[0, 0]]
+
+
+def test_degenerate_windows_and_coordinates(engine):
+    rng = np.random.default_rng(1)
+    n = 300
+    top = 2_147_483_000
+    pos = np.sort(rng.choice(np.arange(top - 100_000, top), size=n, replace=False)).astype(np.int32)
+    mats = [rng.integers(0, 2, size=(n, 12)).astype(np.int8), rng.integers(0, 3, size=(n, 9)).astype(np.int8),
+            np.where(rng.random((n, 2)) < 0.5, 2, 0).astype(np.int8)]
+    wins = [(1, 10), (int(pos[0]), int(pos[0])), (int(pos[-1]), int(pos[-1]) + 5), (int(pos[-1]) + 1, 2**40),
+            (1, 2**40), (int(pos[10]), int(pos[200])), (int(pos[10]), int(pos[200])), (int(pos[50]) + 1, int(pos[51]) - 1),
+            (2**33, 2**34), (int(pos[100]), int(pos[100]) + 3)]
+    res = _score(engine, mats, [2, 2, 2], pos, wins, 1, False, U, Q)
+    for i, w in enumerate(wins):
+        _compare(res, i, _expect(mats, [2, 2, 2], pos, w, 1, False, U, Q))
+    assert res.nsnps[0, 4] == n and res.nsnps[0, 0] == 0 and res.nsnps[0, 8] == 0
+
+
+def test_abi_limits(engine):
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import make_job
+
+    rng = np.random.default_rng(2)
+    n = 500
+    pos = np.arange(10, 10 + 7 * n, 7)
+    # 8 sources (SAI_MAX_SRC), 16 populations (SAI_MAX_POPS) in one matrix, 8 jobs (SAI_MAX_JOBS) in one pass
+    ploidy = [2, 2] + [1, 2, 1, 2, 4, 1, 2, 8] + [2] * 6
+    mats = [rng.integers(0, 2, size=(n, 40)).astype(np.int8), rng.integers(0, 3, size=(n, 33)).astype(np.int8)]
+    for p in ploidy[2:]:
+        g = np.where(rng.random((n, 2)) < 0.7, p, rng.integers(0, p + 1, size=(n, 2))).astype(np.int8)
+        g[rng.random((n, 2)) < 0.02] = -1
+        mats.append(g)
+    assert len(mats) == 16
+    pg = pack_populations(mats, ploidy, pos)
+    assert pg.layout.pop[9].bits == 4 and pg.layout.pop[6].bits == 3
+    wins = [(1, 1200), (600, 2400), (1, 10**6)]
+    jobs, specs = [], []
+    for j in range(8):
+        k = 8 - j  # job j uses the first k sources
+        ys = [(">=", 0.5)] * k
+        u, q = dict(w=0.6, x=0.1 * j, y_list=ys), dict(w=0.6, quantile=0.1 * j, y_list=ys)
+        jobs.append(make_job(0, 1, list(range(2, 2 + k)), j % 2 == 0, u, q))
+        specs.append((k, j % 2 == 0, u, q))
+    res = engine.score(pg, wins, jobs)
+    for j, (k, anc, u, q) in enumerate(specs):
+        for i, w in enumerate(wins):
+            n_exp, eu, eq = _expect(mats, ploidy, pos, w, k, anc, u, q)
+            assert res.nsnps[j, i] == n_exp and res.u[j, i] == eu["value"]
+            assert np.array_equal(res.u_positions(j, i), eu["cdd_pos"])
+            assert (np.isnan(res.q[j, i]) and np.isnan(eq["value"])) or res.q[j, i] == float(eq["value"])
+            assert np.array_equal(res.q_positions(j, i), np.asarray(eq["cdd_pos"], dtype=np.int32))
+    assert res.u.sum() > 0
+    with pytest.raises(ValueError, match="at most 8 source populations"):
+        make_job(0, 1, list(range(2, 11)), True, dict(w=0.1, x=0.1, y_list=[("=", 1.0)] * 9))
+    with pytest.raises(ValueError, match="between 1 and 8 jobs"):
+        engine.score(pg, wins, jobs + jobs[:1])
+    with pytest.raises(ValueError, match="at most 16 populations"):
+        pack_populations(mats + mats[:1], ploidy + [2], pos)
+
+
+@pytest.mark.parametrize("u, q", [
+    (dict(w=0.0, x=0.0, y_list=[("=", 1.0)]), dict(w=0.0, quantile=0.5, y_list=[("=", 1.0)])),   # nothing is < 0
+    (dict(w=1.0, x=1.0, y_list=[(">=", 0.0)]), dict(w=1.0, quantile=0.0, y_list=[(">=", 0.0)])),  # nothing is > 1; q = min
+    (dict(w=1.0, x=0.0, y_list=[("<=", 1.0)]), dict(w=1.0, quantile=1.0, y_list=[("<=", 1.0)])),  # q = max
+    (dict(w=0.3, x=0.5, y_list=[("<", 0.5)]), dict(w=0.3, quantile=0.25, y_list=[(">", 0.5)])),
+    (dict(w=0.3, x=0.5, y_list=[("=", 0.5)]), dict(w=0.3, quantile=0.75, y_list=[("=", 0.5)])),  # y = 1 - y: every match inverts
+])
+@pytest.mark.parametrize("anc", [True, False])
+def test_parameter_extremes(engine, u, q, anc):
+    rng = np.random.default_rng(3)
+    n = 2000
+    pos = np.cumsum(rng.integers(1, 30, size=n)).astype(np.int32)
+    f = rng.beta(0.5, 0.5, size=n)
+    mats = [rng.binomial(2, f[:, None] * 0.3, size=(n, 25)).astype(np.int8), rng.binomial(2, f[:, None], size=(n, 17)).astype(np.int8),
+            rng.binomial(2, np.round(f)[:, None] * 0.5 + 0.25 * (rng.random((n, 1)) < 0.3), size=(n, 2)).astype(np.int8)]
+    for m in mats:
+        m[rng.random(m.shape) < 0.03] = -1
+    wins = [(1, 5000), (2000, 9000), (1, int(pos[-1]))]
+    res = _score(engine, mats, [2, 2, 2], pos, wins, 1, anc, u, q)
+    for i, w in enumerate(wins):
+        _compare(res, i, _expect(mats, [2, 2, 2], pos, w, 1, anc, u, q))
+
+
+gt_matrix = lambda n_sites, n_ind, ploidy: st.lists(
+    st.lists(st.integers(-2, ploidy), min_size=n_ind, max_size=n_ind), min_size=n_sites, max_size=n_sites)
+
+
+@st.composite
+def stat_case(draw):
+    n_sites = draw(st.integers(1, 40))
+    n_src = draw(st.integers(1, 3))
+    ploidy = [draw(st.integers(1, 4)) for _ in range(2 + n_src)]
+    n_ind = [draw(st.integers(1, 5)) for _ in range(2 + n_src)]
+    mats = [np.array(draw(gt_matrix(n_sites, n, p)), dtype=np.int8) for n, p in zip(n_ind, ploidy)]
+    ops = st.sampled_from(["=", "<", ">", "<=", ">="])
+    ys = st.sampled_from([0.0, 0.25, 1 / 3, 0.5, 2 / 3, 0.8, 1.0])
+    y_list = [(draw(ops), draw(ys)) for _ in range(n_src)]
+    w = draw(st.sampled_from([0.0, 0.1, 0.3, 0.5, 1.0]))
+    x = draw(st.sampled_from([0.0, 0.2, 0.5, 0.9]))
+    q = draw(st.sampled_from([0.0, 0.1, 0.5, 0.9, 0.95, 1.0]))
+    return mats, ploidy, n_src, y_list, w, x, q, draw(st.booleans())
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(case=stat_case())
+def test_hypothesis_differential(engine, case):
+    mats, ploidy, n_src, y_list, w, x, q, anc = case
+    n = mats[0].shape[0]
+    pos = np.arange(1, n + 1, dtype=np.int32) * 3
+    u, qq = dict(w=w, x=x, y_list=y_list), dict(w=w, quantile=q, y_list=y_list)
+    wins = [(1, 3 * n), (1, 3 * (n // 2) + 1)]
+    res = _score(engine, mats, ploidy, pos, wins, n_src, anc, u, qq)
+    for i, win in enumerate(wins):
+        _compare(res, i, _expect(mats, ploidy, pos, win, n_src, anc, u, qq))
