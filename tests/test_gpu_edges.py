@@ -87,6 +87,38 @@ def test_degenerate_windows_and_coordinates(engine):
     assert res.nsnps[0, 4] == n and res.nsnps[0, 0] == 0 and res.nsnps[0, 8] == 0
 
 
+def test_many_windows_in_any_order(engine):
+    """More windows than resident warps, so that every warp walks a run of windows
+    and reuses the previous search bounds as hints: sorted, reversed, shuffled
+    and repeated windows must all give the result of the window on its own."""
+    rng = np.random.default_rng(5)
+    n = 30_000
+    pos = np.cumsum(rng.integers(1, 60, size=n)).astype(np.int32)
+    mats = [rng.integers(0, 2, size=(n, 20)).astype(np.int8), rng.integers(0, 3, size=(n, 14)).astype(np.int8),
+            np.where(rng.random((n, 2)) < 0.6, 2, 0).astype(np.int8)]
+    top = int(pos[-1])
+    starts = np.sort(rng.integers(1, top, size=600))
+    base = [(int(s), int(s) + int(l)) for s, l in zip(starts, rng.integers(0, 40_000, size=600))]
+    base += [(1, 2**40), (top + 1, top + 10), (1, 1)]
+    ref = _score(engine, mats, [2, 2, 2], pos, base, 1, True, U, Q)  # one window per warp: no hints carried
+    for i in rng.choice(len(base), size=40, replace=False):
+        _compare(ref, int(i), _expect(mats, [2, 2, 2], pos, base[int(i)], 1, True, U, Q))
+    order = np.concatenate([
+        np.sort(rng.integers(0, len(base), size=30_000)),          # sorted by start (hints hold)
+        np.sort(rng.integers(0, len(base), size=15_000))[::-1],    # descending (every hint must be dropped)
+        rng.integers(0, len(base), size=25_000),                   # shuffled
+    ])
+    wins = [base[i] for i in order]
+    res = _score(engine, mats, [2, 2, 2], pos, wins, 1, True, U, Q)
+    assert np.array_equal(res.nsnps[0], ref.nsnps[0][order])
+    assert np.array_equal(res.u[0], ref.u[0][order])
+    assert np.array_equal(res.q[0], ref.q[0][order], equal_nan=True)
+    assert np.array_equal(res.q_cnt[0], ref.q_cnt[0][order])
+    for i in rng.choice(len(wins), size=300, replace=False):
+        assert np.array_equal(res.u_positions(0, int(i)), ref.u_positions(0, int(order[i])))
+        assert np.array_equal(res.q_positions(0, int(i)), ref.q_positions(0, int(order[i])))
+
+
 def test_abi_limits(engine):
     from sai_b200.encode import pack_populations
     from sai_b200.scoring import make_job
