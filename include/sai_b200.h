@@ -229,6 +229,37 @@ int sai_window_patterns(const sai_layout* lay, const int32_t* d_pos, int64_t n_s
                         int32_t ref_pop, int32_t tgt_pop, int32_t out_pop, const int32_t* src_pops,
                         int32_t n_src, double* d_sums, void* stream);
 
+/* ---- N4: DD (sai/stats/dd_statistic.py:62-77) ------------------------------- */
+/* DD = mean_a( mean_j sum_sites |src_a - ref_j|  -  mean_j sum_sites |src_a - tgt_j| ) uses the RAW
+ * allele sums, missing calls included with their negative value (cdist cityblock,
+ * dd_statistic.py:70-71).  The bit-planes keep a single missing code, so DD takes a
+ * *negative-value table* next to the packed matrix: for population p the entries
+ * neg_off[p] .. neg_off[p+1]-1 of (neg_site = site index, neg_ind = individual index
+ * inside the population, neg_val = raw value < 0), sorted by (site, individual).
+ * neg_off is host memory ([n_pops + 1], neg_off[0] = 0).
+ *
+ * sai_site_hist: one genotype pass over the listed populations; row r of population
+ * pops[q] (rows of earlier populations first, 2^bits - 1 rows each, sai_hist_rows() in total)
+ *     d_hist[r*stride + site] = number of individuals whose called value is r.
+ * d_missing[q] (optional) = missing calls of pops[q] over sites < n_sites, padding excluded.
+ *
+ * sai_window_dd: d_hist must hold {ref_pop, tgt_pop} in this order.  Per source population k,
+ * window i and source individual a (exact integers)
+ *     d_ref_sum[(k*W + i)*m_max + a] = sum_j sum_sites |src_a - ref_j|        (tgt likewise)
+ * *d_err is set to 1 if a missing source call has no table entry.  The caller forms
+ *     DD_k = mean_a( ref_sum/n_ref - tgt_sum/n_tgt )           dd_statistic.py:74-77 */
+int64_t sai_hist_rows(const sai_layout* lay, const int32_t* pops, int32_t n);
+int sai_site_hist(const sai_layout* lay, const void* d_packed, int64_t n_sites, const int32_t* pops,
+                  int32_t n_hist_pops, int32_t* d_hist, int64_t stride, uint64_t* d_missing,
+                  void* stream);
+int sai_window_dd(const sai_layout* lay, const void* d_packed, const int32_t* d_pos, int64_t n_sites,
+                  const int64_t* d_win_start, const int64_t* d_win_end, int64_t n_windows,
+                  const int32_t* d_hist, int64_t stride, int32_t ref_pop, int32_t tgt_pop,
+                  const int32_t* src_pops, int32_t n_src, const int64_t* neg_off,
+                  const int32_t* d_neg_site, const int32_t* d_neg_ind, const int32_t* d_neg_val,
+                  int64_t* d_ref_sum, int64_t* d_tgt_sum, int32_t m_max, int32_t* d_err,
+                  void* stream);
+
 /* ---- host-buffer engine (replaces ChunkPreprocessor.run's inner loop) ----- */
 typedef struct sai_engine sai_engine;
 int sai_engine_create(int32_t device, sai_engine** out);
@@ -267,6 +298,15 @@ int sai_engine_rescore_windows(sai_engine* e, sai_host_results* out);
  * kernel and copies sums[n_src][W][7] to the host. */
 int sai_engine_pattern_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, int32_t tgt_pop,
                             int32_t out_pop, const int32_t* src_pops, int32_t n_src, double* sums);
+
+/* DD sums (see sai_window_dd) for the chunk of the last sai_engine_score_host call; the
+ * negative-value table is HOST memory.  Fails with SAI_E_ARG when the table does not cover
+ * every missing call of ref_pop / tgt_pop / the source populations.
+ * ref_sum / tgt_sum: host, [n_src][W][m_max]. */
+int sai_engine_dd_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, int32_t tgt_pop,
+                       const int32_t* src_pops, int32_t n_src, const int64_t* neg_off,
+                       const int32_t* neg_site, const int32_t* neg_ind, const int32_t* neg_val,
+                       int64_t* ref_sum, int64_t* tgt_sum, int32_t m_max);
 
 /* ---- synthetic genotypes (bench / tests only) ---------------------------- */
 /* Fills tiles [tile0, tile0+n_tiles) of a packed matrix directly on the device

@@ -270,6 +270,34 @@ def four_pop_statistics(ref_gts, tgt_gts, src_gts_list, ref_ploidy, tgt_ploidy, 
 
 
 # --------------------------------------------------------------------------
+# N4  DD                           (sai/stats/dd_statistic.py:62-77)
+# --------------------------------------------------------------------------
+def cityblock_sums(a_gts: np.ndarray, b_gts: np.ndarray) -> np.ndarray:
+    """``out[i, j] = sum_sites |a[site, i] - b[site, j]|`` as float64 -- what
+    ``scipy.spatial.distance.cdist(a.T, b.T, metric="cityblock")`` returns
+    (dd_statistic.py:70-71); the raw values enter, negative missing codes
+    included.  Integer-valued, hence exact in float64 in any summation order."""
+    a = np.asarray(a_gts, dtype=np.float64)
+    b = np.asarray(b_gts, dtype=np.float64)
+    out = np.zeros((a.shape[1], b.shape[1]), dtype=np.float64)
+    for i in range(a.shape[1]):
+        out[i] = np.abs(a[:, i : i + 1] - b).sum(axis=0)
+    return out
+
+
+def dd_statistic(ref_gts, tgt_gts, src_gts_list) -> list:
+    """One DD value per source population: the mean over source individuals of
+    (mean distance to the ref individuals - mean distance to the tgt individuals)
+    (dd_statistic.py:66-79)."""
+    values = []
+    for src_gts in src_gts_list:
+        mean_src_tgt = np.mean(cityblock_sums(src_gts, tgt_gts), axis=1)
+        mean_src_ref = np.mean(cityblock_sums(src_gts, ref_gts), axis=1)
+        values.append(np.mean(mean_src_ref - mean_src_tgt))
+    return values
+
+
+# --------------------------------------------------------------------------
 # A5  window grid                  (sai/utils/utils.py:558-612)
 # --------------------------------------------------------------------------
 def split_genome(pos, window_size: int, step_size: int, start: Optional[int] = None):
@@ -382,7 +410,7 @@ def window_item(win: dict, stat_config, anc_allele_available: bool) -> dict[str,
     """One output item for one window dict.  ``stat_config`` needs ``.root``
     (ordered mapping) and ``.get_parameters(name)``; ``win['ploidy_config']``
     needs ``.get_ploidy(group, pop=None)``.  U, Q and the four site-pattern
-    statistics (Danc, Dplus, df, fd) are covered; DD is not."""
+    statistics (Danc, Dplus, df, fd) and DD are covered."""
     item = {
         "chr_name": win["chr_name"],
         "start": win["start"],
@@ -395,7 +423,7 @@ def window_item(win: dict, stat_config, anc_allele_available: bool) -> dict[str,
         "cdd_pos": {},
     }
     stats = [s for s in stat_config.root.keys() if s in ("U", "Q")]
-    four = [s for s in stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd") and stat_config.root[s] is True]
+    four = [s for s in stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd", "DD") and stat_config.root[s] is True]
     n_src = len(win["src_pop_list"])
     if win["ref_gts"] is None or win["tgt_gts"] is None or win["src_gts_list"] is None:
         for s in stat_config.root.keys():  # feature_preprocessor.py:137-144, in config order
@@ -415,10 +443,13 @@ def window_item(win: dict, stat_config, anc_allele_available: bool) -> dict[str,
         src_ploidy_list=pc.get_ploidy("src"),
     )
     four_vals = None
-    if four:
+    if [s for s in four if s != "DD"]:
         four_vals = four_pop_statistics(**pops, out_gts=win["out_gts"],
                                         out_ploidy=pc.get_ploidy("outgroup", win["out_pop"]) if win["out_pop"] is not None else None)
     for s in stat_config.root.keys():
+        if s == "DD" and s in four:
+            item[s] = dd_statistic(win["ref_gts"], win["tgt_gts"], win["src_gts_list"])
+            continue
         if s in four:
             item[s] = four_vals[s]
             continue

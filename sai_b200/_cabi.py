@@ -113,6 +113,13 @@ SYMBOLS = {
         [_LAY, _P, _I64, _P, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _P],
     ),
     "sai_engine_pattern_sums": (C.c_int, [_P, _LAY, _I32, _I32, _I32, _P, _I32, _P]),
+    "sai_hist_rows": (_I64, [_LAY, _P, _I32]),
+    "sai_site_hist": (C.c_int, [_LAY, _P, _I64, _P, _I32, _P, _I64, _P, _P]),
+    "sai_window_dd": (
+        C.c_int,
+        [_LAY, _P, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _P],
+    ),
+    "sai_engine_dd_sums": (C.c_int, [_P, _LAY, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _I32]),
     "sai_engine_create": (C.c_int, [_I32, C.POINTER(_P)]),
     "sai_engine_destroy": (None, [_P]),
     "sai_engine_score_host": (

@@ -20,7 +20,7 @@ struct sai_engine {
     void* p = nullptr;
     size_t cap = 0;
   };
-  Buf packed, pos, win, mask, qval, res, cand, counts, sums;
+  Buf packed, pos, win, mask, qval, res, cand, counts, sums, hist, neg, dd;
   // state of the last call (for sai_engine_rescore_windows)
   int64_t n_sites = 0, W = 0;
   int32_t n_jobs = 0;
@@ -152,7 +152,7 @@ int sai_engine_create(int32_t device, sai_engine** out) {
 void sai_engine_destroy(sai_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  for (auto* b : {&e->packed, &e->pos, &e->win, &e->mask, &e->qval, &e->res, &e->cand, &e->counts, &e->sums})
+  for (auto* b : {&e->packed, &e->pos, &e->win, &e->mask, &e->qval, &e->res, &e->cand, &e->counts, &e->sums, &e->hist, &e->neg, &e->dd})
     if (b->p) cudaFree(b->p);
   for (auto ev : e->ev) cudaEventDestroy(ev);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
@@ -250,6 +250,71 @@ int sai_engine_pattern_sums(sai_engine* e, const sai_layout* lay, int32_t ref_po
   SAI_CUDA_CHECK(cudaMemcpyAsync(sums, e->sums.p, sizeof(double) * 7 * (size_t)n_src * W,
                                  cudaMemcpyDeviceToHost, e->s_comp));
   SAI_CUDA_CHECK(cudaStreamSynchronize(e->s_comp));
+  return SAI_OK;
+}
+
+int sai_engine_dd_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, int32_t tgt_pop,
+                       const int32_t* src_pops, int32_t n_src, const int64_t* neg_off,
+                       const int32_t* neg_site, const int32_t* neg_ind, const int32_t* neg_val,
+                       int64_t* ref_sum, int64_t* tgt_sum, int32_t m_max) {
+  SAI_REQUIRE(e && e->n_jobs > 0, "no previous sai_engine_score_host call");
+  SAI_REQUIRE(ref_sum && tgt_sum && src_pops && neg_off, "NULL argument");
+  if (int rc = validate_layout(lay)) return rc;
+  SAI_REQUIRE(ref_pop >= 0 && ref_pop < lay->n_pops && tgt_pop >= 0 && tgt_pop < lay->n_pops,
+              "bad population index");
+  SAI_REQUIRE(m_max >= 1, "m_max must be positive");
+  SAI_CUDA_CHECK(cudaSetDevice(e->device));
+  const int64_t n_tiles = sai_num_tiles(e->n_sites);
+  const int64_t stride = n_tiles * kTile;
+  const int64_t W = e->W;
+  if (W == 0 || n_src <= 0) return SAI_OK;
+  const int64_t n_neg = neg_off[lay->n_pops];
+  SAI_REQUIRE(n_neg >= 0 && (n_neg == 0 || (neg_site && neg_ind && neg_val)), "bad negative-value table");
+  const int32_t hp[2] = {ref_pop, tgt_pop};
+  const int64_t rows = sai_hist_rows(lay, hp, 2);
+  const size_t out_n = (size_t)n_src * W * m_max;
+  if (int rc = grow(e->hist, sizeof(int32_t) * (size_t)rows * stride + 512)) return rc;
+  if (int rc = grow(e->neg, sizeof(int32_t) * 3 * (size_t)n_neg + 256)) return rc;
+  if (int rc = grow(e->dd, sizeof(int64_t) * 2 * out_n + 512)) return rc;
+  cudaStream_t st = e->s_comp;
+  // [hist rows][2 x uint64 missing totals][int32 err] share the hist buffer's tail
+  int32_t* d_hist = static_cast<int32_t*>(e->hist.p);
+  uint64_t* d_missing = reinterpret_cast<uint64_t*>(
+      static_cast<char*>(e->hist.p) + align256(sizeof(int32_t) * (size_t)rows * stride));
+  int32_t* d_err = reinterpret_cast<int32_t*>(d_missing + 2);
+  int32_t* d_ns = static_cast<int32_t*>(e->neg.p);
+  int32_t* d_ni = d_ns + n_neg;
+  int32_t* d_nv = d_ni + n_neg;
+  if (n_neg > 0) {
+    SAI_CUDA_CHECK(cudaMemcpyAsync(d_ns, neg_site, sizeof(int32_t) * n_neg, cudaMemcpyHostToDevice, st));
+    SAI_CUDA_CHECK(cudaMemcpyAsync(d_ni, neg_ind, sizeof(int32_t) * n_neg, cudaMemcpyHostToDevice, st));
+    SAI_CUDA_CHECK(cudaMemcpyAsync(d_nv, neg_val, sizeof(int32_t) * n_neg, cudaMemcpyHostToDevice, st));
+  }
+  SAI_CUDA_CHECK(cudaMemsetAsync(d_err, 0, sizeof(int32_t), st));
+  if (int rc = sai_site_hist(lay, e->packed.p, e->n_sites, hp, 2, d_hist, stride, d_missing, st)) return rc;
+  int64_t* d_r = static_cast<int64_t*>(e->dd.p);
+  int64_t* d_t = d_r + out_n;
+  SAI_CUDA_CHECK(cudaMemsetAsync(d_r, 0, sizeof(int64_t) * 2 * out_n, st));
+  const int64_t* d_ws = static_cast<const int64_t*>(e->win.p);
+  if (int rc = sai_window_dd(lay, e->packed.p, static_cast<const int32_t*>(e->pos.p), e->n_sites, d_ws, d_ws + W,
+                             W, d_hist, stride, ref_pop, tgt_pop, src_pops, n_src, neg_off, d_ns, d_ni, d_nv,
+                             d_r, d_t, m_max, d_err, st))
+    return rc;
+  uint64_t h_missing[2] = {0, 0};
+  int32_t h_err = 0;
+  SAI_CUDA_CHECK(cudaMemcpyAsync(ref_sum, d_r, sizeof(int64_t) * out_n, cudaMemcpyDeviceToHost, st));
+  SAI_CUDA_CHECK(cudaMemcpyAsync(tgt_sum, d_t, sizeof(int64_t) * out_n, cudaMemcpyDeviceToHost, st));
+  SAI_CUDA_CHECK(cudaMemcpyAsync(h_missing, d_missing, sizeof(h_missing), cudaMemcpyDeviceToHost, st));
+  SAI_CUDA_CHECK(cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, st));
+  SAI_CUDA_CHECK(cudaStreamSynchronize(st));
+  // the bit-planes keep one missing code: every missing call needs its raw value in the table
+  for (int q = 0; q < 2; ++q) {
+    const int64_t have = neg_off[hp[q] + 1] - neg_off[hp[q]];
+    SAI_REQUIRE((int64_t)h_missing[q] == have,
+                "population %d has %lld missing calls but %lld entries in the negative-value table", hp[q],
+                (long long)h_missing[q], (long long)have);
+  }
+  SAI_REQUIRE(h_err == 0, "a missing source call has no entry in the negative-value table");
   return SAI_OK;
 }
 

@@ -54,6 +54,12 @@ class PackedGenotypes:
     pos: np.ndarray  # int32, sorted, unique
     packed: np.ndarray  # uint8, host
     pop_names: list = field(default_factory=list)
+    # negative-value table (DD only; include/sai_b200.h "N4"): raw values of the calls the
+    # bit-planes code as missing, per population sorted by (site, individual)
+    neg_off: Optional[np.ndarray] = None  # int64 [n_pops + 1]
+    neg_site: Optional[np.ndarray] = None  # int32
+    neg_ind: Optional[np.ndarray] = None  # int32
+    neg_val: Optional[np.ndarray] = None  # int32
 
     @property
     def n_tiles(self) -> int:
@@ -88,9 +94,13 @@ def pack_populations(
     bits: Optional[Sequence[int]] = None,
     n_threads: int = 0,
     out: Optional[np.ndarray] = None,
+    keep_negatives: bool = False,
 ) -> PackedGenotypes:
-    """Packs one matrix per population (all over the same ``pos``)."""
+    """Packs one matrix per population (all over the same ``pos``).
+    ``keep_negatives`` also records the raw values of the missing calls (any
+    ``v < 0``) in the negative-value table the DD statistic needs."""
     lib = _cabi.load()
+    neg = negative_table(gts) if keep_negatives else (None, None, None, None)
     mats = [_as_i8(g) for g in gts]
     pos = np.ascontiguousarray(np.asarray(pos), dtype=np.int32)
     n_sites = int(pos.shape[0])
@@ -111,7 +121,25 @@ def pack_populations(
                 C.byref(lay), i, m.ctypes.data, n_sites, m.shape[1], out.ctypes.data, n_threads
             )
         )
-    return PackedGenotypes(lay, n_sites, pos, out[:nbytes] if nbytes else out[:0], list(pop_names or []))
+    return PackedGenotypes(lay, n_sites, pos, out[:nbytes] if nbytes else out[:0], list(pop_names or []), *neg)
+
+
+def negative_table(gts: Sequence[np.ndarray]):
+    """``(neg_off, neg_site, neg_ind, neg_val)`` of a list of per-population
+    matrices: every entry ``v < 0`` (a missing call; ``-1`` for ``0/.``, ``-2`` for
+    ``./.`` in diploid data, sai/utils/utils.py:405-410), row-major, i.e. sorted by
+    (site, individual) inside a population."""
+    off = np.zeros(len(gts) + 1, dtype=np.int64)
+    sites, inds, vals = [], [], []
+    for i, g in enumerate(gts):
+        g = np.asarray(g)
+        r, c = np.nonzero(g < 0)
+        sites.append(r.astype(np.int32))
+        inds.append(c.astype(np.int32))
+        vals.append(np.maximum(g[r, c].astype(np.int64), -(2**31) + 1).astype(np.int32))
+        off[i + 1] = off[i] + r.shape[0]
+    cat = lambda parts: np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0, np.int32)
+    return off, cat(sites), cat(inds), cat(vals)
 
 
 def unpack_population(pg: PackedGenotypes, pop: int, site0: int = 0, n: Optional[int] = None) -> np.ndarray:

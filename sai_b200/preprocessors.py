@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _cabi
 from .encode import PopData, pack_populations
-from .scoring import HostEngine, four_pop_values, make_job
+from .scoring import HostEngine, dd_values, four_pop_values, make_job
 from .windows import chunk_windows, split_genome
 
 
@@ -56,8 +56,7 @@ def score_populations(
     """Item dicts for every (ref, tgt, src-combination, outgroup) x window."""
     stats = [s for s in stat_config.root.keys() if s in ("U", "Q")]
     four = [s for s in stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd") and stat_config.root[s] is True]
-    if any(s == "DD" and stat_config.root[s] is True for s in stat_config.root.keys()):
-        raise NotImplementedError("the DD statistic is not covered by sai_b200")
+    dd = any(s == "DD" and stat_config.root[s] is True for s in stat_config.root.keys())
     num_src = len(src_data) if num_src is None else num_src
     src_combos = list(combinations(src_data.keys(), num_src))
     outs = list(out_data.keys()) if out_data else [None]
@@ -88,12 +87,17 @@ def score_populations(
         if out_pop is not None and four:
             ploidy.append(ploidy_config.get_ploidy("outgroup", out_pop))
             n_pack += 1
-        pg = pack_populations(rows[:n_pack], ploidy[:n_pack], pos)
-        res = engine.score(pg, windows, [job]) if (stats or four) else None
+        pg = pack_populations(rows[:n_pack], ploidy[:n_pack], pos, keep_negatives=dd)
+        res = engine.score(pg, windows, [job]) if (stats or four or dd) else None
         four_vals = None
         if four:
             sums = engine.pattern_sums(pg, 0, 1, 2 + n_src if (out_pop is not None) else -1, list(range(2, 2 + n_src)))
             four_vals = four_pop_values(sums)
+        dd_vals = None
+        if dd:
+            ref_sum, tgt_sum = engine.dd_sums(pg, 0, 1, list(range(2, 2 + n_src)))
+            dd_vals = dd_values(ref_sum, tgt_sum, rows[0].shape[1], rows[1].shape[1],
+                                [rows[2 + k].shape[1] for k in range(n_src)])
         pos_dtype = np.asarray(pos).dtype
         for i, (start, end) in enumerate(windows):
             nsnps = int(res.nsnps[0, i]) if res is not None else int(
@@ -111,9 +115,11 @@ def score_populations(
                 "cdd_pos": {},
             }
             for s in stat_config.root.keys():
-                if s in four:
+                if s in four or (dd and s == "DD"):
                     if nsnps == 0:  # feature_preprocessor.py:137-141
                         item[s] = [np.nan for _ in range(n_src)] if n_src > 1 else np.nan
+                    elif s == "DD":
+                        item[s] = [dd_vals[k][i] for k in range(n_src)]
                     else:
                         item[s] = [four_vals[s][k][i] for k in range(n_src)]
                     continue
@@ -240,7 +246,7 @@ class ChunkPreprocessor:
     def _empty_items(self, chr_name, windows, ref_samples, tgt_samples, src_samples):
         # no data in the region: window_generator.py:249-289 + feature_preprocessor.py:131-144
         stats = [s for s in self.stat_config.root.keys() if s in ("U", "Q")]
-        four = [s for s in self.stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd")]
+        four = [s for s in self.stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd", "DD")]
         items = []
         for ref_pop, tgt_pop, src_comb in product(
             ref_samples, tgt_samples, list(combinations(src_samples.keys(), self.num_src))

@@ -1,8 +1,8 @@
 """Top-level ``score`` with the signature and file outputs of the reference's
 ``sai.sai.score`` (sai/sai.py:33-151), running the U/Q path on the GPU.
 
-U, Q and the four site-pattern statistics (Danc, Dplus, df, fd) are computed;
-a config that enables DD is rejected instead of silently writing partial rows.  In a reference-side integration ``score`` itself stays
+Every statistic of the reference's registry is computed on the GPU: U, Q, the
+four site-pattern statistics (Danc, Dplus, df, fd) and DD.  In a reference-side integration ``score`` itself stays
 untouched and only the ``ChunkPreprocessor`` it constructs is swapped
 (INTEGRATION.md).
 """
@@ -53,10 +53,10 @@ def score(
 ) -> None:
     cfg = load_config(config)
     stat_config, ploidy_config, pop_config = cfg.statistics, cfg.ploidies, cfg.populations
-    others = [s for s in stat_config.root if s not in ("U", "Q", "Danc", "Dplus", "df", "fd") and stat_config.root[s] is not False]
+    others = [s for s in stat_config.root if s not in ("U", "Q", "Danc", "Dplus", "df", "fd", "DD") and stat_config.root[s] is not False]
     if others:
         raise NotImplementedError(
-            f"sai_b200 covers U, Q, Danc, Dplus, df and fd; the configuration also enables {others}."
+            f"sai_b200 covers U, Q, Danc, Dplus, df, fd and DD; the configuration also enables {others}."
         )
     if anc_allele_file is None:  # sai/sai.py:79-84
         for stat_name in stat_config.root.keys():

@@ -218,6 +218,41 @@ class HostEngine:
         return sums
 
 
+    def dd_sums(self, pg: PackedGenotypes, ref_pop: int, tgt_pop: int, src_pops: Sequence[int]):
+        """Exact integer distance sums of the DD statistic for the chunk scored by
+        the last ``score`` call: ``(ref_sum, tgt_sum)``, int64 ``[n_src, W, m_max]``
+        with ``ref_sum[k, i, a] = sum_j sum_sites |src_a - ref_j|``
+        (sai/stats/dd_statistic.py:70-71).  ``pg`` must carry the negative-value
+        table (``pack_populations(..., keep_negatives=True)``)."""
+        if pg.neg_off is None:
+            raise ValueError("DD needs the raw values of missing calls: pack with keep_negatives=True")
+        lib = _cabi.load()
+        W = self._last_W
+        m_max = max(int(pg.layout.pop[int(s)].n_samples) for s in src_pops)
+        ref_sum = np.zeros((len(src_pops), W, m_max), dtype=np.int64)
+        tgt_sum = np.zeros_like(ref_sum)
+        src = (C.c_int32 * len(src_pops))(*[int(x) for x in src_pops])
+        ptr = lambda a: a.ctypes.data if a.size else None
+        _cabi.check(lib.sai_engine_dd_sums(self._handle(), C.byref(pg.layout), int(ref_pop), int(tgt_pop), src,
+                                           len(src_pops), pg.neg_off.ctypes.data, ptr(pg.neg_site), ptr(pg.neg_ind),
+                                           ptr(pg.neg_val), ref_sum.ctypes.data, tgt_sum.ctypes.data, m_max))
+        return ref_sum, tgt_sum
+
+
+def dd_values(ref_sum: np.ndarray, tgt_sum: np.ndarray, n_ref: int, n_tgt: int, n_src_samples: Sequence[int]) -> list:
+    """DD per source population and window from the integer sums, with the
+    reference's float64 operations (dd_statistic.py:74-77): the row means are one
+    division of an exactly representable integer sum, then ``np.mean`` of the
+    differences.  Returns ``[n_src][W]`` numpy float64 scalars."""
+    out = []
+    for k, m in enumerate(n_src_samples):
+        mean_src_ref = ref_sum[k, :, :m].astype(np.float64) / n_ref
+        mean_src_tgt = tgt_sum[k, :, :m].astype(np.float64) / n_tgt
+        diff = mean_src_ref - mean_src_tgt
+        out.append([np.mean(np.ascontiguousarray(row)) for row in diff])
+    return out
+
+
 def four_pop_values(sums: np.ndarray) -> dict:
     """Danc / Dplus / df / fd per source population and window from the seven
     pattern sums, with the reference's formulas and its ``denominator != 0``

@@ -132,3 +132,25 @@ class QStatistic(GenericStatistic):
             return {"name": self.STAT_NAME, "value": np.nan, "cdd_pos": np.array([])}
         idx = res.q_positions(0, 0).astype(np.intp)
         return {"name": self.STAT_NAME, "value": np.float64(value), "cdd_pos": pos[idx]}
+
+
+@STAT_REGISTRY.register("DD")
+class DdStatistic(GenericStatistic):
+    """``compute()`` -> ``{"name": "DD", "value": [one float per source population]}``
+    (sai/stats/dd_statistic.py:40-77); the integer distance sums come from the GPU."""
+
+    STAT_NAME = "DD"
+
+    def compute(self, **kwargs) -> dict[str, Any]:
+        from .scoring import dd_values
+
+        n_src = len(self.src_gts_list)
+        ploidy = [self.ref_ploidy, self.tgt_ploidy] + list(self.src_ploidy_list)[:n_src]
+        mats = [np.asarray(self.ref_gts), np.asarray(self.tgt_gts)] + [np.asarray(g) for g in self.src_gts_list]
+        n = mats[0].shape[0]
+        pg = pack_populations(mats, ploidy, np.arange(n, dtype=np.int32), keep_negatives=True)
+        eng = _default_engine()
+        eng.score(pg, [(0, max(n - 1, 0))], [make_job(0, 1, list(range(2, 2 + n_src)), True)])
+        ref_sum, tgt_sum = eng.dd_sums(pg, 0, 1, list(range(2, 2 + n_src)))
+        vals = dd_values(ref_sum, tgt_sum, mats[0].shape[1], mats[1].shape[1], [m.shape[1] for m in mats[2:]])
+        return {"name": self.STAT_NAME, "value": [v[0] for v in vals]}

@@ -47,7 +47,7 @@ import sai.stats  # noqa: E402,F401  (registers the statistics)
 from sai.configs import PloidyConfig, StatConfig  # noqa: E402
 from sai.generators.window_generator import WindowGenerator  # noqa: E402
 from sai.preprocessors.feature_preprocessor import FeaturePreprocessor  # noqa: E402
-from sai.stats import QStatistic, UStatistic  # noqa: E402
+from sai.stats import DdStatistic, QStatistic, UStatistic  # noqa: E402
 from sai.utils import split_genome  # noqa: E402
 from sai.utils.genomic_dataclasses import ChromosomeData  # noqa: E402
 
@@ -98,12 +98,14 @@ def stat_cases(n_cases=400, seed=20261018):
                   tgt_ploidy=ploidy[1], src_ploidy_list=ploidy[2:])
         ru = UStatistic(**kw).compute(pos=pos, w=w, x=x, y_list=y_list, anc_allele_available=anc)
         rq = QStatistic(**kw).compute(pos=pos, w=w, y_list=y_list, quantile=q, anc_allele_available=anc)
+        rd = DdStatistic(**kw).compute()
         for k, m in enumerate(mats):
             arrays[f"c{c}_g{k}"] = m.astype(np.int8)
         arrays[f"c{c}_pos"] = pos.astype(np.int32)
         meta.append(dict(ploidy=ploidy, y_list=y_list, w=w, x=x, q=q, anc=anc, n_src=n_src,
                          U=int(ru["value"]), U_pos=[int(p) for p in ru["cdd_pos"]],
-                         Q=fhex(rq["value"]), Q_pos=[int(p) for p in rq["cdd_pos"]]))
+                         Q=fhex(rq["value"]), Q_pos=[int(p) for p in rq["cdd_pos"]],
+                         DD=[fhex(v) for v in rd["value"]]))
     np.savez_compressed(os.path.join(HERE, "stat_cases.npz"), **arrays)
     with open(os.path.join(HERE, "stat_cases.json"), "w") as f:
         json.dump(meta, f)
@@ -152,7 +154,7 @@ def run_reference_pipeline(chr_name, start, end, win_len, win_step, data, ploidi
                 v = it[s]
                 e[s] = fhex(v) if (s == "Q" or v != v) else int(v)
                 e[s + "_pos"] = [int(p) for p in it["cdd_pos"][s]]
-        for s in ("Danc", "Dplus", "df", "fd"):
+        for s in ("Danc", "Dplus", "df", "fd", "DD"):
             if s in it:
                 v = it[s]
                 e[s] = [fhex(x) for x in v] if isinstance(v, list) else fhex(v)
@@ -218,6 +220,20 @@ PIPE_CASES = {
         synth={}, win=(30000, 10000),
         stats={"fd": True, "df": True, "Danc": True, "Dplus": False,
                "U": {"ref": {"R": 0.1}, "tgt": {"T": 0.2}, "src": {"S": "=1"}}},
+        anc=True),
+    "dd_two_src_missing": dict(
+        seed=10, n_sites=2500, gap=100.0,
+        pops={"ref": {"AFR": (70, 2)}, "tgt": {"EUR": (45, 2)}, "src": {"NEA": (3, 2), "DEN": (1, 2)}},
+        synth=dict(missing=0.02, src_all_missing=0.004), win=(40000, 20000),
+        stats={"DD": True,
+               "U": {"ref": {"AFR": 0.05}, "tgt": {"EUR": 0.3}, "src": {"NEA": "=1", "DEN": "=1"}}},
+        anc=False),
+    "dd_mixed_ploidy_many_src": dict(
+        seed=11, n_sites=1500, gap=150.0,
+        pops={"ref": {"R1": (33, 4), "R2": (20, 1)}, "tgt": {"T": (40, 3)}, "src": {"S": (11, 2), "S4": (2, 4)}},
+        synth=dict(missing=0.03), win=(30000, 15000),
+        stats={"fd": True, "DD": True, "Danc": False,
+               "Q": {"ref": {"R1": 0.2, "R2": 0.2}, "tgt": {"T": 0.9}, "src": {"S": ">=0.5", "S4": ">=0.5"}}},
         anc=True),
     "u_only_chunked": dict(
         seed=7, n_sites=1500, gap=100.0,

@@ -76,6 +76,28 @@ def test_pack_unpack_roundtrip(n_sites):
         assert np.array_equal(unpack_population(pg, 2, 35, 4), np.where(mats[2][35:39] < 0, -1, mats[2][35:39]))
 
 
+def test_negative_table_for_dd():
+    """The DD side table: raw values of every missing call, per population in
+    (site, individual) order, for any integer dtype."""
+    from sai_b200.encode import negative_table, pack_populations
+
+    rng = np.random.default_rng(11)
+    mats = [rng.integers(-2, 3, size=(50, n)).astype(dt) for n, dt in ((7, np.int8), (3, np.int64), (1, np.int16))]
+    mats[1][4, 1] = -(2**40)  # clipped, still negative
+    off, site, ind, val = negative_table(mats)
+    assert off[0] == 0 and off.dtype == np.int64 and site.dtype == ind.dtype == val.dtype == np.int32
+    for p, m in enumerate(mats):
+        sl = slice(int(off[p]), int(off[p + 1]))
+        r, c = np.nonzero(m < 0)
+        assert np.array_equal(site[sl], r) and np.array_equal(ind[sl], c)
+        assert np.array_equal(val[sl], np.maximum(m[r, c].astype(np.int64), -(2**31) + 1))
+        key = site[sl].astype(np.int64) * 1000 + ind[sl]
+        assert np.all(np.diff(key) > 0)
+    pg = pack_populations(mats, [2, 2, 2], np.arange(50), keep_negatives=True)
+    assert np.array_equal(pg.neg_off, off) and np.array_equal(pg.neg_val, val)
+    assert pack_populations(mats, [2, 2, 2], np.arange(50)).neg_off is None
+
+
 def test_pack_rejects_out_of_domain():
     from sai_b200.encode import pack_populations
 

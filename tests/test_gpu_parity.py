@@ -124,6 +124,60 @@ def test_stat_cases_gpu():
         assert [int(p) for p in rq["cdd_pos"]] == m["Q_pos"], c
 
 
+def test_dd_cases_gpu():
+    """DD of the same 400 cases through the stat-class mirror: bit-exact against
+    the reference's DdStatistic (integer sums on the GPU, the reference's own
+    float64 steps on top)."""
+    from sai_b200.stats import STAT_REGISTRY
+
+    cls = STAT_REGISTRY.get("DD")
+    meta = json.load(open(os.path.join(GOLDEN, "stat_cases.json")))
+    arrs = np.load(os.path.join(GOLDEN, "stat_cases.npz"))
+    for c, m in enumerate(meta):
+        mats = [arrs[f"c{c}_g{k}"] for k in range(2 + m["n_src"])]
+        pl = m["ploidy"]
+        res = cls(ref_gts=mats[0], tgt_gts=mats[1], src_gts_list=mats[2:], ref_ploidy=pl[0], tgt_ploidy=pl[1],
+                  src_ploidy_list=pl[2:]).compute()
+        assert res["name"] == "DD" and [float(v).hex() for v in res["value"]] == m["DD"], c
+    # tests/stats/test_dd_statistic.py:25-46
+    r = cls(ref_gts=np.array([[1, 1], [0, 0]]), tgt_gts=np.array([[1, 0], [0, 1]]), src_gts_list=[np.array([[0, 1], [1, 1]])],
+            ref_ploidy=1, tgt_ploidy=1, src_ploidy_list=[1]).compute()
+    assert np.isclose(r["value"][0], 0.5)
+
+
+def test_dd_needs_negative_table(engine):
+    """The bit-planes keep one missing code; DD refuses to run without the raw
+    values, and the engine checks that the table covers every missing call."""
+    from sai_b200 import _cabi
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import make_job
+
+    rng = np.random.default_rng(3)
+    mats = [rng.integers(-2, 3, size=(200, n)).astype(np.int8) for n in (40, 33, 3)]
+    pos = np.arange(1, 201, dtype=np.int32)
+    pg = pack_populations(mats, [2, 2, 2], pos)
+    engine.score(pg, [(1, 200)], [make_job(0, 1, [2], True)])
+    with pytest.raises(ValueError, match="keep_negatives"):
+        engine.dd_sums(pg, 0, 1, [2])
+    pg = pack_populations(mats, [2, 2, 2], pos, keep_negatives=True)
+    engine.score(pg, [(1, 200), (50, 120)], [make_job(0, 1, [2], True)])
+    ref_sum, tgt_sum = engine.dd_sums(pg, 0, 1, [2])
+    m64 = [m.astype(np.int64) for m in mats]
+    for i, (a, b) in enumerate([(0, 200), (49, 120)]):
+        assert np.array_equal(ref_sum[0, i], orc.cityblock_sums(m64[2][a:b], m64[0][a:b]).sum(axis=1).astype(np.int64))
+        assert np.array_equal(tgt_sum[0, i], orc.cityblock_sums(m64[2][a:b], m64[1][a:b]).sum(axis=1).astype(np.int64))
+    # a table that misses entries is rejected instead of silently dropping the calls
+    lo, hi = int(pg.neg_off[0]), int(pg.neg_off[1])
+    assert hi - lo > 3
+    keep = np.ones(pg.neg_site.shape[0], bool)
+    keep[lo + 1] = False
+    pg.neg_site, pg.neg_ind, pg.neg_val = pg.neg_site[keep].copy(), pg.neg_ind[keep].copy(), pg.neg_val[keep].copy()
+    pg.neg_off = pg.neg_off.copy()
+    pg.neg_off[1:] -= 1
+    with pytest.raises((_cabi.SaiError, ValueError), match="negative-value table"):
+        engine.dd_sums(pg, 0, 1, [2])
+
+
 # ---------------------------------------------------------------- pipeline level
 @pytest.mark.parametrize("name", pipe_case_names())
 def test_pipeline_golden_gpu(name, engine, tmp_path):
@@ -141,7 +195,7 @@ def test_pipeline_golden_gpu(name, engine, tmp_path):
     check_items(items, case["items"], q_tol=0.0, four_tol=FOUR_TOL)  # U/Q bit-exact, so their TSV text is identical
     out = tmp_path / "scores.tsv"
     write_items(str(out), items, stats)
-    has_four = any(s in case["stats"] for s in ("Danc", "Dplus", "df", "fd"))
+    has_four = any(case["stats"].get(s) is True for s in ("Danc", "Dplus", "df", "fd"))
     if has_four:  # the site-pattern sums differ in summation order: compare the rows numerically
         got_rows = [r.split("\t") for r in out.read_text().splitlines()]
         exp_rows = [r.split("\t") for r in case["text"]["tsv"].splitlines()]

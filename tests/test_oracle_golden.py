@@ -176,6 +176,24 @@ def test_quantile_linear_matches_numpy():
 
 
 # ---------------------------------------------------------------- reference-generated fixtures
+def test_dd_kat():  # tests/stats/test_dd_statistic.py:25-46
+    ref_gts = np.array([[1, 1], [0, 0]])
+    tgt_gts = np.array([[1, 0], [0, 1]])
+    src_gts = np.array([[0, 1], [1, 1]])
+    assert np.isclose(orc.dd_statistic(ref_gts, tgt_gts, [src_gts])[0], 0.5)
+
+
+def test_dd_cases_against_reference_outputs():
+    """DD of the 400 random cases (missing calls as -1 / -2, ploidy 1-4) as the
+    reference's DdStatistic (scipy cdist) returned it: bit-exact."""
+    meta = json.load(open(os.path.join(GOLDEN, "stat_cases.json")))
+    arrs = np.load(os.path.join(GOLDEN, "stat_cases.npz"))
+    for c, m in enumerate(meta):
+        mats = [arrs[f"c{c}_g{k}"].astype(np.int64) for k in range(2 + m["n_src"])]
+        got = orc.dd_statistic(mats[0], mats[1], mats[2:])
+        assert [float(v).hex() for v in got] == m["DD"], c
+
+
 def test_stat_cases_against_reference_outputs():
     meta = json.load(open(os.path.join(GOLDEN, "stat_cases.json")))
     arrs = np.load(os.path.join(GOLDEN, "stat_cases.npz"))
