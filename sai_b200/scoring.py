@@ -373,6 +373,59 @@ class DeviceScorer:
             )
         )
 
+    def pattern_sums(self, d_pos, d_ws, d_we, ref_pop: int, tgt_pop: int, out_pop: int, src_pops: Sequence[int]):
+        """N3 from the cached counts (``site_counts`` / ``site_flags(with_counts=True)`` first):
+        float64 tensor ``[n_src, W, 7]``."""
+        if self.num is None:
+            raise RuntimeError("site_counts() has not been run")
+        torch = self.torch
+        sums = torch.zeros((len(src_pops), self.W, 7), dtype=torch.float64, device=self.device)
+        src = (C.c_int32 * len(src_pops))(*[int(x) for x in src_pops])
+        _cabi.check(
+            self.lib.sai_window_patterns(
+                C.byref(self.layout), d_pos.data_ptr(), self.n_sites, d_ws.data_ptr(), d_we.data_ptr(), self.W,
+                self.num.data_ptr(), self.called.data_ptr(), self.stride, int(ref_pop), int(tgt_pop), int(out_pop),
+                src, len(src_pops), sums.data_ptr(), self._stream(),
+            )
+        )
+        return sums
+
+    def site_hist(self, d_packed, pops: Sequence[int]):
+        """N4 genotype pass: per-site value histograms of ``pops`` -> int32 ``[rows, stride]``
+        and the missing-call totals (uint64 as int64 tensor ``[len(pops)]``)."""
+        torch = self.torch
+        arr = (C.c_int32 * len(pops))(*[int(x) for x in pops])
+        rows = int(self.lib.sai_hist_rows(C.byref(self.layout), arr, len(pops)))
+        hist = torch.zeros((rows, max(1, self.stride)), dtype=torch.int32, device=self.device)
+        missing = torch.zeros(len(pops), dtype=torch.int64, device=self.device)
+        _cabi.check(
+            self.lib.sai_site_hist(C.byref(self.layout), d_packed.data_ptr(), self.n_sites, arr, len(pops),
+                                   hist.data_ptr(), self.stride, missing.data_ptr(), self._stream())
+        )
+        return hist, missing
+
+    def dd_sums(self, d_packed, d_pos, d_ws, d_we, hist, ref_pop: int, tgt_pop: int, src_pops: Sequence[int],
+                neg_off: np.ndarray, d_neg_site, d_neg_ind, d_neg_val):
+        """N4 window kernel on ``hist = site_hist(d_packed, [ref_pop, tgt_pop])[0]``: int64 tensors
+        ``(ref_sum, tgt_sum)`` ``[n_src, W, m_max]`` and the int32 error flag tensor."""
+        torch = self.torch
+        m_max = max(int(self.layout.pop[int(s)].n_samples) for s in src_pops)
+        ref_sum = torch.zeros((len(src_pops), self.W, m_max), dtype=torch.int64, device=self.device)
+        tgt_sum = torch.zeros_like(ref_sum)
+        err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        src = (C.c_int32 * len(src_pops))(*[int(x) for x in src_pops])
+        off = np.ascontiguousarray(neg_off, dtype=np.int64)
+        ptr = lambda t: t.data_ptr() if t is not None and t.numel() else None
+        _cabi.check(
+            self.lib.sai_window_dd(
+                C.byref(self.layout), d_packed.data_ptr(), d_pos.data_ptr(), self.n_sites, d_ws.data_ptr(),
+                d_we.data_ptr(), self.W, hist.data_ptr(), self.stride, int(ref_pop), int(tgt_pop), src, len(src_pops),
+                off.ctypes.data, ptr(d_neg_site), ptr(d_neg_ind), ptr(d_neg_val), ref_sum.data_ptr(),
+                tgt_sum.data_ptr(), m_max, err.data_ptr(), self._stream(),
+            )
+        )
+        return ref_sum, tgt_sum, err
+
     def step(self, d_packed, d_pos, d_ws, d_we, jobs, variant: int = 0):
         """One pass of the hot path over device-resident inputs: the genotype
         pass and the window kernel (2 launches + one 16-byte memset)."""

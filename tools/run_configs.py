@@ -3,6 +3,7 @@
 
     python tools/run_configs.py --config 3            # two sources, haploid + diploid, missing, both anc modes
     python tools/run_configs.py --config 5            # threshold / window sweep on a 20k-sample cohort (cached counts)
+    python tools/run_configs.py --config 6            # all seven statistics incl. DD, missing calls
     torchrun --nproc-per-node N tools/run_configs.py --config 4   # 22 autosomes, 80 M sites, sharded by window range
                                                                   # + genome-wide `sai outlier` thresholds
 
@@ -283,10 +284,75 @@ def config4(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------
+def config6(args):
+    """All seven statistics (U, Q, Danc, Dplus, df, fd, DD) on one chromosome-scale matrix with missing calls:
+    per-kernel times and oracle spot checks (the DD sums are exact integers)."""
+    from sai_b200.encode import negative_table
+    from sai_b200.scoring import dd_values, four_pop_values
+
+    S = args.sites or 1_000_000
+    n_ind = [1500, 1000, 4, 2]
+    lay = make_layout(n_ind, [2, 2, 2, 2], [2, 2, 2, 2])
+    d_packed = device_matrix(lay, S, [0, 1, 2, 0], 20261018 + 6, 0.002)
+    pos = positions(S, 41.5, 6)
+    d_pos = torch.from_numpy(pos).cuda()
+    wins = split_genome([int(pos[0]), int(pos[-1])], 50_000, 10_000)
+    d_ws, d_we = dev_windows(wins)
+    # the device generator only knows one missing code: give every missing call a raw value (-1 = "0/.",
+    # -2 = "./.") and build the negative-value table from the decoded matrix
+    pg_all = PackedGenotypes(lay, S, pos, d_packed.cpu().numpy())
+    mats = [unpack_population(pg_all, p) for p in range(lay.n_pops)]  # int8
+    rng = np.random.default_rng(6)
+    for m in mats:
+        neg = m < 0
+        m[neg] = np.where(rng.random(int(neg.sum())) < 0.5, -1, -2)
+    off, n_site, n_ind_, n_val = negative_table(mats)
+    d_neg = [torch.from_numpy(a).cuda() for a in (n_site, n_ind_, n_val)]
+    u_kw = dict(w=0.01, x=0.5, y_list=[("=", 1.0)])
+    q_kw = dict(w=0.01, quantile=0.95, y_list=[("=", 1.0)])
+    job = make_job(0, 1, [2], True, u=u_kw, q=q_kw)
+    sc = DeviceScorer(lay, S, len(wins), 1, cap_u=1 << 20, cap_q=1 << 21)
+    t = {}
+    t["site_flags+counts"] = timed(lambda: sc.site_flags(d_packed, [job], with_counts=True))
+    t["window_stats"] = timed(lambda: sc.window_stats(d_pos, d_ws, d_we, [job]))
+    t["window_patterns"] = timed(lambda: sc.pattern_sums(d_pos, d_ws, d_we, 0, 1, 3, [2]))
+    t["site_hist"] = timed(lambda: sc.site_hist(d_packed, [0, 1]))
+    hist, missing = sc.site_hist(d_packed, [0, 1])
+    t["window_dd"] = timed(lambda: sc.dd_sums(d_packed, d_pos, d_ws, d_we, hist, 0, 1, [2], off, *d_neg))
+    res = sc.results()
+    sums = sc.pattern_sums(d_pos, d_ws, d_we, 0, 1, 3, [2]).cpu().numpy()
+    ref_sum, tgt_sum, err = sc.dd_sums(d_packed, d_pos, d_ws, d_we, hist, 0, 1, [2], off, *d_neg)
+    assert int(err.item()) == 0
+    assert missing.cpu().tolist() == [int(off[1] - off[0]), int(off[2] - off[1])]
+    four = four_pop_values(sums)
+    dd = dd_values(ref_sum.cpu().numpy(), tgt_sum.cpu().numpy(), n_ind[0], n_ind[1], [n_ind[2]])
+    checked = 0
+    for i in np.linspace(0, len(wins) - 1, 10).astype(int):
+        s, e = wins[i]
+        keep = (pos >= s) & (pos <= e)
+        if not keep.any():
+            continue
+        sub = [m[keep].astype(np.int64) for m in mats]
+        assert res.nsnps[0, i] == keep.sum()
+        assert res.u[0, i] == orc.u_statistic(sub[0], sub[1], [sub[2]], 2, 2, [2], pos=pos[keep], anc_allele_available=True, **u_kw)["value"]
+        eq = orc.q_statistic(sub[0], sub[1], [sub[2]], 2, 2, [2], pos=pos[keep], anc_allele_available=True, **q_kw)["value"]
+        assert (np.isnan(eq) and np.isnan(res.q[0, i])) or res.q[0, i] == float(eq)
+        assert float(dd[0][i]).hex() == float(orc.dd_statistic(sub[0], sub[1], [sub[2]])[0]).hex(), i
+        ef = orc.four_pop_statistics(sub[0], sub[1], [sub[2]], 2, 2, [2], out_gts=sub[3], out_ploidy=2)
+        for name in ("Danc", "Dplus", "df", "fd"):
+            a, b = four[name][0][i], ef[name][0]
+            assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= 1e-12 * max(1.0, abs(b)), (name, i, a, b)
+        checked += 1
+    print(json.dumps(dict(config="all-statistics", n_sites=S, n_samples=sum(n_ind), windows=len(wins),
+                          missing_calls=int(off[-1]), ms={k: round(v, 4) for k, v in t.items()},
+                          oracle_windows_checked=checked)))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True, choices=[3, 4, 5])
+    ap.add_argument("--config", type=int, required=True, choices=[3, 4, 5, 6])
     ap.add_argument("--sites", type=int, default=None)
     ap.add_argument("--dump", action="store_true")
     a = ap.parse_args()
-    {3: config3, 4: config4, 5: config5}[a.config](a)
+    {3: config3, 4: config4, 5: config5, 6: config6}[a.config](a)
