@@ -260,6 +260,32 @@ int sai_window_dd(const sai_layout* lay, const void* d_packed, const int32_t* d_
                   int64_t* d_ref_sum, int64_t* d_tgt_sum, int32_t m_max, int32_t* d_err,
                   void* stream);
 
+/* ---- zt: zero-suppressed tiles, the host->device wire format --------------- */
+/* End to end the path is bound by the PCIe copy of the packed tiles, and most of a genotype
+ * matrix is the hom-ref code 0.  The zt stream holds, per tile (P = pairs_per_site rows of 32
+ * pairs), at byte offset tile_off[T] & ~SAI_ZT_RAW (8-byte aligned):
+ *     u32 n1        non-zero pairs of the tile
+ *     u32 nz[P]     bit s of nz[r]: pair (row r, site s) is non-zero
+ *     u8  mask[n1]  per non-zero pair in (r, s) order: bit k = byte k of the pair is non-zero
+ *     u8  data[..]  the non-zero bytes in the same order, ascending k
+ * where "pair" = stored pair XOR the row's padding constant (ones for the unused individuals
+ * of a population's last group).  A tile that would not shrink is stored as its P*256 raw
+ * bytes, flagged by SAI_ZT_RAW in tile_off[T]; tile_off[n_tiles] = stream length.
+ * Lossless: sai_zt_decode(sai_zt_encode(x)) == x bit for bit. */
+#define SAI_ZT_RAW (1ull << 63)
+uint64_t sai_zt_bound(const sai_layout* lay, int64_t n_sites); /* upper bound of the stream length */
+/* Host: packed tiles -> stream + tile_off[n_tiles + 1].  Returns the stream length or a
+ * negative SAI_E_* code (SAI_E_CAPACITY: out_cap too small). */
+int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_sites, uint8_t* out,
+                      uint64_t out_cap, uint64_t* tile_off, int32_t n_threads);
+/* Host decoder (tests, tools). */
+int sai_zt_decode_host(const sai_layout* lay, const uint8_t* stream, const uint64_t* tile_off,
+                       int64_t n_sites, uint8_t* packed);
+/* Device: rebuilds dense tiles [tile0, tile0 + n_tiles) of d_packed (tile 0 based) from the
+ * stream resident at d_stream (offset 0 based) and its directory d_tile_off. */
+int sai_zt_decode(const sai_layout* lay, const void* d_stream, const uint64_t* d_tile_off,
+                  int64_t tile0, int64_t n_tiles, void* d_packed, void* stream);
+
 /* ---- host-buffer engine (replaces ChunkPreprocessor.run's inner loop) ----- */
 typedef struct sai_engine sai_engine;
 int sai_engine_create(int32_t device, sai_engine** out);
@@ -287,6 +313,14 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
                           const int32_t* pos, int64_t n_sites, const int64_t* win_start,
                           const int64_t* win_end, int64_t n_windows, const sai_job* jobs,
                           int32_t n_jobs, sai_host_results* out);
+
+/* Same as sai_engine_score_host with the tiles in zt form (HOST stream + HOST directory):
+ * the stream is copied in ~32 MB slices, each slice is expanded to dense tiles on the device
+ * and flagged while the next slice is on the wire. */
+int sai_engine_score_host_zt(sai_engine* e, const sai_layout* lay, const uint8_t* zt_stream,
+                             const uint64_t* zt_tile_off, const int32_t* pos, int64_t n_sites,
+                             const int64_t* win_start, const int64_t* win_end, int64_t n_windows,
+                             const sai_job* jobs, int32_t n_jobs, sai_host_results* out);
 
 /* After SAI_E_CAPACITY: re-runs only the window kernel on the flags still
  * resident on the device, with the (larger) buffers of `out`. */

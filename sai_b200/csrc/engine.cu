@@ -20,7 +20,7 @@ struct sai_engine {
     void* p = nullptr;
     size_t cap = 0;
   };
-  Buf packed, pos, win, mask, qval, res, cand, counts, sums, hist, neg, dd;
+  Buf packed, pos, win, mask, qval, res, cand, counts, sums, hist, neg, dd, zt, ztoff;
   // state of the last call (for sai_engine_rescore_windows)
   int64_t n_sites = 0, W = 0;
   int32_t n_jobs = 0;
@@ -152,7 +152,7 @@ int sai_engine_create(int32_t device, sai_engine** out) {
 void sai_engine_destroy(sai_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  for (auto* b : {&e->packed, &e->pos, &e->win, &e->mask, &e->qval, &e->res, &e->cand, &e->counts, &e->sums, &e->hist, &e->neg, &e->dd})
+  for (auto* b : {&e->packed, &e->pos, &e->win, &e->mask, &e->qval, &e->res, &e->cand, &e->counts, &e->sums, &e->hist, &e->neg, &e->dd, &e->zt, &e->ztoff})
     if (b->p) cudaFree(b->p);
   for (auto ev : e->ev) cudaEventDestroy(ev);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
@@ -160,15 +160,17 @@ void sai_engine_destroy(sai_engine* e) {
   delete e;
 }
 
-int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* packed,
-                          const int32_t* pos, int64_t n_sites, const int64_t* win_start,
-                          const int64_t* win_end, int64_t n_windows, const sai_job* jobs,
-                          int32_t n_jobs, sai_host_results* out) {
+// Shared body of the two host entry points: `packed` (dense tiles) or, when
+// `zt_stream` is given, the zero-suppressed stream + its tile directory.
+static int score_host_impl(sai_engine* e, const sai_layout* lay, const uint8_t* packed,
+                           const uint8_t* zt_stream, const uint64_t* zt_off, const int32_t* pos,
+                           int64_t n_sites, const int64_t* win_start, const int64_t* win_end,
+                           int64_t n_windows, const sai_job* jobs, int32_t n_jobs, sai_host_results* out) {
   SAI_REQUIRE(e, "NULL engine");
   if (int rc = validate_layout(lay)) return rc;
   if (int rc = validate_jobs(lay, jobs, n_jobs)) return rc;
   SAI_REQUIRE(n_sites >= 0 && n_windows >= 0, "negative size");
-  SAI_REQUIRE(n_sites == 0 || (packed && pos), "NULL input");
+  SAI_REQUIRE(n_sites == 0 || ((packed || (zt_stream && zt_off)) && pos), "NULL input");
   SAI_REQUIRE(n_windows == 0 || (win_start && win_end), "NULL windows");
   if (int rc = check_results(out)) return rc;
   SAI_CUDA_CHECK(cudaSetDevice(e->device));
@@ -177,6 +179,9 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
   const int64_t stride = n_tiles * kTile;
   const size_t packed_bytes = sai_packed_bytes(lay, n_sites);
   const ResLayout rl = res_layout(W, n_jobs);
+  const bool zt = zt_stream != nullptr && n_sites > 0;
+  const uint64_t kRaw = 1ull << 63;
+  const uint64_t zt_bytes = zt ? (zt_off[n_tiles] & ~kRaw) : 0;
 
   if (int rc = grow(e->packed, packed_bytes + 256)) return rc;
   if (int rc = grow(e->pos, sizeof(int32_t) * (size_t)stride + 256)) return rc;
@@ -184,6 +189,10 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
   if (int rc = grow(e->mask, sizeof(uint32_t) * 2 * (size_t)n_jobs * n_tiles + 256)) return rc;
   if (int rc = grow(e->qval, sizeof(double) * (size_t)n_jobs * stride + 256)) return rc;
   if (int rc = grow(e->res, rl.total + 256)) return rc;
+  if (zt) {
+    if (int rc = grow(e->zt, zt_bytes + 256)) return rc;
+    if (int rc = grow(e->ztoff, sizeof(uint64_t) * (size_t)(n_tiles + 1) + 256)) return rc;
+  }
   e->n_sites = n_sites;
   e->W = W;
   e->n_jobs = n_jobs;
@@ -202,22 +211,53 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
     SAI_CUDA_CHECK(cudaMemcpyAsync(d_ws, win_start, sizeof(int64_t) * W, cudaMemcpyHostToDevice, e->s_copy));
     SAI_CUDA_CHECK(cudaMemcpyAsync(d_ws + W, win_end, sizeof(int64_t) * W, cudaMemcpyHostToDevice, e->s_copy));
   }
-  // sliced H2D of the packed tiles, K1 per slice as soon as it has landed
+  if (zt)
+    SAI_CUDA_CHECK(cudaMemcpyAsync(e->ztoff.p, zt_off, sizeof(uint64_t) * (size_t)(n_tiles + 1),
+                                   cudaMemcpyHostToDevice, e->s_copy));
+  // sliced H2D of the tiles (about 32 MB on the wire per slice); per slice, as soon as it has
+  // landed: [zt: rebuild the dense tiles,] then K1
   const size_t tile_bytes = (size_t)lay->pairs_per_site * kTile * 8;
-  const int64_t slice_tiles = std::max<int64_t>(1, (int64_t)((32ull << 20) / tile_bytes));
-  const int64_t n_slices = (n_tiles + slice_tiles - 1) / slice_tiles;
+  const uint64_t slice_bytes = 32ull << 20;
+  std::vector<int64_t> cut{0};
+  if (!zt) {
+    const int64_t slice_tiles = std::max<int64_t>(1, (int64_t)(slice_bytes / tile_bytes));
+    for (int64_t t = slice_tiles; t < n_tiles; t += slice_tiles) cut.push_back(t);
+  } else {
+    uint64_t start = 0;
+    for (int64_t t = 1; t < n_tiles; ++t) {
+      const uint64_t o = zt_off[t] & ~kRaw;
+      SAI_REQUIRE(o >= (zt_off[t - 1] & ~kRaw) && o <= zt_bytes, "zt tile directory is not monotonic");
+      if (o - start >= slice_bytes) {
+        cut.push_back(t);
+        start = o;
+      }
+    }
+  }
+  if (n_tiles > 0) cut.push_back(n_tiles);
+  const int64_t n_slices = (int64_t)cut.size() - 1;
   while ((int64_t)e->ev.size() < n_slices + 1) {
     cudaEvent_t ev;
     SAI_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     e->ev.push_back(ev);
   }
   for (int64_t s = 0; s < n_slices; ++s) {
-    const int64_t t0 = s * slice_tiles, t1 = std::min(n_tiles, t0 + slice_tiles);
-    SAI_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(e->packed.p) + t0 * tile_bytes,
-                                   packed + t0 * tile_bytes, (size_t)(t1 - t0) * tile_bytes,
-                                   cudaMemcpyHostToDevice, e->s_copy));
+    const int64_t t0 = cut[s], t1 = cut[s + 1];
+    if (!zt) {
+      SAI_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(e->packed.p) + t0 * tile_bytes,
+                                     packed + t0 * tile_bytes, (size_t)(t1 - t0) * tile_bytes,
+                                     cudaMemcpyHostToDevice, e->s_copy));
+    } else {
+      const uint64_t b0 = zt_off[t0] & ~kRaw, b1 = zt_off[t1] & ~kRaw;
+      if (b1 > b0)
+        SAI_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(e->zt.p) + b0, zt_stream + b0, b1 - b0,
+                                       cudaMemcpyHostToDevice, e->s_copy));
+    }
     SAI_CUDA_CHECK(cudaEventRecord(e->ev[s], e->s_copy));
     SAI_CUDA_CHECK(cudaStreamWaitEvent(e->s_comp, e->ev[s], 0));
+    if (zt)
+      if (int rc = sai_zt_decode(lay, e->zt.p, static_cast<const uint64_t*>(e->ztoff.p), t0, t1 - t0,
+                                 e->packed.p, e->s_comp))
+        return rc;
     if (int rc = sai_site_flags(lay, e->packed.p, t0, t1 - t0, n_tiles, jobs, n_jobs, d_mask_u,
                                 d_mask_q, d_qval, stride, nullptr, nullptr, 0, 0, e->s_comp))
       return rc;
@@ -225,6 +265,24 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
   SAI_CUDA_CHECK(cudaEventRecord(e->ev[n_slices], e->s_copy));
   SAI_CUDA_CHECK(cudaStreamWaitEvent(e->s_comp, e->ev[n_slices], 0));
   return run_windows(e, out);
+}
+
+int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* packed,
+                          const int32_t* pos, int64_t n_sites, const int64_t* win_start,
+                          const int64_t* win_end, int64_t n_windows, const sai_job* jobs,
+                          int32_t n_jobs, sai_host_results* out) {
+  SAI_REQUIRE(n_sites <= 0 || packed, "NULL input");
+  return score_host_impl(e, lay, packed, nullptr, nullptr, pos, n_sites, win_start, win_end, n_windows, jobs,
+                         n_jobs, out);
+}
+
+int sai_engine_score_host_zt(sai_engine* e, const sai_layout* lay, const uint8_t* zt_stream,
+                             const uint64_t* zt_tile_off, const int32_t* pos, int64_t n_sites,
+                             const int64_t* win_start, const int64_t* win_end, int64_t n_windows,
+                             const sai_job* jobs, int32_t n_jobs, sai_host_results* out) {
+  SAI_REQUIRE(n_sites <= 0 || (zt_stream && zt_tile_off), "NULL input");
+  return score_host_impl(e, lay, nullptr, zt_stream, zt_tile_off, pos, n_sites, win_start, win_end, n_windows,
+                         jobs, n_jobs, out);
 }
 
 int sai_engine_pattern_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, int32_t tgt_pop,

@@ -1,0 +1,293 @@
+// "zt": zero-suppressed packed tiles -- the wire format between host memory and HBM.
+//
+// End to end the scoring path is bound by the host->device copy of the packed
+// tiles (PCIe Gen5: ~53 GB/s against 6.4 TB/s for the genotype pass), and most
+// of a genotype matrix is the homozygous-reference code 0: with a realistic
+// site-frequency spectrum most sites are rare variants.  The host therefore
+// sends a two-level zero-suppressed form of every tile and a kernel rebuilds
+// the dense tiles in HBM (include/sai_b200.h "Packed genotype layout"); the
+// genotype pass and everything behind it run on the dense tiles, unchanged.
+//
+// Record of tile T (P = pairs_per_site rows of 32 pairs, one pair per site) at
+// byte offset tile_off[T] & ~SAI_ZT_RAW of the stream (8-byte aligned):
+//     u32 n1                 number of non-zero pairs of the tile
+//     u32 nz[P]              bit s of nz[r]: pair (row r, site s) is non-zero
+//     u8  mask[n1]           per non-zero pair, in (r, s) order: bit k = byte k of the pair is non-zero
+//     u8  data[n2]           the non-zero bytes, in the same order, ascending k
+// "Pair" here is the stored pair XOR the row's padding constant (the unused
+// individuals of a population's last group are coded missing, i.e. all-ones in
+// every plane; XOR-ing the constant out makes those bytes zero too).
+// A tile whose record would not be smaller than the dense tile is stored as its
+// P*256 raw bytes and flagged with SAI_ZT_RAW (bit 63) in tile_off[T].
+// tile_off[n_tiles] = total stream length.
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sai {
+
+constexpr uint64_t kZtRaw = 1ull << 63;
+constexpr int kZtWarps = 8;
+
+// padding constant of row (pair index) r: ones for the unused individuals of the
+// population's last group in every plane word of the pair
+__host__ __device__ inline uint64_t pad_constant(const sai_layout& lay, int r) {
+  int pi = 0;
+  while (pi + 1 < lay.n_pops && r >= lay.pop[pi + 1].pair_off) ++pi;
+  const sai_pop_layout& L = lay.pop[pi];
+  uint64_t c = 0;
+  for (int h = 0; h < 2; ++h) {
+    const int word = (r - L.pair_off) * 2 + h;
+    if (word >= L.n_groups * L.bits) continue;  // zero padding word of an odd word count
+    const int real = L.n_samples - 32 * (word / L.bits);
+    const uint32_t bits = real >= 32 ? 0u : (0xffffffffu << real);
+    c |= (uint64_t)bits << (32 * h);
+  }
+  return c;
+}
+
+static inline uint32_t byte_mask(uint64_t v) {  // bit k set iff byte k of v is non-zero
+  const uint64_t lo7 = 0x7f7f7f7f7f7f7f7full;
+  const uint64_t m = (((v & lo7) + lo7) | v) & ~lo7;  // 0x80 in every non-zero byte
+  return (uint32_t)(((m >> 7) * 0x0102040810204080ull) >> 56);
+}
+
+static void run_parallel(int64_t n, int n_threads, const std::function<void(int64_t, int64_t)>& fn) {
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n / 64));
+  if (n_threads <= 1) {
+    fn(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int64_t per = (n + n_threads - 1) / n_threads;
+  for (int i = 0; i < n_threads; ++i) {
+    const int64_t a = i * per, b = std::min<int64_t>(n, a + per);
+    if (a < b) th.emplace_back(fn, a, b);
+  }
+  for (auto& t : th) t.join();
+}
+
+struct ZtDecodeParams {
+  sai_layout lay;
+  const uint8_t* stream;
+  const unsigned long long* tile_off;
+  int64_t tile0, n_tiles;
+  unsigned long long* packed;  // dense tiles, tile 0
+};
+
+// one warp per tile, lane == site
+__global__ void __launch_bounds__(kZtWarps * 32) k_zt_decode(const __grid_constant__ ZtDecodeParams P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pps = P.lay.pairs_per_site;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int64_t t = (int64_t)blockIdx.x * kZtWarps + warp; t < P.n_tiles; t += (int64_t)gridDim.x * kZtWarps) {
+    const int64_t T = P.tile0 + t;
+    const unsigned long long off = __ldg(P.tile_off + T);
+    unsigned long long* out = P.packed + (size_t)T * pps * kTile + lane;
+    const uint8_t* rec = P.stream + (off & ~kZtRaw);
+    if (off & kZtRaw) {
+      const unsigned long long* in = reinterpret_cast<const unsigned long long*>(rec) + lane;
+      for (int r = 0; r < pps; ++r) out[(size_t)r * kTile] = __ldg(in + (size_t)r * kTile);
+      continue;
+    }
+    const uint32_t n1 = __ldg(reinterpret_cast<const uint32_t*>(rec));
+    const uint32_t* nz = reinterpret_cast<const uint32_t*>(rec + 4);
+    const uint8_t* mask = rec + 4 + 4 * (size_t)pps;
+    const uint8_t* data = mask + n1;
+    uint32_t base1 = 0, base2 = 0;
+    for (int r0 = 0; r0 < pps; r0 += 32) {
+      const uint32_t mine = r0 + lane < pps ? __ldg(nz + r0 + lane) : 0u;
+      const int rows = pps - r0 < 32 ? pps - r0 : 32;
+      for (int rr = 0; rr < rows; ++rr) {
+        const uint32_t w = __shfl_sync(0xffffffffu, mine, rr);
+        const int r = r0 + rr;
+        const unsigned long long padc = pad_constant(P.lay, r);
+        if (w == 0u) {
+          out[(size_t)r * kTile] = padc;
+          continue;
+        }
+        const bool has = (w >> lane) & 1u;
+        uint32_t m = has ? (uint32_t)__ldg(mask + base1 + __popc(w & lt)) : 0u;
+        const int nb = __popc(m);
+        int incl = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += up;
+        }
+        const uint8_t* p = data + base2 + (incl - nb);
+        unsigned long long v = 0;
+        while (m) {
+          const int k = __ffs(m) - 1;
+          m &= m - 1;
+          v |= (unsigned long long)__ldg(p++) << (8 * k);
+        }
+        out[(size_t)r * kTile] = v ^ padc;
+        base1 += __popc(w);
+        base2 += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+  }
+}
+
+}  // namespace sai
+
+using namespace sai;
+
+extern "C" {
+
+uint64_t sai_zt_bound(const sai_layout* lay, int64_t n_sites) {
+  if (!lay || n_sites < 0) return 0;
+  // no record is larger than its dense tile
+  return sai_packed_bytes(lay, n_sites) + 8;
+}
+
+int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_sites, uint8_t* out,
+                      uint64_t out_cap, uint64_t* tile_off, int32_t n_threads) {
+  if (int rc = validate_layout(lay)) return rc;
+  SAI_REQUIRE(n_sites >= 0 && tile_off, "bad argument");
+  const int64_t n_tiles = sai_num_tiles(n_sites);
+  const int P = lay->pairs_per_site;
+  const size_t dense = (size_t)P * kTile * 8;
+  tile_off[0] = 0;
+  if (n_tiles == 0) return 0;
+  SAI_REQUIRE(packed && out, "NULL argument");
+  std::vector<uint64_t> padc(P);
+  for (int r = 0; r < P; ++r) padc[r] = pad_constant(*lay, r);
+  // pass 1: record sizes (tile_off[T + 1] = size of tile T, raw flag kept aside)
+  std::vector<uint8_t> raw(n_tiles);
+  run_parallel(n_tiles, n_threads, [&](int64_t t0, int64_t t1) {
+    for (int64_t T = t0; T < t1; ++T) {
+      const uint64_t* d = reinterpret_cast<const uint64_t*>(packed + (size_t)T * dense);
+      size_t n1 = 0, n2 = 0;
+      for (int r = 0; r < P; ++r) {
+        const uint64_t c = padc[r];
+        for (int s = 0; s < kTile; ++s) {
+          const uint64_t v = d[r * kTile + s] ^ c;
+          if (v) {
+            ++n1;
+            n2 += __builtin_popcount(byte_mask(v));
+          }
+        }
+      }
+      const size_t rec = (4 + 4 * (size_t)P + n1 + n2 + 7) & ~size_t(7);
+      raw[T] = rec >= dense;
+      tile_off[T + 1] = raw[T] ? dense : rec;
+    }
+  });
+  uint64_t at = 0;
+  for (int64_t T = 0; T < n_tiles; ++T) {
+    const uint64_t sz = tile_off[T + 1];
+    tile_off[T] = at | (raw[T] ? kZtRaw : 0ull);
+    at += sz;
+  }
+  tile_off[n_tiles] = at;
+  if (at > out_cap) {
+    set_error("zt stream needs %llu bytes, buffer has %llu", (unsigned long long)at, (unsigned long long)out_cap);
+    return SAI_E_CAPACITY;
+  }
+  // pass 2: write the records
+  run_parallel(n_tiles, n_threads, [&](int64_t t0, int64_t t1) {
+    std::vector<uint8_t> tmp(dense);
+    for (int64_t T = t0; T < t1; ++T) {
+      const uint8_t* src = packed + (size_t)T * dense;
+      uint8_t* rec = out + (tile_off[T] & ~kZtRaw);
+      if (tile_off[T] & kZtRaw) {
+        memcpy(rec, src, dense);
+        continue;
+      }
+      const uint64_t* d = reinterpret_cast<const uint64_t*>(src);
+      uint8_t* mp = rec + 4 + 4 * (size_t)P;
+      uint8_t* dp = tmp.data();
+      uint32_t n1 = 0;
+      for (int r = 0; r < P; ++r) {
+        const uint64_t c = padc[r];
+        uint32_t w = 0;
+        for (int s = 0; s < kTile; ++s) {
+          uint64_t v = d[r * kTile + s] ^ c;
+          if (!v) continue;
+          w |= 1u << s;
+          const uint32_t m = byte_mask(v);
+          mp[n1++] = (uint8_t)m;
+          for (int k = 0; k < 8; ++k, v >>= 8)
+            if (v & 0xff) *dp++ = (uint8_t)v;
+        }
+        memcpy(rec + 4 + 4 * (size_t)r, &w, 4);
+      }
+      memcpy(rec, &n1, 4);
+      const size_t n2 = dp - tmp.data();
+      memcpy(mp + n1, tmp.data(), n2);
+      const size_t used = 4 + 4 * (size_t)P + n1 + n2;
+      const size_t end = (tile_off[T + 1] & ~kZtRaw) - (tile_off[T] & ~kZtRaw);
+      if (end > used) memset(rec + used, 0, end - used);
+    }
+  });
+  return (int64_t)at;
+}
+
+int sai_zt_decode_host(const sai_layout* lay, const uint8_t* stream, const uint64_t* tile_off, int64_t n_sites,
+                       uint8_t* packed) {
+  if (int rc = validate_layout(lay)) return rc;
+  SAI_REQUIRE(n_sites >= 0 && tile_off, "bad argument");
+  const int64_t n_tiles = sai_num_tiles(n_sites);
+  if (n_tiles == 0) return SAI_OK;
+  SAI_REQUIRE(stream && packed, "NULL argument");
+  const int P = lay->pairs_per_site;
+  const size_t dense = (size_t)P * kTile * 8;
+  for (int64_t T = 0; T < n_tiles; ++T) {
+    const uint8_t* rec = stream + (tile_off[T] & ~kZtRaw);
+    uint8_t* dst = packed + (size_t)T * dense;
+    if (tile_off[T] & kZtRaw) {
+      memcpy(dst, rec, dense);
+      continue;
+    }
+    uint32_t n1;
+    memcpy(&n1, rec, 4);
+    const uint8_t* mp = rec + 4 + 4 * (size_t)P;
+    const uint8_t* dp = mp + n1;
+    for (int r = 0; r < P; ++r) {
+      uint32_t w;
+      memcpy(&w, rec + 4 + 4 * (size_t)r, 4);
+      const uint64_t c = pad_constant(*lay, r);
+      for (int s = 0; s < kTile; ++s) {
+        uint64_t v = 0;
+        if ((w >> s) & 1u) {
+          const uint32_t m = *mp++;
+          for (int k = 0; k < 8; ++k)
+            if ((m >> k) & 1u) v |= (uint64_t)(*dp++) << (8 * k);
+        }
+        v ^= c;
+        memcpy(dst + ((size_t)r * kTile + s) * 8, &v, 8);
+      }
+    }
+  }
+  return SAI_OK;
+}
+
+int sai_zt_decode(const sai_layout* lay, const void* d_stream, const uint64_t* d_tile_off, int64_t tile0,
+                  int64_t n_tiles, void* d_packed, void* stream) {
+  if (int rc = validate_layout(lay)) return rc;
+  SAI_REQUIRE(tile0 >= 0 && n_tiles >= 0, "bad tile range");
+  if (n_tiles == 0) return SAI_OK;
+  SAI_REQUIRE(d_stream && d_tile_off && d_packed, "NULL device pointer");
+  ZtDecodeParams P{};
+  P.lay = *lay;
+  P.stream = static_cast<const uint8_t*>(d_stream);
+  P.tile_off = reinterpret_cast<const unsigned long long*>(d_tile_off);
+  P.tile0 = tile0;
+  P.n_tiles = n_tiles;
+  P.packed = static_cast<unsigned long long*>(d_packed);
+  const int64_t want = (n_tiles + kZtWarps - 1) / kZtWarps;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  k_zt_decode<<<(unsigned)(want < cap ? want : cap), kZtWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  SAI_CUDA_CHECK(cudaGetLastError());
+  return SAI_OK;
+}
+
+}  // extern "C"

@@ -156,3 +156,58 @@ def unpack_population(pg: PackedGenotypes, pop: int, site0: int = 0, n: Optional
             )
         )
     return out
+
+
+@dataclass
+class ZtGenotypes:
+    """A packed matrix in zt form (zero-suppressed tiles, include/sai_b200.h "zt"):
+    what goes over PCIe.  Lossless; the device rebuilds the dense tiles."""
+
+    layout: "_cabi.Layout"
+    n_sites: int
+    pos: np.ndarray
+    stream: np.ndarray  # uint8, host
+    tile_off: np.ndarray  # uint64 [n_tiles + 1]
+    pop_names: list = field(default_factory=list)
+    neg_off: Optional[np.ndarray] = None
+    neg_site: Optional[np.ndarray] = None
+    neg_ind: Optional[np.ndarray] = None
+    neg_val: Optional[np.ndarray] = None
+
+    @property
+    def n_tiles(self) -> int:
+        return (self.n_sites + _cabi.TILE_SITES - 1) // _cabi.TILE_SITES
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.stream.nbytes) + int(self.tile_off.nbytes)
+
+
+def compress(pg: PackedGenotypes, n_threads: int = 0, out: Optional[np.ndarray] = None) -> ZtGenotypes:
+    """Packed tiles -> zt stream (host, multi-threaded).  ``out``: optional uint8
+    buffer (e.g. pinned memory) of at least ``sai_zt_bound`` bytes."""
+    lib = _cabi.load()
+    n_tiles = pg.n_tiles
+    tile_off = np.zeros(n_tiles + 1, dtype=np.uint64)
+    bound = int(lib.sai_zt_bound(C.byref(pg.layout), pg.n_sites))
+    buf = np.empty(max(bound, 8), dtype=np.uint8) if out is None else out
+    if buf.dtype != np.uint8 or not buf.flags.c_contiguous:
+        raise ValueError("out must be a contiguous uint8 buffer")
+    n = lib.sai_zt_encode(C.byref(pg.layout), pg.packed.ctypes.data if pg.packed.size else None, pg.n_sites,
+                          buf.ctypes.data, buf.nbytes, tile_off.ctypes.data, n_threads)
+    if n < 0:
+        _cabi.check(int(n))
+    stream = buf[: int(n)] if out is not None else buf[: int(n)].copy()
+    return ZtGenotypes(pg.layout, pg.n_sites, pg.pos, stream, tile_off, list(pg.pop_names),
+                       pg.neg_off, pg.neg_site, pg.neg_ind, pg.neg_val)
+
+
+def decompress(zt: ZtGenotypes) -> PackedGenotypes:
+    """Host decoder (tests / tools): zt stream -> packed tiles."""
+    lib = _cabi.load()
+    nbytes = int(lib.sai_packed_bytes(C.byref(zt.layout), zt.n_sites))
+    packed = np.empty(max(nbytes, 1), dtype=np.uint8)
+    _cabi.check(lib.sai_zt_decode_host(C.byref(zt.layout), zt.stream.ctypes.data if zt.stream.size else None,
+                                       zt.tile_off.ctypes.data, zt.n_sites, packed.ctypes.data))
+    return PackedGenotypes(zt.layout, zt.n_sites, zt.pos, packed[:nbytes], list(zt.pop_names),
+                           zt.neg_off, zt.neg_site, zt.neg_ind, zt.neg_val)

@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _cabi
-from .encode import PackedGenotypes
+from .encode import PackedGenotypes, ZtGenotypes
 
 
 # --------------------------------------------------------------------------
@@ -184,10 +184,16 @@ class HostEngine:
 
         pos = np.ascontiguousarray(pg.pos, dtype=np.int32)
         res = c_results()
-        rc = lib.sai_engine_score_host(
+        if isinstance(pg, ZtGenotypes):  # zero-suppressed wire format: expanded on the device
+            entry = lib.sai_engine_score_host_zt
+            tiles = (pg.stream.ctypes.data if pg.stream.size else None, pg.tile_off.ctypes.data)
+        else:
+            entry = lib.sai_engine_score_host
+            tiles = (pg.packed.ctypes.data if pg.packed.size else None,)
+        rc = entry(
             self._handle(),
             C.byref(pg.layout),
-            pg.packed.ctypes.data if pg.packed.size else None,
+            *tiles,
             pos.ctypes.data if pos.size else None,
             pg.n_sites,
             ws.ctypes.data if W else None,

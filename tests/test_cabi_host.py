@@ -98,6 +98,53 @@ def test_negative_table_for_dd():
     assert pack_populations(mats, [2, 2, 2], np.arange(50)).neg_off is None
 
 
+@pytest.mark.parametrize("shape", ["sparse", "dense", "mixed_bits", "tiny", "empty"])
+def test_zt_roundtrip_host(shape):
+    """encode -> host decode is the identity on the packed tiles (sparse data, dense data that
+    takes the raw-tile escape, 3/4-plane populations with odd word counts, partial last tile)."""
+    from sai_b200.encode import compress, decompress, pack_populations
+
+    rng = np.random.default_rng(21)
+    if shape == "sparse":
+        n, sizes, ploidy = 1000, (300, 90, 4), [2, 2, 2]
+        f = rng.beta(0.2, 2.0, size=n)
+        mats = [rng.binomial(2, f[:, None], size=(n, k)).astype(np.int8) for k in sizes]
+        mats[1][rng.random(mats[1].shape) < 0.002] = -1
+    elif shape == "dense":
+        n, sizes, ploidy = 333, (64, 96, 32), [2, 2, 2]
+        mats = [rng.integers(-1, 3, size=(n, k)).astype(np.int8) for k in sizes]
+    elif shape == "mixed_bits":
+        n, ploidy = 257, [4, 3, 1, 8]
+        sizes = (45, 32, 7, 70)
+        f = rng.beta(0.3, 3.0, size=n)
+        mats = [rng.binomial(p, f[:, None], size=(n, k)).astype(np.int8) for k, p in zip(sizes, ploidy)]
+        mats[3][rng.random(mats[3].shape) < 0.01] = -2
+    elif shape == "tiny":
+        n, sizes, ploidy = 1, (1, 1, 1), [1, 2, 1]
+        mats = [np.zeros((1, 1), np.int8) for _ in sizes]
+    else:
+        n, sizes, ploidy = 0, (5, 3, 1), [2, 2, 2]
+        mats = [np.zeros((0, k), np.int8) for k in sizes]
+    pg = pack_populations(mats, ploidy, np.arange(1, n + 1))
+    zt = compress(pg, n_threads=3)
+    assert zt.tile_off.shape == (pg.n_tiles + 1,) and int(zt.tile_off[-1]) == zt.stream.nbytes
+    back = decompress(zt)
+    assert np.array_equal(back.packed, pg.packed)
+    raw = (zt.tile_off[:-1] >> np.uint64(63)).astype(bool)
+    if shape == "sparse":
+        assert not raw.any() and zt.stream.nbytes < 0.5 * pg.packed.nbytes
+    if shape == "dense":
+        assert raw.all() and zt.stream.nbytes == pg.packed.nbytes
+    if shape == "tiny":  # site 0 is all hom-ref (no payload); sites 1..31 of the tile are coded all-missing
+        assert not raw.any() and 0 < zt.stream.nbytes < pg.packed.nbytes
+    # a buffer that is too small is reported, not overrun
+    if n > 0:
+        from sai_b200 import _cabi
+
+        with pytest.raises(_cabi.SaiError):
+            compress(pg, out=np.empty(16, dtype=np.uint8))
+
+
 def test_pack_rejects_out_of_domain():
     from sai_b200.encode import pack_populations
 
