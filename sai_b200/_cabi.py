@@ -96,7 +96,7 @@ SYMBOLS = {
     "sai_unpack_i8": (C.c_int, [_LAY, _I32, _P, _I64, _I64, _I64, _P, _I64]),
     "sai_vcf_parse_gt": (
         _I64,
-        [C.c_char_p, _I64, C.c_char_p, _I64, _I64, _P, _P, _I32, _P, _P, _I64, _P, _P, _I64, _I64, C.POINTER(_I64), _I32],
+        [_P, _I64, C.c_char_p, _I64, _I64, _P, _P, _I32, _P, _P, _I64, _P, _P, _I64, _I64, C.POINTER(_I64), _I32],
     ),
     "sai_site_counts": (C.c_int, [_LAY, _P, _I64, _I64, _P, _P, _I64, _I32, _P]),
     "sai_site_flags": (

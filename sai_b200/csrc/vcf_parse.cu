@@ -25,6 +25,7 @@ namespace sai {
 
 struct KeptLine {
   const char* samples;  // first character after the FORMAT column
+  const char* line;     // start of the record
   int32_t gt_index;     // position of GT among the ':'-separated FORMAT keys
   int32_t pos;
   bool flip;
@@ -78,6 +79,13 @@ static inline const char* gt_sum(const char* f, const char* lend, int gt_index, 
   return p;
 }
 
+// allele of a one-character token: digit, "." (missing = -1) or kBadAllele
+constexpr int kBadAllele = -100;
+static inline int allele_of(char c) {
+  if (c >= '0' && c <= '9') return c - '0';
+  return c == '.' ? -1 : kBadAllele;
+}
+
 }  // namespace sai
 
 using namespace sai;
@@ -96,7 +104,6 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
   const size_t chrom_len = strlen(chrom);
   const bool region = start <= end;
   const char* const tend = text + len;
-  std::vector<KeptLine> kept;
   // columns sorted so that every line is walked once, left to right
   std::vector<int> order(n_out);
   for (int i = 0; i < n_out; ++i) order[i] = i;
@@ -107,67 +114,104 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
       return SAI_E_ARG;
     }
 
-  // ---- pass 1 (serial, cheap): complete lines, record filter, flip decision ----
-  const char* p = text;
-  while (p < tend && (int64_t)kept.size() < rows_cap) {
-    const void* nl = memchr(p, '\n', (size_t)(tend - p));
-    if (!nl) break;  // incomplete last line: left for the next call
-    const char* lend = static_cast<const char*>(nl);
-    const char* line = p;
-    p = lend + 1;
-    if (lend > line && lend[-1] == '\r') --lend;
-    if (line == lend || *line == '#') continue;
-    const char* t0 = next_tab(line, lend);  // CHROM
-    if ((size_t)(t0 - line) != chrom_len || memcmp(line, chrom, chrom_len) != 0) continue;
-    const char* f = t0 + 1;
-    const char* t1 = next_tab(f, lend);  // POS
-    int64_t pos = 0;
-    for (const char* q = f; q < t1; ++q) pos = pos * 10 + (*q - '0');
-    if (region && (pos < start || pos > end)) continue;
-    const char* t2 = next_tab(t1 + 1, lend);  // ID
-    const char* ref = t2 + 1;
-    const char* t3 = next_tab(ref, lend);  // REF
-    const char* alt = t3 + 1;
-    const char* t4 = next_tab(alt, lend);  // ALT
-    const void* comma = memchr(alt, ',', (size_t)(t4 - alt));
-    const char* alt_end = comma ? static_cast<const char*>(comma) : t4;  // alt_number=1: first ALT
-    bool flip = false;
-    if (n_anc > 0) {
-      const int32_t* it = std::lower_bound(anc_pos, anc_pos + n_anc, (int32_t)pos);
-      if (it == anc_pos + n_anc || *it != (int32_t)pos) continue;  // no ancestral allele: dropped
-      const char* a = anc_allele + 8 * (it - anc_pos);
-      const size_t alen = strnlen(a, 8);
-      const bool is_ref = (size_t)(t3 - ref) == alen && memcmp(a, ref, alen) == 0;
-      const bool is_alt = (size_t)(alt_end - alt) == alen && memcmp(a, alt, alen) == 0;
-      if (!is_ref && !is_alt) continue;
-      flip = is_alt;  // utils.py:523-524
-    }
-    const char* t5 = next_tab(t4 + 1, lend);   // QUAL
-    const char* t6 = next_tab(t5 + 1, lend);   // FILTER
-    const char* t7 = next_tab(t6 + 1, lend);   // INFO
-    const char* fmt = t7 + 1;
-    const char* t8 = next_tab(fmt, lend);      // FORMAT
-    int gi = 0;
-    {
-      int k = 0;
-      const char* q = fmt;
-      bool found = false;
-      while (q < t8) {
-        const void* c = memchr(q, ':', (size_t)(t8 - q));
-        const char* ke = c ? static_cast<const char*>(c) : t8;
-        if (ke - q == 2 && q[0] == 'G' && q[1] == 'T') {
-          gi = k;
-          found = true;
-          break;
-        }
-        q = ke + 1;
-        ++k;
+  // ---- pass 1 (parallel over byte segments cut at line starts): complete lines, record
+  //      filter, flip decision ----
+  const void* last_nl = len > 0 ? memrchr(text, '\n', (size_t)len) : nullptr;
+  const char* const complete_end = last_nl ? static_cast<const char*>(last_nl) + 1 : text;  // incomplete last line: next call
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  const int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, (complete_end - text) / (1 << 20)));
+  std::vector<const char*> seg(n_seg + 1);
+  seg[0] = text;
+  seg[n_seg] = complete_end;
+  for (int i = 1; i < n_seg; ++i) {
+    const char* guess = text + (complete_end - text) / n_seg * i;
+    if (guess < seg[i - 1]) guess = seg[i - 1];
+    const void* nl = guess < complete_end ? memchr(guess, '\n', (size_t)(complete_end - guess)) : nullptr;
+    seg[i] = nl ? static_cast<const char*>(nl) + 1 : complete_end;
+  }
+  std::vector<std::vector<KeptLine>> seg_kept(n_seg);
+  auto scan = [&](int si) {
+    std::vector<KeptLine>& kept = seg_kept[si];
+    const char* p = seg[si];
+    const char* const send = seg[si + 1];
+    while (p < send) {
+      const void* nl = memchr(p, '\n', (size_t)(send - p));
+      if (!nl) break;
+      const char* lend = static_cast<const char*>(nl);
+      const char* line = p;
+      p = lend + 1;
+      if (lend > line && lend[-1] == '\r') --lend;
+      if (line == lend || *line == '#') continue;
+      const char* t0 = next_tab(line, lend);  // CHROM
+      if ((size_t)(t0 - line) != chrom_len || memcmp(line, chrom, chrom_len) != 0) continue;
+      const char* f = t0 + 1;
+      const char* t1 = next_tab(f, lend);  // POS
+      int64_t pos = 0;
+      for (const char* q = f; q < t1; ++q) pos = pos * 10 + (*q - '0');
+      if (region && (pos < start || pos > end)) continue;
+      const char* t2 = next_tab(t1 + 1, lend);  // ID
+      const char* ref = t2 + 1;
+      const char* t3 = next_tab(ref, lend);  // REF
+      const char* alt = t3 + 1;
+      const char* t4 = next_tab(alt, lend);  // ALT
+      const void* comma = memchr(alt, ',', (size_t)(t4 - alt));
+      const char* alt_end = comma ? static_cast<const char*>(comma) : t4;  // alt_number=1: first ALT
+      bool flip = false;
+      if (n_anc > 0) {
+        const int32_t* it = std::lower_bound(anc_pos, anc_pos + n_anc, (int32_t)pos);
+        if (it == anc_pos + n_anc || *it != (int32_t)pos) continue;  // no ancestral allele: dropped
+        const char* a = anc_allele + 8 * (it - anc_pos);
+        const size_t alen = strnlen(a, 8);
+        const bool is_ref = (size_t)(t3 - ref) == alen && memcmp(a, ref, alen) == 0;
+        const bool is_alt = (size_t)(alt_end - alt) == alen && memcmp(a, alt, alen) == 0;
+        if (!is_ref && !is_alt) continue;
+        flip = is_alt;  // utils.py:523-524
       }
-      if (!found) gi = 0;
+      const char* t5 = next_tab(t4 + 1, lend);   // QUAL
+      const char* t6 = next_tab(t5 + 1, lend);   // FILTER
+      const char* t7 = next_tab(t6 + 1, lend);   // INFO
+      const char* fmt = t7 + 1;
+      const char* t8 = next_tab(fmt, lend);      // FORMAT
+      int gi = 0;
+      {
+        int k = 0;
+        const char* q = fmt;
+        bool found = false;
+        while (q < t8) {
+          const void* c = memchr(q, ':', (size_t)(t8 - q));
+          const char* ke = c ? static_cast<const char*>(c) : t8;
+          if (ke - q == 2 && q[0] == 'G' && q[1] == 'T') {
+            gi = k;
+            found = true;
+            break;
+          }
+          q = ke + 1;
+          ++k;
+        }
+        if (!found) gi = 0;
+      }
+      if (t8 >= lend) continue;  // no sample columns
+      kept.push_back(KeptLine{t8 + 1, line, gi, (int32_t)pos, flip});
     }
-    if (t8 >= lend) continue;  // no sample columns
-    kept.push_back(KeptLine{t8 + 1, gi, (int32_t)pos, flip});
-    (void)lend;
+  };
+  if (n_seg == 1) {
+    scan(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_seg; ++i) th.emplace_back(scan, i);
+    for (auto& t : th) t.join();
+  }
+  std::vector<KeptLine> kept;
+  {
+    size_t total = 0;
+    for (auto& v : seg_kept) total += v.size();
+    kept.reserve(total);
+    for (auto& v : seg_kept) kept.insert(kept.end(), v.begin(), v.end());
+  }
+  const char* p = complete_end;
+  if ((int64_t)kept.size() > rows_cap) {  // output full: stop in front of the first record that does not fit
+    p = kept[rows_cap].line;
+    kept.resize(rows_cap);
   }
   *bytes_consumed = (int64_t)(p - text);
   const int64_t n_rows = (int64_t)kept.size();
@@ -183,12 +227,17 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
       const char* lend = nl ? static_cast<const char*>(nl) : tend;
       if (lend > K.samples && lend[-1] == '\r') --lend;
       const char* f = K.samples;  // start of sample column `col`
+      const char* fe = nullptr;   // end of the field at f (its tab or lend) when already known
       int col = 0;
       bool have = f < lend;  // a field exists at f
       for (int oi = 0; oi < n_out; ++oi) {
         const int o = order[oi];
         const int want = sample_column[o];
         while (col < want && have) {
+          if (fe) {
+            f = fe;
+            fe = nullptr;
+          }
           while (f < lend && *f != '\t') ++f;
           if (f < lend) {
             ++f;
@@ -201,11 +250,32 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
           row[o] = (int8_t)(-sample_ploidy[o]);  // column absent: all alleles missing
           continue;
         }
-        gt_sum(f, lend, K.gt_index, sample_ploidy[o], K.flip, &row[o]);  // f stays: a column may be requested twice
+        // fast paths for the overwhelmingly common fields "a|b" / "a/b" (diploid) and "a"
+        // (haploid) with single-character alleles and GT first in FORMAT
+        const int ploidy = sample_ploidy[o];
+        if (K.gt_index == 0 && ploidy <= 2) {
+          const int len = ploidy == 2 ? 3 : 1;
+          if (f + len <= lend) {
+            const char e = f + len < lend ? f[len] : '\t';
+            const int a0 = allele_of(f[0]);
+            const int a1 = ploidy == 2 ? allele_of(f[2]) : 0;
+            const bool sep = ploidy == 1 || f[1] == '|' || f[1] == '/';
+            if (sep && a0 != kBadAllele && a1 != kBadAllele && (e == '\t' || e == ':')) {
+              int x0 = a0, x1 = a1;
+              if (K.flip) {
+                x0 = x0 > 0 ? x0 - 1 : 1 - x0;
+                x1 = x1 > 0 ? x1 - 1 : 1 - x1;
+              }
+              row[o] = (int8_t)(ploidy == 2 ? x0 + x1 : x0);
+              if (e == '\t') fe = f + len;  // the field ends right here
+              continue;
+            }
+          }
+        }
+        fe = gt_sum(f, lend, K.gt_index, ploidy, K.flip, &row[o]);  // f stays: a column may be requested twice
       }
     }
   };
-  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
   n_threads = (int)std::min<int64_t>(n_threads, n_rows);
   if (n_threads <= 1) {
     work(0, n_rows);

@@ -26,6 +26,7 @@ covers plain-text and gzip/bgzip VCF.
 from __future__ import annotations
 
 import gzip
+import os
 import warnings
 from typing import Optional
 
@@ -235,57 +236,81 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
     n_out = len(requests)
     consumed = C.c_int64(0)
     region = (start, end) if (start is not None and end is not None) else (1, 0)
-    opener = gzip.open if _is_gzip(vcf_file) else open
-    with opener(vcf_file, "rb") as f:
-        carry = b""
-        while True:
-            block = f.read(chunk_bytes)
-            data = carry + block
-            if not data:
+    def header_columns(line: bytes):
+        names = line.decode().rstrip("\r").split("\t")[9:]
+        index = {n: i for i, n in enumerate(names)}
+        return (np.ascontiguousarray([index[s] for s, _ in requests], dtype=np.int32),  # KeyError like list.index
+                np.ascontiguousarray([p for _, p in requests], dtype=np.int32))
+
+    def parse_buffer(addr: int, length: int) -> int:
+        """Parses complete lines of ``length`` bytes at ``addr``; returns the bytes consumed."""
+        at = 0
+        while at < length:
+            cap = max(1024, min(1 << 20, (length - at) // max(64, 2 * n_out) + 16))
+            out_pos = np.empty(cap, dtype=np.int32)
+            out_gt = np.empty((cap, n_out), dtype=np.int8)
+            n = lib.sai_vcf_parse_gt(
+                addr + at, length - at, chr_name.encode(), region[0], region[1],
+                cols.ctypes.data, ploidies.ctypes.data, n_out,
+                anc_pos.ctypes.data if n_anc else None, anc_buf if n_anc else None, n_anc,
+                out_pos.ctypes.data, out_gt.ctypes.data, n_out, cap, C.byref(consumed), n_threads,
+            )
+            if n < 0:
+                _cabi.check(int(n))
+            if n:
+                pos_parts.append(out_pos[:n].copy())
+                gt_parts.append(out_gt[:n] if n * 4 >= cap * 3 else out_gt[:n].copy())
+            if consumed.value == 0:
                 break
-            if cols is None:
-                # header: find the #CHROM line to map sample names to columns
-                h = data.find(b"#CHROM")
-                if h < 0:
-                    if not block:
-                        break
-                    carry = data
-                    continue
-                he = data.find(b"\n", h)
-                if he < 0:
-                    if not block:
-                        break
-                    carry = data
-                    continue
-                names = data[h:he].decode().rstrip("\r").split("\t")[9:]
-                index = {n: i for i, n in enumerate(names)}
-                cols = np.ascontiguousarray([index[s] for s, _ in requests], dtype=np.int32)  # KeyError like list.index
-                ploidies = np.ascontiguousarray([p for _, p in requests], dtype=np.int32)
-                data = data[he + 1 :]
-            if not block and not data.endswith(b"\n"):
-                data += b"\n"  # last line without a newline
-            at = 0
-            while at < len(data):
-                cap = max(1024, min(1 << 20, (len(data) - at) // max(64, 2 * n_out) + 16))
-                out_pos = np.empty(cap, dtype=np.int32)
-                out_gt = np.empty((cap, n_out), dtype=np.int8)
-                n = lib.sai_vcf_parse_gt(
-                    C.c_char_p(data[at:]) if at else C.c_char_p(data), len(data) - at, chr_name.encode(), region[0], region[1],
-                    cols.ctypes.data, ploidies.ctypes.data, n_out,
-                    anc_pos.ctypes.data if n_anc else None, anc_buf if n_anc else None, n_anc,
-                    out_pos.ctypes.data, out_gt.ctypes.data, n_out, cap, C.byref(consumed), n_threads,
-                )
-                if n < 0:
-                    _cabi.check(int(n))
-                if n:
-                    pos_parts.append(out_pos[:n].copy())
-                    gt_parts.append(out_gt[:n].copy())
-                if consumed.value == 0:
+            at += consumed.value
+        return at
+
+    if not _is_gzip(vcf_file) and os.path.getsize(vcf_file) > 0:
+        # plain text: parse the file in place through a read-only mapping (no copies)
+        import mmap
+
+        with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            h = mm.find(b"#CHROM")
+            he = mm.find(b"\n", h) if h >= 0 else -1
+            if h >= 0 and he >= 0:
+                cols, ploidies = header_columns(mm[h:he])
+                view = np.frombuffer(mm, dtype=np.uint8)
+                try:
+                    body, length = he + 1, len(mm)
+                    done = parse_buffer(view.ctypes.data + body, length - body)
+                    tail = bytes(mm[body + done :])
+                finally:
+                    del view
+                if tail:  # last line without a newline
+                    tail += b"\n"
+                    buf = np.frombuffer(tail, dtype=np.uint8)
+                    parse_buffer(buf.ctypes.data, len(tail))
+    else:
+        with gzip.open(vcf_file, "rb") as f:
+            carry = b""
+            while True:
+                block = f.read(chunk_bytes)
+                data = carry + block
+                if not data:
                     break
-                at += consumed.value
-            carry = data[at:]
-            if not block:
-                break
+                if cols is None:
+                    # header: find the #CHROM line to map sample names to columns
+                    h = data.find(b"#CHROM")
+                    he = data.find(b"\n", h) if h >= 0 else -1
+                    if h < 0 or he < 0:
+                        if not block:
+                            break
+                        carry = data
+                        continue
+                    cols, ploidies = header_columns(data[h:he])
+                    data = data[he + 1 :]
+                if not block and not data.endswith(b"\n"):
+                    data += b"\n"  # last line without a newline
+                buf = np.frombuffer(data, dtype=np.uint8)
+                at = parse_buffer(buf.ctypes.data, len(data)) if len(data) else 0
+                carry = data[at:]
+                if not block:
+                    break
     if cols is None:
         return None
     if not pos_parts:

@@ -320,3 +320,52 @@ def test_native_vcf_reader_matches_python_reader(tmp_path, crlf, final_newline):
     with pytest.raises(ValueError, match="Failed to read VCF"):
         (tmp_path / "bad.list").write_text("R1\tnobody\nR2\ts1\n")
         read_data(str(vcf), "7", pc, str(tmp_path / "bad.list"), lists[1], lists[2], None, None)
+
+
+def test_native_vcf_parser_segments_and_row_cap():
+    """Pass 1 of the native parser cuts the text into per-thread segments at line starts and the
+    caller may offer fewer output rows than there are records: resuming at bytes_consumed gives
+    the same rows as one big call, whatever the thread count."""
+    import ctypes as C
+
+    from sai_b200 import _cabi
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(8)
+    n_rec, n_smp = 420, 2000
+    tok = np.array(["0|0", "0|1", "1|0", "1|1", ".|.", "0/1", "1|.", "10|1"])
+    pos = np.cumsum(rng.integers(1, 50, size=n_rec))
+    lines = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n_smp))]
+    for i in range(n_rec):
+        chrom = "2" if i % 17 == 5 else "1"  # other chromosomes are skipped
+        g = rng.choice(len(tok), size=n_smp, p=[.6, .1, .1, .1, .03, .03, .02, .02])
+        lines.append(f"{chrom}\t{pos[i]}\t.\tA\tG\t.\t.\t.\tGT\t" + "\t".join(tok[g]))
+    text = ("\n".join(lines) + "\n").encode() + b"1\t999999\t.\tA\tG\t.\t.\t.\tGT\t0|0"  # incomplete last line
+    assert len(text) > 3 << 20
+    cols = np.ascontiguousarray(rng.permutation(n_smp)[:300], dtype=np.int32)
+    pl = np.ascontiguousarray(rng.choice([1, 2, 3], size=300), dtype=np.int32)
+
+    def parse(cap, n_threads):
+        at, pos_parts, gt_parts = 0, [], []
+        consumed = C.c_int64(0)
+        while True:
+            out_pos = np.empty(cap, dtype=np.int32)
+            out_gt = np.empty((cap, 300), dtype=np.int8)
+            n = lib.sai_vcf_parse_gt(C.c_char_p(text[at:]), len(text) - at, b"1", 1, 0, cols.ctypes.data, pl.ctypes.data, 300,
+                                     None, None, 0, out_pos.ctypes.data, out_gt.ctypes.data, 300, cap, C.byref(consumed), n_threads)
+            assert n >= 0
+            pos_parts.append(out_pos[:n].copy())
+            gt_parts.append(out_gt[:n].copy())
+            if consumed.value == 0:
+                break
+            at += consumed.value
+        return np.concatenate(pos_parts), np.concatenate(gt_parts), at
+
+    p1, g1, at1 = parse(10_000, 1)
+    assert p1.shape[0] == sum(1 for i in range(n_rec) if i % 17 != 5)
+    assert text[at1:].startswith(b"1\t999999")  # the incomplete line is left for the next call
+    for cap, nt in ((10_000, 4), (37, 3), (1, 8)):
+        p2, g2, at2 = parse(cap, nt)
+        assert np.array_equal(p1, p2) and np.array_equal(g1, g2) and at1 == at2, (cap, nt)
+    # spot-check values against the token table
+    assert set(np.unique(g1)) <= set(range(-3, 23))

@@ -6,6 +6,7 @@
 Writes a synthetic VCF (diploid, phased GT only), then times
   1. the native one-pass parser (sai_vcf_parse_gt, all host threads) -> int8 allele sums,
   2. the host packer (sai_pack_i8) -> tiled bit-planes,
+  2b. the zt wire encoder (sai_zt_encode) -> zero-suppressed tiles,
   3. the pure-Python reader on a slice (the cross-check implementation),
 and prints one JSON line.
 """
@@ -20,7 +21,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sai_b200.configs import PloidyConfig  # noqa: E402
-from sai_b200.encode import pack_populations  # noqa: E402
+from sai_b200.encode import compress, pack_populations  # noqa: E402
 from sai_b200.vcf import read_data  # noqa: E402
 
 
@@ -56,6 +57,10 @@ def main():
         t0 = time.perf_counter()
         pg = pack_populations(mats, [2, 2, 2], d["ref"][0]["REF"].POS)
         t_pack = time.perf_counter() - t0
+        compress(pg)
+        t0 = time.perf_counter()
+        zt = compress(pg)
+        t_zt = time.perf_counter() - t0
         # the Python reader on the first 300 records
         small = os.path.join(tmp, "small.vcf")
         with open(vcf) as f, open(small, "w") as o:
@@ -71,6 +76,8 @@ def main():
         "sites": a.sites, "samples": a.samples, "vcf_bytes": size, "host_threads": os.cpu_count(),
         "native_parse_s": t_parse, "native_parse_MBps": size / t_parse / 1e6, "native_parse_Mgenotypes_per_s": n_gt / t_parse / 1e6,
         "pack_s": t_pack, "pack_Mgenotypes_per_s": n_gt / t_pack / 1e6, "packed_bytes": pg.nbytes,
+        "zt_encode_s": t_zt, "zt_encode_MBps": pg.nbytes / t_zt / 1e6, "zt_bytes": zt.nbytes,
+        "zt_ratio": pg.nbytes / max(1, zt.nbytes),
         "python_reader_Mgenotypes_per_s": 300 * a.samples / t_py / 1e6,
     }))
 
