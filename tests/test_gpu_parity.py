@@ -334,6 +334,52 @@ def test_site_counts_vs_oracle(variant, shape):
         assert not called[i, n_sites:].any()  # padding sites are all-missing
 
 
+@pytest.mark.parametrize("variant", [3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("shape", [(1, [1, 1, 1]), (33, [5, 40, 2]), (1000, [257, 96, 3]), (4097, [1500, 1000, 4]),
+                                   (300, [20000, 8, 1]), (2500, [256, 512, 64, 33])])
+def test_site_counts_pipelined(variant, shape):
+    """The software-pipelined genotype pass (2-plane populations): counts against the oracle and
+    fused masks / Q values against the default kernel, for batch shapes with and without
+    zero-filled remainders."""
+    import torch
+
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import DeviceScorer, make_job
+
+    n_sites, n_ind = shape
+    rng = np.random.default_rng(n_sites + variant)
+    ploidy = [2, 1, 2, 2][: len(n_ind)]
+    f = rng.beta(0.3, 1.5, size=n_sites)
+    mats = []
+    for n, p in zip(n_ind, ploidy):
+        g = rng.binomial(p, f[:, None], size=(n_sites, n)).astype(np.int8)
+        g[rng.random(g.shape) < 0.05] = -1
+        g[rng.random(n_sites) < 0.03] = -2
+        mats.append(g)
+    mats[2][rng.random(n_sites) < 0.2] = ploidy[2]
+    pg = pack_populations(mats, ploidy, np.arange(n_sites))
+    assert all(pg.layout.pop[i].bits == 2 for i in range(len(n_ind)))
+    d_packed = torch.from_numpy(pg.packed).cuda()
+    sc = DeviceScorer(pg.layout, n_sites, 0, 2)
+    num, called = sc.site_counts(d_packed, variant)
+    num, called = num.cpu().numpy(), called.cpu().numpy()
+    for i, g in enumerate(mats):
+        en, ec = orc.site_counts(g)
+        assert np.array_equal(num[i, :n_sites], en), (i, variant)
+        assert np.array_equal(called[i, :n_sites], ec), (i, variant)
+        assert not called[i, n_sites:].any()
+    jobs = [make_job(0, 1, [2], True, u=dict(w=0.4, x=0.1, y_list=[(">=", 0.5)]), q=dict(w=0.4, quantile=0.9, y_list=[(">=", 0.5)])),
+            make_job(1, 0, [2], False, u=dict(w=0.6, x=0.0, y_list=[("=", 1.0)]), q=dict(w=0.6, quantile=0.5, y_list=[("=", 1.0)]))]
+    ref = DeviceScorer(pg.layout, n_sites, 0, 2)
+    ref.site_flags(d_packed, jobs, 0)
+    sc.site_flags(d_packed, jobs, variant, with_counts=True)
+    assert torch.equal(sc.mask_u, ref.mask_u) and torch.equal(sc.mask_q, ref.mask_q)
+    flagged = np.unpackbits(ref.mask_q.cpu().numpy().view(np.uint8), bitorder="little").reshape(2, -1).astype(bool)
+    qa, qb = sc.qval.cpu().numpy(), ref.qval.cpu().numpy()
+    assert np.array_equal(qa[flagged[:, : qa.shape[1]]], qb[flagged[:, : qb.shape[1]]])
+    assert flagged.any() or n_sites < 30
+
+
 # ---------------------------------------------------------------- randomized differential
 def _random_case(seed, n_sites, anc, missing, stats, pops, gap=60.0, win=(20000, 5000)):
     pos, mats = synth.make_populations(seed, n_sites, pops, mean_gap=gap, introgressed=0.02, missing=missing,
