@@ -23,14 +23,14 @@ struct SiteFlags {
   double q_tgt_freq;
 };
 
+// op(f, y) without a jump table: bit 2 = "<", bit 1 = "==", bit 0 = ">" of the relation
+// between f and y, tested against the set of relations the operator accepts
+// (EQ 010, LT 100, GT 001, LE 110, GE 011).  A NaN satisfies none, like the reference's
+// numpy comparisons.
 __device__ __forceinline__ bool cmp_op(int op, double f, double y) {
-  switch (op) {
-    case SAI_OP_EQ: return f == y;
-    case SAI_OP_LT: return f < y;
-    case SAI_OP_GT: return f > y;
-    case SAI_OP_LE: return f <= y;
-    default: return f >= y;
-  }
+  const int accept = (0x3c62 >> (3 * op)) & 7;  // 011 110 001 100 010
+  const int rel = (f < y ? 4 : 0) | (f == y ? 2 : 0) | (f > y ? 1 : 0);
+  return (rel & accept) != 0;
 }
 
 // One condition block; returns cond and the (possibly inverted) tgt frequency.
@@ -51,6 +51,15 @@ __device__ __forceinline__ bool eval_cond(const sai_cond& c, int n_src, bool anc
   return match && (r < c.w);
 }
 
+// num / den in IEEE double for den > 0 and 0 <= num <= den (other inputs: result unused).
+// 0 / den is exact without dividing, and a zero numerator would send the whole warp
+// through __ddiv_rn's slow path (a subroutine call of ~100 instructions): the divider is
+// fed den / den on those lanes instead and the quotient replaced by 0.
+__device__ __forceinline__ double site_freq(int num, int den) {
+  const double q = __ddiv_rn((double)(num > 0 ? num : den), (double)(den > 0 ? den : 1));
+  return num > 0 ? q : 0.0;
+}
+
 template <typename NumFn, typename CalledFn>
 __device__ __forceinline__ SiteFlags eval_site(const sai_job& J, const sai_layout& lay,
                                                NumFn num_of, CalledFn called_of) {
@@ -66,15 +75,30 @@ __device__ __forceinline__ SiteFlags eval_site(const sai_job& J, const sai_layou
       const int sp = J.src_pop[k];
       const int ns = num_of(sp), ds = called_of(sp) * lay.pop[sp].ploidy;
       valid = valid && ds > 0 && ns <= ds;
-      fs[k] = ds > 0 ? __ddiv_rn((double)ns, (double)ds) : 0.0;
+      fs[k] = site_freq(ns, ds);
     } else {
       fs[k] = 0.0;
     }
   }
   if (!valid) return out;
-  const double fr = __ddiv_rn((double)nr, (double)dr);
-  const double ft = __ddiv_rn((double)nt, (double)dt);
+  const double fr = site_freq(nr, dr);
+  const double ft = site_freq(nt, dt);
   const bool anc = J.anc_allele_available != 0;
+  // U and Q of one job usually share w and the source conditions (the reference's configs
+  // repeat them): evaluate the block once then
+  bool shared = J.u.enabled && J.q.enabled && J.u.w == J.q.w;
+#pragma unroll
+  for (int k = 0; k < SAI_MAX_SRC; ++k)
+    if (k < J.n_src)
+      shared = shared && J.u.op[k] == J.q.op[k] && J.u.y[k] == J.q.y[k] && J.u.one_minus_y[k] == J.q.one_minus_y[k];
+  if (shared) {
+    double t;
+    const bool c = eval_cond(J.u, J.n_src, anc, fr, ft, fs, t);
+    out.u = c && (t > J.x);
+    out.q = c;
+    out.q_tgt_freq = t;
+    return out;
+  }
   if (J.u.enabled) {
     double t;
     const bool c = eval_cond(J.u, J.n_src, anc, fr, ft, fs, t);

@@ -268,177 +268,15 @@ static int launch_site(const SiteParams& P, const JobBlock& JB, cudaStream_t st)
 }
 
 
-// ---------------------------------------------------------------------------
-// Variant 3: software-pipelined genotype pass (2-plane populations only).
-//
-// The tile's pairs are cut into batches of up to 8 pairs that never straddle a
-// population (table in shared memory); while the carry-save adders work on one
-// batch, the loads of the next batch -- of the next population or of the warp's
-// next tile -- are already in flight, so the epilogue (float64 divisions, ballots)
-// and the adder tree no longer leave the memory pipe idle.  Short batches are
-// zero-filled instead of taking a separate remainder loop, and the missing-call
-// stream (a & b) skips its adder tree while it is all zero.
-// ---------------------------------------------------------------------------
+// Batch table shared by the experimental variants: the tile's pairs cut into batches of up
+// to 8 pairs that never straddle a population (pair index | valid-1 | population | last-of-population).
 __device__ __forceinline__ uint32_t batch_entry(int pair, int valid, int pop, bool last) {
   return (uint32_t)pair | ((uint32_t)(valid - 1) << 20) | ((uint32_t)pop << 23) | ((uint32_t)last << 27);
 }
 
-__device__ __forceinline__ void load_batch(uint2 (&buf)[8], const uint2* tile, uint32_t e) {
-  const uint2* col = tile + (size_t)(e & 0xfffffu) * kTile;
-  const int valid = (int)((e >> 20) & 7u) + 1;
-  if (valid == 8) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) buf[i] = ld_stream(col + (size_t)i * kTile);
-  } else {
-    // predicated loads (no branches): pairs beyond the population read as zero
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, %4;\n\tmov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\t"
-          "@p ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];\n\t}"
-          : "=r"(buf[i].x), "=r"(buf[i].y)
-          : "l"(col + (size_t)i * kTile), "r"(i), "r"(valid));
-    }
-  }
-}
-
-template <bool FUSED, int MINB>
-__global__ void __launch_bounds__(kSiteWarps * 32, MINB)
-    k_site_pipe(const __grid_constant__ SiteParams P, const __grid_constant__ JobBlock JB, int n_batches,
-                int tab_words) {
-  extern __shared__ int s_mem[];
-  uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_mem);  // [n_batches]
-  int* s_counts = s_mem + tab_words;                     // [warp][2][n_pops][32]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_pops = P.lay.n_pops;
-  if (threadIdx.x == 0) {
-    int b = 0;
-    for (int pi = 0; pi < n_pops; ++pi) {
-      const sai_pop_layout& L = P.lay.pop[pi];
-      for (int q = 0; q < L.n_pairs; q += 8) {
-        const int valid = L.n_pairs - q < 8 ? L.n_pairs - q : 8;
-        s_tab[b++] = batch_entry(L.pair_off + q, valid, pi, q + 8 >= L.n_pairs);
-      }
-    }
-  }
-  __syncthreads();
-  int* s_num = s_counts + warp * (2 * n_pops * kTile);
-  int* s_cal = s_num + n_pops * kTile;
-  const int64_t pps = P.lay.pairs_per_site;
-  const int64_t stride = (int64_t)gridDim.x * kSiteWarps;
-  int64_t t = (int64_t)blockIdx.x * kSiteWarps + warp;
-  if (t >= P.n_tiles) return;
-
-  SliceCounter ca, cb, cm;
-  int b = 0;
-  const uint2* tile = P.packed + (size_t)(P.tile0 + t) * pps * kTile + lane;
-
-  // consumes the batch in `cur` (entry e of tile t) while `nxt` is being filled
-  auto consume = [&](const uint2 (&cur)[8], uint32_t e, int64_t tt, bool tile_done) {
-    uint32_t a[8], bb[8], m[8];
-    uint32_t mo = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      a[i] = cur[i].x;
-      bb[i] = cur[i].y;
-      m[i] = cur[i].x & cur[i].y;
-      mo |= m[i];
-    }
-    ca.add8(a);
-    cb.add8(bb);
-    if (mo) cm.add8(m);
-    if (e >> 27) {  // last batch of its population
-      const int pi = (int)((e >> 23) & 15u);
-      const int miss = cm.total();
-      const int num = ca.total() + 2 * cb.total() - 3 * miss;
-      const int called = P.lay.pop[pi].n_groups * 32 - miss;
-      s_num[pi * kTile + lane] = num;
-      s_cal[pi * kTile + lane] = called;
-      if (P.num) {
-        const int64_t site = (P.tile0 + tt) * kTile + lane;
-        P.num[(size_t)pi * P.count_stride + site] = num;
-        P.called[(size_t)pi * P.count_stride + site] = called;
-      }
-      ca = SliceCounter();
-      cb = SliceCounter();
-      cm = SliceCounter();
-    }
-    if (FUSED && tile_done) {
-      const int64_t T = P.tile0 + tt;
-      const int64_t site = T * kTile + lane;
-      for (int j = 0; j < JB.n_jobs; ++j) {
-        const sai_job& J = JB.job[j];
-        SiteFlags f = eval_site(
-            J, P.lay, [&](int pop) { return s_num[pop * kTile + lane]; },
-            [&](int pop) { return s_cal[pop * kTile + lane]; });
-        const uint32_t mu = __ballot_sync(0xffffffffu, f.u);
-        const uint32_t mq = __ballot_sync(0xffffffffu, f.q);
-        if (lane == 0) {
-          P.mask_u[(size_t)j * P.n_tiles_total + T] = mu;
-          P.mask_q[(size_t)j * P.n_tiles_total + T] = mq;
-        }
-        if (f.q) P.qval[(size_t)j * P.qval_stride + site] = f.q_tgt_freq;
-      }
-    }
-  };
-
-  uint2 A[8], B[8];
-  load_batch(A, tile, s_tab[0]);
-  while (true) {
-    // ---- A holds batch b of tile t: prefetch its successor into B, then consume A ----
-    {
-      const uint32_t e = s_tab[b];
-      const bool done = b + 1 == n_batches;
-      const int64_t tn = done ? t + stride : t;
-      const int bn = done ? 0 : b + 1;
-      const bool more = tn < P.n_tiles;
-      const uint2* tile_n = done ? P.packed + (size_t)(P.tile0 + tn) * pps * kTile + lane : tile;
-      if (more) load_batch(B, tile_n, s_tab[bn]);
-      consume(A, e, t, done);
-      if (!more) break;
-      t = tn;
-      b = bn;
-      tile = tile_n;
-    }
-    // ---- B holds batch b of tile t: prefetch into A, consume B ----
-    {
-      const uint32_t e = s_tab[b];
-      const bool done = b + 1 == n_batches;
-      const int64_t tn = done ? t + stride : t;
-      const int bn = done ? 0 : b + 1;
-      const bool more = tn < P.n_tiles;
-      const uint2* tile_n = done ? P.packed + (size_t)(P.tile0 + tn) * pps * kTile + lane : tile;
-      if (more) load_batch(A, tile_n, s_tab[bn]);
-      consume(B, e, t, done);
-      if (!more) break;
-      t = tn;
-      b = bn;
-      tile = tile_n;
-    }
-  }
-}
-
-template <bool FUSED, int MINB>
-static int launch_site_pipe(const SiteParams& P, const JobBlock& JB, cudaStream_t st) {
-  if (P.n_tiles == 0) return SAI_OK;
-  int n_batches = 0;
-  for (int p = 0; p < P.lay.n_pops; ++p) n_batches += (P.lay.pop[p].n_pairs + 7) / 8;
-  const int tab_words = (n_batches + 31) & ~31;
-  const size_t smem = sizeof(int) * ((size_t)tab_words + (size_t)kSiteWarps * 2 * P.lay.n_pops * kTile);
-  if (smem > 48 * 1024)
-    SAI_CUDA_CHECK(cudaFuncSetAttribute(k_site_pipe<FUSED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  SAI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_site_pipe<FUSED, MINB>, kSiteWarps * 32, smem));
-  if (occ < 1) occ = 1;
-  const int64_t want = (P.n_tiles + kSiteWarps - 1) / kSiteWarps;
-  const int64_t cap = (int64_t)sm_count() * occ;
-  k_site_pipe<FUSED, MINB><<<(int)(want < cap ? want : cap), kSiteWarps * 32, smem, st>>>(P, JB, n_batches, tab_words);
-  SAI_CUDA_CHECK(cudaGetLastError());
-  return SAI_OK;
-}
-
 // ---------------------------------------------------------------------------
-// Variant 5: bulk-copy ring.  The batches of variant 3 are fetched by the copy
+// Variants 5-7: bulk-copy ring (experiment, measured slower than variant 0 --
+// profiles/round1_notes.md).  Batches of up to 8 pairs are fetched by the copy
 // engine (cp.async.bulk global -> shared, completion on an mbarrier) into a
 // per-warp ring of STAGES 2 KB buffers, so the bytes in flight are bounded by
 // shared memory (up to ~190 KB per SM) instead of by registers, and the adder
@@ -612,140 +450,6 @@ static int launch_site_ring(const SiteParams& P, const JobBlock& JB, cudaStream_
   return SAI_OK;
 }
 
-// ---------------------------------------------------------------------------
-// Variant 8: flat groups.  The tile column is read in groups of 8 consecutive
-// pairs regardless of population boundaries, so every trip to memory has 8 loads
-// per lane in flight (the per-population loops of variant 0 end in remainder
-// loops with 4, 3 and 1 loads in flight: for ref 1500 / tgt 1000 / src 4 that is
-// 12 latency-bound phases per tile instead of 10).  A group that straddles a
-// boundary is fed to the adders once per population with the other population's
-// words masked to zero; all control flow is warp-uniform.
-// ---------------------------------------------------------------------------
-template <bool FUSED>
-__global__ void __launch_bounds__(kSiteWarps * 32, 4)
-    k_site_flat(const __grid_constant__ SiteParams P, const __grid_constant__ JobBlock JB) {
-  extern __shared__ int s_counts[];  // [warp][2][n_pops][32]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_pops = P.lay.n_pops;
-  int* s_num = s_counts + warp * (2 * n_pops * kTile);
-  int* s_cal = s_num + n_pops * kTile;
-  const int pps = P.lay.pairs_per_site;
-
-  for (int64_t t = (int64_t)blockIdx.x * kSiteWarps + warp; t < P.n_tiles; t += (int64_t)gridDim.x * kSiteWarps) {
-    const int64_t T = P.tile0 + t;
-    const uint2* col = P.packed + (size_t)T * pps * kTile + lane;
-    SliceCounter ca, cb, cm;
-    int pi = 0;
-    int pop_end = P.lay.pop[0].n_pairs;  // first pair index after the current population
-    for (int g0 = 0; g0 < pps; g0 += 8) {
-      uint2 v[8];
-      const int nload = pps - g0 < 8 ? pps - g0 : 8;
-      if (nload == 8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = ld_stream(col + (size_t)(g0 + i) * kTile);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          asm volatile(
-              "{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, %4;\n\tmov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\t"
-              "@p ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];\n\t}"
-              : "=r"(v[i].x), "=r"(v[i].y)
-              : "l"(col + (size_t)(g0 + i) * kTile), "r"(i), "r"(nload));
-        }
-      }
-      const int g_end = g0 + nload;
-      auto finish_pop = [&]() {  // population pi is complete: counts to shared memory, counters to zero
-        const int miss = cm.total();
-        const int num = ca.total() + 2 * cb.total() - 3 * miss;
-        const int called = P.lay.pop[pi].n_groups * 32 - miss;
-        s_num[pi * kTile + lane] = num;
-        s_cal[pi * kTile + lane] = called;
-        if (P.num) {
-          const int64_t site = T * kTile + lane;
-          P.num[(size_t)pi * P.count_stride + site] = num;
-          P.called[(size_t)pi * P.count_stride + site] = called;
-        }
-        ++pi;
-        pop_end += pi < n_pops ? P.lay.pop[pi].n_pairs : 0;
-      };
-      if (pop_end >= g0 + 8) {
-        // the whole group belongs to the current population
-        uint32_t a[8], b[8], m[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          a[i] = v[i].x;
-          b[i] = v[i].y;
-          m[i] = v[i].x & v[i].y;
-        }
-        ca.add8(a);
-        cb.add8(b);
-        cm.add8(m);
-        if (pop_end == g0 + 8) {
-          finish_pop();
-          ca.ones = ca.twos = ca.fours = 0u, ca.high = 0;
-          cb.ones = cb.twos = cb.fours = 0u, cb.high = 0;
-          cm.ones = cm.twos = cm.fours = 0u, cm.high = 0;
-        }
-      } else {
-        // a boundary inside the group: one masked pass per population
-        int seg = g0;
-        while (seg < g_end) {
-          const int seg_end = pop_end < g_end ? pop_end : g_end;
-          const unsigned lo = (unsigned)(seg - g0), len = (unsigned)(seg_end - seg);
-          uint32_t a[8], b[8], m[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t keep = ((unsigned)i - lo) < len ? 0xffffffffu : 0u;
-            a[i] = v[i].x & keep;
-            b[i] = v[i].y & keep;
-            m[i] = a[i] & b[i];
-          }
-          ca.add8(a);
-          cb.add8(b);
-          cm.add8(m);
-          const bool fin = seg_end == pop_end;
-          if (fin) finish_pop();
-          const uint32_t keepc = fin ? 0u : 0xffffffffu;  // branch-free reset
-          ca.ones &= keepc, ca.twos &= keepc, ca.fours &= keepc, ca.high &= (int)keepc;
-          cb.ones &= keepc, cb.twos &= keepc, cb.fours &= keepc, cb.high &= (int)keepc;
-          cm.ones &= keepc, cm.twos &= keepc, cm.fours &= keepc, cm.high &= (int)keepc;
-          seg = seg_end;
-        }
-      }
-    }
-    if (FUSED) {
-      const int64_t site = T * kTile + lane;
-      for (int j = 0; j < JB.n_jobs; ++j) {
-        const sai_job& J = JB.job[j];
-        SiteFlags f = eval_site(
-            J, P.lay, [&](int pop) { return s_num[pop * kTile + lane]; },
-            [&](int pop) { return s_cal[pop * kTile + lane]; });
-        const uint32_t mu = __ballot_sync(0xffffffffu, f.u);
-        const uint32_t mq = __ballot_sync(0xffffffffu, f.q);
-        if (lane == 0) {
-          P.mask_u[(size_t)j * P.n_tiles_total + T] = mu;
-          P.mask_q[(size_t)j * P.n_tiles_total + T] = mq;
-        }
-        if (f.q) P.qval[(size_t)j * P.qval_stride + site] = f.q_tgt_freq;
-      }
-    }
-  }
-}
-
-template <bool FUSED>
-static int launch_site_flat(const SiteParams& P, const JobBlock& JB, cudaStream_t st) {
-  if (P.n_tiles == 0) return SAI_OK;
-  const size_t smem = (size_t)kSiteWarps * 2 * P.lay.n_pops * kTile * sizeof(int);
-  int occ = 0;
-  SAI_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_site_flat<FUSED>, kSiteWarps * 32, smem));
-  if (occ < 1) occ = 1;
-  const int64_t want = (P.n_tiles + kSiteWarps - 1) / kSiteWarps;
-  const int64_t cap = (int64_t)sm_count() * occ;
-  k_site_flat<FUSED><<<(int)(want < cap ? want : cap), kSiteWarps * 32, smem, st>>>(P, JB);
-  SAI_CUDA_CHECK(cudaGetLastError());
-  return SAI_OK;
-}
-
 static bool all_two_planes(const sai_layout& lay) {
   for (int p = 0; p < lay.n_pops; ++p)
     if (lay.pop[p].bits != 2) return false;
@@ -781,9 +485,6 @@ int sai_site_counts(const sai_layout* lay, const void* d_packed, int64_t tile0, 
                                   : launch_site_ring<false, 6, 2>(P, JB, st);
     if (rc != -1000) return rc;
   }
-  if (variant == 8 && all_two_planes(*lay)) return launch_site_flat<false>(P, JB, st);
-  if (variant == 3 && all_two_planes(*lay)) return launch_site_pipe<false, 3>(P, JB, st);
-  if (variant == 4 && all_two_planes(*lay)) return launch_site_pipe<false, 2>(P, JB, st);
   if (variant == 2) return launch_site<2, false>(P, JB, st);
   if (variant == 1) return launch_site<1, false>(P, JB, st);
   return launch_site<0, false>(P, JB, st);
@@ -823,9 +524,6 @@ int sai_site_flags(const sai_layout* lay, const void* d_packed, int64_t tile0, i
                                   : launch_site_ring<true, 6, 2>(P, JB, st);
     if (rc != -1000) return rc;
   }
-  if (variant == 8 && all_two_planes(*lay)) return launch_site_flat<true>(P, JB, st);
-  if (variant == 3 && all_two_planes(*lay)) return launch_site_pipe<true, 3>(P, JB, st);
-  if (variant == 4 && all_two_planes(*lay)) return launch_site_pipe<true, 2>(P, JB, st);
   if (variant == 2) return launch_site<2, true>(P, JB, st);
   if (variant == 1) return launch_site<1, true>(P, JB, st);
   return launch_site<0, true>(P, JB, st);

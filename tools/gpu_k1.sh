@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "site_counts" 2>&1 | tail -5
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
 for rep in 1 2; do
-for v in 0 8; do
+for v in 0 1; do
   timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu --e2e-steps 0 --variant $v > gpurun_out/knob.log 2>&1
   python - <<PY
 import json
