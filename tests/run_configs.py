@@ -1,10 +1,11 @@
 #!/usr/bin/env python
-"""BASELINE.json configs 3-5 on the GPU (parity-test cases, not bench lines).
+"""BASELINE.json configs 3-5 (+ all seven statistics) on the GPU: parity-test cases at full size, not bench lines.
+Lives under tests/ because it checks against the CPU oracle; it is a script, not collected by pytest.
 
-    python tools/run_configs.py --config 3            # two sources, haploid + diploid, missing, both anc modes
-    python tools/run_configs.py --config 5            # threshold / window sweep on a 20k-sample cohort (cached counts)
-    python tools/run_configs.py --config 6            # all seven statistics incl. DD, missing calls
-    torchrun --nproc-per-node N tools/run_configs.py --config 4   # 22 autosomes, 80 M sites, sharded by window range
+    python tests/run_configs.py --config 3            # two sources, haploid + diploid, missing, both anc modes
+    python tests/run_configs.py --config 5            # threshold / window sweep on a 20k-sample cohort (cached counts)
+    python tests/run_configs.py --config 6            # all seven statistics incl. DD, missing calls
+    torchrun --nproc-per-node N tests/run_configs.py --config 4   # 22 autosomes, 80 M sites, sharded by window range
                                                                   # + genome-wide `sai outlier` thresholds
 
 Every run spot-checks GPU results against the CPU oracle on decoded slices of

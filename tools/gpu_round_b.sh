@@ -9,7 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-fi
 echo "launch list exit $?"
 ncu --set full --clock-control none --import-source on -k regex:k_zt_decode -s 40 -c 1 -o gpurun_out/prof_k_zt_decode $CMD > gpurun_out/ncu_full_zt.log 2>&1
 echo "zt capture exit $?"
-CMD6="python tools/run_configs.py --config 6"
+CMD6="python tests/run_configs.py --config 6"
 $CMD6 > gpurun_out/config6.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"k_site_hist|k_window_dd" -s 2 -c 2 -o gpurun_out/prof_dd $CMD6 > gpurun_out/ncu_full_dd.log 2>&1
 echo "dd capture exit $?"

@@ -10,7 +10,7 @@ for n in 1 2 4 8; do
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n bench.py --gpus $n --steps 20 --warmup 3 > gpurun_out/scale_bench_n$n.log 2>&1
     fi
     echo "bench n=$n exit $?"
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n tools/run_configs.py --config 4 > gpurun_out/scale_config4_n$n.log 2>&1
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n tests/run_configs.py --config 4 > gpurun_out/scale_config4_n$n.log 2>&1
     echo "config4 n=$n exit $?"
   fi
 done
