@@ -113,4 +113,88 @@ __device__ __forceinline__ SiteFlags eval_site(const sai_job& J, const sai_layou
   return out;
 }
 
+// ---------------------------------------------------------------------------
+// Integer fast path.  For a FIXED denominator d (= individuals * ploidy: every call of
+// the population present), freq(n) = fl(n / d) is non-decreasing in the count n and
+// fl(1 - freq(n)) non-increasing, so each float64 decision of compute_matching_loci is
+// an interval test on n.  The host finds the interval ends by bisection with the very
+// same IEEE operations (build_job_fast), and a site whose populations are all fully
+// called is decided with integer compares only -- the divisions are left to the sites
+// that fail this test (missing calls) and to the Q-flagged sites, whose target
+// frequency is an output.  Decisions are identical by construction; the tests compare
+// the masks and Q values of both paths on random data.
+// ---------------------------------------------------------------------------
+struct CondFast {
+  int32_t ref_max;      // not inverted: ref_freq < w      <=>  num_ref <= ref_max
+  int32_t ref_inv_min;  // inverted:     1 - ref_freq < w  <=>  num_ref >= ref_inv_min
+  int32_t y_lo[SAI_MAX_SRC], y_hi[SAI_MAX_SRC];  // op(src_freq, y)      <=>  y_lo <= num_src <= y_hi
+  int32_t f_lo[SAI_MAX_SRC], f_hi[SAI_MAX_SRC];  // op(src_freq, 1 - y)  <=>  f_lo <= num_src <= f_hi
+};
+struct JobFast {
+  int32_t ok;  // thresholds are valid
+  int32_t den_ref, den_tgt, den_src[SAI_MAX_SRC];
+  int32_t tgt_min;      // not inverted: tgt_freq > x      <=>  num_tgt >= tgt_min
+  int32_t tgt_inv_max;  // inverted:     1 - tgt_freq > x  <=>  num_tgt <= tgt_inv_max
+  CondFast u, q;
+};
+struct JobFastBlock {
+  JobFast job[SAI_MAX_JOBS];
+};
+
+template <typename NumFn, typename CalledFn>
+__device__ __forceinline__ SiteFlags eval_site_fast(const JobFast& F, const sai_job& J, const sai_layout& lay,
+                                                    NumFn num_of, CalledFn called_of) {
+  const int nr = num_of(J.ref_pop), dr = called_of(J.ref_pop) * lay.pop[J.ref_pop].ploidy;
+  const int nt = num_of(J.tgt_pop), dt = called_of(J.tgt_pop) * lay.pop[J.tgt_pop].ploidy;
+  bool full = F.ok != 0 && dr == F.den_ref && dt == F.den_tgt;
+  bool valid = nr <= dr && nt <= dt;
+  int ns[SAI_MAX_SRC];
+#pragma unroll
+  for (int k = 0; k < SAI_MAX_SRC; ++k) {
+    if (k < J.n_src) {
+      const int sp = J.src_pop[k];
+      ns[k] = num_of(sp);
+      const int ds = called_of(sp) * lay.pop[sp].ploidy;
+      full = full && ds == F.den_src[k];
+      valid = valid && ns[k] <= ds;
+    } else {
+      ns[k] = 0;
+    }
+  }
+  // warp-uniform choice: a tile with a missing call anywhere takes the division path
+  if (!__all_sync(0xffffffffu, full)) return eval_site(J, lay, num_of, called_of);
+  SiteFlags out{false, false, 0.0};
+  const bool anc = J.anc_allele_available != 0;
+  auto cond = [&](const CondFast& C, bool& inv) {
+    bool my = true, mf = true;
+#pragma unroll
+    for (int k = 0; k < SAI_MAX_SRC; ++k) {
+      if (k < J.n_src) {
+        my = my && ns[k] >= C.y_lo[k] && ns[k] <= C.y_hi[k];
+        mf = mf && ns[k] >= C.f_lo[k] && ns[k] <= C.f_hi[k];
+      }
+    }
+    inv = !anc && mf;
+    return valid && (my || inv) && (inv ? nr >= C.ref_inv_min : nr <= C.ref_max);
+  };
+  if (J.u.enabled) {
+    bool inv;
+    const bool c = cond(F.u, inv);
+    out.u = c && (inv ? nt <= F.tgt_inv_max : nt >= F.tgt_min);
+  }
+  if (J.q.enabled) {
+    bool inv;
+    const bool c = cond(F.q, inv);
+    out.q = c;
+    if (c) {
+      const double ft = site_freq(nt, dt);
+      out.q_tgt_freq = inv ? __dsub_rn(1.0, ft) : ft;
+    }
+  }
+  return out;
+}
+
+// host: interval ends for one job (plain IEEE double division / subtraction, as on the device)
+void build_job_fast(const sai_layout& lay, const sai_job& J, JobFast& F);
+
 }  // namespace sai

@@ -9,6 +9,10 @@
 // HBM-bound: every packed byte is read exactly once with coalesced 256-byte
 // warp requests (8 bytes per lane); outputs are two 32-bit masks per tile and
 // job plus one double per Q-flagged site.
+#include <string.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "site_cond.cuh"
 
@@ -146,6 +150,64 @@ __device__ __forceinline__ void count_generic(const uint2* __restrict__ col, int
   miss = accm;
 }
 
+// ---- host side of the integer fast path (site_cond.cuh) ----------------------------
+namespace {
+// first n in [0, d + 1] for which pred(n) holds; pred must be monotone (false ... false true ... true)
+template <typename Pred>
+int first_true(int d, Pred pred) {
+  int lo = 0, hi = d + 1;
+  while (lo < hi) {
+    const int mid = lo + (hi - lo) / 2;
+    if (pred(mid)) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+inline double freq_of(int n, int d) { return (double)n / (double)d; }
+// {n in [0, d] : op(freq(n), y)} as [lo, hi] (empty: lo > hi); freq is non-decreasing in n
+void op_interval(int op, double y, int d, int32_t& lo, int32_t& hi) {
+  const int ge = first_true(d, [&](int n) { return freq_of(n, d) >= y; });  // first n with freq >= y
+  const int gt = first_true(d, [&](int n) { return freq_of(n, d) > y; });   // first n with freq >  y
+  switch (op) {
+    case SAI_OP_EQ: lo = ge, hi = gt - 1; break;
+    case SAI_OP_LT: lo = 0, hi = ge - 1; break;
+    case SAI_OP_GT: lo = gt, hi = d; break;
+    case SAI_OP_LE: lo = 0, hi = gt - 1; break;
+    default: lo = ge, hi = d; break;
+  }
+  if (y != y) lo = 1, hi = 0;  // NaN compares false (cannot pass validation, but stay exact)
+}
+}  // namespace
+
+void build_job_fast(const sai_layout& lay, const sai_job& J, JobFast& F) {
+  memset(&F, 0, sizeof(F));
+  auto den = [&](int pop) { return (int64_t)lay.pop[pop].n_samples * lay.pop[pop].ploidy; };
+  int64_t dmax = std::max(den(J.ref_pop), den(J.tgt_pop));
+  for (int k = 0; k < J.n_src; ++k) dmax = std::max(dmax, den(J.src_pop[k]));
+  if (dmax >= (1ll << 30)) return;  // F.ok = 0: always the division path
+  const int dr = (int)den(J.ref_pop), dt = (int)den(J.tgt_pop);
+  F.den_ref = dr;
+  F.den_tgt = dt;
+  // tgt_freq > x  <=> n >= tgt_min;   1 - tgt_freq > x  <=> n <= tgt_inv_max (non-increasing in n)
+  F.tgt_min = first_true(dt, [&](int n) { return freq_of(n, dt) > J.x; });
+  F.tgt_inv_max = first_true(dt, [&](int n) { return !(1.0 - freq_of(n, dt) > J.x); }) - 1;
+  const sai_cond* cs[2] = {&J.u, &J.q};
+  CondFast* fs[2] = {&F.u, &F.q};
+  for (int c = 0; c < 2; ++c) {
+    const sai_cond& C = *cs[c];
+    CondFast& X = *fs[c];
+    // ref_freq < w  <=> n <= ref_max;   1 - ref_freq < w  <=> n >= ref_inv_min
+    X.ref_max = first_true(dr, [&](int n) { return !(freq_of(n, dr) < C.w); }) - 1;
+    X.ref_inv_min = first_true(dr, [&](int n) { return 1.0 - freq_of(n, dr) < C.w; });
+    for (int k = 0; k < J.n_src; ++k) {
+      const int ds = (int)den(J.src_pop[k]);
+      F.den_src[k] = ds;
+      op_interval(C.op[k], C.y[k], ds, X.y_lo[k], X.y_hi[k]);
+      op_interval(C.op[k], C.one_minus_y[k], ds, X.f_lo[k], X.f_hi[k]);
+    }
+  }
+  F.ok = 1;
+}
+
 struct SiteParams {
   sai_layout lay;
   const uint2* packed;  // tile 0
@@ -163,7 +225,8 @@ constexpr int kSiteWarps = 8;
 
 template <int MODE, bool FUSED>
 __global__ void __launch_bounds__(kSiteWarps * 32, MODE == 1 ? 3 : 4)
-    k_site(const __grid_constant__ SiteParams P, const __grid_constant__ JobBlock JB) {
+    k_site(const __grid_constant__ SiteParams P, const __grid_constant__ JobBlock JB,
+           const __grid_constant__ JobFastBlock JF) {
   extern __shared__ int s_counts[];  // [warp][2][n_pops][32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_pops = P.lay.n_pops;
@@ -196,8 +259,8 @@ __global__ void __launch_bounds__(kSiteWarps * 32, MODE == 1 ? 3 : 4)
       const int64_t site = T * kTile + lane;
       for (int j = 0; j < JB.n_jobs; ++j) {
         const sai_job& J = JB.job[j];
-        SiteFlags f = eval_site(
-            J, P.lay, [&](int pop) { return s_num[pop * kTile + lane]; },
+        SiteFlags f = eval_site_fast(
+            JF.job[j], J, P.lay, [&](int pop) { return s_num[pop * kTile + lane]; },
             [&](int pop) { return s_cal[pop * kTile + lane]; });
         const uint32_t mu = __ballot_sync(0xffffffffu, f.u);
         const uint32_t mq = __ballot_sync(0xffffffffu, f.q);
@@ -226,8 +289,8 @@ struct CountFlagParams {
 
 // Site conditions from cached counts: one lane per site, one warp per tile.
 __global__ void __launch_bounds__(256)
-    k_flags_from_counts(const __grid_constant__ CountFlagParams P,
-                        const __grid_constant__ JobBlock JB) {
+    k_flags_from_counts(const __grid_constant__ CountFlagParams P, const __grid_constant__ JobBlock JB,
+                        const __grid_constant__ JobFastBlock JF) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t T = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; T < P.n_tiles_total;
@@ -236,8 +299,8 @@ __global__ void __launch_bounds__(256)
     const bool live = site < P.n_sites;
     for (int j = 0; j < JB.n_jobs; ++j) {
       const sai_job& J = JB.job[j];
-      SiteFlags f = eval_site(
-          J, P.lay,
+      SiteFlags f = eval_site_fast(
+          JF.job[j], J, P.lay,
           [&](int pop) { return live ? P.num[(size_t)pop * P.count_stride + site] : 0; },
           [&](int pop) { return live ? P.called[(size_t)pop * P.count_stride + site] : 0; });
       const uint32_t mu = __ballot_sync(0xffffffffu, f.u);
@@ -251,6 +314,11 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+static void fill_job_fast(const sai_layout& lay, const JobBlock& JB, JobFastBlock& JF) {
+  memset(&JF, 0, sizeof(JF));
+  for (int j = 0; j < JB.n_jobs; ++j) build_job_fast(lay, JB.job[j], JF.job[j]);
+}
+
 template <int MODE, bool FUSED>
 static int launch_site(const SiteParams& P, const JobBlock& JB, cudaStream_t st) {
   if (P.n_tiles == 0) return SAI_OK;
@@ -262,7 +330,9 @@ static int launch_site(const SiteParams& P, const JobBlock& JB, cudaStream_t st)
   int64_t want = (P.n_tiles + kSiteWarps - 1) / kSiteWarps;
   int64_t cap = (int64_t)sm_count() * occ;
   int grid = (int)(want < cap ? want : cap);
-  k_site<MODE, FUSED><<<grid, kSiteWarps * 32, smem, st>>>(P, JB);
+  JobFastBlock JF;
+  fill_job_fast(P.lay, JB, JF);
+  k_site<MODE, FUSED><<<grid, kSiteWarps * 32, smem, st>>>(P, JB, JF);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }
@@ -307,8 +377,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 template <bool FUSED, int STAGES, int MINB>
 __global__ void __launch_bounds__(kSiteWarps * 32, MINB)
-    k_site_ring(const __grid_constant__ SiteParams P, const __grid_constant__ JobBlock JB, int n_batches,
-                int tab_words) {
+    k_site_ring(const __grid_constant__ SiteParams P, const __grid_constant__ JobBlock JB,
+                const __grid_constant__ JobFastBlock JF, int n_batches, int tab_words) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   // [ring: warps x STAGES x 2 KB][mbarriers: warps x STAGES x 8 B][table][counts]
   uint2* s_ring = reinterpret_cast<uint2*>(s_raw);
@@ -411,8 +481,8 @@ __global__ void __launch_bounds__(kSiteWarps * 32, MINB)
         const int64_t site = T * kTile + lane;
         for (int j = 0; j < JB.n_jobs; ++j) {
           const sai_job& J = JB.job[j];
-          SiteFlags f = eval_site(
-              J, P.lay, [&](int pop) { return s_num[pop * kTile + lane]; },
+          SiteFlags f = eval_site_fast(
+              JF.job[j], J, P.lay, [&](int pop) { return s_num[pop * kTile + lane]; },
               [&](int pop) { return s_cal[pop * kTile + lane]; });
           const uint32_t mu = __ballot_sync(0xffffffffu, f.u);
           const uint32_t mq = __ballot_sync(0xffffffffu, f.q);
@@ -445,7 +515,9 @@ static int launch_site_ring(const SiteParams& P, const JobBlock& JB, cudaStream_
   if (occ < 1) occ = 1;
   const int64_t want = (P.n_tiles + kSiteWarps - 1) / kSiteWarps;
   const int64_t cap = (int64_t)sm_count() * occ;
-  kern<<<(int)(want < cap ? want : cap), kSiteWarps * 32, smem, st>>>(P, JB, n_batches, tab_words);
+  JobFastBlock JF;
+  fill_job_fast(P.lay, JB, JF);
+  kern<<<(int)(want < cap ? want : cap), kSiteWarps * 32, smem, st>>>(P, JB, JF, n_batches, tab_words);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }
@@ -555,7 +627,9 @@ int sai_flags_from_counts(const sai_layout* lay, const int32_t* d_num, const int
   const int64_t want = (P.n_tiles_total + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 8;
   const int grid = (int)(want < cap ? want : cap);
-  k_flags_from_counts<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P, JB);
+  JobFastBlock JF;
+  fill_job_fast(*lay, JB, JF);
+  k_flags_from_counts<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P, JB, JF);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }

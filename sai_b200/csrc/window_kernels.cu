@@ -48,7 +48,6 @@ struct WinParams {
   int64_t cap_u;
   int32_t* q_cand;
   int64_t cap_q;
-  int32_t use_hints;
 };
 
 __device__ __forceinline__ int clamp_key(int64_t k) {
@@ -441,21 +440,15 @@ __device__ void window_generic(const WinParams& P, const JobView& J, SlowScratch
 
 // 32-ary lower bounds of 2*kBatch keys at once (same invariant as a single
 // search: answer in [lo, hi]); every round has 2*kBatch loads in flight.
-// `hint[t]` is a lower bound of the answer (0 when nothing is known): the
-// first round then probes [hint, hint + 1024) with step 32, which settles keys
-// that lie close behind the hint in 2 rounds; otherwise the search continues
-// on the rest of the array.
 template <int kBatch>
 __device__ __forceinline__ void warp_lower_bound_batch(const int32_t* __restrict__ pos, int n,
-                                                       const int64_t (&key)[2 * kBatch],
-                                                       const int (&hint)[2 * kBatch], int lane,
+                                                       const int64_t (&key)[2 * kBatch], int lane,
                                                        int (&out)[2 * kBatch]) {
   int lo[2 * kBatch], hi[2 * kBatch], k32[2 * kBatch];
-  bool first = true;
 #pragma unroll
   for (int t = 0; t < 2 * kBatch; ++t) {
     k32[t] = clamp_key(key[t]);
-    lo[t] = key[t] > 2147483647ll ? n : hint[t];
+    lo[t] = key[t] > 2147483647ll ? n : 0;
     hi[t] = n;
   }
   while (true) {
@@ -469,20 +462,16 @@ __device__ __forceinline__ void warp_lower_bound_batch(const int32_t* __restrict
     for (int t = 0; t < 2 * kBatch; ++t) {
       const int nn = hi[t] - lo[t];
       step[t] = nn > 32 ? (nn + 31) >> 5 : 1;
-      if (first && hint[t] > 0 && step[t] > 32) step[t] = 32;  // gallop: only [lo, lo + 1024) this round
       const unsigned idx = (unsigned)lo[t] + (unsigned)(lane + 1) * (unsigned)step[t] - 1u;
       pred[t] = idx < (unsigned)hi[t] && __ldg(pos + idx) < k32[t];
     }
-    first = false;
 #pragma unroll
     for (int t = 0; t < 2 * kBatch; ++t) {
       const int c = __popc(__ballot_sync(0xffffffffu, pred[t]));
       if (hi[t] > lo[t]) {
         const unsigned nhi = (unsigned)lo[t] + (unsigned)(c + 1) * (unsigned)step[t] - 1u;
         lo[t] += c * step[t];
-        // probe c (the first one not below the key) bounds the answer; with all 32
-        // probes below the key (possible only in a galloping round) nothing is known above
-        if (c < 32 && nhi < (unsigned)hi[t]) hi[t] = (int)nhi;
+        if (nhi < (unsigned)hi[t]) hi[t] = (int)nhi;
         if (lo[t] > hi[t]) lo[t] = hi[t];
       }
     }
@@ -514,20 +503,7 @@ __global__ void __launch_bounds__(kWinWarps * 32, kMinBlocks)
   WarpScratch<kBatch>& SC = s_scratch[warp];
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  // every warp owns a contiguous run of windows: consecutive windows start close
-  // to each other, so the previous bounds are hints for the next search
-  const int n_warps = gridDim.x * kWinWarps;
-  const int per_warp = ((P.W + n_warps * kBatch - 1) / (n_warps * kBatch)) * kBatch;
-  const int w_begin = (blockIdx.x * kWinWarps + warp) * per_warp;
-  const int w_end = w_begin + per_warp < P.W ? w_begin + per_warp : P.W;
-  int64_t prev_key[2 * kBatch];
-  int hint[2 * kBatch];
-#pragma unroll
-  for (int t = 0; t < 2 * kBatch; ++t) {
-    prev_key[t] = 0;
-    hint[t] = 0;
-  }
-  for (int i0 = w_begin; i0 < w_end; i0 += kBatch) {
+  for (int i0 = (blockIdx.x * kWinWarps + warp) * kBatch; i0 < P.W; i0 += gridDim.x * kWinWarps * kBatch) {
     // ---- A: window bounds as keys (one coalesced load for the whole batch) ----
     int64_t key[2 * kBatch];
     {
@@ -539,16 +515,7 @@ __global__ void __launch_bounds__(kWinWarps * 32, kMinBlocks)
     }
     // ---- B: all searches together ----
     int bnd[2 * kBatch];
-#pragma unroll
-    for (int t = 0; t < 2 * kBatch; ++t)
-      if (key[t] < prev_key[t]) hint[t] = 0;  // windows not sorted: the hint does not hold
-    warp_lower_bound_batch<kBatch>(P.pos, P.n_sites, key, hint, lane, bnd);
-#pragma unroll
-    for (int t = 0; t < 2 * kBatch; ++t) {
-      // window i0 + kBatch + k is searched next with the bounds of window i0 + k as hints
-      prev_key[t] = key[t];
-      hint[t] = P.use_hints ? bnd[t] : 0;
-    }
+    warp_lower_bound_batch<kBatch>(P.pos, P.n_sites, key, lane, bnd);
 
     // ---- C: masks of all windows ----
     uint32_t a[kBatch][2], b[kBatch][2];
@@ -755,11 +722,6 @@ extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int
   const int64_t want = (n_windows + per_block - 1) / per_block;
   const int64_t cap = (int64_t)sm_count() * 32;
   const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_jobs);
-  static const int hints = [] {
-    const char* e = getenv("SAI_WIN_HINT");
-    return e ? atoi(e) : 1;
-  }();
-  P.use_hints = hints;
   static const int minb = [] {
     const char* e = getenv("SAI_WIN_MINB");
     return e ? atoi(e) : 12;

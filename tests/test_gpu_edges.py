@@ -279,3 +279,60 @@ def test_zt_wire_format_gpu(engine, shape):
         assert np.array_equal(a.u_positions(0, i), b.u_positions(0, i))
         assert np.array_equal(a.q_positions(0, i), b.q_positions(0, i))
     assert (zt.stream.nbytes < pg.packed.nbytes) == (shape != "dense")
+
+
+def test_integer_fast_path_thresholds(engine):
+    """Fully called sites are decided by integer interval tests whose ends the host finds by
+    bisection (site_cond.cuh); sites with a missing call take the float64 division path.  Every
+    count combination of a small layout x thresholds sitting exactly on, just below and just above
+    every attainable frequency (and 1 - frequency) x every operator, with and without ancestral
+    alleles, with and without one missing call per site: all against the oracle."""
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import make_job
+
+    rng = np.random.default_rng(77)
+    n_ref, n_tgt, n_src = 3, 2, 1  # diploid: denominators 6, 4, 2
+    combos = [(a, b, c) for a in range(7) for b in range(5) for c in range(3)]
+
+    def column(total, n_ind):
+        g = np.zeros(n_ind, np.int8)
+        for i in range(n_ind):
+            g[i] = min(2, total)
+            total -= g[i]
+        return g
+
+    base = [np.array([column(c[k], n) for c in combos], dtype=np.int8) for k, n in enumerate((n_ref, n_tgt, n_src))]
+    # second half: the same sites with one extra individual per population that is missing -> division path
+    with_missing = [np.concatenate([m, np.full((len(combos), 1), -1, np.int8)], axis=1) for m in base]
+    crit = sorted({n / d for d in (6, 4, 2, 8, 3) for n in range(d + 1)} | {1 - n / d for d in (6, 4, 2) for n in range(d + 1)})
+    crit = sorted({float(v) for c in crit for v in (c, np.nextafter(c, 2.0), np.nextafter(c, -1.0)) if 0.0 <= v <= 1.0})
+    ops = ["=", "<", ">", "<=", ">="]
+    pos = np.arange(1, len(combos) + 1, dtype=np.int32)
+    wins = [(int(p), int(p)) for p in pos]
+    checked = 0
+    for mats in (base, with_missing):
+        pg = pack_populations(mats, [2, 2, 2], pos)
+        m64 = [m.astype(np.int64) for m in mats]
+        for batch in range(6):
+            specs, jobs = [], []
+            for _ in range(8):
+                w, x, y, q = (float(rng.choice(crit)) for _ in range(4))
+                op, anc = str(rng.choice(ops)), bool(rng.integers(0, 2))
+                yq, opq = (y, op) if rng.random() < 0.5 else (float(rng.choice(crit)), str(rng.choice(ops)))
+                u = dict(w=w, x=x, y_list=[(op, y)])
+                qd = dict(w=w if rng.random() < 0.5 else float(rng.choice(crit)), quantile=q, y_list=[(opq, yq)])
+                specs.append((anc, u, qd))
+                jobs.append(make_job(0, 1, [2], anc, u, qd))
+            res = engine.score(pg, wins, jobs)
+            for j, (anc, u, qd) in enumerate(specs):
+                for i in range(len(combos)):
+                    sub = [m[i : i + 1] for m in m64]
+                    eu = orc.u_statistic(sub[0], sub[1], [sub[2]], 2, 2, [2], pos=pos[i : i + 1], anc_allele_available=anc, **u)
+                    eq = orc.q_statistic(sub[0], sub[1], [sub[2]], 2, 2, [2], pos=pos[i : i + 1], anc_allele_available=anc, **qd)
+                    assert res.u[j, i] == eu["value"], (j, i, u, anc, combos[i])
+                    if np.isnan(eq["value"]):
+                        assert np.isnan(res.q[j, i]), (j, i, qd, anc, combos[i])
+                    else:
+                        assert res.q[j, i] == float(eq["value"]), (j, i, qd, anc, combos[i])
+                    checked += 1
+    assert checked == 2 * 6 * 8 * len(combos)
