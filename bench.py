@@ -460,6 +460,8 @@ def main():
                 "bound": "hbm", "kernel": "k_site (genotype pass, fused site conditions)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "k1_ms": k1_ms, "algorithmic_bytes": alg,
+                "note": "peak is a copy (read + write) bandwidth; a read-only kernel with k_site's access pattern "
+                        "reaches 7.0-7.2 TB/s on this GPU (tools/readbw.cu, profiles/round1_notes.md), so frac can exceed 1",
             },
             "cpu_baseline": cpu,
             "e2e": e2e,
