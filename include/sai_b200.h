@@ -155,6 +155,18 @@ int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* chrom, int64
                          int64_t n_anc, int32_t* out_pos, int8_t* out_gt, int64_t row_stride,
                          int64_t rows_cap, int64_t* bytes_consumed, int32_t n_threads);
 
+/* BGZF (bgzip) input: a .vcf.gz written by bgzip is a sequence of independent gzip members of
+ * <= 64 KB.  sai_bgzf_scan indexes the complete blocks at the start of `data` (at most
+ * max_blocks, stopping before the uncompressed total exceeds max_out_bytes unless it is the
+ * first block): block_off[i] = offset of block i, out_off[i] = offset of its text,
+ * out_off[n] = total text bytes, *consumed = compressed bytes covered; returns n.
+ * sai_bgzf_inflate inflates those blocks in parallel (CRC checked) into `out`. */
+int32_t sai_is_bgzf(const uint8_t* data, int64_t len);
+int64_t sai_bgzf_scan(const uint8_t* data, int64_t len, int64_t max_blocks, int64_t max_out_bytes,
+                      int64_t* block_off, int64_t* out_off, int64_t* consumed);
+int sai_bgzf_inflate(const uint8_t* data, const int64_t* block_off, const int64_t* out_off,
+                     int64_t n_blocks, uint8_t* out, int32_t n_threads);
+
 /* ---- K1: site counts (replaces calc_freq's passes, stat_utils.py:45-49) --- */
 /* For tiles [tile0, tile0+n_tiles): per population p and site s
  *     num[p*stride + s]    = sum of called values      (stat_utils.py:48)

@@ -98,6 +98,9 @@ SYMBOLS = {
         _I64,
         [_P, _I64, C.c_char_p, _I64, _I64, _P, _P, _I32, _P, _P, _I64, _P, _P, _I64, _I64, C.POINTER(_I64), _I32],
     ),
+    "sai_is_bgzf": (_I32, [_P, _I64]),
+    "sai_bgzf_scan": (_I64, [_P, _I64, _I64, _I64, _P, _P, C.POINTER(_I64)]),
+    "sai_bgzf_inflate": (C.c_int, [_P, _P, _P, _I64, _P, _I32]),
     "sai_site_counts": (C.c_int, [_LAY, _P, _I64, _I64, _P, _P, _I64, _I32, _P]),
     "sai_site_flags": (
         C.c_int,

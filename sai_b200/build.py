@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
            "-Xcompiler", "-fPIC,-pthread", "-o", str(LIB)] + [
         str(o) for o in objs
-    ]
+    ] + ["-lz"]  # zlib: BGZF blocks of .vcf.gz inputs (host ingest)
     subprocess.run(cmd, check=True)
     return LIB
 

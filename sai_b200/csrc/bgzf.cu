@@ -1,0 +1,139 @@
+// Host-side BGZF (bgzip) reader for the VCF ingest (N2).  No device code in this file.
+//
+// The reference reads `.vcf.gz` through scikit-allel / pysam (htslib).  A bgzip file is a
+// sequence of independent gzip members of at most 64 KB ("blocks", SAM spec section 4.1): a
+// gzip header whose extra field carries the subfield 'B','C' = total block size - 1, raw
+// deflate data, CRC32 and ISIZE.  Independent blocks inflate in parallel, which turns the
+// single-threaded decompression (the slowest stage of ingest once the parser runs at GB/s)
+// into a multi-threaded one.
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sai {
+
+static inline uint32_t le16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+static inline uint32_t le32(const uint8_t* p) { return le16(p) | (le16(p + 2) << 16); }
+
+// total size of the block at p (0: not a complete / valid BGZF block within `avail` bytes)
+static int64_t block_size(const uint8_t* p, int64_t avail, int64_t* payload_off) {
+  if (avail < 18) return 0;
+  if (p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) return -1;
+  const int64_t xlen = le16(p + 10);
+  if (avail < 12 + xlen) return 0;
+  const uint8_t* x = p + 12;
+  const uint8_t* xe = x + xlen;
+  int64_t bsize = -1;
+  while (x + 4 <= xe) {
+    const int64_t slen = le16(x + 2);
+    if (x[0] == 'B' && x[1] == 'C' && slen == 2 && x + 6 <= xe) bsize = (int64_t)le16(x + 4) + 1;
+    x += 4 + slen;
+  }
+  if (bsize < 0) return -1;
+  if (bsize < 12 + xlen + 8) return -1;
+  if (avail < bsize) return 0;
+  *payload_off = 12 + xlen;
+  return bsize;
+}
+
+}  // namespace sai
+
+using namespace sai;
+
+extern "C" {
+
+int32_t sai_is_bgzf(const uint8_t* data, int64_t len) {
+  int64_t off = 0;
+  return data && block_size(data, len, &off) > 0 ? 1 : 0;
+}
+
+int64_t sai_bgzf_scan(const uint8_t* data, int64_t len, int64_t max_blocks, int64_t max_out_bytes,
+                      int64_t* block_off, int64_t* out_off, int64_t* consumed) {
+  if (!data || len < 0 || max_blocks < 0 || !block_off || !out_off || !consumed) {
+    set_error("sai_bgzf_scan: bad argument");
+    return SAI_E_ARG;
+  }
+  int64_t at = 0, n = 0, out = 0;
+  out_off[0] = 0;
+  while (n < max_blocks && at < len) {
+    int64_t payload = 0;
+    const int64_t bs = block_size(data + at, len - at, &payload);
+    if (bs < 0) {
+      set_error("not a BGZF block at offset %lld", (long long)at);
+      return SAI_E_ARG;
+    }
+    if (bs == 0) break;  // incomplete block: the caller supplies more bytes
+    const int64_t isize = le32(data + at + bs - 4);
+    if (n > 0 && out + isize > max_out_bytes) break;
+    block_off[n] = at;
+    out += isize;
+    out_off[++n] = out;
+    at += bs;
+  }
+  *consumed = at;
+  return n;
+}
+
+int sai_bgzf_inflate(const uint8_t* data, const int64_t* block_off, const int64_t* out_off, int64_t n_blocks,
+                     uint8_t* out, int32_t n_threads) {
+  if (!data || !block_off || !out_off || n_blocks < 0 || (n_blocks > 0 && !out)) {
+    set_error("sai_bgzf_inflate: bad argument");
+    return SAI_E_ARG;
+  }
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n_blocks / 4));
+  std::atomic<int64_t> next{0};
+  std::atomic<int64_t> bad{-1};
+  auto work = [&]() {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) {
+      bad.store(0);
+      return;
+    }
+    for (;;) {
+      const int64_t b0 = next.fetch_add(16);
+      if (b0 >= n_blocks || bad.load(std::memory_order_relaxed) >= 0) break;
+      const int64_t b1 = std::min(n_blocks, b0 + 16);
+      for (int64_t b = b0; b < b1; ++b) {
+        const uint8_t* p = data + block_off[b];
+        int64_t payload = 0;
+        const int64_t bs = block_size(p, (int64_t)1 << 20, &payload);  // validated by the scan
+        const int64_t want = out_off[b + 1] - out_off[b];
+        if (want == 0) continue;  // empty block (the EOF marker)
+        inflateReset(&zs);
+        zs.next_in = const_cast<Bytef*>(p + payload);
+        zs.avail_in = (uInt)(bs - payload - 8);
+        zs.next_out = out + out_off[b];
+        zs.avail_out = (uInt)want;
+        const bool ok = inflate(&zs, Z_FINISH) == Z_STREAM_END && (int64_t)zs.total_out == want &&
+                        crc32(crc32(0L, Z_NULL, 0), out + out_off[b], (uInt)want) == le32(p + bs - 8);
+        if (!ok) {
+          bad.store(b);
+          break;
+        }
+      }
+    }
+    inflateEnd(&zs);
+  };
+  if (n_threads <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_threads; ++i) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  if (bad.load() >= 0) {
+    set_error("BGZF block %lld is corrupt", (long long)bad.load());
+    return SAI_E_ARG;
+  }
+  return SAI_OK;
+}
+
+}  // extern "C"

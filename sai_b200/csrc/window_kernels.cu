@@ -516,6 +516,9 @@ __global__ void __launch_bounds__(kWinWarps * 32, kMinBlocks)
     // ---- B: all searches together ----
     int bnd[2 * kBatch];
     warp_lower_bound_batch<kBatch>(P.pos, P.n_sites, key, lane, bnd);
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k)  // end < start: the reference's masks select nothing (window_generator.py:173-174)
+      if (bnd[2 * k + 1] < bnd[2 * k]) bnd[2 * k + 1] = bnd[2 * k];
 
     // ---- C: masks of all windows ----
     uint32_t a[kBatch][2], b[kBatch][2];

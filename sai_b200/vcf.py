@@ -213,7 +213,8 @@ def load_population_group(
     return data, samples
 
 
-def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chunk_bytes=64 << 20):
+def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chunk_bytes=64 << 20,
+                 batch_bytes=256 << 20):
     """One pass of the native parser (``sai_vcf_parse_gt``) over the file.
     ``requests`` = list of (sample_name, ploidy); returns ``(pos, gt)`` with one
     int8 column per request, or ``None`` for the sample names line missing."""
@@ -285,6 +286,54 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
                     tail += b"\n"
                     buf = np.frombuffer(tail, dtype=np.uint8)
                     parse_buffer(buf.ctypes.data, len(tail))
+    elif _is_bgzf(vcf_file):
+        # bgzip: independent <= 64 KB blocks, inflated in parallel by the native library in
+        # batches of ~256 MB of text; an incomplete last line is carried to the next batch
+        import mmap
+
+        with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            view = np.frombuffer(mm, dtype=np.uint8)
+            try:
+                base, total = view.ctypes.data, len(mm)
+                max_blocks = 1 << 14
+                block_off = np.empty(max_blocks, dtype=np.int64)
+                out_off = np.empty(max_blocks + 1, dtype=np.int64)
+                at, carry = 0, b""
+                while True:
+                    n = int(lib.sai_bgzf_scan(base + at, total - at, max_blocks, batch_bytes, block_off.ctypes.data,
+                                              out_off.ctypes.data, C.byref(consumed))) if at < total else 0
+                    if n < 0:
+                        _cabi.check(n)
+                    last = n == 0 or at + consumed.value >= total
+                    text_len = int(out_off[n]) if n else 0
+                    buf = np.empty(len(carry) + text_len + 1, dtype=np.uint8)
+                    buf[: len(carry)] = np.frombuffer(carry, dtype=np.uint8)
+                    if n:
+                        _cabi.check(lib.sai_bgzf_inflate(base + at, block_off.ctypes.data, out_off.ctypes.data, n,
+                                                         buf.ctypes.data + len(carry), n_threads))
+                        at += consumed.value
+                    length = len(carry) + text_len
+                    start_at = 0
+                    if cols is None:
+                        head = buf[:length].tobytes() if length < (64 << 20) else bytes(buf[: 64 << 20])
+                        h = head.find(b"#CHROM")
+                        he = head.find(b"\n", h) if h >= 0 else -1
+                        if h < 0 or he < 0:
+                            if last:
+                                break
+                            carry = buf[:length].tobytes()
+                            continue
+                        cols, ploidies = header_columns(head[h:he])
+                        start_at = he + 1
+                    if last and length > start_at and buf[length - 1] != 10:
+                        buf[length] = 10  # last line without a newline
+                        length += 1
+                    done = start_at + (parse_buffer(buf.ctypes.data + start_at, length - start_at) if length > start_at else 0)
+                    carry = buf[done:length].tobytes()
+                    if last:
+                        break
+            finally:
+                del view
     else:
         with gzip.open(vcf_file, "rb") as f:
             carry = b""
@@ -316,6 +365,34 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
     if not pos_parts:
         return np.empty(0, dtype=np.int32), np.empty((0, n_out), dtype=np.int8)
     return np.concatenate(pos_parts), np.concatenate(gt_parts)
+
+
+def _is_bgzf(path: str) -> bool:
+    """bgzip container (gzip members with a 'BC' extra subfield, SAM spec 4.1)?"""
+    import ctypes as C
+
+    from . import _cabi
+
+    with open(path, "rb") as f:
+        head = f.read(1 << 16)
+    return bool(_cabi.load().sai_is_bgzf(head, len(head))) if len(head) >= 18 else False
+
+
+def write_bgzf(path: str, data: bytes, block: int = 0xFF00, level: int = 6) -> None:
+    """Writes ``data`` as a bgzip file (tests / tools; no htslib here)."""
+    import struct
+    import zlib
+
+    with open(path, "wb") as f:
+        for at in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if at is None else data[at : at + block]
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            payload = co.compress(chunk) + co.flush()
+            bsize = 12 + 6 + len(payload) + 8
+            f.write(struct.pack("<BBBBIBBH", 31, 139, 8, 4, 0, 0, 255, 6))
+            f.write(b"BC" + struct.pack("<HH", 2, bsize - 1))
+            f.write(payload)
+            f.write(struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
 
 
 def _is_gzip(path: str) -> bool:

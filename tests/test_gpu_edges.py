@@ -80,11 +80,12 @@ def test_degenerate_windows_and_coordinates(engine):
             np.where(rng.random((n, 2)) < 0.5, 2, 0).astype(np.int8)]
     wins = [(1, 10), (int(pos[0]), int(pos[0])), (int(pos[-1]), int(pos[-1]) + 5), (int(pos[-1]) + 1, 2**40),
             (1, 2**40), (int(pos[10]), int(pos[200])), (int(pos[10]), int(pos[200])), (int(pos[50]) + 1, int(pos[51]) - 1),
-            (2**33, 2**34), (int(pos[100]), int(pos[100]) + 3)]
+            (2**33, 2**34), (int(pos[100]), int(pos[100]) + 3), (int(pos[200]), int(pos[10])), (2**40, 1)]
     res = _score(engine, mats, [2, 2, 2], pos, wins, 1, False, U, Q)
     for i, w in enumerate(wins):
         _compare(res, i, _expect(mats, [2, 2, 2], pos, w, 1, False, U, Q))
     assert res.nsnps[0, 4] == n and res.nsnps[0, 0] == 0 and res.nsnps[0, 8] == 0
+    assert res.nsnps[0, 10] == 0 and res.nsnps[0, 11] == 0  # end < start: empty, like the reference's masks
 
 
 def test_many_windows_in_any_order(engine):
