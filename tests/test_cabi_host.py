@@ -369,3 +369,57 @@ def test_native_vcf_parser_segments_and_row_cap():
         assert np.array_equal(p1, p2) and np.array_equal(g1, g2) and at1 == at2, (cap, nt)
     # spot-check values against the token table
     assert set(np.unique(g1)) <= set(range(-3, 23))
+
+
+def test_bgzf_parallel_inflate_and_reader(tmp_path):
+    """bgzip input: blocks are indexed and inflated in parallel by the native library; reading a
+    bgzipped VCF gives exactly what the plain-text and the plain-gzip files give, for batch sizes
+    that cut lines in the middle; corrupt blocks are reported."""
+    import ctypes as C
+    import gzip
+
+    from sai_b200 import _cabi
+    from sai_b200.vcf import _is_bgzf, _native_read, write_bgzf
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(5)
+    n_rec, n_smp = 600, 300
+    tok = np.array(["0|0", "0|1", "1|0", "1|1", ".|.", "0/1"])
+    pos = np.cumsum(rng.integers(1, 50, size=n_rec))
+    lines = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n_smp))]
+    for i in range(n_rec):
+        g = rng.choice(len(tok), size=n_smp, p=[.6, .1, .1, .1, .05, .05])
+        lines.append(f"1\t{pos[i]}\t.\tA\tG\t.\t.\t.\tGT\t" + "\t".join(tok[g]))
+    text = ("\n".join(lines) + "\n").encode()
+    plain, bgz, gz = tmp_path / "a.vcf", tmp_path / "a.vcf.gz", tmp_path / "b.vcf.gz"
+    plain.write_bytes(text)
+    write_bgzf(str(bgz), text, block=4000)
+    with gzip.open(gz, "wb") as f:
+        f.write(text)
+    assert _is_bgzf(str(bgz)) and not _is_bgzf(str(gz)) and not _is_bgzf(str(plain))
+    # raw API: scan + inflate == the text
+    raw = np.frombuffer(bgz.read_bytes(), dtype=np.uint8)
+    nb = 1 << 12
+    block_off, out_off = np.empty(nb, np.int64), np.empty(nb + 1, np.int64)
+    consumed = C.c_int64(0)
+    n = lib.sai_bgzf_scan(raw.ctypes.data, raw.size, nb, 1 << 40, block_off.ctypes.data, out_off.ctypes.data, C.byref(consumed))
+    assert n == -(-len(text) // 4000) + 1 and consumed.value == raw.size and out_off[n] == len(text)
+    out = np.empty(len(text), np.uint8)
+    _cabi.check(lib.sai_bgzf_inflate(raw.ctypes.data, block_off.ctypes.data, out_off.ctypes.data, n, out.ctypes.data, 3))
+    assert out.tobytes() == text
+    bad = raw.copy()
+    bad[int(block_off[5]) + 30] ^= 0xFF
+    with pytest.raises(ValueError, match="corrupt"):
+        _cabi.check(lib.sai_bgzf_inflate(bad.ctypes.data, block_off.ctypes.data, out_off.ctypes.data, n, out.ctypes.data, 2))
+    # the reader: same rows from the three containers, for several batch sizes
+    req = [(f"s{i}", 2) for i in rng.permutation(n_smp)[:40]]
+    p0, g0 = _native_read(str(plain), "1", None, None, req, None)
+    assert p0.shape[0] == n_rec
+    for path, kw in ((gz, {}), (bgz, {}), (bgz, dict(batch_bytes=10_000)), (bgz, dict(batch_bytes=1))):
+        p1, g1 = _native_read(str(path), "1", None, None, req, None, **kw)
+        assert np.array_equal(p0, p1) and np.array_equal(g0, g1), (path, kw)
+    # no trailing newline + region filter
+    write_bgzf(str(bgz), text[:-1], block=3000)
+    p1, g1 = _native_read(str(bgz), "1", int(pos[10]), int(pos[500]), req, None, batch_bytes=50_000)
+    keep = (p0 >= pos[10]) & (p0 <= pos[500])
+    assert np.array_equal(p0[keep], p1) and np.array_equal(g0[keep], g1)
