@@ -53,7 +53,12 @@ def score_populations(
     out_data: Optional[dict[str, PopData]] = None,
     num_src: Optional[int] = None,
 ) -> list[dict[str, Any]]:
-    """Item dicts for every (ref, tgt, src-combination, outgroup) x window."""
+    """Item dicts for every (ref, tgt, src-combination, outgroup) x window.
+
+    When every population sits on the same positions and every target population has the same
+    windows (always the case for ``ChunkPreprocessor.run(chr, start, end)`` on one VCF), ALL
+    populations are packed once and the population product becomes up to ``SAI_MAX_JOBS`` jobs per
+    genotype pass, instead of one pack + one transfer + one pass per combination."""
     stats = [s for s in stat_config.root.keys() if s in ("U", "Q")]
     four = [s for s in stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd") and stat_config.root[s] is True]
     dd = any(s == "DD" and stat_config.root[s] is True for s in stat_config.root.keys())
@@ -61,46 +66,34 @@ def score_populations(
     src_combos = list(combinations(src_data.keys(), num_src))
     outs = list(out_data.keys()) if out_data else [None]
     src_ploidies = ploidy_config.get_ploidy("src")
+    combos = list(product(ref_data, tgt_data, src_combos, outs))
     items: list[dict[str, Any]] = []
+    if not combos:
+        return items
 
-    for ref_pop, tgt_pop, src_comb, out_pop in product(ref_data, tgt_data, src_combos, outs):
-        windows = windows_by_tgt[tgt_pop]
-        members = [ref_data[ref_pop], tgt_data[tgt_pop]] + [src_data[s] for s in src_comb]
-        if out_pop is not None:
-            members.append(out_data[out_pop])
-        pos, rows = _common_rows(members)
-        n_src = len(src_comb)
-        # positional zip of src genotypes / y_list / ploidies, exactly as
-        # feature_preprocessor.py:160,168-170 and stat_utils.py:116-119 do
-        ploidy = [ploidy_config.get_ploidy("ref", ref_pop), ploidy_config.get_ploidy("tgt", tgt_pop)]
-        ploidy += list(src_ploidies[:n_src])
-        if len(ploidy) != 2 + n_src:
-            raise ValueError("The length of src_gts_list and src ploidies must match.")
+    def job_for(ref_pop, tgt_pop, ref_idx, tgt_idx, src_idx):
         specs = {}
         for s in stats:
             prm = stat_config.get_parameters(s)
             spec = {"w": prm["ref"][ref_pop], "y_list": list(prm["src"].values())}
             spec["x" if s == "U" else "quantile"] = prm["tgt"][tgt_pop]
             specs[s] = spec
-        job = make_job(0, 1, list(range(2, 2 + n_src)), anc_allele_available, specs.get("U"), specs.get("Q"))
-        n_pack = 2 + n_src
-        if out_pop is not None and four:
-            ploidy.append(ploidy_config.get_ploidy("outgroup", out_pop))
-            n_pack += 1
-        pg = pack_populations(rows[:n_pack], ploidy[:n_pack], pos, keep_negatives=dd)
-        res = engine.score(pg, windows, [job]) if (stats or four or dd) else None
-        four_vals = None
-        if four:
-            sums = engine.pattern_sums(pg, 0, 1, 2 + n_src if (out_pop is not None) else -1, list(range(2, 2 + n_src)))
-            four_vals = four_pop_values(sums)
-        dd_vals = None
-        if dd:
-            ref_sum, tgt_sum = engine.dd_sums(pg, 0, 1, list(range(2, 2 + n_src)))
-            dd_vals = dd_values(ref_sum, tgt_sum, rows[0].shape[1], rows[1].shape[1],
-                                [rows[2 + k].shape[1] for k in range(n_src)])
+        return make_job(ref_idx, tgt_idx, src_idx, anc_allele_available, specs.get("U"), specs.get("Q"))
+
+    def src_ploidy_list(n_src):
+        # positional zip of src genotypes / y_list / ploidies, exactly as
+        # feature_preprocessor.py:160,168-170 and stat_utils.py:116-119 do
+        pl = list(src_ploidies[:n_src])
+        if len(pl) != n_src:
+            raise ValueError("The length of src_gts_list and src ploidies must match.")
+        return pl
+
+    def emit(combo, windows, pos, res, j, four_vals, dd_vals):
+        ref_pop, tgt_pop, src_comb, out_pop = combo
+        n_src = len(src_comb)
         pos_dtype = np.asarray(pos).dtype
         for i, (start, end) in enumerate(windows):
-            nsnps = int(res.nsnps[0, i]) if res is not None else int(
+            nsnps = int(res.nsnps[j, i]) if res is not None else int(
                 np.count_nonzero((pos >= start) & (pos <= end))
             )
             item = {
@@ -129,17 +122,96 @@ def score_populations(
                     item[s] = np.nan
                     item["cdd_pos"][s] = np.array([])
                 elif s == "U":
-                    item[s] = int(res.u[0, i])
-                    item["cdd_pos"][s] = res.u_positions(0, i).astype(pos_dtype)
+                    item[s] = int(res.u[j, i])
+                    item["cdd_pos"][s] = res.u_positions(j, i).astype(pos_dtype)
                 else:
-                    qv = res.q[0, i]
+                    qv = res.q[j, i]
                     if np.isnan(qv):  # q_statistic.py:96-98
                         item[s] = np.nan
                         item["cdd_pos"][s] = np.array([])
                     else:
                         item[s] = np.float64(qv)
-                        item["cdd_pos"][s] = res.q_positions(0, i).astype(pos_dtype)
+                        item["cdd_pos"][s] = res.q_positions(j, i).astype(pos_dtype)
             items.append(item)
+
+    def extras(pg, ref_idx, tgt_idx, src_idx, out_idx, n_ref, n_tgt, n_srcs):
+        four_vals = dd_vals = None
+        if four:
+            four_vals = four_pop_values(engine.pattern_sums(pg, ref_idx, tgt_idx, out_idx, src_idx))
+        if dd:
+            ref_sum, tgt_sum = engine.dd_sums(pg, ref_idx, tgt_idx, src_idx)
+            dd_vals = dd_values(ref_sum, tgt_sum, n_ref, n_tgt, n_srcs)
+        return four_vals, dd_vals
+
+    # ---- all populations in one packed matrix, the product as fused jobs ------------------
+    use_out = bool(out_data) and bool(four)
+    everyone = list(ref_data.values()) + list(tgt_data.values()) + list(src_data.values())
+    if use_out:
+        everyone += list(out_data.values())
+    win_lists = list(windows_by_tgt.values())
+    fused = (
+        len(combos) > 1
+        and len(src_combos) == 1
+        and len(everyone) <= _cabi.MAX_POPS
+        and _same_positions(everyone)
+        and all(w == win_lists[0] for w in win_lists[1:])
+        and (stats or four or dd)
+    )
+    if fused:
+        index, mats, ploidy = {}, [], []
+        for group, data in (("ref", ref_data), ("tgt", tgt_data)):
+            for name, d in data.items():
+                index[(group, name)] = len(mats)
+                mats.append(d.GT)
+                ploidy.append(ploidy_config.get_ploidy(group, name))
+        src_comb = src_combos[0]
+        for name, pl in zip(src_comb, src_ploidy_list(len(src_comb))):
+            index[("src", name)] = len(mats)
+            mats.append(src_data[name].GT)
+            ploidy.append(pl)
+        if use_out:
+            for name, d in out_data.items():
+                index[("out", name)] = len(mats)
+                mats.append(d.GT)
+                ploidy.append(ploidy_config.get_ploidy("outgroup", name))
+        pos = everyone[0].POS
+        windows = win_lists[0]
+        pg = pack_populations(mats, ploidy, pos, keep_negatives=dd)
+        src_idx = [index[("src", s)] for s in src_comb]
+        for b0 in range(0, len(combos), _cabi.MAX_JOBS):
+            batch = combos[b0 : b0 + _cabi.MAX_JOBS]
+            jobs = [job_for(r, t, index[("ref", r)], index[("tgt", t)], src_idx) for r, t, _, _ in batch]
+            res = engine.score(pg, windows, jobs)
+            for j, combo in enumerate(batch):
+                r, t, _, o = combo
+                four_vals, dd_vals = extras(
+                    pg, index[("ref", r)], index[("tgt", t)], src_idx, index[("out", o)] if (use_out and o is not None) else -1,
+                    ref_data[r].GT.shape[1], tgt_data[t].GT.shape[1], [src_data[s].GT.shape[1] for s in src_comb])
+                emit(combo, windows, pos, res, j, four_vals, dd_vals)
+        return items
+
+    # ---- general case: one packed matrix per combination ----------------------------------
+    for combo in combos:
+        ref_pop, tgt_pop, src_comb, out_pop = combo
+        windows = windows_by_tgt[tgt_pop]
+        members = [ref_data[ref_pop], tgt_data[tgt_pop]] + [src_data[s] for s in src_comb]
+        if out_pop is not None:
+            members.append(out_data[out_pop])
+        pos, rows = _common_rows(members)
+        n_src = len(src_comb)
+        ploidy = [ploidy_config.get_ploidy("ref", ref_pop), ploidy_config.get_ploidy("tgt", tgt_pop)]
+        ploidy += src_ploidy_list(n_src)
+        src_idx = list(range(2, 2 + n_src))
+        job = job_for(ref_pop, tgt_pop, 0, 1, src_idx)
+        n_pack = 2 + n_src
+        if out_pop is not None and four:
+            ploidy.append(ploidy_config.get_ploidy("outgroup", out_pop))
+            n_pack += 1
+        pg = pack_populations(rows[:n_pack], ploidy[:n_pack], pos, keep_negatives=dd)
+        res = engine.score(pg, windows, [job]) if (stats or four or dd) else None
+        four_vals, dd_vals = extras(pg, 0, 1, src_idx, 2 + n_src if (out_pop is not None and four) else -1,
+                                    rows[0].shape[1], rows[1].shape[1], [rows[2 + k].shape[1] for k in range(n_src)])
+        emit(combo, windows, pos, res, 0, four_vals, dd_vals)
     return items
 
 
