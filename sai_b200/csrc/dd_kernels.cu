@@ -29,8 +29,9 @@ namespace sai {
 
 constexpr int kHistWarps = 8;
 constexpr int kDdWarps = 8;
-constexpr int kDdChunk = 8;    // source individuals per pass (8 | 32: one group per chunk)
+constexpr int kDdChunkMax = 8; // source individuals per pass: 1, 2, 4 or 8 (all divide 32: one group per chunk)
 constexpr int kMaxCodes = 15;  // called values of a 4-plane population
+constexpr int kDdUnroll = 2;   // table entries per lane and trip in k_window_dd
 
 struct HistParams {
   const uint2* packed;
@@ -173,15 +174,6 @@ __device__ __forceinline__ long long called_distance(const DdParams& P, const Dd
   return d;
 }
 
-// bit-plane code of individual `a` of population `pp` at `site`
-__device__ __forceinline__ int code_of(const DdParams& P, const DdPop& pp, int site, int a) {
-  const uint2* col = P.packed + ((size_t)(site >> 5) * P.pairs_per_site + pp.pair_off) * kTile + (site & 31);
-  const int g = a >> 5, bit = a & 31;
-  int code = 0;
-  for (int b = 0; b < pp.bits; ++b) code |= ((plane_word(col, g * pp.bits + b) >> bit) & 1) << b;
-  return code;
-}
-
 // raw value of a missing call: entry (site, ind) of the population's table slice
 __device__ __forceinline__ bool raw_lookup(const DdParams& P, const DdPop& pp, int site, int ind, int& raw) {
   int64_t lo = pp.neg_lo, hi = pp.neg_hi;
@@ -200,16 +192,8 @@ __device__ __forceinline__ bool raw_lookup(const DdParams& P, const DdPop& pp, i
   return false;
 }
 
-// value of source individual `a` at `site`, raw when missing
-__device__ __forceinline__ int src_value(const DdParams& P, const DdPop& sp, int site, int a) {
-  const int code = code_of(P, sp, site, a);
-  if (code != (1 << sp.bits) - 1) return code;
-  int raw = -1;
-  if (!raw_lookup(P, sp, site, a, raw)) *P.err = 1;
-  return raw;
-}
-
 // grid: x = windows (one warp each, grid-stride), y = source population
+template <int kDdChunk>
 __global__ void __launch_bounds__(kDdWarps * 32) k_window_dd(const __grid_constant__ DdParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.y;
@@ -256,30 +240,77 @@ __global__ void __launch_bounds__(kDdWarps * 32) k_window_dd(const __grid_consta
           const DdPop& pp = t == 0 ? P.ref : P.tgt;
           const int32_t* h = P.hist + (size_t)pp.code_base * P.stride + s;
           const int n_called = (1 << pp.bits) - 1;
-          for (int u = 0; u < n_called; ++u) {
-            const long long c = __ldg(h + (size_t)u * P.stride);
+          if (sp.bits == 2) {
+            // distance of each of the three called source values to the population, once per site
+            long long D0 = 0, D1 = 0, D2 = 0;
+            for (int u = 0; u < n_called; ++u) {
+              const long long c = __ldg(h + (size_t)u * P.stride);
+              D0 += c * u;
+              D1 += c * (u > 1 ? u - 1 : 1 - u);
+              D2 += c * (u > 2 ? u - 2 : 2 - u);
+            }
 #pragma unroll
             for (int j = 0; j < kDdChunk; ++j) {
-              if (code[j] != s_missing) {
-                const int diff = code[j] - u;
-                const long long d = c * (diff < 0 ? -diff : diff);
-                if (t == 0) R[j] += d; else T[j] += d;
+              const long long d = code[j] == 0 ? D0 : (code[j] == 1 ? D1 : (code[j] == 2 ? D2 : 0));
+              if (t == 0) R[j] += d; else T[j] += d;
+            }
+          } else {
+            for (int u = 0; u < n_called; ++u) {
+              const long long c = __ldg(h + (size_t)u * P.stride);
+#pragma unroll
+              for (int j = 0; j < kDdChunk; ++j) {
+                if (code[j] != s_missing) {
+                  const int diff = code[j] - u;
+                  const long long d = c * (diff < 0 ? -diff : diff);
+                  if (t == 0) R[j] += d; else T[j] += d;
+                }
               }
             }
           }
         }
       }
-      // (2) missing ref / tgt individuals against every source individual of the chunk
+      // (2) missing ref / tgt individuals against every source individual of the chunk.  kDdUnroll
+      //     table entries per lane and trip: the chain entry -> site -> source planes is two dependent
+      //     memory round trips, so independent chains are what hides the latency here.
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        for (int64_t e = e_lo[t] + lane; e < e_hi[t]; e += 32) {
-          const int site = __ldg(P.neg_site + e), v = __ldg(P.neg_val + e);
+        for (int64_t e0 = e_lo[t] + lane; e0 < e_hi[t]; e0 += 32 * kDdUnroll) {
+          int site[kDdUnroll], v[kDdUnroll];
+          bool live[kDdUnroll];
 #pragma unroll
-          for (int j = 0; j < kDdChunk; ++j) {
-            if (a0 + j < m) {
-              const int diff = src_value(P, sp, site, a0 + j) - v;
-              const long long d = diff < 0 ? -diff : diff;
-              if (t == 0) R[j] += d; else T[j] += d;
+          for (int u = 0; u < kDdUnroll; ++u) {
+            const int64_t e = e0 + 32 * u;
+            live[u] = e < e_hi[t];
+            site[u] = live[u] ? __ldg(P.neg_site + e) : 0;
+            v[u] = live[u] ? __ldg(P.neg_val + e) : 0;
+          }
+          uint32_t w[kDdUnroll][4];
+#pragma unroll
+          for (int u = 0; u < kDdUnroll; ++u) {
+            const uint2* col =
+                P.packed + ((size_t)(site[u] >> 5) * P.pairs_per_site + sp.pair_off) * kTile + (site[u] & 31);
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              w[u][b] = (live[u] && b < sp.bits) ? plane_word(col, (a0 >> 5) * sp.bits + b) : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < kDdUnroll; ++u) {
+            if (!live[u]) continue;
+#pragma unroll
+            for (int j = 0; j < kDdChunk; ++j) {
+              if (a0 + j < m) {
+                const int bit = (a0 + j) & 31;
+                int sv = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) sv |= (int)((w[u][b] >> bit) & 1u) << b;
+                if (sv == s_missing) {  // the source call is missing too: its raw value is in the table
+                  sv = -1;
+                  if (!raw_lookup(P, sp, site[u], a0 + j, sv)) *P.err = 1;
+                }
+                const int diff = sv - v[u];
+                const long long d = diff < 0 ? -diff : diff;
+                if (t == 0) R[j] += d; else T[j] += d;
+              }
             }
           }
         }
@@ -434,7 +465,18 @@ extern "C" int sai_window_dd(const sai_layout* lay, const void* d_packed, const 
   const int64_t want = (n_windows + kDdWarps - 1) / kDdWarps;
   const int64_t cap = (int64_t)sm_count() * 8;
   const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_src);
-  k_window_dd<<<grid, kDdWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  // chunk = the smallest of 1, 2, 4, 8 that holds the largest source population (less predicated-off work)
+  int m_top = 1;
+  for (int k = 0; k < n_src; ++k) m_top = m_top > P.src[k].n_samples ? m_top : P.src[k].n_samples;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (m_top <= 1)
+    k_window_dd<1><<<grid, kDdWarps * 32, 0, st>>>(P);
+  else if (m_top <= 2)
+    k_window_dd<2><<<grid, kDdWarps * 32, 0, st>>>(P);
+  else if (m_top <= 4)
+    k_window_dd<4><<<grid, kDdWarps * 32, 0, st>>>(P);
+  else
+    k_window_dd<kDdChunkMax><<<grid, kDdWarps * 32, 0, st>>>(P);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }

@@ -145,6 +145,46 @@ def test_dd_cases_gpu():
     assert np.isclose(r["value"][0], 0.5)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_dd_random_vs_oracle(seed, engine):
+    """DD sums against the oracle for shapes the fixtures do not reach: ploidy up to 8 (4 planes),
+    missing values anywhere in -ploidy..-1, more than 8 and more than 32 source individuals
+    (chunks / groups), several source populations, overlapping and empty windows."""
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import dd_values, make_job
+
+    rng = np.random.default_rng(100 + seed)
+    n_sites = int(rng.integers(50, 400))
+    ploidy = [int(rng.choice([1, 2, 3, 4, 8])) for _ in range(4)]
+    n_ind = [int(rng.integers(1, 90)), int(rng.integers(1, 70)), int(rng.choice([1, 3, 9, 33, 41])), int(rng.integers(1, 12))]
+    f = rng.beta(0.4, 1.0, size=n_sites)
+    mats = []
+    for n, p in zip(n_ind, ploidy):
+        g = rng.binomial(p, f[:, None], size=(n_sites, n)).astype(np.int8)
+        miss = rng.random(g.shape) < float(rng.choice([0.0, 0.03, 0.3]))
+        g[miss] = -rng.integers(1, p + 1, size=int(miss.sum()))
+        mats.append(g)
+    pos = np.cumsum(rng.integers(1, 30, size=n_sites)).astype(np.int32)
+    top = int(pos[-1])
+    wins = [(1, top), (int(pos[3]), int(pos[n_sites // 2])), (top + 1, top + 50), (int(pos[10]), int(pos[10]))]
+    wins += [(s, s + 999) for s in range(1, top, 500)]
+    pg = pack_populations(mats, ploidy, pos, keep_negatives=True)
+    engine.score(pg, wins, [make_job(0, 1, [2, 3], True)])
+    ref_sum, tgt_sum = engine.dd_sums(pg, 0, 1, [2, 3])
+    got = dd_values(ref_sum, tgt_sum, n_ind[0], n_ind[1], n_ind[2:])
+    m64 = [m.astype(np.int64) for m in mats]
+    for i, (a, b) in enumerate(wins):
+        keep = (pos >= a) & (pos <= b)
+        if not keep.any():
+            assert not ref_sum[:, i].any() and not tgt_sum[:, i].any()
+            continue
+        exp = orc.dd_statistic(m64[0][keep], m64[1][keep], [m64[2][keep], m64[3][keep]])
+        for k in range(2):
+            assert float(got[k][i]).hex() == float(exp[k]).hex(), (seed, i, k)
+            assert np.array_equal(ref_sum[k, i, : n_ind[2 + k]],
+                                  orc.cityblock_sums(m64[2 + k][keep], m64[0][keep]).sum(axis=1).astype(np.int64))
+
+
 def test_dd_needs_negative_table(engine):
     """The bit-planes keep one missing code; DD refuses to run without the raw
     values, and the engine checks that the table covers every missing call."""
