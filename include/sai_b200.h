@@ -155,6 +155,13 @@ int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* chrom, int64
                          int64_t n_anc, int32_t* out_pos, int8_t* out_gt, int64_t row_stride,
                          int64_t rows_cap, int64_t* bytes_consumed, int32_t n_threads);
 
+/* First / last POS (file order) and number of records of `chrom` among the complete lines of
+ * `text` (replaces the pysam loop of ChunkGenerator.__init__, chunk_generator.py:64-76).
+ * *first = *last = -1 when the chromosome does not occur. */
+int sai_vcf_chrom_span(const char* text, int64_t len, const char* chrom, int64_t* first,
+                       int64_t* last, int64_t* n_records, int64_t* bytes_consumed,
+                       int32_t n_threads);
+
 /* BGZF (bgzip) input: a .vcf.gz written by bgzip is a sequence of independent gzip members of
  * <= 64 KB.  sai_bgzf_scan indexes the complete blocks at the start of `data` (at most
  * max_blocks, stopping before the uncompressed total exceeds max_out_bytes unless it is the

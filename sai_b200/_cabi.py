@@ -98,6 +98,7 @@ SYMBOLS = {
         _I64,
         [_P, _I64, C.c_char_p, _I64, _I64, _P, _P, _I32, _P, _P, _I64, _P, _P, _I64, _I64, C.POINTER(_I64), _I32],
     ),
+    "sai_vcf_chrom_span": (C.c_int, [_P, _I64, C.c_char_p, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64), _I32]),
     "sai_is_bgzf": (_I32, [_P, _I64]),
     "sai_bgzf_scan": (_I64, [_P, _I64, _I64, _I64, _P, _P, C.POINTER(_I64)]),
     "sai_bgzf_inflate": (C.c_int, [_P, _P, _P, _I64, _P, _I32]),

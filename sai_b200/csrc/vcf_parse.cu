@@ -290,3 +290,71 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
   }
   return n_rows;
 }
+
+
+// First and last POS (in file order) and the number of records of `chrom` among the complete
+// lines of `text` -- what ChunkGenerator.__init__ finds by iterating pysam's fetch(chrom)
+// (sai/generators/chunk_generator.py:64-76).  Parallel over byte segments cut at line starts.
+extern "C" int sai_vcf_chrom_span(const char* text, int64_t len, const char* chrom, int64_t* first,
+                                  int64_t* last, int64_t* n_records, int64_t* bytes_consumed,
+                                  int32_t n_threads) {
+  if (!text || len < 0 || !chrom || !first || !last || !n_records || !bytes_consumed) {
+    set_error("sai_vcf_chrom_span: bad argument");
+    return SAI_E_ARG;
+  }
+  const size_t chrom_len = strlen(chrom);
+  const void* last_nl = len > 0 ? memrchr(text, '\n', (size_t)len) : nullptr;
+  const char* const complete_end = last_nl ? static_cast<const char*>(last_nl) + 1 : text;
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  const int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, (complete_end - text) / (1 << 20)));
+  std::vector<const char*> seg(n_seg + 1);
+  seg[0] = text;
+  seg[n_seg] = complete_end;
+  for (int i = 1; i < n_seg; ++i) {
+    const char* guess = text + (complete_end - text) / n_seg * i;
+    if (guess < seg[i - 1]) guess = seg[i - 1];
+    const void* nl = guess < complete_end ? memchr(guess, '\n', (size_t)(complete_end - guess)) : nullptr;
+    seg[i] = nl ? static_cast<const char*>(nl) + 1 : complete_end;
+  }
+  struct Span {
+    int64_t first = -1, last = -1, n = 0;
+  };
+  std::vector<Span> out(n_seg);
+  auto scan = [&](int si) {
+    Span sp;
+    const char* p = seg[si];
+    const char* const send = seg[si + 1];
+    while (p < send) {
+      const void* nl = memchr(p, '\n', (size_t)(send - p));
+      if (!nl) break;
+      const char* lend = static_cast<const char*>(nl);
+      const char* line = p;
+      p = lend + 1;
+      if (line == lend || *line == '#') continue;
+      if ((size_t)(lend - line) <= chrom_len || memcmp(line, chrom, chrom_len) != 0 || line[chrom_len] != '\t') continue;
+      int64_t pos = 0;
+      for (const char* q = line + chrom_len + 1; q < lend && *q >= '0' && *q <= '9'; ++q) pos = pos * 10 + (*q - '0');
+      if (sp.first < 0) sp.first = pos;
+      sp.last = pos;
+      ++sp.n;
+    }
+    out[si] = sp;
+  };
+  if (n_seg == 1) {
+    scan(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_seg; ++i) th.emplace_back(scan, i);
+    for (auto& t : th) t.join();
+  }
+  *first = *last = -1;
+  *n_records = 0;
+  for (const Span& sp : out) {
+    if (sp.n == 0) continue;
+    if (*first < 0) *first = sp.first;
+    *last = sp.last;
+    *n_records += sp.n;
+  }
+  *bytes_consumed = (int64_t)(complete_end - text);
+  return SAI_OK;
+}

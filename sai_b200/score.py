@@ -14,30 +14,17 @@ from pathlib import Path
 
 from .configs import load_config
 from .preprocessors import ChunkPreprocessor
-from .vcf import _open_text
+from .vcf import chromosome_span as _vcf_chromosome_span
 from .windows import split_genome, split_windows_ranges
 
 
 def chromosome_span(vcf_file: str, chr_name: str) -> tuple[int, int]:
     """First and last POS of ``chr_name`` (what ``ChunkGenerator.__init__``
     finds with pysam, sai/generators/chunk_generator.py:64-76)."""
-    first = last = None
-    with _open_text(vcf_file) as f:
-        for line in f:
-            if line.startswith("#"):
-                continue
-            tab = line.find("\t")
-            if line[:tab] != chr_name:
-                if first is not None:
-                    break
-                continue
-            p = int(line[tab + 1 : line.find("\t", tab + 1)])
-            if first is None:
-                first = p
-            last = p
-    if first is None:
+    span = _vcf_chromosome_span(vcf_file, chr_name)
+    if span is None:
         raise ValueError(f"Chromosome {chr_name} not found in VCF.")
-    return first, last
+    return span[0], span[1]
 
 
 def score(

@@ -213,6 +213,142 @@ def load_population_group(
     return data, samples
 
 
+def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20, batch_bytes=256 << 20):
+    """Feeds the text of a VCF (plain, bgzip or gzip) to ``on_lines(addr, length) -> bytes consumed``
+    in large buffers of whole-or-partial lines (an incomplete last line is carried to the next
+    buffer), after calling ``on_header(line)`` once with the ``#CHROM`` line.  Plain text is
+    mapped read-only and handed over in place; bgzip blocks are inflated in parallel by the
+    native library; plain gzip streams through Python's reader."""
+    import ctypes as C
+
+    from . import _cabi
+
+    lib = _cabi.load()
+    consumed = C.c_int64(0)
+    seen_header = False
+    if os.path.getsize(vcf_file) == 0:
+        return
+    if not _is_gzip(vcf_file):
+        import mmap
+
+        with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            h = mm.find(b"#CHROM")
+            he = mm.find(b"\n", h) if h >= 0 else -1
+            if h >= 0 and he >= 0:
+                on_header(mm[h:he])
+                view = np.frombuffer(mm, dtype=np.uint8)
+                try:
+                    body, length = he + 1, len(mm)
+                    done = on_lines(view.ctypes.data + body, length - body) if length > body else 0
+                    tail = bytes(mm[body + done :])
+                finally:
+                    del view
+                if tail:  # last line without a newline
+                    tail += b"\n"
+                    buf = np.frombuffer(tail, dtype=np.uint8)
+                    on_lines(buf.ctypes.data, len(tail))
+    elif _is_bgzf(vcf_file):
+        import mmap
+
+        with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            view = np.frombuffer(mm, dtype=np.uint8)
+            try:
+                base, total = view.ctypes.data, len(mm)
+                max_blocks = 1 << 14
+                block_off = np.empty(max_blocks, dtype=np.int64)
+                out_off = np.empty(max_blocks + 1, dtype=np.int64)
+                at, carry = 0, b""
+                while True:
+                    n = int(lib.sai_bgzf_scan(base + at, total - at, max_blocks, batch_bytes, block_off.ctypes.data,
+                                              out_off.ctypes.data, C.byref(consumed))) if at < total else 0
+                    if n < 0:
+                        _cabi.check(n)
+                    last = n == 0 or at + consumed.value >= total
+                    text_len = int(out_off[n]) if n else 0
+                    buf = np.empty(len(carry) + text_len + 1, dtype=np.uint8)
+                    buf[: len(carry)] = np.frombuffer(carry, dtype=np.uint8)
+                    if n:
+                        _cabi.check(lib.sai_bgzf_inflate(base + at, block_off.ctypes.data, out_off.ctypes.data, n,
+                                                         buf.ctypes.data + len(carry), n_threads))
+                        at += consumed.value
+                    length = len(carry) + text_len
+                    start_at = 0
+                    if not seen_header:
+                        head = buf[:length].tobytes() if length < (64 << 20) else bytes(buf[: 64 << 20])
+                        h = head.find(b"#CHROM")
+                        he = head.find(b"\n", h) if h >= 0 else -1
+                        if h < 0 or he < 0:
+                            if last:
+                                break
+                            carry = buf[:length].tobytes()
+                            continue
+                        on_header(head[h:he])
+                        seen_header = True
+                        start_at = he + 1
+                    if last and length > start_at and buf[length - 1] != 10:
+                        buf[length] = 10  # last line without a newline
+                        length += 1
+                    done = start_at + (on_lines(buf.ctypes.data + start_at, length - start_at) if length > start_at else 0)
+                    carry = buf[done:length].tobytes()
+                    if last:
+                        break
+            finally:
+                del view
+    else:
+        with gzip.open(vcf_file, "rb") as f:
+            carry = b""
+            while True:
+                block = f.read(chunk_bytes)
+                data = carry + block
+                if not data:
+                    break
+                if not seen_header:
+                    h = data.find(b"#CHROM")
+                    he = data.find(b"\n", h) if h >= 0 else -1
+                    if h < 0 or he < 0:
+                        if not block:
+                            break
+                        carry = data
+                        continue
+                    on_header(data[h:he])
+                    seen_header = True
+                    data = data[he + 1 :]
+                if not block and not data.endswith(b"\n"):
+                    data += b"\n"  # last line without a newline
+                buf = np.frombuffer(data, dtype=np.uint8)
+                at = on_lines(buf.ctypes.data, len(data)) if len(data) else 0
+                carry = data[at:]
+                if not block:
+                    break
+
+
+def chromosome_span(vcf_file: str, chr_name: str, n_threads: int = 0):
+    """``(first POS, last POS, number of records)`` of ``chr_name`` in file order, or ``None`` when
+    the chromosome does not occur -- what ``ChunkGenerator.__init__`` finds with pysam
+    (sai/generators/chunk_generator.py:64-76); one parallel native scan of the text."""
+    import ctypes as C
+
+    from . import _cabi
+
+    lib = _cabi.load()
+    first, last, n = None, None, 0
+    f1, l1, n1, used = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+
+    def on_lines(addr: int, length: int) -> int:
+        nonlocal first, last, n
+        _cabi.check(lib.sai_vcf_chrom_span(addr, length, chr_name.encode(), C.byref(f1), C.byref(l1), C.byref(n1),
+                                           C.byref(used), n_threads))
+        if n1.value:
+            if first is None:
+                first = int(f1.value)
+            last = int(l1.value)
+            n += int(n1.value)
+        return int(used.value)
+
+    _scan_text(vcf_file, lambda line: None, on_lines, n_threads)
+    return None if first is None else (first, last, n)
+
+
 def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chunk_bytes=64 << 20,
                  batch_bytes=256 << 20):
     """One pass of the native parser (``sai_vcf_parse_gt``) over the file.
@@ -266,100 +402,11 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
             at += consumed.value
         return at
 
-    if not _is_gzip(vcf_file) and os.path.getsize(vcf_file) > 0:
-        # plain text: parse the file in place through a read-only mapping (no copies)
-        import mmap
+    def on_header(line: bytes):
+        nonlocal cols, ploidies
+        cols, ploidies = header_columns(line)
 
-        with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-            h = mm.find(b"#CHROM")
-            he = mm.find(b"\n", h) if h >= 0 else -1
-            if h >= 0 and he >= 0:
-                cols, ploidies = header_columns(mm[h:he])
-                view = np.frombuffer(mm, dtype=np.uint8)
-                try:
-                    body, length = he + 1, len(mm)
-                    done = parse_buffer(view.ctypes.data + body, length - body)
-                    tail = bytes(mm[body + done :])
-                finally:
-                    del view
-                if tail:  # last line without a newline
-                    tail += b"\n"
-                    buf = np.frombuffer(tail, dtype=np.uint8)
-                    parse_buffer(buf.ctypes.data, len(tail))
-    elif _is_bgzf(vcf_file):
-        # bgzip: independent <= 64 KB blocks, inflated in parallel by the native library in
-        # batches of ~256 MB of text; an incomplete last line is carried to the next batch
-        import mmap
-
-        with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
-            view = np.frombuffer(mm, dtype=np.uint8)
-            try:
-                base, total = view.ctypes.data, len(mm)
-                max_blocks = 1 << 14
-                block_off = np.empty(max_blocks, dtype=np.int64)
-                out_off = np.empty(max_blocks + 1, dtype=np.int64)
-                at, carry = 0, b""
-                while True:
-                    n = int(lib.sai_bgzf_scan(base + at, total - at, max_blocks, batch_bytes, block_off.ctypes.data,
-                                              out_off.ctypes.data, C.byref(consumed))) if at < total else 0
-                    if n < 0:
-                        _cabi.check(n)
-                    last = n == 0 or at + consumed.value >= total
-                    text_len = int(out_off[n]) if n else 0
-                    buf = np.empty(len(carry) + text_len + 1, dtype=np.uint8)
-                    buf[: len(carry)] = np.frombuffer(carry, dtype=np.uint8)
-                    if n:
-                        _cabi.check(lib.sai_bgzf_inflate(base + at, block_off.ctypes.data, out_off.ctypes.data, n,
-                                                         buf.ctypes.data + len(carry), n_threads))
-                        at += consumed.value
-                    length = len(carry) + text_len
-                    start_at = 0
-                    if cols is None:
-                        head = buf[:length].tobytes() if length < (64 << 20) else bytes(buf[: 64 << 20])
-                        h = head.find(b"#CHROM")
-                        he = head.find(b"\n", h) if h >= 0 else -1
-                        if h < 0 or he < 0:
-                            if last:
-                                break
-                            carry = buf[:length].tobytes()
-                            continue
-                        cols, ploidies = header_columns(head[h:he])
-                        start_at = he + 1
-                    if last and length > start_at and buf[length - 1] != 10:
-                        buf[length] = 10  # last line without a newline
-                        length += 1
-                    done = start_at + (parse_buffer(buf.ctypes.data + start_at, length - start_at) if length > start_at else 0)
-                    carry = buf[done:length].tobytes()
-                    if last:
-                        break
-            finally:
-                del view
-    else:
-        with gzip.open(vcf_file, "rb") as f:
-            carry = b""
-            while True:
-                block = f.read(chunk_bytes)
-                data = carry + block
-                if not data:
-                    break
-                if cols is None:
-                    # header: find the #CHROM line to map sample names to columns
-                    h = data.find(b"#CHROM")
-                    he = data.find(b"\n", h) if h >= 0 else -1
-                    if h < 0 or he < 0:
-                        if not block:
-                            break
-                        carry = data
-                        continue
-                    cols, ploidies = header_columns(data[h:he])
-                    data = data[he + 1 :]
-                if not block and not data.endswith(b"\n"):
-                    data += b"\n"  # last line without a newline
-                buf = np.frombuffer(data, dtype=np.uint8)
-                at = parse_buffer(buf.ctypes.data, len(data)) if len(data) else 0
-                carry = data[at:]
-                if not block:
-                    break
+    _scan_text(vcf_file, on_header, parse_buffer, n_threads, chunk_bytes, batch_bytes)
     if cols is None:
         return None
     if not pos_parts:

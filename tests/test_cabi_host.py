@@ -423,3 +423,31 @@ def test_bgzf_parallel_inflate_and_reader(tmp_path):
     p1, g1 = _native_read(str(bgz), "1", int(pos[10]), int(pos[500]), req, None, batch_bytes=50_000)
     keep = (p0 >= pos[10]) & (p0 <= pos[500])
     assert np.array_equal(p0[keep], p1) and np.array_equal(g0[keep], g1)
+
+
+def test_chromosome_span_native(tmp_path):
+    """First / last POS and record count of a chromosome (ChunkGenerator.__init__,
+    chunk_generator.py:64-76) from one native scan, for the three containers, a chromosome
+    name that is a prefix of another one, and a file without a trailing newline."""
+    import gzip
+
+    from sai_b200.vcf import chromosome_span, write_bgzf
+
+    rng = np.random.default_rng(9)
+    head = "##fileformat=VCFv4.1\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts0\ts1\n"
+    recs, expect = [], {}
+    for chrom, n in (("1", 4000), ("11", 2500), ("X", 1)):
+        pos = np.cumsum(rng.integers(1, 90, size=n))
+        expect[chrom] = (int(pos[0]), int(pos[-1]), n)
+        recs += [f"{chrom}\t{p}\t.\tA\tG\t.\t.\t.\tGT\t0|1\t" + "1|1" * 300 for p in pos]  # long lines: > 1 MB segments
+    text = (head + "\n".join(recs)).encode()  # no trailing newline
+    assert len(text) > 4 << 20
+    plain, bgz, gz = tmp_path / "a.vcf", tmp_path / "a.bgz.vcf.gz", tmp_path / "a.vcf.gz"
+    plain.write_bytes(text)
+    write_bgzf(str(bgz), text)
+    with gzip.open(gz, "wb") as f:
+        f.write(text)
+    for path in (plain, bgz, gz):
+        for chrom, want in expect.items():
+            assert chromosome_span(str(path), chrom, n_threads=3) == want, (path, chrom)
+        assert chromosome_span(str(path), "2") is None
