@@ -185,6 +185,44 @@ def test_dd_random_vs_oracle(seed, engine):
                                   orc.cityblock_sums(m64[2 + k][keep], m64[0][keep]).sum(axis=1).astype(np.int64))
 
 
+def test_torch_custom_ops_match_device_scorer(engine):
+    """torch.ops.sai_b200.site_flags / window_stats (sai_b200/ops.py) give the results of the ctypes path."""
+    import torch
+
+    import sai_b200.ops as ops
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import make_job
+
+    pos, mats = synth.make_populations(17, 5000, {"ref": {"R": (90, 2)}, "tgt": {"T": (70, 2)}, "src": {"S": (3, 2)}},
+                                       mean_gap=60.0, introgressed=0.03, missing=0.01)
+    g = [mats["ref"]["R"], mats["tgt"]["T"], mats["src"]["S"]]
+    pg = pack_populations(g, [2, 2, 2], pos)
+    wins = [(s, s + 19_999) for s in range(1, int(pos[-1]), 5_000)]
+    jobs = [make_job(0, 1, [2], True, u=dict(w=0.05, x=0.2, y_list=[("=", 1.0)]), q=dict(w=0.05, quantile=0.95, y_list=[("=", 1.0)])),
+            make_job(0, 1, [2], False, u=dict(w=0.3, x=0.1, y_list=[(">=", 0.5)]), q=dict(w=0.3, quantile=0.5, y_list=[(">=", 0.5)]))]
+    ref = engine.score(pg, wins, jobs)
+    dev = torch.device("cuda")
+    J, W, nt = len(jobs), len(wins), pg.n_tiles
+    packed = torch.from_numpy(pg.packed).to(dev)
+    d_pos = torch.from_numpy(pg.pos).to(dev)
+    ws = torch.tensor([w[0] for w in wins], dtype=torch.int64, device=dev)
+    we = torch.tensor([w[1] for w in wins], dtype=torch.int64, device=dev)
+    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+    mask_u, mask_q, qval = z((J, nt), torch.int32), z((J, nt), torch.int32), z((J, nt * 32), torch.float64)
+    nsnps, u, q, q_cnt = z((J, W), torch.int32), z((J, W), torch.int64), z((J, W), torch.float64), z((J, W), torch.int32)
+    u_start, q_start, totals = z((J, W), torch.int64), z((J, W), torch.int64), z((J, 2), torch.int64)
+    u_cand, q_cand = z((J, 4 * W + 1024), torch.int32), z((J, 4 * W + 1024), torch.int32)
+    lay, jb = ops.struct_tensor(pg.layout), ops.jobs_tensor(jobs)
+    torch.ops.sai_b200.site_flags(packed, lay, jb, pg.n_sites, mask_u, mask_q, qval, 0)
+    torch.ops.sai_b200.window_stats(d_pos, ws, we, jb, mask_u, mask_q, qval, nsnps, u, q, q_cnt, u_start, q_start,
+                                    totals, u_cand, q_cand)
+    assert np.array_equal(nsnps.cpu().numpy(), ref.nsnps) and np.array_equal(u.cpu().numpy(), ref.u)
+    assert np.array_equal(q.cpu().numpy(), ref.q, equal_nan=True) and np.array_equal(totals.cpu().numpy(), ref.totals)
+    assert ref.u.sum() > 0
+    with pytest.raises(ValueError):
+        torch.ops.sai_b200.site_flags(packed, lay[:-1], jb, pg.n_sites, mask_u, mask_q, qval, 0)
+
+
 def test_dd_needs_negative_table(engine):
     """The bit-planes keep one missing code; DD refuses to run without the raw
     values, and the engine checks that the table covers every missing call."""
