@@ -138,6 +138,12 @@ int sai_unpack_i8(const sai_layout* lay, int32_t pop, const uint8_t* packed,
                   int64_t n_sites_total, int64_t site0, int64_t n, int8_t* gt,
                   int64_t row_stride);
 
+/* Negative-value table of one int8 population matrix (the side table of DD, see "N4" below):
+ * every entry v < 0, row-major -> (site, individual, value).  Returns the number of entries;
+ * nothing is written when cap is 0 (counting call) or smaller than that number. */
+int64_t sai_neg_table_i8(const int8_t* gt, int64_t n_sites, int32_t n_samples, int64_t row_stride,
+                         int32_t* site, int32_t* ind, int32_t* val, int64_t cap, int32_t n_threads);
+
 /* ---- host VCF ingest (replaces read_geno_data + check_anc_allele + flip_snps +
  * reshape_genotypes(is_phased=False), sai/utils/utils.py:78-186, 492-555, 405-410) */
 /* One pass over VCF text (complete lines are consumed; *bytes_consumed tells

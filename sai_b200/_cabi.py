@@ -94,6 +94,7 @@ SYMBOLS = {
     "sai_packed_bytes": (_U64, [_LAY, _I64]),
     "sai_pack_i8": (C.c_int, [_LAY, _I32, _P, _I64, _I64, _P, _I32]),
     "sai_unpack_i8": (C.c_int, [_LAY, _I32, _P, _I64, _I64, _I64, _P, _I64]),
+    "sai_neg_table_i8": (_I64, [_P, _I64, _I32, _I64, _P, _P, _P, _I64, _I32]),
     "sai_vcf_parse_gt": (
         _I64,
         [_P, _I64, C.c_char_p, _I64, _I64, _P, _P, _I32, _P, _P, _I64, _P, _P, _I64, _I64, C.POINTER(_I64), _I32],

@@ -216,6 +216,69 @@ int sai_pack_i8(const sai_layout* lay, int32_t pop, const int8_t* gt, int64_t n_
   return SAI_OK;
 }
 
+// Negative-value table of one int8 population matrix (DD, include/sai_b200.h "N4"): every entry v < 0 in
+// row-major order.  Two parallel passes over site blocks: count, then fill at the prefix offsets.
+int64_t sai_neg_table_i8(const int8_t* gt, int64_t n_sites, int32_t n_samples, int64_t row_stride,
+                         int32_t* site, int32_t* ind, int32_t* val, int64_t cap, int32_t n_threads) {
+  if (!gt || n_sites < 0 || n_samples < 1 || row_stride < n_samples || cap < 0 || (cap > 0 && (!site || !ind || !val))) {
+    set_error("sai_neg_table_i8: bad argument");
+    return SAI_E_ARG;
+  }
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  const int64_t n_blocks = std::max<int64_t>(1, std::min<int64_t>(n_threads * 4, n_sites / 256));
+  const int64_t per = (n_sites + n_blocks - 1) / n_blocks;
+  std::vector<int64_t> count(n_blocks + 1, 0);
+  auto run = [&](auto&& fn) {
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+      for (int64_t b = next.fetch_add(1); b < n_blocks; b = next.fetch_add(1)) fn(b);
+    };
+    const int nt = (int)std::min<int64_t>(n_threads, n_blocks);
+    if (nt <= 1) {
+      work();
+      return;
+    }
+    std::vector<std::thread> th;
+    for (int i = 0; i < nt; ++i) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  };
+  const uint64_t signs = 0x8080808080808080ull;
+  run([&](int64_t b) {
+    int64_t c = 0;
+    for (int64_t s = b * per; s < std::min(n_sites, (b + 1) * per); ++s) {
+      const int8_t* row = gt + s * row_stride;
+      int i = 0;
+      for (; i + 8 <= n_samples; i += 8) {
+        uint64_t x;
+        memcpy(&x, row + i, 8);
+        c += __builtin_popcountll(x & signs);
+      }
+      for (; i < n_samples; ++i) c += row[i] < 0;
+    }
+    count[b + 1] = c;
+  });
+  for (int64_t b = 0; b < n_blocks; ++b) count[b + 1] += count[b];
+  const int64_t total = count[n_blocks];
+  if (cap == 0 || total > cap) return total;  // counting call / buffers too small: nothing written
+  run([&](int64_t b) {
+    int64_t at = count[b];
+    for (int64_t s = b * per; s < std::min(n_sites, (b + 1) * per); ++s) {
+      const int8_t* row = gt + s * row_stride;
+      int i = 0;
+      for (; i + 8 <= n_samples; i += 8) {
+        uint64_t x;
+        memcpy(&x, row + i, 8);
+        if (!(x & signs)) continue;
+        for (int k = 0; k < 8; ++k)
+          if (row[i + k] < 0) site[at] = (int32_t)s, ind[at] = i + k, val[at] = row[i + k], ++at;
+      }
+      for (; i < n_samples; ++i)
+        if (row[i] < 0) site[at] = (int32_t)s, ind[at] = i, val[at] = row[i], ++at;
+    }
+  });
+  return total;
+}
+
 int sai_unpack_i8(const sai_layout* lay, int32_t pop, const uint8_t* packed, int64_t n_sites_total,
                   int64_t site0, int64_t n, int8_t* gt, int64_t row_stride) {
   if (int rc = validate_layout(lay)) return rc;

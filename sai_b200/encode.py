@@ -129,15 +129,30 @@ def negative_table(gts: Sequence[np.ndarray]):
     matrices: every entry ``v < 0`` (a missing call; ``-1`` for ``0/.``, ``-2`` for
     ``./.`` in diploid data, sai/utils/utils.py:405-410), row-major, i.e. sorted by
     (site, individual) inside a population."""
+    lib = _cabi.load()
     off = np.zeros(len(gts) + 1, dtype=np.int64)
     sites, inds, vals = [], [], []
     for i, g in enumerate(gts):
         g = np.asarray(g)
-        r, c = np.nonzero(g < 0)
-        sites.append(r.astype(np.int32))
-        inds.append(c.astype(np.int32))
-        vals.append(np.maximum(g[r, c].astype(np.int64), -(2**31) + 1).astype(np.int32))
-        off[i + 1] = off[i] + r.shape[0]
+        if g.dtype == np.int8 and g.ndim == 2 and g.flags.c_contiguous and g.shape[1] >= 1:
+            # native two-pass scan (multi-threaded); int8 is what the VCF reader produces
+            n = int(lib.sai_neg_table_i8(g.ctypes.data, g.shape[0], g.shape[1], g.shape[1], None, None, None, 0, 0))
+            if n < 0:
+                _cabi.check(n)
+            r, c, v = (np.empty(n, dtype=np.int32) for _ in range(3))
+            if n:
+                m = int(lib.sai_neg_table_i8(g.ctypes.data, g.shape[0], g.shape[1], g.shape[1], r.ctypes.data,
+                                             c.ctypes.data, v.ctypes.data, n, 0))
+                assert m == n
+            sites.append(r)
+            inds.append(c)
+            vals.append(v)
+        else:
+            r, c = np.nonzero(g < 0)
+            sites.append(r.astype(np.int32))
+            inds.append(c.astype(np.int32))
+            vals.append(np.maximum(g[r, c].astype(np.int64), -(2**31) + 1).astype(np.int32))
+        off[i + 1] = off[i] + sites[-1].shape[0]
     cat = lambda parts: np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0, np.int32)
     return off, cat(sites), cat(inds), cat(vals)
 

@@ -95,6 +95,13 @@ def test_negative_table_for_dd():
         assert np.all(np.diff(key) > 0)
     pg = pack_populations(mats, [2, 2, 2], np.arange(50), keep_negatives=True)
     assert np.array_equal(pg.neg_off, off) and np.array_equal(pg.neg_val, val)
+    # the native int8 scan over many site blocks and odd widths
+    for width in (1, 7, 8, 37, 64):
+        big = rng.integers(-3, 3, size=(6000, width)).astype(np.int8)
+        big[rng.random(big.shape) < 0.7] = 0
+        o, s_, i_, v_ = negative_table([big])
+        r, c = np.nonzero(big < 0)
+        assert o[1] == r.shape[0] and np.array_equal(s_, r) and np.array_equal(i_, c) and np.array_equal(v_, big[r, c])
     assert pack_populations(mats, [2, 2, 2], np.arange(50)).neg_off is None
 
 
