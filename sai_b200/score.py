@@ -14,17 +14,7 @@ from pathlib import Path
 
 from .configs import load_config
 from .preprocessors import ChunkPreprocessor
-from .vcf import chromosome_span as _vcf_chromosome_span
-from .windows import split_genome, split_windows_ranges
-
-
-def chromosome_span(vcf_file: str, chr_name: str) -> tuple[int, int]:
-    """First and last POS of ``chr_name`` (what ``ChunkGenerator.__init__``
-    finds with pysam, sai/generators/chunk_generator.py:64-76)."""
-    span = _vcf_chromosome_span(vcf_file, chr_name)
-    if span is None:
-        raise ValueError(f"Chromosome {chr_name} not found in VCF.")
-    return span[0], span[1]
+from .generators import ChunkGenerator
 
 
 def score(
@@ -51,11 +41,10 @@ def score(
                 raise ValueError(
                     f"The {stat_name} statistic requires polarized data, please provide the ancestral allele information with `--anc-alleles`."
                 )
-    first, last = chromosome_span(vcf_file, chr_name)
-    windows = split_genome([first, last], win_len, win_step)
     # one chunk per worker slot, processed one after the other on this GPU
-    # (sai.py:92 fixes num_chunks=1; the multi-GPU driver is sai_b200.distributed)
-    chunks = split_windows_ranges(windows, max(1, int(num_workers)))
+    # (sai.py:86-93 fixes num_chunks=1; the multi-GPU driver is sai_b200.distributed)
+    generator = ChunkGenerator(vcf_file=vcf_file, chr_name=chr_name, window_size=win_len, step_size=win_step,
+                               num_chunks=max(1, int(num_workers)))
     pre = ChunkPreprocessor(
         vcf_file=vcf_file,
         ref_ind_file=pop_config.get_population("ref"),
@@ -89,6 +78,6 @@ def score(
             with open(Path(output_file).with_suffix(f".{key}.log"), "w") as f:
                 f.write(f"Chrom\tStart\tEnd\t{key}_SNP\n")
     items = []
-    for start, end in chunks:
-        items.extend(pre.run(chr_name, start, end))
+    for params in generator.get():  # sai.py:148-149
+        items.extend(pre.run(**params))
     pre.process_items(items)

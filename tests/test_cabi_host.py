@@ -458,3 +458,24 @@ def test_chromosome_span_native(tmp_path):
         for chrom, want in expect.items():
             assert chromosome_span(str(path), chrom, n_threads=3) == want, (path, chrom)
         assert chromosome_span(str(path), "2") is None
+
+
+def test_chunk_generator_mirror(tmp_path):
+    """ChunkGenerator(vcf, chr, step, window, num_chunks): the reference's constructor order,
+    ``get()`` dicts and the window-range chunks with their overlap
+    (tests/generators/test_chunk_generator.py:25-40: chr21 2309..48989, 10 kb / 5 kb, 2 chunks
+    -> [(1, 30000), (25001, 55000)])."""
+    from sai_b200.generators import ChunkGenerator
+
+    vcf_path = tmp_path / "t.vcf"
+    rows = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts0"]
+    rows += [f"20\t{p}\t.\tA\tG\t.\t.\t.\tGT\t0|1" for p in (5, 77)]
+    rows += [f"21\t{p}\t.\tA\tG\t.\t.\t.\tGT\t0|1" for p in (2309, 9000, 31000, 48989)]
+    vcf_path.write_text("\n".join(rows) + "\n")
+    gen = ChunkGenerator(vcf_file=str(vcf_path), chr_name="21", window_size=10000, step_size=5000, num_chunks=2)
+    assert len(gen) == 2
+    assert list(gen.get()) == [{"chr_name": "21", "start": 1, "end": 30000}, {"chr_name": "21", "start": 25001, "end": 55000}]
+    # more chunks than windows: empty ranges are dropped (chunk_generator.py:136-139)
+    assert len(ChunkGenerator(str(vcf_path), "20", 1000, 1000, 5)) == 1
+    with pytest.raises(ValueError, match="Chromosome 22 not found in VCF."):
+        ChunkGenerator(str(vcf_path), "22", 5000, 10000, 2)

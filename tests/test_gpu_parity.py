@@ -352,6 +352,40 @@ def test_score_entry_point_gpu(tmp_path):
         score(os.path.join(GOLDEN, case["vcf"]), "7", 6666, 6666, None, str(out), str(cfg), 1)
 
 
+def test_mp_pool_one_worker_per_gpu(tmp_path):
+    """mp_pool (mirror of sai/multiprocessing/mp_pool.py): chunks of the ChunkGenerator scored by
+    spawned worker processes, each with its own engine, give the file the serial loop writes."""
+    import yaml
+
+    from sai_b200.configs import load_config
+    from sai_b200.generators import ChunkGenerator
+    from sai_b200.multiprocessing import mp_pool
+    from sai_b200.preprocessors import ChunkPreprocessor
+    from sai_b200.score import score
+
+    name = "outgroup_shape"
+    case = json.load(open(os.path.join(GOLDEN, f"vcf_{name}.json")))
+    lists = {g: os.path.join(GOLDEN, f"vcf_{name}.{g}.list") for g in ("ref", "tgt", "src")}
+    cfg = tmp_path / "cfg.yaml"
+    cfg.write_text(yaml.safe_dump({"statistics": case["stats"], "ploidies": case["ploidies"], "populations": lists}))
+    anc = os.path.join(GOLDEN, f"vcf_{name}.anc.bed")
+    vcf_path = os.path.join(GOLDEN, case["vcf"])
+    serial = tmp_path / "serial.tsv"
+    score(vcf_path, case["chr_name"], case["win_len"], case["win_step"], anc, str(serial), str(cfg), 3)
+    c = load_config(str(cfg))
+    pooled = tmp_path / "pooled.tsv"
+    pre = ChunkPreprocessor(vcf_file=vcf_path, ref_ind_file=lists["ref"], tgt_ind_file=lists["tgt"], src_ind_file=lists["src"],
+                            out_ind_file=None, win_len=case["win_len"], win_step=case["win_step"], output_file=str(pooled),
+                            ploidy_config=c.ploidies, stat_config=c.statistics, anc_allele_file=anc)
+    gen = ChunkGenerator(vcf_path, case["chr_name"], case["win_step"], case["win_len"], 3)
+    assert len(gen) >= 2
+    mp_pool(pre, gen, nprocess=2)
+    rows = serial.read_text().split("\n", 1)[1]
+    assert pooled.read_text() == rows and rows.count("\n") == len(case["items"])
+    for key in ("U", "Q"):
+        assert (tmp_path / f"pooled.{key}.log").read_text() == (tmp_path / f"serial.{key}.log").read_text().split("\n", 1)[1]
+
+
 def test_sharded_equals_unsharded_gpu(engine):
     """Window-range shards with their win_len - win_step halo (the multi-GPU
     partition, chunk_generator.py:111-142) give exactly the unsharded rows."""

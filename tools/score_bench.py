@@ -81,7 +81,7 @@ def main():
         out = os.path.join(tmp, "scores.tsv")
         score_mod.score(vcf_path, "1", 50000, 10000, anc, out, cfg, 1)  # warm-up: CUDA context, page cache
         tm = Timer()
-        score_mod._vcf_chromosome_span = tm.wrap("chromosome_scan", score_mod._vcf_chromosome_span)
+        score_mod.ChunkGenerator = tm.wrap("chromosome_scan", score_mod.ChunkGenerator)
         vcf_read, pack, eng = vcf.read_data, preprocessors.pack_populations, preprocessors.HostEngine.score
         vcf.read_data = tm.wrap("vcf_parse", vcf_read)
         preprocessors.pack_populations = tm.wrap("pack", pack)
