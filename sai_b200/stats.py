@@ -154,3 +154,47 @@ class DdStatistic(GenericStatistic):
         ref_sum, tgt_sum = eng.dd_sums(pg, 0, 1, list(range(2, 2 + n_src)))
         vals = dd_values(ref_sum, tgt_sum, mats[0].shape[1], mats[1].shape[1], [m.shape[1] for m in mats[2:]])
         return {"name": self.STAT_NAME, "value": [v[0] for v in vals]}
+
+
+class _FourPopStatistic(GenericStatistic):
+    """Shared body of Danc / Dplus / df / fd: ``compute()`` -> ``{"name", "value": [one float per
+    source population]}`` (danc_statistic.py:62-83, dplus_statistic.py:63-86, df_statistic.py:62-84,
+    fd_statistic.py:63-89); the seven site-pattern sums come from the GPU (one window over all sites)."""
+
+    def compute(self, **kwargs) -> dict[str, Any]:
+        from .scoring import four_pop_values
+
+        n_src = len(self.src_gts_list)
+        ploidy = [self.ref_ploidy, self.tgt_ploidy] + list(self.src_ploidy_list)[:n_src]
+        mats = [np.asarray(self.ref_gts), np.asarray(self.tgt_gts)] + [np.asarray(g) for g in self.src_gts_list]
+        out_idx = -1
+        if self.out_gts is not None:  # no outgroup: frequency 0 (stat_utils.py:212-213)
+            out_idx = len(mats)
+            mats.append(np.asarray(self.out_gts))
+            ploidy.append(self.out_ploidy)
+        n = mats[0].shape[0]
+        pg = pack_populations(mats, ploidy, np.arange(n, dtype=np.int32))
+        eng = _default_engine()
+        eng.score(pg, [(0, max(n - 1, 0))], [make_job(0, 1, list(range(2, 2 + n_src)), True)])
+        vals = four_pop_values(eng.pattern_sums(pg, 0, 1, out_idx, list(range(2, 2 + n_src))))
+        return {"name": self.STAT_NAME, "value": [vals[self.STAT_NAME][k][0] for k in range(n_src)]}
+
+
+@STAT_REGISTRY.register("Danc")
+class DancStatistic(_FourPopStatistic):
+    STAT_NAME = "Danc"
+
+
+@STAT_REGISTRY.register("Dplus")
+class DplusStatistic(_FourPopStatistic):
+    STAT_NAME = "Dplus"
+
+
+@STAT_REGISTRY.register("df")
+class DfStatistic(_FourPopStatistic):
+    STAT_NAME = "df"
+
+
+@STAT_REGISTRY.register("fd")
+class FdStatistic(_FourPopStatistic):
+    STAT_NAME = "fd"

@@ -223,6 +223,33 @@ def test_torch_custom_ops_match_device_scorer(engine):
         torch.ops.sai_b200.site_flags(packed, lay[:-1], jb, pg.n_sites, mask_u, mask_q, qval, 0)
 
 
+def test_four_pop_stat_classes_gpu():
+    """Danc / Dplus / df / fd through the registry (same constructor / compute() as the reference's
+    classes), with and without an outgroup, against the oracle (1e-12 relative: summation order)."""
+    from sai_b200.stats import STAT_REGISTRY
+
+    assert sorted(STAT_REGISTRY.list_registered()) == sorted(["U", "Q", "DD", "Danc", "Dplus", "df", "fd"])
+    rng = np.random.default_rng(42)
+    for case in range(12):
+        n = int(rng.integers(5, 300))
+        pl = [int(rng.choice([1, 2, 4])) for _ in range(4)]
+        f = rng.beta(0.5, 0.8, size=n)
+        mk = lambda k, p: rng.binomial(p, f[:, None], size=(n, k)).astype(np.int64)
+        ref, tgt, src1, src2, out = mk(30, pl[0]), mk(22, pl[1]), mk(2, pl[2]), mk(3, pl[2]), mk(2, pl[3])
+        if case % 3 == 0:
+            tgt[rng.random(tgt.shape) < 0.05] = -1
+        with_out = case % 2 == 0
+        kw = dict(ref_gts=ref, tgt_gts=tgt, src_gts_list=[src1, src2], ref_ploidy=pl[0], tgt_ploidy=pl[1],
+                  src_ploidy_list=[pl[2], pl[2]], out_gts=out if with_out else None, out_ploidy=pl[3] if with_out else None)
+        exp = orc.four_pop_statistics(ref, tgt, [src1, src2], pl[0], pl[1], [pl[2], pl[2]],
+                                      out_gts=out if with_out else None, out_ploidy=pl[3] if with_out else None)
+        for name in ("Danc", "Dplus", "df", "fd"):
+            res = STAT_REGISTRY.get(name)(**kw).compute()
+            assert res["name"] == name and len(res["value"]) == 2
+            for a, b in zip(res["value"], exp[name]):
+                assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= FOUR_TOL * max(1.0, abs(b)), (case, name, a, b)
+
+
 def test_dd_needs_negative_table(engine):
     """The bit-planes keep one missing code; DD refuses to run without the raw
     values, and the engine checks that the table covers every missing call."""
