@@ -9,7 +9,8 @@
 //
 // Site model (DESIGN.md "Synthetic inputs"):
 //   class  = hash(site) : 0.5 % "introgressed", rest "background"
-//   background: derived-allele frequency f = u^4 (SFS-like, mostly rare);
+//   background: derived-allele frequency f ~ Beta(0.2, 2.0) (inverse CDF of a
+//               uniform hash, so the draw stays a pure function of (seed, site));
 //               ref, tgt and src individuals draw alleles ~ Bernoulli(f)
 //   introgressed: src fixed derived; ref f = 0.0005; tgt f ~ U(0, 0.8)
 //   each individual is missing with probability `missing_rate`
@@ -41,8 +42,16 @@ __device__ __forceinline__ void site_model(uint64_t seed, int64_t site, int role
   const double u2 = (double)((h >> 40) & 0xffffff) * (1.0 / 16777216.0);
   double f;
   if (!intro) {
-    const double s = u1 * u1;
-    f = s * s;
+    // Beta(0.2, 2): CDF(x) = 1.2 x^0.2 - 0.2 x^1.2.  With y = x^0.2: 1.2 y - 0.2 y^6 = u, monotone on
+    // [0, 1]; 40 bisection steps resolve y to 2^-40, then f = y^5.
+    double lo = 0.0, hi = 1.0;
+    for (int it = 0; it < 40; ++it) {
+      const double y = 0.5 * (lo + hi);
+      const double y2 = y * y;
+      if (1.2 * y - 0.2 * y2 * y2 * y2 < u1) lo = y; else hi = y;
+    }
+    const double y = 0.5 * (lo + hi), y2 = y * y;
+    f = y2 * y2 * y;
   } else if (role == 0) {
     f = 0.0005;
   } else if (role == 1) {
