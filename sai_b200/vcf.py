@@ -322,15 +322,105 @@ def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20,
                     break
 
 
+def _span_from_ends(vcf_file: str, chr_name: str, tail_bytes: int = 1 << 20):
+    """``(first POS, last POS, -1)`` when the first and the last record of a plain-text or bgzip
+    file are both on ``chr_name`` (the usual one-file-per-chromosome layout; records of a
+    chromosome are contiguous in a sorted VCF), else ``None``."""
+    import ctypes as C
+    import mmap
+
+    from . import _cabi
+
+    if os.path.getsize(vcf_file) == 0 or (_is_gzip(vcf_file) and not _is_bgzf(vcf_file)):
+        return None
+
+    def record_of(line: bytes):
+        parts = line.rstrip(b"\r").split(b"\t", 2)
+        if len(parts) < 3 or not parts[1].isdigit():
+            return None
+        return parts[0].decode(), int(parts[1])
+
+    def first_record(text: bytes):
+        at = 0
+        while at < len(text):
+            nl = text.find(b"\n", at)
+            if nl < 0:
+                return None  # incomplete line: not enough text
+            if nl > at and text[at : at + 1] != b"#":
+                return record_of(text[at:nl])
+            at = nl + 1
+        return None
+
+    def last_record(text: bytes, complete_start: bool):
+        body = text[:-1] if text.endswith(b"\n") else text
+        nl = body.rfind(b"\n")
+        if nl < 0 and not complete_start:
+            return None
+        line = body[nl + 1 :]
+        return None if (not line or line.startswith(b"#")) else record_of(line)
+
+    with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+        total = len(mm)
+        if not _is_gzip(vcf_file):
+            head_end = min(total, 64 << 20)
+            head = first_record(mm[:head_end])
+            tail = last_record(mm[max(0, total - tail_bytes) :], total <= tail_bytes)
+        else:
+            lib = _cabi.load()
+            view = np.frombuffer(mm, dtype=np.uint8)
+            try:
+                base = view.ctypes.data
+                nb = 1 << 12
+                block_off, out_off = np.empty(nb, np.int64), np.empty(nb + 1, np.int64)
+                used = C.c_int64(0)
+
+                def inflate(at: int, length: int, limit: int):
+                    n = int(lib.sai_bgzf_scan(base + at, length, nb, limit, block_off.ctypes.data, out_off.ctypes.data,
+                                              C.byref(used)))
+                    if n <= 0:
+                        return None
+                    buf = np.empty(int(out_off[n]), dtype=np.uint8)
+                    if lib.sai_bgzf_inflate(base + at, block_off.ctypes.data, out_off.ctypes.data, n,
+                                            buf.ctypes.data if buf.size else None, 0) != 0:
+                        return None
+                    return buf.tobytes()
+
+                text = inflate(0, total, 64 << 20)
+                head = first_record(text) if text is not None else None
+                tail = None
+                # the last blocks: look for a block boundary in the last ~256 KB of the file
+                start = max(0, total - (256 << 10))
+                magic = b"\x1f\x8b\x08\x04"
+                while tail is None and start < total:
+                    start = mm.find(magic, start)
+                    if start < 0:
+                        break
+                    text = inflate(start, total - start, 1 << 40)
+                    if text is not None and used.value == total - start:  # a true block chain up to the end of the file
+                        tail = last_record(text, start == 0)
+                        break
+                    start += 1
+            finally:
+                del view
+    if head is None or tail is None or head[0] != chr_name or tail[0] != chr_name:
+        return None
+    return head[1], tail[1], -1
+
+
 def chromosome_span(vcf_file: str, chr_name: str, n_threads: int = 0):
     """``(first POS, last POS, number of records)`` of ``chr_name`` in file order, or ``None`` when
     the chromosome does not occur -- what ``ChunkGenerator.__init__`` finds with pysam
-    (sai/generators/chunk_generator.py:64-76); one parallel native scan of the text."""
+    (sai/generators/chunk_generator.py:64-76).  A per-chromosome file (first and last record on
+    ``chr_name``) is answered from its two ends without reading the middle (record count -1 =
+    not counted); anything else takes one parallel native scan of the text."""
     import ctypes as C
 
     from . import _cabi
 
     lib = _cabi.load()
+    quick = _span_from_ends(vcf_file, chr_name)
+    if quick is not None:
+        return quick
     first, last, n = None, None, 0
     f1, l1, n1, used = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
 

@@ -458,6 +458,15 @@ def test_chromosome_span_native(tmp_path):
         for chrom, want in expect.items():
             assert chromosome_span(str(path), chrom, n_threads=3) == want, (path, chrom)
         assert chromosome_span(str(path), "2") is None
+    # one-chromosome files are answered from their two ends (record count -1 = not counted)
+    only = [r for r in recs if r.startswith("11\t")]
+    for trailing in (b"\n", b""):
+        text1 = (head + "\n".join(only)).encode() + trailing
+        plain.write_bytes(text1)
+        write_bgzf(str(bgz), text1, block=5000)
+        for path in (plain, bgz):
+            assert chromosome_span(str(path), "11") == expect["11"][:2] + (-1,), (path, trailing)
+            assert chromosome_span(str(path), "1") is None
 
 
 def test_chunk_generator_mirror(tmp_path):
