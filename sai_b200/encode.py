@@ -74,8 +74,8 @@ def _as_i8(gt: np.ndarray) -> np.ndarray:
     gt = np.asarray(gt)
     if gt.ndim != 2:
         raise ValueError("genotype matrix must be 2-D (sites x individuals)")
-    if gt.dtype == np.int8 and gt.flags.c_contiguous:
-        return gt
+    if gt.dtype == np.int8 and (gt.flags.c_contiguous or (gt.strides[1] == 1 and gt.strides[0] >= gt.shape[1])):
+        return gt  # row-strided views (column blocks of one parsed matrix) are packed in place
     # negative = missing (any negative value, sai/stats/stat_utils.py:45); large
     # values are clipped to 127 and rejected by the packer's domain check
     return np.ascontiguousarray(np.clip(gt, -1, 127).astype(np.int8))
@@ -118,7 +118,8 @@ def pack_populations(
     for i, m in enumerate(mats):
         _cabi.check(
             lib.sai_pack_i8(
-                C.byref(lay), i, m.ctypes.data, n_sites, m.shape[1], out.ctypes.data, n_threads
+                C.byref(lay), i, m.ctypes.data, n_sites, m.strides[0] if n_sites > 1 else m.shape[1], out.ctypes.data,
+                n_threads
             )
         )
     return PackedGenotypes(lay, n_sites, pos, out[:nbytes] if nbytes else out[:0], list(pop_names or []), *neg)
@@ -134,14 +135,15 @@ def negative_table(gts: Sequence[np.ndarray]):
     sites, inds, vals = [], [], []
     for i, g in enumerate(gts):
         g = np.asarray(g)
-        if g.dtype == np.int8 and g.ndim == 2 and g.flags.c_contiguous and g.shape[1] >= 1:
+        if g.dtype == np.int8 and g.ndim == 2 and g.shape[1] >= 1 and g.strides[1] == 1 and g.strides[0] >= g.shape[1]:
             # native two-pass scan (multi-threaded); int8 is what the VCF reader produces
-            n = int(lib.sai_neg_table_i8(g.ctypes.data, g.shape[0], g.shape[1], g.shape[1], None, None, None, 0, 0))
+            stride = g.strides[0] if g.shape[0] > 1 else g.shape[1]
+            n = int(lib.sai_neg_table_i8(g.ctypes.data, g.shape[0], g.shape[1], stride, None, None, None, 0, 0))
             if n < 0:
                 _cabi.check(n)
             r, c, v = (np.empty(n, dtype=np.int32) for _ in range(3))
             if n:
-                m = int(lib.sai_neg_table_i8(g.ctypes.data, g.shape[0], g.shape[1], g.shape[1], r.ctypes.data,
+                m = int(lib.sai_neg_table_i8(g.ctypes.data, g.shape[0], g.shape[1], stride, r.ctypes.data,
                                              c.ctypes.data, v.ctypes.data, n, 0))
                 assert m == n
             sites.append(r)

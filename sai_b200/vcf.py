@@ -611,5 +611,6 @@ def read_data(
         if pos.size == 0 or not pops:
             out[group] = (None, samples)
             continue
-        out[group] = ({p: PopData(pos.copy(), np.ascontiguousarray(gt[:, a:b])) for p, a, b in pops}, samples)
+        # column blocks of the one parsed matrix, as views: the packer takes a row stride
+        out[group] = ({p: PopData(pos, gt[:, a:b]) for p, a, b in pops}, samples)
     return out

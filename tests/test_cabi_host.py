@@ -103,6 +103,13 @@ def test_negative_table_for_dd():
         r, c = np.nonzero(big < 0)
         assert o[1] == r.shape[0] and np.array_equal(s_, r) and np.array_equal(i_, c) and np.array_equal(v_, big[r, c])
     assert pack_populations(mats, [2, 2, 2], np.arange(50)).neg_off is None
+    # column blocks of one matrix (what the VCF reader hands out) pack in place: same tiles, same table
+    wide = rng.integers(-2, 3, size=(300, 60)).astype(np.int8)
+    views = [wide[:, 0:33], wide[:, 33:40], wide[:, 40:60]]
+    a = pack_populations(views, [2, 2, 2], np.arange(300), keep_negatives=True)
+    b = pack_populations([np.ascontiguousarray(v) for v in views], [2, 2, 2], np.arange(300), keep_negatives=True)
+    assert not views[0].flags.c_contiguous and np.array_equal(a.packed, b.packed)
+    assert all(np.array_equal(getattr(a, k), getattr(b, k)) for k in ("neg_off", "neg_site", "neg_ind", "neg_val"))
 
 
 @pytest.mark.parametrize("shape", ["sparse", "dense", "mixed_bits", "tiny", "empty"])
