@@ -362,8 +362,11 @@ def _span_from_ends(vcf_file: str, chr_name: str, tail_bytes: int = 1 << 20):
     with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
         total = len(mm)
         if not _is_gzip(vcf_file):
-            head_end = min(total, 64 << 20)
-            head = first_record(mm[:head_end])
+            head = None
+            for limit in (1 << 20, 64 << 20):
+                head = first_record(mm[: min(total, limit)])
+                if head is not None:
+                    break
             tail = last_record(mm[max(0, total - tail_bytes) :], total <= tail_bytes)
         else:
             lib = _cabi.load()
@@ -385,8 +388,12 @@ def _span_from_ends(vcf_file: str, chr_name: str, tail_bytes: int = 1 << 20):
                         return None
                     return buf.tobytes()
 
-                text = inflate(0, total, 64 << 20)
-                head = first_record(text) if text is not None else None
+                head = None
+                for limit in (1 << 20, 64 << 20):  # the header usually fits the first megabyte of text
+                    text = inflate(0, total, limit)
+                    head = first_record(text) if text is not None else None
+                    if head is not None:
+                        break
                 tail = None
                 # the last blocks: look for a block boundary in the last ~256 KB of the file
                 start = max(0, total - (256 << 10))
