@@ -413,6 +413,63 @@ def test_mp_pool_one_worker_per_gpu(tmp_path):
         assert (tmp_path / f"pooled.{key}.log").read_text() == (tmp_path / f"serial.{key}.log").read_text().split("\n", 1)[1]
 
 
+def test_score_mixed_ploidy_df_kat_gpu(tmp_path):
+    """`score()` on the reference's mixed-ploidy VCF with its own config (tests/data/test_mixed_ploidy.config.yaml:
+    df: True, fd: False, U with two sources) and its own assertions (tests/test_sai.py:127-151): no fd columns,
+    df.src1 / df.src2 columns with the stored values, U rows [0, 1]."""
+    import pandas as pd
+    import yaml
+
+    from sai_b200.score import score
+
+    name = "mixed_ploidy"
+    case = json.load(open(os.path.join(GOLDEN, f"vcf_{name}.json")))
+    cfg = tmp_path / "cfg.yaml"
+    cfg.write_text(yaml.safe_dump({
+        "statistics": {"df": True, "fd": False, "U": case["stats"]["U"]}, "ploidies": case["ploidies"],
+        "populations": {g: os.path.join(GOLDEN, f"vcf_{name}.{g}.list") for g in ("ref", "tgt", "src")}}, sort_keys=False))
+    out = tmp_path / "scores.tsv"
+    score(os.path.join(GOLDEN, case["vcf"]), "21", 50000, 50000, os.path.join(GOLDEN, f"vcf_{name}.anc.bed"), str(out), str(cfg), 1)
+    df = pd.read_csv(out, sep="\t")
+    assert "fd" not in df.columns and "fd.src1" not in df.columns and "fd.src2" not in df.columns
+    assert list(df.columns) == ["Chrom", "Start", "End", "Ref", "Tgt", "Src", "Outgroup", "N(Variants)", "df.src1", "df.src2", "U"]
+    assert np.isclose(df["df.src1"].iloc[0], -0.6086956521739131) and np.isclose(df["df.src2"].iloc[1], -0.45454545454545453)
+    assert abs(df["df.src1"].iloc[0] - -0.6086956521739131) <= 1e-14 and abs(df["df.src2"].iloc[1] - -0.45454545454545453) <= 1e-14
+    assert df["U"].iloc[0] == 0 and df["U"].iloc[1] == 1
+    with pytest.raises(ValueError, match="requires polarized data"):  # tests/test_sai.py:113-124
+        score(os.path.join(GOLDEN, case["vcf"]), "21", 50000, 50000, None, str(out), str(cfg), 1)
+
+
+def test_source_combinations_gpu(engine):
+    """num_src smaller than the number of source populations: one item list per source combination, outermost
+    ref x tgt x combination like WindowGenerator (window_generator.py:164-167; the reference's
+    tests/generators/test_window_generator.py:57-62 counts windows x 2 tgt x 2 combinations), each equal to
+    scoring that combination on its own.  (The general path: the source ploidies are zipped positionally.)"""
+    from sai_b200.preprocessors import score_populations
+    from sai_b200.windows import chunk_windows
+
+    pops = {"ref": {"R": (40, 2)}, "tgt": {"T1": (30, 2), "T2": (25, 2)}, "src": {"S1": (2, 2), "S2": (3, 2)}}
+    pos, mats = synth.make_populations(23, 3000, pops, mean_gap=70.0, introgressed=0.03, missing=0.01)
+    ploidies = {g: {p: v[1] for p, v in pops[g].items()} for g in pops}
+    stats = SimpleStats({"U": {"ref": {"R": 0.1}, "tgt": {"T1": 0.2, "T2": 0.3}, "src": {"S1": "=1"}},
+                         "Q": {"ref": {"R": 0.1}, "tgt": {"T1": 0.9, "T2": 0.5}, "src": {"S1": "=1"}}})
+    wins = chunk_windows(1, int(pos[-1]) // 10000 * 10000 + 30000, 30000, 10000)
+    mk = lambda d: {p: _pop(pos, m) for p, m in d.items()}
+    both = score_populations("1", {t: wins for t in pops["tgt"]}, mk(mats["ref"]), mk(mats["tgt"]), mk(mats["src"]),
+                             SimplePloidy(ploidies), stats, True, engine, num_src=1)
+    assert len(both) == len(wins) * 2 * 2
+    assert [(b["tgt_pop"], b["src_pop_list"]) for b in both[:: len(wins)]] == [("T1", ("S1",)), ("T1", ("S2",)), ("T2", ("S1",)), ("T2", ("S2",))]
+    for t_i, t in enumerate(("T1", "T2")):
+        for s_i, sname in enumerate(("S1", "S2")):
+            alone = score_populations("1", {t: wins}, mk(mats["ref"]), {t: _pop(pos, mats["tgt"][t])},
+                                      {sname: _pop(pos, mats["src"][sname])}, SimplePloidy(ploidies), stats, True, engine)
+            part = both[(t_i * 2 + s_i) * len(wins) : (t_i * 2 + s_i + 1) * len(wins)]
+            for a, b in zip(part, alone):
+                assert (a["start"], a["nsnps"], a["U"]) == (b["start"], b["nsnps"], b["U"])
+                assert (np.isnan(a["Q"]) and np.isnan(b["Q"])) or a["Q"] == b["Q"]
+    assert sum(it["U"] for it in both if not np.isnan(it["U"])) > 0
+
+
 def test_sharded_equals_unsharded_gpu(engine):
     """Window-range shards with their win_len - win_step halo (the multi-GPU
     partition, chunk_generator.py:111-142) give exactly the unsharded rows."""

@@ -261,3 +261,23 @@ def test_vcf_fixtures_against_reference_outputs(name):
         assert items[0]["U"] == 3
     if name == "mixed_ploidy":
         assert [it["U"] for it in items] == [0, 1]
+
+
+def test_mixed_ploidy_df_kat():
+    """The reference's KAT for df with two sources on the mixed-ploidy VCF
+    (tests/test_sai.py:127-151: df.src1 row 0 == -0.6086956521739131, df.src2 row 1 == -0.45454545454545453,
+    U rows [0, 1], config df: True / fd: False) through the host ingest + the oracle."""
+    from sai_b200 import vcf as V
+
+    name = "mixed_ploidy"
+    case = json.load(open(os.path.join(GOLDEN, f"vcf_{name}.json")))
+    pc = SimplePloidy(case["ploidies"])
+    stats = SimpleStats({"df": True, "fd": False, "U": case["stats"]["U"]})
+    groups = V.read_data(os.path.join(GOLDEN, case["vcf"]), case["chr_name"], pc,
+                         *[os.path.join(GOLDEN, f"vcf_{name}.{g}.list") for g in ("ref", "tgt", "src")], None,
+                         os.path.join(GOLDEN, f"vcf_{name}.anc.bed"), start=case["start"], end=case["end"])
+    mk = lambda d: {p: orc.PopData(x.POS, x.GT.astype(np.int64)) for p, x in d.items()}
+    items = orc.score_chunk(case["chr_name"], case["start"], case["end"], case["win_len"], case["win_step"],
+                            mk(groups["ref"][0]), mk(groups["tgt"][0]), mk(groups["src"][0]), pc, stats, True)
+    assert [it["U"] for it in items] == [0, 1] and all("fd" not in it for it in items)
+    assert np.isclose(items[0]["df"][0], -0.6086956521739131) and np.isclose(items[1]["df"][1], -0.45454545454545453)
