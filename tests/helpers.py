@@ -80,3 +80,33 @@ def check_items(got: list[dict], exp: list[dict], q_tol: float = 0.0, four_tol: 
                 else:
                     want = float.fromhex(b)
                     assert abs(float(a) - want) <= four_tol * max(1.0, abs(want)), (n, s, float(a), want)
+
+
+# ---- fakes for the process-pool tests (module level: the pool uses the spawn start method) ----
+class SquareProcessor:
+    """``run(x)`` -> ``[x * x, worker device]``; ``process_items`` keeps what it is given."""
+
+    def __init__(self, path=None):
+        self.path = path
+
+    def run(self, x: int) -> list:
+        from sai_b200 import multiprocessing as smp
+
+        if x < 0:
+            raise ValueError(f"cannot process {x}")
+        return [(x * x, smp._worker_device)]
+
+    def process_items(self, results: list) -> None:
+        self.final_results = results
+        if self.path:
+            with open(self.path, "w") as f:
+                f.write(repr(results))
+
+
+class ListGenerator:
+    def __init__(self, data: list):
+        self.data = data
+
+    def get(self):
+        for x in self.data:
+            yield {"x": x}

@@ -495,3 +495,22 @@ def test_chunk_generator_mirror(tmp_path):
     assert len(ChunkGenerator(str(vcf_path), "20", 1000, 1000, 5)) == 1
     with pytest.raises(ValueError, match="Chromosome 22 not found in VCF."):
         ChunkGenerator(str(vcf_path), "22", 5000, 10000, 2)
+
+
+def test_mp_pool_contract():
+    """mp_pool (sai/multiprocessing/mp_pool.py:43-73; reference test tests/multiprocessing/test_mp_pool.py:25-46):
+    every parameter dict goes through ``run`` in a spawned worker, results reach ``process_items`` in generator order,
+    every worker is pinned to one of the given devices, and an exception in ``run`` surfaces in the caller."""
+    from helpers import ListGenerator, SquareProcessor
+
+    from sai_b200.multiprocessing import mp_pool, mp_worker
+
+    assert mp_worker((SquareProcessor(), {"x": 3})) == [(9, None)]
+    proc = SquareProcessor()
+    mp_pool(proc, ListGenerator([1, 2, 3, 4, 5]), nprocess=2, devices=[0, 1])
+    assert [v for v, _ in proc.final_results] == [1, 4, 9, 16, 25]
+    assert {d for _, d in proc.final_results} <= {0, 1}
+    with pytest.raises(ValueError, match="cannot process -2"):
+        mp_pool(SquareProcessor(), ListGenerator([1, -2, 3]), nprocess=2, devices=[0])
+    with pytest.raises(RuntimeError, match="needs a CUDA device"):
+        mp_pool(SquareProcessor(), ListGenerator([1]), nprocess=1, devices=[])
