@@ -249,7 +249,9 @@ int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win
  *   Dplus = (abba - baba + baaa - abaa) / (abba + baba + baaa + abaa)   dplus_statistic.py:76-83
  *   df    = (abba - baba) / (abba + baba + 2 bbaa)         df_statistic.py:75-81
  *   fd    = (abba - baba) / (abba_d - baba_d)              fd_statistic.py:83-86
- * (NaN when the denominator is 0), formed by the caller. */
+ * (NaN when the denominator is 0), formed by the caller.  The sums are accumulated in the order
+ * of numpy's pairwise summation (np.sum of a contiguous float64 vector), so they are bit-identical
+ * to the reference's. */
 int sai_window_patterns(const sai_layout* lay, const int32_t* d_pos, int64_t n_sites,
                         const int64_t* d_win_start, const int64_t* d_win_end, int64_t n_windows,
                         const int32_t* d_num, const int32_t* d_called, int64_t count_stride,

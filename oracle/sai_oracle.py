@@ -244,6 +244,39 @@ def pattern_sum(freqs, pattern: str) -> float:
     return float(np.sum(prod))
 
 
+def pairwise_sum_model(a) -> float:
+    """``float(np.sum(a))`` for a contiguous float64 vector, spelled out: numpy's pairwise
+    summation (numpy/core/src/umath/loops_utils.h.src ``DOUBLE_pairwise_sum``; block size 128,
+    eight accumulators; unchanged between the reference's numpy 1.26 and 2.x).  ``pattern_sum``
+    calls ``np.sum`` itself; this restatement documents the order the CUDA kernel reproduces and
+    is pinned against numpy in tests/test_oracle_golden.py."""
+    a = [float(x) for x in a]
+
+    def pw(lo: int, n: int) -> float:
+        if n < 8:
+            res = 0.0
+            for i in range(lo, lo + n):
+                res = res + a[i]
+            return res
+        if n <= 128:
+            r = a[lo : lo + 8]
+            i = 8
+            while i < n - (n % 8):
+                for j in range(8):
+                    r[j] = r[j] + a[lo + i + j]
+                i += 8
+            res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+            while i < n:
+                res = res + a[lo + i]
+                i += 1
+            return res
+        n2 = n // 2
+        n2 -= n2 % 8
+        return pw(lo, n2) + pw(lo + n2, n - n2)
+
+    return pw(0, len(a))
+
+
 def four_pop_statistics(ref_gts, tgt_gts, src_gts_list, ref_ploidy, tgt_ploidy, src_ploidy_list,
                         out_gts=None, out_ploidy=None) -> dict[str, list[float]]:
     """``{"Danc": [...], "Dplus": [...], "df": [...], "fd": [...]}``, one value per

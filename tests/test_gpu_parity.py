@@ -18,7 +18,7 @@ from helpers import GOLDEN, SimplePloidy, SimpleStats, check_items, load_pipe_ca
 pytestmark = pytest.mark.gpu
 
 Q_TOL = 1e-12  # absolute tolerance stated by BASELINE.json's north_star
-FOUR_TOL = 1e-12  # relative (abs below 1): Danc/Dplus/df/fd are float sums whose order differs from numpy's pairwise sum
+FOUR_TOL = 0.0  # Danc/Dplus/df/fd: the pattern kernel sums in numpy's pairwise order -> bit-exact
 
 
 @pytest.fixture(scope="module")
@@ -300,17 +300,7 @@ def test_pipeline_golden_gpu(name, engine, tmp_path):
     check_items(items, case["items"], q_tol=0.0, four_tol=FOUR_TOL)  # U/Q bit-exact, so their TSV text is identical
     out = tmp_path / "scores.tsv"
     write_items(str(out), items, stats)
-    has_four = any(case["stats"].get(s) is True for s in ("Danc", "Dplus", "df", "fd"))
-    if has_four:  # the site-pattern sums differ in summation order: compare the rows numerically
-        got_rows = [r.split("\t") for r in out.read_text().splitlines()]
-        exp_rows = [r.split("\t") for r in case["text"]["tsv"].splitlines()]
-        assert len(got_rows) == len(exp_rows)
-        for g, e in zip(got_rows, exp_rows):
-            assert g[:8] == e[:8] and len(g) == len(e)
-            for a, b in zip(g[8:], e[8:]):
-                assert a == b or abs(float(a) - float(b)) <= FOUR_TOL * max(1.0, abs(float(b))), (a, b)
-    else:
-        assert out.read_text() == case["text"]["tsv"]
+    assert out.read_text() == case["text"]["tsv"]  # every column, the four site-pattern statistics included
     for key in ("U", "Q"):
         if key in case["text"]:
             assert (tmp_path / f"scores.{key}.log").read_text() == case["text"][key]
@@ -341,10 +331,8 @@ def test_vcf_fixture_gpu(name, tmp_path):
     if name == "outgroup_stats":  # reference tests/test_sai.py:92-110 (np.isclose against test.with.outgroup.res.tsv)
         want = dict(fd=0.0012826844929596443, df=0.0012417913767941238, Danc=-0.12498082112760132, Dplus=-0.12149240420484364)
         for k, v in want.items():
-            assert np.isclose(items[0][k][0], v) and abs(items[0][k][0] - v) <= 1e-14
-        assert out.read_text().split("\t")[:8] == case["text"]["tsv"].split("\t")[:8]
-    else:
-        assert out.read_text() == case["text"]["tsv"]
+            assert np.isclose(items[0][k][0], v) and items[0][k][0] == v
+    assert out.read_text() == case["text"]["tsv"]
     if name == "example_q":
         assert float(items[0]["Q"]) == 0.9  # reference tests/test_sai.py:63
     if name == "example_u":

@@ -281,3 +281,16 @@ def test_mixed_ploidy_df_kat():
                             mk(groups["ref"][0]), mk(groups["tgt"][0]), mk(groups["src"][0]), pc, stats, True)
     assert [it["U"] for it in items] == [0, 1] and all("fd" not in it for it in items)
     assert np.isclose(items[0]["df"][0], -0.6086956521739131) and np.isclose(items[1]["df"][1], -0.45454545454545453)
+
+
+def test_pairwise_sum_model_matches_numpy():
+    """The summation order the pattern kernel reproduces IS numpy's: np.sum of a contiguous float64
+    vector against the spelled-out pairwise model, for every structural case (n < 8, one block,
+    tails, recursion, beyond the 8192-element iterator buffer)."""
+    rng = np.random.default_rng(3)
+    sizes = list(range(0, 40)) + [63, 64, 65, 127, 128, 129, 130, 200, 255, 256, 257, 1000, 1199, 1200, 1201,
+                                  4096, 8191, 8192, 8193, 8200, 20000, 50001]
+    for n in sizes:
+        for rep in range(3):
+            a = (rng.random(n) ** 3) * rng.choice([1e-3, 1.0, 1e3], size=n)
+            assert orc.pairwise_sum_model(a) == float(np.sum(a)), (n, rep)
