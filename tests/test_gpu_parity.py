@@ -573,6 +573,51 @@ def _random_case(seed, n_sites, anc, missing, stats, pops, gap=60.0, win=(20000,
     return pos, mats, ploidies, (1, end), win
 
 
+@pytest.mark.parametrize("seed, missing, win", [(21, 0.0, (20000, 5000)), (22, 0.02, (3000, 3000)), (23, 0.3, (150000, 50000)),
+                                                (24, 0.01, (700, 100))])
+def test_all_statistics_differential_vs_oracle(seed, missing, win, engine):
+    """All seven statistics, two targets x two sources + an outgroup (the fused multi-job path), random data with
+    missing calls, windows from a handful of sites (< 8: numpy's sequential sum) to thousands (the pairwise recursion):
+    every value equal to the oracle's, bit for bit."""
+    from sai_b200.preprocessors import score_populations
+    from sai_b200.windows import chunk_windows
+
+    pops = {"ref": {"R": (120, 2)}, "tgt": {"T1": (90, 2), "T2": (40, 4)}, "src": {"N": (2, 2), "D": (3, 1)},
+            "outgroup": {"O": (2, 2)}}
+    stats = {"Danc": True, "DD": True, "fd": True,
+             "U": {"ref": {"R": 0.05}, "tgt": {"T1": 0.3, "T2": 0.2}, "src": {"N": "=1", "D": ">=0.5"}},
+             "df": True, "Dplus": True,
+             "Q": {"ref": {"R": 0.1}, "tgt": {"T1": 0.95, "T2": 0.5}, "src": {"N": ">=0.5", "D": "=1"}}}
+    pos, mats = synth.make_populations(seed, 12000, pops, mean_gap=25.0, introgressed=0.02, missing=missing,
+                                       src_all_missing=0.002 if missing else 0.0)
+    ploidies = {g: {p: pops[g][p][1] for p in pops[g]} for g in pops}
+    start, end = 1, int(pos[-1]) // win[1] * win[1] + win[0]
+    sc, pc = SimpleStats(stats), SimplePloidy(ploidies)
+    wins = chunk_windows(start, end, *win)
+    mkg = lambda d: {p: _pop(pos, m) for p, m in d.items()}
+    got = score_populations("3", {t: wins for t in pops["tgt"]}, mkg(mats["ref"]), mkg(mats["tgt"]), mkg(mats["src"]), pc, sc,
+                            True, engine, out_data=mkg(mats["outgroup"]))
+    mk = lambda d: {p: orc.PopData(pos, m.astype(np.int64)) for p, m in d.items()}
+    exp = orc.score_chunk("3", start, end, win[0], win[1], mk(mats["ref"]), mk(mats["tgt"]), mk(mats["src"]), pc, sc, True,
+                          out_data=mk(mats["outgroup"]))
+    assert len(got) == len(exp) == 2 * len(wins)
+    same = lambda a, b: (np.isnan(a) and np.isnan(b)) or float(a).hex() == float(b).hex()
+    n_val = 0
+    for g, e in zip(got, exp):
+        assert (g["start"], g["end"], g["tgt_pop"], g["nsnps"], g["out_pop"]) == (e["start"], e["end"], e["tgt_pop"], e["nsnps"], e["out_pop"])
+        assert list(g.keys()) == list(e.keys())
+        for s in ("U", "Q"):
+            assert same(g[s], e[s]), (s, g["start"], g[s], e[s])
+            assert np.array_equal(np.asarray(g["cdd_pos"][s]), np.asarray(e["cdd_pos"][s]))
+        for s in ("Danc", "Dplus", "df", "fd", "DD"):
+            gv, ev = (g[s], e[s]) if isinstance(e[s], list) else ([g[s]], [e[s]])
+            assert len(gv) == len(ev) == 2
+            for a, b in zip(gv, ev):
+                assert same(a, b), (s, g["start"], a, b)
+                n_val += not np.isnan(b)
+    assert n_val > 20
+
+
 @pytest.mark.parametrize("seed, anc, missing", [(11, True, 0.0), (12, False, 0.01), (13, False, 0.2), (14, True, 0.05)])
 def test_differential_vs_oracle(seed, anc, missing, engine):
     from sai_b200.preprocessors import score_populations
