@@ -311,9 +311,11 @@ int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_si
 int sai_zt_decode_host(const sai_layout* lay, const uint8_t* stream, const uint64_t* tile_off,
                        int64_t n_sites, uint8_t* packed);
 /* Device: rebuilds dense tiles [tile0, tile0 + n_tiles) of d_packed (tile 0 based) from the
- * stream resident at d_stream (offset 0 based) and its directory d_tile_off. */
-int sai_zt_decode(const sai_layout* lay, const void* d_stream, const uint64_t* d_tile_off,
-                  int64_t tile0, int64_t n_tiles, void* d_packed, void* stream);
+ * stream resident at d_stream (offset 0 based, 8-byte aligned, stream_bytes = tile_off[n_tiles_total]
+ * long: the decoder never loads beyond it) and its directory d_tile_off. */
+int sai_zt_decode(const sai_layout* lay, const void* d_stream, uint64_t stream_bytes,
+                  const uint64_t* d_tile_off, int64_t tile0, int64_t n_tiles, void* d_packed,
+                  void* stream);
 
 /* ---- host-buffer engine (replaces ChunkPreprocessor.run's inner loop) ----- */
 typedef struct sai_engine sai_engine;

@@ -255,7 +255,7 @@ static int score_host_impl(sai_engine* e, const sai_layout* lay, const uint8_t* 
     SAI_CUDA_CHECK(cudaEventRecord(e->ev[s], e->s_copy));
     SAI_CUDA_CHECK(cudaStreamWaitEvent(e->s_comp, e->ev[s], 0));
     if (zt)
-      if (int rc = sai_zt_decode(lay, e->zt.p, static_cast<const uint64_t*>(e->ztoff.p), t0, t1 - t0,
+      if (int rc = sai_zt_decode(lay, e->zt.p, zt_bytes, static_cast<const uint64_t*>(e->ztoff.p), t0, t1 - t0,
                                  e->packed.p, e->s_comp))
         return rc;
     if (int rc = sai_site_flags(lay, e->packed.p, t0, t1 - t0, n_tiles, jobs, n_jobs, d_mask_u,

@@ -76,16 +76,44 @@ static void run_parallel(int64_t n, int n_threads, const std::function<void(int6
 struct ZtDecodeParams {
   sai_layout lay;
   const uint8_t* stream;
+  unsigned long long stream_bytes;  // loads never reach past it
   const unsigned long long* tile_off;
   int64_t tile0, n_tiles;
   unsigned long long* packed;  // dense tiles, tile 0
 };
 
+// Shared tables of the decoder.  For a byte mask m (which of a pair's 8 bytes are present) the
+// packed bytes c0, c1, ... go to the set positions of m: two PRMT selectors (byte k of the
+// output <- packed byte rank_k) and two byte masks that clear the absent positions.
+struct ZtTables {
+  uint2 sel[256];   // PRMT selectors for output bytes 0-3 / 4-7
+  uint2 keep[256];  // 0xff in every present byte
+};
+
 // one warp per tile, lane == site
 __global__ void __launch_bounds__(kZtWarps * 32) k_zt_decode(const __grid_constant__ ZtDecodeParams P) {
+  extern __shared__ __align__(16) unsigned char s_zt[];
+  ZtTables& TB = *reinterpret_cast<ZtTables*>(s_zt);
+  unsigned long long* s_pad = reinterpret_cast<unsigned long long*>(s_zt + sizeof(ZtTables));  // [pairs_per_site]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pps = P.lay.pairs_per_site;
+  for (int m = threadIdx.x; m < 256; m += blockDim.x) {
+    uint32_t sel[2] = {0u, 0u}, keep[2] = {0u, 0u};
+    int rank = 0;
+    for (int k = 0; k < 8; ++k) {
+      if ((m >> k) & 1) {
+        sel[k >> 2] |= (uint32_t)rank << (4 * (k & 3));
+        keep[k >> 2] |= 0xffu << (8 * (k & 3));
+        ++rank;
+      }
+    }
+    TB.sel[m] = make_uint2(sel[0], sel[1]);
+    TB.keep[m] = make_uint2(keep[0], keep[1]);
+  }
+  for (int r = threadIdx.x; r < pps; r += blockDim.x) s_pad[r] = pad_constant(P.lay, r);
+  __syncthreads();
   const unsigned lt = (1u << lane) - 1u;
+  const uint8_t* const stream_end = P.stream + P.stream_bytes;
   for (int64_t t = (int64_t)blockIdx.x * kZtWarps + warp; t < P.n_tiles; t += (int64_t)gridDim.x * kZtWarps) {
     const int64_t T = P.tile0 + t;
     const unsigned long long off = __ldg(P.tile_off + T);
@@ -107,13 +135,13 @@ __global__ void __launch_bounds__(kZtWarps * 32) k_zt_decode(const __grid_consta
       for (int rr = 0; rr < rows; ++rr) {
         const uint32_t w = __shfl_sync(0xffffffffu, mine, rr);
         const int r = r0 + rr;
-        const unsigned long long padc = pad_constant(P.lay, r);
+        const unsigned long long padc = s_pad[r];
         if (w == 0u) {
           out[(size_t)r * kTile] = padc;
           continue;
         }
         const bool has = (w >> lane) & 1u;
-        uint32_t m = has ? (uint32_t)__ldg(mask + base1 + __popc(w & lt)) : 0u;
+        const uint32_t m = has ? (uint32_t)__ldg(mask + base1 + __popc(w & lt)) : 0u;
         const int nb = __popc(m);
         int incl = nb;
 #pragma unroll
@@ -121,12 +149,22 @@ __global__ void __launch_bounds__(kZtWarps * 32) k_zt_decode(const __grid_consta
           const int up = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += up;
         }
-        const uint8_t* p = data + base2 + (incl - nb);
         unsigned long long v = 0;
-        while (m) {
-          const int k = __ffs(m) - 1;
-          m &= m - 1;
-          v |= (unsigned long long)__ldg(p++) << (8 * k);
+        if (nb) {
+          // the lane's nb <= 8 bytes start at p (any alignment): two aligned 8-byte loads + funnel shift
+          const uint8_t* p = data + base2 + (incl - nb);
+          const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+          const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+          const int sh = (int)(a & 7) * 8;
+          const unsigned long long lo = __ldg(q);
+          const unsigned long long hi =
+              (sh && reinterpret_cast<const uint8_t*>(q + 2) <= stream_end) ? __ldg(q + 1) : 0ull;
+          const unsigned long long c = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+          const uint32_t c0 = (uint32_t)c, c1 = (uint32_t)(c >> 32);
+          const uint2 sel = TB.sel[m], keep = TB.keep[m];
+          const uint32_t v0 = __byte_perm(c0, c1, sel.x) & keep.x;
+          const uint32_t v1 = __byte_perm(c0, c1, sel.y) & keep.y;
+          v = (unsigned long long)v0 | ((unsigned long long)v1 << 32);
         }
         out[(size_t)r * kTile] = v ^ padc;
         base1 += __popc(w);
@@ -270,8 +308,8 @@ int sai_zt_decode_host(const sai_layout* lay, const uint8_t* stream, const uint6
   return SAI_OK;
 }
 
-int sai_zt_decode(const sai_layout* lay, const void* d_stream, const uint64_t* d_tile_off, int64_t tile0,
-                  int64_t n_tiles, void* d_packed, void* stream) {
+int sai_zt_decode(const sai_layout* lay, const void* d_stream, uint64_t stream_bytes, const uint64_t* d_tile_off,
+                  int64_t tile0, int64_t n_tiles, void* d_packed, void* stream) {
   if (int rc = validate_layout(lay)) return rc;
   SAI_REQUIRE(tile0 >= 0 && n_tiles >= 0, "bad tile range");
   if (n_tiles == 0) return SAI_OK;
@@ -279,13 +317,19 @@ int sai_zt_decode(const sai_layout* lay, const void* d_stream, const uint64_t* d
   ZtDecodeParams P{};
   P.lay = *lay;
   P.stream = static_cast<const uint8_t*>(d_stream);
+  P.stream_bytes = stream_bytes;
   P.tile_off = reinterpret_cast<const unsigned long long*>(d_tile_off);
   P.tile0 = tile0;
   P.n_tiles = n_tiles;
   P.packed = static_cast<unsigned long long*>(d_packed);
   const int64_t want = (n_tiles + kZtWarps - 1) / kZtWarps;
   const int64_t cap = (int64_t)sm_count() * 8;
-  k_zt_decode<<<(unsigned)(want < cap ? want : cap), kZtWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  SAI_REQUIRE((reinterpret_cast<uintptr_t>(d_stream) & 7) == 0 && (stream_bytes & 7) == 0,
+              "zt stream must be 8-byte aligned and a multiple of 8 bytes long");
+  const size_t smem = sizeof(ZtTables) + sizeof(unsigned long long) * (size_t)lay->pairs_per_site;
+  if (smem > 48 * 1024)
+    SAI_CUDA_CHECK(cudaFuncSetAttribute(k_zt_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_zt_decode<<<(unsigned)(want < cap ? want : cap), kZtWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(P);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }

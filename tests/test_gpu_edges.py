@@ -261,7 +261,7 @@ def test_zt_wire_format_gpu(engine, shape):
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     half = pg.n_tiles // 2
     for t0, nt in ((half, pg.n_tiles - half), (0, half)):
-        _cabi.check(lib.sai_zt_decode(C.byref(pg.layout), d_stream.data_ptr(), d_off.data_ptr(), t0, nt,
+        _cabi.check(lib.sai_zt_decode(C.byref(pg.layout), d_stream.data_ptr(), d_stream.numel(), d_off.data_ptr(), t0, nt,
                                       d_packed.data_ptr(), st))
     assert np.array_equal(d_packed.cpu().numpy(), pg.packed)
     # engine: zt stream vs dense tiles
