@@ -414,6 +414,171 @@ def _span_from_ends(vcf_file: str, chr_name: str, tail_bytes: int = 1 << 20):
     return head[1], tail[1], -1
 
 
+def _scan_sorted_region(vcf_file, chr_name, start, end, on_header, on_lines, n_threads=0, batch_bytes=256 << 20):
+    """Region read without an index, for the usual one-chromosome, position-sorted file (plain text or
+    bgzip): bisection over line starts / bgzip blocks finds the byte range that holds every record with
+    ``start <= POS <= end`` (plus a little slack; the parser still filters by POS), and only that range is
+    inflated and parsed -- a chunk of a sharded run costs its share of the file, not the whole file.
+    Returns False (nothing done) when the file does not qualify; the caller then scans everything."""
+    import ctypes as C
+    import mmap
+
+    from . import _cabi
+
+    if _span_from_ends(vcf_file, chr_name) is None:  # not a single-chromosome file of a supported container
+        return False
+    lib = _cabi.load()
+
+    def pos_of_line(text: bytes, at: int):
+        t1 = text.find(b"\t", at)
+        t2 = text.find(b"\t", t1 + 1) if t1 >= 0 else -1
+        if t2 < 0 or not text[t1 + 1 : t2].isdigit():
+            return None
+        return int(text[t1 + 1 : t2])
+
+    with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+        total = len(mm)
+        if not _is_gzip(vcf_file):
+            h = mm.find(b"#CHROM")
+            he = mm.find(b"\n", h) if h >= 0 else -1
+            if h < 0 or he < 0:
+                return False
+            body = he + 1
+
+            def line_at(off: int):  # first line starting at or after `off`
+                ls = body if off <= body else (lambda nl: total if nl < 0 else nl + 1)(mm.find(b"\n", off - 1))
+                if ls >= total:
+                    return total, None
+                return ls, pos_of_line(mm[ls : min(total, ls + 64)], 0)
+
+            def first_line(pred):  # start of the first line whose POS satisfies the monotone `pred`
+                lo, hi = body, total
+                while lo < hi:
+                    mid = (lo + hi) // 2
+                    ls, p = line_at(mid)
+                    if p is None or pred(p):
+                        hi = mid
+                    else:
+                        lo = ls + 1
+                return line_at(lo)[0]
+
+            lo, hi = first_line(lambda p: p >= start), first_line(lambda p: p > end)
+            on_header(mm[h:he])
+            if hi > lo:
+                view = np.frombuffer(mm, dtype=np.uint8)
+                try:
+                    done = on_lines(view.ctypes.data + lo, hi - lo)
+                    tail = bytes(mm[lo + done : hi])
+                finally:
+                    del view
+                if tail:  # the file's last line without a newline
+                    tail += b"\n"
+                    buf = np.frombuffer(tail, dtype=np.uint8)
+                    on_lines(buf.ctypes.data, len(tail))
+            return True
+
+        # bgzip: table of block offsets (headers only), then bisection on the first full line of a block
+        view = np.frombuffer(mm, dtype=np.uint8)
+        try:
+            base = view.ctypes.data
+            used = C.c_int64(0)
+            offs, at = [], 0
+            cap = 1 << 16
+            b_off, o_off = np.empty(cap, np.int64), np.empty(cap + 1, np.int64)
+            while at < total:
+                n = int(lib.sai_bgzf_scan(base + at, total - at, cap, 1 << 62, b_off.ctypes.data, o_off.ctypes.data, C.byref(used)))
+                if n <= 0:
+                    break
+                offs.append(b_off[:n] + at)
+                at += used.value
+            if at != total or not offs:
+                return False
+            boff = np.concatenate(offs + [np.array([total], dtype=np.int64)])
+            n_blocks = boff.shape[0] - 1
+            def inflate(b0: int, b1: int) -> bytes:
+                n = int(lib.sai_bgzf_scan(base + int(boff[b0]), int(boff[b1] - boff[b0]), b1 - b0, 1 << 62,
+                                          b_off.ctypes.data, o_off.ctypes.data, C.byref(used)))
+                if n != b1 - b0:
+                    raise ValueError("bgzip block table changed under the reader")
+                buf = np.empty(max(1, int(o_off[n])), dtype=np.uint8)
+                _cabi.check(lib.sai_bgzf_inflate(base + int(boff[b0]), b_off.ctypes.data, o_off.ctypes.data, n,
+                                                 buf.ctypes.data, n_threads))
+                return buf[: int(o_off[n])].tobytes()
+
+            # the header: blocks from the start until the #CHROM line is complete
+            hb, head = 0, b""
+            while hb < n_blocks:
+                head += inflate(hb, hb + 1)
+                hb += 1
+                h = head.find(b"#CHROM")
+                he = head.find(b"\n", h) if h >= 0 else -1
+                if he >= 0:
+                    break
+            else:
+                return False
+            first_data_block = hb - 1  # the block in which the records start
+
+            def first_pos(b: int):  # POS of the first line that starts inside block b (None: no such line)
+                if b <= first_data_block:
+                    return -1
+                text = inflate(b, b + 1)
+                nl = text.find(b"\n")
+                return None if nl < 0 else pos_of_line(text, nl + 1)
+
+            def first_block(pred):  # first block > first_data_block whose first line satisfies the monotone pred
+                lo, hi = first_data_block + 1, n_blocks
+                while lo < hi:
+                    mid = (lo + hi) // 2
+                    p, probe = None, mid
+                    while p is None and probe < hi:  # blocks without a line start: look further right
+                        p = first_pos(probe)
+                        probe += 1
+                    if p is None or pred(p):
+                        hi = mid
+                    else:
+                        lo = probe
+                return lo
+
+            b_lo = max(first_data_block, first_block(lambda p: p >= start) - 1)  # last block whose first line is < start
+            # through the block whose first line is > end (it still holds the tail of the last wanted record);
+            # blocks without a line start in between (or up to the end of the file) belong to the region
+            probe, p_hi = first_block(lambda p: p > end), None
+            while p_hi is None and probe < n_blocks:
+                p_hi = first_pos(probe)
+                probe += 1
+            b_hi = n_blocks if p_hi is None else probe
+            on_header(head[h:he])
+            # the records of the first data block follow the header inside `head`
+            from_head = b_lo == first_data_block
+            pending = head[he + 1 :] if from_head else b""
+            b = hb if from_head else b_lo
+            carry, first = b"", True
+            per_batch = max(1, batch_bytes >> 16)  # a block inflates to at most 64 KB
+            while True:
+                e = max(b, min(b_hi, b + per_batch))
+                text = inflate(b, e) if e > b else b""
+                if first:
+                    if not from_head:  # the tail of a record that started in the block before: POS < start
+                        nl = text.find(b"\n")
+                        text = text[nl + 1 :] if nl >= 0 else b""
+                    text = pending + text
+                    first = False
+                b = e
+                last = b >= b_hi
+                data = carry + text
+                if last and b_hi == n_blocks and data and not data.endswith(b"\n"):
+                    data += b"\n"  # the file's last line without a newline
+                if data:
+                    buf = np.frombuffer(data, dtype=np.uint8)
+                    done = on_lines(buf.ctypes.data, len(data))
+                    carry = data[done:]
+                if last:
+                    break
+            return True
+        finally:
+            del view
+
+
 def chromosome_span(vcf_file: str, chr_name: str, n_threads: int = 0):
     """``(first POS, last POS, number of records)`` of ``chr_name`` in file order, or ``None`` when
     the chromosome does not occur -- what ``ChunkGenerator.__init__`` finds with pysam
@@ -503,7 +668,11 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
         nonlocal cols, ploidies
         cols, ploidies = header_columns(line)
 
-    _scan_text(vcf_file, on_header, parse_buffer, n_threads, chunk_bytes, batch_bytes)
+    handled = False
+    if start is not None and end is not None:
+        handled = _scan_sorted_region(vcf_file, chr_name, int(start), int(end), on_header, parse_buffer, n_threads, batch_bytes)
+    if not handled:
+        _scan_text(vcf_file, on_header, parse_buffer, n_threads, chunk_bytes, batch_bytes)
     if cols is None:
         return None
     if not pos_parts:

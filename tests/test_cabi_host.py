@@ -514,3 +514,47 @@ def test_mp_pool_contract():
         mp_pool(SquareProcessor(), ListGenerator([1, -2, 3]), nprocess=2, devices=[0])
     with pytest.raises(RuntimeError, match="needs a CUDA device"):
         mp_pool(SquareProcessor(), ListGenerator([1]), nprocess=1, devices=[])
+
+
+@pytest.mark.parametrize("n_smp, block", [(120, 3000), (700, 1000)])  # lines shorter / longer than a bgzip block
+def test_sorted_region_read_without_index(tmp_path, n_smp, block):
+    """Region reads of a one-chromosome sorted file (plain and bgzip) touch only the byte range of the region --
+    found by bisection, no index file -- and return exactly the rows of a full scan filtered by POS, for regions at
+    the start, in the middle, at the end, empty ones and single positions; other files fall back to the full scan."""
+    import gzip
+
+    from sai_b200 import vcf as V
+
+    rng = np.random.default_rng(12)
+    n_rec = 3000 if n_smp < 200 else 600
+    tok = np.array(["0|0", "0|1", "1|0", "1|1", ".|."])
+    pos = np.cumsum(rng.integers(1, 40, size=n_rec))
+    head = "##fileformat=VCFv4.1\n##contig=<ID=7>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n_smp)) + "\n"
+    recs = [f"7\t{p}\t.\tA\tG\t.\t.\t.\tGT\t" + "\t".join(tok[rng.choice(5, size=n_smp, p=[.7, .1, .1, .05, .05])]) for p in pos]
+    text = (head + "\n".join(recs)).encode()  # no trailing newline
+    plain, bgz = tmp_path / "r.vcf", tmp_path / "r.vcf.gz"
+    plain.write_bytes(text)
+    V.write_bgzf(str(bgz), text, block=block)  # hundreds of blocks: the bisection has something to do
+    req = [(f"s{i}", 2) for i in (5, 0, 77, 119)]
+    p_all, g_all = V._native_read(str(plain), "7", None, None, req, None)
+    assert p_all.shape[0] == n_rec
+    calls = []
+    orig = V._scan_text
+    V._scan_text = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        regions = [(1, int(pos[10])), (int(pos[0]), int(pos[0])), (int(pos[n_rec // 2]), int(pos[n_rec // 2 + 200])),
+                   (int(pos[n_rec - 10]), 10**9), (int(pos[-1]), int(pos[-1])), (int(pos[100]) + 1, int(pos[101]) - 1),
+                   (10**9, 2 * 10**9), (1, 10**9), (int(pos[77]), int(pos[77]))]
+        for path in (plain, bgz):
+            for a, b in regions:
+                p1, g1 = V._native_read(str(path), "7", a, b, req, None, batch_bytes=200_000)
+                keep = (p_all >= a) & (p_all <= b)
+                assert np.array_equal(p1, p_all[keep]) and np.array_equal(g1, g_all[keep]), (path, a, b)
+        assert not calls  # every region was served by the bisection path
+        # a second chromosome in the file: not eligible, full scan (still correct)
+        two = tmp_path / "two.vcf"
+        two.write_bytes(text + b"\n8\t5\t.\tA\tG\t.\t.\t.\tGT\t" + b"\t".join([b"0|1"] * n_smp) + b"\n")
+        p1, g1 = V._native_read(str(two), "7", int(pos[5]), int(pos[50]), req, None)
+        assert calls and np.array_equal(p1, p_all[5:51])
+    finally:
+        V._scan_text = orig
