@@ -584,22 +584,35 @@ def _scan_sorted_region(vcf_file, chr_name, start, end, on_header, on_lines, n_t
             per_batch = max(1, batch_bytes >> 16)  # a block inflates to at most 64 KB
             while True:
                 e = max(b, min(b_hi, b + per_batch))
-                text = inflate(b, e) if e > b else b""
-                if first:
-                    if not from_head:  # the tail of a record that started in the block before: POS < start
-                        nl = text.find(b"\n")
-                        text = text[nl + 1 :] if nl >= 0 else b""
-                    text = pending + text
-                    first = False
+                # inflate the batch straight behind the carried bytes (no intermediate copies)
+                n, text_len = 0, 0
+                if e > b:
+                    n = int(lib.sai_bgzf_scan(base + int(boff[b]), int(boff[e] - boff[b]), e - b, 1 << 62,
+                                              b_off.ctypes.data, o_off.ctypes.data, C.byref(used)))
+                    if n != e - b:
+                        raise ValueError("bgzip block table changed under the reader")
+                    text_len = int(o_off[n])
+                prefix = len(carry) + (len(pending) if first else 0)
+                buf = np.empty(prefix + text_len + 1, dtype=np.uint8)
+                buf[: len(carry)] = np.frombuffer(carry, dtype=np.uint8)
+                if first and pending:
+                    buf[len(carry) : prefix] = np.frombuffer(pending, dtype=np.uint8)
+                if n:
+                    _cabi.check(lib.sai_bgzf_inflate(base + int(boff[b]), b_off.ctypes.data, o_off.ctypes.data, n,
+                                                     buf.ctypes.data + prefix, n_threads))
+                start_at, length = 0, prefix + text_len
+                if first and not from_head:  # the tail of a record that started in the block before: POS < start
+                    probe = buf[prefix : prefix + min(text_len, 4 << 20)].tobytes()
+                    nl = probe.find(b"\n")
+                    start_at = prefix + nl + 1 if nl >= 0 else length
+                first = False
                 b = e
                 last = b >= b_hi
-                data = carry + text
-                if last and b_hi == n_blocks and data and not data.endswith(b"\n"):
-                    data += b"\n"  # the file's last line without a newline
-                if data:
-                    buf = np.frombuffer(data, dtype=np.uint8)
-                    done = on_lines(buf.ctypes.data, len(data))
-                    carry = data[done:]
+                if last and b_hi == n_blocks and length > start_at and buf[length - 1] != 10:
+                    buf[length] = 10  # the file's last line without a newline
+                    length += 1
+                done = start_at + (on_lines(buf.ctypes.data + start_at, length - start_at) if length > start_at else 0)
+                carry = buf[done:length].tobytes()
                 if last:
                     break
             return True
