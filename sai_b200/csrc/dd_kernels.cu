@@ -24,6 +24,7 @@
 //                 the negative-value table (the bit-planes keep a single
 //                 "missing" code; the table restores the raw values).
 #include "common.cuh"
+#include "popcount.cuh"
 
 namespace sai {
 
@@ -52,21 +53,48 @@ __device__ __forceinline__ uint32_t plane_word(const uint2* __restrict__ col, in
   return __ldg(p + (word & 1));
 }
 
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // grid-stride over tiles, one warp per tile, lane == site
-__global__ void __launch_bounds__(kHistWarps * 32) k_site_hist(const __grid_constant__ HistParams P) {
+__global__ void __launch_bounds__(kHistWarps * 32, 4) k_site_hist(const __grid_constant__ HistParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t T = (int64_t)blockIdx.x * kHistWarps + warp; T < P.n_tiles; T += (int64_t)gridDim.x * kHistWarps) {
-    const uint2* tile = P.packed + (size_t)T * P.pairs_per_site * kTile + lane;
-    const int64_t site = T * kTile + lane;
-    for (int q = 0; q < P.n_slots; ++q) {
+  // population by population (each one's pairs are a contiguous 256 B x n_pairs run of a tile)
+  for (int q = 0; q < P.n_slots; ++q) {
+    unsigned long long miss_total = 0;
+    for (int64_t T = (int64_t)blockIdx.x * kHistWarps + warp; T < P.n_tiles; T += (int64_t)gridDim.x * kHistWarps) {
+      const uint2* tile = P.packed + (size_t)T * P.pairs_per_site * kTile + lane;
+      const int64_t site = T * kTile + lane;
       const uint2* col = tile + (size_t)P.pair_off[q] * kTile;
       const int B = P.bits[q], G = P.n_groups[q];
       int32_t* out = P.hist + (size_t)P.code_base[q] * P.stride + site;
       int miss = 0;
       if (B == 2) {
-        int c1 = 0, c2 = 0;
-        for (int g = 0; g < G; ++g) {
-          const uint2 w = __ldg(col + (size_t)g * kTile);
+        // three word streams (value 1, value 2, missing) through carry-save adders, 8 groups per trip
+        SliceCounter k1, k2, km;
+        int g = 0;
+        for (; g + 8 <= G; g += 8) {
+          uint2 w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = ld_stream(col + (size_t)(g + i) * kTile);
+          uint32_t x1[8], x2[8], xm[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            x1[i] = w[i].x & ~w[i].y;
+            x2[i] = w[i].y & ~w[i].x;
+            xm[i] = w[i].x & w[i].y;
+          }
+          k1.add8(x1);
+          k2.add8(x2);
+          km.add8(xm);
+        }
+        int c1 = k1.total(), c2 = k2.total();
+        miss = km.total();
+        for (; g < G; ++g) {
+          const uint2 w = ld_stream(col + (size_t)g * kTile);
           c1 += __popc(w.x & ~w.y);
           c2 += __popc(w.y & ~w.x);
           miss += __popc(w.x & w.y);
@@ -103,11 +131,12 @@ __global__ void __launch_bounds__(kHistWarps * 32) k_site_hist(const __grid_cons
         for (int u = 0; u < kMaxCodes; ++u)
           if (u < n_called) out[(size_t)u * P.stride] = cnt[u];
       }
-      if (P.missing) {
-        int real = site < P.n_sites ? miss - P.pad[q] : 0;
-        real = __reduce_add_sync(0xffffffffu, real);
-        if (lane == 0 && real) atomicAdd(P.missing + q, (unsigned long long)real);
-      }
+      if (site < P.n_sites) miss_total += miss - P.pad[q];
+    }
+    // one atomic per warp and population (per tile they would serialise on a single address)
+    if (P.missing) {
+      const unsigned long long tot = warp_sum_u64(miss_total);
+      if (lane == 0 && tot) atomicAdd(P.missing + q, tot);
     }
   }
 }
@@ -402,7 +431,7 @@ extern "C" int sai_site_hist(const sai_layout* lay, const void* d_packed, int64_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d_missing) SAI_CUDA_CHECK(cudaMemsetAsync(d_missing, 0, sizeof(uint64_t) * n_hist_pops, st));
   const int64_t want = (n_tiles + kHistWarps - 1) / kHistWarps;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t cap = (int64_t)sm_count() * 4;  // 56 registers: 4 resident blocks per SM, one wave
   k_site_hist<<<(unsigned)(want < cap ? want : cap), kHistWarps * 32, 0, st>>>(P);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;

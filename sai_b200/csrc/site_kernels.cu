@@ -14,56 +14,10 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "popcount.cuh"
 #include "site_cond.cuh"
 
 namespace sai {
-
-// streaming 8-byte load: read-only path, do not allocate in L1.  (An L2
-// evict-first cache hint was measured: it made the window kernel 14 us faster
-// but this kernel 80 us slower -- profiles/round1_notes.md.)
-__device__ __forceinline__ uint2 ld_stream(const uint2* p) {
-  uint2 r;
-  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
-}
-
-__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-  return r;
-}
-__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-  return r;
-}
-
-// Bit-sliced counter of one word stream: ones/twos/fours hold weights 1/2/4,
-// `high` counts completed weight-8 carries.
-struct SliceCounter {
-  uint32_t ones = 0, twos = 0, fours = 0;
-  int high = 0;
-  __device__ __forceinline__ void add8(const uint32_t (&w)[8]) {
-    uint32_t tA = maj3(ones, w[0], w[1]);
-    ones = xor3(ones, w[0], w[1]);
-    uint32_t tB = maj3(ones, w[2], w[3]);
-    ones = xor3(ones, w[2], w[3]);
-    uint32_t fA = maj3(twos, tA, tB);
-    twos = xor3(twos, tA, tB);
-    tA = maj3(ones, w[4], w[5]);
-    ones = xor3(ones, w[4], w[5]);
-    tB = maj3(ones, w[6], w[7]);
-    ones = xor3(ones, w[6], w[7]);
-    uint32_t fB = maj3(twos, tA, tB);
-    twos = xor3(twos, tA, tB);
-    uint32_t e = maj3(fours, fA, fB);
-    fours = xor3(fours, fA, fB);
-    high += __popc(e);
-  }
-  __device__ __forceinline__ int total() const {
-    return 8 * high + 4 * __popc(fours) + 2 * __popc(twos) + __popc(ones);
-  }
-};
 
 // B == 2 population: planes (a = bit0, b = bit1) of one group sit in one pair.
 //   num  = popc(a) + 2 popc(b) - 3 popc(a&b),   missing = popc(a&b)
