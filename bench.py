@@ -264,7 +264,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sites", type=int, default=WORKLOAD["n_sites"], help="override the number of sites (debug)")
-    ap.add_argument("--variant", type=int, default=0, help="K1 variant (0 = carry-save popcount, 2 = direct popcount)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-sample-sites", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debug)")
@@ -314,7 +313,7 @@ def main():
 
     # ---- warm-up ----
     for _ in range(args.warmup):
-        sc.step(d_packed, d_pos, d_ws, d_we, [job], args.variant)
+        sc.step(d_packed, d_pos, d_ws, d_we, [job])
     torch.cuda.synchronize()
     res = sc.results()  # also checks the candidate capacity
     u_total, q_finite = int(res.u.sum()), int(np.isfinite(res.q).sum())
@@ -330,7 +329,7 @@ def main():
     ev0.record()
     for i in range(K):
         k1a[i].record()
-        sc.site_flags(d_packed, [job], args.variant)
+        sc.site_flags(d_packed, [job])
         k1b[i].record()
         sc.window_stats(d_pos, d_ws, d_we, [job])
     ev1.record()
@@ -453,7 +452,6 @@ def main():
                 "windows_per_gpu": W,
                 "sharding": "one chromosome-scale shard per GPU, no data-path collective",
                 "l2": f"inputs ({packed_bytes / 1e9:.2f} GB per step) larger than L2 (126 MB); no explicit flush",
-                "k1_variant": args.variant,
             },
             "genotype_gbps": world * alg / (ms_per_step / 1e3) / 1e9,
             "roofline": {

@@ -184,12 +184,9 @@ int sai_bgzf_inflate(const uint8_t* data, const int64_t* block_off, const int64_
 /* For tiles [tile0, tile0+n_tiles): per population p and site s
  *     num[p*stride + s]    = sum of called values      (stat_utils.py:48)
  *     called[p*stride + s] = number of called individuals (stat_utils.py:46)
- * d_packed points at tile 0.  variant (tuning / A-B knob, same results):
- *   0 = carry-save popcount, 8 loads in flight per lane, 4 blocks/SM (default)
- *   1 = carry-save popcount, 16 loads in flight per lane, 3 blocks/SM
- *   2 = direct POPC per word (XU-pipe bound; kept as the baseline)
- *   5, 6, 7 = bulk-copy (cp.async.bulk + mbarrier) ring of 3 / 4 / 6 stages per warp,
- *             2-plane populations only (measured slower: profiles/round1_notes.md) */
+ * d_packed points at tile 0.  `variant` must be 0 (carry-save popcount, 8 streaming loads in
+ * flight per lane, 4 blocks/SM); other values select A/B variants that exist only in
+ * -DSAI_EXPERIMENTS builds (tools/, profiles/round1_notes.md) and are rejected with SAI_E_ARG. */
 int sai_site_counts(const sai_layout* lay, const void* d_packed, int64_t tile0,
                     int64_t n_tiles, int32_t* d_num, int32_t* d_called,
                     int64_t stride, int32_t variant, void* stream);

@@ -155,7 +155,10 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    import os
+
+    override = os.environ.get("SAI_B200_LIB")  # tools/ A/B scripts: the -DSAI_EXPERIMENTS build
+    path = Path(override) if override else _build.build()
     lib = C.CDLL(str(path))
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library diverge

@@ -47,18 +47,30 @@ def is_stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+EXPERIMENTS_LIB = ROOT.parent / "tools" / "bin" / "libsai_b200_exp.so"
+
+
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> Path:
+    """``experiments=True`` builds ``tools/bin/libsai_b200_exp.so`` with -DSAI_EXPERIMENTS: the
+    genotype-pass and window-kernel variants that were measured slower (profiles/round1_notes.md)
+    stay available to the A/B scripts under tools/ without shipping in the product library
+    (select it with ``SAI_B200_LIB=tools/bin/libsai_b200_exp.so``)."""
+    if experiments:
+        return _compile(EXPERIMENTS_LIB, ROOT.parent / "tools" / "bin" / "obj", ["-DSAI_EXPERIMENTS"], verbose)
     if not force and not is_stale():
         return LIB
+    return _compile(LIB, ROOT / "lib" / "obj", [], verbose)
+
+
+def _compile(LIB: Path, obj_dir: Path, defines: list, verbose: bool) -> Path:
     LIB.parent.mkdir(parents=True, exist_ok=True)
     objs = []
-    obj_dir = ROOT / "lib" / "obj"
     obj_dir.mkdir(parents=True, exist_ok=True)
     nvcc = _nvcc()
     procs = []
     for src in sources():
         obj = obj_dir / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
@@ -79,4 +91,4 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv))

@@ -47,6 +47,18 @@ struct SliceCounter {
     fours = xor3(fours, fA, fB);
     high += __popc(e);
   }
+  // four words: one weight-4 carry, absorbed by `fours` (one POPC per 4 words instead of per 8;
+  // used by the 3- and 4-plane populations, whose groups come 4 per batch of loads)
+  __device__ __forceinline__ void add4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    const uint32_t tA = maj3(ones, w0, w1);
+    ones = xor3(ones, w0, w1);
+    const uint32_t tB = maj3(ones, w2, w3);
+    ones = xor3(ones, w2, w3);
+    const uint32_t fA = maj3(twos, tA, tB);
+    twos = xor3(twos, tA, tB);
+    high += __popc(fours & fA);
+    fours ^= fA;
+  }
   __device__ __forceinline__ int total() const {
     return 8 * high + 4 * __popc(fours) + 2 * __popc(twos) + __popc(ones);
   }

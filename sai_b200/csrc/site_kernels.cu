@@ -21,6 +21,8 @@ namespace sai {
 
 // B == 2 population: planes (a = bit0, b = bit1) of one group sit in one pair.
 //   num  = popc(a) + 2 popc(b) - 3 popc(a&b),   missing = popc(a&b)
+// MODE 0 is the product path (carry-save, 8 loads in flight per lane); MODE 1 (16 loads in
+// flight) and MODE 2 (direct POPC per word) exist only in -DSAI_EXPERIMENTS builds (tools/).
 template <int MODE>
 __device__ __forceinline__ void count_b2(const uint2* __restrict__ col, int n_pairs, int& num,
                                          int& miss) {
@@ -28,8 +30,8 @@ __device__ __forceinline__ void count_b2(const uint2* __restrict__ col, int n_pa
   int acc_a = 0, acc_b = 0, acc_m = 0;
   if (MODE != 2) {
     SliceCounter ca, cb, cm;
+#ifdef SAI_EXPERIMENTS
     if (MODE == 1) {
-      // 16 loads in flight per lane
       for (; p + 16 <= n_pairs; p += 16) {
         uint2 v[16];
 #pragma unroll
@@ -49,6 +51,7 @@ __device__ __forceinline__ void count_b2(const uint2* __restrict__ col, int n_pa
         }
       }
     }
+#endif
     for (; p + 8 <= n_pairs; p += 8) {
       uint2 v[8];
 #pragma unroll
@@ -80,28 +83,72 @@ __device__ __forceinline__ void count_b2(const uint2* __restrict__ col, int n_pa
   miss = acc_m;
 }
 
-// General B (3 or 4): groups of B words packed back to back into pairs.
-__device__ __forceinline__ void count_generic(const uint2* __restrict__ col, int n_groups, int B,
-                                              int& num, int& miss) {
-  const uint32_t* base = reinterpret_cast<const uint32_t*>(col);
-  const int all = (1 << B) - 1;
-  int acc = 0, accm = 0;
-  for (int g = 0; g < n_groups; ++g) {
-    uint32_t andw = 0xffffffffu;
-    int s = 0;
-    for (int b = 0; b < B; ++b) {
-      const int word = g * B + b;
-      // word w of this lane: pair (w>>1) is 32 lanes * 2 words further on
-      uint32_t x = __ldg(base + (size_t)(word >> 1) * (kTile * 2) + (word & 1));
-      s += __popc(x) << b;
-      andw &= x;
-    }
-    const int m = __popc(andw);
-    acc += s - all * m;
-    accm += m;
+// B == 4 population (values up to 14: high ploidy, or the reference's flipped-missing
+// quirk, sai/utils/utils.py:555): a group is two pairs (planes 0,1 | planes 2,3).
+//   num = sum_b 2^b popc(plane_b) - 15 popc(and of the planes),   missing = popc(and)
+// Same streaming 8-byte loads and carry-save counters as count_b2: 8 loads (4 groups) in
+// flight per lane, one counter per plane plus one for the missing mask.
+__device__ __forceinline__ void count_b4(const uint2* __restrict__ col, int n_groups, int& num,
+                                         int& miss) {
+  SliceCounter c0, c1, c2, c3, cm;
+  int g = 0;
+  for (; g + 4 <= n_groups; g += 4) {
+    uint2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ld_stream(col + (size_t)(2 * g + i) * kTile);
+    c0.add4(v[0].x, v[2].x, v[4].x, v[6].x);
+    c1.add4(v[0].y, v[2].y, v[4].y, v[6].y);
+    c2.add4(v[1].x, v[3].x, v[5].x, v[7].x);
+    c3.add4(v[1].y, v[3].y, v[5].y, v[7].y);
+    cm.add4(v[0].x & v[0].y & v[1].x & v[1].y, v[2].x & v[2].y & v[3].x & v[3].y,
+            v[4].x & v[4].y & v[5].x & v[5].y, v[6].x & v[6].y & v[7].x & v[7].y);
   }
-  num = acc;
-  miss = accm;
+  int a0 = c0.total(), a1 = c1.total(), a2 = c2.total(), a3 = c3.total(), am = cm.total();
+  for (; g < n_groups; ++g) {
+    const uint2 lo = ld_stream(col + (size_t)(2 * g) * kTile);
+    const uint2 hi = ld_stream(col + (size_t)(2 * g + 1) * kTile);
+    a0 += __popc(lo.x);
+    a1 += __popc(lo.y);
+    a2 += __popc(hi.x);
+    a3 += __popc(hi.y);
+    am += __popc(lo.x & lo.y & hi.x & hi.y);
+  }
+  num = a0 + 2 * a1 + 4 * a2 + 8 * a3 - 15 * am;
+  miss = am;
+}
+
+// B == 3 population (ploidy 3..6, values up to 6): two groups share three pairs
+// (a0,a1 | a2,b0 | b1,b2); an odd last group ends with a zero pad word.
+__device__ __forceinline__ void count_b3(const uint2* __restrict__ col, int n_groups, int& num,
+                                         int& miss) {
+  SliceCounter c0, c1, c2, cm;
+  int g = 0;
+  for (; g + 4 <= n_groups; g += 4) {
+    uint2 v[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = ld_stream(col + (size_t)(3 * (g >> 1) + i) * kTile);
+    c0.add4(v[0].x, v[1].y, v[3].x, v[4].y);
+    c1.add4(v[0].y, v[2].x, v[3].y, v[5].x);
+    c2.add4(v[1].x, v[2].y, v[4].x, v[5].y);
+    cm.add4(v[0].x & v[0].y & v[1].x, v[1].y & v[2].x & v[2].y, v[3].x & v[3].y & v[4].x,
+            v[4].y & v[5].x & v[5].y);
+  }
+  int a0 = c0.total(), a1 = c1.total(), a2 = c2.total(), am = cm.total();
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(col);
+  for (; g < n_groups; ++g) {
+    uint32_t x[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int word = g * 3 + b;  // word w of this lane: pair (w>>1) is 32 lanes * 2 words further on
+      x[b] = __ldg(base + (size_t)(word >> 1) * (kTile * 2) + (word & 1));
+    }
+    a0 += __popc(x[0]);
+    a1 += __popc(x[1]);
+    a2 += __popc(x[2]);
+    am += __popc(x[0] & x[1] & x[2]);
+  }
+  num = a0 + 2 * a1 + 4 * a2 - 7 * am;
+  miss = am;
 }
 
 // ---- host side of the integer fast path (site_cond.cuh) ----------------------------
@@ -198,8 +245,10 @@ __global__ void __launch_bounds__(kSiteWarps * 32, MODE == 1 ? 3 : 4)
       int num, miss;
       if (L.bits == 2)
         count_b2<MODE>(col, L.n_pairs, num, miss);
+      else if (L.bits == 4)
+        count_b4(col, L.n_groups, num, miss);
       else
-        count_generic(col, L.n_groups, L.bits, num, miss);
+        count_b3(col, L.n_groups, num, miss);
       const int called = L.n_groups * 32 - miss;
       s_num[pi * kTile + lane] = num;
       s_cal[pi * kTile + lane] = called;
@@ -292,6 +341,7 @@ static int launch_site(const SiteParams& P, const JobBlock& JB, cudaStream_t st)
 }
 
 
+#ifdef SAI_EXPERIMENTS
 // Batch table shared by the experimental variants: the tile's pairs cut into batches of up
 // to 8 pairs that never straddle a population (pair index | valid-1 | population | last-of-population).
 __device__ __forceinline__ uint32_t batch_entry(int pair, int valid, int pop, bool last) {
@@ -482,6 +532,8 @@ static bool all_two_planes(const sai_layout& lay) {
   return true;
 }
 
+#endif  // SAI_EXPERIMENTS
+
 }  // namespace sai
 
 using namespace sai;
@@ -505,6 +557,7 @@ int sai_site_counts(const sai_layout* lay, const void* d_packed, int64_t tile0, 
   P.count_stride = stride;
   JobBlock JB{};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#ifdef SAI_EXPERIMENTS
   if (variant >= 5 && variant <= 7 && all_two_planes(*lay)) {
     const int rc = variant == 5   ? launch_site_ring<false, 3, 4>(P, JB, st)
                    : variant == 6 ? launch_site_ring<false, 4, 3>(P, JB, st)
@@ -513,6 +566,9 @@ int sai_site_counts(const sai_layout* lay, const void* d_packed, int64_t tile0, 
   }
   if (variant == 2) return launch_site<2, false>(P, JB, st);
   if (variant == 1) return launch_site<1, false>(P, JB, st);
+#else
+  SAI_REQUIRE(variant == 0, "variant %d exists only in -DSAI_EXPERIMENTS builds", variant);
+#endif
   return launch_site<0, false>(P, JB, st);
 }
 
@@ -544,6 +600,7 @@ int sai_site_flags(const sai_layout* lay, const void* d_packed, int64_t tile0, i
   JB.n_jobs = n_jobs;
   for (int j = 0; j < n_jobs; ++j) JB.job[j] = jobs[j];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#ifdef SAI_EXPERIMENTS
   if (variant >= 5 && variant <= 7 && all_two_planes(*lay)) {
     const int rc = variant == 5   ? launch_site_ring<true, 3, 4>(P, JB, st)
                    : variant == 6 ? launch_site_ring<true, 4, 3>(P, JB, st)
@@ -552,6 +609,9 @@ int sai_site_flags(const sai_layout* lay, const void* d_packed, int64_t tile0, i
   }
   if (variant == 2) return launch_site<2, true>(P, JB, st);
   if (variant == 1) return launch_site<1, true>(P, JB, st);
+#else
+  SAI_REQUIRE(variant == 0, "variant %d exists only in -DSAI_EXPERIMENTS builds", variant);
+#endif
   return launch_site<0, true>(P, JB, st);
 }
 

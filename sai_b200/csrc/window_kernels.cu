@@ -716,19 +716,21 @@ extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SAI_CUDA_CHECK(cudaMemsetAsync(d_totals, 0, sizeof(int64_t) * 2 * n_jobs, st));
   if (n_windows == 0) return SAI_OK;
+  const int64_t cap = (int64_t)sm_count() * 32;
+#ifdef SAI_EXPERIMENTS
+  // tuning knobs of tools/ builds: windows per warp and the occupancy bound
   static const int batch = [] {
-    const char* e = getenv("SAI_WIN_BATCH");  // tuning knob: windows per warp (1, 2 or 4)
+    const char* e = getenv("SAI_WIN_BATCH");
     const int b = e ? atoi(e) : 1;
     return (b == 2 || b == 4) ? b : 1;
   }();
-  const int64_t per_block = kWinWarps * batch;
-  const int64_t want = (n_windows + per_block - 1) / per_block;
-  const int64_t cap = (int64_t)sm_count() * 32;
-  const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_jobs);
   static const int minb = [] {
     const char* e = getenv("SAI_WIN_MINB");
     return e ? atoi(e) : 12;
   }();
+  const int64_t per_block = kWinWarps * batch;
+  const int64_t want = (n_windows + per_block - 1) / per_block;
+  const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_jobs);
   if (batch == 1 && minb == 10)
     k_window_stats<1, 10><<<grid, kWinWarps * 32, 0, st>>>(P);
   else if (batch == 1 && minb == 12)
@@ -739,6 +741,13 @@ extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int
     k_window_stats<2, 6><<<grid, kWinWarps * 32, 0, st>>>(P);
   else
     k_window_stats<4, 4><<<grid, kWinWarps * 32, 0, st>>>(P);
+#else
+  // one window per warp, 12 blocks per SM: the configuration that measured fastest
+  // (profiles/round1_notes.md); the batched variants live in -DSAI_EXPERIMENTS builds
+  const int64_t want = (n_windows + kWinWarps - 1) / kWinWarps;
+  const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_jobs);
+  k_window_stats<1, 12><<<grid, kWinWarps * 32, 0, st>>>(P);
+#endif
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }

@@ -302,31 +302,33 @@ class ChunkPreprocessor:
         ref_data, ref_samples = groups["ref"]
         tgt_data, tgt_samples = groups["tgt"]
         src_data, src_samples = groups["src"]
-        out_data, _ = groups["outgroup"]
+        out_data, out_samples = groups["outgroup"]
         if start is None and end is None:
             windows = {t: split_genome(tgt_data[t].POS, self.win_len, self.win_step) for t in tgt_samples}
         else:
             wins = chunk_windows(start, end, self.win_len, self.win_step)
             windows = {t: wins for t in tgt_samples}
         if ref_data is None or tgt_data is None or src_data is None:
-            return self._empty_items(chr_name, windows, ref_samples, tgt_samples, src_samples)
+            return self._empty_items(chr_name, windows, ref_samples, tgt_samples, src_samples, out_samples)
         return score_populations(
             chr_name, windows, ref_data, tgt_data, src_data, self.ploidy_config, self.stat_config,
             self.anc_allele_available, self.engine, out_data=out_data, num_src=self.num_src,
         )
 
-    def _empty_items(self, chr_name, windows, ref_samples, tgt_samples, src_samples):
-        # no data in the region: window_generator.py:249-289 + feature_preprocessor.py:131-144
+    def _empty_items(self, chr_name, windows, ref_samples, tgt_samples, src_samples, out_samples=None):
+        # no data in the region: window_generator.py:249-289 (product over the outgroup populations
+        # too, :269-273) + feature_preprocessor.py:131-144
         stats = [s for s in self.stat_config.root.keys() if s in ("U", "Q")]
         four = [s for s in self.stat_config.root.keys() if s in ("Danc", "Dplus", "df", "fd", "DD")]
         items = []
-        for ref_pop, tgt_pop, src_comb in product(
-            ref_samples, tgt_samples, list(combinations(src_samples.keys(), self.num_src))
+        for ref_pop, tgt_pop, src_comb, out_pop in product(
+            ref_samples, tgt_samples, list(combinations(src_samples.keys(), self.num_src)), out_samples or [None]
         ):
             for start, end in windows[tgt_pop]:
                 it = {
                     "chr_name": chr_name, "start": start, "end": end, "ref_pop": ref_pop, "tgt_pop": tgt_pop,
-                    "src_pop_list": src_comb, "out_pop": "NA", "nsnps": 0, "cdd_pos": {},
+                    "src_pop_list": src_comb, "out_pop": "NA" if out_pop is None else out_pop, "nsnps": 0,
+                    "cdd_pos": {},
                 }
                 for s in four:
                     it[s] = [np.nan for _ in src_comb] if len(src_comb) > 1 else np.nan

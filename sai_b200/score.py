@@ -41,10 +41,11 @@ def score(
                 raise ValueError(
                     f"The {stat_name} statistic requires polarized data, please provide the ancestral allele information with `--anc-alleles`."
                 )
-    # one chunk per worker slot, processed one after the other on this GPU
-    # (sai.py:86-93 fixes num_chunks=1; the multi-GPU driver is sai_b200.distributed)
+    # ONE chunk, as sai.py:86-93 (num_chunks=1; `num_workers` is accepted and ignored there too):
+    # rows come out product-major / windows-inner, identical to the reference's text.  Real
+    # parallelism is sai_b200.multiprocessing.mp_pool (one worker per GPU) or sai_b200.distributed.
     generator = ChunkGenerator(vcf_file=vcf_file, chr_name=chr_name, window_size=win_len, step_size=win_step,
-                               num_chunks=max(1, int(num_workers)))
+                               num_chunks=1)
     pre = ChunkPreprocessor(
         vcf_file=vcf_file,
         ref_ind_file=pop_config.get_population("ref"),

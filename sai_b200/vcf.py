@@ -473,11 +473,19 @@ def _scan_sorted_region(vcf_file, chr_name, start, end, on_header, on_lines, n_t
                 return False
             body = he + 1
 
-            def line_at(off: int):  # first line starting at or after `off`
+            class _Unparsable(Exception):
+                pass
+
+            def line_at(off: int):  # first line starting at or after `off`; POS None only past the last line
                 ls = body if off <= body else (lambda nl: total if nl < 0 else nl + 1)(mm.find(b"\n", off - 1))
                 if ls >= total:
                     return total, None
-                return ls, pos_of_line(mm[ls : min(total, ls + 64)], 0)
+                # CHROM <TAB> POS <TAB>: probe to the second TAB (contig names can be long), not a fixed width
+                t1 = mm.find(b"\t", ls)
+                t2 = mm.find(b"\t", t1 + 1) if t1 >= 0 else -1
+                if t2 < 0 or t2 - t1 > 12 or not mm[t1 + 1 : t2].isdigit():
+                    raise _Unparsable  # not a data line we understand: let the full scan deal with the file
+                return ls, int(mm[t1 + 1 : t2])
 
             def first_line(pred):  # start of the first line whose POS satisfies the monotone `pred`
                 lo, hi = body, total
@@ -490,7 +498,10 @@ def _scan_sorted_region(vcf_file, chr_name, start, end, on_header, on_lines, n_t
                         lo = ls + 1
                 return line_at(lo)[0]
 
-            lo, hi = first_line(lambda p: p >= start), first_line(lambda p: p > end)
+            try:
+                lo, hi = first_line(lambda p: p >= start), first_line(lambda p: p > end)
+            except _Unparsable:
+                return False
             on_header(mm[h:he])
             if hi > lo:
                 view = np.frombuffer(mm, dtype=np.uint8)
@@ -775,13 +786,24 @@ def read_data(
     ``is_phased=False``, no fixed-variant / missing filters).  ``native=True``
     parses the file once for all populations with ``sai_vcf_parse_gt``;
     ``native=False`` is the pure-Python reader kept as a cross-check."""
-    anc = None
+    # The reference reads the VCF region first and returns None (-> NaN rows) when it holds no
+    # record, BEFORE it looks at the ancestral-allele table (utils.py:123-141 then :152-158): a
+    # chunk that falls into a gap (centromere) must not fail because the table is empty there too.
+    # So an empty table is only an error once the region turns out to have records.
+    anc, anc_error = None, None
     if anc_allele_file:
-        anc = read_anc_arrays(anc_allele_file, chr_name, start, end)
+        try:
+            anc = read_anc_arrays(anc_allele_file, chr_name, start, end)
+        except ValueError as e:
+            if "No ancestral allele is found" not in str(e):
+                raise
+            anc_error = e
     groups = (("ref", ref_ind_file), ("tgt", tgt_ind_file), ("src", src_ind_file), ("outgroup", out_ind_file))
     if not native:
         anc = anc.as_dict() if anc is not None else None
         region = VcfRegion(vcf_file, chr_name, start, end)
+        if anc_error is not None and region.pos.size:
+            raise anc_error
         out = {}
         for group, ind_file in groups:
             if ind_file is None or (group == "outgroup" and group not in ploidy_config.root):
@@ -828,6 +850,8 @@ def read_data(
         return read_data(vcf_file, chr_name, ploidy_config, ref_ind_file, tgt_ind_file, src_ind_file, out_ind_file,
                          anc_allele_file, start, end, native=False)
     pos, gt = parsed
+    if anc_error is not None and pos.size:  # records but no ancestral allele in the region: the reference raises
+        raise anc_error
     for group, samples, pops in plan:
         if pos.size == 0 or not pops:
             out[group] = (None, samples)

@@ -370,7 +370,23 @@ def _write_list(case, group, pops):
     return path
 
 
+# ---- 4. the input of the reference's own ingest KATs -------------------------
+def ingest_kat_inputs():
+    """tests/utils/test_utils.py:204-209 (read_anc_allele), :269-318 (check_anc_allele) run on
+    tests/data/test.data.vcf + test.anc.allele.bed + test.{ref,tgt,src}.ind.list: normalised
+    copies, so that tests/test_cabi_host.py can assert the expected values the reference's tests
+    hold (transcribed there with file:line) on the GPU box too."""
+    write_normalised_vcf(os.path.join(REF, "tests", "data", "test.data.vcf"), os.path.join(HERE, "vcf_testdata.vcf"))
+    with open(os.path.join(HERE, "vcf_testdata.anc.bed"), "w") as f:
+        for l in open(os.path.join(REF, "tests", "data", "test.anc.allele.bed")):
+            if l.strip():
+                f.write("\t".join(l.split()[:4]) + "\n")
+    for g in ("ref", "tgt", "src"):
+        _write_list("testdata", g, my_vcf.parse_ind_file(os.path.join(REF, "tests", "data", f"test.{g}.ind.list")))
+    print("vcf_testdata: inputs of the reference's ingest KATs")
+
+
 if __name__ == "__main__":
-    stat_cases()
-    pipe_cases()
-    vcf_cases()
+    steps = {"stat": stat_cases, "pipe": pipe_cases, "vcf": vcf_cases, "ingest": ingest_kat_inputs}
+    for name in (sys.argv[1:] or list(steps)):
+        steps[name]()

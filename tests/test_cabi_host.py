@@ -558,3 +558,167 @@ def test_sorted_region_read_without_index(tmp_path, n_smp, block):
         assert calls and np.array_equal(p1, p_all[5:51])
     finally:
         V._scan_text = orig
+
+
+# ---------------------------------------------------------------- N2 pinned to the reference's own ingest KATs
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _testdata_paths():
+    return (os.path.join(GOLDEN, "vcf_testdata.vcf"), os.path.join(GOLDEN, "vcf_testdata.anc.bed"),
+            *[os.path.join(GOLDEN, f"vcf_testdata.{g}.list") for g in ("ref", "tgt", "src")])
+
+
+def test_reference_kat_read_anc_allele():
+    """tests/utils/test_utils.py:204-209: `read_anc_allele(test.anc.allele.bed, "21")` ==
+    {"21": {2309: "G", 7879: "A", 11484: "-", 48989: "C"}} -- the "-" entry is kept as is."""
+    from sai_b200.vcf import read_anc_allele, read_anc_arrays
+
+    _, anc, *_ = _testdata_paths()
+    assert read_anc_allele(anc, "21") == {2309: "G", 7879: "A", 11484: "-", 48989: "C"}
+    arr = read_anc_arrays(anc, "21", 5000, 20000)
+    assert arr.as_dict() == {7879: "A", 11484: "-"}
+    with pytest.raises(ValueError, match="No ancestral allele is found for chromosome 22."):
+        read_anc_allele(anc, "22")
+    with pytest.raises(ValueError, match="in the region 3000-4000"):
+        read_anc_allele(anc, "21", 3000, 4000)
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_reference_kat_check_anc_allele(native):
+    """tests/utils/test_utils.py:269-318 (`test_check_anc_allele`): test.data.vcf filtered and
+    polarised by test.anc.allele.bed keeps positions [2309, 7879, 48989] (11484 has "-": neither
+    REF nor ALT -> removed) and flips 7879 (ancestral == ALT "A").  The reference's test holds the
+    haplotype matrices (is_phased=True default: `.reshape(3, 4)`); the scoring path uses
+    is_phased=False (window_generator.py:113), i.e. the per-individual sums of the same literals:
+        ref1 [[0,0],[0,0]] [[1,1],[1,1]] [[0,0],[0,0]]  -> [[0,0],[2,2],[0,0]]
+        tgt1 [[1,0],[0,0]] [[1,1],[1,0]] [[0,0],[0,1]]  -> [[1,0],[2,1],[0,1]]
+        tgt2 [[0,0],[0,0]] [[1,1],[1,1]] [[0,0],[0,0]]  -> [[0,0],[2,2],[0,0]]"""
+    from sai_b200.configs import PloidyConfig
+    from sai_b200.vcf import read_data
+
+    vcf, anc, ref_l, tgt_l, src_l = _testdata_paths()
+    pc = PloidyConfig({"ref": {"ref1": 2}, "tgt": {"tgt1": 2, "tgt2": 2}, "src": {"src1": 2, "src2": 2}})
+    d = read_data(vcf, "21", pc, ref_l, tgt_l, None, None, anc, native=native)
+    exp_pos = [2309, 7879, 48989]
+    assert np.array_equal(d["ref"][0]["ref1"].GT, [[0, 0], [2, 2], [0, 0]])
+    assert np.array_equal(d["tgt"][0]["tgt1"].GT, [[1, 0], [2, 1], [0, 1]])
+    assert np.array_equal(d["tgt"][0]["tgt2"].GT, [[0, 0], [2, 2], [0, 0]])
+    for g, p in (("ref", "ref1"), ("tgt", "tgt1"), ("tgt", "tgt2")):
+        assert np.array_equal(d[g][0][p].POS, exp_pos)
+    assert d["src"] == (None, None)
+    # tests/utils/test_utils.py:154-200 (`test_read_data_from_file`): without the table all 19
+    # records of chromosome 21 come back (`.reshape(19, 4)`), the chromosome-20 line does not;
+    # the sample dicts are those of parse_ind_file
+    d = read_data(vcf, "21", pc, ref_l, tgt_l, None, None, None, native=native)
+    assert d["ref"][0]["ref1"].GT.shape == (19, 2) and d["tgt"][0]["tgt2"].GT.shape == (19, 2)
+    assert d["ref"][1] == {"ref1": ["ind5", "ind6"]} and d["tgt"][1] == {"tgt1": ["ind1", "ind2"], "tgt2": ["ind3", "ind4"]}
+    assert d["tgt"][0]["tgt1"].POS[0] == 2309 and d["tgt"][0]["tgt1"].GT[0].tolist() == [1, 0]
+
+
+def test_reference_kat_flip_snps():
+    """tests/utils/test_utils.py:404-419 (`test_flip_snps`): flipping positions 100, 200, 400 of
+        100 [[0,1],[1,1]]  200 [[1,1],[1,1]]  300 [[0,0],[0,1]]  400 [[1,0],[0,0]]
+    gives [[1,0],[0,0]], [[0,0],[0,0]], [[0,0],[0,1]] (unchanged), [[0,1],[1,1]] -- here through
+    the native parser's flip (ancestral allele == ALT) and the pure-Python `_polarise`, as sums."""
+    from sai_b200.configs import PloidyConfig
+    from sai_b200.vcf import read_data
+
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        vcf = os.path.join(tmp, "f.vcf")
+        rows = {100: ("0|1", "1|1"), 200: ("1|1", "1|1"), 300: ("0|0", "0|1"), 400: ("1|0", "0|0")}
+        with open(vcf, "w") as f:
+            f.write("##fileformat=VCFv4.1\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\n")
+            for p, (a, b) in rows.items():
+                f.write(f"1\t{p}\t.\tA\tC\t.\t.\t.\tGT\t{a}\t{b}\n")
+        bed = os.path.join(tmp, "anc.bed")
+        with open(bed, "w") as f:
+            for p in rows:
+                f.write(f"1\t{p - 1}\t{p}\t{'A' if p == 300 else 'C'}\n")  # ALT ancestral at 100, 200, 400
+        lst = os.path.join(tmp, "p.list")
+        open(lst, "w").write("P\ta\nP\tb\n")
+        pc = PloidyConfig({"ref": {"P": 2}, "tgt": {"P": 2}, "src": {"P": 2}})
+        for native in (True, False):
+            d = read_data(vcf, "1", pc, lst, lst, lst, None, bed, native=native)
+            assert d["ref"][0]["P"].GT.tolist() == [[1, 0], [0, 0], [0, 1], [1, 2]], native
+            assert d["ref"][0]["P"].POS.tolist() == [100, 200, 300, 400]
+
+
+# ---------------------------------------------------------------- advisor findings (round 1)
+def _gap_vcf(tmp_path, contig="9"):
+    """Sites at 1000..4000 and 60000..64000: a gap in between (a centromere)."""
+    vcf = tmp_path / "gap.vcf"
+    pos = list(range(1000, 4001, 10)) + list(range(60000, 64001, 10))
+    with open(vcf, "w") as f:
+        f.write("##fileformat=VCFv4.1\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\tc\n")
+        for i, p in enumerate(pos):
+            f.write(f"{contig}\t{p}\t.\tA\tC\t.\t.\t.\tGT\t{i % 2}|0\t0|{(i // 2) % 2}\t1|1\n")
+    bed = tmp_path / "gap.bed"
+    with open(bed, "w") as f:
+        for p in pos:
+            f.write(f"{contig}\t{p - 1}\t{p}\tA\n")
+    for g, s in (("ref", "a"), ("tgt", "b"), ("src", "c"), ("out", "a")):
+        (tmp_path / f"{g}.list").write_text(f"{g.upper()}\t{s}\n")
+    return str(vcf), str(bed), pos
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_gap_chunk_with_anc_alleles_is_empty_not_an_error(tmp_path, native):
+    """A chunk without records AND without ancestral alleles: the reference returns None from the
+    VCF read before it opens the table (utils.py:123-141) -> NaN rows; only a region WITH records
+    and no ancestral allele raises."""
+    from sai_b200.configs import PloidyConfig
+    from sai_b200.vcf import read_data
+
+    vcf, bed, pos = _gap_vcf(tmp_path)
+    pc = PloidyConfig({"ref": {"REF": 2}, "tgt": {"TGT": 2}, "src": {"SRC": 2}})
+    lists = [str(tmp_path / f"{g}.list") for g in ("ref", "tgt", "src")]
+    d = read_data(vcf, "9", pc, *lists, None, bed, start=20001, end=50000, native=native)
+    for g in ("ref", "tgt", "src"):
+        assert d[g][0] is None and d[g][1] is not None
+    d = read_data(vcf, "9", pc, *lists, None, bed, start=1, end=50000, native=native)
+    assert d["ref"][0]["REF"].POS.size == 301
+    short = tmp_path / "short.bed"  # ancestral alleles only for the second block
+    short.write_text("".join(f"9\t{p - 1}\t{p}\tA\n" for p in pos if p >= 60000))
+    with pytest.raises(ValueError, match="No ancestral allele is found for chromosome 9 in the region 1-50000"):
+        read_data(vcf, "9", pc, *lists, None, str(short), start=1, end=50000, native=native)
+    d = read_data(vcf, "9", pc, *lists, None, str(short), start=20001, end=50000, native=native)
+    assert d["tgt"][0] is None
+
+
+def test_sorted_region_read_with_long_contig_name(tmp_path):
+    """The text bisection reads POS up to the second TAB, whatever the length of CHROM."""
+    from sai_b200.configs import PloidyConfig
+    from sai_b200.vcf import read_data
+
+    contig = "scaffold_" + "x" * 60  # 69 characters
+    vcf, bed, pos = _gap_vcf(tmp_path, contig)
+    pc = PloidyConfig({"ref": {"REF": 2}, "tgt": {"TGT": 2}, "src": {"SRC": 2}})
+    lists = [str(tmp_path / f"{g}.list") for g in ("ref", "tgt", "src")]
+    for region in ((2000, 3000), (3500, 61000), (1, 100000), (4001, 59999)):
+        a = read_data(vcf, contig, pc, *lists, None, None, start=region[0], end=region[1], native=True)
+        b = read_data(vcf, contig, pc, *lists, None, None, start=region[0], end=region[1], native=False)
+        want = [p for p in pos if region[0] <= p <= region[1]]
+        if not want:
+            assert a["ref"][0] is None and b["ref"][0] is None
+            continue
+        assert a["ref"][0]["REF"].POS.tolist() == want == b["ref"][0]["REF"].POS.tolist()
+        assert np.array_equal(a["tgt"][0]["TGT"].GT, b["tgt"][0]["TGT"].GT)
+
+
+def test_empty_items_carry_the_outgroup(tmp_path):
+    """window_generator.py:269-273: the rows of an empty region are the product over the outgroup
+    populations too and name them in the Outgroup column."""
+    from sai_b200.configs import PloidyConfig, StatConfig
+    from sai_b200.preprocessors import ChunkPreprocessor
+
+    vcf, bed, _ = _gap_vcf(tmp_path)
+    pc = PloidyConfig({"ref": {"REF": 2}, "tgt": {"TGT": 2}, "src": {"SRC": 2}, "outgroup": {"OUT": 2}})
+    sc = StatConfig({"U": {"ref": {"REF": 0.5}, "tgt": {"TGT": 0.1}, "src": {"SRC": "=1"}}, "fd": True})
+    pre = ChunkPreprocessor(vcf, *[str(tmp_path / f"{g}.list") for g in ("ref", "tgt", "src", "out")], 10000, 10000,
+                            str(tmp_path / "o.tsv"), pc, sc, anc_allele_file=bed)
+    items = pre.run("9", 20001, 50000)  # no record in the region: no GPU work
+    assert len(items) == 3 and [it["out_pop"] for it in items] == ["OUT"] * 3
+    assert all(np.isnan(it["U"]) and np.isnan(it["fd"]) and it["nsnps"] == 0 for it in items)

@@ -489,17 +489,20 @@ def test_sharded_equals_unsharded_gpu(engine):
 
 
 # ---------------------------------------------------------------- K1 alone
-@pytest.mark.parametrize("variant", [0, 2])
-@pytest.mark.parametrize("shape", [(1, [1, 1, 1]), (33, [5, 40, 2]), (1000, [257, 96, 3]), (4097, [1500, 1000, 4])])
-def test_site_counts_vs_oracle(variant, shape):
+@pytest.mark.parametrize("ploidy", [[2, 1, 4], [4, 8, 6], [3, 12, 2], [14, 5, 7]])
+@pytest.mark.parametrize("shape", [(1, [1, 1, 1]), (33, [5, 40, 2]), (1000, [257, 96, 3]), (4097, [1500, 1000, 4]),
+                                   (300, [20000, 8, 1]), (2500, [256, 512, 129]), (700, [97, 1120, 1185])])
+def test_site_counts_vs_oracle(ploidy, shape):
+    """Counts of every population against calc_freq's numerator / called count for 2-, 3- and
+    4-plane populations (ploidy 1..14), with group counts that exercise the carry-save batches
+    (8 pairs / 4 groups) and their remainders."""
     import torch
 
     from sai_b200.encode import pack_populations
     from sai_b200.scoring import DeviceScorer
 
     n_sites, n_ind = shape
-    rng = np.random.default_rng(n_sites)
-    ploidy = [2, 1, 4]
+    rng = np.random.default_rng(n_sites + 7 * ploidy[0])
     mats = []
     for n, p in zip(n_ind, ploidy):
         g = rng.integers(0, p + 1, size=(n_sites, n)).astype(np.int8)
@@ -507,61 +510,30 @@ def test_site_counts_vs_oracle(variant, shape):
         g[rng.random(n_sites) < 0.05] = -2  # whole population missing at some sites
         mats.append(g)
     pg = pack_populations(mats, ploidy, np.arange(n_sites))
+    want_bits = [2 if p <= 2 else 3 if p <= 6 else 4 for p in ploidy]
+    assert [pg.layout.pop[i].bits for i in range(3)] == want_bits
     sc = DeviceScorer(pg.layout, n_sites, 0, 1)
     d_packed = torch.from_numpy(pg.packed).cuda()
-    num, called = sc.site_counts(d_packed, variant)
+    num, called = sc.site_counts(d_packed)
     num, called = num.cpu().numpy(), called.cpu().numpy()
     for i, g in enumerate(mats):
         en, ec = orc.site_counts(g)
-        assert np.array_equal(num[i, :n_sites], en), (i, variant)
-        assert np.array_equal(called[i, :n_sites], ec), (i, variant)
+        assert np.array_equal(num[i, :n_sites], en), i
+        assert np.array_equal(called[i, :n_sites], ec), i
         assert not called[i, n_sites:].any()  # padding sites are all-missing
 
 
-@pytest.mark.parametrize("variant", [1, 5, 6, 7])
-@pytest.mark.parametrize("shape", [(1, [1, 1, 1]), (33, [5, 40, 2]), (1000, [257, 96, 3]), (4097, [1500, 1000, 4]),
-                                   (300, [20000, 8, 1]), (2500, [256, 512, 64, 33])])
-def test_site_counts_variants(variant, shape):
-    """The alternative genotype passes (16 loads in flight; bulk-copy rings of 3 / 4 / 6 stages):
-    counts against the oracle and fused masks / Q values against the default kernel, for batch
-    shapes with and without partial batches."""
+def test_site_variants_are_not_in_the_product_library():
+    """The A/B variants of the genotype pass live in -DSAI_EXPERIMENTS builds only."""
     import torch
 
     from sai_b200.encode import pack_populations
-    from sai_b200.scoring import DeviceScorer, make_job
+    from sai_b200.scoring import DeviceScorer
 
-    n_sites, n_ind = shape
-    rng = np.random.default_rng(n_sites + variant)
-    ploidy = [2, 1, 2, 2][: len(n_ind)]
-    f = rng.beta(0.3, 1.5, size=n_sites)
-    mats = []
-    for n, p in zip(n_ind, ploidy):
-        g = rng.binomial(p, f[:, None], size=(n_sites, n)).astype(np.int8)
-        g[rng.random(g.shape) < 0.05] = -1
-        g[rng.random(n_sites) < 0.03] = -2
-        mats.append(g)
-    mats[2][rng.random(n_sites) < 0.2] = ploidy[2]
-    pg = pack_populations(mats, ploidy, np.arange(n_sites))
-    assert all(pg.layout.pop[i].bits == 2 for i in range(len(n_ind)))
-    d_packed = torch.from_numpy(pg.packed).cuda()
-    sc = DeviceScorer(pg.layout, n_sites, 0, 2)
-    num, called = sc.site_counts(d_packed, variant)
-    num, called = num.cpu().numpy(), called.cpu().numpy()
-    for i, g in enumerate(mats):
-        en, ec = orc.site_counts(g)
-        assert np.array_equal(num[i, :n_sites], en), (i, variant)
-        assert np.array_equal(called[i, :n_sites], ec), (i, variant)
-        assert not called[i, n_sites:].any()
-    jobs = [make_job(0, 1, [2], True, u=dict(w=0.4, x=0.1, y_list=[(">=", 0.5)]), q=dict(w=0.4, quantile=0.9, y_list=[(">=", 0.5)])),
-            make_job(1, 0, [2], False, u=dict(w=0.6, x=0.0, y_list=[("=", 1.0)]), q=dict(w=0.6, quantile=0.5, y_list=[("=", 1.0)]))]
-    ref = DeviceScorer(pg.layout, n_sites, 0, 2)
-    ref.site_flags(d_packed, jobs, 0)
-    sc.site_flags(d_packed, jobs, variant, with_counts=True)
-    assert torch.equal(sc.mask_u, ref.mask_u) and torch.equal(sc.mask_q, ref.mask_q)
-    flagged = np.unpackbits(ref.mask_q.cpu().numpy().view(np.uint8), bitorder="little").reshape(2, -1).astype(bool)
-    qa, qb = sc.qval.cpu().numpy(), ref.qval.cpu().numpy()
-    assert np.array_equal(qa[flagged[:, : qa.shape[1]]], qb[flagged[:, : qb.shape[1]]])
-    assert flagged.any() or n_sites < 30
+    pg = pack_populations([np.zeros((40, 3), dtype=np.int8)], [2], np.arange(40))
+    sc = DeviceScorer(pg.layout, 40, 0, 1)
+    with pytest.raises(ValueError, match="SAI_EXPERIMENTS"):
+        sc.site_counts(torch.from_numpy(pg.packed).cuda(), variant=5)
 
 
 # ---------------------------------------------------------------- randomized differential
@@ -705,12 +677,10 @@ def test_device_scorer_matches_engine_and_cached_counts(engine):
     d_pos = torch.from_numpy(pg.pos).cuda()
     d_ws = torch.tensor([w[0] for w in wins], dtype=torch.int64, device="cuda")
     d_we = torch.tensor([w[1] for w in wins], dtype=torch.int64, device="cuda")
-    for mode in ("fused", "counts", "simple"):
+    for mode in ("fused", "counts"):
         sc = DeviceScorer(pg.layout, pg.n_sites, len(wins), len(jobs))
         if mode == "fused":
             sc.step(d_packed, d_pos, d_ws, d_we, jobs)
-        elif mode == "simple":
-            sc.step(d_packed, d_pos, d_ws, d_we, jobs, variant=2)
         else:
             sc.site_counts(d_packed)
             sc.flags_from_counts(jobs)
