@@ -178,8 +178,13 @@ def algorithmic_bytes(wl, n_windows: int) -> int:
 
 
 # --------------------------------------------------------------------------
-# CPU baseline: the oracle on a bounded sample, all host cores
+# CPU arm: the reference's own implementation of the path on the host cores
 # --------------------------------------------------------------------------
+# kind "reference": the UNMODIFIED reference package (oracle/_ref, pip-installed from
+# /root/reference by oracle/build_ref.py at build() time; it travels with the snapshot) --
+# WindowGenerator._window_generator + FeaturePreprocessor.run driven by the reference's own
+# sai.multiprocessing.mp_pool over ChunkGenerator._split_windows_ranges chunks (oracle/ref_driver.py).
+# kind "port": oracle/sai_oracle.py over a fork pool -- only when oracle/_ref is absent.
 _CPU = {}
 
 
@@ -191,25 +196,26 @@ def _cpu_chunk(args):
     pos = d["pos"]
     lo, hi = np.searchsorted(pos, start, "left"), np.searchsorted(pos, end, "right")
     sub = lambda m: {k: orc.PopData(pos[lo:hi], v[lo:hi]) for k, v in m.items()}  # region read
-    items = orc.score_chunk("1", start, end, d["win_len"], d["win_step"], sub(d["ref"]), sub(d["tgt"]), sub(d["src"]),
-                            d["pc"], d["sc"], d["anc"])
-    return len(items)
+    return orc.score_chunk("1", start, end, d["win_len"], d["win_step"], sub(d["ref"]), sub(d["tgt"]), sub(d["src"]),
+                           d["pc"], d["sc"], d["anc"])
 
 
 def cpu_reference_setup(wl, sample_sites: int, seed: int):
     """Decodes `sample_sites` of the synthetic workload (generated by the same
-    device generator, so the CPU and GPU arms see the same data model) into the
-    int64 matrices the reference holds."""
+    device generator, so the CPU and GPU arms see the same data: the sample is
+    the first `sample_sites` sites of the GPU arm's chromosome) into the int64
+    matrices the reference holds.  Returns the windows fully inside the sample."""
     import ctypes as C
 
     import torch
 
     from sai_b200 import _cabi
-    from sai_b200.configs import PloidyConfig, StatConfig
     from sai_b200.encode import PackedGenotypes, make_layout, unpack_population
     from sai_b200.scoring import synth_fill
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_driver
+
     lay = make_layout(list(wl["n_ind"]), list(wl["ploidy"]), [2, 2, 2])
     nbytes = int(_cabi.load().sai_packed_bytes(C.byref(lay), sample_sites))
     d_packed = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
@@ -220,40 +226,86 @@ def cpu_reference_setup(wl, sample_sites: int, seed: int):
     mats = [unpack_population(pg, p).astype(np.int64) for p in range(3)]  # int64, as the reference holds them
     op, y = wl["y"]
     ystr = f"{op}{y}"
-    _CPU.update(
-        pos=pos, ref={"REF": mats[0]}, tgt={"TGT": mats[1]}, src={"SRC": mats[2]},
-        win_len=wl["win_len"], win_step=wl["win_step"], anc=wl["anc"],
-        pc=PloidyConfig({"ref": {"REF": 2}, "tgt": {"TGT": 2}, "src": {"SRC": 2}}),
-        sc=StatConfig({"U": {"ref": {"REF": wl["w"]}, "tgt": {"TGT": wl["x"]}, "src": {"SRC": ystr}},
-                       "Q": {"ref": {"REF": wl["w"]}, "tgt": {"TGT": wl["quantile"]}, "src": {"SRC": ystr}}}),
-    )
+    ploidies = {"ref": {"REF": 2}, "tgt": {"TGT": 2}, "src": {"SRC": 2}}
+    stats = {"U": {"ref": {"REF": wl["w"]}, "tgt": {"TGT": wl["x"]}, "src": {"SRC": ystr}},
+             "Q": {"ref": {"REF": wl["w"]}, "tgt": {"TGT": wl["quantile"]}, "src": {"SRC": ystr}}}
+    _CPU.update(pos=pos, ref={"REF": mats[0]}, tgt={"TGT": mats[1]}, src={"SRC": mats[2]},
+                win_len=wl["win_len"], win_step=wl["win_step"], anc=wl["anc"], ploidies=ploidies, stats=stats,
+                kind="reference" if ref_driver.available() else "port")
+    if _CPU["kind"] == "reference":
+        ref_driver.set_data("bench", pos, _CPU["ref"], _CPU["tgt"], _CPU["src"])
+    else:
+        from sai_b200.configs import PloidyConfig, StatConfig
+
+        _CPU.update(pc=PloidyConfig(ploidies), sc=StatConfig(stats))
     from sai_b200.windows import split_genome
 
     wins = split_genome([int(pos[0]), int(pos[-1])], wl["win_len"], wl["win_step"])
-    # only windows fully inside the sample
-    return [w for w in wins if w[1] <= int(pos[-1])]
+    return [w for w in wins if w[1] <= int(pos[-1])]  # only windows fully inside the sample
 
 
-def cpu_reference_run(wins, n_windows: int, nproc: int, pool):
-    """Scores the first `n_windows` windows of the sample, split into
-    contiguous window ranges like ChunkGenerator._split_windows_ranges
-    (8 chunks per worker, sai/sai.py:91), mapped over a process pool like
-    sai.multiprocessing.mp_pool.  Returns (windows, seconds)."""
-    from sai_b200.windows import split_windows_ranges
-
+def cpu_reference_run(wins, n_windows: int, nproc: int):
+    """Scores the first `n_windows` windows of the sample, split into contiguous
+    window ranges by ChunkGenerator._split_windows_ranges (8 chunks per worker,
+    the commented-out `num_chunks=num_workers * 8` of sai/sai.py:91), mapped over
+    `nproc` processes by the reference's mp_pool (fork Pool.map, mp_pool.py:70-71;
+    pool start-up is part of the call, as it is for a reference user).
+    Returns (items, seconds)."""
     use = wins[:n_windows]
-    chunks = split_windows_ranges(use, max(1, min(len(use), nproc * 8)))
+    n_chunks = max(1, min(len(use), nproc * 8))
+    d = _CPU
     t0 = time.perf_counter()
-    done = sum(pool.map(_cpu_chunk, chunks)) if pool is not None else sum(map(_cpu_chunk, chunks))
-    return done, time.perf_counter() - t0
+    if d["kind"] == "reference":
+        import ref_driver
+
+        items = ref_driver.score_windows("bench", "1", use, n_chunks, nproc, d["win_len"], d["win_step"],
+                                         d["ploidies"], d["stats"], d["anc"])
+    else:
+        import multiprocessing as mp
+
+        from sai_b200.windows import split_windows_ranges
+
+        chunks = split_windows_ranges(use, n_chunks)
+        if nproc <= 1:
+            parts = list(map(_cpu_chunk, chunks))
+        else:
+            with mp.get_context("fork").Pool(nproc) as pool:
+                parts = pool.map(_cpu_chunk, chunks)
+        items = [it for part in parts for it in part]
+    return items, time.perf_counter() - t0
 
 
-def cpu_pool(nproc: int):
-    import multiprocessing as mp
+def cpu_sample_text(n_windows, sample_sites, cores):
+    if _CPU["kind"] == "reference":
+        how = ("the unmodified reference (oracle/_ref: WindowGenerator + FeaturePreprocessor.run) under its own "
+               f"sai.multiprocessing.mp_pool, {cores} processes")
+    else:
+        how = f"oracle/sai_oracle.py (numpy port; oracle/_ref absent) over a {cores}-process fork pool"
+    return (f"first {n_windows} windows ({sample_sites} sites decoded to int64) of the same workload, {how}, "
+            f"8 window-range chunks per worker")
 
-    if nproc <= 1:
-        return None
-    return mp.get_context("fork").Pool(nproc)
+
+def compare_items_with_gpu(items, res, j=0):
+    """Window by window: the CPU arm's items against the GPU results of the same windows (the
+    sample is a prefix of the GPU arm's chromosome).  N(Variants), U and both candidate lists must
+    be identical, |dQ| <= 1e-12 with NaN <-> NaN (the contract); Q bit-identity is reported too."""
+    isnan = lambda v: isinstance(v, (float, np.floating)) and np.isnan(v)
+    n_bad, q_exact, max_dq = 0, True, 0.0
+    for i, it in enumerate(items):
+        ok = int(it["nsnps"]) == int(res.nsnps[j, i])
+        if it["nsnps"] > 0:  # an empty window is NaN / NaN on both sides by construction of the item
+            ok = ok and not isnan(it["U"]) and int(it["U"]) == int(res.u[j, i])
+            ok = ok and np.array_equal(np.asarray(it["cdd_pos"]["U"], dtype=np.int64), res.u_positions(j, i).astype(np.int64))
+            if isnan(it["Q"]):
+                ok = ok and bool(np.isnan(res.q[j, i])) and int(res.q_cnt[j, i]) == 0
+            else:
+                dq = abs(float(it["Q"]) - float(res.q[j, i]))
+                max_dq = max(max_dq, dq) if dq == dq else float("inf")
+                q_exact = q_exact and float(it["Q"]) == float(res.q[j, i])
+                ok = ok and dq <= 1e-12
+                ok = ok and np.array_equal(np.asarray(it["cdd_pos"]["Q"], dtype=np.int64), res.q_positions(j, i).astype(np.int64))
+        n_bad += 0 if ok else 1
+    return {"windows_compared": len(items), "mismatches": n_bad, "q_bit_identical": bool(q_exact), "max_abs_dq": max_dq}
 
 
 # --------------------------------------------------------------------------
@@ -414,22 +466,19 @@ def main():
     except Exception:
         pass
 
-    # ---- CPU baseline (rank 0, N=1 only) ----
+    # ---- CPU baseline (rank 0, N=1 only): the reference itself on a bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         sample_sites = args.cpu_sample_sites or min(S, 480_000)
         wins = cpu_reference_setup(wl, sample_sites, seed)
-        pool = cpu_pool(cores)
         n_w = len(wins)  # the whole sample: ~10-20 s of CPU work on 16 cores
-        done, secs = cpu_reference_run(wins, n_w, cores, pool)
-        if pool is not None:
-            pool.close()
+        items, secs = cpu_reference_run(wins, n_w, cores)
         cpu = {
-            "value": done / secs, "unit": "windows/s", "cores": cores, "kind": "port",
-            "sample": f"first {done} windows ({sample_sites} sites decoded to int64) of the same workload, "
-                      f"oracle/sai_oracle.py over a {cores}-process fork pool, 8 window-range chunks per worker",
-            "seconds": secs,
+            "value": len(items) / secs, "unit": "windows/s", "cores": cores, "kind": _CPU["kind"],
+            "sample": cpu_sample_text(len(items), sample_sites, cores), "seconds": secs,
+            # the same windows out of the GPU arm's device-resident pass, item by item
+            "gpu_vs_cpu_arm": compare_items_with_gpu(items, res),
         }
 
     if rank == 0:
@@ -473,37 +522,33 @@ def main():
 
 
 def reference_arm(args, wl, rank, world):
-    """The reference's CPU implementation of the path, timed on the host cores.
-    The reference is pure Python and /root/reference does not exist on the GPU
-    box, so this runs the oracle port (oracle/sai_oracle.py, a numpy restatement
-    pinned against the reference's outputs) over all host cores, the way the
-    reference's own mp_pool + _split_windows_ranges would."""
+    """The reference's CPU implementation of the path, timed on the host cores: the UNMODIFIED
+    reference package (oracle/_ref, installed from /root/reference by oracle/build_ref.py; it
+    travels to the GPU box with the snapshot) driven through its own mp_pool over all host cores
+    on a bounded sample of the workload -- see cpu_reference_run.  Falls back to the numpy port
+    (oracle/sai_oracle.py, kind "port") only when oracle/_ref is absent."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     S = wl["n_sites"]
     sample_sites = args.cpu_sample_sites or min(S, 240_000)
     wins = cpu_reference_setup(wl, sample_sites, wl["seed"])
-    pool = cpu_pool(cores)
     # calibrate: one short run, then size a step to fit the whole run in ~3 minutes
-    n0 = min(len(wins), max(8, cores))
-    done, secs = cpu_reference_run(wins, n0, cores, pool)
-    rate = done / secs
+    n0 = min(len(wins), max(8, 2 * cores))
+    items, secs = cpu_reference_run(wins, n0, cores)
+    rate = len(items) / secs
     budget = 150.0 / (args.steps + args.warmup)
     n_w = int(max(n0, min(len(wins), rate * min(budget, 15.0))))
     for _ in range(args.warmup):
-        cpu_reference_run(wins, n_w, cores, pool)
+        cpu_reference_run(wins, n_w, cores)
     t0 = time.perf_counter()
     total = 0
     for _ in range(args.steps):
-        d, _s = cpu_reference_run(wins, n_w, cores, pool)
-        total += d
+        items, _s = cpu_reference_run(wins, n_w, cores)
+        total += len(items)
     elapsed = time.perf_counter() - t0
-    if pool is not None:
-        pool.close()
     value = total / elapsed
-    sample = (f"{n_w} windows per step ({sample_sites} sites decoded to int64) of the same workload, "
-              f"oracle/sai_oracle.py over a {cores}-process fork pool, 8 window-range chunks per worker")
+    sample = "per step: " + cpu_sample_text(n_w, sample_sites, cores)
     out = {
         "impl": "reference",
         "metric": "u_q95_windows_per_sec",
@@ -520,7 +565,7 @@ def reference_arm(args, wl, rank, world):
         "data": "synthetic (same device generator, decoded to int64 on the host)",
         "config": {"workload": f"{wl['name']}: bounded sample of {S} sites x {sum(wl['n_ind'])} diploid, "
                                f"win {wl['win_len']}/{wl['win_step']}, U + Q{int(wl['quantile'] * 100)}"},
-        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": _CPU["kind"], "sample": sample},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))

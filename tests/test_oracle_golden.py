@@ -294,3 +294,40 @@ def test_pairwise_sum_model_matches_numpy():
         for rep in range(3):
             a = (rng.random(n) ** 3) * rng.choice([1e-3, 1.0, 1e3], size=n)
             assert orc.pairwise_sum_model(a) == float(np.sum(a)), (n, rep)
+
+
+# ---------------------------------------------------------------- the installed reference (oracle/_ref)
+def test_installed_reference_pool_matches_the_oracle():
+    """oracle/_ref (the unmodified reference, pip-installed by oracle/build_ref.py) driven through its
+    own mp_pool + _split_windows_ranges -- the CPU arm of bench.py -- gives the oracle's items, with
+    and without worker processes (window-range chunks with their halo == one chunk)."""
+    import ref_driver
+
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref not installed (python oracle/build_ref.py where /root/reference is mounted)")
+    import synth
+    from sai_b200.configs import PloidyConfig, StatConfig
+
+    pops = {"ref": {"AFR": (90, 2)}, "tgt": {"EUR": (70, 2)}, "src": {"NEA": (2, 2), "DEN": (1, 2)}}
+    pos, mats = synth.make_populations(11, 5000, pops, mean_gap=60.0, introgressed=0.03, missing=0.02, src_all_missing=0.003)
+    pl = {g: {p: v[1] for p, v in pops[g].items()} for g in pops}
+    stats = {"U": {"ref": {"AFR": 0.05}, "tgt": {"EUR": 0.3}, "src": {"NEA": "=1", "DEN": ">=0.5"}},
+             "Q": {"ref": {"AFR": 0.05}, "tgt": {"EUR": 0.9}, "src": {"NEA": "=1", "DEN": ">=0.5"}}}
+    i64 = lambda d: {p: m.astype(np.int64) for p, m in d.items()}
+    ref_driver.set_data("t", pos, i64(mats["ref"]), i64(mats["tgt"]), i64(mats["src"]))
+    _, _, ref_split = ref_driver.make_classes()
+    wins = ref_split([int(pos[0]), int(pos[-1])], 20000, 5000)
+    assert wins == orc.split_genome([int(pos[0]), int(pos[-1])], 20000, 5000)
+    pooled = ref_driver.score_windows("t", "1", wins, 7, 2, 20000, 5000, pl, stats, False)
+    serial = ref_driver.score_windows("t", "1", wins, 1, 1, 20000, 5000, pl, stats, False)
+    mk = lambda d: {p: orc.PopData(pos, m.astype(np.int64)) for p, m in d.items()}
+    exp = orc.score_chunk("1", wins[0][0], wins[-1][1], 20000, 5000, mk(mats["ref"]), mk(mats["tgt"]), mk(mats["src"]),
+                          PloidyConfig(pl), StatConfig(stats), False)
+    assert len(pooled) == len(serial) == len(exp) == len(wins)
+    same = lambda a, b: (a != a and b != b) or a == b
+    for a, b, e in zip(pooled, serial, exp):
+        for o in (b, e):
+            assert (a["start"], a["end"], a["nsnps"], a["src_pop_list"]) == (o["start"], o["end"], o["nsnps"], tuple(o["src_pop_list"]))
+            assert same(a["U"], o["U"]) and same(a["Q"], o["Q"])
+            assert np.array_equal(a["cdd_pos"]["U"], o["cdd_pos"]["U"]) and np.array_equal(a["cdd_pos"]["Q"], o["cdd_pos"]["Q"])
+    assert sum(a["U"] for a in pooled if a["U"] == a["U"]) > 0
