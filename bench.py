@@ -81,7 +81,7 @@ class ClockSampler:
         0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
     }
 
-    def __init__(self, index: int, period_s: float = 0.01):
+    def __init__(self, index: int, period_s: float = 0.001):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
@@ -169,6 +169,21 @@ def make_job_for(wl):
         u=dict(w=wl["w"], x=wl["x"], y_list=[wl["y"]]),
         q=dict(w=wl["w"], quantile=wl["quantile"], y_list=[wl["y"]]),
     )
+
+
+K1_SOURCES = ("site_kernels.cu", "site_cond.cuh", "popcount.cuh", "common.cuh")
+
+
+def k1_source_sha() -> str:
+    """Stamp of the sources that define k_site: profiles/k1_traffic.json (the ncu DRAM-byte
+    capture, tools/k1_traffic.py) is only quoted when it was taken from these very sources."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in K1_SOURCES:
+        with open(os.path.join(ROOT, "sai_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 def algorithmic_bytes(wl, n_windows: int) -> int:
@@ -309,6 +324,128 @@ def compare_items_with_gpu(items, res, j=0):
 
 
 # --------------------------------------------------------------------------
+# strong scaling: BASELINE config 4 (whole genome, sharded by window range + outlier threshold)
+# --------------------------------------------------------------------------
+HG19_MB = [249, 243, 198, 191, 181, 171, 159, 146, 141, 136, 135, 134, 115, 107, 103, 90, 81, 78, 59, 63, 48, 51]
+
+
+def strong_record(args, wl, lay, rank, world, local, barrier):
+    """The north_star partition, measured in the same launch as the headline: 22 autosomes with
+    hg19-proportional lengths (80 M sites x 2504, 51 GB packed), the flattened (chromosome, window)
+    list cut into `world` contiguous ranges like ChunkGenerator._split_windows_ranges, every rank
+    loading the sites of its own ranges (+ halo) and scoring them with ONE genotype pass and ONE
+    window launch (sai_b200.genome); then the genome-wide `sai outlier` threshold of the U and Q
+    columns: one all_gather_into_tensor over NVLink + the device select (no host copy).
+    TOTAL work is fixed as N grows: `ms` (max over ranks, CUDA events) should fall as 1/N.  With
+    N > 1, rank 0 also scores the whole genome alone right after, so the speed-up is measured
+    inside one run on one box (`n1_ms`)."""
+    import torch
+    import torch.distributed as dist
+
+    from sai_b200.genome import GenomeBatch, piece_site_range, shard_genome, synth_fill_piece
+    from sai_b200.outlier import device_thresholds
+    from sai_b200.windows import split_genome
+
+    total = int(args.genome_sites)
+    chrom_sites = [max(64, int(total * mb / sum(HG19_MB)) // 32 * 32) for mb in HG19_MB]
+    L, st = wl["win_len"], wl["win_step"]
+    chrom_pos = [make_positions(n, mb * 1e6 / n, 100 + c) for c, (n, mb) in enumerate(zip(chrom_sites, HG19_MB))]
+    chrom_wins = [split_genome([int(p[0]), int(p[-1])], L, st) for p in chrom_pos]
+    total_windows = sum(len(w) for w in chrom_wins)
+    job = make_job_for(wl)
+    K = max(3, min(args.steps, 10))
+
+    def build(pieces):
+        ranges = [piece_site_range(chrom_pos[p.chrom], chrom_wins[p.chrom], p) for p in pieces]
+        wins = [chrom_wins[p.chrom][p.win_lo : p.win_hi] for p in pieces]
+        n_w = sum(len(w) for w in wins)
+        batch = GenomeBatch(lay, [hi - lo for lo, hi in ranges], wins, 1, cap_u=max(8 * n_w, 1 << 16), cap_q=max(32 * n_w, 1 << 18))
+        for k, (p, (lo, hi)) in enumerate(zip(pieces, ranges)):
+            synth_fill_piece(batch, k, lo, chrom_sites[p.chrom], [0, 1, 2], 777 + p.chrom, 0.0)
+            batch.pos_view(k).copy_(torch.from_numpy(chrom_pos[p.chrom][lo:hi]))
+        torch.cuda.synchronize()
+        return batch
+
+    def time_passes(batch, sync_ranks):
+        for _ in range(3):
+            batch.score([job])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sync_ranks:
+            barrier()
+        a.record()
+        for _ in range(K):
+            batch.score([job])
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / K
+
+    shards = shard_genome(chrom_wins, world)
+    mine = shards[rank]
+    batch = build(mine)
+    ms_local = time_passes(batch, True)
+    sc = batch.scorer
+    res_totals = sc.totals.cpu().numpy()
+    assert res_totals[0, 0] <= sc.cap_u and res_totals[0, 1] <= sc.cap_q, "candidate buffers too small"
+    # the score columns stay on the device: U (NaN for an empty window, like the score file) and Q
+    u = sc.u[0].to(torch.float64)
+    cols = torch.stack([torch.where(sc.nsnps[0] == 0, torch.full_like(u, float("nan")), u), sc.q[0]])
+    max_len = max(sum(p.win_hi - p.win_lo for p in s_) for s_ in shards)  # known from the sharding: no size exchange
+    thr = device_thresholds(cols, 0.99, max_len=max_len)  # warm-up (NCCL sets the collective up lazily)
+    reps, t_thr = 5, 0.0
+    for _ in range(reps):
+        barrier()
+        t0 = time.perf_counter()
+        thr = device_thresholds(cols, 0.99, max_len=max_len)
+        t_thr += time.perf_counter() - t0
+    t_thr /= reps
+    stats = torch.tensor([ms_local, 1e3 * t_thr, float(sc.u[0].sum().item()), float(torch.isfinite(sc.q[0]).sum().item()),
+                          float(sum(batch.n_sites))], dtype=torch.float64, device="cuda")
+    per_rank = [stats.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, stats)
+    per_rank = [t.cpu().tolist() for t in per_rank]
+    ms = max(r[0] for r in per_rank)
+    out = {
+        "workload": f"BASELINE config 4: 22 autosomes, {sum(chrom_sites)} sites x {sum(wl['n_ind'])} diploid, "
+                    f"win {L}/{st}, U + Q{int(wl['quantile'] * 100)}, sharded by contiguous window ranges (+ halo) over {world} GPU(s)",
+        "scaling": "strong", "total_sites": int(sum(chrom_sites)), "total_windows": int(total_windows), "steps": K,
+        "ms": ms, "windows_per_s": total_windows / (ms / 1e3), "per_rank_ms": [r[0] for r in per_rank],
+        "per_rank_sites": [int(r[4]) for r in per_rank], "launches_per_rank_per_step": 2,
+        "threshold_ms": max(r[1] for r in per_rank), "threshold_quantile": 0.99,
+        "thresholds": {"U": thr[0], "Q": thr[1]},
+        "threshold_how": "one all_gather_into_tensor of the device-resident U / Q columns + sai_column_quantiles (device radix select); wall clock incl. the 64-byte result read",
+        "u_total": sum(r[2] for r in per_rank), "windows_with_q": int(sum(r[3] for r in per_rank)),
+    }
+    del batch, sc, cols
+    torch.cuda.empty_cache()
+    if world > 1:  # the same genome on ONE GPU of the same box, same run
+        n1 = None
+        if rank == 0:
+            whole = build(shard_genome(chrom_wins, 1)[0])
+            n1 = time_passes(whole, False)
+            wu = whole.scorer.u[0].to(torch.float64)
+            wc = torch.stack([torch.where(whole.scorer.nsnps[0] == 0, torch.full_like(wu, float("nan")), wu), whole.scorer.q[0]])
+            # single-GPU thresholds through the same kernel (no process group involved)
+            o = torch.empty((2, 4), dtype=torch.float64, device="cuda")
+            import ctypes as C
+
+            from sai_b200 import _cabi
+
+            _cabi.check(_cabi.load().sai_column_quantiles(wc.data_ptr(), 2, 1, 0, wc.shape[1], wc.shape[1], 0.99, o.data_ptr(),
+                                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            thr1 = o[:, 0].cpu().tolist()
+            out["n1_ms"] = n1
+            out["speedup_vs_one_gpu"] = n1 / ms
+            out["u_total_one_gpu"] = float(whole.scorer.u[0].sum().item())
+            out["thresholds_equal_one_gpu"] = bool(thr1[0] == thr[0] and thr1[1] == thr[1])
+            del whole
+            torch.cuda.empty_cache()
+        barrier()
+    return out if rank == 0 else None
+
+
+# --------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,6 +456,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--cpu-sample-sites", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debug)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the whole-genome strong-scaling record (debug)")
+    ap.add_argument("--genome-sites", type=int, default=80_000_000, help="sites of the whole-genome strong-scaling record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -457,14 +596,24 @@ def main():
     peak, peak_src = measured_peaks()
     alg = algorithmic_bytes(wl, W)
     achieved = alg / (k1_ms / 1e3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, "no ncu capture for this build (tools/gpu/gpu_traffic.sh writes profiles/k1_traffic.json)"
     try:
         with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("n_sites") == S:
+        if tj.get("n_sites") != S:
+            traffic_note = f"capture is for {tj.get('n_sites')} sites"
+        elif tj.get("k1_source_sha") != k1_source_sha():
+            traffic_note = "stale: the k_site sources changed since the ncu capture; re-run tools/gpu/gpu_traffic.sh"
+        else:
             traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = tj.get("source")
     except Exception:
         pass
+
+    # ---- strong scaling of the north-star partition: whole genome sharded by window range ----
+    strong = None
+    if not args.no_strong:
+        strong = strong_record(args, wl, lay, rank, world, local, barrier)
 
     # ---- CPU baseline (rank 0, N=1 only): the reference itself on a bounded sample ----
     cpu = None
@@ -506,12 +655,14 @@ def main():
             "roofline": {
                 "bound": "hbm", "kernel": "k_site (genotype pass, fused site conditions)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "k1_ms": k1_ms, "algorithmic_bytes": alg,
+                "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "k1_ms": k1_ms,
+                "algorithmic_bytes": alg,
                 "note": "peak is a copy (read + write) bandwidth; a read-only kernel with k_site's access pattern "
                         "reaches 7.0-7.2 TB/s on this GPU (tools/readbw.cu, profiles/round1_notes.md), so frac can exceed 1",
             },
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "strong": strong,
             "gpu_launches": 2 * K,
             "clocks": clocks.summary(),
             "check": {"u_total": u_total, "windows_with_q": q_finite},

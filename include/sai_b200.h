@@ -236,6 +236,34 @@ int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win
                      int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand, int64_t cap_u,
                      int32_t* d_q_cand, int64_t cap_q, void* stream);
 
+/* Several chromosomes (or chromosome pieces) in ONE launch: the pieces' tiles and positions are
+ * concatenated (every piece starts on a tile boundary; positions sorted inside a piece) and window
+ * i is searched only among the sites [d_win_first_site[i], d_win_last_site[i]) of its own piece.
+ * This is how one GPU scores its share of a whole-genome run -- the window ranges of
+ * ChunkGenerator._split_windows_ranges (sai/generators/chunk_generator.py:111-142) over the
+ * flattened (chromosome, window) list -- with one genotype pass and one window launch instead of
+ * one pair per chromosome.  Everything else as sai_window_stats. */
+int sai_window_stats_pieces(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
+                            const int64_t* d_win_end, const int32_t* d_win_first_site,
+                            const int32_t* d_win_last_site, int64_t n_windows, const sai_job* jobs,
+                            int32_t n_jobs, const uint32_t* d_mask_u, const uint32_t* d_mask_q,
+                            const double* d_qval, int64_t qval_stride, int32_t* d_nsnps,
+                            int64_t* d_u, double* d_q, int32_t* d_q_cnt, int64_t* d_u_start,
+                            int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand, int64_t cap_u,
+                            int32_t* d_q_cand, int64_t cap_q, void* stream);
+
+/* ---- N1: genome-wide outlier threshold (sai/sai.py:192-214) ------------------------------- */
+/* Linear quantile `q` (pandas Series.quantile -> numpy 'linear') of the non-NaN values of each of
+ * n_cols score columns, exact (radix select on the float64 bit patterns, numpy's separately
+ * rounded lerp).  A column is the union of n_chunks pieces of `len` doubles:
+ *     value(col, chunk, i) = d_vals[chunk*chunk_stride + col*col_stride + i]     (NaN = no value)
+ * -- the layout ONE all_gather_into_tensor of the per-GPU score arrays produces, so the
+ * multi-GPU threshold needs no host copy and no sort.  d_out[col*4 + 0..3] = threshold (NaN when
+ * the column is empty or holds a single distinct value: the reference then writes an empty
+ * table, sai.py:195-207), number of values, minimum, maximum. */
+int sai_column_quantiles(const double* d_vals, int32_t n_cols, int32_t n_chunks, int64_t chunk_stride,
+                         int64_t col_stride, int64_t len, double q, double* d_out, void* stream);
+
 /* ---- N3: site-pattern sums for Danc / Dplus / df / fd ------------------------ */
 /* From the cached counts of sai_site_counts: for every source population k and
  * window i the seven sums d_sums[(k*W + i)*7 + t], t = abba, baba, baaa, abaa,

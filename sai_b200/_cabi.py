@@ -113,6 +113,11 @@ SYMBOLS = {
         C.c_int,
         [_P, _I64, _P, _P, _I64, _JOB, _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _P],
     ),
+    "sai_window_stats_pieces": (
+        C.c_int,
+        [_P, _I64, _P, _P, _P, _P, _I64, _JOB, _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _P],
+    ),
+    "sai_column_quantiles": (C.c_int, [_P, _I32, _I32, _I64, _I64, _I64, C.c_double, _P, _P]),
     "sai_window_patterns": (
         C.c_int,
         [_LAY, _P, _I64, _P, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _P],

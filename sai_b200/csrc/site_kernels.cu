@@ -290,29 +290,77 @@ struct CountFlagParams {
   int64_t n_tiles_total;
 };
 
-// Site conditions from cached counts: one lane per site, one warp per tile.
+// Site conditions from cached counts (threshold sweeps, BASELINE config 5): lane == site, one warp
+// takes kFcTiles consecutive tiles per trip.  The counts of every population are loaded ONCE --
+// 2 * NP * kFcTiles independent coalesced 128-byte loads in flight per warp -- and then all jobs
+// of the launch (up to 8 parameter sets) are evaluated out of registers, so a set costs 1/8 of the
+// count traffic (8 (2 + K) bytes per site, L2-resident for chromosome-scale inputs) plus ~50
+// integer instructions per site.  NP = populations of the layout held in registers (1..4);
+// NP == 0 is the generic version that re-reads the counts per job through L1.
+constexpr int kFcTiles = 4;
+
+template <int NP>
+__device__ __forceinline__ int pick(const int (&a)[NP > 0 ? NP : 1], int pop) {
+  int r = a[0];
+#pragma unroll
+  for (int i = 1; i < NP; ++i) r = pop == i ? a[i] : r;  // pop is warp-uniform (kernel parameter)
+  return r;
+}
+
+template <int NP>
 __global__ void __launch_bounds__(256)
     k_flags_from_counts(const __grid_constant__ CountFlagParams P, const __grid_constant__ JobBlock JB,
                         const __grid_constant__ JobFastBlock JF) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t T = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; T < P.n_tiles_total;
-       T += warps) {
-    const int64_t site = T * kTile + lane;
-    const bool live = site < P.n_sites;
+  const int64_t n_trips = (P.n_tiles_total + kFcTiles - 1) / kFcTiles;
+  for (int64_t trip = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; trip < n_trips; trip += warps) {
+    const int64_t T0 = trip * kFcTiles;
+    int num[kFcTiles][NP > 0 ? NP : 1], cal[kFcTiles][NP > 0 ? NP : 1];
+    if (NP > 0) {
+#pragma unroll
+      for (int t = 0; t < kFcTiles; ++t) {
+        const int64_t site = (T0 + t) * kTile + lane;
+        const bool live = site < P.n_sites;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          num[t][p] = live ? __ldg(P.num + (size_t)p * P.count_stride + site) : 0;
+          cal[t][p] = live ? __ldg(P.called + (size_t)p * P.count_stride + site) : 0;
+        }
+      }
+    }
     for (int j = 0; j < JB.n_jobs; ++j) {
       const sai_job& J = JB.job[j];
-      SiteFlags f = eval_site_fast(
-          JF.job[j], J, P.lay,
-          [&](int pop) { return live ? P.num[(size_t)pop * P.count_stride + site] : 0; },
-          [&](int pop) { return live ? P.called[(size_t)pop * P.count_stride + site] : 0; });
-      const uint32_t mu = __ballot_sync(0xffffffffu, f.u);
-      const uint32_t mq = __ballot_sync(0xffffffffu, f.q);
-      if (lane == 0) {
-        P.mask_u[(size_t)j * P.n_tiles_total + T] = mu;
-        P.mask_q[(size_t)j * P.n_tiles_total + T] = mq;
+      uint32_t mu[kFcTiles], mq[kFcTiles];
+#pragma unroll
+      for (int t = 0; t < kFcTiles; ++t) {
+        const int64_t site = (T0 + t) * kTile + lane;
+        const bool live = site < P.n_sites;
+        SiteFlags f;
+        if (NP > 0) {
+          f = eval_site_fast(JF.job[j], J, P.lay, [&](int pop) { return pick<NP>(num[t], pop); },
+                             [&](int pop) { return pick<NP>(cal[t], pop); });
+        } else {
+          f = eval_site_fast(
+              JF.job[j], J, P.lay,
+              [&](int pop) { return live ? __ldg(P.num + (size_t)pop * P.count_stride + site) : 0; },
+              [&](int pop) { return live ? __ldg(P.called + (size_t)pop * P.count_stride + site) : 0; });
+        }
+        mu[t] = __ballot_sync(0xffffffffu, f.u);
+        mq[t] = __ballot_sync(0xffffffffu, f.q);
+        if (f.q) P.qval[(size_t)j * P.qval_stride + site] = f.q_tgt_freq;
       }
-      if (f.q) P.qval[(size_t)j * P.qval_stride + site] = f.q_tgt_freq;
+      // lanes 0..3 store the trip's four mask words side by side (one 16-byte segment per array)
+      uint32_t wu = mu[0], wq = mq[0];
+#pragma unroll
+      for (int t = 1; t < kFcTiles; ++t) {
+        wu = lane == t ? mu[t] : wu;
+        wq = lane == t ? mq[t] : wq;
+      }
+      if (lane < kFcTiles && T0 + lane < P.n_tiles_total) {
+        P.mask_u[(size_t)j * P.n_tiles_total + T0 + lane] = wu;
+        P.mask_q[(size_t)j * P.n_tiles_total + T0 + lane] = wq;
+      }
     }
   }
 }
@@ -638,12 +686,20 @@ int sai_flags_from_counts(const sai_layout* lay, const int32_t* d_num, const int
   JobBlock JB{};
   JB.n_jobs = n_jobs;
   for (int j = 0; j < n_jobs; ++j) JB.job[j] = jobs[j];
-  const int64_t want = (P.n_tiles_total + 7) / 8;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t n_trips = (P.n_tiles_total + kFcTiles - 1) / kFcTiles;
+  const int64_t want = (n_trips + 7) / 8;  // 8 warps per block
+  const int64_t cap = (int64_t)sm_count() * 16;
   const int grid = (int)(want < cap ? want : cap);
   JobFastBlock JF;
   fill_job_fast(*lay, JB, JF);
-  k_flags_from_counts<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P, JB, JF);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (lay->n_pops) {
+    case 1: k_flags_from_counts<1><<<grid, 256, 0, st>>>(P, JB, JF); break;
+    case 2: k_flags_from_counts<2><<<grid, 256, 0, st>>>(P, JB, JF); break;
+    case 3: k_flags_from_counts<3><<<grid, 256, 0, st>>>(P, JB, JF); break;
+    case 4: k_flags_from_counts<4><<<grid, 256, 0, st>>>(P, JB, JF); break;
+    default: k_flags_from_counts<0><<<grid, 256, 0, st>>>(P, JB, JF); break;
+  }
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }

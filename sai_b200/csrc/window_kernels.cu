@@ -28,6 +28,8 @@ struct WinParams {
   int32_t n_tiles;
   const int64_t* ws;
   const int64_t* we;
+  const int32_t* seg_lo;  // optional: window i only sees the sites [seg_lo[i], seg_hi[i]) --
+  const int32_t* seg_hi;  // several chromosomes (pieces) in one launch
   int32_t W;
   int32_t n_jobs;
   int32_t u_enabled[SAI_MAX_JOBS];
@@ -441,15 +443,16 @@ __device__ void window_generic(const WinParams& P, const JobView& J, SlowScratch
 // 32-ary lower bounds of 2*kBatch keys at once (same invariant as a single
 // search: answer in [lo, hi]); every round has 2*kBatch loads in flight.
 template <int kBatch>
-__device__ __forceinline__ void warp_lower_bound_batch(const int32_t* __restrict__ pos, int n,
+__device__ __forceinline__ void warp_lower_bound_batch(const int32_t* __restrict__ pos,
+                                                       const int (&first)[kBatch], const int (&last)[kBatch],
                                                        const int64_t (&key)[2 * kBatch], int lane,
                                                        int (&out)[2 * kBatch]) {
   int lo[2 * kBatch], hi[2 * kBatch], k32[2 * kBatch];
 #pragma unroll
   for (int t = 0; t < 2 * kBatch; ++t) {
     k32[t] = clamp_key(key[t]);
-    lo[t] = key[t] > 2147483647ll ? n : 0;
-    hi[t] = n;
+    lo[t] = key[t] > 2147483647ll ? last[t >> 1] : first[t >> 1];  // search inside [first, last)
+    hi[t] = last[t >> 1];
   }
   while (true) {
     bool any = false;
@@ -513,9 +516,18 @@ __global__ void __launch_bounds__(kWinWarps * 32, kMinBlocks)
 #pragma unroll
       for (int t = 0; t < 2 * kBatch; ++t) key[t] = (int64_t)shfl64((unsigned long long)mine, t);
     }
-    // ---- B: all searches together ----
+    // ---- B: all searches together (inside the window's own piece when pieces are given) ----
     int bnd[2 * kBatch];
-    warp_lower_bound_batch<kBatch>(P.pos, P.n_sites, key, lane, bnd);
+    {
+      int first[kBatch], last[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const bool seg = P.seg_lo != nullptr && i0 + k < P.W;
+        first[k] = seg ? __ldg(P.seg_lo + i0 + k) : 0;
+        last[k] = seg ? __ldg(P.seg_hi + i0 + k) : P.n_sites;
+      }
+      warp_lower_bound_batch<kBatch>(P.pos, first, last, key, lane, bnd);
+    }
 #pragma unroll
     for (int k = 0; k < kBatch; ++k)  // end < start: the reference's masks select nothing (window_generator.py:173-174)
       if (bnd[2 * k + 1] < bnd[2 * k]) bnd[2 * k + 1] = bnd[2 * k];
@@ -664,13 +676,14 @@ __global__ void __launch_bounds__(kWinWarps * 32, kMinBlocks)
 
 using namespace sai;
 
-extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
-                                const int64_t* d_win_end, int64_t n_windows, const sai_job* jobs,
-                                int32_t n_jobs, const uint32_t* d_mask_u, const uint32_t* d_mask_q,
-                                const double* d_qval, int64_t qval_stride, int32_t* d_nsnps,
-                                int64_t* d_u, double* d_q, int32_t* d_q_cnt, int64_t* d_u_start,
-                                int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand,
-                                int64_t cap_u, int32_t* d_q_cand, int64_t cap_q, void* stream) {
+static int window_stats_impl(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
+                             const int64_t* d_win_end, const int32_t* d_seg_lo, const int32_t* d_seg_hi,
+                             int64_t n_windows, const sai_job* jobs,
+                             int32_t n_jobs, const uint32_t* d_mask_u, const uint32_t* d_mask_q,
+                             const double* d_qval, int64_t qval_stride, int32_t* d_nsnps,
+                             int64_t* d_u, double* d_q, int32_t* d_q_cnt, int64_t* d_u_start,
+                             int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand,
+                             int64_t cap_u, int32_t* d_q_cand, int64_t cap_q, void* stream) {
   SAI_REQUIRE(d_pos && d_mask_u && d_mask_q && d_qval && d_totals, "NULL device pointer");
   SAI_REQUIRE(n_sites >= 0 && n_sites < (1ll << 31) - 64, "n_sites out of range");
   SAI_REQUIRE(n_windows >= 0 && n_windows < (1ll << 31) - 1024, "window count out of range");
@@ -688,6 +701,8 @@ extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int
   P.n_tiles = (int32_t)sai_num_tiles(n_sites);
   P.ws = d_win_start;
   P.we = d_win_end;
+  P.seg_lo = d_seg_lo;
+  P.seg_hi = d_seg_hi;
   P.W = (int32_t)n_windows;
   P.n_jobs = n_jobs;
   for (int j = 0; j < n_jobs; ++j) {
@@ -750,4 +765,30 @@ extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int
 #endif
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
+}
+
+extern "C" int sai_window_stats(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
+                                const int64_t* d_win_end, int64_t n_windows, const sai_job* jobs,
+                                int32_t n_jobs, const uint32_t* d_mask_u, const uint32_t* d_mask_q,
+                                const double* d_qval, int64_t qval_stride, int32_t* d_nsnps,
+                                int64_t* d_u, double* d_q, int32_t* d_q_cnt, int64_t* d_u_start,
+                                int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand,
+                                int64_t cap_u, int32_t* d_q_cand, int64_t cap_q, void* stream) {
+  return window_stats_impl(d_pos, n_sites, d_win_start, d_win_end, nullptr, nullptr, n_windows, jobs, n_jobs,
+                           d_mask_u, d_mask_q, d_qval, qval_stride, d_nsnps, d_u, d_q, d_q_cnt, d_u_start,
+                           d_q_start, d_totals, d_u_cand, cap_u, d_q_cand, cap_q, stream);
+}
+
+extern "C" int sai_window_stats_pieces(const int32_t* d_pos, int64_t n_sites, const int64_t* d_win_start,
+                                       const int64_t* d_win_end, const int32_t* d_win_first_site,
+                                       const int32_t* d_win_last_site, int64_t n_windows, const sai_job* jobs,
+                                       int32_t n_jobs, const uint32_t* d_mask_u, const uint32_t* d_mask_q,
+                                       const double* d_qval, int64_t qval_stride, int32_t* d_nsnps,
+                                       int64_t* d_u, double* d_q, int32_t* d_q_cnt, int64_t* d_u_start,
+                                       int64_t* d_q_start, int64_t* d_totals, int32_t* d_u_cand,
+                                       int64_t cap_u, int32_t* d_q_cand, int64_t cap_q, void* stream) {
+  SAI_REQUIRE(n_windows == 0 || (d_win_first_site && d_win_last_site), "NULL piece bounds");
+  return window_stats_impl(d_pos, n_sites, d_win_start, d_win_end, d_win_first_site, d_win_last_site, n_windows,
+                           jobs, n_jobs, d_mask_u, d_mask_q, d_qval, qval_stride, d_nsnps, d_u, d_q, d_q_cnt,
+                           d_u_start, d_q_start, d_totals, d_u_cand, cap_u, d_q_cand, cap_q, stream);
 }

@@ -9,9 +9,11 @@ Chrom/Start/End and written as ``{prefix}.{column}.{q}.outliers.tsv``.
 
 Multi-GPU: every rank holds the score rows of its own window ranges; the
 genome-wide threshold is the same on all ranks after ONE small all-gather of
-the per-rank column values (NCCL over NVLink on GPUs, gloo on CPU in tests):
-U counts travel as a histogram (exact integer order statistics), Q values as
-the padded value arrays (a histogram of floats would not be exact).
+the per-rank column values.  On GPUs (``device_thresholds``) the score arrays
+never leave the device: one ``all_gather_into_tensor`` over NVLink for ALL
+columns, then ``sai_column_quantiles`` selects the order statistics exactly
+(radix select on the float64 bit patterns) -- no host copy, no sort.  The gloo
+path (CPU tests) gathers U counts as a histogram and Q values as padded arrays.
 """
 
 from __future__ import annotations
@@ -67,15 +69,65 @@ def threshold_from_histogram(counts: np.ndarray, q: float) -> Optional[float]:
     return float(b - np.float64(d * np.float64(1 - g))) if g >= 0.5 else float(a + np.float64(d * g))
 
 
+def device_thresholds(cols, q: float, group=None, max_len: Optional[int] = None) -> list[Optional[float]]:
+    """Genome-wide thresholds of ``C`` score columns resident on the GPU.
+
+    ``cols``: float64 CUDA tensor ``[C, n_local]`` -- this rank's values of every column (U counts
+    as exact doubles, Q values; NaN = window without a value).  With an initialised NCCL group the
+    ranks' arrays are padded to ``max_len`` (the largest ``n_local``; found with one tiny MAX
+    all-reduce unless the caller knows it from the sharding) and exchanged with ONE
+    ``all_gather_into_tensor``; ``sai_column_quantiles`` then computes every column's linear
+    quantile on the device, identically on every rank.  One 32-byte-per-column read comes back.
+    ``None`` = empty or single-valued column (the reference writes an empty table, sai.py:195-207)."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _cabi
+
+    if cols.dtype != torch.float64 or cols.dim() != 2 or not cols.is_cuda:
+        raise ValueError("cols must be a float64 CUDA tensor [columns, values]")
+    n_cols, n_local = int(cols.shape[0]), int(cols.shape[1])
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    out = torch.empty((max(n_cols, 1), 4), dtype=torch.float64, device=cols.device)
+    stream = C.c_void_p(torch.cuda.current_stream(cols.device).cuda_stream)
+    lib = _cabi.load()
+    if world == 1:
+        src = cols.contiguous()
+        _cabi.check(lib.sai_column_quantiles(src.data_ptr(), n_cols, 1, 0, n_local, n_local, float(q), out.data_ptr(), stream))
+    else:
+        if max_len is None:
+            m = torch.tensor([n_local], dtype=torch.int64, device=cols.device)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+            max_len = int(m.item())
+        if n_local == max_len:
+            mine = cols.contiguous()
+        else:
+            mine = torch.full((n_cols, max_len), float("nan"), dtype=torch.float64, device=cols.device)
+            mine[:, :n_local] = cols
+        gathered = torch.empty((world, n_cols, max_len), dtype=torch.float64, device=cols.device)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+        _cabi.check(lib.sai_column_quantiles(gathered.data_ptr(), n_cols, world, n_cols * max_len, max_len, max_len,
+                                             float(q), out.data_ptr(), stream))
+    thr = out[:n_cols, 0].cpu().numpy()  # the one host read (synchronises)
+    return [None if np.isnan(t) else float(t) for t in thr]
+
+
 def distributed_threshold(local_values: np.ndarray, q: float, column: str, group=None, device=None) -> Optional[float]:
     """Genome-wide threshold of one metric column whose rows are spread over
-    the ranks of ``group``; identical on every rank."""
+    the ranks of ``group``; identical on every rank.  Host-array interface (the file-level
+    ``outlier``); with an NCCL group the values go through ``device_thresholds``."""
     import torch
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return threshold_from_values(local_values, q)
     world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        v = torch.from_numpy(np.ascontiguousarray(local_values, dtype=np.float64)).to(dev)
+        return device_thresholds(v.reshape(1, -1), q, group)[0]
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     v = np.asarray(local_values, dtype=np.float64)

@@ -285,7 +285,8 @@ class DeviceScorer:
     """Runs the kernels on data already resident in HBM, on torch's current
     stream.  torch is used for allocation and streams only."""
 
-    def __init__(self, layout, n_sites: int, n_windows: int, n_jobs: int, device=None, cap_u=None, cap_q=None):
+    def __init__(self, layout, n_sites: int, n_windows: int, n_jobs: int, device=None, cap_u=None, cap_q=None,
+                 _share: Optional["DeviceScorer"] = None):
         import torch
 
         if not torch.cuda.is_available():
@@ -299,9 +300,12 @@ class DeviceScorer:
         self.stride = self.n_tiles * _cabi.TILE_SITES
         d = self.device
         J, W = self.J, self.W
-        self.mask_u = torch.zeros((J, max(1, self.n_tiles)), dtype=torch.int32, device=d)
-        self.mask_q = torch.zeros((J, max(1, self.n_tiles)), dtype=torch.int32, device=d)
-        self.qval = torch.zeros((J, max(1, self.stride)), dtype=torch.float64, device=d)
+        if _share is not None:
+            self.mask_u, self.mask_q, self.qval = _share.mask_u, _share.mask_q, _share.qval
+        else:
+            self.mask_u = torch.zeros((J, max(1, self.n_tiles)), dtype=torch.int32, device=d)
+            self.mask_q = torch.zeros((J, max(1, self.n_tiles)), dtype=torch.int32, device=d)
+            self.qval = torch.zeros((J, max(1, self.stride)), dtype=torch.float64, device=d)
         self.nsnps = torch.zeros((J, W), dtype=torch.int32, device=d)
         self.u = torch.zeros((J, W), dtype=torch.int64, device=d)
         self.q = torch.zeros((J, W), dtype=torch.float64, device=d)
@@ -313,11 +317,19 @@ class DeviceScorer:
         self.cap_q = max(1, 4 * W + 1024) if cap_q is None else int(cap_q)
         self.u_cand = torch.zeros((J, self.cap_u), dtype=torch.int32, device=d)
         self.q_cand = torch.zeros((J, self.cap_q), dtype=torch.int32, device=d)
-        self.num = None
-        self.called = None
+        self.num = None if _share is None else _share.num
+        self.called = None if _share is None else _share.called
 
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sibling(self, n_windows: int, cap_u=None, cap_q=None) -> "DeviceScorer":
+        """A scorer over the SAME site masks / Q values / cached counts with result buffers for
+        another window list: a window-shape sweep flags the sites once and scores every
+        (win-len, step) grid from the same masks."""
+        other = DeviceScorer(self.layout, self.n_sites, n_windows, self.J, device=self.device, cap_u=cap_u, cap_q=cap_q,
+                             _share=self)
+        return other
 
     def site_counts(self, d_packed, variant: int = 0):
         """K1 alone: returns ``(num, called)`` int32 tensors ``[n_pops, stride]``."""
@@ -366,18 +378,24 @@ class DeviceScorer:
             )
         )
 
-    def window_stats(self, d_pos, d_ws, d_we, jobs):
+    def window_stats(self, d_pos, d_ws, d_we, jobs, d_first_site=None, d_last_site=None):
+        """K4.  ``d_first_site`` / ``d_last_site`` (int32 per window): the site range of the
+        window's own chromosome piece when several pieces are laid side by side
+        (``sai_window_stats_pieces``, see sai_b200.genome)."""
         jarr = _job_array(jobs)
-        self._last = (d_pos, d_ws, d_we, jobs)
-        _cabi.check(
-            self.lib.sai_window_stats(
-                d_pos.data_ptr(), self.n_sites, d_ws.data_ptr(), d_we.data_ptr(), self.W, jarr, len(jobs),
-                self.mask_u.data_ptr(), self.mask_q.data_ptr(), self.qval.data_ptr(), self.qval.shape[1],
-                self.nsnps.data_ptr(), self.u.data_ptr(), self.q.data_ptr(), self.q_cnt.data_ptr(),
-                self.u_start.data_ptr(), self.q_start.data_ptr(), self.totals.data_ptr(),
-                self.u_cand.data_ptr(), self.cap_u, self.q_cand.data_ptr(), self.cap_q, self._stream(),
-            )
+        self._last = (d_pos, d_ws, d_we, jobs, d_first_site, d_last_site)
+        head = (d_pos.data_ptr(), self.n_sites, d_ws.data_ptr(), d_we.data_ptr())
+        tail = (
+            self.W, jarr, len(jobs),
+            self.mask_u.data_ptr(), self.mask_q.data_ptr(), self.qval.data_ptr(), self.qval.shape[1],
+            self.nsnps.data_ptr(), self.u.data_ptr(), self.q.data_ptr(), self.q_cnt.data_ptr(),
+            self.u_start.data_ptr(), self.q_start.data_ptr(), self.totals.data_ptr(),
+            self.u_cand.data_ptr(), self.cap_u, self.q_cand.data_ptr(), self.cap_q, self._stream(),
         )
+        if d_first_site is None:
+            _cabi.check(self.lib.sai_window_stats(*head, *tail))
+        else:
+            _cabi.check(self.lib.sai_window_stats_pieces(*head, d_first_site.data_ptr(), d_last_site.data_ptr(), *tail))
 
     def pattern_sums(self, d_pos, d_ws, d_we, ref_pop: int, tgt_pop: int, out_pop: int, src_pops: Sequence[int]):
         """N3 from the cached counts (``site_counts`` / ``site_flags(with_counts=True)`` first):
@@ -437,7 +455,6 @@ class DeviceScorer:
         pass and the window kernel (2 launches + one 16-byte memset)."""
         self.site_flags(d_packed, jobs, variant)
         self.window_stats(d_pos, d_ws, d_we, jobs)
-        self._last = (d_pos, d_ws, d_we, jobs)
 
     def results(self) -> WindowResults:
         """Copies the results to the host (synchronises).  If the candidate

@@ -134,54 +134,61 @@ def config3(args):
 
 # --------------------------------------------------------------------------
 def config5(args):
-    """Threshold / window sweep on a 20 000-sample cohort: one genotype pass caches (num, called); every parameter
-    set re-derives the site masks from the cache."""
+    """Threshold / window sweep on a 20 000-sample cohort: one genotype pass caches (num, called); the 20 (w, x, y)
+    parameter sets are flagged from the cache 8 per launch -- once, the masks do not depend on the window shape --
+    and every (win-len, step) grid is scored from the same masks, 8 sets per window launch."""
     S = args.sites or 1_000_000
     n_ind = [12_000, 7_996, 4]
     lay = make_layout(n_ind, [2, 2, 2], [2, 2, 2])
     d_packed = device_matrix(lay, S, [0, 1, 2], 20261018 + 5, 0.0)
     pos = positions(S, 41.5, 5)
     d_pos = torch.from_numpy(pos).cuda()
-    grid_w, grid_x, grid_y = [0.01, 0.05, 0.1, 0.2, 0.5], [0.0, 0.01], [0.5, 1.0]
+    sets = [(w, x, y) for w in (0.01, 0.05, 0.1, 0.2, 0.5) for x in (0.0, 0.01) for y in (0.5, 1.0)]
+    kws = [(dict(w=w, x=x, y_list=[("=", y)]), dict(w=w, quantile=0.95, y_list=[("=", y)])) for w, x, y in sets]
+    jobs = [make_job(0, 1, [2], True, u=u, q=q) for u, q in kws]
     grid_win = [(L, st) for L in (10_000, 50_000, 100_000) for st in (5_000, 10_000, 50_000) if st <= L]
-    max_w = max(len(split_genome([int(pos[0]), int(pos[-1])], L, st)) for L, st in grid_win)
-    sc = DeviceScorer(lay, S, max_w, 1, cap_u=1 << 22, cap_q=1 << 23)
-    t_counts = timed(lambda: sc.site_counts(d_packed), reps=3)
-    packed_bytes = d_packed.numel()
+    batches = [(b, min(b + 8, len(jobs))) for b in range(0, len(jobs), 8)]
+    masters = [DeviceScorer(lay, S, 0, b1 - b0) for b0, b1 in batches]
+    t_counts = timed(lambda: masters[0].site_counts(d_packed), reps=3)
+    for m in masters[1:]:
+        m.num, m.called = masters[0].num, masters[0].called
     alg = S * (sum(n_ind) * 2 / 8 + 4)
+
+    def flag_all():
+        for m, (b0, b1) in zip(masters, batches):
+            m.flags_from_counts(jobs[b0:b1])
+
+    t_flags = timed(flag_all, reps=10)  # all 20 sets
+    t_flags1 = timed(lambda: masters[0].flags_from_counts(jobs[:1]), reps=10)  # one set per launch, for comparison
+    t_flags8 = timed(lambda: masters[0].flags_from_counts(jobs[:8]), reps=10)
+    flag_all()
     sub_pos, mats = decode_slice(lay, d_packed, pos, 9000, 128)
-    n_sets, t_flags, t_win, checked = 0, 0.0, 0.0, 0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    u_total = 0
+    t_win, checked, u_total, n_sets = 0.0, 0, 0, 0
     for (L, st) in grid_win:
         wins = split_genome([int(pos[0]), int(pos[-1])], L, st)
         d_ws, d_we = dev_windows(wins)
-        sc.W = len(wins)
-        for w in grid_w:
-            for x in grid_x:
-                for y in grid_y:
-                    u_kw = dict(w=w, x=x, y_list=[("=", y)])
-                    q_kw = dict(w=w, quantile=0.95, y_list=[("=", y)])
-                    job = make_job(0, 1, [2], True, u=u_kw, q=q_kw)
-                    ev[0].record()
-                    sc.flags_from_counts([job])
-                    ev[1].record()
-                    sc.window_stats(d_pos, d_ws, d_we, [job])
-                    ev[2].record()
-                    torch.cuda.synchronize()
-                    t_flags += ev[0].elapsed_time(ev[1])
-                    t_win += ev[1].elapsed_time(ev[2])
-                    n_sets += 1
-                    if n_sets % 9 == 1:
-                        res = sc.results()
-                        # results arrays are allocated for max_w windows; only the first len(wins) are live
-                        checked += check_windows(res, 0, wins, sub_pos, mats, [2, 2, 2], [2], u_kw, q_kw, True, max_checks=4)
-                        u_total += int(res.u[0, : len(wins)].sum())
-    print(json.dumps(dict(config=5, n_sites=S, n_samples=sum(n_ind), parameter_sets=n_sets,
+        scs = [m.sibling(len(wins), cap_u=1 << 22, cap_q=1 << 23) for m in masters]
+
+        def win_all():
+            for sc, (b0, b1) in zip(scs, batches):
+                sc.window_stats(d_pos, d_ws, d_we, jobs[b0:b1])
+
+        t_win += timed(win_all, reps=3)
+        for sc, (b0, b1) in zip(scs, batches):
+            res = sc.results()
+            for j in range(0, b1 - b0, 3):
+                checked += check_windows(res, j, wins, sub_pos, mats, [2, 2, 2], [2], *kws[b0 + j], True, max_checks=4)
+            u_total += int(res.u.sum())
+        n_sets += len(jobs)
+    counts_bytes = S * 8 * 3  # (num, called) int32 pairs of ref, tgt, src
+    print(json.dumps(dict(config=5, n_sites=S, n_samples=sum(n_ind), parameter_sets=n_sets, flag_sets=len(jobs),
                           genotype_pass_ms=t_counts, genotype_pass_gbps_algorithmic=alg / t_counts / 1e6,
-                          genotype_pass_gbps_packed=packed_bytes / t_counts / 1e6,
-                          flags_from_counts_ms_per_set=t_flags / n_sets, window_stats_ms_per_set=t_win / n_sets,
-                          oracle_windows_checked=checked, u_total_checked_sets=u_total)))
+                          flags_ms_all_20_sets=t_flags, flags_ms_per_set=t_flags / len(jobs),
+                          flags_ms_one_set_launch=t_flags1, flags_ms_eight_set_launch=t_flags8,
+                          flags_counts_gbps_eight_set_launch=counts_bytes / t_flags8 / 1e6,
+                          window_stats_ms_all_160=t_win, window_stats_ms_per_set=t_win / n_sets,
+                          sweep_ms_total=t_counts + t_flags + t_win,
+                          oracle_windows_checked=checked, u_total=u_total)))
 
 
 # --------------------------------------------------------------------------

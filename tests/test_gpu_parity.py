@@ -812,23 +812,28 @@ def test_full_size_properties():
     assert np.array_equal(rb.nsnps[0], cn[hi] - cn[np.arange(k)])
     _, rb2 = run(big)
     assert np.array_equal(rb.q, rb2.q, equal_nan=True) and np.array_equal(rb.u, rb2.u)
-    # decoded slice vs oracle
-    t0, nt = 100_000, 256
+    # decoded slices vs oracle: three places of the chromosome, every window inside them
     pps = lay.pairs_per_site
-    sl = d_packed[t0 * pps * 256 : (t0 + nt) * pps * 256].cpu().numpy()
-    sub_pos = pos[t0 * 32 : (t0 + nt) * 32]
-    pg = PackedGenotypes(lay, nt * 32, sub_pos, sl)
-    mats = [unpack_population(pg, p).astype(np.int64) for p in range(3)]
     checked = 0
-    for i, (s, e) in enumerate(big):
-        if s < sub_pos[0] or e > sub_pos[-1]:
-            continue
-        keep = (sub_pos >= s) & (sub_pos <= e)
-        eu = orc.u_statistic(mats[0][keep], mats[1][keep], [mats[2][keep]], 2, 2, [2], pos=sub_pos[keep], w=0.01, x=0.5,
-                             y_list=[("=", 1.0)], anc_allele_available=True)
-        eq = orc.q_statistic(mats[0][keep], mats[1][keep], [mats[2][keep]], 2, 2, [2], pos=sub_pos[keep], w=0.01,
-                             quantile=0.95, y_list=[("=", 1.0)], anc_allele_available=True)
-        assert rb.u[0, i] == eu["value"] and rb.nsnps[0, i] == keep.sum()
-        assert (np.isnan(rb.q[0, i]) and np.isnan(eq["value"])) or rb.q[0, i] == float(eq["value"])
-        checked += 1
-    assert checked >= 10
+    for t0, nt in ((1_000, 256), (100_000, 256), (180_000, 320)):
+        sl = d_packed[t0 * pps * 256 : (t0 + nt) * pps * 256].cpu().numpy()
+        sub_pos = pos[t0 * 32 : (t0 + nt) * 32]
+        pg = PackedGenotypes(lay, nt * 32, sub_pos, sl)
+        mats = [unpack_population(pg, p).astype(np.int64) for p in range(3)]
+        here = 0
+        for i, (s, e) in enumerate(big):
+            if s < sub_pos[0] or e > sub_pos[-1]:
+                continue
+            keep = (sub_pos >= s) & (sub_pos <= e)
+            eu = orc.u_statistic(mats[0][keep], mats[1][keep], [mats[2][keep]], 2, 2, [2], pos=sub_pos[keep], w=0.01, x=0.5,
+                                 y_list=[("=", 1.0)], anc_allele_available=True)
+            eq = orc.q_statistic(mats[0][keep], mats[1][keep], [mats[2][keep]], 2, 2, [2], pos=sub_pos[keep], w=0.01,
+                                 quantile=0.95, y_list=[("=", 1.0)], anc_allele_available=True)
+            assert rb.u[0, i] == eu["value"] and rb.nsnps[0, i] == keep.sum()
+            assert np.array_equal(rb.u_positions(0, i), eu["cdd_pos"])
+            assert (np.isnan(rb.q[0, i]) and np.isnan(eq["value"])) or rb.q[0, i] == float(eq["value"])
+            assert np.array_equal(rb.q_positions(0, i), np.asarray(eq["cdd_pos"], dtype=np.int32))
+            here += 1
+        assert here >= 10
+        checked += here
+    assert checked >= 40
