@@ -133,6 +133,12 @@ uint64_t sai_packed_bytes(const sai_layout* lay, int64_t n_sites);
 int sai_pack_i8(const sai_layout* lay, int32_t pop, const int8_t* gt,
                 int64_t n_sites, int64_t row_stride, uint8_t* packed,
                 int32_t n_threads);
+/* The vector path the packer selected on this CPU: "avx512bw", "avx2", "sse2" or "portable";
+ * sai_pack_i8_isa forces one (1 portable, 2 sse2, 3 avx2, 4 avx512bw; 0 = best; an unavailable
+ * choice falls back to the best) -- all paths produce identical bytes (tests). */
+const char* sai_pack_isa(void);
+int sai_pack_i8_isa(const sai_layout* lay, int32_t pop, const int8_t* gt, int64_t n_sites,
+                    int64_t row_stride, uint8_t* packed, int32_t n_threads, int32_t isa);
 /* Inverse of sai_pack_i8 for sites [site0, site0+n): missing decodes to -1. */
 int sai_unpack_i8(const sai_layout* lay, int32_t pop, const uint8_t* packed,
                   int64_t n_sites_total, int64_t site0, int64_t n, int8_t* gt,
@@ -377,6 +383,29 @@ int sai_engine_score_host_zt(sai_engine* e, const sai_layout* lay, const uint8_t
                              const uint64_t* zt_tile_off, const int32_t* pos, int64_t n_sites,
                              const int64_t* win_start, const int64_t* win_end, int64_t n_windows,
                              const sai_job* jobs, int32_t n_jobs, sai_host_results* out);
+
+/* Same as sai_engine_score_host straight from the reference-side representation: gt[p] is the
+ * row-major int8 matrix of population p's per-individual allele sums
+ * (gt[p][site * row_stride[p] + individual], negative = missing; what reshape_genotypes leaves
+ * in memory, sai/utils/utils.py:405-410, narrowed to int8), ordinary pageable host memory.
+ * A pool of host threads (sai_engine_set_host_threads; default: all cores) packs ~16 MB slices
+ * of tiles into a ring of pinned staging buffers with the CPU's vector unit (sai_pack_isa); each
+ * finished slice is copied to the GPU and flagged while the following slices are being packed,
+ * so the call costs about max(pack, copy) instead of pack + copy.  Returns SAI_E_DOMAIN when a
+ * value does not fit the layout's bit-planes (retry with a wider layout). */
+int sai_engine_score_host_i8(sai_engine* e, const sai_layout* lay, const int8_t* const* gt,
+                             const int64_t* row_stride, const int32_t* pos, int64_t n_sites,
+                             const int64_t* win_start, const int64_t* win_end, int64_t n_windows,
+                             const sai_job* jobs, int32_t n_jobs, sai_host_results* out);
+/* Host threads the int8 pipeline may use (<= 0: hardware concurrency).  One engine per GPU:
+ * with several ranks on a box give each its share of the cores. */
+int sai_engine_set_host_threads(sai_engine* e, int32_t n_threads);
+
+/* Another batch of jobs over the chunk of the last sai_engine_score_host* call, whose tiles,
+ * positions and windows are still resident on the device: genotype pass + window kernel, no host
+ * to device traffic.  This is how a population product of more than SAI_MAX_JOBS combinations
+ * (sai/generators/window_generator.py:164-166) is scored with ONE upload. */
+int sai_engine_score_resident(sai_engine* e, const sai_job* jobs, int32_t n_jobs, sai_host_results* out);
 
 /* After SAI_E_CAPACITY: re-runs only the window kernel on the flags still
  * resident on the device, with the (larger) buffers of `out`. */

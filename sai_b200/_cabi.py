@@ -93,6 +93,8 @@ SYMBOLS = {
     "sai_num_tiles": (_I64, [_I64]),
     "sai_packed_bytes": (_U64, [_LAY, _I64]),
     "sai_pack_i8": (C.c_int, [_LAY, _I32, _P, _I64, _I64, _P, _I32]),
+    "sai_pack_isa": (C.c_char_p, []),
+    "sai_pack_i8_isa": (C.c_int, [_LAY, _I32, _P, _I64, _I64, _P, _I32, _I32]),
     "sai_unpack_i8": (C.c_int, [_LAY, _I32, _P, _I64, _I64, _I64, _P, _I64]),
     "sai_neg_table_i8": (_I64, [_P, _I64, _I32, _I64, _P, _P, _P, _I64, _I32]),
     "sai_vcf_parse_gt": (
@@ -140,6 +142,12 @@ SYMBOLS = {
         C.c_int,
         [_P, _LAY, _P, _P, _P, _I64, _P, _P, _I64, _JOB, _I32, C.POINTER(HostResults)],
     ),
+    "sai_engine_score_host_i8": (
+        C.c_int,
+        [_P, _LAY, _P, _P, _P, _I64, _P, _P, _I64, _JOB, _I32, C.POINTER(HostResults)],
+    ),
+    "sai_engine_set_host_threads": (C.c_int, [_P, _I32]),
+    "sai_engine_score_resident": (C.c_int, [_P, _JOB, _I32, C.POINTER(HostResults)]),
     "sai_engine_rescore_windows": (C.c_int, [_P, C.POINTER(HostResults)]),
     "sai_zt_bound": (_U64, [_LAY, _I64]),
     "sai_zt_encode": (_I64, [_LAY, _P, _I64, _P, _U64, _P, _I32]),

@@ -36,14 +36,18 @@ def _nvcc() -> str:
 
 
 def sources() -> list[Path]:
-    return sorted(CSRC.glob("*.cu"))
+    """CUDA sources (nvcc) and plain C++ sources (g++: the host packer's x86 vector paths)."""
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
+
+
+GXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread", "-Wall"]
 
 
 def is_stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) + list(INCLUDE.glob("*.h"))
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -70,8 +74,11 @@ def _compile(LIB: Path, obj_dir: Path, defines: list, verbose: bool) -> Path:
     procs = []
     for src in sources():
         obj = obj_dir / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *defines, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
-        if verbose:
+        if src.suffix == ".cpp":
+            cmd = [os.environ.get("CXX", "g++"), *GXX_FLAGS, *defines, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        else:
+            cmd = [nvcc, *NVCC_FLAGS, *defines, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        if verbose and src.suffix != ".cpp":
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -81,7 +88,7 @@ def _compile(LIB: Path, obj_dir: Path, defines: list, verbose: bool) -> Path:
         if verbose or p.returncode != 0:
             sys.stderr.write(out.decode(errors="replace"))
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src.name}")
+            raise RuntimeError(f"compiling {src.name} failed")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
            "-Xcompiler", "-fPIC,-pthread", "-o", str(LIB)] + [
         str(o) for o in objs

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_pack.h"
 
 namespace sai {
 
@@ -142,79 +143,44 @@ static inline uint32_t* word_ptr(const sai_layout* lay, const sai_pop_layout& L,
 
 int sai_pack_i8(const sai_layout* lay, int32_t pop, const int8_t* gt, int64_t n_sites,
                 int64_t row_stride, uint8_t* packed, int32_t n_threads) {
+  return sai_pack_i8_isa(lay, pop, gt, n_sites, row_stride, packed, n_threads, 0);
+}
+
+int sai_pack_i8_isa(const sai_layout* lay, int32_t pop, const int8_t* gt, int64_t n_sites,
+                    int64_t row_stride, uint8_t* packed, int32_t n_threads, int32_t isa) {
   if (int rc = validate_layout(lay)) return rc;
   SAI_REQUIRE(pop >= 0 && pop < lay->n_pops, "bad population index %d", pop);
   SAI_REQUIRE(gt && packed && n_sites >= 0, "NULL argument");
   const sai_pop_layout& L = lay->pop[pop];
   SAI_REQUIRE(row_stride >= L.n_samples, "row_stride smaller than n_samples");
-  const int B = L.bits;
-  const int miss_code = (1 << B) - 1;
   const int64_t n_tiles = sai_num_tiles(n_sites);
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-  n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n_tiles));
+  n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n_tiles / 8));
   std::atomic<int> domain_err{0};
-
-  // 8 individuals per 64-bit word: sign bit -> missing code, (code >> b) & 1 gathered
-  // with a multiply ("movemask") into 8 plane bits.
-  auto pack32 = [&](const int8_t* v, uint32_t* plane) -> bool {
+  // blocks of tiles handed out dynamically (the vector row packers live in pack_simd.cpp)
+  const int64_t block = 64;
+  std::atomic<int64_t> next{0};
+  auto work = [&]() {
     bool bad = false;
-    const uint64_t ones = 0x0101010101010101ull;
-    for (int b = 0; b < B; ++b) plane[b] = 0;
-    for (int q = 0; q < 4; ++q) {
-      uint64_t x;
-      memcpy(&x, v + 8 * q, 8);
-      const uint64_t negm = ((x >> 7) & ones) * 0xffull;  // 0xff in every negative byte
-      const uint64_t val = x & ~negm;
-      // a called value must be < miss_code: byte + (128 - miss_code) sets bit 7 otherwise
-      bad |= (((val + ones * (uint64_t)(128 - miss_code)) | val) & (ones << 7)) != 0;
-      const uint64_t code = val | (negm & (ones * (uint64_t)miss_code));
-      for (int b = 0; b < B; ++b)
-        plane[b] |= (uint32_t)((((code >> b) & ones) * 0x0102040810204080ull) >> 56) << (8 * q);
-    }
-    return bad;
-  };
-  auto work = [&](int64_t t0, int64_t t1) {
-    int8_t tail[32];
-    bool bad = false;
-    for (int64_t T = t0; T < t1; ++T) {
-      for (int s = 0; s < kTile; ++s) {
-        const int64_t site = T * kTile + s;
-        const int8_t* row = site < n_sites ? gt + site * row_stride : nullptr;
-        for (int g = 0; g < L.n_groups; ++g) {
-          uint32_t plane[4];
-          const int i0 = g * 32;
-          const int cnt = row ? std::min(32, L.n_samples - i0) : 0;
-          if (cnt == 32) {
-            bad |= pack32(row + i0, plane);
-          } else {
-            memset(tail, 0xff, sizeof(tail));  // -1: missing
-            if (cnt > 0) memcpy(tail, row + i0, cnt);
-            bad |= pack32(tail, plane);
-          }
-          for (int b = 0; b < B; ++b) *word_ptr(lay, L, packed, T, s, g * B + b) = plane[b];
-        }
-        if ((L.n_groups * B) & 1) *word_ptr(lay, L, packed, T, s, L.n_groups * B) = 0u;
-      }
-    }
+    for (int64_t t0 = next.fetch_add(block); t0 < n_tiles; t0 = next.fetch_add(block))
+      bad |= pack_tiles_i8(*lay, pop, gt, n_sites, row_stride, t0, std::min(n_tiles, t0 + block), 0, packed, isa);
     if (bad) domain_err.store(1, std::memory_order_relaxed);
   };
-  if (n_threads == 1) {
-    work(0, n_tiles);
+  if (n_threads <= 1) {
+    work();
   } else {
     std::vector<std::thread> th;
-    const int64_t per = (n_tiles + n_threads - 1) / n_threads;
-    for (int i = 0; i < n_threads; ++i) {
-      int64_t a = i * per, b = std::min<int64_t>(n_tiles, a + per);
-      if (a < b) th.emplace_back(work, a, b);
-    }
+    for (int i = 0; i < n_threads; ++i) th.emplace_back(work);
     for (auto& t : th) t.join();
   }
   if (domain_err.load()) {
-    set_error("population %d: a genotype value does not fit %d bit-planes", pop, B);
+    set_error("population %d: a genotype value does not fit %d bit-planes", pop, L.bits);
     return SAI_E_DOMAIN;
   }
   return SAI_OK;
 }
+
+const char* sai_pack_isa(void) { return pack_isa(); }
 
 // Negative-value table of one int8 population matrix (DD, include/sai_b200.h "N4"): every entry v < 0 in
 // row-major order.  Two parallel passes over site blocks: count, then fill at the prefix offsets.

@@ -7,14 +7,24 @@
 // batch of device->host copies.  Device buffers are grow-only and reused across
 // calls (one engine per GPU / per worker process).
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
+#include "host_pack.h"
 
 struct sai_engine {
   int device = 0;
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   std::vector<cudaEvent_t> ev;
+  std::vector<cudaEvent_t> ev_block;  // blocking-sync events: the host sleeps on them (int8 pipeline)
+  int host_threads = 0;               // packer threads of the int8 pipeline (0: hardware concurrency)
+  void* ring = nullptr;               // pinned staging ring of the int8 pipeline
+  size_t ring_cap = 0;
   // grow-only device buffers
   struct Buf {
     void* p = nullptr;
@@ -25,6 +35,7 @@ struct sai_engine {
   int64_t n_sites = 0, W = 0;
   int32_t n_jobs = 0;
   sai_job jobs[SAI_MAX_JOBS];
+  sai_layout lay{};  // layout of the resident tiles (sai_engine_score_resident)
 };
 
 namespace sai {
@@ -155,22 +166,155 @@ void sai_engine_destroy(sai_engine* e) {
   for (auto* b : {&e->packed, &e->pos, &e->win, &e->mask, &e->qval, &e->res, &e->cand, &e->counts, &e->sums, &e->hist, &e->neg, &e->dd, &e->zt, &e->ztoff})
     if (b->p) cudaFree(b->p);
   for (auto ev : e->ev) cudaEventDestroy(ev);
+  for (auto ev : e->ev_block) cudaEventDestroy(ev);
+  if (e->ring) cudaFreeHost(e->ring);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
   delete e;
 }
 
-// Shared body of the two host entry points: `packed` (dense tiles) or, when
-// `zt_stream` is given, the zero-suppressed stream + its tile directory.
+// int8 pipeline (sai_engine_score_host_i8): the reference-side representation -- one int8 matrix
+// of per-individual allele sums per population, pageable host memory -- is packed into tiled
+// bit-planes by a pool of host threads, slice by slice, straight into a ring of pinned staging
+// buffers; as soon as a slice is complete it goes H2D and, once landed, through the genotype
+// pass, while the threads are already packing the following slices.  Three stages overlap: pack
+// (host cores, reads 4x the bytes it writes) | PCIe copy | K1.
+struct I8Source {
+  const int8_t* const* gt;
+  const int64_t* row_stride;
+};
+
+static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8Source& src, int64_t n_sites,
+                                int64_t n_tiles, const sai_job* jobs, int32_t n_jobs, uint32_t* d_mask_u,
+                                uint32_t* d_mask_q, double* d_qval, int64_t stride) {
+  const size_t tile_bytes = (size_t)lay->pairs_per_site * kTile * 8;
+  const int64_t slice_tiles = std::max<int64_t>(1, (int64_t)((16ull << 20) / tile_bytes));
+  const int64_t n_slices = (n_tiles + slice_tiles - 1) / slice_tiles;
+  const int kRing = 4;
+  const size_t slot_bytes = (size_t)slice_tiles * tile_bytes;
+  if (e->ring_cap < slot_bytes * kRing) {
+    if (e->ring) SAI_CUDA_CHECK(cudaFreeHost(e->ring));
+    e->ring = nullptr;
+    e->ring_cap = 0;
+    SAI_CUDA_CHECK(cudaHostAlloc(&e->ring, slot_bytes * kRing, cudaHostAllocDefault));
+    e->ring_cap = slot_bytes * kRing;
+  }
+  while ((int64_t)e->ev_block.size() < kRing) {
+    cudaEvent_t ev;
+    SAI_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
+    e->ev_block.push_back(ev);
+  }
+  while ((int64_t)e->ev.size() < kRing) {
+    cudaEvent_t ev;
+    SAI_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->ev.push_back(ev);
+  }
+  int n_threads = e->host_threads > 0 ? e->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  // packing tasks: blocks of tiles, in slice order
+  const int64_t block_tiles = std::max<int64_t>(1, std::min<int64_t>(32, (slice_tiles + 2 * n_threads - 1) / (2 * n_threads)));
+  const int64_t blocks_per_slice = (slice_tiles + block_tiles - 1) / block_tiles;
+  auto blocks_of = [&](int64_t s) {
+    const int64_t tiles = std::min(slice_tiles, n_tiles - s * slice_tiles);
+    return (tiles + block_tiles - 1) / block_tiles;
+  };
+  const int64_t n_tasks = (n_slices - 1) * blocks_per_slice + blocks_of(n_slices - 1);
+  n_threads = (int)std::min<int64_t>(n_threads, n_tasks);
+  std::atomic<int64_t> next_task{0}, allowed{kRing};
+  std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[n_slices]);
+  for (int64_t s = 0; s < n_slices; ++s) done[s].store(0);
+  std::atomic<int> bad{0}, abort_flag{0};
+  std::mutex mu;
+  std::condition_variable cv;
+  uint8_t* ring = static_cast<uint8_t*>(e->ring);
+  auto worker = [&]() {
+    for (;;) {
+      const int64_t i = next_task.fetch_add(1);
+      if (i >= n_tasks) break;
+      const int64_t s = i / blocks_per_slice, b = i % blocks_per_slice;
+      if (s >= allowed.load(std::memory_order_acquire)) {  // the slice's ring slot is still on the wire
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return s < allowed.load(std::memory_order_acquire) || abort_flag.load(); });
+      }
+      if (abort_flag.load()) break;
+      const int64_t t0 = s * slice_tiles + b * block_tiles;
+      const int64_t t1 = std::min(std::min(n_tiles, (s + 1) * slice_tiles), t0 + block_tiles);
+      uint8_t* slot = ring + (size_t)(s % kRing) * slot_bytes;
+      bool oob = false;
+      for (int p = 0; p < lay->n_pops; ++p)
+        oob |= pack_tiles_i8(*lay, p, src.gt[p], n_sites, src.row_stride[p], t0, t1, s * slice_tiles, slot, 0);
+      if (oob) bad.store(1);
+      if (done[s].fetch_add(1, std::memory_order_acq_rel) + 1 == (int)blocks_of(s)) {
+        std::lock_guard<std::mutex> lk(mu);
+        cv.notify_all();
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int i = 0; i < n_threads; ++i) pool.emplace_back(worker);
+  int rc = SAI_OK;
+  auto fail = [&](int code) {
+    rc = code;
+    abort_flag.store(1);
+    std::lock_guard<std::mutex> lk(mu);
+    cv.notify_all();
+  };
+#define SAI_I8_CUDA(expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+      fail(SAI_E_CUDA);                                                                        \
+    }                                                                                          \
+  } while (0)
+  for (int64_t s = 0; s < n_slices && rc == SAI_OK; ++s) {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return done[s].load(std::memory_order_acquire) == (int)blocks_of(s); });
+    }
+    if (bad.load()) {
+      fail(SAI_E_DOMAIN);
+      break;
+    }
+    const int64_t t0 = s * slice_tiles, t1 = std::min(n_tiles, t0 + slice_tiles);
+    const int slot = (int)(s % kRing);
+    SAI_I8_CUDA(cudaMemcpyAsync(static_cast<char*>(e->packed.p) + (size_t)t0 * tile_bytes, ring + (size_t)slot * slot_bytes,
+                                (size_t)(t1 - t0) * tile_bytes, cudaMemcpyHostToDevice, e->s_copy));
+    SAI_I8_CUDA(cudaEventRecord(e->ev_block[slot], e->s_copy));
+    SAI_I8_CUDA(cudaEventRecord(e->ev[slot], e->s_copy));
+    SAI_I8_CUDA(cudaStreamWaitEvent(e->s_comp, e->ev[slot], 0));
+    if (rc == SAI_OK)
+      if (int k = sai_site_flags(lay, e->packed.p, t0, t1 - t0, n_tiles, jobs, n_jobs, d_mask_u, d_mask_q, d_qval,
+                                 stride, nullptr, nullptr, 0, 0, e->s_comp))
+        fail(k);
+    // the slot may be refilled once its copy has left the host (the threads are meanwhile packing
+    // the next kRing - 1 slices; the host sleeps in this wait)
+    SAI_I8_CUDA(cudaEventSynchronize(e->ev_block[slot]));
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      allowed.store(s + 1 + kRing, std::memory_order_release);
+      cv.notify_all();
+    }
+  }
+#undef SAI_I8_CUDA
+  for (auto& t : pool) t.join();
+  if (rc == SAI_E_DOMAIN || (rc == SAI_OK && bad.load())) {
+    set_error("a genotype value does not fit the bit-planes of its population");
+    return SAI_E_DOMAIN;
+  }
+  return rc;
+}
+
+// Shared body of the host entry points: `packed` (dense tiles), the zero-suppressed stream +
+// its tile directory when `zt_stream` is given, or int8 matrices (`i8`).
 static int score_host_impl(sai_engine* e, const sai_layout* lay, const uint8_t* packed,
-                           const uint8_t* zt_stream, const uint64_t* zt_off, const int32_t* pos,
+                           const uint8_t* zt_stream, const uint64_t* zt_off, const I8Source* i8, const int32_t* pos,
                            int64_t n_sites, const int64_t* win_start, const int64_t* win_end,
                            int64_t n_windows, const sai_job* jobs, int32_t n_jobs, sai_host_results* out) {
   SAI_REQUIRE(e, "NULL engine");
   if (int rc = validate_layout(lay)) return rc;
   if (int rc = validate_jobs(lay, jobs, n_jobs)) return rc;
   SAI_REQUIRE(n_sites >= 0 && n_windows >= 0, "negative size");
-  SAI_REQUIRE(n_sites == 0 || ((packed || (zt_stream && zt_off)) && pos), "NULL input");
+  SAI_REQUIRE(n_sites == 0 || ((packed || (zt_stream && zt_off) || i8) && pos), "NULL input");
   SAI_REQUIRE(n_windows == 0 || (win_start && win_end), "NULL windows");
   if (int rc = check_results(out)) return rc;
   SAI_CUDA_CHECK(cudaSetDevice(e->device));
@@ -196,6 +340,7 @@ static int score_host_impl(sai_engine* e, const sai_layout* lay, const uint8_t* 
   e->n_sites = n_sites;
   e->W = W;
   e->n_jobs = n_jobs;
+  e->lay = *lay;
   for (int j = 0; j < n_jobs; ++j) e->jobs[j] = jobs[j];
 
   uint32_t* d_mask_u = static_cast<uint32_t*>(e->mask.p);
@@ -214,6 +359,18 @@ static int score_host_impl(sai_engine* e, const sai_layout* lay, const uint8_t* 
   if (zt)
     SAI_CUDA_CHECK(cudaMemcpyAsync(e->ztoff.p, zt_off, sizeof(uint64_t) * (size_t)(n_tiles + 1),
                                    cudaMemcpyHostToDevice, e->s_copy));
+  if (i8 && n_tiles > 0) {
+    if (int rc = stream_tiles_from_i8(e, lay, *i8, n_sites, n_tiles, jobs, n_jobs, d_mask_u, d_mask_q, d_qval, stride))
+      return rc;
+    while (e->ev.empty()) {
+      cudaEvent_t ev;
+      SAI_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->ev.push_back(ev);
+    }
+    SAI_CUDA_CHECK(cudaEventRecord(e->ev[0], e->s_copy));  // positions / windows went on the copy stream
+    SAI_CUDA_CHECK(cudaStreamWaitEvent(e->s_comp, e->ev[0], 0));
+    return run_windows(e, out);
+  }
   // sliced H2D of the tiles (about 32 MB on the wire per slice); per slice, as soon as it has
   // landed: [zt: rebuild the dense tiles,] then K1
   const size_t tile_bytes = (size_t)lay->pairs_per_site * kTile * 8;
@@ -272,7 +429,7 @@ int sai_engine_score_host(sai_engine* e, const sai_layout* lay, const uint8_t* p
                           const int64_t* win_end, int64_t n_windows, const sai_job* jobs,
                           int32_t n_jobs, sai_host_results* out) {
   SAI_REQUIRE(n_sites <= 0 || packed, "NULL input");
-  return score_host_impl(e, lay, packed, nullptr, nullptr, pos, n_sites, win_start, win_end, n_windows, jobs,
+  return score_host_impl(e, lay, packed, nullptr, nullptr, nullptr, pos, n_sites, win_start, win_end, n_windows, jobs,
                          n_jobs, out);
 }
 
@@ -281,8 +438,29 @@ int sai_engine_score_host_zt(sai_engine* e, const sai_layout* lay, const uint8_t
                              const int64_t* win_start, const int64_t* win_end, int64_t n_windows,
                              const sai_job* jobs, int32_t n_jobs, sai_host_results* out) {
   SAI_REQUIRE(n_sites <= 0 || (zt_stream && zt_tile_off), "NULL input");
-  return score_host_impl(e, lay, nullptr, zt_stream, zt_tile_off, pos, n_sites, win_start, win_end, n_windows,
+  return score_host_impl(e, lay, nullptr, zt_stream, zt_tile_off, nullptr, pos, n_sites, win_start, win_end, n_windows,
                          jobs, n_jobs, out);
+}
+
+int sai_engine_score_host_i8(sai_engine* e, const sai_layout* lay, const int8_t* const* gt,
+                             const int64_t* row_stride, const int32_t* pos, int64_t n_sites,
+                             const int64_t* win_start, const int64_t* win_end, int64_t n_windows,
+                             const sai_job* jobs, int32_t n_jobs, sai_host_results* out) {
+  SAI_REQUIRE(lay && gt && row_stride, "NULL input");
+  if (int rc = validate_layout(lay)) return rc;
+  for (int p = 0; p < lay->n_pops; ++p) {
+    SAI_REQUIRE(n_sites <= 0 || gt[p], "NULL genotype matrix of population %d", p);
+    SAI_REQUIRE(row_stride[p] >= lay->pop[p].n_samples, "row_stride of population %d smaller than n_samples", p);
+  }
+  const I8Source src{gt, row_stride};
+  return score_host_impl(e, lay, nullptr, nullptr, nullptr, &src, pos, n_sites, win_start, win_end, n_windows, jobs,
+                         n_jobs, out);
+}
+
+int sai_engine_set_host_threads(sai_engine* e, int32_t n_threads) {
+  SAI_REQUIRE(e, "NULL engine");
+  e->host_threads = n_threads > 0 ? n_threads : 0;
+  return SAI_OK;
 }
 
 int sai_engine_pattern_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, int32_t tgt_pop,
@@ -374,6 +552,29 @@ int sai_engine_dd_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, in
   }
   SAI_REQUIRE(h_err == 0, "a missing source call has no entry in the negative-value table");
   return SAI_OK;
+}
+
+int sai_engine_score_resident(sai_engine* e, const sai_job* jobs, int32_t n_jobs, sai_host_results* out) {
+  SAI_REQUIRE(e && e->n_jobs > 0, "no previous sai_engine_score_host call");
+  const sai_layout* lay = &e->lay;
+  if (int rc = validate_jobs(lay, jobs, n_jobs)) return rc;
+  if (int rc = check_results(out)) return rc;
+  SAI_CUDA_CHECK(cudaSetDevice(e->device));
+  const int64_t n_tiles = sai_num_tiles(e->n_sites);
+  const int64_t stride = n_tiles * kTile;
+  const ResLayout rl = res_layout(e->W, n_jobs);
+  if (int rc = grow(e->mask, sizeof(uint32_t) * 2 * (size_t)n_jobs * n_tiles + 256)) return rc;
+  if (int rc = grow(e->qval, sizeof(double) * (size_t)n_jobs * stride + 256)) return rc;
+  if (int rc = grow(e->res, rl.total + 256)) return rc;
+  e->n_jobs = n_jobs;
+  for (int j = 0; j < n_jobs; ++j) e->jobs[j] = jobs[j];
+  uint32_t* d_mask_u = static_cast<uint32_t*>(e->mask.p);
+  if (n_tiles > 0)
+    if (int rc = sai_site_flags(lay, e->packed.p, 0, n_tiles, n_tiles, jobs, n_jobs, d_mask_u,
+                                d_mask_u + (size_t)n_jobs * n_tiles, static_cast<double*>(e->qval.p), stride, nullptr,
+                                nullptr, 0, 0, e->s_comp))
+      return rc;
+  return run_windows(e, out);
 }
 
 int sai_engine_rescore_windows(sai_engine* e, sai_host_results* out) {

@@ -1,0 +1,218 @@
+// Host packer core: int8 per-individual allele sums -> tiled bit-planes (include/sai_b200.h),
+// the encoding that replaces the reference's int64 matrices (reshape_genotypes,
+// sai/utils/utils.py:405-410).  Plain C++ (compiled by g++, not nvcc) so that the x86 vector
+// paths can be selected at run time: AVX-512BW (64 individuals per instruction group), AVX2
+// (32) or a portable 64-bit multiply "movemask" (8).
+//
+// One call packs one population of a run of tiles.  A tile is 32 sites; per site the 32-individual
+// groups of the row are turned into B plane words (bit i of plane b = bit b of individual i's
+// code; a negative value = missing = all-ones code) and stored at the site's slot of each pair
+// row, 256 bytes apart -- the whole tile (pairs_per_site * 256 B, 20 KB for 2504 diploids) stays
+// in L1/L2 while its 32 input rows stream through.
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "host_pack.h"
+
+#if defined(__x86_64__) || defined(_M_X64)
+#include <immintrin.h>
+#define SAI_X86 1
+#endif
+
+namespace sai {
+
+namespace {
+
+constexpr int kTileSites = SAI_TILE_SITES;
+
+// Row packers: words[g * B + b] for g < n_groups; returns true when a called value exceeds the
+// planes (>= 2^B - 1).  `n` individuals; the last group is padded with the missing code.
+typedef bool (*row_fn)(const int8_t* row, int n, int n_groups, int B, uint32_t* words);
+
+bool row_portable(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
+  const uint64_t ones = 0x0101010101010101ull;
+  const int miss_code = (1 << B) - 1;
+  bool bad = false;
+  int8_t tail[32];
+  for (int g = 0; g < n_groups; ++g) {
+    const int i0 = g * 32, cnt = std::min(32, n - i0);
+    const int8_t* v = row + i0;
+    if (cnt < 32) {
+      memset(tail, 0xff, sizeof(tail));
+      memcpy(tail, row + i0, cnt);
+      v = tail;
+    }
+    uint32_t* plane = words + (size_t)g * B;
+    for (int b = 0; b < B; ++b) plane[b] = 0;
+    for (int q = 0; q < 4; ++q) {
+      uint64_t x;
+      memcpy(&x, v + 8 * q, 8);
+      const uint64_t negm = ((x >> 7) & ones) * 0xffull;  // 0xff in every negative byte
+      const uint64_t val = x & ~negm;
+      // a called value must be < miss_code: byte + (128 - miss_code) sets bit 7 otherwise
+      bad |= (((val + ones * (uint64_t)(128 - miss_code)) | val) & (ones << 7)) != 0;
+      const uint64_t code = val | (negm & (ones * (uint64_t)miss_code));
+      for (int b = 0; b < B; ++b)
+        plane[b] |= (uint32_t)((((code >> b) & ones) * 0x0102040810204080ull) >> 56) << (8 * q);
+    }
+  }
+  return bad;
+}
+
+#ifdef SAI_X86
+// SSE2 is part of x86-64: 16 individuals per instruction group, two per 32-individual group.
+// (The B200 boxes' virtual CPUs expose AVX but neither AVX2 nor AVX-512: this is their path.)
+bool row_sse2(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
+  const __m128i lim = _mm_set1_epi8((char)((1 << B) - 2));  // largest called value
+  __m128i bad = _mm_setzero_si128();
+  auto half = [&](__m128i v, uint32_t (&p)[4]) {
+    const uint32_t neg = (uint32_t)_mm_movemask_epi8(v);  // sign bits: missing calls
+    bad = _mm_or_si128(bad, _mm_cmpgt_epi8(v, lim));
+    p[0] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 7)) | neg;
+    p[1] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 6)) | neg;
+    if (B > 2) p[2] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 5)) | neg;
+    if (B > 3) p[3] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 4)) | neg;
+  };
+  const int full = n / 32;
+  for (int g = 0; g < full; ++g) {
+    uint32_t lo[4], hi[4];
+    half(_mm_loadu_si128((const __m128i*)(row + 32 * g)), lo);
+    half(_mm_loadu_si128((const __m128i*)(row + 32 * g + 16)), hi);
+    for (int b = 0; b < B; ++b) words[(size_t)g * B + b] = lo[b] | (hi[b] << 16);
+  }
+  if (full < n_groups) {
+    alignas(16) int8_t tail[32];
+    memset(tail, 0xff, sizeof(tail));
+    memcpy(tail, row + 32 * full, n - 32 * full);
+    uint32_t lo[4], hi[4];
+    half(_mm_load_si128((const __m128i*)tail), lo);
+    half(_mm_load_si128((const __m128i*)(tail + 16)), hi);
+    for (int b = 0; b < B; ++b) words[(size_t)full * B + b] = lo[b] | (hi[b] << 16);
+  }
+  return _mm_movemask_epi8(bad) != 0;
+}
+
+// (pragma rather than the function attribute: the lambdas inside must carry the target too)
+#pragma GCC push_options
+#pragma GCC target("avx2")
+bool row_avx2(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
+  const __m256i lim = _mm256_set1_epi8((char)((1 << B) - 2));  // largest called value
+  __m256i bad = _mm256_setzero_si256();
+  const int full = n / 32;
+  auto group = [&](__m256i v, uint32_t* plane) {
+    const uint32_t neg = (uint32_t)_mm256_movemask_epi8(v);  // sign bits: missing calls
+    bad = _mm256_or_si256(bad, _mm256_cmpgt_epi8(v, lim));
+    // bit b of every byte moved to the byte's sign position, then gathered
+    plane[0] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 7)) | neg;
+    plane[1] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6)) | neg;
+    if (B > 2) plane[2] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5)) | neg;
+    if (B > 3) plane[3] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 4)) | neg;
+  };
+  for (int g = 0; g < full; ++g) group(_mm256_loadu_si256((const __m256i*)(row + 32 * g)), words + (size_t)g * B);
+  if (full < n_groups) {
+    alignas(32) int8_t tail[32];
+    memset(tail, 0xff, sizeof(tail));
+    memcpy(tail, row + 32 * full, n - 32 * full);
+    group(_mm256_load_si256((const __m256i*)tail), words + (size_t)full * B);
+  }
+  return !_mm256_testz_si256(bad, bad);
+}
+
+#pragma GCC pop_options
+
+#pragma GCC push_options
+#pragma GCC target("avx512f,avx512bw")
+bool row_avx512(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
+  const __m512i lim = _mm512_set1_epi8((char)((1 << B) - 2));
+  __mmask64 bad = 0;
+  const __m512i bit0 = _mm512_set1_epi8(1), bit1 = _mm512_set1_epi8(2), bit2 = _mm512_set1_epi8(4), bit3 = _mm512_set1_epi8(8);
+  auto pair = [&](__m512i v, int g, int groups_here) {  // 64 individuals = groups g and g + 1
+    const uint64_t neg = _mm512_movepi8_mask(v);
+    bad |= _mm512_cmpgt_epi8_mask(v, lim);
+    uint64_t p[4];
+    p[0] = _mm512_test_epi8_mask(v, bit0) | neg;
+    p[1] = _mm512_test_epi8_mask(v, bit1) | neg;
+    if (B > 2) p[2] = _mm512_test_epi8_mask(v, bit2) | neg;
+    if (B > 3) p[3] = _mm512_test_epi8_mask(v, bit3) | neg;
+    for (int h = 0; h < groups_here; ++h)
+      for (int b = 0; b < B; ++b) words[(size_t)(g + h) * B + b] = (uint32_t)(p[b] >> (32 * h));
+  };
+  const int full = n / 64;
+  for (int k = 0; k < full; ++k) pair(_mm512_loadu_si512(row + 64 * k), 2 * k, 2);
+  const int rest = n - 64 * full;
+  if (rest > 0) {  // masked load; lanes beyond the row read as -1 (missing)
+    const __mmask64 m = rest >= 64 ? ~0ull : ((1ull << rest) - 1ull);
+    const __m512i v = _mm512_mask_loadu_epi8(_mm512_set1_epi8(-1), m, row + 64 * full);
+    pair(v, 2 * full, n_groups - 2 * full);
+  }
+  return bad != 0;
+}
+#pragma GCC pop_options
+#endif
+
+row_fn pick_row_fn() {
+#ifdef SAI_X86
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) return row_avx512;
+  if (__builtin_cpu_supports("avx2")) return row_avx2;
+  return row_sse2;
+#endif
+  return row_portable;
+}
+
+}  // namespace
+
+const char* pack_isa() {
+#ifdef SAI_X86
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) return "avx512bw";
+  if (__builtin_cpu_supports("avx2")) return "avx2";
+  return "sse2";
+#endif
+  return "portable";
+}
+
+bool pack_tiles_i8(const sai_layout& lay, int pop, const int8_t* gt, int64_t n_sites, int64_t row_stride,
+                   int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa) {
+  static const row_fn best = pick_row_fn();
+  row_fn fn = best;
+  if (isa == 1) fn = row_portable;
+#ifdef SAI_X86
+  if (isa == 2) fn = row_sse2;
+  if (isa == 3 && __builtin_cpu_supports("avx2")) fn = row_avx2;
+  if (isa == 4 && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) fn = row_avx512;
+#endif
+  const sai_pop_layout& L = lay.pop[pop];
+  const int B = L.bits;
+  const int n_words = L.n_groups * B;
+  const int n_pairs = L.n_pairs;
+  const size_t tile_bytes = (size_t)lay.pairs_per_site * kTileSites * 8;
+  // words of one row, padded to whole pairs (+1 zero word when odd)
+  uint32_t stack_words[1024];
+  uint32_t* words = n_words + 1 <= 1024 ? stack_words : new uint32_t[n_words + 1];
+  bool bad = false;
+  for (int64_t T = t0; T < t1; ++T) {
+    uint8_t* tile = packed_base + (size_t)(T - tile_base) * tile_bytes + (size_t)L.pair_off * kTileSites * 8;
+    for (int s = 0; s < kTileSites; ++s) {
+      const int64_t site = T * kTileSites + s;
+      if (site < n_sites) {
+        bad |= fn(gt + site * row_stride, L.n_samples, L.n_groups, B, words);
+      } else {
+        for (int w = 0; w < n_words; ++w) words[w] = 0xffffffffu;  // padding site: all missing
+      }
+      words[n_words] = 0u;
+      uint64_t* dst = reinterpret_cast<uint64_t*>(tile) + s;
+      for (int p = 0; p < n_pairs; ++p) {
+        uint64_t pair;
+        memcpy(&pair, words + 2 * p, 8);
+        dst[(size_t)p * kTileSites] = pair;
+      }
+    }
+  }
+  if (words != stack_words) delete[] words;
+  return bad;
+}
+
+}  // namespace sai

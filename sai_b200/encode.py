@@ -70,6 +70,23 @@ class PackedGenotypes:
         return int(self.packed.nbytes)
 
 
+@dataclass
+class MatrixGenotypes:
+    """Unpacked input of ``HostEngine.score_matrices``: one int8 matrix ``(sites, individuals)``
+    per population (row-strided views of one parsed matrix are fine) plus the layout the engine
+    packs them into on the fly."""
+
+    layout: "_cabi.Layout"
+    n_sites: int
+    pos: np.ndarray
+    mats: list
+    pop_names: list = field(default_factory=list)
+    neg_off: Optional[np.ndarray] = None
+    neg_site: Optional[np.ndarray] = None
+    neg_ind: Optional[np.ndarray] = None
+    neg_val: Optional[np.ndarray] = None
+
+
 def _as_i8(gt: np.ndarray) -> np.ndarray:
     gt = np.asarray(gt)
     if gt.ndim != 2:

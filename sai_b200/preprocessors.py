@@ -19,7 +19,7 @@ from typing import Any, Optional
 import numpy as np
 
 from . import _cabi
-from .encode import PopData, pack_populations
+from .encode import PopData
 from .scoring import HostEngine, dd_values, four_pop_values, make_job
 from .windows import chunk_windows, split_genome
 
@@ -176,12 +176,15 @@ def score_populations(
                 ploidy.append(ploidy_config.get_ploidy("outgroup", name))
         pos = everyone[0].POS
         windows = win_lists[0]
-        pg = pack_populations(mats, ploidy, pos, keep_negatives=dd)
         src_idx = [index[("src", s)] for s in src_comb]
+        pg = None
         for b0 in range(0, len(combos), _cabi.MAX_JOBS):
             batch = combos[b0 : b0 + _cabi.MAX_JOBS]
             jobs = [job_for(r, t, index[("ref", r)], index[("tgt", t)], src_idx) for r, t, _, _ in batch]
-            res = engine.score(pg, windows, jobs)
+            if pg is None:  # int8 matrices -> pack | copy | genotype pass, pipelined; ONE upload for all batches
+                res, pg = engine.score_matrices(mats, ploidy, pos, windows, jobs, keep_negatives=dd)
+            else:
+                res = engine.score_resident(jobs)
             for j, combo in enumerate(batch):
                 r, t, _, o = combo
                 four_vals, dd_vals = extras(
@@ -207,8 +210,9 @@ def score_populations(
         if out_pop is not None and four:
             ploidy.append(ploidy_config.get_ploidy("outgroup", out_pop))
             n_pack += 1
-        pg = pack_populations(rows[:n_pack], ploidy[:n_pack], pos, keep_negatives=dd)
-        res = engine.score(pg, windows, [job]) if (stats or four or dd) else None
+        res = pg = None
+        if stats or four or dd:
+            res, pg = engine.score_matrices(rows[:n_pack], ploidy[:n_pack], pos, windows, [job], keep_negatives=dd)
         four_vals, dd_vals = extras(pg, 0, 1, src_idx, 2 + n_src if (out_pop is not None and four) else -1,
                                     rows[0].shape[1], rows[1].shape[1], [rows[2 + k].shape[1] for k in range(n_src)])
         emit(combo, windows, pos, res, 0, four_vals, dd_vals)

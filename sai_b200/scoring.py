@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _cabi
-from .encode import PackedGenotypes, ZtGenotypes
+from .encode import MatrixGenotypes, PackedGenotypes, ZtGenotypes
 
 
 # --------------------------------------------------------------------------
@@ -156,7 +156,14 @@ class HostEngine:
         we = np.ascontiguousarray([w[1] for w in windows], dtype=np.int64)
         return self.score_arrays(pg, ws, we, jobs, cap_u, cap_q)
 
+    def set_host_threads(self, n_threads: int) -> None:
+        """Host threads of the int8 pipeline (``score_matrices``); <= 0: all cores."""
+        _cabi.check(_cabi.load().sai_engine_set_host_threads(self._handle(), int(n_threads)))
+
     def score_arrays(self, pg, ws, we, jobs, cap_u=None, cap_q=None) -> WindowResults:
+        """``pg``: ``PackedGenotypes`` (dense tiles), ``ZtGenotypes`` (zero-suppressed wire format)
+        or ``MatrixGenotypes`` (int8 matrices: packed by host threads slice by slice while earlier
+        slices are on the wire and in the genotype pass, ``sai_engine_score_host_i8``)."""
         lib = _cabi.load()
         J, W = len(jobs), int(ws.shape[0])
         self._last_W = W
@@ -187,6 +194,12 @@ class HostEngine:
         if isinstance(pg, ZtGenotypes):  # zero-suppressed wire format: expanded on the device
             entry = lib.sai_engine_score_host_zt
             tiles = (pg.stream.ctypes.data if pg.stream.size else None, pg.tile_off.ctypes.data)
+        elif isinstance(pg, MatrixGenotypes):  # int8 matrices: host pack | copy | genotype pass, pipelined
+            entry = lib.sai_engine_score_host_i8
+            n = len(pg.mats)
+            ptrs = (C.c_void_p * n)(*[m.ctypes.data for m in pg.mats])
+            strides = (C.c_int64 * n)(*[m.strides[0] if m.shape[0] > 1 else max(1, m.shape[1]) for m in pg.mats])
+            tiles = (ptrs, strides)
         else:
             entry = lib.sai_engine_score_host
             tiles = (pg.packed.ctypes.data if pg.packed.size else None,)
@@ -211,8 +224,67 @@ class HostEngine:
         _cabi.check(rc)
         return r
 
+    def score_resident(self, jobs, cap_u=None, cap_q=None) -> WindowResults:
+        """Another batch of jobs over the chunk of the last ``score*`` call, still resident on the
+        device (no upload): a population product of more than 8 combinations costs one transfer."""
+        lib = _cabi.load()
+        J, W = len(jobs), self._last_W
+        cap_u = max(1, 4 * W + 1024) if cap_u is None else int(cap_u)
+        cap_q = max(1, 4 * W + 1024) if cap_q is None else int(cap_q)
+        r = WindowResults(
+            nsnps=np.zeros((J, W), dtype=np.int32), u=np.zeros((J, W), dtype=np.int64),
+            q=np.full((J, W), np.nan, dtype=np.float64), q_cnt=np.zeros((J, W), dtype=np.int32),
+            u_start=np.zeros((J, W), dtype=np.int64), q_start=np.zeros((J, W), dtype=np.int64),
+            totals=np.zeros((J, 2), dtype=np.int64), u_cand=np.zeros((J, cap_u), dtype=np.int32),
+            q_cand=np.zeros((J, cap_q), dtype=np.int32),
+        )
 
-    def pattern_sums(self, pg: PackedGenotypes, ref_pop: int, tgt_pop: int, out_pop: int, src_pops: Sequence[int]) -> np.ndarray:
+        def c_results():
+            h = _cabi.HostResults()
+            for name in ("nsnps", "u", "q", "q_cnt", "u_start", "q_start", "totals", "u_cand", "q_cand"):
+                setattr(h, name, getattr(r, name).ctypes.data)
+            h.cap_u, h.cap_q = r.u_cand.shape[1], r.q_cand.shape[1]
+            return h
+
+        res = c_results()
+        rc = lib.sai_engine_score_resident(self._handle(), _job_array(jobs), J, C.byref(res))
+        if rc == _cabi.E_CAPACITY:
+            r.u_cand = np.zeros((J, max(1, int(r.totals[:, 0].max()))), dtype=np.int32)
+            r.q_cand = np.zeros((J, max(1, int(r.totals[:, 1].max()))), dtype=np.int32)
+            res = c_results()
+            rc = lib.sai_engine_rescore_windows(self._handle(), C.byref(res))
+        _cabi.check(rc)
+        return r
+
+    def score_matrices(self, mats, ploidy, pos, windows, jobs, bits=None, keep_negatives: bool = False,
+                       cap_u=None, cap_q=None):
+        """Scores int8 (or any integer) per-individual allele-sum matrices -- one per population,
+        all over ``pos`` -- without a separate packing pass.  Returns ``(results, genotypes)``;
+        ``genotypes`` (layout, negative-value table) is what ``pattern_sums`` / ``dd_sums`` take.
+        The bit-planes are chosen from the ploidies; data with larger values (the reference's
+        flipped-missing quirk, sai/utils/utils.py:555) is detected by the packer and the call is
+        repeated with planes chosen from the data."""
+        from .encode import MatrixGenotypes, _as_i8, bits_for, make_layout, negative_table
+
+        neg = negative_table(mats) if keep_negatives else (None, None, None, None)
+        m8 = [_as_i8(m) for m in mats]
+        pos = np.ascontiguousarray(np.asarray(pos), dtype=np.int32)
+        for m in m8:
+            if m.shape[0] != pos.shape[0]:
+                raise ValueError("every population must have one row per position")
+        ws = np.ascontiguousarray([w[0] for w in windows], dtype=np.int64)
+        we = np.ascontiguousarray([w[1] for w in windows], dtype=np.int64)
+        lay = make_layout([m.shape[1] for m in m8], ploidy, bits)
+        mg = MatrixGenotypes(lay, int(pos.shape[0]), pos, m8, [], *neg)
+        try:
+            return self.score_arrays(mg, ws, we, jobs, cap_u, cap_q), mg
+        except ValueError as e:
+            if bits is not None or "does not fit" not in str(e):
+                raise
+        mg.layout = make_layout([m.shape[1] for m in m8], ploidy, [bits_for(m, p) for m, p in zip(m8, ploidy)])
+        return self.score_arrays(mg, ws, we, jobs, cap_u, cap_q), mg
+
+    def pattern_sums(self, pg, ref_pop: int, tgt_pop: int, out_pop: int, src_pops: Sequence[int]) -> np.ndarray:
         """Site-pattern sums ``[n_src, W, 7]`` (abba, baba, baaa, abaa, bbaa,
         abba_d, baba_d) of the chunk scored by the last ``score`` call."""
         lib = _cabi.load()
@@ -224,7 +296,7 @@ class HostEngine:
         return sums
 
 
-    def dd_sums(self, pg: PackedGenotypes, ref_pop: int, tgt_pop: int, src_pops: Sequence[int]):
+    def dd_sums(self, pg, ref_pop: int, tgt_pop: int, src_pops: Sequence[int]):
         """Exact integer distance sums of the DD statistic for the chunk scored by
         the last ``score`` call: ``(ref_sum, tgt_sum)``, int64 ``[n_src, W, m_max]``
         with ``ref_sum[k, i, a] = sum_j sum_sites |src_a - ref_j|``

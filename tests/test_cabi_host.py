@@ -722,3 +722,39 @@ def test_empty_items_carry_the_outgroup(tmp_path):
     items = pre.run("9", 20001, 50000)  # no record in the region: no GPU work
     assert len(items) == 3 and [it["out_pop"] for it in items] == ["OUT"] * 3
     assert all(np.isnan(it["U"]) and np.isnan(it["fd"]) and it["nsnps"] == 0 for it in items)
+
+
+@pytest.mark.parametrize("bits, vmax", [(2, 2), (3, 6), (4, 14)])
+def test_packer_vector_paths_are_identical(bits, vmax):
+    """Portable, SSE2, AVX2 and AVX-512 row packers (whichever this CPU has) write the same bytes,
+    for full and partial 32-/64-individual groups, row-strided views and padding sites, and all
+    report an out-of-domain value."""
+    from sai_b200 import _cabi
+    from sai_b200.encode import make_layout
+
+    lib = _cabi.load()
+    assert lib.sai_pack_isa() in (b"avx512bw", b"avx2", b"sse2", b"portable")
+    rng = np.random.default_rng(bits)
+    n_ind = [1, 31, 32, 33, 63, 64, 65, 100, 257]
+    n_sites = 70
+    whole = rng.integers(0, vmax + 1, size=(n_sites, sum(n_ind) + 5)).astype(np.int8)
+    whole[rng.random(whole.shape) < 0.1] = -1
+    whole[rng.random(whole.shape) < 0.05] = -2
+    lay = make_layout(n_ind, [1] * len(n_ind), [bits] * len(n_ind))
+    nbytes = int(lib.sai_packed_bytes(C.byref(lay), n_sites))
+    outs = []
+    for isa in (1, 2, 3, 4, 0):
+        out = np.full(nbytes, 0xAB, dtype=np.uint8)
+        at = 0
+        for p, n in enumerate(n_ind):
+            view = whole[:, at : at + n]  # row stride = whole row
+            assert lib.sai_pack_i8_isa(C.byref(lay), p, view.ctypes.data, n_sites, whole.strides[0], out.ctypes.data, 3, isa) == 0
+            at += n
+        outs.append(out)
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+    bad = whole.copy()
+    bad[17, 70] = vmax + 1  # population 3 holds columns 64..96
+    for isa in (1, 2, 3, 4):
+        rc = lib.sai_pack_i8_isa(C.byref(lay), 3, bad[:, 64:].ctypes.data, n_sites, bad.strides[0], outs[0].ctypes.data, 1, isa)
+        assert rc == _cabi.E_DOMAIN, isa

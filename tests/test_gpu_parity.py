@@ -837,3 +837,80 @@ def test_full_size_properties():
         assert here >= 10
         checked += here
     assert checked >= 40
+
+
+# ---------------------------------------------------------------- int8 pipeline (pack | copy | genotype pass)
+def _same_results(a, b, n_jobs, n_windows):
+    assert np.array_equal(a.nsnps, b.nsnps) and np.array_equal(a.u, b.u)
+    assert np.array_equal(a.q, b.q, equal_nan=True) and np.array_equal(a.q_cnt, b.q_cnt)
+    for j in range(n_jobs):
+        for i in range(n_windows):
+            assert np.array_equal(a.u_positions(j, i), b.u_positions(j, i)), (j, i)
+            assert np.array_equal(a.q_positions(j, i), b.q_positions(j, i)), (j, i)
+
+
+@pytest.mark.parametrize("n_sites, n_ind, ploidy, threads", [
+    (1, [3, 2, 1], [2, 2, 2], 0), (33, [5, 40, 2], [2, 1, 2], 1), (5000, [257, 96, 3], [2, 1, 4], 3),
+    (70_000, [1500, 1000, 4], [2, 2, 2], 0),  # 45 MB of tiles: three slices of the staging ring and a partial one
+    (150_000, [1500, 1000, 4], [2, 2, 2], 5),  # more slices than ring slots: slots are reused
+])
+def test_int8_pipeline_matches_packed_engine(n_sites, n_ind, ploidy, threads, engine):
+    """sai_engine_score_host_i8 (int8 matrices packed by host threads into the pinned ring while
+    earlier slices are copied and flagged) == packing first and sai_engine_score_host, bit for bit;
+    a follow-up batch of jobs over the resident tiles (sai_engine_score_resident) likewise."""
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import make_job
+    from sai_b200.windows import split_genome
+
+    rng = np.random.default_rng(n_sites)
+    f = rng.beta(0.3, 1.5, size=n_sites)
+    whole = np.empty((n_sites, sum(n_ind)), dtype=np.int8)  # populations are column blocks of one matrix
+    at, mats = 0, []
+    for n, p in zip(n_ind, ploidy):
+        whole[:, at : at + n] = rng.binomial(p, f[:, None], size=(n_sites, n))
+        mats.append(whole[:, at : at + n])
+        at += n
+    whole[rng.random(whole.shape) < 0.01] = -1
+    mats[2][rng.random(n_sites) < 0.3] = ploidy[2]
+    pos = np.cumsum(rng.integers(1, 80, size=n_sites)).astype(np.int32)
+    wins = split_genome([int(pos[0]), int(pos[-1])], 50_000, 25_000)
+    jobs = [make_job(0, 1, [2], True, u=dict(w=0.4, x=0.1, y_list=[(">=", 0.5)]), q=dict(w=0.4, quantile=0.9, y_list=[(">=", 0.5)])),
+            make_job(1, 0, [2], False, u=dict(w=0.6, x=0.0, y_list=[("=", 1.0)]), q=dict(w=0.6, quantile=0.5, y_list=[("=", 1.0)]))]
+    more = [make_job(0, 1, [2], False, u=dict(w=0.2, x=0.3, y_list=[("=", 1.0)]), q=dict(w=0.2, quantile=0.95, y_list=[("=", 1.0)]))]
+    cap = dict(cap_u=1 << 20, cap_q=1 << 20)
+    pg = pack_populations(mats, ploidy, pos)
+    want = engine.score(pg, wins, jobs, **cap)
+    want_more = engine.score(pg, wins, more, **cap)
+    engine.set_host_threads(threads)
+    got, mg = engine.score_matrices(mats, ploidy, pos, wins, jobs, **cap)
+    got_more = engine.score_resident(more, **cap)
+    engine.set_host_threads(0)
+    assert [mg.layout.pop[i].bits for i in range(3)] == [pg.layout.pop[i].bits for i in range(3)]
+    _same_results(got, want, len(jobs), len(wins))
+    _same_results(got_more, want_more, 1, len(wins))
+    assert n_sites < 100 or int(want.u.sum()) > 0
+
+
+def test_int8_pipeline_widens_the_planes_when_the_data_needs_it(engine):
+    """Values above the ploidy (the reference's flipped-missing quirk, utils.py:555): the packer
+    reports them and score_matrices repeats the call with planes chosen from the data."""
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import make_job
+    from sai_b200.windows import split_genome
+
+    rng = np.random.default_rng(5)
+    n_sites = 4000
+    mats = [rng.integers(0, 3, size=(n_sites, n)).astype(np.int8) for n in (40, 30, 2)]
+    mats[1][rng.random(mats[1].shape) < 0.01] = 4  # diploid individual with two flipped missing alleles
+    mats[0][rng.random(mats[0].shape) < 0.05] = -1
+    pos = np.arange(1, n_sites + 1, dtype=np.int32) * 13
+    wins = split_genome([int(pos[0]), int(pos[-1])], 10_000, 5_000)
+    job = make_job(0, 1, [2], False, u=dict(w=0.7, x=0.3, y_list=[(">=", 0.5)]), q=dict(w=0.7, quantile=0.9, y_list=[(">=", 0.5)]))
+    pg = pack_populations(mats, [2, 2, 2], pos)
+    assert pg.layout.pop[1].bits == 3
+    want = engine.score(pg, wins, [job])
+    got, mg = engine.score_matrices(mats, [2, 2, 2], pos, wins, [job])
+    assert mg.layout.pop[1].bits == 3
+    _same_results(got, want, 1, len(wins))
+    with pytest.raises(ValueError, match="does not fit"):
+        engine.score_matrices(mats, [2, 2, 2], pos, wins, [job], bits=[2, 2, 2])

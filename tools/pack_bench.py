@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Host packer throughput (int8 allele sums -> tiled bit-planes) by thread count and vector path.
+
+    python tools/pack_bench.py [--sites 1000000]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sai_b200 import _cabi  # noqa: E402
+from sai_b200.encode import make_layout  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sites", type=int, default=1_000_000)
+    a = ap.parse_args()
+    lib = _cabi.load()
+    S, n_ind = a.sites, [1500, 1000, 4]
+    rng = np.random.default_rng(0)
+    g = (rng.random((S, sum(n_ind)), dtype=np.float32) < 0.1).astype(np.int8)
+    lay = make_layout(n_ind, [2, 2, 2], [2, 2, 2])
+    out = np.zeros(int(lib.sai_packed_bytes(C.byref(lay), S)), dtype=np.uint8)
+    cols = np.cumsum([0] + n_ind)
+    res = {"isa_best": lib.sai_pack_isa().decode(), "cpus": os.cpu_count(), "sites": S, "int8_gb": g.nbytes / 1e9, "gbps": {}}
+    t0 = time.perf_counter(); g.copy(); res["numpy_copy_gbps_1thread"] = round(g.nbytes / (time.perf_counter() - t0) / 1e9, 2)
+    for isa, name in ((1, "portable"), (2, "sse2"), (0, "best")):
+        for th in (1, 2, 4, 8, 16, 32, 64):
+            if th > (os.cpu_count() or 1):
+                break
+            best = 1e9
+            for _ in range(2):
+                t0 = time.perf_counter()
+                for p in range(3):
+                    rc = lib.sai_pack_i8_isa(C.byref(lay), p, g.ctypes.data + int(cols[p]), S, g.strides[0], out.ctypes.data, th, isa)
+                    assert rc == 0
+                best = min(best, time.perf_counter() - t0)
+            res["gbps"][f"{name}_{th}"] = round(g.nbytes / best / 1e9, 2)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
