@@ -93,6 +93,7 @@ SYMBOLS = {
     "sai_num_tiles": (_I64, [_I64]),
     "sai_packed_bytes": (_U64, [_LAY, _I64]),
     "sai_pack_i8": (C.c_int, [_LAY, _I32, _P, _I64, _I64, _P, _I32]),
+    "sai_pack_i8_all": (C.c_int, [_LAY, _P, _P, _I64, _P, _I32]),
     "sai_pack_isa": (C.c_char_p, []),
     "sai_pack_i8_isa": (C.c_int, [_LAY, _I32, _P, _I64, _I64, _P, _I32, _I32]),
     "sai_unpack_i8": (C.c_int, [_LAY, _I32, _P, _I64, _I64, _I64, _P, _I64]),

@@ -180,6 +180,40 @@ int sai_pack_i8_isa(const sai_layout* lay, int32_t pop, const int8_t* gt, int64_
   return SAI_OK;
 }
 
+int sai_pack_i8_all(const sai_layout* lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
+                    uint8_t* packed, int32_t n_threads) {
+  if (int rc = validate_layout(lay)) return rc;
+  SAI_REQUIRE(gt && row_stride && packed && n_sites >= 0, "NULL argument");
+  for (int p = 0; p < lay->n_pops; ++p) {
+    SAI_REQUIRE(n_sites == 0 || gt[p], "NULL genotype matrix of population %d", p);
+    SAI_REQUIRE(row_stride[p] >= lay->pop[p].n_samples, "row_stride of population %d smaller than n_samples", p);
+  }
+  const int64_t n_tiles = sai_num_tiles(n_sites);
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, n_tiles / 8));
+  std::atomic<int> domain_err{0};
+  const int64_t block = 32;
+  std::atomic<int64_t> next{0};
+  auto work = [&]() {
+    bool bad = false;
+    for (int64_t t0 = next.fetch_add(block); t0 < n_tiles; t0 = next.fetch_add(block))
+      bad |= pack_tiles_i8_all(*lay, gt, row_stride, n_sites, t0, std::min(n_tiles, t0 + block), 0, packed, 0);
+    if (bad) domain_err.store(1, std::memory_order_relaxed);
+  };
+  if (n_threads <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_threads; ++i) th.emplace_back(work);
+    for (auto& t : th) t.join();
+  }
+  if (domain_err.load()) {
+    set_error("a genotype value does not fit the bit-planes of its population");
+    return SAI_E_DOMAIN;
+  }
+  return SAI_OK;
+}
+
 const char* sai_pack_isa(void) { return pack_isa(); }
 
 // Negative-value table of one int8 population matrix (DD, include/sai_b200.h "N4"): every entry v < 0 in

@@ -239,10 +239,7 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       const int64_t t0 = s * slice_tiles + b * block_tiles;
       const int64_t t1 = std::min(std::min(n_tiles, (s + 1) * slice_tiles), t0 + block_tiles);
       uint8_t* slot = ring + (size_t)(s % kRing) * slot_bytes;
-      bool oob = false;
-      for (int p = 0; p < lay->n_pops; ++p)
-        oob |= pack_tiles_i8(*lay, p, src.gt[p], n_sites, src.row_stride[p], t0, t1, s * slice_tiles, slot, 0);
-      if (oob) bad.store(1);
+      if (pack_tiles_i8_all(*lay, src.gt, src.row_stride, n_sites, t0, t1, s * slice_tiles, slot, 0)) bad.store(1);
       if (done[s].fetch_add(1, std::memory_order_acq_rel) + 1 == (int)blocks_of(s)) {
         std::lock_guard<std::mutex> lk(mu);
         cv.notify_all();

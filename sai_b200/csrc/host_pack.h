@@ -13,6 +13,10 @@ namespace sai {
 // an unavailable choice falls back to the best available).
 bool pack_tiles_i8(const sai_layout& lay, int pop, const int8_t* gt, int64_t n_sites, int64_t row_stride,
                    int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa);
+// All populations, site by site (one sequential stream when the populations are column blocks of
+// one matrix): the int8 pipeline's packer.
+bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
+                       int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa);
 const char* pack_isa();
 
 }  // namespace sai

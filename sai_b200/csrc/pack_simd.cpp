@@ -174,8 +174,8 @@ const char* pack_isa() {
   return "portable";
 }
 
-bool pack_tiles_i8(const sai_layout& lay, int pop, const int8_t* gt, int64_t n_sites, int64_t row_stride,
-                   int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa) {
+namespace {
+row_fn row_fn_for(int isa) {
   static const row_fn best = pick_row_fn();
   row_fn fn = best;
   if (isa == 1) fn = row_portable;
@@ -184,31 +184,90 @@ bool pack_tiles_i8(const sai_layout& lay, int pop, const int8_t* gt, int64_t n_s
   if (isa == 3 && __builtin_cpu_supports("avx2")) fn = row_avx2;
   if (isa == 4 && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) fn = row_avx512;
 #endif
+  return fn;
+}
+
+inline void prefetch_row(const int8_t* row, int n) {
+#ifdef SAI_X86
+  for (int i = 0; i < n; i += 64) _mm_prefetch(reinterpret_cast<const char*>(row + i), _MM_HINT_T0);
+#else
+  (void)row, (void)n;
+#endif
+}
+
+// the words of one site's row -> its slot (site s of the tile) of the population's pair rows
+inline void scatter_site(const uint32_t* words, int n_pairs, uint8_t* tile_pop, int s) {
+  uint64_t* dst = reinterpret_cast<uint64_t*>(tile_pop) + s;
+  for (int p = 0; p < n_pairs; ++p) {
+    uint64_t pair;
+    memcpy(&pair, words + 2 * p, 8);
+    dst[(size_t)p * kTileSites] = pair;
+  }
+}
+}  // namespace
+
+// All populations of tiles [t0, t1), site by site: when the populations are column blocks of one
+// row-major matrix (what a VCF parse leaves behind) the whole matrix is read as ONE sequential
+// stream, which is what the hardware prefetcher wants; the rows a few sites ahead are prefetched
+// explicitly as well.  Returns true when a value does not fit its population's bit-planes.
+bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
+                       int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa) {
+  const row_fn fn = row_fn_for(isa);
+  const size_t tile_bytes = (size_t)lay.pairs_per_site * kTileSites * 8;
+  int max_words = 0;
+  for (int p = 0; p < lay.n_pops; ++p) max_words = std::max(max_words, lay.pop[p].n_groups * lay.pop[p].bits);
+  uint32_t stack_words[1024];
+  uint32_t* words = max_words + 1 <= 1024 ? stack_words : new uint32_t[max_words + 1];
+  constexpr int kAhead = 3;  // sites
+  bool bad = false;
+  for (int64_t T = t0; T < t1; ++T) {
+    uint8_t* tile = packed_base + (size_t)(T - tile_base) * tile_bytes;
+    for (int s = 0; s < kTileSites; ++s) {
+      const int64_t site = T * kTileSites + s;
+      if (site + kAhead < n_sites)
+        for (int p = 0; p < lay.n_pops; ++p) prefetch_row(gt[p] + (site + kAhead) * row_stride[p], lay.pop[p].n_samples);
+      for (int p = 0; p < lay.n_pops; ++p) {
+        const sai_pop_layout& L = lay.pop[p];
+        const int n_words = L.n_groups * L.bits;
+        if (site < n_sites) {
+          bad |= fn(gt[p] + site * row_stride[p], L.n_samples, L.n_groups, L.bits, words);
+        } else {
+          for (int w = 0; w < n_words; ++w) words[w] = 0xffffffffu;  // padding site: all missing
+        }
+        words[n_words] = 0u;
+        scatter_site(words, L.n_pairs, tile + (size_t)L.pair_off * kTileSites * 8, s);
+      }
+    }
+  }
+  if (words != stack_words) delete[] words;
+  return bad;
+}
+
+// One population of tiles [t0, t1) (sai_pack_i8).
+bool pack_tiles_i8(const sai_layout& lay, int pop, const int8_t* gt, int64_t n_sites, int64_t row_stride,
+                   int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa) {
+  const row_fn fn = row_fn_for(isa);
   const sai_pop_layout& L = lay.pop[pop];
   const int B = L.bits;
   const int n_words = L.n_groups * B;
-  const int n_pairs = L.n_pairs;
   const size_t tile_bytes = (size_t)lay.pairs_per_site * kTileSites * 8;
   // words of one row, padded to whole pairs (+1 zero word when odd)
   uint32_t stack_words[1024];
   uint32_t* words = n_words + 1 <= 1024 ? stack_words : new uint32_t[n_words + 1];
+  constexpr int kAhead = 3;
   bool bad = false;
   for (int64_t T = t0; T < t1; ++T) {
     uint8_t* tile = packed_base + (size_t)(T - tile_base) * tile_bytes + (size_t)L.pair_off * kTileSites * 8;
     for (int s = 0; s < kTileSites; ++s) {
       const int64_t site = T * kTileSites + s;
+      if (site + kAhead < n_sites) prefetch_row(gt + (site + kAhead) * row_stride, L.n_samples);
       if (site < n_sites) {
         bad |= fn(gt + site * row_stride, L.n_samples, L.n_groups, B, words);
       } else {
         for (int w = 0; w < n_words; ++w) words[w] = 0xffffffffu;  // padding site: all missing
       }
       words[n_words] = 0u;
-      uint64_t* dst = reinterpret_cast<uint64_t*>(tile) + s;
-      for (int p = 0; p < n_pairs; ++p) {
-        uint64_t pair;
-        memcpy(&pair, words + 2 * p, 8);
-        dst[(size_t)p * kTileSites] = pair;
-      }
+      scatter_site(words, L.n_pairs, tile, s);
     }
   }
   if (words != stack_words) delete[] words;

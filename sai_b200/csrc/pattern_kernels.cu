@@ -20,6 +20,8 @@
 //   0 abba  1 baba  2 baaa  3 abaa  4 bbaa  5 abba_d  6 baba_d
 // where the _d sums use dnr = max(tgt, src) for both middle populations
 // (sai/stats/fd_statistic.py:78-81).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sai {
@@ -73,137 +75,144 @@ __device__ __forceinline__ double freq_of(const PatParams& P, int pop, int site)
 }
 
 constexpr int kLeaf = 128;   // numpy's PW_BLOCKSIZE
-constexpr int kMaxDepth = 40;
+constexpr int kMaxDepth = 32;  // recursion depth of pairwise_sum for n < 2^31 is <= 25
 
-// per-warp scratch: the seven products of one leaf's sites, and the recursion stack
-struct PatScratch {
-  double a[kPatSums][kLeaf];
-  double left[kMaxDepth][kPatSums];
-  int start[kMaxDepth], len[kMaxDepth], state[kMaxDepth];
+// ---- pass 1: the seven products of every site, once (a site lies in win_len / win_step windows:
+// computing them per window would repeat the four float64 divisions that many times) ----------
+// prod[(k * 7 + t) * stride + site], t in the order above; one thread per site, all sources.
+struct ProdParams {
+  PatParams P;
+  double* prod;
+  int64_t stride;
 };
 
-// numpy's pairwise_sum of the <= 128 values of every product held in S.a: lane (g, j) = (lane >> 3,
-// lane & 7) runs accumulator j of the sums g and g + 4; returns this lane's two sums
-__device__ __forceinline__ void leaf_sums(const PatScratch& S, int L, int lane, double& s0, double& s1) {
-  const int g = lane >> 3, j = lane & 7;
-  const int t0 = g, t1 = g + 4;  // t1 == 7 does not exist
+__global__ void __launch_bounds__(256) k_site_products(const __grid_constant__ ProdParams Q) {
+  const PatParams& P = Q.P;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < P.n_sites; s += (int64_t)gridDim.x * blockDim.x) {
+    const int site = (int)s;
+    const double fr = freq_of(P, P.ref_pop, site);
+    const double ft = freq_of(P, P.tgt_pop, site);
+    const double fo = P.out_pop >= 0 ? freq_of(P, P.out_pop, site) : 0.0;
+    const double ar = __dsub_rn(1.0, fr), at = __dsub_rn(1.0, ft), ao = __dsub_rn(1.0, fo);
+    for (int k = 0; k < P.n_src; ++k) {
+      const double fs = freq_of(P, P.src_pop[k], site);
+      const double as = __dsub_rn(1.0, fs);
+      // np.maximum propagates NaN
+      const double dn = (ft != ft || fs != fs) ? (ft + fs) : (ft > fs ? ft : fs);
+      const double adn = __dsub_rn(1.0, dn);
+      double* o = Q.prod + (size_t)k * kPatSums * Q.stride + s;
+      // product = 1; product *= f(ref); *= f(tgt); *= f(src); *= f(out)   (stat_utils.py:261-270)
+      o[0 * Q.stride] = __dmul_rn(__dmul_rn(__dmul_rn(ar, ft), fs), ao);   // abba
+      o[1 * Q.stride] = __dmul_rn(__dmul_rn(__dmul_rn(fr, at), fs), ao);   // baba
+      o[2 * Q.stride] = __dmul_rn(__dmul_rn(__dmul_rn(fr, at), as), ao);   // baaa
+      o[3 * Q.stride] = __dmul_rn(__dmul_rn(__dmul_rn(ar, ft), as), ao);   // abaa
+      o[4 * Q.stride] = __dmul_rn(__dmul_rn(__dmul_rn(fr, ft), as), ao);   // bbaa
+      o[5 * Q.stride] = __dmul_rn(__dmul_rn(__dmul_rn(ar, dn), dn), ao);   // abba_d
+      o[6 * Q.stride] = __dmul_rn(__dmul_rn(__dmul_rn(fr, adn), dn), ao);  // baba_d
+    }
+  }
+}
+
+// ---- pass 2: window sums in numpy's pairwise order ---------------------------------------------
+// One warp per (source population, window).  Lane (g, j) = (lane >> 3, lane & 7) runs accumulator
+// j of the sums g and g + 4 (sum 7 does not exist), straight from the product rows in L2; the
+// recursion above 128 elements is walked depth first with a per-lane stack (every lane follows
+// the same path, so no shared memory and no warp barrier is needed).
+__device__ __forceinline__ void leaf_sums(const double* __restrict__ a0, const double* __restrict__ a1, bool has1,
+                                          int L, int j, double& s0, double& s1) {
   if (L < 8) {
     double r0 = 0.0, r1 = 0.0;
     for (int i = 0; i < L; ++i) {
-      r0 = __dadd_rn(r0, S.a[t0][i]);
-      if (t1 < kPatSums) r1 = __dadd_rn(r1, S.a[t1][i]);
+      r0 = __dadd_rn(r0, __ldg(a0 + i));
+      if (has1) r1 = __dadd_rn(r1, __ldg(a1 + i));
     }
     s0 = r0, s1 = r1;
     return;
   }
   const int body = L - (L & 7);
-  double r0 = S.a[t0][j], r1 = t1 < kPatSums ? S.a[t1][j] : 0.0;
-  for (int i = 8 + j; i < body; i += 8) {
-    r0 = __dadd_rn(r0, S.a[t0][i]);
-    if (t1 < kPatSums) r1 = __dadd_rn(r1, S.a[t1][i]);
+  double r0 = __ldg(a0 + j), r1 = has1 ? __ldg(a1 + j) : 0.0;
+  int i = 8 + j;
+  for (; i + 24 < body; i += 32) {  // four independent loads per row in flight, added in order
+    double v0[4], v1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v0[u] = __ldg(a0 + i + 8 * u);
+      v1[u] = has1 ? __ldg(a1 + i + 8 * u) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      r0 = __dadd_rn(r0, v0[u]);
+      r1 = __dadd_rn(r1, v1[u]);
+    }
+  }
+  for (; i < body; i += 8) {
+    r0 = __dadd_rn(r0, __ldg(a0 + i));
+    if (has1) r1 = __dadd_rn(r1, __ldg(a1 + i));
   }
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) {  // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) inside every group of 8 lanes
     r0 = __dadd_rn(r0, __shfl_xor_sync(0xffffffffu, r0, o));
     r1 = __dadd_rn(r1, __shfl_xor_sync(0xffffffffu, r1, o));
   }
-  for (int i = body; i < L; ++i) {
-    r0 = __dadd_rn(r0, S.a[t0][i]);
-    if (t1 < kPatSums) r1 = __dadd_rn(r1, S.a[t1][i]);
+  for (int t = body; t < L; ++t) {
+    r0 = __dadd_rn(r0, __ldg(a0 + t));
+    if (has1) r1 = __dadd_rn(r1, __ldg(a1 + t));
   }
   s0 = r0, s1 = r1;
 }
 
 // grid: x = windows (one warp each, grid-stride), y = source population
-__global__ void __launch_bounds__(kPatWarps * 32) k_window_patterns(const __grid_constant__ PatParams P) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
+__global__ void __launch_bounds__(kPatWarps * 32) k_window_patterns(const __grid_constant__ ProdParams Q) {
+  const PatParams& P = Q.P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  PatScratch& S = reinterpret_cast<PatScratch*>(s_raw)[warp];
   const int k = blockIdx.y;
-  const int sp = P.src_pop[k];
-  const int g = lane >> 3;
+  const int g = lane >> 3, j = lane & 7;
+  const bool has1 = g + 4 < kPatSums;
+  const double* row0 = Q.prod + ((size_t)k * kPatSums + g) * Q.stride;
+  const double* row1 = Q.prod + ((size_t)k * kPatSums + (has1 ? g + 4 : g)) * Q.stride;
   for (int i = blockIdx.x * kPatWarps + warp; i < P.W; i += gridDim.x * kPatWarps) {
     const int lo = warp_lower_bound1(P.pos, P.n_sites, P.ws[i], lane);
     int hi = warp_lower_bound1(P.pos, P.n_sites, P.we[i] + 1, lane);
     if (hi < lo) hi = lo;
-    // the products of sites [start, start + L) into S.a
-    auto fill = [&](int start, int L) {
-      for (int e = lane; e < L; e += 32) {
-        const int s = start + e;
-        const double fr = freq_of(P, P.ref_pop, s);
-        const double ft = freq_of(P, P.tgt_pop, s);
-        const double fs = freq_of(P, sp, s);
-        const double fo = P.out_pop >= 0 ? freq_of(P, P.out_pop, s) : 0.0;
-        const double ar = __dsub_rn(1.0, fr), at = __dsub_rn(1.0, ft), as = __dsub_rn(1.0, fs),
-                     ao = __dsub_rn(1.0, fo);
-        // np.maximum propagates NaN
-        const double dn = (ft != ft || fs != fs) ? (ft + fs) : (ft > fs ? ft : fs);
-        const double adn = __dsub_rn(1.0, dn);
-        // product = 1; product *= f(ref); *= f(tgt); *= f(src); *= f(out)
-        S.a[0][e] = __dmul_rn(__dmul_rn(__dmul_rn(ar, ft), fs), ao);   // abba
-        S.a[1][e] = __dmul_rn(__dmul_rn(__dmul_rn(fr, at), fs), ao);   // baba
-        S.a[2][e] = __dmul_rn(__dmul_rn(__dmul_rn(fr, at), as), ao);   // baaa
-        S.a[3][e] = __dmul_rn(__dmul_rn(__dmul_rn(ar, ft), as), ao);   // abaa
-        S.a[4][e] = __dmul_rn(__dmul_rn(__dmul_rn(fr, ft), as), ao);   // bbaa
-        S.a[5][e] = __dmul_rn(__dmul_rn(__dmul_rn(ar, dn), dn), ao);   // abba_d
-        S.a[6][e] = __dmul_rn(__dmul_rn(__dmul_rn(fr, adn), dn), ao);  // baba_d
-      }
-      __syncwarp();
-    };
-    // numpy's recursion, depth first with an explicit stack; every lane follows the same path
+    // numpy's recursion, depth first; the stack is lane-uniform
+    int st_start[kMaxDepth], st_len[kMaxDepth], st_state[kMaxDepth];
+    double st_left0[kMaxDepth], st_left1[kMaxDepth];
     double ret0 = 0.0, ret1 = 0.0;  // this lane's sums g and g + 4 of the node just finished
-    int sp_ = 0;
-    if (lane == 0) S.start[0] = lo, S.len[0] = hi - lo, S.state[0] = 0;
-    sp_ = 1;
-    __syncwarp();
+    int sp_ = 1;
+    st_start[0] = lo, st_len[0] = hi - lo, st_state[0] = 0;
     while (sp_ > 0) {
       const int top = sp_ - 1;
-      const int start = S.start[top], len = S.len[top], state = S.state[top];
+      const int start = st_start[top], len = st_len[top];
       if (len <= kLeaf) {
-        fill(start, len);
-        leaf_sums(S, len, lane, ret0, ret1);
-        __syncwarp();
+        leaf_sums(row0 + start, row1 + start, has1, len, j, ret0, ret1);
         --sp_;
-        // hand the result to the ancestors
-        while (sp_ > 0) {
+        while (sp_ > 0) {  // hand the result to the ancestors
           const int par = sp_ - 1;
-          if (S.state[par] == 1) {  // the left half is done: keep it, descend into the right half
-            const int n2 = (S.len[par] / 2) - ((S.len[par] / 2) % 8);
-            __syncwarp();
-            if ((lane & 7) == 0) {
-              S.left[par][g] = ret0;
-              if (g + 4 < kPatSums) S.left[par][g + 4] = ret1;
-            }
-            if (lane == 0) {
-              S.state[par] = 2;
-              S.start[sp_] = S.start[par] + n2, S.len[sp_] = S.len[par] - n2, S.state[sp_] = 0;
-            }
+          if (st_state[par] == 1) {  // the left half is done: keep it, descend into the right half
+            const int n2 = (st_len[par] / 2) - ((st_len[par] / 2) % 8);
+            st_left0[par] = ret0, st_left1[par] = ret1;
+            st_state[par] = 2;
+            st_start[sp_] = st_start[par] + n2, st_len[sp_] = st_len[par] - n2, st_state[sp_] = 0;
             ++sp_;
-            __syncwarp();
             break;
           }
           // both halves are done: pairwise(left) + pairwise(right)
-          ret0 = __dadd_rn(S.left[par][g], ret0);
-          if (g + 4 < kPatSums) ret1 = __dadd_rn(S.left[par][g + 4], ret1);
+          ret0 = __dadd_rn(st_left0[par], ret0);
+          ret1 = __dadd_rn(st_left1[par], ret1);
           --sp_;
         }
-      } else if (state == 0) {  // descend into the left half
+      } else {  // state 0: descend into the left half
         const int n2 = (len / 2) - ((len / 2) % 8);
-        __syncwarp();
-        if (lane == 0) {
-          S.state[top] = 1;
-          S.start[sp_] = start, S.len[sp_] = n2, S.state[sp_] = 0;
-        }
+        st_state[top] = 1;
+        st_start[sp_] = start, st_len[sp_] = n2, st_state[sp_] = 0;
         ++sp_;
-        __syncwarp();
       }
     }
-    if ((lane & 7) == 0) {
+    if (j == 0) {
       double* out = P.sums + ((size_t)k * P.W + i) * kPatSums;
       out[g] = hi > lo ? ret0 : 0.0;
-      if (g + 4 < kPatSums) out[g + 4] = hi > lo ? ret1 : 0.0;
+      if (has1) out[g + 4] = hi > lo ? ret1 : 0.0;
     }
-    __syncwarp();
   }
 }
 
@@ -246,12 +255,26 @@ extern "C" int sai_window_patterns(const sai_layout* lay, const int32_t* d_pos, 
   for (int p = 0; p < lay->n_pops; ++p) P.ploidy[p] = lay->pop[p].ploidy;
   P.sums = d_sums;
   if (n_windows == 0) return SAI_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // scratch for the per-site products: stream-ordered allocation, freed after the window pass
+  const int64_t stride = (n_sites + 31) / 32 * 32;
+  ProdParams Q{};
+  Q.P = P;
+  Q.stride = stride;
+  void* scratch = nullptr;
+  SAI_CUDA_CHECK(cudaMallocAsync(&scratch, sizeof(double) * kPatSums * (size_t)n_src * (size_t)std::max<int64_t>(stride, 32), st));
+  Q.prod = static_cast<double*>(scratch);
+  if (n_sites > 0) {
+    const int64_t blocks = (n_sites + 255) / 256;
+    const int64_t capb = (int64_t)sm_count() * 16;
+    k_site_products<<<(unsigned)(blocks < capb ? blocks : capb), 256, 0, st>>>(Q);
+    SAI_CUDA_CHECK(cudaGetLastError());
+  }
   const int64_t want = (n_windows + kPatWarps - 1) / kPatWarps;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t cap = (int64_t)sm_count() * 16;
   const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_src);
-  const size_t smem = sizeof(PatScratch) * kPatWarps;
-  SAI_CUDA_CHECK(cudaFuncSetAttribute(k_window_patterns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_window_patterns<<<grid, kPatWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  k_window_patterns<<<grid, kPatWarps * 32, 0, st>>>(Q);
   SAI_CUDA_CHECK(cudaGetLastError());
+  SAI_CUDA_CHECK(cudaFreeAsync(scratch, st));
   return SAI_OK;
 }

@@ -132,13 +132,9 @@ def pack_populations(
         out = np.empty(max(nbytes, 1), dtype=np.uint8)
     elif out.nbytes < nbytes or out.dtype != np.uint8:
         raise ValueError("output buffer too small")
-    for i, m in enumerate(mats):
-        _cabi.check(
-            lib.sai_pack_i8(
-                C.byref(lay), i, m.ctypes.data, n_sites, m.strides[0] if n_sites > 1 else m.shape[1], out.ctypes.data,
-                n_threads
-            )
-        )
+    ptrs = (C.c_void_p * len(mats))(*[m.ctypes.data for m in mats])
+    strides = (C.c_int64 * len(mats))(*[m.strides[0] if n_sites > 1 else max(1, m.shape[1]) for m in mats])
+    _cabi.check(lib.sai_pack_i8_all(C.byref(lay), ptrs, strides, n_sites, out.ctypes.data, n_threads))
     return PackedGenotypes(lay, n_sites, pos, out[:nbytes] if nbytes else out[:0], list(pop_names or []), *neg)
 
 

@@ -42,6 +42,17 @@ def main():
                     assert rc == 0
                 best = min(best, time.perf_counter() - t0)
             res["gbps"][f"{name}_{th}"] = round(g.nbytes / best / 1e9, 2)
+    ptrs = (C.c_void_p * 3)(*[g.ctypes.data + int(cols[p]) for p in range(3)])
+    strides = (C.c_int64 * 3)(*[g.strides[0]] * 3)
+    for th in (1, 2, 4, 8, 16, 32, 64):
+        if th > (os.cpu_count() or 1):
+            break
+        best = 1e9
+        for _ in range(2):
+            t0 = time.perf_counter()
+            assert lib.sai_pack_i8_all(C.byref(lay), ptrs, strides, S, out.ctypes.data, th) == 0
+            best = min(best, time.perf_counter() - t0)
+        res["gbps"][f"all_pops_{th}"] = round(g.nbytes / best / 1e9, 2)
     print(json.dumps(res))
 
 
