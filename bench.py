@@ -581,7 +581,9 @@ def main():
     if Ke > 0:
         from sai_b200.encode import MatrixGenotypes, compress, pack_populations
 
-        host_threads = max(1, (os.cpu_count() or 1) // world)
+        # this rank's share of the host cores; with several ranks one core per rank is left to the thread
+        # that feeds the copy engine (the 8-GPU boxes of this pool have 4 vCPUs per GPU)
+        host_threads = max(1, (os.cpu_count() or 1) // world - (1 if world > 1 else 0))
         t0 = time.perf_counter()
         h_i8 = device_unpack_i8(lay, d_packed, S)  # [S, 2504] int8, pageable (synthetic-data preparation, untimed)
         t_unpack = time.perf_counter() - t0
@@ -739,6 +741,9 @@ def main():
             },
             "cpu_baseline": cpu,
             "e2e": e2e,
+            # the same record under the name VERDICT r1 asked for: e2e IS the from-int8 path now
+            "e2e_from_int8": None if e2e is None else {k: e2e[k] for k in (
+                "value", "unit", "ms_per_step", "pack_alone_ms", "wire_alone_ms", "pipeline_vs_slowest_stage", "host_threads")},
             "strong": strong,
             "gpu_launches": 2 * K,
             "clocks": clocks.summary(),

@@ -18,11 +18,14 @@
 // with c_u the number of individuals holding the called value u:
 //   k_site_hist   one genotype pass over ref and tgt -> c_u per site (bit-plane
 //                 match masks + POPC; lane == site as in k_site)
-//   k_window_dd   one warp per (source population, window): lanes stride over the
-//                 window's sites (called part from c_u and the source
-//                 individual's bit-plane code), then over the window's entries of
-//                 the negative-value table (the bit-planes keep a single
-//                 "missing" code; the table restores the raw values).
+//   k_site_dd     per site and source individual the two distances sum_j |src_a - ref_j|,
+//                 sum_j |src_a - tgt_j| (called part from c_u, missing calls from the
+//                 negative-value table: the bit-planes keep a single "missing" code, the table
+//                 restores the raw values) -- once per site, not once per overlapping window
+//   k_window_dd   one warp per (source population, window): exact int64 sums of those
+//                 per-site integers over the window's site range.
+#include <algorithm>
+
 #include "common.cuh"
 #include "popcount.cuh"
 
@@ -30,9 +33,7 @@ namespace sai {
 
 constexpr int kHistWarps = 8;
 constexpr int kDdWarps = 8;
-constexpr int kDdChunkMax = 8; // source individuals per pass: 1, 2, 4 or 8 (all divide 32: one group per chunk)
 constexpr int kMaxCodes = 15;  // called values of a 4-plane population
-constexpr int kDdUnroll = 2;   // table entries per lane and trip in k_window_dd
 
 struct HistParams {
   const uint2* packed;
@@ -152,6 +153,7 @@ struct DdParams {
   int32_t pairs_per_site;
   const int32_t* pos;
   int32_t n_sites;
+  int64_t n_tiles;
   const int64_t* ws;
   const int64_t* we;
   int32_t W;
@@ -160,9 +162,11 @@ struct DdParams {
   DdPop ref, tgt;
   int32_t n_src;
   DdPop src[SAI_MAX_SRC];
+  int32_t slot0[SAI_MAX_SRC];  // first row pair of source population k in `dist`
   const int32_t* neg_site;
   const int32_t* neg_ind;
   const int32_t* neg_val;
+  int32_t* dist;       // [slot][2][stride]: per site, sum_j |src_a - ref_j| and sum_j |src_a - tgt_j|
   long long* ref_sum;  // [n_src][W][m_max]
   long long* tgt_sum;
   int32_t m_max;
@@ -191,190 +195,155 @@ __device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ 
   return lo;
 }
 
-// sum_u c_u |s - u| over the called values of population `pp` at `site` (s may be negative)
-__device__ __forceinline__ long long called_distance(const DdParams& P, const DdPop& pp, int site, int s) {
-  const int32_t* h = P.hist + (size_t)pp.code_base * P.stride + site;
-  const int n_called = (1 << pp.bits) - 1;
-  long long d = 0;
-  for (int u = 0; u < n_called; ++u) {
-    const int diff = s - u;
-    d += (long long)__ldg(h + (size_t)u * P.stride) * (diff < 0 ? -diff : diff);
-  }
-  return d;
-}
-
-// raw value of a missing call: entry (site, ind) of the population's table slice
-__device__ __forceinline__ bool raw_lookup(const DdParams& P, const DdPop& pp, int site, int ind, int& raw) {
-  int64_t lo = pp.neg_lo, hi = pp.neg_hi;
+// first entry of [lo, hi) whose site is >= key (per-lane binary search inside a tile's short run)
+__device__ __forceinline__ int64_t lane_lower_bound(const int32_t* __restrict__ site, int64_t lo, int64_t hi, int key) {
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
-    const int s = __ldg(P.neg_site + mid);
-    if (s < site || (s == site && __ldg(P.neg_ind + mid) < ind))
-      lo = mid + 1;
-    else
-      hi = mid;
+    if (__ldg(site + mid) < key) lo = mid + 1; else hi = mid;
   }
-  if (lo < pp.neg_hi && __ldg(P.neg_site + lo) == site && __ldg(P.neg_ind + lo) == ind) {
-    raw = __ldg(P.neg_val + lo);
-    return true;
-  }
-  return false;
+  return lo;
 }
 
-// grid: x = windows (one warp each, grid-stride), y = source population
-template <int kDdChunk>
-__global__ void __launch_bounds__(kDdWarps * 32) k_window_dd(const __grid_constant__ DdParams P) {
+// ---- pass 2: per-site distances, once per site -------------------------------------------------
+// A site lies in win_len / win_step windows; its contribution
+//     dist[a][ref] = sum_j |src_a - ref_j| = sum_u c_u |s_a - u| + sum_{missing j} |s_a - raw_j|
+// (s_a: the source individual's called value, or its raw negative value from the table when its
+// call is missing) does not depend on the window, so it is computed once here and the window
+// kernel only adds integers.  One warp per tile, lane == site; the tile's run of table entries is
+// found with one cooperative search per population, the lane's own entries inside it by bisection.
+__global__ void __launch_bounds__(kDdWarps * 32) k_site_dd(const __grid_constant__ DdParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = blockIdx.y;
-  const DdPop& sp = P.src[k];
-  const int m = sp.n_samples;
-  const int s_missing = (1 << sp.bits) - 1;
-  for (int i = blockIdx.x * kDdWarps + warp; i < P.W; i += gridDim.x * kDdWarps) {
-    const int lo = (int)warp_lower_bound(P.pos, P.n_sites, P.ws[i], lane);
-    const int hi = (int)warp_lower_bound(P.pos, P.n_sites, P.we[i] + 1, lane);
-    // table entries of the window's sites (tables are sorted by site index)
-    int64_t e_lo[3], e_hi[3];
-    const DdPop* pops[3] = {&P.ref, &P.tgt, &sp};
+  for (int64_t T = (int64_t)blockIdx.x * kDdWarps + warp; T < P.n_tiles; T += (int64_t)gridDim.x * kDdWarps) {
+    const int site = (int)(T * kTile) + lane;
+    // this lane's entries of the ref / tgt tables
+    int64_t e_lo[2], e_hi[2];
+    int cu[2][kMaxCodes];
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const int64_t n = pops[t]->neg_hi - pops[t]->neg_lo;
-      const int32_t* base = P.neg_site + pops[t]->neg_lo;
-      e_lo[t] = pops[t]->neg_lo + (n > 0 ? warp_lower_bound(base, n, lo, lane) : 0);
-      e_hi[t] = pops[t]->neg_lo + (n > 0 ? warp_lower_bound(base, n, hi, lane) : 0);
+    for (int t = 0; t < 2; ++t) {
+      const DdPop& pp = t == 0 ? P.ref : P.tgt;
+      const int64_t n = pp.neg_hi - pp.neg_lo;
+      const int32_t* base = P.neg_site + pp.neg_lo;
+      const int64_t a = n > 0 ? warp_lower_bound(base, n, T * kTile, lane) : 0;
+      const int64_t b = n > 0 ? warp_lower_bound(base, n, T * kTile + kTile, lane) : 0;
+      e_lo[t] = pp.neg_lo + lane_lower_bound(base, a, b, site);
+      e_hi[t] = pp.neg_lo + lane_lower_bound(base, a, b, site + 1);
+      const int32_t* h = P.hist + (size_t)pp.code_base * P.stride + site;
+      const int n_called = (1 << pp.bits) - 1;
+#pragma unroll
+      for (int u = 0; u < kMaxCodes; ++u) cu[t][u] = u < n_called ? __ldg(h + (size_t)u * P.stride) : 0;
     }
-    for (int a0 = 0; a0 < m; a0 += kDdChunk) {
-      long long R[kDdChunk], T[kDdChunk];
+    // distance of a source value s to population t at this site
+    auto distance = [&](int t, int s) {
+      int d = 0;
 #pragma unroll
-      for (int j = 0; j < kDdChunk; ++j) R[j] = T[j] = 0;
-      // (1) called source value against the called ref / tgt values
-      for (int s = lo + lane; s < hi; s += 32) {
-        const uint2* col = P.packed + ((size_t)(s >> 5) * P.pairs_per_site + sp.pair_off) * kTile + (s & 31);
+      for (int u = 0; u < kMaxCodes; ++u) {
+        const int diff = s - u;
+        d += cu[t][u] * (diff < 0 ? -diff : diff);  // cu is 0 beyond the population's called values
+      }
+      for (int64_t e = e_lo[t]; e < e_hi[t]; ++e) {
+        const int diff = s - __ldg(P.neg_val + e);
+        d += diff < 0 ? -diff : diff;
+      }
+      return d;
+    };
+    for (int k = 0; k < P.n_src; ++k) {
+      const DdPop& sp = P.src[k];
+      const int s_missing = (1 << sp.bits) - 1;
+      const int64_t n = sp.neg_hi - sp.neg_lo;
+      const int32_t* base = P.neg_site + sp.neg_lo;
+      const int64_t ta = n > 0 ? warp_lower_bound(base, n, T * kTile, lane) : 0;
+      const int64_t tb = n > 0 ? warp_lower_bound(base, n, T * kTile + kTile, lane) : 0;
+      const int64_t s_lo = sp.neg_lo + lane_lower_bound(base, ta, tb, site);
+      const int64_t s_hi = sp.neg_lo + lane_lower_bound(base, ta, tb, site + 1);
+      const uint2* col = P.packed + ((size_t)T * P.pairs_per_site + sp.pair_off) * kTile + lane;
+      // called source values repeat (0, 1, 2 for two planes): their distances once per site
+      int dcalled[2][3];
+      if (sp.bits == 2) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int v = 0; v < 3; ++v) dcalled[t][v] = distance(t, v);
+      }
+      for (int a0 = 0; a0 < sp.n_samples; a0 += 32) {
         uint32_t w[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) w[b] = b < sp.bits ? plane_word(col, (a0 >> 5) * sp.bits + b) : 0u;
-        int code[kDdChunk];
-        bool any = false;
+        const int cnt = sp.n_samples - a0 < 32 ? sp.n_samples - a0 : 32;
+        for (int bit = 0; bit < cnt; ++bit) {
+          int sv = 0;
 #pragma unroll
-        for (int j = 0; j < kDdChunk; ++j) {
-          const int bit = (a0 + j) & 31;
-          int c = 0;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) c |= ((w[b] >> bit) & 1) << b;
-          code[j] = (a0 + j < m) ? c : s_missing;
-          any = any || code[j] != s_missing;
-        }
-        if (!any) continue;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const DdPop& pp = t == 0 ? P.ref : P.tgt;
-          const int32_t* h = P.hist + (size_t)pp.code_base * P.stride + s;
-          const int n_called = (1 << pp.bits) - 1;
-          if (sp.bits == 2) {
-            // distance of each of the three called source values to the population, once per site
-            long long D0 = 0, D1 = 0, D2 = 0;
-            for (int u = 0; u < n_called; ++u) {
-              const long long c = __ldg(h + (size_t)u * P.stride);
-              D0 += c * u;
-              D1 += c * (u > 1 ? u - 1 : 1 - u);
-              D2 += c * (u > 2 ? u - 2 : 2 - u);
+          for (int b = 0; b < 4; ++b) sv |= (int)((w[b] >> bit) & 1u) << b;
+          int dr, dt;
+          if (sv == s_missing) {  // the raw value of the missing source call is in the table
+            bool found = false;
+            for (int64_t e = s_lo; e < s_hi; ++e)
+              if (__ldg(P.neg_ind + e) == a0 + bit) {
+                sv = __ldg(P.neg_val + e);
+                found = true;
+              }
+            if (!found) {
+              sv = -1;
+              if (site < P.n_sites) *P.err = 1;
             }
-#pragma unroll
-            for (int j = 0; j < kDdChunk; ++j) {
-              const long long d = code[j] == 0 ? D0 : (code[j] == 1 ? D1 : (code[j] == 2 ? D2 : 0));
-              if (t == 0) R[j] += d; else T[j] += d;
-            }
+            dr = distance(0, sv);
+            dt = distance(1, sv);
+          } else if (sp.bits == 2) {
+            dr = sv == 0 ? dcalled[0][0] : (sv == 1 ? dcalled[0][1] : dcalled[0][2]);
+            dt = sv == 0 ? dcalled[1][0] : (sv == 1 ? dcalled[1][1] : dcalled[1][2]);
           } else {
-            for (int u = 0; u < n_called; ++u) {
-              const long long c = __ldg(h + (size_t)u * P.stride);
-#pragma unroll
-              for (int j = 0; j < kDdChunk; ++j) {
-                if (code[j] != s_missing) {
-                  const int diff = code[j] - u;
-                  const long long d = c * (diff < 0 ? -diff : diff);
-                  if (t == 0) R[j] += d; else T[j] += d;
-                }
-              }
-            }
+            dr = distance(0, sv);
+            dt = distance(1, sv);
           }
+          int32_t* o = P.dist + (size_t)(P.slot0[k] + a0 + bit) * 2 * P.stride + site;
+          o[0] = dr;
+          o[P.stride] = dt;
         }
       }
-      // (2) missing ref / tgt individuals against every source individual of the chunk.  kDdUnroll
-      //     table entries per lane and trip: the chain entry -> site -> source planes is two dependent
-      //     memory round trips, so independent chains are what hides the latency here.
+    }
+  }
+}
+
+// ---- pass 3: window sums of the per-site distances ----------------------------------------------
+// grid: x = windows (one warp each, grid-stride), y = source population.  Exact int64 sums.
+__global__ void __launch_bounds__(kDdWarps * 32) k_window_dd(const __grid_constant__ DdParams P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.y;
+  const int m = P.src[k].n_samples;
+  for (int i = blockIdx.x * kDdWarps + warp; i < P.W; i += gridDim.x * kDdWarps) {
+    const int lo = (int)warp_lower_bound(P.pos, P.n_sites, P.ws[i], lane);
+    int hi = (int)warp_lower_bound(P.pos, P.n_sites, P.we[i] + 1, lane);
+    if (hi < lo) hi = lo;
+    for (int a = 0; a < m; ++a) {
+      const int32_t* dr = P.dist + (size_t)(P.slot0[k] + a) * 2 * P.stride;
+      const int32_t* dt = dr + P.stride;
+      long long R = 0, Tt = 0;
+      int s = lo + lane;
+      for (; s + 96 < hi; s += 128) {  // four coalesced loads per row in flight
+        int r[4], t[4];
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        for (int64_t e0 = e_lo[t] + lane; e0 < e_hi[t]; e0 += 32 * kDdUnroll) {
-          int site[kDdUnroll], v[kDdUnroll];
-          bool live[kDdUnroll];
+        for (int u = 0; u < 4; ++u) {
+          r[u] = __ldg(dr + s + 32 * u);
+          t[u] = __ldg(dt + s + 32 * u);
+        }
 #pragma unroll
-          for (int u = 0; u < kDdUnroll; ++u) {
-            const int64_t e = e0 + 32 * u;
-            live[u] = e < e_hi[t];
-            site[u] = live[u] ? __ldg(P.neg_site + e) : 0;
-            v[u] = live[u] ? __ldg(P.neg_val + e) : 0;
-          }
-          uint32_t w[kDdUnroll][4];
-#pragma unroll
-          for (int u = 0; u < kDdUnroll; ++u) {
-            const uint2* col =
-                P.packed + ((size_t)(site[u] >> 5) * P.pairs_per_site + sp.pair_off) * kTile + (site[u] & 31);
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-              w[u][b] = (live[u] && b < sp.bits) ? plane_word(col, (a0 >> 5) * sp.bits + b) : 0u;
-          }
-#pragma unroll
-          for (int u = 0; u < kDdUnroll; ++u) {
-            if (!live[u]) continue;
-#pragma unroll
-            for (int j = 0; j < kDdChunk; ++j) {
-              if (a0 + j < m) {
-                const int bit = (a0 + j) & 31;
-                int sv = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) sv |= (int)((w[u][b] >> bit) & 1u) << b;
-                if (sv == s_missing) {  // the source call is missing too: its raw value is in the table
-                  sv = -1;
-                  if (!raw_lookup(P, sp, site[u], a0 + j, sv)) *P.err = 1;
-                }
-                const int diff = sv - v[u];
-                const long long d = diff < 0 ? -diff : diff;
-                if (t == 0) R[j] += d; else T[j] += d;
-              }
-            }
-          }
+        for (int u = 0; u < 4; ++u) {
+          R += r[u];
+          Tt += t[u];
         }
       }
-      // (3) missing source individuals against the called ref / tgt values
-      for (int64_t e = e_lo[2] + lane; e < e_hi[2]; e += 32) {
-        const int a = __ldg(P.neg_ind + e);
-        if (a < a0 || a >= a0 + kDdChunk) continue;
-        const int site = __ldg(P.neg_site + e), v = __ldg(P.neg_val + e);
-        const long long dr = called_distance(P, P.ref, site, v), dt = called_distance(P, P.tgt, site, v);
-#pragma unroll
-        for (int j = 0; j < kDdChunk; ++j) {
-          if (a == a0 + j) {
-            R[j] += dr;
-            T[j] += dt;
-          }
-        }
+      for (; s < hi; s += 32) {
+        R += __ldg(dr + s);
+        Tt += __ldg(dt + s);
       }
 #pragma unroll
-      for (int j = 0; j < kDdChunk; ++j) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          R[j] += __shfl_xor_sync(0xffffffffu, R[j], o);
-          T[j] += __shfl_xor_sync(0xffffffffu, T[j], o);
-        }
+      for (int o = 16; o > 0; o >>= 1) {
+        R += __shfl_xor_sync(0xffffffffu, R, o);
+        Tt += __shfl_xor_sync(0xffffffffu, Tt, o);
       }
       if (lane == 0) {
-        const size_t at = ((size_t)k * P.W + i) * P.m_max + a0;
-#pragma unroll
-        for (int j = 0; j < kDdChunk; ++j) {
-          if (a0 + j < m) {
-            P.ref_sum[at + j] = R[j];
-            P.tgt_sum[at + j] = T[j];
-          }
-        }
+        const size_t at = ((size_t)k * P.W + i) * P.m_max + a;
+        P.ref_sum[at] = R;
+        P.tgt_sum[at] = Tt;
       }
     }
   }
@@ -491,21 +460,29 @@ extern "C" int sai_window_dd(const sai_layout* lay, const void* d_packed, const 
   P.err = d_err;
   if (n_windows == 0) return SAI_OK;
   SAI_REQUIRE(n_sites == 0 || (d_packed && d_pos), "NULL input");
-  const int64_t want = (n_windows + kDdWarps - 1) / kDdWarps;
-  const int64_t cap = (int64_t)sm_count() * 8;
-  const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_src);
-  // chunk = the smallest of 1, 2, 4, 8 that holds the largest source population (less predicated-off work)
-  int m_top = 1;
-  for (int k = 0; k < n_src; ++k) m_top = m_top > P.src[k].n_samples ? m_top : P.src[k].n_samples;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (m_top <= 1)
-    k_window_dd<1><<<grid, kDdWarps * 32, 0, st>>>(P);
-  else if (m_top <= 2)
-    k_window_dd<2><<<grid, kDdWarps * 32, 0, st>>>(P);
-  else if (m_top <= 4)
-    k_window_dd<4><<<grid, kDdWarps * 32, 0, st>>>(P);
-  else
-    k_window_dd<kDdChunkMax><<<grid, kDdWarps * 32, 0, st>>>(P);
+  // per-site distances: one int32 pair (ref, tgt) per source individual and site (stream-ordered scratch)
+  int32_t slots = 0;
+  for (int k = 0; k < n_src; ++k) {
+    P.slot0[k] = slots;
+    slots += P.src[k].n_samples;
+  }
+  P.n_tiles = sai_num_tiles(n_sites);
+  SAI_REQUIRE(stride >= P.n_tiles * kTile, "stride smaller than the tiled site count");
+  void* scratch = nullptr;
+  SAI_CUDA_CHECK(cudaMallocAsync(&scratch, sizeof(int32_t) * 2 * (size_t)slots * (size_t)std::max<int64_t>(stride, 32), st));
+  P.dist = static_cast<int32_t*>(scratch);
+  if (P.n_tiles > 0) {
+    const int64_t wantt = (P.n_tiles + kDdWarps - 1) / kDdWarps;
+    const int64_t capt = (int64_t)sm_count() * 16;
+    k_site_dd<<<(unsigned)(wantt < capt ? wantt : capt), kDdWarps * 32, 0, st>>>(P);
+    SAI_CUDA_CHECK(cudaGetLastError());
+  }
+  const int64_t want = (n_windows + kDdWarps - 1) / kDdWarps;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_src);
+  k_window_dd<<<grid, kDdWarps * 32, 0, st>>>(P);
   SAI_CUDA_CHECK(cudaGetLastError());
+  SAI_CUDA_CHECK(cudaFreeAsync(scratch, st));
   return SAI_OK;
 }

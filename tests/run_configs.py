@@ -357,10 +357,47 @@ def config6(args):
                           oracle_windows_checked=checked)))
 
 
+# --------------------------------------------------------------------------
+def config7(args):
+    """The genotype pass on 3- and 4-plane populations (ploidy 4; B = 3 is what the encoder picks, B = 4 what
+    high ploidy or the flipped-missing quirk needs): counts against the oracle on a slice, time and bandwidth."""
+    S = args.sites or 1_000_000
+    n_ind = [1500, 1000, 4]
+    out = {"config": "wide-planes", "n_sites": S, "cases": []}
+    for bits in (2, 3, 4):
+        ploidy = 2 if bits == 2 else 4
+        lay = make_layout(n_ind, [ploidy] * 3, [bits] * 3)
+        d_packed = device_matrix(lay, S, [0, 1, 2], 20261018 + 7 + bits, 0.002)
+        pos = positions(S, 41.5, 7)
+        d_pos = torch.from_numpy(pos).cuda()
+        wins = split_genome([int(pos[0]), int(pos[-1])], 50_000, 10_000)
+        d_ws, d_we = dev_windows(wins)
+        u_kw = dict(w=0.01, x=0.5, y_list=[("=", 1.0)])
+        q_kw = dict(w=0.01, quantile=0.95, y_list=[("=", 1.0)])
+        job = make_job(0, 1, [2], True, u=u_kw, q=q_kw)
+        sc = DeviceScorer(lay, S, len(wins), 1, cap_u=1 << 20, cap_q=1 << 21)
+        t_counts = timed(lambda: sc.site_counts(d_packed))
+        t_fused = timed(lambda: sc.site_flags(d_packed, [job]))
+        sc.step(d_packed, d_pos, d_ws, d_we, [job])
+        res = sc.results()
+        sub_pos, mats = decode_slice(lay, d_packed, pos, 7000, 160)
+        num, called = sc.site_counts(d_packed)
+        num, called = num.cpu().numpy(), called.cpu().numpy()
+        for p in range(3):
+            en, ec = orc.site_counts(mats[p])
+            assert np.array_equal(num[p, 7000 * 32 : 7160 * 32], en) and np.array_equal(called[p, 7000 * 32 : 7160 * 32], ec)
+        checked = check_windows(res, 0, wins, sub_pos, mats, [ploidy] * 3, [2], u_kw, q_kw, True, max_checks=8)
+        alg = S * (sum(n_ind) * bits / 8 + 4)
+        out["cases"].append(dict(bits=bits, ploidy=ploidy, packed_gb=d_packed.numel() / 1e9, site_counts_ms=t_counts,
+                                 site_flags_ms=t_fused, site_flags_gbps_algorithmic=alg / t_fused / 1e6,
+                                 site_flags_gbps_packed=d_packed.numel() / t_fused / 1e6, oracle_windows_checked=checked))
+    print(json.dumps(out))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True, choices=[3, 4, 5, 6])
+    ap.add_argument("--config", type=int, required=True, choices=[3, 4, 5, 6, 7])
     ap.add_argument("--sites", type=int, default=None)
     ap.add_argument("--dump", action="store_true")
     a = ap.parse_args()
-    {3: config3, 4: config4, 5: config5, 6: config6}[a.config](a)
+    {3: config3, 4: config4, 5: config5, 6: config6, 7: config7}[a.config](a)
