@@ -10,6 +10,7 @@
 // row, 256 bytes apart -- the whole tile (pairs_per_site * 256 B, 20 KB for 2504 diploids) stays
 // in L1/L2 while its 32 input rows stream through.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -209,37 +210,67 @@ inline void scatter_site(const uint32_t* words, int n_pairs, uint8_t* tile_pop, 
 // All populations of tiles [t0, t1), site by site: when the populations are column blocks of one
 // row-major matrix (what a VCF parse leaves behind) the whole matrix is read as ONE sequential
 // stream, which is what the hardware prefetcher wants; the rows a few sites ahead are prefetched
-// explicitly as well.  Returns true when a value does not fit its population's bit-planes.
+// explicitly as well.  Output: the words of 8 consecutive sites are collected in a small buffer
+// and every pair row then receives its 8 x 8 bytes as ONE full cache line of non-temporal stores
+// (no read-for-ownership of the destination, no cache pollution: the tiles are consumed by the
+// DMA engine or a later pass, never by this core).  Returns true when a value does not fit its
+// population's bit-planes.
 bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
                        int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa) {
   const row_fn fn = row_fn_for(isa);
-  const size_t tile_bytes = (size_t)lay.pairs_per_site * kTileSites * 8;
-  int max_words = 0;
-  for (int p = 0; p < lay.n_pops; ++p) max_words = std::max(max_words, lay.pop[p].n_groups * lay.pop[p].bits);
-  uint32_t stack_words[1024];
-  uint32_t* words = max_words + 1 <= 1024 ? stack_words : new uint32_t[max_words + 1];
-  constexpr int kAhead = 3;  // sites
+  const int pps = lay.pairs_per_site;
+  const size_t tile_bytes = (size_t)pps * kTileSites * 8;
+  const int col_words = 2 * pps;  // words of one site's whole column (zero pad words included)
+  constexpr int kBatch = 8;       // sites per output cache line
+  uint32_t stack_words[kBatch * 512 + 2];
+  uint32_t* wbuf = col_words + 2 <= 512 ? stack_words : new uint32_t[(size_t)kBatch * (col_words + 2)];
+  const int wstride = col_words + 2;
+  constexpr int kAhead = 4;  // sites
+  // SAI_PACK_NT=0 (read once) switches the non-temporal stores off: an A/B knob for tools/pack_bench.py
+  static const bool nt_enabled = [] {
+    const char* e = getenv("SAI_PACK_NT");
+    return !(e && e[0] == '0');
+  }();
+  const bool aligned = nt_enabled && (reinterpret_cast<uintptr_t>(packed_base) & 63) == 0;
   bool bad = false;
   for (int64_t T = t0; T < t1; ++T) {
     uint8_t* tile = packed_base + (size_t)(T - tile_base) * tile_bytes;
-    for (int s = 0; s < kTileSites; ++s) {
-      const int64_t site = T * kTileSites + s;
-      if (site + kAhead < n_sites)
-        for (int p = 0; p < lay.n_pops; ++p) prefetch_row(gt[p] + (site + kAhead) * row_stride[p], lay.pop[p].n_samples);
-      for (int p = 0; p < lay.n_pops; ++p) {
-        const sai_pop_layout& L = lay.pop[p];
-        const int n_words = L.n_groups * L.bits;
-        if (site < n_sites) {
-          bad |= fn(gt[p] + site * row_stride[p], L.n_samples, L.n_groups, L.bits, words);
-        } else {
-          for (int w = 0; w < n_words; ++w) words[w] = 0xffffffffu;  // padding site: all missing
+    for (int s8 = 0; s8 < kTileSites; s8 += kBatch) {
+      for (int j = 0; j < kBatch; ++j) {
+        const int64_t site = T * kTileSites + s8 + j;
+        uint32_t* col = wbuf + (size_t)j * wstride;
+        if (site + kAhead < n_sites)
+          for (int p = 0; p < lay.n_pops; ++p) prefetch_row(gt[p] + (site + kAhead) * row_stride[p], lay.pop[p].n_samples);
+        for (int p = 0; p < lay.n_pops; ++p) {
+          const sai_pop_layout& L = lay.pop[p];
+          const int n_words = L.n_groups * L.bits;
+          uint32_t* words = col + 2 * L.pair_off;
+          if (site < n_sites) {
+            bad |= fn(gt[p] + site * row_stride[p], L.n_samples, L.n_groups, L.bits, words);
+          } else {
+            for (int w = 0; w < n_words; ++w) words[w] = 0xffffffffu;  // padding site: all missing
+          }
+          if (n_words & 1) words[n_words] = 0u;  // the population's pad word
         }
-        words[n_words] = 0u;
-        scatter_site(words, L.n_pairs, tile + (size_t)L.pair_off * kTileSites * 8, s);
+      }
+      for (int p = 0; p < pps; ++p) {
+        uint64_t line[kBatch];
+        for (int j = 0; j < kBatch; ++j) memcpy(&line[j], wbuf + (size_t)j * wstride + 2 * p, 8);
+        uint8_t* dst = tile + ((size_t)p * kTileSites + s8) * 8;
+#ifdef SAI_X86
+        if (aligned) {
+          for (int j = 0; j < kBatch; ++j) _mm_stream_si64(reinterpret_cast<long long*>(dst) + j, (long long)line[j]);
+          continue;
+        }
+#endif
+        memcpy(dst, line, sizeof(line));
       }
     }
   }
-  if (words != stack_words) delete[] words;
+#ifdef SAI_X86
+  _mm_sfence();  // the non-temporal stores are visible before the caller publishes the tiles
+#endif
+  if (wbuf != stack_words) delete[] wbuf;
   return bad;
 }
 

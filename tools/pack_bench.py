@@ -26,9 +26,12 @@ def main():
     rng = np.random.default_rng(0)
     g = (rng.random((S, sum(n_ind)), dtype=np.float32) < 0.1).astype(np.int8)
     lay = make_layout(n_ind, [2, 2, 2], [2, 2, 2])
-    out = np.zeros(int(lib.sai_packed_bytes(C.byref(lay), S)), dtype=np.uint8)
+    nbytes = int(lib.sai_packed_bytes(C.byref(lay), S))
+    raw = np.zeros(nbytes + 4096, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 4096
+    out = raw[off : off + nbytes]  # page aligned, like the engine's pinned staging ring
     cols = np.cumsum([0] + n_ind)
-    res = {"isa_best": lib.sai_pack_isa().decode(), "cpus": os.cpu_count(), "sites": S, "int8_gb": g.nbytes / 1e9, "gbps": {}}
+    res = {"isa_best": lib.sai_pack_isa().decode(), "nt_stores": os.environ.get("SAI_PACK_NT", "1") != "0", "cpus": os.cpu_count(), "sites": S, "int8_gb": g.nbytes / 1e9, "gbps": {}}
     t0 = time.perf_counter(); g.copy(); res["numpy_copy_gbps_1thread"] = round(g.nbytes / (time.perf_counter() - t0) / 1e9, 2)
     for isa, name in ((1, "portable"), (2, "sse2"), (0, "best")):
         for th in (1, 2, 4, 8, 16, 32, 64):
