@@ -8,11 +8,13 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 #include "common.cuh"
 #include "host_pack.h"
+#include "scratch.cuh"
 
 namespace sai {
 
@@ -36,6 +38,38 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+int scratch_alloc(void** out, size_t bytes, cudaStream_t st) {
+  static cudaMemPool_t pools[64] = {nullptr};
+  static std::mutex mu;
+  int dev = 0;
+  SAI_CUDA_CHECK(cudaGetDevice(&dev));
+  SAI_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      SAI_CUDA_CHECK(cudaMemPoolCreate(&pools[dev], &props));
+      uint64_t never = ~0ull;
+      SAI_CUDA_CHECK(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &never));
+    }
+  }
+  cudaError_t e = cudaMallocFromPoolAsync(out, bytes ? bytes : 256, pools[dev], st);
+  if (e != cudaSuccess) {
+    set_error("scratch allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? SAI_E_NOMEM : SAI_E_CUDA;
+  }
+  return SAI_OK;
+}
+
+int scratch_free(void* p, cudaStream_t st) {
+  if (p) SAI_CUDA_CHECK(cudaFreeAsync(p, st));
+  return SAI_OK;
 }
 
 int validate_layout(const sai_layout* lay) {

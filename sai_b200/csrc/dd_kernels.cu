@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "popcount.cuh"
+#include "scratch.cuh"
 
 namespace sai {
 
@@ -195,74 +196,51 @@ __device__ __forceinline__ int64_t warp_lower_bound(const int32_t* __restrict__ 
   return lo;
 }
 
-// first entry of [lo, hi) whose site is >= key (per-lane binary search inside a tile's short run)
-__device__ __forceinline__ int64_t lane_lower_bound(const int32_t* __restrict__ site, int64_t lo, int64_t hi, int key) {
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (__ldg(site + mid) < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
 // ---- pass 2: per-site distances, once per site -------------------------------------------------
 // A site lies in win_len / win_step windows; its contribution
 //     dist[a][ref] = sum_j |src_a - ref_j| = sum_u c_u |s_a - u| + sum_{missing j} |s_a - raw_j|
 // (s_a: the source individual's called value, or its raw negative value from the table when its
-// call is missing) does not depend on the window, so it is computed once here and the window
-// kernel only adds integers.  One warp per tile, lane == site; the tile's run of table entries is
-// found with one cooperative search per population, the lane's own entries inside it by bisection.
+// call is missing) does not depend on the window, so it is computed once and the window kernel
+// only adds integers.  Two launches, neither of which searches the tables per site:
+//   k_site_dd    site-driven, lane == site: the called part sum_u c_u |s_a - u| of every CALLED
+//                source individual (0 for a missing one) -- plain stores;
+//   k_entry_dd   entry-driven, one thread per table entry: a missing ref / tgt call adds
+//                |s_a - raw| for every source individual of its site; a missing source call adds
+//                its called part sum_u c_u |raw - u| -- integer atomics, order-free and exact.
+__device__ __forceinline__ int called_part(const int (&cu)[kMaxCodes], int s) {
+  int d = 0;
+#pragma unroll
+  for (int u = 0; u < kMaxCodes; ++u) {
+    const int diff = s - u;
+    d += cu[u] * (diff < 0 ? -diff : diff);  // cu is 0 beyond the population's called values
+  }
+  return d;
+}
+
 __global__ void __launch_bounds__(kDdWarps * 32) k_site_dd(const __grid_constant__ DdParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t T = (int64_t)blockIdx.x * kDdWarps + warp; T < P.n_tiles; T += (int64_t)gridDim.x * kDdWarps) {
     const int site = (int)(T * kTile) + lane;
-    // this lane's entries of the ref / tgt tables
-    int64_t e_lo[2], e_hi[2];
     int cu[2][kMaxCodes];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const DdPop& pp = t == 0 ? P.ref : P.tgt;
-      const int64_t n = pp.neg_hi - pp.neg_lo;
-      const int32_t* base = P.neg_site + pp.neg_lo;
-      const int64_t a = n > 0 ? warp_lower_bound(base, n, T * kTile, lane) : 0;
-      const int64_t b = n > 0 ? warp_lower_bound(base, n, T * kTile + kTile, lane) : 0;
-      e_lo[t] = pp.neg_lo + lane_lower_bound(base, a, b, site);
-      e_hi[t] = pp.neg_lo + lane_lower_bound(base, a, b, site + 1);
       const int32_t* h = P.hist + (size_t)pp.code_base * P.stride + site;
       const int n_called = (1 << pp.bits) - 1;
 #pragma unroll
       for (int u = 0; u < kMaxCodes; ++u) cu[t][u] = u < n_called ? __ldg(h + (size_t)u * P.stride) : 0;
     }
-    // distance of a source value s to population t at this site
-    auto distance = [&](int t, int s) {
-      int d = 0;
-#pragma unroll
-      for (int u = 0; u < kMaxCodes; ++u) {
-        const int diff = s - u;
-        d += cu[t][u] * (diff < 0 ? -diff : diff);  // cu is 0 beyond the population's called values
-      }
-      for (int64_t e = e_lo[t]; e < e_hi[t]; ++e) {
-        const int diff = s - __ldg(P.neg_val + e);
-        d += diff < 0 ? -diff : diff;
-      }
-      return d;
-    };
     for (int k = 0; k < P.n_src; ++k) {
       const DdPop& sp = P.src[k];
       const int s_missing = (1 << sp.bits) - 1;
-      const int64_t n = sp.neg_hi - sp.neg_lo;
-      const int32_t* base = P.neg_site + sp.neg_lo;
-      const int64_t ta = n > 0 ? warp_lower_bound(base, n, T * kTile, lane) : 0;
-      const int64_t tb = n > 0 ? warp_lower_bound(base, n, T * kTile + kTile, lane) : 0;
-      const int64_t s_lo = sp.neg_lo + lane_lower_bound(base, ta, tb, site);
-      const int64_t s_hi = sp.neg_lo + lane_lower_bound(base, ta, tb, site + 1);
       const uint2* col = P.packed + ((size_t)T * P.pairs_per_site + sp.pair_off) * kTile + lane;
       // called source values repeat (0, 1, 2 for two planes): their distances once per site
-      int dcalled[2][3];
+      int dc[2][3];
       if (sp.bits == 2) {
 #pragma unroll
         for (int t = 0; t < 2; ++t)
 #pragma unroll
-          for (int v = 0; v < 3; ++v) dcalled[t][v] = distance(t, v);
+          for (int v = 0; v < 3; ++v) dc[t][v] = called_part(cu[t], v);
       }
       for (int a0 = 0; a0 < sp.n_samples; a0 += 32) {
         uint32_t w[4];
@@ -273,31 +251,98 @@ __global__ void __launch_bounds__(kDdWarps * 32) k_site_dd(const __grid_constant
           int sv = 0;
 #pragma unroll
           for (int b = 0; b < 4; ++b) sv |= (int)((w[b] >> bit) & 1u) << b;
-          int dr, dt;
-          if (sv == s_missing) {  // the raw value of the missing source call is in the table
-            bool found = false;
-            for (int64_t e = s_lo; e < s_hi; ++e)
-              if (__ldg(P.neg_ind + e) == a0 + bit) {
-                sv = __ldg(P.neg_val + e);
-                found = true;
-              }
-            if (!found) {
-              sv = -1;
-              if (site < P.n_sites) *P.err = 1;
+          int dr = 0, dt = 0;
+          if (sv != s_missing) {
+            if (sp.bits == 2) {
+              dr = sv == 0 ? dc[0][0] : (sv == 1 ? dc[0][1] : dc[0][2]);
+              dt = sv == 0 ? dc[1][0] : (sv == 1 ? dc[1][1] : dc[1][2]);
+            } else {
+              dr = called_part(cu[0], sv);
+              dt = called_part(cu[1], sv);
             }
-            dr = distance(0, sv);
-            dt = distance(1, sv);
-          } else if (sp.bits == 2) {
-            dr = sv == 0 ? dcalled[0][0] : (sv == 1 ? dcalled[0][1] : dcalled[0][2]);
-            dt = sv == 0 ? dcalled[1][0] : (sv == 1 ? dcalled[1][1] : dcalled[1][2]);
-          } else {
-            dr = distance(0, sv);
-            dt = distance(1, sv);
           }
           int32_t* o = P.dist + (size_t)(P.slot0[k] + a0 + bit) * 2 * P.stride + site;
           o[0] = dr;
           o[P.stride] = dt;
         }
+      }
+    }
+  }
+}
+
+// raw value of a missing call: entry (site, ind) of the population's table slice
+__device__ __forceinline__ bool raw_lookup(const DdParams& P, const DdPop& pp, int site, int ind, int& raw) {
+  int64_t lo = pp.neg_lo, hi = pp.neg_hi;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int s = __ldg(P.neg_site + mid);
+    if (s < site || (s == site && __ldg(P.neg_ind + mid) < ind))
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  if (lo < pp.neg_hi && __ldg(P.neg_site + lo) == site && __ldg(P.neg_ind + lo) == ind) {
+    raw = __ldg(P.neg_val + lo);
+    return true;
+  }
+  return false;
+}
+
+// one thread per entry of the ref table, the tgt table and the source tables, in that order
+__global__ void __launch_bounds__(256) k_entry_dd(const __grid_constant__ DdParams P, int64_t n_ref, int64_t n_tgt,
+                                                  int64_t n_total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n_ref + n_tgt) {
+      // a missing ref / tgt call against every source individual of its site
+      const int t = i < n_ref ? 0 : 1;
+      const DdPop& pp = t == 0 ? P.ref : P.tgt;
+      const int64_t e = pp.neg_lo + (t == 0 ? i : i - n_ref);
+      const int site = __ldg(P.neg_site + e), v = __ldg(P.neg_val + e);
+      if (site < 0 || site >= P.n_sites) continue;
+      for (int k = 0; k < P.n_src; ++k) {
+        const DdPop& sp = P.src[k];
+        const int s_missing = (1 << sp.bits) - 1;
+        const uint2* col = P.packed + ((size_t)(site >> 5) * P.pairs_per_site + sp.pair_off) * kTile + (site & 31);
+        for (int a0 = 0; a0 < sp.n_samples; a0 += 32) {
+          uint32_t w[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) w[b] = b < sp.bits ? plane_word(col, (a0 >> 5) * sp.bits + b) : 0u;
+          const int cnt = sp.n_samples - a0 < 32 ? sp.n_samples - a0 : 32;
+          for (int bit = 0; bit < cnt; ++bit) {
+            int sv = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) sv |= (int)((w[b] >> bit) & 1u) << b;
+            if (sv == s_missing) {  // the source call is missing too: its raw value is in the table
+              sv = -1;
+              if (!raw_lookup(P, sp, site, a0 + bit, sv)) *P.err = 1;
+            }
+            const int diff = sv - v;
+            atomicAdd(P.dist + ((size_t)(P.slot0[k] + a0 + bit) * 2 + t) * P.stride + site, diff < 0 ? -diff : diff);
+          }
+        }
+      }
+    } else {
+      // a missing source call against the called ref / tgt values of its site
+      int64_t r = i - n_ref - n_tgt;
+      int k = 0;
+      while (k + 1 < P.n_src && r >= P.src[k].neg_hi - P.src[k].neg_lo) {
+        r -= P.src[k].neg_hi - P.src[k].neg_lo;
+        ++k;
+      }
+      const int64_t e = P.src[k].neg_lo + r;
+      const int site = __ldg(P.neg_site + e), a = __ldg(P.neg_ind + e), v = __ldg(P.neg_val + e);
+      if (site < 0 || site >= P.n_sites || a < 0 || a >= P.src[k].n_samples) continue;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const DdPop& pp = t == 0 ? P.ref : P.tgt;
+        const int32_t* h = P.hist + (size_t)pp.code_base * P.stride + site;
+        const int n_called = (1 << pp.bits) - 1;
+        int d = 0;
+        for (int u = 0; u < n_called; ++u) {
+          const int diff = v - u;
+          d += __ldg(h + (size_t)u * P.stride) * (diff < 0 ? -diff : diff);
+        }
+        atomicAdd(P.dist + ((size_t)(P.slot0[k] + a) * 2 + t) * P.stride + site, d);
       }
     }
   }
@@ -470,19 +515,27 @@ extern "C" int sai_window_dd(const sai_layout* lay, const void* d_packed, const 
   P.n_tiles = sai_num_tiles(n_sites);
   SAI_REQUIRE(stride >= P.n_tiles * kTile, "stride smaller than the tiled site count");
   void* scratch = nullptr;
-  SAI_CUDA_CHECK(cudaMallocAsync(&scratch, sizeof(int32_t) * 2 * (size_t)slots * (size_t)std::max<int64_t>(stride, 32), st));
+  if (int rc = scratch_alloc(&scratch, sizeof(int32_t) * 2 * (size_t)slots * (size_t)std::max<int64_t>(stride, 32), st)) return rc;
   P.dist = static_cast<int32_t*>(scratch);
   if (P.n_tiles > 0) {
     const int64_t wantt = (P.n_tiles + kDdWarps - 1) / kDdWarps;
     const int64_t capt = (int64_t)sm_count() * 16;
     k_site_dd<<<(unsigned)(wantt < capt ? wantt : capt), kDdWarps * 32, 0, st>>>(P);
     SAI_CUDA_CHECK(cudaGetLastError());
+    const int64_t n_ref = P.ref.neg_hi - P.ref.neg_lo, n_tgt = P.tgt.neg_hi - P.tgt.neg_lo;
+    int64_t n_total = n_ref + n_tgt;
+    for (int k = 0; k < n_src; ++k) n_total += P.src[k].neg_hi - P.src[k].neg_lo;
+    if (n_total > 0) {
+      const int64_t wante = (n_total + 255) / 256;
+      const int64_t cape = (int64_t)sm_count() * 32;
+      k_entry_dd<<<(unsigned)(wante < cape ? wante : cape), 256, 0, st>>>(P, n_ref, n_tgt, n_total);
+      SAI_CUDA_CHECK(cudaGetLastError());
+    }
   }
   const int64_t want = (n_windows + kDdWarps - 1) / kDdWarps;
   const int64_t cap = (int64_t)sm_count() * 16;
   const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_src);
   k_window_dd<<<grid, kDdWarps * 32, 0, st>>>(P);
   SAI_CUDA_CHECK(cudaGetLastError());
-  SAI_CUDA_CHECK(cudaFreeAsync(scratch, st));
-  return SAI_OK;
+  return scratch_free(scratch, st);
 }

@@ -503,18 +503,26 @@ int sai_engine_dd_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, in
   if (W == 0 || n_src <= 0) return SAI_OK;
   const int64_t n_neg = neg_off[lay->n_pops];
   SAI_REQUIRE(n_neg >= 0 && (n_neg == 0 || (neg_site && neg_ind && neg_val)), "bad negative-value table");
-  const int32_t hp[2] = {ref_pop, tgt_pop};
-  const int64_t rows = sai_hist_rows(lay, hp, 2);
+  // histograms of ref and tgt (what the distance kernels read) and, behind them, of the source
+  // populations: only their missing-call totals are used, to check the table against the tiles
+  SAI_REQUIRE(n_src <= SAI_MAX_SRC, "n_src %d outside [1,%d]", n_src, SAI_MAX_SRC);
+  int32_t hp[2 + SAI_MAX_SRC] = {ref_pop, tgt_pop};
+  for (int k = 0; k < n_src; ++k) {
+    SAI_REQUIRE(src_pops[k] >= 0 && src_pops[k] < lay->n_pops, "bad source population index");
+    hp[2 + k] = src_pops[k];
+  }
+  const int n_hp = 2 + n_src;
+  const int64_t rows = sai_hist_rows(lay, hp, n_hp);
   const size_t out_n = (size_t)n_src * W * m_max;
   if (int rc = grow(e->hist, sizeof(int32_t) * (size_t)rows * stride + 512)) return rc;
   if (int rc = grow(e->neg, sizeof(int32_t) * 3 * (size_t)n_neg + 256)) return rc;
   if (int rc = grow(e->dd, sizeof(int64_t) * 2 * out_n + 512)) return rc;
   cudaStream_t st = e->s_comp;
-  // [hist rows][2 x uint64 missing totals][int32 err] share the hist buffer's tail
+  // [hist rows][uint64 missing totals][int32 err] share the hist buffer's tail
   int32_t* d_hist = static_cast<int32_t*>(e->hist.p);
   uint64_t* d_missing = reinterpret_cast<uint64_t*>(
       static_cast<char*>(e->hist.p) + align256(sizeof(int32_t) * (size_t)rows * stride));
-  int32_t* d_err = reinterpret_cast<int32_t*>(d_missing + 2);
+  int32_t* d_err = reinterpret_cast<int32_t*>(d_missing + n_hp);
   int32_t* d_ns = static_cast<int32_t*>(e->neg.p);
   int32_t* d_ni = d_ns + n_neg;
   int32_t* d_nv = d_ni + n_neg;
@@ -524,7 +532,7 @@ int sai_engine_dd_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, in
     SAI_CUDA_CHECK(cudaMemcpyAsync(d_nv, neg_val, sizeof(int32_t) * n_neg, cudaMemcpyHostToDevice, st));
   }
   SAI_CUDA_CHECK(cudaMemsetAsync(d_err, 0, sizeof(int32_t), st));
-  if (int rc = sai_site_hist(lay, e->packed.p, e->n_sites, hp, 2, d_hist, stride, d_missing, st)) return rc;
+  if (int rc = sai_site_hist(lay, e->packed.p, e->n_sites, hp, n_hp, d_hist, stride, d_missing, st)) return rc;
   int64_t* d_r = static_cast<int64_t*>(e->dd.p);
   int64_t* d_t = d_r + out_n;
   SAI_CUDA_CHECK(cudaMemsetAsync(d_r, 0, sizeof(int64_t) * 2 * out_n, st));
@@ -533,15 +541,15 @@ int sai_engine_dd_sums(sai_engine* e, const sai_layout* lay, int32_t ref_pop, in
                              W, d_hist, stride, ref_pop, tgt_pop, src_pops, n_src, neg_off, d_ns, d_ni, d_nv,
                              d_r, d_t, m_max, d_err, st))
     return rc;
-  uint64_t h_missing[2] = {0, 0};
+  uint64_t h_missing[2 + SAI_MAX_SRC] = {0};
   int32_t h_err = 0;
   SAI_CUDA_CHECK(cudaMemcpyAsync(ref_sum, d_r, sizeof(int64_t) * out_n, cudaMemcpyDeviceToHost, st));
   SAI_CUDA_CHECK(cudaMemcpyAsync(tgt_sum, d_t, sizeof(int64_t) * out_n, cudaMemcpyDeviceToHost, st));
-  SAI_CUDA_CHECK(cudaMemcpyAsync(h_missing, d_missing, sizeof(h_missing), cudaMemcpyDeviceToHost, st));
+  SAI_CUDA_CHECK(cudaMemcpyAsync(h_missing, d_missing, sizeof(uint64_t) * n_hp, cudaMemcpyDeviceToHost, st));
   SAI_CUDA_CHECK(cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, st));
   SAI_CUDA_CHECK(cudaStreamSynchronize(st));
   // the bit-planes keep one missing code: every missing call needs its raw value in the table
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < n_hp; ++q) {
     const int64_t have = neg_off[hp[q] + 1] - neg_off[hp[q]];
     SAI_REQUIRE((int64_t)h_missing[q] == have,
                 "population %d has %lld missing calls but %lld entries in the negative-value table", hp[q],

@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "scratch.cuh"
 
 namespace sai {
 
@@ -262,7 +263,7 @@ extern "C" int sai_window_patterns(const sai_layout* lay, const int32_t* d_pos, 
   Q.P = P;
   Q.stride = stride;
   void* scratch = nullptr;
-  SAI_CUDA_CHECK(cudaMallocAsync(&scratch, sizeof(double) * kPatSums * (size_t)n_src * (size_t)std::max<int64_t>(stride, 32), st));
+  if (int rc = scratch_alloc(&scratch, sizeof(double) * kPatSums * (size_t)n_src * (size_t)std::max<int64_t>(stride, 32), st)) return rc;
   Q.prod = static_cast<double*>(scratch);
   if (n_sites > 0) {
     const int64_t blocks = (n_sites + 255) / 256;
@@ -275,6 +276,5 @@ extern "C" int sai_window_patterns(const sai_layout* lay, const int32_t* d_pos, 
   const dim3 grid((unsigned)(want < cap ? want : cap), (unsigned)n_src);
   k_window_patterns<<<grid, kPatWarps * 32, 0, st>>>(Q);
   SAI_CUDA_CHECK(cudaGetLastError());
-  SAI_CUDA_CHECK(cudaFreeAsync(scratch, st));
-  return SAI_OK;
+  return scratch_free(scratch, st);
 }
