@@ -21,7 +21,6 @@ struct sai_engine {
   int device = 0;
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   std::vector<cudaEvent_t> ev;
-  std::vector<cudaEvent_t> ev_block;  // blocking-sync events: the host sleeps on them (int8 pipeline)
   int host_threads = 0;               // packer threads of the int8 pipeline (0: hardware concurrency)
   void* ring = nullptr;               // pinned staging ring of the int8 pipeline
   size_t ring_cap = 0;
@@ -166,7 +165,6 @@ void sai_engine_destroy(sai_engine* e) {
   for (auto* b : {&e->packed, &e->pos, &e->win, &e->mask, &e->qval, &e->res, &e->cand, &e->counts, &e->sums, &e->hist, &e->neg, &e->dd, &e->zt, &e->ztoff})
     if (b->p) cudaFree(b->p);
   for (auto ev : e->ev) cudaEventDestroy(ev);
-  for (auto ev : e->ev_block) cudaEventDestroy(ev);
   if (e->ring) cudaFreeHost(e->ring);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
@@ -184,11 +182,27 @@ struct I8Source {
   const int64_t* row_stride;
 };
 
+struct I8Sync {
+  std::atomic<int64_t> allowed{0};  // slices [0, allowed) may be packed: their ring slot is free
+  std::mutex mu;
+  std::condition_variable cv;
+};
+
+// runs on a CUDA callback thread when the copy of a slice has left its ring slot
+static void CUDART_CB i8_slot_free(void* p) {
+  I8Sync* y = static_cast<I8Sync*>(p);
+  {
+    std::lock_guard<std::mutex> lk(y->mu);
+    y->allowed.fetch_add(1, std::memory_order_release);
+  }
+  y->cv.notify_all();
+}
+
 static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8Source& src, int64_t n_sites,
                                 int64_t n_tiles, const sai_job* jobs, int32_t n_jobs, uint32_t* d_mask_u,
                                 uint32_t* d_mask_q, double* d_qval, int64_t stride) {
   const size_t tile_bytes = (size_t)lay->pairs_per_site * kTile * 8;
-  const int64_t slice_tiles = std::max<int64_t>(1, (int64_t)((16ull << 20) / tile_bytes));
+  const int64_t slice_tiles = std::max<int64_t>(1, (int64_t)((32ull << 20) / tile_bytes));
   const int64_t n_slices = (n_tiles + slice_tiles - 1) / slice_tiles;
   const int kRing = 4;
   const size_t slot_bytes = (size_t)slice_tiles * tile_bytes;
@@ -198,11 +212,6 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
     e->ring_cap = 0;
     SAI_CUDA_CHECK(cudaHostAlloc(&e->ring, slot_bytes * kRing, cudaHostAllocDefault));
     e->ring_cap = slot_bytes * kRing;
-  }
-  while ((int64_t)e->ev_block.size() < kRing) {
-    cudaEvent_t ev;
-    SAI_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
-    e->ev_block.push_back(ev);
   }
   while ((int64_t)e->ev.size() < kRing) {
     cudaEvent_t ev;
@@ -219,21 +228,21 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
   };
   const int64_t n_tasks = (n_slices - 1) * blocks_per_slice + blocks_of(n_slices - 1);
   n_threads = (int)std::min<int64_t>(n_threads, n_tasks);
-  std::atomic<int64_t> next_task{0}, allowed{kRing};
+  std::atomic<int64_t> next_task{0};
   std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[n_slices]);
   for (int64_t s = 0; s < n_slices; ++s) done[s].store(0);
   std::atomic<int> bad{0}, abort_flag{0};
-  std::mutex mu;
-  std::condition_variable cv;
+  I8Sync sync;
+  sync.allowed.store(kRing);
   uint8_t* ring = static_cast<uint8_t*>(e->ring);
   auto worker = [&]() {
     for (;;) {
       const int64_t i = next_task.fetch_add(1);
       if (i >= n_tasks) break;
       const int64_t s = i / blocks_per_slice, b = i % blocks_per_slice;
-      if (s >= allowed.load(std::memory_order_acquire)) {  // the slice's ring slot is still on the wire
-        std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return s < allowed.load(std::memory_order_acquire) || abort_flag.load(); });
+      if (s >= sync.allowed.load(std::memory_order_acquire)) {  // the slice's ring slot is still on the wire
+        std::unique_lock<std::mutex> lk(sync.mu);
+        sync.cv.wait(lk, [&] { return s < sync.allowed.load(std::memory_order_acquire) || abort_flag.load(); });
       }
       if (abort_flag.load()) break;
       const int64_t t0 = s * slice_tiles + b * block_tiles;
@@ -241,8 +250,8 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       uint8_t* slot = ring + (size_t)(s % kRing) * slot_bytes;
       if (pack_tiles_i8_all(*lay, src.gt, src.row_stride, n_sites, t0, t1, s * slice_tiles, slot, 0)) bad.store(1);
       if (done[s].fetch_add(1, std::memory_order_acq_rel) + 1 == (int)blocks_of(s)) {
-        std::lock_guard<std::mutex> lk(mu);
-        cv.notify_all();
+        std::lock_guard<std::mutex> lk(sync.mu);
+        sync.cv.notify_all();
       }
     }
   };
@@ -252,21 +261,24 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
   auto fail = [&](int code) {
     rc = code;
     abort_flag.store(1);
-    std::lock_guard<std::mutex> lk(mu);
-    cv.notify_all();
+    std::lock_guard<std::mutex> lk(sync.mu);
+    sync.cv.notify_all();
   };
 #define SAI_I8_CUDA(expr)                                                                      \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \
-    if (_e != cudaSuccess) {                                                                   \
+    if (_e != cudaSuccess && rc == SAI_OK) {                                                   \
       set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
       fail(SAI_E_CUDA);                                                                        \
     }                                                                                          \
   } while (0)
+  // The feeding thread never waits for the GPU: it sleeps until the next slice is packed, hands it
+  // to the copy engine and queues (a) the genotype pass behind the copy and (b) a host callback
+  // that returns the ring slot to the packers once the copy has left it.
   for (int64_t s = 0; s < n_slices && rc == SAI_OK; ++s) {
     {
-      std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] { return done[s].load(std::memory_order_acquire) == (int)blocks_of(s); });
+      std::unique_lock<std::mutex> lk(sync.mu);
+      sync.cv.wait(lk, [&] { return done[s].load(std::memory_order_acquire) == (int)blocks_of(s); });
     }
     if (bad.load()) {
       fail(SAI_E_DOMAIN);
@@ -276,27 +288,25 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
     const int slot = (int)(s % kRing);
     SAI_I8_CUDA(cudaMemcpyAsync(static_cast<char*>(e->packed.p) + (size_t)t0 * tile_bytes, ring + (size_t)slot * slot_bytes,
                                 (size_t)(t1 - t0) * tile_bytes, cudaMemcpyHostToDevice, e->s_copy));
-    SAI_I8_CUDA(cudaEventRecord(e->ev_block[slot], e->s_copy));
     SAI_I8_CUDA(cudaEventRecord(e->ev[slot], e->s_copy));
+    SAI_I8_CUDA(cudaLaunchHostFunc(e->s_copy, i8_slot_free, &sync));
     SAI_I8_CUDA(cudaStreamWaitEvent(e->s_comp, e->ev[slot], 0));
     if (rc == SAI_OK)
       if (int k = sai_site_flags(lay, e->packed.p, t0, t1 - t0, n_tiles, jobs, n_jobs, d_mask_u, d_mask_q, d_qval,
                                  stride, nullptr, nullptr, 0, 0, e->s_comp))
         fail(k);
-    // the slot may be refilled once its copy has left the host (the threads are meanwhile packing
-    // the next kRing - 1 slices; the host sleeps in this wait)
-    SAI_I8_CUDA(cudaEventSynchronize(e->ev_block[slot]));
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      allowed.store(s + 1 + kRing, std::memory_order_release);
-      cv.notify_all();
-    }
   }
 #undef SAI_I8_CUDA
   for (auto& t : pool) t.join();
+  // every queued callback refers to `sync` on this stack frame: drain the copy stream before leaving
+  const cudaError_t drained = cudaStreamSynchronize(e->s_copy);
   if (rc == SAI_E_DOMAIN || (rc == SAI_OK && bad.load())) {
     set_error("a genotype value does not fit the bit-planes of its population");
     return SAI_E_DOMAIN;
+  }
+  if (rc == SAI_OK && drained != cudaSuccess) {
+    set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(drained));
+    return SAI_E_CUDA;
   }
   return rc;
 }
