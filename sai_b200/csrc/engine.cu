@@ -6,11 +6,14 @@
 // window kernels run once all slices are flagged; results come back in one
 // batch of device->host copies.  Device buffers are grow-only and reused across
 // calls (one engine per GPU / per worker process).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -202,9 +205,14 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
                                 int64_t n_tiles, const sai_job* jobs, int32_t n_jobs, uint32_t* d_mask_u,
                                 uint32_t* d_mask_q, double* d_qval, int64_t stride) {
   const size_t tile_bytes = (size_t)lay->pairs_per_site * kTile * 8;
-  const int64_t slice_tiles = std::max<int64_t>(1, (int64_t)((32ull << 20) / tile_bytes));
+  uint64_t slice_bytes = 32ull << 20;
+  int kRing = 4;
+#ifdef SAI_EXPERIMENTS
+  if (const char* v = getenv("SAI_I8_SLICE_MB")) slice_bytes = (uint64_t)std::max(1, atoi(v)) << 20;  // tools/ A/B knobs
+  if (const char* v = getenv("SAI_I8_RING")) kRing = std::max(2, atoi(v));
+#endif
+  const int64_t slice_tiles = std::max<int64_t>(1, (int64_t)(slice_bytes / tile_bytes));
   const int64_t n_slices = (n_tiles + slice_tiles - 1) / slice_tiles;
-  const int kRing = 4;
   const size_t slot_bytes = (size_t)slice_tiles * tile_bytes;
   if (e->ring_cap < slot_bytes * kRing) {
     if (e->ring) SAI_CUDA_CHECK(cudaFreeHost(e->ring));
@@ -235,7 +243,53 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
   I8Sync sync;
   sync.allowed.store(kRing);
   uint8_t* ring = static_cast<uint8_t*>(e->ring);
+  // Slices are handed to the GPU by whichever packer thread completes them (in slice order, under
+  // issue_mu): no hand-off to a feeding thread, so no wake-up latency between "packed" and "on the
+  // wire".  Per slice: the copy, an event the genotype pass waits for, and a host callback behind
+  // the copy that returns the ring slot to the packers.
+  std::mutex issue_mu;
+  int64_t next_issue = 0;  // guarded by issue_mu
+  int rc = SAI_OK;         // guarded by issue_mu
+  std::string err_msg;     // the failing thread's message (sai_last_error is thread-local)
+  auto fail_locked = [&](int code) {
+    if (rc == SAI_OK) {
+      rc = code;
+      err_msg = sai_last_error();
+    }
+    abort_flag.store(1);
+    std::lock_guard<std::mutex> lk(sync.mu);
+    sync.cv.notify_all();
+  };
+  auto issue_ready_slices = [&]() {
+    std::lock_guard<std::mutex> lk(issue_mu);
+    while (rc == SAI_OK && next_issue < n_slices &&
+           done[next_issue].load(std::memory_order_acquire) == (int)blocks_of(next_issue)) {
+      const int64_t s = next_issue++;
+      if (bad.load()) {
+        fail_locked(SAI_E_DOMAIN);
+        break;
+      }
+      const int64_t t0 = s * slice_tiles, t1 = std::min(n_tiles, t0 + slice_tiles);
+      const int slot = (int)(s % kRing);
+      cudaError_t ce = cudaMemcpyAsync(static_cast<char*>(e->packed.p) + (size_t)t0 * tile_bytes,
+                                       ring + (size_t)slot * slot_bytes, (size_t)(t1 - t0) * tile_bytes,
+                                       cudaMemcpyHostToDevice, e->s_copy);
+      if (ce == cudaSuccess) ce = cudaEventRecord(e->ev[slot], e->s_copy);
+      if (ce == cudaSuccess) ce = cudaLaunchHostFunc(e->s_copy, i8_slot_free, &sync);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->s_comp, e->ev[slot], 0);
+      if (ce != cudaSuccess) {
+        set_error("int8 pipeline: CUDA call failed: %s", cudaGetErrorString(ce));
+        fail_locked(SAI_E_CUDA);
+        break;
+      }
+      if (int k = sai_site_flags(lay, e->packed.p, t0, t1 - t0, n_tiles, jobs, n_jobs, d_mask_u, d_mask_q, d_qval,
+                                 stride, nullptr, nullptr, 0, 0, e->s_comp))
+        fail_locked(k);
+    }
+  };
+  const int device = e->device;
   auto worker = [&]() {
+    cudaSetDevice(device);  // a fresh thread starts on device 0
     for (;;) {
       const int64_t i = next_task.fetch_add(1);
       if (i >= n_tasks) break;
@@ -249,55 +303,13 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       const int64_t t1 = std::min(std::min(n_tiles, (s + 1) * slice_tiles), t0 + block_tiles);
       uint8_t* slot = ring + (size_t)(s % kRing) * slot_bytes;
       if (pack_tiles_i8_all(*lay, src.gt, src.row_stride, n_sites, t0, t1, s * slice_tiles, slot, 0)) bad.store(1);
-      if (done[s].fetch_add(1, std::memory_order_acq_rel) + 1 == (int)blocks_of(s)) {
-        std::lock_guard<std::mutex> lk(sync.mu);
-        sync.cv.notify_all();
-      }
+      if (done[s].fetch_add(1, std::memory_order_acq_rel) + 1 == (int)blocks_of(s)) issue_ready_slices();
     }
   };
   std::vector<std::thread> pool;
   for (int i = 0; i < n_threads; ++i) pool.emplace_back(worker);
-  int rc = SAI_OK;
-  auto fail = [&](int code) {
-    rc = code;
-    abort_flag.store(1);
-    std::lock_guard<std::mutex> lk(sync.mu);
-    sync.cv.notify_all();
-  };
-#define SAI_I8_CUDA(expr)                                                                      \
-  do {                                                                                         \
-    cudaError_t _e = (expr);                                                                   \
-    if (_e != cudaSuccess && rc == SAI_OK) {                                                   \
-      set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
-      fail(SAI_E_CUDA);                                                                        \
-    }                                                                                          \
-  } while (0)
-  // The feeding thread never waits for the GPU: it sleeps until the next slice is packed, hands it
-  // to the copy engine and queues (a) the genotype pass behind the copy and (b) a host callback
-  // that returns the ring slot to the packers once the copy has left it.
-  for (int64_t s = 0; s < n_slices && rc == SAI_OK; ++s) {
-    {
-      std::unique_lock<std::mutex> lk(sync.mu);
-      sync.cv.wait(lk, [&] { return done[s].load(std::memory_order_acquire) == (int)blocks_of(s); });
-    }
-    if (bad.load()) {
-      fail(SAI_E_DOMAIN);
-      break;
-    }
-    const int64_t t0 = s * slice_tiles, t1 = std::min(n_tiles, t0 + slice_tiles);
-    const int slot = (int)(s % kRing);
-    SAI_I8_CUDA(cudaMemcpyAsync(static_cast<char*>(e->packed.p) + (size_t)t0 * tile_bytes, ring + (size_t)slot * slot_bytes,
-                                (size_t)(t1 - t0) * tile_bytes, cudaMemcpyHostToDevice, e->s_copy));
-    SAI_I8_CUDA(cudaEventRecord(e->ev[slot], e->s_copy));
-    SAI_I8_CUDA(cudaLaunchHostFunc(e->s_copy, i8_slot_free, &sync));
-    SAI_I8_CUDA(cudaStreamWaitEvent(e->s_comp, e->ev[slot], 0));
-    if (rc == SAI_OK)
-      if (int k = sai_site_flags(lay, e->packed.p, t0, t1 - t0, n_tiles, jobs, n_jobs, d_mask_u, d_mask_q, d_qval,
-                                 stride, nullptr, nullptr, 0, 0, e->s_comp))
-        fail(k);
-  }
-#undef SAI_I8_CUDA
   for (auto& t : pool) t.join();
+  issue_ready_slices();  // nothing left unless a packer bailed out
   // every queued callback refers to `sync` on this stack frame: drain the copy stream before leaving
   const cudaError_t drained = cudaStreamSynchronize(e->s_copy);
   if (rc == SAI_E_DOMAIN || (rc == SAI_OK && bad.load())) {
@@ -308,6 +320,7 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
     set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(drained));
     return SAI_E_CUDA;
   }
+  if (rc != SAI_OK) set_error("%s", err_msg.c_str());
   return rc;
 }
 

@@ -193,101 +193,32 @@ def config5(args):
 
 # --------------------------------------------------------------------------
 def config4(args):
-    """Whole genome: 22 autosomes (80 M sites by default) sharded by contiguous window ranges over the ranks, then
-    the genome-wide outlier thresholds with one all-gather per column."""
+    """Whole genome: 22 autosomes (80 M sites by default) sharded by contiguous window ranges over the ranks, one
+    launch pair per rank (sai_b200.genome), then the genome-wide outlier thresholds with one all_gather_into_tensor
+    + the device select.  This is bench.py's `strong` record run on its own (bench.py prints it in every run)."""
+    import types
+
     import torch.distributed as dist
 
-    from sai_b200.outlier import distributed_threshold, outlier_mask, threshold_from_values
+    import bench
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    total = args.sites or 80_000_000
-    n_ind = [1500, 1000, 4]
-    lay = make_layout(n_ind, [2, 2, 2], [2, 2, 2])
-    chrom_sites = [int(total * mb / sum(HG19_MB)) // 32 * 32 for mb in HG19_MB]
-    L, st = 50_000, 10_000
-    # the flattened (chromosome, window) list, split like _split_windows_ranges
-    chrom_pos = [positions(n, mb * 1e6 / n, 100 + c) for c, (n, mb) in enumerate(zip(chrom_sites, HG19_MB))]
-    chrom_wins = [split_genome([int(p[0]), int(p[-1])], L, st) for p in chrom_pos]
-    flat = [(c, w) for c, wins in enumerate(chrom_wins) for w in wins]
-    base, extra = divmod(len(flat), world)
-    lo = rank * base + min(rank, extra)
-    hi = lo + base + (1 if rank < extra else 0)
-    mine = flat[lo:hi]
-    u_kw = dict(w=0.01, x=0.5, y_list=[("=", 1.0)])
-    q_kw = dict(w=0.01, quantile=0.95, y_list=[("=", 1.0)])
-    job = make_job(0, 1, [2], True, u=u_kw, q=q_kw)
 
-    # per chromosome piece of this rank: the sites of [first.start, last.end]
-    pieces = []
-    for c in sorted({c for c, _ in mine}):
-        wins = [w for cc, w in mine if cc == c]
-        pos = chrom_pos[c]
-        s_lo = int(np.searchsorted(pos, wins[0][0], "left")) // 32 * 32  # tile aligned: the generator is tile-addressed
-        s_hi = int(np.searchsorted(pos, wins[-1][1], "right"))
-        pieces.append((c, wins, s_lo, s_hi))
-    # generate every piece on the device (untimed), then time the scoring of all pieces
-    data = []
-    for c, wins, s_lo, s_hi in pieces:
-        n = s_hi - s_lo
-        nbytes = int(_cabi.load().sai_packed_bytes(C.byref(lay), n))
-        d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        # tile0 offsets the generator so that a site has the same genotypes whichever rank holds it
-        role = (C.c_int32 * 3)(0, 1, 2)
-        _cabi.check(_cabi.load().sai_synth_fill(C.byref(lay), d.data_ptr() - (s_lo // 32) * lay.pairs_per_site * 256,
-                                                s_lo // 32, (n + 31) // 32, chrom_sites[c], role, 777 + c, 0.0,
-                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        d_pos = torch.from_numpy(chrom_pos[c][s_lo:s_hi].copy()).cuda()
-        d_ws, d_we = dev_windows(wins)
-        sc = DeviceScorer(lay, n, len(wins), 1, cap_u=max(8 * len(wins), 1 << 16), cap_q=max(32 * len(wins), 1 << 18))
-        data.append((c, wins, d, d_pos, d_ws, d_we, sc, s_lo))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for rep in range(2):  # first pass warms up
-        a.record()
-        for c, wins, d, d_pos, d_ws, d_we, sc, s_lo in data:
-            sc.step(d, d_pos, d_ws, d_we, [job])
-        b.record()
+    def barrier():
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    results = [(c, wins, sc.results()) for c, wins, d, d_pos, d_ws, d_we, sc, s_lo in data]
-    u_local = np.concatenate([r.u[0] for _, _, r in results]).astype(np.float64) if results else np.array([])
-    q_local = np.concatenate([r.q[0] for _, _, r in results]) if results else np.array([])
-    t0 = time.perf_counter()
-    thr_u = distributed_threshold(u_local, 0.99, "U")
-    thr_q = distributed_threshold(q_local, 0.99, "Q")
-    t_thr = time.perf_counter() - t0
-    n_out_u = int(outlier_mask(u_local, thr_u, "U").sum())
-    n_out_q = int(outlier_mask(q_local, thr_q, "Q").sum())
-    # oracle spot check on this rank's first piece
-    c, wins, d, d_pos, d_ws, d_we, sc, s_lo = data[0]
-    sub_pos, mats = decode_slice(lay, d, chrom_pos[c][s_lo:], 64, 128)
-    checked = check_windows(results[0][2], 0, wins, sub_pos, mats, [2, 2, 2], [2], u_kw, q_kw, True, max_checks=6)
-    gathered = [None] * world
-    summary = dict(rank=rank, windows=len(mine), sites=int(sum(dd[3].numel() for dd in data)),
-                   ms=ms, u_sum=float(u_local.sum()), q_windows=int(np.isfinite(q_local).sum()), outliers_u=n_out_u,
-                   outliers_q=n_out_q, oracle_windows_checked=checked,
-                   u_values=u_local.tolist() if args.dump else None, q_values=q_local.tolist() if args.dump else None)
-    if world > 1:
-        dist.all_gather_object(gathered, summary)
-    else:
-        gathered = [summary]
+
+    wl = dict(bench.WORKLOAD)
+    lay = make_layout(list(wl["n_ind"]), list(wl["ploidy"]), [2, 2, 2])
+    rec = bench.strong_record(types.SimpleNamespace(genome_sites=args.sites or 80_000_000, steps=10), wl, lay, rank, world,
+                              local, barrier)
     if rank == 0:
-        tot_w = sum(g["windows"] for g in gathered)
-        print(json.dumps(dict(config=4, n_gpus=world, total_sites=int(sum(chrom_sites)), total_windows=tot_w,
-                              max_rank_ms=float(t.item()), windows_per_s=tot_w / (float(t.item()) / 1e3),
-                              threshold_u_q99=thr_u, threshold_q_q99=thr_q, threshold_allgather_s=t_thr,
-                              outliers_u=sum(g["outliers_u"] for g in gathered), outliers_q=sum(g["outliers_q"] for g in gathered),
-                              u_sum=sum(g["u_sum"] for g in gathered), q_windows=sum(g["q_windows"] for g in gathered),
-                              per_rank=[{k: g[k] for k in ("rank", "windows", "sites", "ms", "oracle_windows_checked")} for g in gathered])))
+        print(json.dumps(dict(config=4, n_gpus=world, **rec)))
     if world > 1:
         dist.destroy_process_group()
 

@@ -758,3 +758,48 @@ def test_packer_vector_paths_are_identical(bits, vmax):
     for isa in (1, 2, 3, 4):
         rc = lib.sai_pack_i8_isa(C.byref(lay), 3, bad[:, 64:].ctypes.data, n_sites, bad.strides[0], outs[0].ctypes.data, 1, isa)
         assert rc == _cabi.E_DOMAIN, isa
+
+
+# ---------------------------------------------------------------- whole-genome sharding (host logic)
+def test_shard_genome_follows_split_windows_ranges():
+    """`shard_genome` cuts the flattened (chromosome, window) list like
+    ChunkGenerator._split_windows_ranges (chunk_generator.py:130-141): on one chromosome the pieces
+    ARE its ranges (incl. the reference's own KAT [(1, 30000), (25001, 55000)],
+    tests/generators/test_chunk_generator.py:39); across chromosomes every window lands in exactly
+    one piece, pieces never straddle a chromosome, shard sizes differ by at most one window, and a
+    piece's site range is the region read `chr:first.start-last.end` (the halo)."""
+    import sai_oracle as orc
+    from sai_b200.genome import Piece, piece_site_range, shard_genome
+    from sai_b200.windows import split_genome, split_windows_ranges
+
+    wins = split_genome([1, 46000], 30000, 5000)  # the reference KAT's grid: window_size 30000, step 5000... checked below
+    two = shard_genome([wins], 2)
+    ranges = [(wins[p[0].win_lo][0], wins[p[0].win_hi - 1][1]) for p in two]
+    assert ranges == split_windows_ranges(wins, 2) == orc.split_windows_ranges(wins, 2)
+    kat = split_genome([1, 30000], 30000, 25000)  # [(1, 30000), (25001, 55000)]
+    assert [(kat[p[0].win_lo][0], kat[p[0].win_hi - 1][1]) for p in shard_genome([kat], 2)] == [(1, 30000), (25001, 55000)]
+
+    rng = np.random.default_rng(4)
+    chrom_pos = [np.cumsum(rng.integers(1, 400, size=n)).astype(np.int32) for n in (900, 40, 333, 1, 700)]
+    chrom_wins = [split_genome([int(p[0]), int(p[-1])], 20000, 5000) for p in chrom_pos]
+    total = sum(len(w) for w in chrom_wins)
+    for world in (1, 2, 3, 8, 64, total + 5):
+        shards = shard_genome(chrom_wins, world)
+        assert len(shards) == world
+        sizes = [sum(p.win_hi - p.win_lo for p in s) for s in shards]
+        assert sum(sizes) == total and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+        seen = []
+        for s in shards:
+            for p in s:
+                assert 0 <= p.win_lo < p.win_hi <= len(chrom_wins[p.chrom])
+                seen += [(p.chrom, i) for i in range(p.win_lo, p.win_hi)]
+        assert seen == [(c, i) for c, w in enumerate(chrom_wins) for i in range(len(w))]  # genome order, once each
+        for s in shards:
+            for p in s:
+                pos, w = chrom_pos[p.chrom], chrom_wins[p.chrom]
+                lo, hi = piece_site_range(pos, w, p, align=False)
+                inside = (pos >= w[p.win_lo][0]) & (pos <= w[p.win_hi - 1][1])
+                assert (hi - lo) == int(inside.sum()) and (hi == lo or (inside[lo] and inside[hi - 1]))
+                lo_a, hi_a = piece_site_range(pos, w, p)
+                assert lo_a % 32 == 0 and lo - 31 <= lo_a <= lo and hi_a == max(hi, lo_a)
+    assert shard_genome([[]], 3) == [[], [], []]
