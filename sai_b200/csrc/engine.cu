@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -185,22 +186,6 @@ struct I8Source {
   const int64_t* row_stride;
 };
 
-struct I8Sync {
-  std::atomic<int64_t> allowed{0};  // slices [0, allowed) may be packed: their ring slot is free
-  std::mutex mu;
-  std::condition_variable cv;
-};
-
-// runs on a CUDA callback thread when the copy of a slice has left its ring slot
-static void CUDART_CB i8_slot_free(void* p) {
-  I8Sync* y = static_cast<I8Sync*>(p);
-  {
-    std::lock_guard<std::mutex> lk(y->mu);
-    y->allowed.fetch_add(1, std::memory_order_release);
-  }
-  y->cv.notify_all();
-}
-
 static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8Source& src, int64_t n_sites,
                                 int64_t n_tiles, const sai_job* jobs, int32_t n_jobs, uint32_t* d_mask_u,
                                 uint32_t* d_mask_q, double* d_qval, int64_t stride) {
@@ -240,31 +225,41 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
   std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[n_slices]);
   for (int64_t s = 0; s < n_slices; ++s) done[s].store(0);
   std::atomic<int> bad{0}, abort_flag{0};
-  I8Sync sync;
-  sync.allowed.store(kRing);
   uint8_t* ring = static_cast<uint8_t*>(e->ring);
   // Slices are handed to the GPU by whichever packer thread completes them (in slice order, under
   // issue_mu): no hand-off to a feeding thread, so no wake-up latency between "packed" and "on the
-  // wire".  Per slice: the copy, an event the genotype pass waits for, and a host callback behind
-  // the copy that returns the ring slot to the packers.
+  // wire", and nothing but copies in the copy stream (a host callback there would stall the next
+  // copy until a CPU is free to run it -- all of them are packing).  A ring slot is free again when
+  // the copy event of the slice that used it last has completed; the packers check that themselves
+  // (`slot_free`), which in the pack-bound steady state is a single relaxed load.
   std::mutex issue_mu;
-  int64_t next_issue = 0;  // guarded by issue_mu
-  int rc = SAI_OK;         // guarded by issue_mu
-  std::string err_msg;     // the failing thread's message (sai_last_error is thread-local)
+  int64_t next_issue = 0;          // guarded by issue_mu
+  std::atomic<int64_t> issued{0};  // == next_issue, readable without the lock
+  std::atomic<int64_t> freed{0};   // copies [0, freed) have left their ring slots
+  std::mutex free_mu;
+  int rc = SAI_OK;      // guarded by issue_mu
+  std::string err_msg;  // the failing thread's message (sai_last_error is thread-local)
   auto fail_locked = [&](int code) {
     if (rc == SAI_OK) {
       rc = code;
       err_msg = sai_last_error();
     }
     abort_flag.store(1);
-    std::lock_guard<std::mutex> lk(sync.mu);
-    sync.cv.notify_all();
+  };
+  auto slot_free = [&](int64_t s) {  // may slice s be packed into its ring slot?
+    if (s < kRing || freed.load(std::memory_order_acquire) > s - kRing) return true;
+    std::lock_guard<std::mutex> lk(free_mu);
+    int64_t f = freed.load(std::memory_order_relaxed);
+    // the event of slot f % kRing still belongs to slice f: slice f + kRing is not packed before f is freed
+    while (f < issued.load(std::memory_order_acquire) && cudaEventQuery(e->ev[f % kRing]) == cudaSuccess) ++f;
+    freed.store(f, std::memory_order_release);
+    return f > s - kRing;
   };
   auto issue_ready_slices = [&]() {
     std::lock_guard<std::mutex> lk(issue_mu);
     while (rc == SAI_OK && next_issue < n_slices &&
            done[next_issue].load(std::memory_order_acquire) == (int)blocks_of(next_issue)) {
-      const int64_t s = next_issue++;
+      const int64_t s = next_issue;
       if (bad.load()) {
         fail_locked(SAI_E_DOMAIN);
         break;
@@ -275,13 +270,14 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
                                        ring + (size_t)slot * slot_bytes, (size_t)(t1 - t0) * tile_bytes,
                                        cudaMemcpyHostToDevice, e->s_copy);
       if (ce == cudaSuccess) ce = cudaEventRecord(e->ev[slot], e->s_copy);
-      if (ce == cudaSuccess) ce = cudaLaunchHostFunc(e->s_copy, i8_slot_free, &sync);
       if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->s_comp, e->ev[slot], 0);
       if (ce != cudaSuccess) {
         set_error("int8 pipeline: CUDA call failed: %s", cudaGetErrorString(ce));
         fail_locked(SAI_E_CUDA);
         break;
       }
+      ++next_issue;
+      issued.store(next_issue, std::memory_order_release);
       if (int k = sai_site_flags(lay, e->packed.p, t0, t1 - t0, n_tiles, jobs, n_jobs, d_mask_u, d_mask_q, d_qval,
                                  stride, nullptr, nullptr, 0, 0, e->s_comp))
         fail_locked(k);
@@ -294,10 +290,8 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       const int64_t i = next_task.fetch_add(1);
       if (i >= n_tasks) break;
       const int64_t s = i / blocks_per_slice, b = i % blocks_per_slice;
-      if (s >= sync.allowed.load(std::memory_order_acquire)) {  // the slice's ring slot is still on the wire
-        std::unique_lock<std::mutex> lk(sync.mu);
-        sync.cv.wait(lk, [&] { return s < sync.allowed.load(std::memory_order_acquire) || abort_flag.load(); });
-      }
+      while (!slot_free(s) && !abort_flag.load())  // the slot's previous slice is still on the wire (rare:
+        std::this_thread::sleep_for(std::chrono::microseconds(50));  // the copy is faster than the packers)
       if (abort_flag.load()) break;
       const int64_t t0 = s * slice_tiles + b * block_tiles;
       const int64_t t1 = std::min(std::min(n_tiles, (s + 1) * slice_tiles), t0 + block_tiles);
@@ -310,8 +304,7 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
   for (int i = 0; i < n_threads; ++i) pool.emplace_back(worker);
   for (auto& t : pool) t.join();
   issue_ready_slices();  // nothing left unless a packer bailed out
-  // every queued callback refers to `sync` on this stack frame: drain the copy stream before leaving
-  const cudaError_t drained = cudaStreamSynchronize(e->s_copy);
+  const cudaError_t drained = cudaStreamSynchronize(e->s_copy);  // the ring may be reused by the next call
   if (rc == SAI_E_DOMAIN || (rc == SAI_OK && bad.load())) {
     set_error("a genotype value does not fit the bit-planes of its population");
     return SAI_E_DOMAIN;
