@@ -88,14 +88,34 @@ def score_populations(
             raise ValueError("The length of src_gts_list and src ploidies must match.")
         return pl
 
+    stat_order = [s for s in stat_config.root.keys() if s in stats or s in four or (dd and s == "DD")]
+    empty_cdd = np.array([])
+
     def emit(combo, windows, pos, res, j, four_vals, dd_vals):
+        """One item dict per window (feature_preprocessor.py:119-191).  A chromosome-scale chunk has
+        tens of thousands of windows, so the per-window work is kept to plain Python objects: the
+        result columns are turned into lists once and the candidate lists are views into one
+        converted array."""
         ref_pop, tgt_pop, src_comb, out_pop = combo
         n_src = len(src_comb)
+        out_name = "NA" if out_pop is None else out_pop
         pos_dtype = np.asarray(pos).dtype
+        if res is not None:
+            nsnps_l = res.nsnps[j].tolist()
+        else:
+            nsnps_l = [int(np.count_nonzero((pos >= s_) & (pos <= e_))) for s_, e_ in windows]
+        want_u, want_q = "U" in stats, "Q" in stats
+        if want_u:
+            u_l, us_l = res.u[j].tolist(), res.u_start[j].tolist()
+            u_cand = res.u_cand[j].astype(pos_dtype, copy=False)
+        if want_q:
+            q_col, qnan_l = res.q[j], np.isnan(res.q[j]).tolist()  # q_col[i] is a numpy.float64, like np.nanquantile's
+            qs_l, qc_l = res.q_start[j].tolist(), res.q_cnt[j].tolist()
+            q_cand = res.q_cand[j].astype(pos_dtype, copy=False)
+        nan_list = [np.nan for _ in range(n_src)] if n_src > 1 else np.nan
         for i, (start, end) in enumerate(windows):
-            nsnps = int(res.nsnps[j, i]) if res is not None else int(
-                np.count_nonzero((pos >= start) & (pos <= end))
-            )
+            nsnps = nsnps_l[i]
+            cdd = {}
             item = {
                 "chr_name": chr_name,
                 "start": start,
@@ -103,35 +123,32 @@ def score_populations(
                 "ref_pop": ref_pop,
                 "tgt_pop": tgt_pop,
                 "src_pop_list": src_comb,
-                "out_pop": "NA" if out_pop is None else out_pop,
+                "out_pop": out_name,
                 "nsnps": nsnps,
-                "cdd_pos": {},
+                "cdd_pos": cdd,
             }
-            for s in stat_config.root.keys():
-                if s in four or (dd and s == "DD"):
-                    if nsnps == 0:  # feature_preprocessor.py:137-141
-                        item[s] = [np.nan for _ in range(n_src)] if n_src > 1 else np.nan
-                    elif s == "DD":
-                        item[s] = [dd_vals[k][i] for k in range(n_src)]
-                    else:
-                        item[s] = [four_vals[s][k][i] for k in range(n_src)]
-                    continue
-                if s not in stats:
-                    continue
-                if nsnps == 0:  # empty window: feature_preprocessor.py:131-144
-                    item[s] = np.nan
-                    item["cdd_pos"][s] = np.array([])
-                elif s == "U":
-                    item[s] = int(res.u[j, i])
-                    item["cdd_pos"][s] = res.u_positions(j, i).astype(pos_dtype)
-                else:
-                    qv = res.q[j, i]
-                    if np.isnan(qv):  # q_statistic.py:96-98
+            for s in stat_order:
+                if s == "U":
+                    if nsnps == 0:  # empty window: feature_preprocessor.py:131-144
                         item[s] = np.nan
-                        item["cdd_pos"][s] = np.array([])
+                        cdd[s] = empty_cdd
                     else:
-                        item[s] = np.float64(qv)
-                        item["cdd_pos"][s] = res.q_positions(j, i).astype(pos_dtype)
+                        n = u_l[i]
+                        item[s] = n
+                        cdd[s] = u_cand[us_l[i] : us_l[i] + n]
+                elif s == "Q":
+                    if nsnps == 0 or qnan_l[i]:  # q_statistic.py:96-98
+                        item[s] = np.nan
+                        cdd[s] = empty_cdd
+                    else:
+                        item[s] = q_col[i]
+                        cdd[s] = q_cand[qs_l[i] : qs_l[i] + qc_l[i]]
+                elif nsnps == 0:  # feature_preprocessor.py:137-141
+                    item[s] = list(nan_list) if n_src > 1 else np.nan
+                elif s == "DD":
+                    item[s] = [dd_vals[k][i] for k in range(n_src)]
+                else:
+                    item[s] = [four_vals[s][k][i] for k in range(n_src)]
             items.append(item)
 
     def extras(pg, ref_idx, tgt_idx, src_idx, out_idx, n_ref, n_tgt, n_srcs):
@@ -221,31 +238,41 @@ def score_populations(
 
 def write_items(output_file: str, items: list[dict[str, Any]], stat_config) -> None:
     """Appends score rows and ``.U.log`` / ``.Q.log`` rows with the reference's
-    text layout (feature_preprocessor.py:193-258)."""
+    text layout (feature_preprocessor.py:193-258); lines are assembled in memory and written
+    with one call per file."""
     names = [s for s in stat_config.root.keys() if s in ("U", "Q") or stat_config.root[s] is True]
+    rows = []
+    for it in items:
+        parts = []
+        n_src = len(it["src_pop_list"])
+        for s in names:
+            v = it.get(s)
+            if isinstance(v, list) and len(v) == n_src:
+                parts.extend("" if x is None else str(x) for x in v)
+            else:
+                if isinstance(v, list):
+                    v = v[0] if v else ""
+                parts.append("" if v is None else str(v))
+        rows.append(
+            f"{it['chr_name']}\t{it['start']}\t{it['end']}\t{it['ref_pop']}\t{it['tgt_pop']}\t"
+            f"{','.join(it['src_pop_list'])}\t{it['out_pop']}\t{it['nsnps']}\t" + "\t".join(parts) + "\n"
+        )
     with open(output_file, "a") as f:
-        for it in items:
-            parts = []
-            for s in names:
-                v = it.get(s)
-                if isinstance(v, list) and len(v) == len(it["src_pop_list"]):
-                    parts.extend("" if x is None else str(x) for x in v)
-                else:
-                    if isinstance(v, list):
-                        v = v[0] if v else ""
-                    parts.append("" if v is None else str(v))
-            f.write(
-                f"{it['chr_name']}\t{it['start']}\t{it['end']}\t{it['ref_pop']}\t{it['tgt_pop']}\t"
-                f"{','.join(it['src_pop_list'])}\t{it['out_pop']}\t{it['nsnps']}\t" + "\t".join(parts) + "\n"
-            )
+        f.write("".join(rows))
     for key in ("U", "Q"):
         if key not in stat_config.root:
             continue
+        rows = []
+        for it in items:
+            c = it["cdd_pos"][key]
+            if c.size == 0:
+                txt = "NA"
+            else:
+                prefix = f"{it['chr_name']}:"
+                txt = ",".join([prefix + p for p in map(str, c.tolist())])
+            rows.append(f"{it['chr_name']}\t{it['start']}\t{it['end']}\t{txt}\n")
         with open(Path(output_file).with_suffix(f".{key}.log"), "a") as f:
-            for it in items:
-                c = it["cdd_pos"][key]
-                txt = "NA" if c.size == 0 else ",".join(f"{it['chr_name']}:{p}" for p in c)
-                f.write(f"{it['chr_name']}\t{it['start']}\t{it['end']}\t{txt}\n")
+            f.write("".join(rows))
 
 
 class ChunkPreprocessor:

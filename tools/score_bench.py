@@ -6,8 +6,8 @@
 Writes a synthetic bgzipped VCF (diploid, phased GT only; site frequencies ~ Beta(0.2, 2), 0.5 %
 introgressed sites), a config with U + Q (or all seven statistics), then times
 `sai_b200.score.score` (signature of sai.sai.score, sai/sai.py:33-151) end to end: chromosome
-scan, native VCF parse of every population, bit-plane packing, H2D + kernels + D2H, item dicts,
-TSV / .log writing.  Prints one JSON line with the phase breakdown (a GPU is required).
+scan, native VCF parse of every population, the int8 pipeline (pack | H2D | kernels) + D2H, item
+dicts, TSV / .log writing.  Prints one JSON line with the phase breakdown (a GPU is required).
 """
 import argparse
 import json
@@ -82,10 +82,11 @@ def main():
         score_mod.score(vcf_path, "1", 50000, 10000, anc, out, cfg, 1)  # warm-up: CUDA context, page cache
         tm = Timer()
         score_mod.ChunkGenerator = tm.wrap("chromosome_scan", score_mod.ChunkGenerator)
-        vcf_read, pack, eng = vcf.read_data, preprocessors.pack_populations, preprocessors.HostEngine.score
-        vcf.read_data = tm.wrap("vcf_parse", vcf_read)
-        preprocessors.pack_populations = tm.wrap("pack", pack)
-        preprocessors.HostEngine.score = tm.wrap("gpu_score_host", eng)
+        vcf.read_data = tm.wrap("vcf_parse", vcf.read_data)
+        # int8 matrices -> host pack | copy | kernels (pipelined) -> host results
+        preprocessors.HostEngine.score_matrices = tm.wrap("gpu_score_matrices", preprocessors.HostEngine.score_matrices)
+        preprocessors.HostEngine.pattern_sums = tm.wrap("gpu_pattern_sums", preprocessors.HostEngine.pattern_sums)
+        preprocessors.HostEngine.dd_sums = tm.wrap("gpu_dd_sums", preprocessors.HostEngine.dd_sums)
         preprocessors.write_items = tm.wrap("write_tsv_logs", preprocessors.write_items)
         t0 = time.perf_counter()
         score_mod.score(vcf_path, "1", 50000, 10000, anc, out, cfg, 1)
