@@ -26,7 +26,11 @@
  *
  *  - An individual's value v (sum of its alleles; any v < 0 = missing call) is
  *    stored in `bits` = B bit-planes as the binary code of v; the all-ones code
- *    (2^B - 1) means missing.  B = 2 covers haploid/diploid data (0,1,2,missing).
+ *    (2^B - 1) means missing.  B = 2 covers haploid/diploid data (0,1,2,missing); B up to 8
+ *    holds every int8 value (multi-allelic GT indices are not recoded by the reference, and a
+ *    flipped missing allele counts 2: sai/utils/utils.py:119-135, :555).  The genotype pass is
+ *    at the HBM roofline for B = 2..4; B = 5..8 take a plain per-word path, and DD
+ *    (sai_site_hist / sai_window_dd) is limited to B <= 4.
  *  - 32 individuals of one population form a *group*: B consecutive 32-bit
  *    words (plane 0 .. plane B-1), bit i of a word = individual 32*g + i.
  *    Unused individuals of the last group are coded missing.
@@ -53,6 +57,7 @@ extern "C" {
 #define SAI_MAX_SRC 8    /* source populations of one job             */
 #define SAI_MAX_JOBS 8   /* (ref,tgt) jobs fused into one genotype pass */
 #define SAI_TILE_SITES 32
+#define SAI_MAX_BITS 8    /* bit-planes per population: values 0..254, i.e. all of int8 */
 
 enum {
   SAI_OK = 0,
@@ -70,7 +75,7 @@ enum { SAI_OP_EQ = 0, SAI_OP_LT = 1, SAI_OP_GT = 2, SAI_OP_LE = 3, SAI_OP_GE = 4
 typedef struct {
   int32_t n_samples; /* individuals in the population                     */
   int32_t ploidy;    /* configured ploidy: frequency denominator factor   */
-  int32_t bits;      /* bit-planes B (2..4)                               */
+  int32_t bits;      /* bit-planes B (2..SAI_MAX_BITS)                    */
   int32_t pair_off;  /* first pair of this population in a site column    */
   int32_t n_pairs;   /* pairs owned by this population                    */
   int32_t n_groups;  /* ceil(n_samples / 32)                              */

@@ -81,7 +81,7 @@ int validate_layout(const sai_layout* lay) {
     const sai_pop_layout& L = lay->pop[p];
     SAI_REQUIRE(L.n_samples >= 1, "population %d has no samples", p);
     SAI_REQUIRE(L.ploidy >= 1, "ploidy must be a positive integer.");
-    SAI_REQUIRE(L.bits >= 2 && L.bits <= 4, "population %d: bits %d outside [2,4]", p, L.bits);
+    SAI_REQUIRE(L.bits >= 2 && L.bits <= SAI_MAX_BITS, "population %d: bits %d outside [2,%d]", p, L.bits, SAI_MAX_BITS);
     SAI_REQUIRE(L.n_groups == (L.n_samples + 31) / 32, "population %d: bad n_groups", p);
     SAI_REQUIRE(L.n_pairs == (L.n_groups * L.bits + 1) / 2, "population %d: bad n_pairs", p);
     SAI_REQUIRE(L.pair_off == at, "population %d: bad pair_off", p);
@@ -150,7 +150,7 @@ int sai_layout_init(sai_layout* lay, int32_t n_pops, const int32_t* n_samples,
     L.n_samples = n_samples[p];
     L.ploidy = ploidy[p];
     L.bits = (bits && bits[p] > 0) ? bits[p] : sai_bits_for_max_value(ploidy[p]);
-    SAI_REQUIRE(L.bits >= 2 && L.bits <= 4, "population %d needs %d bit-planes (max 4)", p, L.bits);
+    SAI_REQUIRE(L.bits >= 2 && L.bits <= SAI_MAX_BITS, "population %d needs %d bit-planes (max %d)", p, L.bits, SAI_MAX_BITS);
     L.n_groups = (L.n_samples + 31) / 32;
     L.n_pairs = (L.n_groups * L.bits + 1) / 2;
     L.pair_off = at;
@@ -328,7 +328,7 @@ int sai_unpack_i8(const sai_layout* lay, int32_t pop, const uint8_t* packed, int
     const int s = (int)(site % kTile);
     int8_t* row = gt + (site - site0) * row_stride;
     for (int g = 0; g < L.n_groups; ++g) {
-      uint32_t plane[4] = {0, 0, 0, 0};
+      uint32_t plane[SAI_MAX_BITS] = {0};
       for (int b = 0; b < B; ++b)
         plane[b] = *word_ptr(lay, L, const_cast<uint8_t*>(packed), T, s, g * B + b);
       const int i0 = g * 32;

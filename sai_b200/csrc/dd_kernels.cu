@@ -433,6 +433,7 @@ extern "C" int sai_site_hist(const sai_layout* lay, const void* d_packed, int64_
   for (int q = 0; q < n_hist_pops; ++q) {
     SAI_REQUIRE(pops[q] >= 0 && pops[q] < lay->n_pops, "bad population index");
     const sai_pop_layout& L = lay->pop[pops[q]];
+    SAI_REQUIRE(L.bits <= 4, "DD supports per-individual values up to 14 (population %d has %d bit-planes)", pops[q], L.bits);
     P.pair_off[q] = L.pair_off;
     P.n_groups[q] = L.n_groups;
     P.bits[q] = L.bits;
@@ -469,6 +470,10 @@ extern "C" int sai_window_dd(const sai_layout* lay, const void* d_packed, const 
   SAI_REQUIRE(neg_off[0] == 0, "neg_off[0] must be 0");
   for (int p = 0; p < lay->n_pops; ++p) SAI_REQUIRE(neg_off[p + 1] >= neg_off[p], "neg_off must be non-decreasing");
   SAI_REQUIRE(neg_off[lay->n_pops] == 0 || (d_neg_site && d_neg_ind && d_neg_val), "NULL negative-value table");
+  for (int k = 0; k < n_src; ++k)
+    SAI_REQUIRE(src_pops[k] >= 0 && src_pops[k] < lay->n_pops && lay->pop[src_pops[k]].bits <= 4,
+                "DD supports per-individual values up to 14");
+  SAI_REQUIRE(lay->pop[ref_pop].bits <= 4 && lay->pop[tgt_pop].bits <= 4, "DD supports per-individual values up to 14");
   auto fill = [&](DdPop& d, int pop, int32_t code_base) {
     const sai_pop_layout& L = lay->pop[pop];
     d.pair_off = L.pair_off;

@@ -53,7 +53,8 @@ bool row_portable(const int8_t* row, int n, int n_groups, int B, uint32_t* words
       const uint64_t negm = ((x >> 7) & ones) * 0xffull;  // 0xff in every negative byte
       const uint64_t val = x & ~negm;
       // a called value must be < miss_code: byte + (128 - miss_code) sets bit 7 otherwise
-      bad |= (((val + ones * (uint64_t)(128 - miss_code)) | val) & (ones << 7)) != 0;
+      // (8 planes hold every non-negative int8)
+      if (miss_code < 128) bad |= (((val + ones * (uint64_t)(128 - miss_code)) | val) & (ones << 7)) != 0;
       const uint64_t code = val | (negm & (ones * (uint64_t)miss_code));
       for (int b = 0; b < B; ++b)
         plane[b] |= (uint32_t)((((code >> b) & ones) * 0x0102040810204080ull) >> 56) << (8 * q);
@@ -66,19 +67,23 @@ bool row_portable(const int8_t* row, int n, int n_groups, int B, uint32_t* words
 // SSE2 is part of x86-64: 16 individuals per instruction group, two per 32-individual group.
 // (The B200 boxes' virtual CPUs expose AVX but neither AVX2 nor AVX-512: this is their path.)
 bool row_sse2(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
-  const __m128i lim = _mm_set1_epi8((char)((1 << B) - 2));  // largest called value
+  const __m128i lim = _mm_set1_epi8((char)std::min((1 << B) - 2, 127));  // largest called value
   __m128i bad = _mm_setzero_si128();
-  auto half = [&](__m128i v, uint32_t (&p)[4]) {
+  auto half = [&](__m128i v, uint32_t (&p)[SAI_MAX_BITS]) {
     const uint32_t neg = (uint32_t)_mm_movemask_epi8(v);  // sign bits: missing calls
     bad = _mm_or_si128(bad, _mm_cmpgt_epi8(v, lim));
     p[0] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 7)) | neg;
     p[1] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 6)) | neg;
     if (B > 2) p[2] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 5)) | neg;
     if (B > 3) p[3] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 4)) | neg;
+    if (B > 4) p[4] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 3)) | neg;
+    if (B > 5) p[5] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 2)) | neg;
+    if (B > 6) p[6] = (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(v, 1)) | neg;
+    if (B > 7) p[7] = neg;  // bit 7 of a called value is never set: the plane is the missing mask
   };
   const int full = n / 32;
   for (int g = 0; g < full; ++g) {
-    uint32_t lo[4], hi[4];
+    uint32_t lo[SAI_MAX_BITS], hi[SAI_MAX_BITS];
     half(_mm_loadu_si128((const __m128i*)(row + 32 * g)), lo);
     half(_mm_loadu_si128((const __m128i*)(row + 32 * g + 16)), hi);
     for (int b = 0; b < B; ++b) words[(size_t)g * B + b] = lo[b] | (hi[b] << 16);
@@ -87,7 +92,7 @@ bool row_sse2(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
     alignas(16) int8_t tail[32];
     memset(tail, 0xff, sizeof(tail));
     memcpy(tail, row + 32 * full, n - 32 * full);
-    uint32_t lo[4], hi[4];
+    uint32_t lo[SAI_MAX_BITS], hi[SAI_MAX_BITS];
     half(_mm_load_si128((const __m128i*)tail), lo);
     half(_mm_load_si128((const __m128i*)(tail + 16)), hi);
     for (int b = 0; b < B; ++b) words[(size_t)full * B + b] = lo[b] | (hi[b] << 16);
@@ -99,7 +104,7 @@ bool row_sse2(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
 #pragma GCC push_options
 #pragma GCC target("avx2")
 bool row_avx2(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
-  const __m256i lim = _mm256_set1_epi8((char)((1 << B) - 2));  // largest called value
+  const __m256i lim = _mm256_set1_epi8((char)std::min((1 << B) - 2, 127));  // largest called value
   __m256i bad = _mm256_setzero_si256();
   const int full = n / 32;
   auto group = [&](__m256i v, uint32_t* plane) {
@@ -110,6 +115,10 @@ bool row_avx2(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
     plane[1] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6)) | neg;
     if (B > 2) plane[2] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5)) | neg;
     if (B > 3) plane[3] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 4)) | neg;
+    if (B > 4) plane[4] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 3)) | neg;
+    if (B > 5) plane[5] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 2)) | neg;
+    if (B > 6) plane[6] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 1)) | neg;
+    if (B > 7) plane[7] = neg;  // bit 7 of a called value is never set: the plane is the missing mask
   };
   for (int g = 0; g < full; ++g) group(_mm256_loadu_si256((const __m256i*)(row + 32 * g)), words + (size_t)g * B);
   if (full < n_groups) {
@@ -126,17 +135,18 @@ bool row_avx2(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
 #pragma GCC push_options
 #pragma GCC target("avx512f,avx512bw")
 bool row_avx512(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
-  const __m512i lim = _mm512_set1_epi8((char)((1 << B) - 2));
+  const __m512i lim = _mm512_set1_epi8((char)std::min((1 << B) - 2, 127));
   __mmask64 bad = 0;
   const __m512i bit0 = _mm512_set1_epi8(1), bit1 = _mm512_set1_epi8(2), bit2 = _mm512_set1_epi8(4), bit3 = _mm512_set1_epi8(8);
   auto pair = [&](__m512i v, int g, int groups_here) {  // 64 individuals = groups g and g + 1
     const uint64_t neg = _mm512_movepi8_mask(v);
     bad |= _mm512_cmpgt_epi8_mask(v, lim);
-    uint64_t p[4];
+    uint64_t p[SAI_MAX_BITS];
     p[0] = _mm512_test_epi8_mask(v, bit0) | neg;
     p[1] = _mm512_test_epi8_mask(v, bit1) | neg;
     if (B > 2) p[2] = _mm512_test_epi8_mask(v, bit2) | neg;
     if (B > 3) p[3] = _mm512_test_epi8_mask(v, bit3) | neg;
+    for (int b = 4; b < B; ++b) p[b] = _mm512_test_epi8_mask(v, _mm512_set1_epi8((char)(1 << b))) | neg;
     for (int h = 0; h < groups_here; ++h)
       for (int b = 0; b < B; ++b) words[(size_t)(g + h) * B + b] = (uint32_t)(p[b] >> (32 * h));
   };

@@ -151,6 +151,29 @@ __device__ __forceinline__ void count_b3(const uint2* __restrict__ col, int n_gr
   miss = am;
 }
 
+// B = 5..8 (per-individual values above 14: multi-allelic genotype indices >= 8): plain per-word
+// path, the planes of a group back to back.  Correct for any B; not tuned -- such data is rare.
+__device__ __forceinline__ void count_wide(const uint2* __restrict__ col, int n_groups, int B, int& num, int& miss) {
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(col);
+  const int all = (1 << B) - 1;
+  int acc = 0, accm = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    uint32_t andw = 0xffffffffu;
+    int s = 0;
+    for (int b = 0; b < B; ++b) {
+      const int word = g * B + b;  // word w of this lane: pair (w >> 1) is 32 lanes * 2 words further on
+      const uint32_t x = __ldg(base + (size_t)(word >> 1) * (kTile * 2) + (word & 1));
+      s += __popc(x) << b;
+      andw &= x;
+    }
+    const int m = __popc(andw);
+    acc += s - all * m;
+    accm += m;
+  }
+  num = acc;
+  miss = accm;
+}
+
 // ---- host side of the integer fast path (site_cond.cuh) ----------------------------
 namespace {
 // first n in [0, d + 1] for which pred(n) holds; pred must be monotone (false ... false true ... true)
@@ -247,8 +270,10 @@ __global__ void __launch_bounds__(kSiteWarps * 32, MODE == 1 ? 3 : 4)
         count_b2<MODE>(col, L.n_pairs, num, miss);
       else if (L.bits == 4)
         count_b4(col, L.n_groups, num, miss);
-      else
+      else if (L.bits == 3)
         count_b3(col, L.n_groups, num, miss);
+      else
+        count_wide(col, L.n_groups, L.bits, num, miss);
       const int called = L.n_groups * 32 - miss;
       s_num[pi * kTile + lane] = num;
       s_cal[pi * kTile + lane] = called;

@@ -93,9 +93,11 @@ def _as_i8(gt: np.ndarray) -> np.ndarray:
         raise ValueError("genotype matrix must be 2-D (sites x individuals)")
     if gt.dtype == np.int8 and (gt.flags.c_contiguous or (gt.strides[1] == 1 and gt.strides[0] >= gt.shape[1])):
         return gt  # row-strided views (column blocks of one parsed matrix) are packed in place
-    # negative = missing (any negative value, sai/stats/stat_utils.py:45); large
-    # values are clipped to 127 and rejected by the packer's domain check
-    return np.ascontiguousarray(np.clip(gt, -1, 127).astype(np.int8))
+    # negative = missing (any negative value, sai/stats/stat_utils.py:45).  8 bit-planes hold every
+    # non-negative int8; a per-individual allele sum above 127 has no encoding
+    if gt.size and int(gt.max()) > 127:
+        raise ValueError("per-individual allele sums above 127 are not supported by the packed layout")
+    return np.ascontiguousarray(np.maximum(gt, -1).astype(np.int8))
 
 
 def bits_for(gt: np.ndarray, ploidy: int) -> int:

@@ -724,7 +724,7 @@ def test_empty_items_carry_the_outgroup(tmp_path):
     assert all(np.isnan(it["U"]) and np.isnan(it["fd"]) and it["nsnps"] == 0 for it in items)
 
 
-@pytest.mark.parametrize("bits, vmax", [(2, 2), (3, 6), (4, 14)])
+@pytest.mark.parametrize("bits, vmax", [(2, 2), (3, 6), (4, 14), (5, 30), (7, 126), (8, 127)])
 def test_packer_vector_paths_are_identical(bits, vmax):
     """Portable, SSE2, AVX2 and AVX-512 row packers (whichever this CPU has) write the same bytes,
     for full and partial 32-/64-individual groups, row-strided views and padding sites, and all
@@ -753,6 +753,8 @@ def test_packer_vector_paths_are_identical(bits, vmax):
         outs.append(out)
     for o in outs[1:]:
         assert np.array_equal(o, outs[0])
+    if bits == 8:
+        return  # every non-negative int8 fits 8 planes
     bad = whole.copy()
     bad[17, 70] = vmax + 1  # population 3 holds columns 64..96
     for isa in (1, 2, 3, 4):

@@ -337,3 +337,41 @@ def test_integer_fast_path_thresholds(engine):
                         assert res.q[j, i] == float(eq["value"]), (j, i, qd, anc, combos[i])
                     checked += 1
     assert checked == 2 * 6 * 8 * len(combos)
+
+
+@pytest.mark.gpu
+def test_multiallelic_values_above_14_score_like_the_oracle():
+    """Multi-allelic genotype indices are not recoded by the reference (alt_number=1 only limits
+    ALT, utils.py:119-135), so a diploid sum can exceed 14: the layout widens to 5..8 planes and
+    U / Q / candidate lists stay identical to the oracle (most such sites are simply invalid:
+    frequency above 1)."""
+    from sai_b200.scoring import HostEngine, make_job
+    from sai_b200.windows import split_genome
+
+    rng = np.random.default_rng(77)
+    n_sites = 3000
+    f = rng.beta(0.3, 1.5, size=n_sites)
+    mats = [rng.binomial(2, f[:, None], size=(n_sites, n)).astype(np.int8) for n in (60, 45, 3)]
+    mats[2][rng.random(n_sites) < 0.3] = 2
+    for m, vmax in zip(mats, (16, 40, 127)):  # a few multi-allelic calls per population
+        hit = rng.random(m.shape) < 0.003
+        m[hit] = rng.integers(3, vmax + 1, size=int(hit.sum()))
+    mats[0][rng.random(mats[0].shape) < 0.02] = -1
+    pos = np.cumsum(rng.integers(1, 60, size=n_sites)).astype(np.int32)
+    wins = split_genome([int(pos[0]), int(pos[-1])], 20_000, 5_000)
+    u_kw = dict(w=0.5, x=0.2, y_list=[(">=", 0.5)])
+    q_kw = dict(w=0.5, quantile=0.9, y_list=[(">=", 0.5)])
+    eng = HostEngine(0)
+    got, mg = eng.score_matrices(mats, [2, 2, 2], pos, wins, [make_job(0, 1, [2], False, u=u_kw, q=q_kw)])
+    eng.close()
+    assert [mg.layout.pop[i].bits for i in range(3)] == [5, 6, 8]
+    m64 = [m.astype(np.int64) for m in mats]
+    for i, (s, e) in enumerate(wins):
+        keep = (pos >= s) & (pos <= e)
+        eu = orc.u_statistic(m64[0][keep], m64[1][keep], [m64[2][keep]], 2, 2, [2], pos=pos[keep], anc_allele_available=False, **u_kw)
+        eq = orc.q_statistic(m64[0][keep], m64[1][keep], [m64[2][keep]], 2, 2, [2], pos=pos[keep], anc_allele_available=False, **q_kw)
+        assert got.nsnps[0, i] == keep.sum() and got.u[0, i] == eu["value"]
+        assert np.array_equal(got.u_positions(0, i), eu["cdd_pos"])
+        assert (np.isnan(got.q[0, i]) and np.isnan(eq["value"])) or got.q[0, i] == float(eq["value"])
+        assert np.array_equal(got.q_positions(0, i), np.asarray(eq["cdd_pos"], dtype=np.int32))
+    assert int(got.u.sum()) > 0

@@ -489,13 +489,13 @@ def test_sharded_equals_unsharded_gpu(engine):
 
 
 # ---------------------------------------------------------------- K1 alone
-@pytest.mark.parametrize("ploidy", [[2, 1, 4], [4, 8, 6], [3, 12, 2], [14, 5, 7]])
+@pytest.mark.parametrize("ploidy", [[2, 1, 4], [4, 8, 6], [3, 12, 2], [14, 5, 7], [30, 127, 60]])
 @pytest.mark.parametrize("shape", [(1, [1, 1, 1]), (33, [5, 40, 2]), (1000, [257, 96, 3]), (4097, [1500, 1000, 4]),
                                    (300, [20000, 8, 1]), (2500, [256, 512, 129]), (700, [97, 1120, 1185])])
 def test_site_counts_vs_oracle(ploidy, shape):
-    """Counts of every population against calc_freq's numerator / called count for 2-, 3- and
-    4-plane populations (ploidy 1..14), with group counts that exercise the carry-save batches
-    (8 pairs / 4 groups) and their remainders."""
+    """Counts of every population against calc_freq's numerator / called count for 2- to 8-plane
+    populations (values up to 127: all of int8), with group counts that exercise the carry-save
+    batches (8 pairs / 4 groups) and their remainders."""
     import torch
 
     from sai_b200.encode import pack_populations
@@ -510,7 +510,7 @@ def test_site_counts_vs_oracle(ploidy, shape):
         g[rng.random(n_sites) < 0.05] = -2  # whole population missing at some sites
         mats.append(g)
     pg = pack_populations(mats, ploidy, np.arange(n_sites))
-    want_bits = [2 if p <= 2 else 3 if p <= 6 else 4 for p in ploidy]
+    want_bits = [next(b for b in range(2, 9) if (1 << b) - 1 > p) for p in ploidy]  # 2..8 planes
     assert [pg.layout.pop[i].bits for i in range(3)] == want_bits
     sc = DeviceScorer(pg.layout, n_sites, 0, 1)
     d_packed = torch.from_numpy(pg.packed).cuda()
