@@ -278,9 +278,16 @@ def cpu_reference_setup(wl, sample_sites: int, seed: int):
     ploidies = {"ref": {"REF": 2}, "tgt": {"TGT": 2}, "src": {"SRC": 2}}
     stats = {"U": {"ref": {"REF": wl["w"]}, "tgt": {"TGT": wl["x"]}, "src": {"SRC": ystr}},
              "Q": {"ref": {"REF": wl["w"]}, "tgt": {"TGT": wl["quantile"]}, "src": {"SRC": ystr}}}
+    kind, why_port = "port", "oracle/_ref absent"
+    if ref_driver.available():
+        try:
+            ref_driver.make_classes()  # imports the installed reference behind the three stubs
+            kind, why_port = "reference", None
+        except Exception as e:  # e.g. a dependency of the reference missing on this box: keep the bench line alive
+            why_port = f"oracle/_ref not importable: {type(e).__name__}: {e}"
     _CPU.update(pos=pos, ref={"REF": mats[0]}, tgt={"TGT": mats[1]}, src={"SRC": mats[2]},
                 win_len=wl["win_len"], win_step=wl["win_step"], anc=wl["anc"], ploidies=ploidies, stats=stats,
-                kind="reference" if ref_driver.available() else "port")
+                kind=kind, why_port=why_port)
     if _CPU["kind"] == "reference":
         ref_driver.set_data("bench", pos, _CPU["ref"], _CPU["tgt"], _CPU["src"])
     else:
@@ -329,7 +336,7 @@ def cpu_sample_text(n_windows, sample_sites, cores):
         how = ("the unmodified reference (oracle/_ref: WindowGenerator + FeaturePreprocessor.run) under its own "
                f"sai.multiprocessing.mp_pool, {cores} processes")
     else:
-        how = f"oracle/sai_oracle.py (numpy port; oracle/_ref absent) over a {cores}-process fork pool"
+        how = f"oracle/sai_oracle.py (numpy port; {_CPU.get('why_port')}) over a {cores}-process fork pool"
     return (f"first {n_windows} windows ({sample_sites} sites decoded to int64) of the same workload, {how}, "
             f"8 window-range chunks per worker")
 
