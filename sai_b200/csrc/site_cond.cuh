@@ -148,43 +148,32 @@ __device__ __forceinline__ SiteFlags eval_site_fast(const JobFast& F, const sai_
   const int nt = num_of(J.tgt_pop), dt = called_of(J.tgt_pop) * lay.pop[J.tgt_pop].ploidy;
   bool full = F.ok != 0 && dr == F.den_ref && dt == F.den_tgt;
   bool valid = nr <= dr && nt <= dt;
-  int ns[SAI_MAX_SRC];
-#pragma unroll
-  for (int k = 0; k < SAI_MAX_SRC; ++k) {
-    if (k < J.n_src) {
-      const int sp = J.src_pop[k];
-      ns[k] = num_of(sp);
-      const int ds = called_of(sp) * lay.pop[sp].ploidy;
-      full = full && ds == F.den_src[k];
-      valid = valid && ns[k] <= ds;
-    } else {
-      ns[k] = 0;
-    }
+  // one pass over the sources (n_src is warp-uniform: a plain loop, no per-source arrays): the
+  // interval tests of both condition blocks against y and against 1 - y
+  bool my_u = true, mf_u = true, my_q = true, mf_q = true;
+  for (int k = 0; k < J.n_src; ++k) {
+    const int sp = J.src_pop[k];
+    const int ns = num_of(sp);
+    const int ds = called_of(sp) * lay.pop[sp].ploidy;
+    full = full && ds == F.den_src[k];
+    valid = valid && ns <= ds;
+    my_u = my_u && ns >= F.u.y_lo[k] && ns <= F.u.y_hi[k];
+    mf_u = mf_u && ns >= F.u.f_lo[k] && ns <= F.u.f_hi[k];
+    my_q = my_q && ns >= F.q.y_lo[k] && ns <= F.q.y_hi[k];
+    mf_q = mf_q && ns >= F.q.f_lo[k] && ns <= F.q.f_hi[k];
   }
   // warp-uniform choice: a tile with a missing call anywhere takes the division path
   if (!__all_sync(0xffffffffu, full)) return eval_site(J, lay, num_of, called_of);
   SiteFlags out{false, false, 0.0};
   const bool anc = J.anc_allele_available != 0;
-  auto cond = [&](const CondFast& C, bool& inv) {
-    bool my = true, mf = true;
-#pragma unroll
-    for (int k = 0; k < SAI_MAX_SRC; ++k) {
-      if (k < J.n_src) {
-        my = my && ns[k] >= C.y_lo[k] && ns[k] <= C.y_hi[k];
-        mf = mf && ns[k] >= C.f_lo[k] && ns[k] <= C.f_hi[k];
-      }
-    }
-    inv = !anc && mf;
-    return valid && (my || inv) && (inv ? nr >= C.ref_inv_min : nr <= C.ref_max);
-  };
   if (J.u.enabled) {
-    bool inv;
-    const bool c = cond(F.u, inv);
+    const bool inv = !anc && mf_u;
+    const bool c = valid && (my_u || inv) && (inv ? nr >= F.u.ref_inv_min : nr <= F.u.ref_max);
     out.u = c && (inv ? nt <= F.tgt_inv_max : nt >= F.tgt_min);
   }
   if (J.q.enabled) {
-    bool inv;
-    const bool c = cond(F.q, inv);
+    const bool inv = !anc && mf_q;
+    const bool c = valid && (my_q || inv) && (inv ? nr >= F.q.ref_inv_min : nr <= F.q.ref_max);
     out.q = c;
     if (c) {
       const double ft = site_freq(nt, dt);

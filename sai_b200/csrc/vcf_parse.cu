@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "vcf_simd.h"
 
 namespace sai {
 
@@ -219,6 +220,7 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
 
   // ---- pass 2 (parallel over records): walk the sample columns ----
   auto work = [&](int64_t r0, int64_t r1) {
+    std::vector<int8_t> a0, a1, sum2;  // alleles (and diploid sums) of every field of a regular record (vcf_simd.cpp)
     for (int64_t r = r0; r < r1; ++r) {
       const KeptLine& K = kept[r];
       out_pos[r] = K.pos;
@@ -226,6 +228,53 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
       const void* nl = memchr(K.samples, '\n', (size_t)(tend - K.samples));
       const char* lend = nl ? static_cast<const char*>(nl) : tend;
       if (lend > K.samples && lend[-1] == '\r') --lend;
+      // Regular diploid record (every field `x|y` / `x/y`): all fields are converted 16 at a time,
+      // then the requested columns are picked with their own ploidy -- cut / padded with missing
+      // alleles and flipped exactly like gt_sum does field by field.
+      if (K.gt_index == 0) {
+        const int64_t max_fields = (lend - K.samples + 1) / 4 + 1;
+        if ((int64_t)a0.size() < max_fields) {
+          a0.resize(max_fields);
+          a1.resize(max_fields);
+          sum2.resize(max_fields);
+        }
+        int64_t nf = 0;
+        if (vcf_regular_diploid(K.samples, lend, a0.data(), a1.data(), (int64_t)a0.size(), &nf)) {
+          // diploid requests (the common case): the sums of all fields in one vectorisable sweep,
+          // then one byte move per requested column
+          int8_t* s2 = sum2.data();
+          const int8_t *p0 = a0.data(), *p1 = a1.data();
+          if (K.flip) {  // |a - 1| on every allele (utils.py:555)
+            for (int64_t i = 0; i < nf; ++i) {
+              const int x0 = p0[i], x1 = p1[i];
+              s2[i] = (int8_t)((x0 > 0 ? x0 - 1 : 1 - x0) + (x1 > 0 ? x1 - 1 : 1 - x1));
+            }
+          } else {
+            for (int64_t i = 0; i < nf; ++i) s2[i] = (int8_t)(p0[i] + p1[i]);
+          }
+          for (int o = 0; o < n_out; ++o) {
+            const int col = sample_column[o], ploidy = sample_ploidy[o];
+            if (col >= nf) {
+              row[o] = (int8_t)(-ploidy);  // column absent: all alleles missing
+              continue;
+            }
+            if (ploidy == 2) {
+              row[o] = s2[col];
+              continue;
+            }
+            int x0 = p0[col], x1 = ploidy >= 2 ? p1[col] : 0;
+            int rest = ploidy > 2 ? ploidy - 2 : 0;  // alleles beyond the field: missing (-1)
+            if (K.flip) {
+              x0 = x0 > 0 ? x0 - 1 : 1 - x0;
+              if (ploidy >= 2) x1 = x1 > 0 ? x1 - 1 : 1 - x1;
+              rest *= -2;
+            }
+            const int sum = x0 + x1 - rest;
+            row[o] = (int8_t)(sum < -128 ? -128 : (sum > 127 ? 127 : sum));
+          }
+          continue;
+        }
+      }
       const char* f = K.samples;  // start of sample column `col`
       const char* fe = nullptr;   // end of the field at f (its tab or lend) when already known
       int col = 0;

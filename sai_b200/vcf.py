@@ -732,6 +732,8 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
         return None
     if not pos_parts:
         return np.empty(0, dtype=np.int32), np.empty((0, n_out), dtype=np.int8)
+    if len(pos_parts) == 1:  # the usual case (one mapped text file / one batch): no second copy of the matrix
+        return pos_parts[0], gt_parts[0]
     return np.concatenate(pos_parts), np.concatenate(gt_parts)
 
 

@@ -805,3 +805,70 @@ def test_shard_genome_follows_split_windows_ranges():
                 lo_a, hi_a = piece_site_range(pos, w, p)
                 assert lo_a % 32 == 0 and lo - 31 <= lo_a <= lo and hi_a == max(hi, lo_a)
     assert shard_genome([[]], 3) == [[], [], []]
+
+
+@pytest.mark.parametrize("crlf, final_newline", [(False, True), (True, True), (False, False)])
+def test_regular_record_fast_path_matches_python_reader(tmp_path, crlf, final_newline):
+    """Records whose sample fields are all `x|y` / `x/y` take the vector fast path of the native
+    parser (16 fields per AVX-512 step); records with anything else in them (a two-digit allele, a
+    haploid or triploid field, GT:DP) fall back to the field walker.  Both must give exactly what
+    the pure-Python reader gives: "." alleles, multi-allelic indices, requested ploidy 1 / 2 / 3 / 4
+    on diploid fields (cut or padded with missing), flipped records (|a - 1| on every allele, the
+    padded ones too), a sample requested by two populations, region reads."""
+    from sai_b200.configs import PloidyConfig
+    from sai_b200.vcf import read_data
+
+    rng = np.random.default_rng(5 + crlf + 2 * final_newline)
+    n_samples, n_sites = 131, 600  # 131 fields: eight full 16-field steps and a ragged tail
+    nl = "\r\n" if crlf else "\n"
+    lines = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n_samples))]
+    pos = np.cumsum(rng.integers(1, 50, size=n_sites))
+    bases = "ACGT"
+    recs, n_irregular = [], 0
+    for p in pos:
+        ref = bases[rng.integers(4)]
+        alt = bases[(bases.index(ref) + 1 + rng.integers(3)) % 4]
+        toks = []
+        for _ in range(n_samples):
+            a = [("." if rng.random() < 0.05 else str(int(rng.integers(0, 10 if rng.random() < 0.03 else 2)))) for _ in range(2)]
+            toks.append(a[0] + ("|" if rng.random() < 0.7 else "/") + a[1])
+        fmt = "GT"
+        kind = rng.random()
+        if kind < 0.04:
+            toks[int(rng.integers(n_samples))] = "10|1"  # two-digit allele
+        elif kind < 0.08:
+            toks[int(rng.integers(n_samples))] = "1"  # haploid field
+        elif kind < 0.12:
+            toks[int(rng.integers(n_samples))] = "0/1/1"
+        elif kind < 0.16:
+            fmt, toks = "GT:DP", [t + ":7" for t in toks]
+        n_irregular += kind < 0.16
+        lines.append("\t".join(["3", str(p), ".", ref, alt, ".", "PASS", ".", fmt] + toks))
+        recs.append((int(p), ref, alt))
+    assert 20 < n_irregular < 200
+    vcf = tmp_path / "reg.vcf"
+    open(vcf, "w", newline="").write(nl.join(lines) + (nl if final_newline else ""))
+    anc = tmp_path / "anc.bed"
+    with open(anc, "w") as f:
+        for p, ref, alt in recs:
+            r = rng.random()
+            if r < 0.1:
+                continue
+            f.write(f"3\t{p - 1}\t{p}\t{ref if r < 0.5 else (alt if r < 0.92 else 'N')}\n")
+    (tmp_path / "ref.list").write_text("".join(f"R1\ts{i}\n" for i in range(0, 70)) + "".join(f"R4\ts{i}\n" for i in range(60, 100)))
+    (tmp_path / "tgt.list").write_text("".join(f"T1\ts{i}\n" for i in range(90, 131)) + "T3\ts5\nT3\ts130\n")
+    (tmp_path / "src.list").write_text("S\ts0\nS\ts64\nS\ts129\n")
+    pc = PloidyConfig({"ref": {"R1": 2, "R4": 4}, "tgt": {"T1": 1, "T3": 3}, "src": {"S": 2}})
+    lists = [str(tmp_path / f"{g}.list") for g in ("ref", "tgt", "src")]
+    for anc_file in (None, str(anc)):
+        for region in ((None, None), (int(pos[50]), int(pos[500]))):
+            a = read_data(str(vcf), "3", pc, *lists, None, anc_file, start=region[0], end=region[1], native=True)
+            b = read_data(str(vcf), "3", pc, *lists, None, anc_file, start=region[0], end=region[1], native=False)
+            rows = 0
+            for g in ("ref", "tgt", "src"):
+                assert list(a[g][0]) == list(b[g][0])
+                for p in a[g][0]:
+                    assert np.array_equal(a[g][0][p].POS, b[g][0][p].POS), (g, p)
+                    assert np.array_equal(a[g][0][p].GT, b[g][0][p].GT), (g, p, anc_file, region)
+                    rows = a[g][0][p].POS.size
+            assert rows > 300
