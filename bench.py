@@ -659,7 +659,7 @@ def main():
             "matches_device_path": same_i8,
             "input": f"int8 per-individual allele sums, {h_i8.nbytes / 1e9:.2f} GB of pageable host memory per rank "
                      f"(the reference holds the same matrix as int64); packed on the fly by {host_threads} host threads "
-                     f"({_cabi.load().sai_pack_isa().decode()} row packer) into pinned 16 MB slices, pipelined with the copy and K1",
+                     f"({_cabi.load().sai_pack_isa().decode()} row packer) into pinned 32 MB slices, pipelined with the copy and K1",
             "host_threads": host_threads,
             "pack_alone_ms": 1e3 * t_pack, "pack_alone_gbps_int8": h_i8.nbytes / t_pack / 1e9, "pack_reproduces_device_tiles": pack_matches,
             "wire_alone_ms": 1e3 * t_dense,

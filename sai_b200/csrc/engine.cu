@@ -196,7 +196,8 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
   if (const char* v = getenv("SAI_I8_SLICE_MB")) slice_bytes = (uint64_t)std::max(1, atoi(v)) << 20;  // tools/ A/B knobs
   if (const char* v = getenv("SAI_I8_RING")) kRing = std::max(2, atoi(v));
 #endif
-  const int64_t slice_tiles = std::max<int64_t>(1, (int64_t)(slice_bytes / tile_bytes));
+  // a small chunk does not need (or pay for) the full ring: at most n_tiles / kRing tiles per slot
+  const int64_t slice_tiles = std::max<int64_t>(1, std::min<int64_t>((int64_t)(slice_bytes / tile_bytes), (n_tiles + kRing - 1) / kRing));
   const int64_t n_slices = (n_tiles + slice_tiles - 1) / slice_tiles;
   const size_t slot_bytes = (size_t)slice_tiles * tile_bytes;
   if (e->ring_cap < slot_bytes * kRing) {
