@@ -7,9 +7,9 @@
 // all_gather_into_tensor over NVLink; NaN = padding or a window without a value), so nothing is
 // copied or sorted on the host.  One 1024-thread block per column selects the order statistic
 // exactly by an MSB-first radix select over the order-preserving 64-bit image of the doubles
-// (sign-flipped, so negative statistics such as Danc / fd work too): 8 passes with a 256-bin
-// shared histogram, stopping as soon as one key is left.  Everything is exact: the result equals
-// what sorting the column gives.
+// (sign-flipped, so negative statistics such as Danc / fd work too): passes with a 256-bin shared
+// histogram over the L2-resident column until the selected bin fits shared memory, then the
+// remaining digits there.  Everything is exact: the result equals what sorting the column gives.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -40,15 +40,16 @@ __device__ __forceinline__ double key_value(unsigned long long k) {
 // f(key) for every non-NaN value of the column, spread over the block's threads
 template <typename F>
 __device__ __forceinline__ void for_each_key(const ColParams& P, int col, F f) {
+  constexpr int kInFlight = 8;  // independent loads per thread: the block is alone on its SM, latency is all there is
   for (int c = 0; c < P.n_chunks; ++c) {
     const double* p = P.vals + (size_t)c * P.chunk_stride + (size_t)col * P.col_stride;
     int64_t i = threadIdx.x;
-    for (; i + 3 * kQThreads < P.len; i += 4 * kQThreads) {  // four loads in flight per thread
-      double v[4];
+    for (; i + (kInFlight - 1) * kQThreads < P.len; i += kInFlight * kQThreads) {
+      double v[kInFlight];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(p + i + u * kQThreads);
+      for (int u = 0; u < kInFlight; ++u) v[u] = __ldg(p + i + u * kQThreads);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < kInFlight; ++u)
         if (v[u] == v[u]) f(ordered_key(v[u]));
     }
     for (; i < P.len; i += kQThreads) {
@@ -74,57 +75,82 @@ __device__ __forceinline__ unsigned long long block_min64(unsigned long long v, 
   return r;
 }
 
-// exact k-th smallest key (0-based); count_le = number of keys <= it
-__device__ unsigned long long block_radix_select(const ColParams& P, int col, long long k, int* s_hist,
-                                                 long long* s_bcast, unsigned long long* s_red, long long& count_le) {
+constexpr int kQCap = 4096;  // candidate keys kept in shared memory once the selected bin is that small
+
+struct SelectScratch {
+  int hist[256];
+  long long bcast[4];
+  unsigned long long red[kQThreads / 32];
+  unsigned long long keys[kQCap];
+  int n_keys;
+};
+
+// Exact k-th smallest key (0-based) by MSB-first radix select; count_le = number of keys <= it.
+// The passes read the column from L2 until the selected bin holds <= kQCap keys; those are then
+// gathered into shared memory once and the remaining digits are resolved there.  `n_cand` /
+// S.keys stay valid for the caller (the successor search): all keys that share the answer's
+// prefix down to the digit at which they were gathered.
+__device__ unsigned long long block_radix_select(const ColParams& P, int col, long long k, SelectScratch& S,
+                                                 long long& count_le, int& n_cand) {
   unsigned long long prefix = 0;
   long long kk = k, eq = 0;
+  bool in_smem = false;
+  int n_smem = 0;
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 56 - 8 * pass;
     __syncthreads();
-    if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x < 256) S.hist[threadIdx.x] = 0;
     __syncthreads();
-    for_each_key(P, col, [&](unsigned long long key) {
-      if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&s_hist[(int)((key >> shift) & 255ull)], 1);
-    });
+    auto count = [&](unsigned long long key) {
+      if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&S.hist[(int)((key >> shift) & 255ull)], 1);
+    };
+    if (in_smem) {
+      for (int i = threadIdx.x; i < n_smem; i += kQThreads) count(S.keys[i]);
+    } else {
+      for_each_key(P, col, count);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {  // 256 bins: a serial scan is cheaper than a block scan here
       long long run = 0;
       int bin = 255;
       for (int b = 0; b < 256; ++b) {
-        if (kk < run + s_hist[b]) {
+        if (kk < run + S.hist[b]) {
           bin = b;
           break;
         }
-        run += s_hist[b];
+        run += S.hist[b];
       }
-      s_bcast[0] = bin;
-      s_bcast[1] = run;
-      s_bcast[2] = s_hist[bin];
+      S.bcast[0] = bin;
+      S.bcast[1] = run;
+      S.bcast[2] = S.hist[bin];
     }
     __syncthreads();
-    const int bin = (int)s_bcast[0];
-    const long long below = s_bcast[1], cnt = s_bcast[2];
+    const int bin = (int)S.bcast[0];
+    const long long below = S.bcast[1], cnt = S.bcast[2];
     prefix |= (unsigned long long)bin << shift;
     kk -= below;
     eq = cnt;
-    if (cnt == 1 && pass < 7) {  // a single key carries this prefix: fetch it and stop
-      unsigned long long found = ~0ull;
+    if (!in_smem && cnt <= kQCap && pass < 7) {  // gather the bin's keys once; finish in shared memory
+      if (threadIdx.x == 0) S.n_keys = 0;
+      __syncthreads();
       for_each_key(P, col, [&](unsigned long long key) {
-        if ((key >> shift) == (prefix >> shift)) found = key;
+        if ((key >> shift) == (prefix >> shift)) {
+          const int at = atomicAdd(&S.n_keys, 1);
+          if (at < kQCap) S.keys[at] = key;
+        }
       });
-      prefix = block_min64(found, s_red);
-      break;
+      __syncthreads();
+      in_smem = true;
+      n_smem = S.n_keys < kQCap ? S.n_keys : kQCap;
     }
   }
   count_le = (k - kk) + eq;
+  n_cand = in_smem ? n_smem : 0;
   return prefix;
 }
 
-__global__ void __launch_bounds__(kQThreads) k_column_quantile(const __grid_constant__ ColParams P) {
-  __shared__ int s_hist[256];
-  __shared__ long long s_bcast[4];
-  __shared__ unsigned long long s_red[kQThreads / 32];
+__global__ void __launch_bounds__(kQThreads, 1) k_column_quantile(const __grid_constant__ ColParams P) {
+  __shared__ SelectScratch S;
   __shared__ unsigned long long s_stat[3];
   const int col = blockIdx.x;
   if (threadIdx.x == 0) {
@@ -155,14 +181,25 @@ __global__ void __launch_bounds__(kQThreads) k_column_quantile(const __grid_cons
       const double fl = floor(vi);
       const long long k = (long long)fl;
       const double g = __dsub_rn(vi, fl);
-      const unsigned long long ka = block_radix_select(P, col, k, s_hist, s_bcast, s_red, cle);
+      int n_cand;
+      const unsigned long long ka = block_radix_select(P, col, k, S, cle, n_cand);
       unsigned long long kb = ka;
       if (k + 1 >= cle) {  // the next order statistic is the smallest key above ka
+        // first among the gathered candidates: a larger key that shares ka's prefix is smaller than
+        // every key outside the bin; only if ka is the bin's largest key the column is read again
         unsigned long long best = ~0ull;
-        for_each_key(P, col, [&](unsigned long long key) {
+        for (int i = threadIdx.x; i < n_cand; i += kQThreads) {
+          const unsigned long long key = S.keys[i];
           if (key > ka && key < best) best = key;
-        });
-        kb = block_min64(best, s_red);
+        }
+        kb = block_min64(best, S.red);
+        if (kb == ~0ull) {
+          best = ~0ull;
+          for_each_key(P, col, [&](unsigned long long key) {
+            if (key > ka && key < best) best = key;
+          });
+          kb = block_min64(best, S.red);
+        }
       }
       const double a = key_value(ka), b = key_value(kb);
       const double d = __dsub_rn(b, a);
