@@ -397,7 +397,7 @@ int sai_engine_score_host_zt(sai_engine* e, const sai_layout* lay, const uint8_t
  * row-major int8 matrix of population p's per-individual allele sums
  * (gt[p][site * row_stride[p] + individual], negative = missing; what reshape_genotypes leaves
  * in memory, sai/utils/utils.py:405-410, narrowed to int8), ordinary pageable host memory.
- * A pool of host threads (sai_engine_set_host_threads; default: all cores) packs ~16 MB slices
+ * A pool of host threads (sai_engine_set_host_threads; default: all cores) packs 32 MB slices
  * of tiles into a ring of pinned staging buffers with the CPU's vector unit (sai_pack_isa); each
  * finished slice is copied to the GPU and flagged while the following slices are being packed,
  * so the call costs about max(pack, copy) instead of pack + copy.  Returns SAI_E_DOMAIN when a
