@@ -339,6 +339,38 @@ def test_column_quantiles_vs_numpy(n):
             assert o[c, 1] == np.count_nonzero(~np.isnan(v))
 
 
+def test_torch_ops_pieces_and_quantiles():
+    """torch.ops.sai_b200.window_stats_pieces / column_quantiles (sai_b200/ops.py) == the ctypes path
+    (GenomeBatch / sai_column_quantiles) on the small genome."""
+    import torch
+
+    import sai_b200.ops as ops
+    from sai_b200.encode import make_layout
+    from sai_b200.genome import shard_genome
+    from sai_b200.scoring import make_job
+
+    chroms = _small_genome(total_sites=20_000)
+    lay = make_layout([150, 100, 4], [2, 2, 2], [2, 2, 2])
+    job = make_job(0, 1, [2], True, u=dict(w=0.05, x=0.3, y_list=[("=", 1.0)]), q=dict(w=0.05, quantile=0.95, y_list=[("=", 1.0)]))
+    pieces = shard_genome([ch["wins"] for ch in chroms], 1)[0]
+    batch, res = _score_rank(chroms, pieces, lay, job)
+    sc = batch.scorer
+    z = lambda t: torch.zeros_like(t)
+    nsnps, u, q, q_cnt, u_start, q_start, totals = z(sc.nsnps), z(sc.u), z(sc.q), z(sc.q_cnt), z(sc.u_start), z(sc.q_start), z(sc.totals)
+    u_cand, q_cand = z(sc.u_cand), z(sc.q_cand)
+    torch.ops.sai_b200.window_stats_pieces(batch.d_pos, batch.d_ws, batch.d_we, batch.d_first, batch.d_last, ops.jobs_tensor([job]),
+                                           sc.mask_u, sc.mask_q, sc.qval, nsnps, u, q, q_cnt, u_start, q_start, totals, u_cand, q_cand)
+    assert torch.equal(nsnps, sc.nsnps) and torch.equal(u, sc.u) and torch.equal(q_cnt, sc.q_cnt) and torch.equal(totals, sc.totals)
+    assert np.array_equal(q.cpu().numpy(), res.q, equal_nan=True) and int(u.sum()) > 0
+    cols = torch.stack([sc.u[0].to(torch.float64), sc.q[0]]).contiguous()
+    out = torch.empty((2, 4), dtype=torch.float64, device="cuda")
+    torch.ops.sai_b200.column_quantiles(cols, 0.9, out)
+    o = out.cpu().numpy()
+    assert o[0, 0] == orc.outlier_threshold(res.u[0].astype(np.float64), 0.9) and o[1, 0] == orc.outlier_threshold(res.q[0], 0.9)
+    with pytest.raises(ValueError):
+        torch.ops.sai_b200.column_quantiles(cols.to(torch.float32), 0.9, out)
+
+
 def test_outlier_thresholds_nccl_two_gpus(tmp_path):
     """The NCCL path itself: two ranks score their shards of the small genome on their own GPUs
     and exchange ONE all_gather_into_tensor; thresholds identical on both ranks and equal to the
