@@ -5,18 +5,23 @@
 //
 // The column arrives as `n_chunks` equally long pieces (one per rank after ONE
 // all_gather_into_tensor over NVLink; NaN = padding or a window without a value), so nothing is
-// copied or sorted on the host.  One 1024-thread block per column selects the order statistic
+// copied or sorted on the host.  One thread-block cluster (8 CTAs of 1024 threads, histograms
+// merged through distributed shared memory) per column selects the order statistic
 // exactly by an MSB-first radix select over the order-preserving 64-bit image of the doubles
 // (sign-flipped, so negative statistics such as Danc / fd work too): passes with a 256-bin shared
 // histogram over the L2-resident column until the selected bin fits shared memory, then the
 // remaining digits there.  Everything is exact: the result equals what sorting the column gives.
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include "common.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace sai {
 
 constexpr int kQThreads = 1024;
+constexpr int kQCluster = 8;  // CTAs (SMs) per column: one thread-block cluster, histograms merged through DSMEM
 
 struct ColParams {
   const double* vals;
@@ -37,27 +42,46 @@ __device__ __forceinline__ double key_value(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
-// f(key) for every non-NaN value of the column, spread over the block's threads
+// One thread-block CLUSTER of kQCluster CTAs per column (8 SMs instead of one): CTA r owns the
+// elements [r*1024 + tid + j*8192]; per radix pass every CTA histograms its share in its own shared
+// memory, the cluster barrier publishes the eight histograms and every CTA merges them through
+// distributed shared memory, so all CTAs pick the same bin without a trip through global memory.
+
+// f(key) for every non-NaN value of this CTA's share of the column
 template <typename F>
-__device__ __forceinline__ void for_each_key(const ColParams& P, int col, F f) {
-  constexpr int kInFlight = 8;  // independent loads per thread: the block is alone on its SM, latency is all there is
+__device__ __forceinline__ void for_each_key(const ColParams& P, int col, int rank, F f) {
+  constexpr int kInFlight = 4;  // independent loads per thread
+  constexpr int64_t kStride = (int64_t)kQCluster * kQThreads;
   for (int c = 0; c < P.n_chunks; ++c) {
     const double* p = P.vals + (size_t)c * P.chunk_stride + (size_t)col * P.col_stride;
-    int64_t i = threadIdx.x;
-    for (; i + (kInFlight - 1) * kQThreads < P.len; i += kInFlight * kQThreads) {
+    int64_t i = (int64_t)rank * kQThreads + threadIdx.x;
+    for (; i + (kInFlight - 1) * kStride < P.len; i += kInFlight * kStride) {
       double v[kInFlight];
 #pragma unroll
-      for (int u = 0; u < kInFlight; ++u) v[u] = __ldg(p + i + u * kQThreads);
+      for (int u = 0; u < kInFlight; ++u) v[u] = __ldg(p + i + u * kStride);
 #pragma unroll
       for (int u = 0; u < kInFlight; ++u)
         if (v[u] == v[u]) f(ordered_key(v[u]));
     }
-    for (; i < P.len; i += kQThreads) {
+    for (; i < P.len; i += kStride) {
       const double v = __ldg(p + i);
       if (v == v) f(ordered_key(v));
     }
   }
 }
+
+constexpr int kQCap = 4096;  // candidate keys kept in shared memory once the selected bin is that small
+
+struct SelectScratch {
+  int hist[256];      // this CTA's histogram of the current digit (read by the whole cluster)
+  int merged[256];    // the cluster's histogram
+  long long bcast[4];
+  unsigned long long red[kQThreads / 32];
+  unsigned long long stat[3];      // this CTA's n_valid / min key / max key (read by the whole cluster)
+  unsigned long long best;         // this CTA's candidate in a cluster-wide min (read by the whole cluster)
+  unsigned long long keys[kQCap];  // this CTA's share of the gathered candidates
+  int n_keys;
+};
 
 __device__ __forceinline__ unsigned long long block_min64(unsigned long long v, unsigned long long* s_red) {
 #pragma unroll
@@ -75,30 +99,33 @@ __device__ __forceinline__ unsigned long long block_min64(unsigned long long v, 
   return r;
 }
 
-constexpr int kQCap = 4096;  // candidate keys kept in shared memory once the selected bin is that small
-
-struct SelectScratch {
-  int hist[256];
-  long long bcast[4];
-  unsigned long long red[kQThreads / 32];
-  unsigned long long keys[kQCap];
-  int n_keys;
-};
+// minimum over the cluster of every CTA's block-wide minimum
+__device__ __forceinline__ unsigned long long cluster_min64(cg::cluster_group& cluster, unsigned long long v, SelectScratch& S) {
+  const unsigned long long mine = block_min64(v, S.red);
+  if (threadIdx.x == 0) S.best = mine;
+  cluster.sync();
+  unsigned long long r = ~0ull;
+  for (int c = 0; c < kQCluster; ++c) {
+    const unsigned long long o = *cluster.map_shared_rank(&S.best, c);
+    r = o < r ? o : r;
+  }
+  cluster.sync();  // nobody overwrites S.best while a neighbour still reads it
+  return r;
+}
 
 // Exact k-th smallest key (0-based) by MSB-first radix select; count_le = number of keys <= it.
 // The passes read the column from L2 until the selected bin holds <= kQCap keys; those are then
-// gathered into shared memory once and the remaining digits are resolved there.  `n_cand` /
-// S.keys stay valid for the caller (the successor search): all keys that share the answer's
-// prefix down to the digit at which they were gathered.
-__device__ unsigned long long block_radix_select(const ColParams& P, int col, long long k, SelectScratch& S,
-                                                 long long& count_le, int& n_cand) {
+// gathered into shared memory once (every CTA keeps the candidates of its own share) and the
+// remaining digits are resolved there.  n_cand = this CTA's gathered candidates (for the
+// successor search): all of its keys that share the answer's prefix down to the gathering digit.
+__device__ unsigned long long cluster_radix_select(cg::cluster_group& cluster, const ColParams& P, int col, int rank,
+                                                   long long k, SelectScratch& S, long long& count_le, int& n_cand) {
   unsigned long long prefix = 0;
   long long kk = k, eq = 0;
   bool in_smem = false;
   int n_smem = 0;
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 56 - 8 * pass;
-    __syncthreads();
     if (threadIdx.x < 256) S.hist[threadIdx.x] = 0;
     __syncthreads();
     auto count = [&](unsigned long long key) {
@@ -107,41 +134,45 @@ __device__ unsigned long long block_radix_select(const ColParams& P, int col, lo
     if (in_smem) {
       for (int i = threadIdx.x; i < n_smem; i += kQThreads) count(S.keys[i]);
     } else {
-      for_each_key(P, col, count);
+      for_each_key(P, col, rank, count);
     }
-    __syncthreads();
+    cluster.sync();  // all eight histograms are complete
+    if (threadIdx.x < 256) {
+      int sum = 0;
+      for (int c = 0; c < kQCluster; ++c) sum += cluster.map_shared_rank(S.hist, c)[threadIdx.x];
+      S.merged[threadIdx.x] = sum;
+    }
+    cluster.sync();  // ... and read by everybody: S.hist may be reset in the next pass
     if (threadIdx.x == 0) {  // 256 bins: a serial scan is cheaper than a block scan here
       long long run = 0;
       int bin = 255;
       for (int b = 0; b < 256; ++b) {
-        if (kk < run + S.hist[b]) {
+        if (kk < run + S.merged[b]) {
           bin = b;
           break;
         }
-        run += S.hist[b];
+        run += S.merged[b];
       }
       S.bcast[0] = bin;
       S.bcast[1] = run;
-      S.bcast[2] = S.hist[bin];
+      S.bcast[2] = S.merged[bin];
     }
     __syncthreads();
     const int bin = (int)S.bcast[0];
     const long long below = S.bcast[1], cnt = S.bcast[2];
+    __syncthreads();  // S.bcast is rewritten in the next pass
     prefix |= (unsigned long long)bin << shift;
     kk -= below;
     eq = cnt;
     if (!in_smem && cnt <= kQCap && pass < 7) {  // gather the bin's keys once; finish in shared memory
       if (threadIdx.x == 0) S.n_keys = 0;
       __syncthreads();
-      for_each_key(P, col, [&](unsigned long long key) {
-        if ((key >> shift) == (prefix >> shift)) {
-          const int at = atomicAdd(&S.n_keys, 1);
-          if (at < kQCap) S.keys[at] = key;
-        }
+      for_each_key(P, col, rank, [&](unsigned long long key) {
+        if ((key >> shift) == (prefix >> shift)) S.keys[atomicAdd(&S.n_keys, 1)] = key;  // <= cnt <= kQCap keys in the whole cluster
       });
       __syncthreads();
       in_smem = true;
-      n_smem = S.n_keys < kQCap ? S.n_keys : kQCap;
+      n_smem = S.n_keys;
     }
   }
   count_le = (k - kk) + eq;
@@ -149,30 +180,38 @@ __device__ unsigned long long block_radix_select(const ColParams& P, int col, lo
   return prefix;
 }
 
-__global__ void __launch_bounds__(kQThreads, 1) k_column_quantile(const __grid_constant__ ColParams P) {
+__global__ void __cluster_dims__(kQCluster, 1, 1) __launch_bounds__(kQThreads, 1)
+    k_column_quantile(const __grid_constant__ ColParams P) {
   __shared__ SelectScratch S;
-  __shared__ unsigned long long s_stat[3];
-  const int col = blockIdx.x;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int col = blockIdx.y;
   if (threadIdx.x == 0) {
-    s_stat[0] = 0;       // n_valid
-    s_stat[1] = ~0ull;   // min key
-    s_stat[2] = 0;       // max key
+    S.stat[0] = 0;       // n_valid
+    S.stat[1] = ~0ull;   // min key
+    S.stat[2] = 0;       // max key
   }
   __syncthreads();
   unsigned long long n_loc = 0, mn = ~0ull, mx = 0;
-  for_each_key(P, col, [&](unsigned long long key) {
+  for_each_key(P, col, rank, [&](unsigned long long key) {
     ++n_loc;
     mn = key < mn ? key : mn;
     mx = key > mx ? key : mx;
   });
-  atomicAdd(&s_stat[0], n_loc);
-  atomicMin(&s_stat[1], mn);
-  atomicMax(&s_stat[2], mx);
-  __syncthreads();
-  const long long n = (long long)s_stat[0];
-  const unsigned long long kmin = s_stat[1], kmax = s_stat[2];
+  atomicAdd(&S.stat[0], n_loc);
+  atomicMin(&S.stat[1], mn);
+  atomicMax(&S.stat[2], mx);
+  cluster.sync();
+  long long n = 0;
+  unsigned long long kmin = ~0ull, kmax = 0;
+  for (int c = 0; c < kQCluster; ++c) {
+    const unsigned long long* st = cluster.map_shared_rank(S.stat, c);
+    n += (long long)st[0];
+    kmin = st[1] < kmin ? st[1] : kmin;
+    kmax = st[2] > kmax ? st[2] : kmax;
+  }
   double thr = CUDART_NAN;
-  if (n > 0 && kmin != kmax) {  // empty or single-valued column: no threshold (sai.py:195-207)
+  if (n > 0 && kmin != kmax) {  // empty or single-valued column: no threshold (sai.py:195-207); cluster-uniform
     const double vi = __dmul_rn((double)(n - 1), P.q);
     long long cle;
     if (vi >= (double)(n - 1)) {
@@ -182,7 +221,7 @@ __global__ void __launch_bounds__(kQThreads, 1) k_column_quantile(const __grid_c
       const long long k = (long long)fl;
       const double g = __dsub_rn(vi, fl);
       int n_cand;
-      const unsigned long long ka = block_radix_select(P, col, k, S, cle, n_cand);
+      const unsigned long long ka = cluster_radix_select(cluster, P, col, rank, k, S, cle, n_cand);
       unsigned long long kb = ka;
       if (k + 1 >= cle) {  // the next order statistic is the smallest key above ka
         // first among the gathered candidates: a larger key that shares ka's prefix is smaller than
@@ -192,13 +231,13 @@ __global__ void __launch_bounds__(kQThreads, 1) k_column_quantile(const __grid_c
           const unsigned long long key = S.keys[i];
           if (key > ka && key < best) best = key;
         }
-        kb = block_min64(best, S.red);
+        kb = cluster_min64(cluster, best, S);
         if (kb == ~0ull) {
           best = ~0ull;
-          for_each_key(P, col, [&](unsigned long long key) {
+          for_each_key(P, col, rank, [&](unsigned long long key) {
             if (key > ka && key < best) best = key;
           });
-          kb = block_min64(best, S.red);
+          kb = cluster_min64(cluster, best, S);
         }
       }
       const double a = key_value(ka), b = key_value(kb);
@@ -206,13 +245,14 @@ __global__ void __launch_bounds__(kQThreads, 1) k_column_quantile(const __grid_c
       thr = g >= 0.5 ? __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, g))) : __dadd_rn(a, __dmul_rn(d, g));
     }
   }
-  if (threadIdx.x == 0) {
+  if (rank == 0 && threadIdx.x == 0) {
     double* o = P.out + 4 * (size_t)col;
     o[0] = thr;
     o[1] = (double)n;
     o[2] = n > 0 ? key_value(kmin) : CUDART_NAN;
     o[3] = n > 0 ? key_value(kmax) : CUDART_NAN;
   }
+  cluster.sync();  // no CTA leaves while a neighbour may still read its shared memory
 }
 
 }  // namespace sai
@@ -226,7 +266,7 @@ extern "C" int sai_column_quantiles(const double* d_vals, int32_t n_cols, int32_
   if (n_cols == 0) return SAI_OK;
   SAI_REQUIRE(d_out && (len == 0 || d_vals), "NULL device pointer");
   ColParams P{d_vals, n_chunks, chunk_stride, col_stride, len, q, d_out};
-  k_column_quantile<<<n_cols, kQThreads, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  k_column_quantile<<<dim3(kQCluster, (unsigned)n_cols), kQThreads, 0, static_cast<cudaStream_t>(stream)>>>(P);
   SAI_CUDA_CHECK(cudaGetLastError());
   return SAI_OK;
 }
