@@ -137,25 +137,30 @@ __device__ unsigned long long cluster_radix_select(cg::cluster_group& cluster, c
       for_each_key(P, col, rank, count);
     }
     cluster.sync();  // all eight histograms are complete
+    // merge the eight histograms through distributed shared memory and find the bin that holds rank kk:
+    // threads 0..255 own one bin each; inclusive scan = warp shuffles + the eight warp totals
+    int mine = 0, incl = 0;
     if (threadIdx.x < 256) {
-      int sum = 0;
-      for (int c = 0; c < kQCluster; ++c) sum += cluster.map_shared_rank(S.hist, c)[threadIdx.x];
-      S.merged[threadIdx.x] = sum;
-    }
-    cluster.sync();  // ... and read by everybody: S.hist may be reset in the next pass
-    if (threadIdx.x == 0) {  // 256 bins: a serial scan is cheaper than a block scan here
-      long long run = 0;
-      int bin = 255;
-      for (int b = 0; b < 256; ++b) {
-        if (kk < run + S.merged[b]) {
-          bin = b;
-          break;
-        }
-        run += S.merged[b];
+      for (int c = 0; c < kQCluster; ++c) mine += cluster.map_shared_rank(S.hist, c)[threadIdx.x];
+      incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += y;
       }
-      S.bcast[0] = bin;
-      S.bcast[1] = run;
-      S.bcast[2] = S.merged[bin];
+      if ((threadIdx.x & 31) == 31) S.merged[threadIdx.x >> 5] = incl;  // warp totals
+    }
+    if (threadIdx.x == 0) S.bcast[0] = 255, S.bcast[1] = 0, S.bcast[2] = 0;
+    cluster.sync();  // ... the histograms are read by everybody: S.hist may be reset in the next pass
+    if (threadIdx.x < 256) {
+      long long before = 0;
+      for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += S.merged[w];
+      const long long hi = before + incl, lo = hi - mine;
+      if (mine > 0 && kk >= lo && kk < hi) {  // exactly one bin
+        S.bcast[0] = threadIdx.x;
+        S.bcast[1] = lo;
+        S.bcast[2] = mine;
+      }
     }
     __syncthreads();
     const int bin = (int)S.bcast[0];
