@@ -110,6 +110,10 @@ def _worker(rank, world, port, out):
 
         items = run_sharded(FakePre(), "21", 2309, 48989, 10000, 5000)
         res["items"] = items
+        from sai_b200.distributed import run_genome_sharded
+
+        spans = {"1": (120, 81000), "2": (7, 9000), "X": (40000, 66000)}
+        res["genome"] = run_genome_sharded({c: FakePre() for c in spans}, spans, 10000, 5000)
         res["ranges"] = shard_ranges(2309, 48989, 10000, 5000, world)
         out[rank] = res
     finally:
@@ -141,3 +145,11 @@ def test_two_rank_threshold_and_sharding():
     assert [(it["start"], it["end"]) for it in res[0]["items"]] == wins
     assert [it["rank"] for it in res[0]["items"]] == [0] * 5 + [1] * 5
     assert [(it["start"], it["end"]) for it in res[1]["items"]] == wins[5:]
+    # whole genome: the flattened (chromosome, window) list cut in two; rank 0 sees every window once, in genome order
+    spans = {"1": (120, 81000), "2": (7, 9000), "X": (40000, 66000)}
+    flat = [(c, w) for c in spans for w in split_genome(list(spans[c]), 10000, 5000)]
+    got = [(it["chr_name"], (it["start"], it["end"])) for it in res[0]["genome"]]
+    assert got == flat
+    half = (len(flat) + 1) // 2
+    assert [it["rank"] for it in res[0]["genome"]] == [0] * half + [1] * (len(flat) - half)
+    assert [(it["chr_name"], (it["start"], it["end"])) for it in res[1]["genome"]] == flat[half:]
