@@ -142,9 +142,10 @@ int sai_pack_i8(const sai_layout* lay, int32_t pop, const int8_t* gt,
  * matrix (what a VCF parse leaves behind) the input is read as one sequential stream. */
 int sai_pack_i8_all(const sai_layout* lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
                     uint8_t* packed, int32_t n_threads);
-/* The vector path the packer selected on this CPU: "avx512bw", "avx2", "sse2" or "portable";
- * sai_pack_i8_isa forces one (1 portable, 2 sse2, 3 avx2, 4 avx512bw; 0 = best; an unavailable
- * choice falls back to the best) -- all paths produce identical bytes (tests). */
+/* The vector path the packer selected on this CPU: "avx512gfni" (AVX-512 + GFNI + VBMI: 8x8
+ * bit-matrix transposes), "avx512bw", "avx2", "sse2" or "portable"; sai_pack_i8_isa forces one
+ * (1 portable, 2 sse2, 3 avx2, 4 avx512bw, 5 avx512gfni; 0 = best; an unavailable choice falls
+ * back to the best) -- all paths produce identical bytes (tests). */
 const char* sai_pack_isa(void);
 int sai_pack_i8_isa(const sai_layout* lay, int32_t pop, const int8_t* gt, int64_t n_sites,
                     int64_t row_stride, uint8_t* packed, int32_t n_threads, int32_t isa);

@@ -9,7 +9,7 @@ namespace sai {
 // Packs population `pop` of tiles [t0, t1) from the row-major int8 matrix `gt`
 // (gt[site * row_stride + individual], n_sites rows) into the tile buffer whose tile `tile_base`
 // starts at `packed_base`; true = a value does not fit the population's bit-planes.
-// isa: 0 = best available on this CPU, 1 = portable, 2 = sse2, 3 = avx2, 4 = avx512bw (tests;
+// isa: 0 = best available on this CPU, 1 = portable, 2 = sse2, 3 = avx2, 4 = avx512bw, 5 = avx512gfni (tests;
 // an unavailable choice falls back to the best available).
 bool pack_tiles_i8(const sai_layout& lay, int pop, const int8_t* gt, int64_t n_sites, int64_t row_stride,
                    int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa);

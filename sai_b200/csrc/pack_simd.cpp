@@ -1,8 +1,9 @@
 // Host packer core: int8 per-individual allele sums -> tiled bit-planes (include/sai_b200.h),
 // the encoding that replaces the reference's int64 matrices (reshape_genotypes,
 // sai/utils/utils.py:405-410).  Plain C++ (compiled by g++, not nvcc) so that the x86 vector
-// paths can be selected at run time: AVX-512BW (64 individuals per instruction group), AVX2
-// (32) or a portable 64-bit multiply "movemask" (8).
+// paths can be selected at run time: AVX-512 with GFNI + VBMI (64 individuals per 8x8 bit-matrix
+// transpose + one byte permute), AVX-512BW (64 per mask-test group), AVX2 (32), SSE2 (16) or a
+// portable 64-bit multiply "movemask" (8).
 //
 // One call packs one population of a run of tiles.  A tile is 32 sites; per site the 32-individual
 // groups of the row are turned into B plane words (bit i of plane b = bit b of individual i's
@@ -161,12 +162,140 @@ bool row_avx512(const int8_t* row, int n, int n_groups, int B, uint32_t* words) 
   return bad != 0;
 }
 #pragma GCC pop_options
+
+// GFNI + VBMI (Ice Lake and later): no mask registers on the data path.  Per 64 individuals:
+// the code bytes (missing -> 0xff) are byte-reversed inside every 8-byte group, vgf2p8affineqb with
+// the DATA as the bit matrix and a one-hot selector per output byte transposes each group (output
+// byte b = bit b of its 8 individuals, individual i at bit i), and one vpermb gathers byte b of four
+// neighbouring groups into the plane word -- for the two 32-individual groups at once, already in
+// the stored order [group][plane], so the row costs 8 vector instructions per 64 input bytes
+// whatever the plane count.
+#pragma GCC push_options
+#pragma GCC target("avx512f,avx512bw,avx512vbmi,gfni")
+struct GatherTables {
+  alignas(64) uint8_t idx[SAI_MAX_BITS + 1][64];
+  GatherTables() {
+    memset(idx, 0, sizeof(idx));
+    for (int B = 1; B <= SAI_MAX_BITS; ++B)
+      for (int h = 0; h < 2; ++h)
+        for (int b = 0; b < B; ++b)
+          for (int k = 0; k < 4; ++k) idx[B][(h * B + b) * 4 + k] = (uint8_t)((4 * h + k) * 8 + b);
+  }
+};
+
+bool row_avx512gfni(const int8_t* row, int n, int n_groups, int B, uint32_t* words) {
+  static const GatherTables tables;
+  const __m512i ones = _mm512_set1_epi8(-1);
+  const __m512i one_hot = _mm512_set1_epi64((long long)0x8040201008040201ull);  // output byte b selects bit b
+  const __m512i rev8 = _mm512_broadcast_i32x4(_mm_set_epi8(8, 9, 10, 11, 12, 13, 14, 15, 0, 1, 2, 3, 4, 5, 6, 7));
+  const __m512i gather = _mm512_load_si512(tables.idx[B]);
+  __m512i vmax = _mm512_set1_epi8(-128);
+  auto planes = [&](__m512i v) {
+    vmax = _mm512_max_epi8(vmax, v);
+    const __m512i code = _mm512_mask_mov_epi8(v, _mm512_movepi8_mask(v), ones);
+    const __m512i t = _mm512_gf2p8affine_epi64_epi8(one_hot, _mm512_shuffle_epi8(code, rev8), 0);
+    return _mm512_permutexvar_epi8(gather, t);
+  };
+  const int full = n / 64;
+  if (B == 2) {
+    for (int k = 0; k < full; ++k)
+      _mm_storeu_si128((__m128i*)(words + 4 * k), _mm512_castsi512_si128(planes(_mm512_loadu_si512(row + 64 * k))));
+  } else if (B == 4) {
+    for (int k = 0; k < full; ++k)
+      _mm256_storeu_si256((__m256i*)(words + 8 * k), _mm512_castsi512_si256(planes(_mm512_loadu_si512(row + 64 * k))));
+  } else {
+    const __mmask64 m = B == 8 ? ~0ull : ((1ull << (8 * B)) - 1ull);
+    for (int k = 0; k < full; ++k)
+      _mm512_mask_storeu_epi8(words + (size_t)2 * B * k, m, planes(_mm512_loadu_si512(row + 64 * k)));
+  }
+  const int rest = n - 64 * full;
+  if (rest > 0) {  // masked load; lanes beyond the row read as -1 (missing)
+    const __m512i v = _mm512_mask_loadu_epi8(ones, (1ull << rest) - 1ull, row + 64 * full);
+    const int out_bytes = (n_groups - 2 * full) * B * 4;
+    _mm512_mask_storeu_epi8(words + (size_t)2 * B * full, out_bytes >= 64 ? ~0ull : ((1ull << out_bytes) - 1ull), planes(v));
+  }
+  const __m512i lim = _mm512_set1_epi8((char)std::min((1 << B) - 2, 127));
+  return _mm512_cmpgt_epi8_mask(vmax, lim) != 0;
+}
+#pragma GCC pop_options
+
+// The words of 8 consecutive sites (rows of `wbuf`, `wstride` words apart) -> one 64-byte line per
+// pair row at `dst0 + p * 256`.  AVX-512: 8 x 8 transpose of 64-bit pairs in registers, one
+// 64-byte (non-temporal) store per line.
+typedef void (*flush_fn)(const uint32_t* wbuf, int wstride, int pps, uint8_t* dst0, bool nt);
+
+#pragma GCC push_options
+#pragma GCC target("avx512f,avx512bw")
+void flush8_avx512(const uint32_t* wbuf, int wstride, int pps, uint8_t* dst0, bool nt) {
+  int p = 0;
+  for (; p + 8 <= pps; p += 8) {
+    __m512i r[8], t[8], u[8];
+    for (int j = 0; j < 8; ++j) r[j] = _mm512_loadu_si512(wbuf + (size_t)j * wstride + 2 * p);
+    for (int j = 0; j < 8; j += 2) {
+      t[j] = _mm512_unpacklo_epi64(r[j], r[j + 1]);      // pairs 0,2,4,6 of sites j, j+1
+      t[j + 1] = _mm512_unpackhi_epi64(r[j], r[j + 1]);  // pairs 1,3,5,7
+    }
+    for (int odd = 0; odd < 2; ++odd) {
+      u[4 * odd + 0] = _mm512_shuffle_i64x2(t[odd], t[2 + odd], 0x88);      // lanes 0,2 of sites 0-1 | 2-3
+      u[4 * odd + 1] = _mm512_shuffle_i64x2(t[odd], t[2 + odd], 0xdd);      // lanes 1,3
+      u[4 * odd + 2] = _mm512_shuffle_i64x2(t[4 + odd], t[6 + odd], 0x88);  // sites 4-5 | 6-7
+      u[4 * odd + 3] = _mm512_shuffle_i64x2(t[4 + odd], t[6 + odd], 0xdd);
+    }
+    __m512i out[8];
+    for (int odd = 0; odd < 2; ++odd) {
+      out[0 + odd] = _mm512_shuffle_i64x2(u[4 * odd + 0], u[4 * odd + 2], 0x88);  // pair 0 / 1 of all 8 sites
+      out[4 + odd] = _mm512_shuffle_i64x2(u[4 * odd + 0], u[4 * odd + 2], 0xdd);  // pair 4 / 5
+      out[2 + odd] = _mm512_shuffle_i64x2(u[4 * odd + 1], u[4 * odd + 3], 0x88);  // pair 2 / 3
+      out[6 + odd] = _mm512_shuffle_i64x2(u[4 * odd + 1], u[4 * odd + 3], 0xdd);  // pair 6 / 7
+    }
+    uint8_t* dst = dst0 + (size_t)p * kTileSites * 8;
+    if (nt) {
+      for (int c = 0; c < 8; ++c) _mm512_stream_si512((__m512i*)(dst + (size_t)c * kTileSites * 8), out[c]);
+    } else {
+      for (int c = 0; c < 8; ++c) _mm512_storeu_si512(dst + (size_t)c * kTileSites * 8, out[c]);
+    }
+  }
+  for (; p < pps; ++p) {
+    uint64_t line[8];
+    for (int j = 0; j < 8; ++j) memcpy(&line[j], wbuf + (size_t)j * wstride + 2 * p, 8);
+    uint8_t* dst = dst0 + (size_t)p * kTileSites * 8;
+    if (nt) {
+      for (int j = 0; j < 8; ++j) _mm_stream_si64(reinterpret_cast<long long*>(dst) + j, (long long)line[j]);
+    } else {
+      memcpy(dst, line, sizeof(line));
+    }
+  }
+}
+#pragma GCC pop_options
+#endif
+
+namespace {
+void flush8_scalar(const uint32_t* wbuf, int wstride, int pps, uint8_t* dst0, bool nt) {
+  for (int p = 0; p < pps; ++p) {
+    uint64_t line[8];
+    for (int j = 0; j < 8; ++j) memcpy(&line[j], wbuf + (size_t)j * wstride + 2 * p, 8);
+    uint8_t* dst = dst0 + (size_t)p * kTileSites * 8;
+#ifdef SAI_X86
+    if (nt) {
+      for (int j = 0; j < 8; ++j) _mm_stream_si64(reinterpret_cast<long long*>(dst) + j, (long long)line[j]);
+      continue;
+    }
+#endif
+    memcpy(dst, line, sizeof(line));
+  }
+}
+}  // namespace
+
+#ifdef SAI_X86
+bool cpu_has_avx512bw() { return __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f"); }
+bool cpu_has_gfni_vbmi() { return cpu_has_avx512bw() && __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("gfni"); }
 #endif
 
 row_fn pick_row_fn() {
 #ifdef SAI_X86
   __builtin_cpu_init();
-  if (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) return row_avx512;
+  if (cpu_has_gfni_vbmi()) return row_avx512gfni;
+  if (cpu_has_avx512bw()) return row_avx512;
   if (__builtin_cpu_supports("avx2")) return row_avx2;
   return row_sse2;
 #endif
@@ -178,7 +307,8 @@ row_fn pick_row_fn() {
 const char* pack_isa() {
 #ifdef SAI_X86
   __builtin_cpu_init();
-  if (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) return "avx512bw";
+  if (cpu_has_gfni_vbmi()) return "avx512gfni";
+  if (cpu_has_avx512bw()) return "avx512bw";
   if (__builtin_cpu_supports("avx2")) return "avx2";
   return "sse2";
 #endif
@@ -189,13 +319,31 @@ namespace {
 row_fn row_fn_for(int isa) {
   static const row_fn best = pick_row_fn();
   row_fn fn = best;
+#ifdef SAI_EXPERIMENTS
+  static const int forced = [] { const char* e = getenv("SAI_PACK_ISA"); return e ? atoi(e) : 0; }();  // A/B knob
+  if (isa == 0) isa = forced;
+#endif
   if (isa == 1) fn = row_portable;
 #ifdef SAI_X86
   if (isa == 2) fn = row_sse2;
   if (isa == 3 && __builtin_cpu_supports("avx2")) fn = row_avx2;
-  if (isa == 4 && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f")) fn = row_avx512;
+  if (isa == 4 && cpu_has_avx512bw()) fn = row_avx512;
+  if (isa == 5 && cpu_has_gfni_vbmi()) fn = row_avx512gfni;
 #endif
   return fn;
+}
+
+// isa 1 (portable) keeps the scalar line writer so that the tests compare both
+flush_fn flush_fn_for(int isa) {
+#ifdef SAI_X86
+  static const bool wide = (__builtin_cpu_init(), cpu_has_avx512bw());
+#ifdef SAI_EXPERIMENTS
+  static const bool off = [] { const char* e = getenv("SAI_PACK_FLUSH"); return e && e[0] == '0'; }();  // A/B knob
+  if (off) return flush8_scalar;
+#endif
+  if (wide && (isa == 0 || isa >= 4)) return flush8_avx512;
+#endif
+  return flush8_scalar;
 }
 
 inline void prefetch_row(const int8_t* row, int n) {
@@ -228,14 +376,24 @@ inline void scatter_site(const uint32_t* words, int n_pairs, uint8_t* tile_pop, 
 bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
                        int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa) {
   const row_fn fn = row_fn_for(isa);
+  const flush_fn flush = flush_fn_for(isa);
   const int pps = lay.pairs_per_site;
   const size_t tile_bytes = (size_t)pps * kTileSites * 8;
   const int col_words = 2 * pps;  // words of one site's whole column (zero pad words included)
   constexpr int kBatch = 8;       // sites per output cache line
-  uint32_t stack_words[kBatch * 512 + 2];
-  uint32_t* wbuf = col_words + 2 <= 512 ? stack_words : new uint32_t[(size_t)kBatch * (col_words + 2)];
+  // +16: the vector row packers and the line writer move whole 64-byte vectors
+  // +16: the vector row packers and the line writer move whole 64-byte vectors
+  uint32_t stack_words[kBatch * 512 + 16];
   const int wstride = col_words + 2;
+  uint32_t* wbuf = wstride <= 512 ? stack_words : new uint32_t[(size_t)kBatch * wstride + 16];
+#ifdef SAI_EXPERIMENTS
+  static const int kAhead = [] {  // tools/ A/B knob: prefetch distance in sites
+    const char* e = getenv("SAI_PACK_AHEAD");
+    return e ? atoi(e) : 4;
+  }();
+#else
   constexpr int kAhead = 4;  // sites
+#endif
   // SAI_PACK_NT=0 (read once) switches the non-temporal stores off: an A/B knob for tools/pack_bench.py
   static const bool nt_enabled = [] {
     const char* e = getenv("SAI_PACK_NT");
@@ -263,18 +421,7 @@ bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int
           if (n_words & 1) words[n_words] = 0u;  // the population's pad word
         }
       }
-      for (int p = 0; p < pps; ++p) {
-        uint64_t line[kBatch];
-        for (int j = 0; j < kBatch; ++j) memcpy(&line[j], wbuf + (size_t)j * wstride + 2 * p, 8);
-        uint8_t* dst = tile + ((size_t)p * kTileSites + s8) * 8;
-#ifdef SAI_X86
-        if (aligned) {
-          for (int j = 0; j < kBatch; ++j) _mm_stream_si64(reinterpret_cast<long long*>(dst) + j, (long long)line[j]);
-          continue;
-        }
-#endif
-        memcpy(dst, line, sizeof(line));
-      }
+      flush(wbuf, wstride, pps, tile + (size_t)s8 * 8, aligned);
     }
   }
 #ifdef SAI_X86

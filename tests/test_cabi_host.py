@@ -726,14 +726,14 @@ def test_empty_items_carry_the_outgroup(tmp_path):
 
 @pytest.mark.parametrize("bits, vmax", [(2, 2), (3, 6), (4, 14), (5, 30), (7, 126), (8, 127)])
 def test_packer_vector_paths_are_identical(bits, vmax):
-    """Portable, SSE2, AVX2 and AVX-512 row packers (whichever this CPU has) write the same bytes,
+    """Portable, SSE2, AVX2, AVX-512BW and AVX-512 GFNI row packers (whichever this CPU has) write the same bytes,
     for full and partial 32-/64-individual groups, row-strided views and padding sites, and all
     report an out-of-domain value."""
     from sai_b200 import _cabi
     from sai_b200.encode import make_layout
 
     lib = _cabi.load()
-    assert lib.sai_pack_isa() in (b"avx512bw", b"avx2", b"sse2", b"portable")
+    assert lib.sai_pack_isa() in (b"avx512gfni", b"avx512bw", b"avx2", b"sse2", b"portable")
     rng = np.random.default_rng(bits)
     n_ind = [1, 31, 32, 33, 63, 64, 65, 100, 257]
     n_sites = 70
@@ -743,7 +743,7 @@ def test_packer_vector_paths_are_identical(bits, vmax):
     lay = make_layout(n_ind, [1] * len(n_ind), [bits] * len(n_ind))
     nbytes = int(lib.sai_packed_bytes(C.byref(lay), n_sites))
     outs = []
-    for isa in (1, 2, 3, 4, 0):
+    for isa in (1, 2, 3, 4, 5, 0):
         out = np.full(nbytes, 0xAB, dtype=np.uint8)
         at = 0
         for p, n in enumerate(n_ind):
@@ -757,9 +757,45 @@ def test_packer_vector_paths_are_identical(bits, vmax):
         return  # every non-negative int8 fits 8 planes
     bad = whole.copy()
     bad[17, 70] = vmax + 1  # population 3 holds columns 64..96
-    for isa in (1, 2, 3, 4):
+    for isa in (1, 2, 3, 4, 5):
         rc = lib.sai_pack_i8_isa(C.byref(lay), 3, bad[:, 64:].ctypes.data, n_sites, bad.strides[0], outs[0].ctypes.data, 1, isa)
         assert rc == _cabi.E_DOMAIN, isa
+
+
+@pytest.mark.parametrize("n_ind, bits", [([1500, 1000, 4], 2), ([257, 100, 65, 33], 3), ([700, 90], 4), ([40], 2), ([300, 300], 8)])
+def test_all_populations_packer_matches_per_population_packer(n_ind, bits):
+    """`sai_pack_i8_all` (the int8 pipeline's packer: site-by-site over all populations, 8 sites per
+    output cache line, vector line writer, non-temporal stores when the output is 64-byte aligned)
+    writes exactly the bytes of the portable per-population packer -- aligned and unaligned output,
+    site counts that end inside a tile and inside an 8-site batch, 1..n threads."""
+    from sai_b200 import _cabi
+    from sai_b200.encode import make_layout
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(sum(n_ind) + bits)
+    lay = make_layout(n_ind, [1] * len(n_ind), [bits] * len(n_ind))
+    vmax = min((1 << bits) - 2, 127)
+    for n_sites in (1, 31, 32, 37, 200, 1029):
+        whole = rng.integers(0, vmax + 1, size=(n_sites, sum(n_ind) + 3)).astype(np.int8)
+        whole[rng.random(whole.shape) < 0.1] = -1
+        nbytes = int(lib.sai_packed_bytes(C.byref(lay), n_sites))
+        want = np.full(nbytes, 0xAB, dtype=np.uint8)
+        cols = np.cumsum([0] + n_ind)
+        for p in range(len(n_ind)):
+            assert lib.sai_pack_i8_isa(C.byref(lay), p, whole.ctypes.data + int(cols[p]), n_sites, whole.strides[0], want.ctypes.data, 1, 1) == 0
+        ptrs = (C.c_void_p * len(n_ind))(*[whole.ctypes.data + int(cols[p]) for p in range(len(n_ind))])
+        strides = (C.c_int64 * len(n_ind))(*[whole.strides[0]] * len(n_ind))
+        raw = np.full(nbytes + 128, 0xCD, dtype=np.uint8)
+        base = (-raw.ctypes.data) % 64
+        for shift, threads in ((0, 1), (0, 5), (8, 3), (3, 2)):
+            raw[:] = 0xCD
+            got = raw[base + shift : base + shift + nbytes]
+            assert lib.sai_pack_i8_all(C.byref(lay), ptrs, strides, n_sites, got.ctypes.data, threads) == 0
+            assert np.array_equal(got, want), (n_sites, shift, threads)
+            assert (raw[: base + shift] == 0xCD).all() and (raw[base + shift + nbytes :] == 0xCD).all()
+    if bits < 8:
+        whole[n_sites // 2, 1] = vmax + 1
+        assert lib.sai_pack_i8_all(C.byref(lay), ptrs, strides, n_sites, got.ctypes.data, 2) == _cabi.E_DOMAIN
 
 
 # ---------------------------------------------------------------- whole-genome sharding (host logic)
