@@ -642,7 +642,11 @@ def main():
             return r, same, t / steps
 
         Ki = max(2, min(Ke, 5))
-        r2, same_i8, t_i8 = run_wire(mg, Ki)
+        r2, same_i8, t_i8 = run_wire(mg, Ki)  # default wire: zt records built by the packers
+        i8_wire_bytes = eng.i8_wire_bytes()
+        eng.set_i8_wire(dense=True)
+        _, same_i8_dense, t_i8_dense = run_wire(mg, Ki)
+        eng.set_i8_wire(dense=False)
         _, same_zt, t_zt = run_wire(zt, Ke)
         _, same_dense, t_dense = run_wire(pg, Ke)
         small = pos.nbytes + ws.nbytes + we.nbytes
@@ -655,15 +659,26 @@ def main():
         t_pack = float(tp.item())
         e2e = {
             "value": world * W / t_i8, "unit": "windows/s",
-            "h2d_bytes_per_step": int(packed_bytes + small), "d2h_bytes_per_step": d2h, "steps": Ki, "ms_per_step": 1e3 * t_i8,
+            "h2d_bytes_per_step": int(i8_wire_bytes + small), "d2h_bytes_per_step": d2h, "steps": Ki, "ms_per_step": 1e3 * t_i8,
             "matches_device_path": same_i8,
             "input": f"int8 per-individual allele sums, {h_i8.nbytes / 1e9:.2f} GB of pageable host memory per rank "
                      f"(the reference holds the same matrix as int64); packed on the fly by {host_threads} host threads "
-                     f"({_cabi.load().sai_pack_isa().decode()} row packer) into pinned 32 MB slices, pipelined with the copy and K1",
+                     f"({_cabi.load().sai_pack_isa().decode()} row packer), each tile zt-encoded while still in the packer's L1 "
+                     f"({_cabi.load().sai_zt_isa().decode()} record encoder), records streamed into pinned 32 MB ring slots, "
+                     "pipelined with the copy, the device-side decode and K1",
             "host_threads": host_threads,
+            "wire": "zt records built by the packers", "wire_ratio": packed_bytes / max(1, i8_wire_bytes),
+            "int8_gbps": h_i8.nbytes / t_i8 / 1e9,
             "pack_alone_ms": 1e3 * t_pack, "pack_alone_gbps_int8": h_i8.nbytes / t_pack / 1e9, "pack_reproduces_device_tiles": pack_matches,
+            "pack_alone_note": "dense packer alone (int8 -> dense tiles in a pinned buffer, no GPU work)",
             "wire_alone_ms": 1e3 * t_dense,
-            "pipeline_vs_slowest_stage": t_i8 / max(t_pack, t_dense),
+            "pipeline_vs_slowest_stage": t_i8 / max(t_pack, t_zt),
+            "dense_wire": {
+                "value": world * W / t_i8_dense, "unit": "windows/s", "ms_per_step": 1e3 * t_i8_dense,
+                "h2d_bytes_per_step": int(packed_bytes + small), "matches_device_path": same_i8_dense,
+                "pipeline_vs_slowest_stage": t_i8_dense / max(t_pack, t_dense),
+                "note": "same call with sai_engine_set_i8_wire(1): dense tiles through the ring (data without a hom-ref majority)",
+            },
             "prepacked_zt": {
                 "value": world * W / t_zt, "unit": "windows/s", "h2d_bytes_per_step": int(zt.stream.nbytes + zt.tile_off.nbytes + small),
                 "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": 1e3 * t_zt, "matches_device_path": same_zt,

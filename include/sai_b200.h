@@ -348,6 +348,11 @@ uint64_t sai_zt_bound(const sai_layout* lay, int64_t n_sites); /* upper bound of
  * negative SAI_E_* code (SAI_E_CAPACITY: out_cap too small). */
 int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_sites, uint8_t* out,
                       uint64_t out_cap, uint64_t* tile_off, int32_t n_threads);
+/* The encoder's vector path on this CPU: "avx512vbmi2" (vpcompressb) or "portable";
+ * sai_zt_encode_isa forces one (0 = best, 1 = portable) -- identical bytes (tests). */
+const char* sai_zt_isa(void);
+int64_t sai_zt_encode_isa(const sai_layout* lay, const uint8_t* packed, int64_t n_sites, uint8_t* out,
+                          uint64_t out_cap, uint64_t* tile_off, int32_t n_threads, int32_t isa);
 /* Host decoder (tests, tools). */
 int sai_zt_decode_host(const sai_layout* lay, const uint8_t* stream, const uint64_t* tile_off,
                        int64_t n_sites, uint8_t* packed);
@@ -407,6 +412,14 @@ int sai_engine_score_host_i8(sai_engine* e, const sai_layout* lay, const int8_t*
                              const int64_t* row_stride, const int32_t* pos, int64_t n_sites,
                              const int64_t* win_start, const int64_t* win_end, int64_t n_windows,
                              const sai_job* jobs, int32_t n_jobs, sai_host_results* out);
+/* Wire format of the int8 pipeline.  0 (default): every packer turns the tile it has just packed
+ * into a zt record while it is still in its L1 and only the records cross host memory and PCIe
+ * (k_zt_decode rebuilds the dense tiles in HBM) -- the packers are bound by the host's memory
+ * system, so the bytes not written and not read back by the copy engine are throughput.
+ * 1: dense tiles (data known not to compress: no hom-ref majority).  Results are identical.
+ * sai_engine_i8_wire_bytes: tile bytes the last sai_engine_score_host_i8 call copied. */
+int sai_engine_set_i8_wire(sai_engine* e, int32_t mode);
+uint64_t sai_engine_i8_wire_bytes(const sai_engine* e);
 /* Host threads the int8 pipeline may use (<= 0: hardware concurrency).  One engine per GPU:
  * with several ranks on a box give each its share of the cores. */
 int sai_engine_set_host_threads(sai_engine* e, int32_t n_threads);

@@ -148,10 +148,14 @@ SYMBOLS = {
         [_P, _LAY, _P, _P, _P, _I64, _P, _P, _I64, _JOB, _I32, C.POINTER(HostResults)],
     ),
     "sai_engine_set_host_threads": (C.c_int, [_P, _I32]),
+    "sai_engine_set_i8_wire": (C.c_int, [_P, _I32]),
+    "sai_engine_i8_wire_bytes": (_U64, [_P]),
     "sai_engine_score_resident": (C.c_int, [_P, _JOB, _I32, C.POINTER(HostResults)]),
     "sai_engine_rescore_windows": (C.c_int, [_P, C.POINTER(HostResults)]),
     "sai_zt_bound": (_U64, [_LAY, _I64]),
     "sai_zt_encode": (_I64, [_LAY, _P, _I64, _P, _U64, _P, _I32]),
+    "sai_zt_encode_isa": (_I64, [_LAY, _P, _I64, _P, _U64, _P, _I32, _I32]),
+    "sai_zt_isa": (C.c_char_p, []),
     "sai_zt_decode_host": (C.c_int, [_LAY, _P, _P, _I64, _P]),
     "sai_zt_decode": (C.c_int, [_LAY, _P, _U64, _P, _I64, _I64, _P, _P]),
     "sai_synth_fill": (C.c_int, [_LAY, _P, _I64, _I64, _I64, _P, _U64, C.c_double, _P]),

@@ -20,14 +20,20 @@
 
 #include "common.cuh"
 #include "host_pack.h"
+#include "zt_format.cuh"
+#include "zt_simd.h"
 
 struct sai_engine {
   int device = 0;
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   std::vector<cudaEvent_t> ev;
   int host_threads = 0;               // packer threads of the int8 pipeline (0: hardware concurrency)
+  int i8_wire = 0;                    // wire format of the int8 pipeline: 0 = zt records, 1 = dense tiles
   void* ring = nullptr;               // pinned staging ring of the int8 pipeline
   size_t ring_cap = 0;
+  void* h_ztoff = nullptr;            // pinned tile directory of the int8 pipeline's zt records
+  size_t h_ztoff_cap = 0;
+  uint64_t i8_wire_bytes = 0;         // bytes the last int8 call put on the wire (tiles only)
   // grow-only device buffers
   struct Buf {
     void* p = nullptr;
@@ -170,6 +176,7 @@ void sai_engine_destroy(sai_engine* e) {
     if (b->p) cudaFree(b->p);
   for (auto ev : e->ev) cudaEventDestroy(ev);
   if (e->ring) cudaFreeHost(e->ring);
+  if (e->h_ztoff) cudaFreeHost(e->h_ztoff);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
   delete e;
@@ -181,6 +188,15 @@ void sai_engine_destroy(sai_engine* e) {
 // buffers; as soon as a slice is complete it goes H2D and, once landed, through the genotype
 // pass, while the threads are already packing the following slices.  Three stages overlap: pack
 // (host cores, reads 4x the bytes it writes) | PCIe copy | K1.
+//
+// Wire format (sai_engine_set_i8_wire).  The packers saturate the host's memory system, so every
+// byte they do not write -- and the copy engine does not read back -- is throughput.  By default a
+// packer keeps the tile it has just packed in its L1, turns it into a zt record on the spot
+// (zt_simd.cpp) and streams the records of its block of tiles, back to back, to the block's fixed
+// region of the ring slot (region = where the dense tiles would have gone, so no packer waits for
+// another one's length).  A slice then goes out as ONE strided copy (rows = blocks, width = the
+// longest block) into a device stream buffer laid out the same way, followed by the slice's part
+// of the tile directory; k_zt_decode rebuilds the dense tiles in HBM in front of K1.
 struct I8Source {
   const int8_t* const* gt;
   const int64_t* row_stride;
@@ -212,6 +228,24 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
     SAI_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     e->ev.push_back(ev);
   }
+  const bool zt = e->i8_wire == 0;
+  const int P = lay->pairs_per_site;
+  std::vector<uint64_t> padc(P);
+  uint64_t* h_off = nullptr;
+  if (zt) {
+    for (int r = 0; r < P; ++r) padc[r] = pad_constant(*lay, r);
+    const size_t need = sizeof(uint64_t) * (size_t)(n_tiles + 1);
+    if (e->h_ztoff_cap < need) {
+      if (e->h_ztoff) SAI_CUDA_CHECK(cudaFreeHost(e->h_ztoff));
+      e->h_ztoff = nullptr;
+      e->h_ztoff_cap = 0;
+      SAI_CUDA_CHECK(cudaHostAlloc(&e->h_ztoff, need + need / 4, cudaHostAllocDefault));
+      e->h_ztoff_cap = need + need / 4;
+    }
+    h_off = static_cast<uint64_t*>(e->h_ztoff);
+    if (int k = grow(e->zt, (size_t)n_tiles * tile_bytes + 256)) return k;
+    if (int k = grow(e->ztoff, need + 256)) return k;
+  }
   int n_threads = e->host_threads > 0 ? e->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   // packing tasks: blocks of tiles, in slice order
   const int64_t block_tiles = std::max<int64_t>(1, std::min<int64_t>(32, (slice_tiles + 2 * n_threads - 1) / (2 * n_threads)));
@@ -222,6 +256,8 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
   };
   const int64_t n_tasks = (n_slices - 1) * blocks_per_slice + blocks_of(n_slices - 1);
   n_threads = (int)std::min<int64_t>(n_threads, n_tasks);
+  std::unique_ptr<uint32_t[]> used(new uint32_t[n_tasks]);  // zt: bytes of block i's records (whole 64-byte lines)
+  std::atomic<uint64_t> wire_bytes{0};
   std::atomic<int64_t> next_task{0};
   std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[n_slices]);
   for (int64_t s = 0; s < n_slices; ++s) done[s].store(0);
@@ -267,9 +303,33 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       }
       const int64_t t0 = s * slice_tiles, t1 = std::min(n_tiles, t0 + slice_tiles);
       const int slot = (int)(s % kRing);
-      cudaError_t ce = cudaMemcpyAsync(static_cast<char*>(e->packed.p) + (size_t)t0 * tile_bytes,
-                                       ring + (size_t)slot * slot_bytes, (size_t)(t1 - t0) * tile_bytes,
-                                       cudaMemcpyHostToDevice, e->s_copy);
+      cudaError_t ce = cudaSuccess;
+      if (!zt) {
+        ce = cudaMemcpyAsync(static_cast<char*>(e->packed.p) + (size_t)t0 * tile_bytes, ring + (size_t)slot * slot_bytes,
+                             (size_t)(t1 - t0) * tile_bytes, cudaMemcpyHostToDevice, e->s_copy);
+        wire_bytes.fetch_add((uint64_t)(t1 - t0) * tile_bytes, std::memory_order_relaxed);
+      } else {
+        // rows = the slice's blocks (pitch = a block's dense size), width = the longest record run;
+        // a shorter last block goes separately so that no row reaches past the slot
+        const int64_t nb = blocks_of(s), task0 = s * blocks_per_slice;
+        const bool short_last = (t1 - t0) % block_tiles != 0;
+        const int64_t rows = short_last ? nb - 1 : nb;
+        const size_t pitch = (size_t)block_tiles * tile_bytes;
+        size_t width = 0;
+        for (int64_t b = 0; b < rows; ++b) width = std::max<size_t>(width, used[task0 + b]);
+        char* dst = static_cast<char*>(e->zt.p) + (size_t)t0 * tile_bytes;
+        const uint8_t* srcp = ring + (size_t)slot * slot_bytes;
+        if (rows > 0 && width > 0)
+          ce = cudaMemcpy2DAsync(dst, pitch, srcp, pitch, width, (size_t)rows, cudaMemcpyHostToDevice, e->s_copy);
+        if (ce == cudaSuccess && short_last && used[task0 + nb - 1] > 0)
+          ce = cudaMemcpyAsync(dst + (size_t)rows * pitch, srcp + (size_t)rows * pitch, used[task0 + nb - 1],
+                               cudaMemcpyHostToDevice, e->s_copy);
+        if (ce == cudaSuccess)
+          ce = cudaMemcpyAsync(static_cast<uint64_t*>(e->ztoff.p) + t0, h_off + t0, sizeof(uint64_t) * (size_t)(t1 - t0),
+                               cudaMemcpyHostToDevice, e->s_copy);
+        wire_bytes.fetch_add((uint64_t)width * rows + (short_last ? used[task0 + nb - 1] : 0) + 8ull * (t1 - t0),
+                             std::memory_order_relaxed);
+      }
       if (ce == cudaSuccess) ce = cudaEventRecord(e->ev[slot], e->s_copy);
       if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->s_comp, e->ev[slot], 0);
       if (ce != cudaSuccess) {
@@ -279,14 +339,65 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       }
       ++next_issue;
       issued.store(next_issue, std::memory_order_release);
+      if (zt)
+        if (int k = sai_zt_decode(lay, e->zt.p, (uint64_t)n_tiles * tile_bytes, static_cast<const uint64_t*>(e->ztoff.p), t0,
+                                  t1 - t0, e->packed.p, e->s_comp)) {
+          fail_locked(k);
+          break;
+        }
       if (int k = sai_site_flags(lay, e->packed.p, t0, t1 - t0, n_tiles, jobs, n_jobs, d_mask_u, d_mask_q, d_qval,
                                  stride, nullptr, nullptr, 0, 0, e->s_comp))
         fail_locked(k);
     }
   };
+  // zt: the records of tiles [t0, t1) -> the block's region of the ring slot, as whole 64-byte lines
+  // written around the caches; returns the bytes written.  `tilebuf` (one dense tile) and `stage`
+  // (one record + the < 64 bytes carried over from the previous one) stay in this core's L1/L2.
+  auto pack_block_zt = [&](int64_t t0, int64_t t1, uint8_t* region, uint8_t* tilebuf, uint8_t* stage, uint8_t* tmp) {
+    const uint64_t dev_base = (uint64_t)t0 * tile_bytes;  // the device stream buffer is laid out like the dense tiles
+    size_t emitted = 0, carry = 0;                        // bytes streamed out / waiting at the head of `stage`
+    bool bad_here = false;
+    for (int64_t T = t0; T < t1; ++T) {
+      bad_here |= pack_tiles_i8_all(*lay, src.gt, src.row_stride, n_sites, T, T + 1, T, tilebuf, 0, false);
+      uint8_t* rec = stage + carry;
+      const size_t unpadded = zt_encode_tile(reinterpret_cast<const uint64_t*>(tilebuf), P, padc.data(), rec, tmp, 0);
+      size_t len = (unpadded + 7) & ~size_t(7);
+      uint64_t flag = 0;
+      if (len >= tile_bytes) {  // not smaller than the tile itself: raw
+        memcpy(rec, tilebuf, tile_bytes);
+        len = tile_bytes;
+        flag = 1ull << 63;
+      } else {
+        memset(rec + unpadded, 0, len - unpadded);
+      }
+      h_off[T] = (dev_base + emitted + carry) | flag;
+      const size_t total = carry + len, lines = total / 64;
+      stream_lines(region + emitted, stage, lines);
+      emitted += lines * 64;
+      carry = total - lines * 64;
+      if (carry) memmove(stage, stage + lines * 64, carry);
+    }
+    if (carry) {
+      memset(stage + carry, 0, 64 - carry);
+      stream_lines(region + emitted, stage, 1);
+      emitted += 64;
+    }
+    stream_fence();
+    if (bad_here) bad.store(1);
+    return emitted;
+  };
   const int device = e->device;
   auto worker = [&]() {
     cudaSetDevice(device);  // a fresh thread starts on device 0
+    std::unique_ptr<uint8_t[]> scratch;
+    uint8_t *tilebuf = nullptr, *stage = nullptr, *tmp = nullptr;
+    if (zt) {
+      const size_t stage_bytes = (64 + std::max(zt_record_cap(P), tile_bytes) + 63) & ~size_t(63);
+      scratch.reset(new uint8_t[64 + tile_bytes + stage_bytes + zt_tmp_cap(P)]);
+      tilebuf = scratch.get() + ((64 - reinterpret_cast<uintptr_t>(scratch.get()) % 64) % 64);
+      stage = tilebuf + tile_bytes;
+      tmp = stage + stage_bytes;
+    }
     for (;;) {
       const int64_t i = next_task.fetch_add(1);
       if (i >= n_tasks) break;
@@ -297,7 +408,11 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       const int64_t t0 = s * slice_tiles + b * block_tiles;
       const int64_t t1 = std::min(std::min(n_tiles, (s + 1) * slice_tiles), t0 + block_tiles);
       uint8_t* slot = ring + (size_t)(s % kRing) * slot_bytes;
-      if (pack_tiles_i8_all(*lay, src.gt, src.row_stride, n_sites, t0, t1, s * slice_tiles, slot, 0)) bad.store(1);
+      if (zt) {
+        used[i] = (uint32_t)pack_block_zt(t0, t1, slot + (size_t)(t0 - s * slice_tiles) * tile_bytes, tilebuf, stage, tmp);
+      } else if (pack_tiles_i8_all(*lay, src.gt, src.row_stride, n_sites, t0, t1, s * slice_tiles, slot, 0)) {
+        bad.store(1);
+      }
       if (done[s].fetch_add(1, std::memory_order_acq_rel) + 1 == (int)blocks_of(s)) issue_ready_slices();
     }
   };
@@ -306,6 +421,7 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
   for (auto& t : pool) t.join();
   issue_ready_slices();  // nothing left unless a packer bailed out
   const cudaError_t drained = cudaStreamSynchronize(e->s_copy);  // the ring may be reused by the next call
+  e->i8_wire_bytes = wire_bytes.load();
   if (rc == SAI_E_DOMAIN || (rc == SAI_OK && bad.load())) {
     set_error("a genotype value does not fit the bit-planes of its population");
     return SAI_E_DOMAIN;
@@ -470,6 +586,15 @@ int sai_engine_score_host_i8(sai_engine* e, const sai_layout* lay, const int8_t*
   return score_host_impl(e, lay, nullptr, nullptr, nullptr, &src, pos, n_sites, win_start, win_end, n_windows, jobs,
                          n_jobs, out);
 }
+
+int sai_engine_set_i8_wire(sai_engine* e, int32_t mode) {
+  SAI_REQUIRE(e, "NULL engine");
+  SAI_REQUIRE(mode == 0 || mode == 1, "wire format: 0 = zt records, 1 = dense tiles");
+  e->i8_wire = mode;
+  return SAI_OK;
+}
+
+uint64_t sai_engine_i8_wire_bytes(const sai_engine* e) { return e ? e->i8_wire_bytes : 0; }
 
 int sai_engine_set_host_threads(sai_engine* e, int32_t n_threads) {
   SAI_REQUIRE(e, "NULL engine");

@@ -14,9 +14,15 @@ namespace sai {
 bool pack_tiles_i8(const sai_layout& lay, int pop, const int8_t* gt, int64_t n_sites, int64_t row_stride,
                    int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa);
 // All populations, site by site (one sequential stream when the populations are column blocks of
-// one matrix): the int8 pipeline's packer.
+// one matrix): the int8 pipeline's packer.  Full cache lines go out with non-temporal stores when
+// the destination is 64-byte aligned, unless `allow_nt` is false (a tile that is consumed again
+// by this core, e.g. by the zt encoder).
 bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
-                       int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa);
+                       int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa, bool allow_nt = true);
+// n_lines 64-byte lines src -> dst (both 64-byte aligned) with non-temporal stores; stream_fence()
+// orders them before a later publication of the buffer.
+void stream_lines(uint8_t* dst, const uint8_t* src, size_t n_lines);
+void stream_fence();
 const char* pack_isa();
 
 }  // namespace sai

@@ -374,7 +374,7 @@ inline void scatter_site(const uint32_t* words, int n_pairs, uint8_t* tile_pop, 
 // DMA engine or a later pass, never by this core).  Returns true when a value does not fit its
 // population's bit-planes.
 bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
-                       int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa) {
+                       int64_t t0, int64_t t1, int64_t tile_base, uint8_t* packed_base, int isa, bool allow_nt) {
   const row_fn fn = row_fn_for(isa);
   const flush_fn flush = flush_fn_for(isa);
   const int pps = lay.pairs_per_site;
@@ -399,7 +399,7 @@ bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int
     const char* e = getenv("SAI_PACK_NT");
     return !(e && e[0] == '0');
   }();
-  const bool aligned = nt_enabled && (reinterpret_cast<uintptr_t>(packed_base) & 63) == 0;
+  const bool aligned = allow_nt && nt_enabled && (reinterpret_cast<uintptr_t>(packed_base) & 63) == 0;
   bool bad = false;
   for (int64_t T = t0; T < t1; ++T) {
     uint8_t* tile = packed_base + (size_t)(T - tile_base) * tile_bytes;
@@ -429,6 +429,22 @@ bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int
 #endif
   if (wbuf != stack_words) delete[] wbuf;
   return bad;
+}
+
+// n_lines 64-byte lines, src -> dst (both 64-byte aligned), written around the caches.
+void stream_lines(uint8_t* dst, const uint8_t* src, size_t n_lines) {
+#ifdef SAI_X86
+  for (size_t i = 0; i < n_lines * 4; ++i)
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + i, _mm_load_si128(reinterpret_cast<const __m128i*>(src) + i));
+#else
+  memcpy(dst, src, n_lines * 64);
+#endif
+}
+
+void stream_fence() {
+#ifdef SAI_X86
+  _mm_sfence();
+#endif
 }
 
 // One population of tiles [t0, t1) (sai_pack_i8).

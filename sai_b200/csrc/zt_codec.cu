@@ -28,34 +28,13 @@
 #include <vector>
 
 #include "common.cuh"
+#include "zt_format.cuh"
+#include "zt_simd.h"
 
 namespace sai {
 
 constexpr uint64_t kZtRaw = 1ull << 63;
 constexpr int kZtWarps = 8;
-
-// padding constant of row (pair index) r: ones for the unused individuals of the
-// population's last group in every plane word of the pair
-__host__ __device__ inline uint64_t pad_constant(const sai_layout& lay, int r) {
-  int pi = 0;
-  while (pi + 1 < lay.n_pops && r >= lay.pop[pi + 1].pair_off) ++pi;
-  const sai_pop_layout& L = lay.pop[pi];
-  uint64_t c = 0;
-  for (int h = 0; h < 2; ++h) {
-    const int word = (r - L.pair_off) * 2 + h;
-    if (word >= L.n_groups * L.bits) continue;  // zero padding word of an odd word count
-    const int real = L.n_samples - 32 * (word / L.bits);
-    const uint32_t bits = real >= 32 ? 0u : (0xffffffffu << real);
-    c |= (uint64_t)bits << (32 * h);
-  }
-  return c;
-}
-
-static inline uint32_t byte_mask(uint64_t v) {  // bit k set iff byte k of v is non-zero
-  const uint64_t lo7 = 0x7f7f7f7f7f7f7f7full;
-  const uint64_t m = (((v & lo7) + lo7) | v) & ~lo7;  // 0x80 in every non-zero byte
-  return (uint32_t)(((m >> 7) * 0x0102040810204080ull) >> 56);
-}
 
 static void run_parallel(int64_t n, int n_threads, const std::function<void(int64_t, int64_t)>& fn) {
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -186,8 +165,8 @@ uint64_t sai_zt_bound(const sai_layout* lay, int64_t n_sites) {
   return sai_packed_bytes(lay, n_sites) + 8;
 }
 
-int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_sites, uint8_t* out,
-                      uint64_t out_cap, uint64_t* tile_off, int32_t n_threads) {
+int64_t sai_zt_encode_isa(const sai_layout* lay, const uint8_t* packed, int64_t n_sites, uint8_t* out,
+                          uint64_t out_cap, uint64_t* tile_off, int32_t n_threads, int32_t isa) {
   if (int rc = validate_layout(lay)) return rc;
   SAI_REQUIRE(n_sites >= 0 && tile_off, "bad argument");
   const int64_t n_tiles = sai_num_tiles(n_sites);
@@ -203,18 +182,7 @@ int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_si
   run_parallel(n_tiles, n_threads, [&](int64_t t0, int64_t t1) {
     for (int64_t T = t0; T < t1; ++T) {
       const uint64_t* d = reinterpret_cast<const uint64_t*>(packed + (size_t)T * dense);
-      size_t n1 = 0, n2 = 0;
-      for (int r = 0; r < P; ++r) {
-        const uint64_t c = padc[r];
-        for (int s = 0; s < kTile; ++s) {
-          const uint64_t v = d[r * kTile + s] ^ c;
-          if (v) {
-            ++n1;
-            n2 += __builtin_popcount(byte_mask(v));
-          }
-        }
-      }
-      const size_t rec = (4 + 4 * (size_t)P + n1 + n2 + 7) & ~size_t(7);
+      const size_t rec = (zt_tile_size(d, P, padc.data(), isa) + 7) & ~size_t(7);
       raw[T] = rec >= dense;
       tile_off[T + 1] = raw[T] ? dense : rec;
     }
@@ -230,44 +198,31 @@ int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_si
     set_error("zt stream needs %llu bytes, buffer has %llu", (unsigned long long)at, (unsigned long long)out_cap);
     return SAI_E_CAPACITY;
   }
-  // pass 2: write the records
+  // pass 2: write the records (built in a private buffer: the vector encoder stores whole vectors)
   run_parallel(n_tiles, n_threads, [&](int64_t t0, int64_t t1) {
-    std::vector<uint8_t> tmp(dense);
+    std::vector<uint8_t> tmp(zt_tmp_cap(P)), rec(zt_record_cap(P));
     for (int64_t T = t0; T < t1; ++T) {
       const uint8_t* src = packed + (size_t)T * dense;
-      uint8_t* rec = out + (tile_off[T] & ~kZtRaw);
+      uint8_t* dst = out + (tile_off[T] & ~kZtRaw);
       if (tile_off[T] & kZtRaw) {
-        memcpy(rec, src, dense);
+        memcpy(dst, src, dense);
         continue;
       }
-      const uint64_t* d = reinterpret_cast<const uint64_t*>(src);
-      uint8_t* mp = rec + 4 + 4 * (size_t)P;
-      uint8_t* dp = tmp.data();
-      uint32_t n1 = 0;
-      for (int r = 0; r < P; ++r) {
-        const uint64_t c = padc[r];
-        uint32_t w = 0;
-        for (int s = 0; s < kTile; ++s) {
-          uint64_t v = d[r * kTile + s] ^ c;
-          if (!v) continue;
-          w |= 1u << s;
-          const uint32_t m = byte_mask(v);
-          mp[n1++] = (uint8_t)m;
-          for (int k = 0; k < 8; ++k, v >>= 8)
-            if (v & 0xff) *dp++ = (uint8_t)v;
-        }
-        memcpy(rec + 4 + 4 * (size_t)r, &w, 4);
-      }
-      memcpy(rec, &n1, 4);
-      const size_t n2 = dp - tmp.data();
-      memcpy(mp + n1, tmp.data(), n2);
-      const size_t used = 4 + 4 * (size_t)P + n1 + n2;
+      const size_t used = zt_encode_tile(reinterpret_cast<const uint64_t*>(src), P, padc.data(), rec.data(), tmp.data(), isa);
       const size_t end = (tile_off[T + 1] & ~kZtRaw) - (tile_off[T] & ~kZtRaw);
-      if (end > used) memset(rec + used, 0, end - used);
+      memset(rec.data() + used, 0, end - used);
+      memcpy(dst, rec.data(), end);
     }
   });
   return (int64_t)at;
 }
+
+int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_sites, uint8_t* out,
+                      uint64_t out_cap, uint64_t* tile_off, int32_t n_threads) {
+  return sai_zt_encode_isa(lay, packed, n_sites, out, out_cap, tile_off, n_threads, 0);
+}
+
+const char* sai_zt_isa(void) { return zt_isa(); }
 
 int sai_zt_decode_host(const sai_layout* lay, const uint8_t* stream, const uint64_t* tile_off, int64_t n_sites,
                        uint8_t* packed) {

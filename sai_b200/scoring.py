@@ -160,6 +160,15 @@ class HostEngine:
         """Host threads of the int8 pipeline (``score_matrices``); <= 0: all cores."""
         _cabi.check(_cabi.load().sai_engine_set_host_threads(self._handle(), int(n_threads)))
 
+    def set_i8_wire(self, dense: bool) -> None:
+        """Wire format of the int8 pipeline: zt records built by the packers (default) or dense
+        tiles (``dense=True``: data without a hom-ref majority).  Same results either way."""
+        _cabi.check(_cabi.load().sai_engine_set_i8_wire(self._handle(), 1 if dense else 0))
+
+    def i8_wire_bytes(self) -> int:
+        """Tile bytes the last int8 call copied to the GPU."""
+        return int(_cabi.load().sai_engine_i8_wire_bytes(self._handle()))
+
     def score_arrays(self, pg, ws, we, jobs, cap_u=None, cap_q=None) -> WindowResults:
         """``pg``: ``PackedGenotypes`` (dense tiles), ``ZtGenotypes`` (zero-suppressed wire format)
         or ``MatrixGenotypes`` (int8 matrices: packed by host threads slice by slice while earlier

@@ -112,6 +112,37 @@ def test_negative_table_for_dd():
     assert all(np.array_equal(getattr(a, k), getattr(b, k)) for k in ("neg_off", "neg_site", "neg_ind", "neg_val"))
 
 
+def test_zt_encoder_vector_path_is_identical():
+    """The AVX-512 VBMI2 record encoder (when this CPU has it) writes the bytes of the portable
+    one: sparse, half-dense and dense tiles, odd pair counts, padding constants, partial last tile."""
+    from sai_b200 import _cabi
+    from sai_b200.encode import pack_populations
+
+    lib = _cabi.load()
+    assert lib.sai_zt_isa() in (b"avx512vbmi2", b"portable")
+    rng = np.random.default_rng(77)
+    for sizes, ploidy, density in (((300, 90, 4), [2, 2, 2], 0.02), ((45, 33, 7, 70), [4, 3, 1, 8], 0.2),
+                                   ((64, 96, 32), [2, 2, 2], 0.9), ((1500, 1000, 4), [2, 2, 2], 0.05)):
+        n = 333
+        f = rng.beta(0.3, 3.0, size=n) * density * 5
+        mats = [rng.binomial(p, np.clip(f, 0, 1)[:, None], size=(n, k)).astype(np.int8) for k, p in zip(sizes, ploidy)]
+        mats[0][rng.random(mats[0].shape) < 0.01] = -1
+        pg = pack_populations(mats, ploidy, np.arange(1, n + 1))
+        outs = []
+        for isa in (1, 0):
+            cap = int(lib.sai_zt_bound(C.byref(pg.layout), n))
+            out = np.full(cap, 0xEE, dtype=np.uint8)
+            off = np.zeros(pg.n_tiles + 1, dtype=np.uint64)
+            length = lib.sai_zt_encode_isa(C.byref(pg.layout), pg.packed.ctypes.data, n, out.ctypes.data, cap, off.ctypes.data, 2, isa)
+            assert length >= 0
+            outs.append((out[:length].copy(), off))
+            assert (out[length:] == 0xEE).all()
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        back = np.empty_like(pg.packed)
+        assert lib.sai_zt_decode_host(C.byref(pg.layout), outs[1][0].ctypes.data, outs[1][1].ctypes.data, n, back.ctypes.data) == 0
+        assert np.array_equal(back, pg.packed)
+
+
 @pytest.mark.parametrize("shape", ["sparse", "dense", "mixed_bits", "tiny", "empty"])
 def test_zt_roundtrip_host(shape):
     """encode -> host decode is the identity on the packed tiles (sparse data, dense data that

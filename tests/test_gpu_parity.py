@@ -854,10 +854,12 @@ def _same_results(a, b, n_jobs, n_windows):
     (70_000, [1500, 1000, 4], [2, 2, 2], 0),  # 45 MB of tiles: three slices of the staging ring and a partial one
     (150_000, [1500, 1000, 4], [2, 2, 2], 5),  # more slices than ring slots: slots are reused
 ])
-def test_int8_pipeline_matches_packed_engine(n_sites, n_ind, ploidy, threads, engine):
+@pytest.mark.parametrize("wire", ["zt", "dense"])
+def test_int8_pipeline_matches_packed_engine(n_sites, n_ind, ploidy, threads, wire, engine):
     """sai_engine_score_host_i8 (int8 matrices packed by host threads into the pinned ring while
     earlier slices are copied and flagged) == packing first and sai_engine_score_host, bit for bit;
-    a follow-up batch of jobs over the resident tiles (sai_engine_score_resident) likewise."""
+    a follow-up batch of jobs over the resident tiles (sai_engine_score_resident) likewise.  Both
+    wire formats: zt records built by the packers (default; decoded on the GPU) and dense tiles."""
     from sai_b200.encode import pack_populations
     from sai_b200.scoring import make_job
     from sai_b200.windows import split_genome
@@ -882,13 +884,57 @@ def test_int8_pipeline_matches_packed_engine(n_sites, n_ind, ploidy, threads, en
     want = engine.score(pg, wins, jobs, **cap)
     want_more = engine.score(pg, wins, more, **cap)
     engine.set_host_threads(threads)
-    got, mg = engine.score_matrices(mats, ploidy, pos, wins, jobs, **cap)
-    got_more = engine.score_resident(more, **cap)
-    engine.set_host_threads(0)
+    engine.set_i8_wire(dense=wire == "dense")
+    try:
+        got, mg = engine.score_matrices(mats, ploidy, pos, wins, jobs, **cap)
+        wire_bytes = engine.i8_wire_bytes()
+        got_more = engine.score_resident(more, **cap)
+    finally:
+        engine.set_host_threads(0)
+        engine.set_i8_wire(dense=False)
+    if wire == "dense":
+        assert wire_bytes == pg.packed.nbytes
+    else:
+        assert 0 < wire_bytes <= pg.packed.nbytes + 8 * pg.n_tiles + 64 * pg.n_tiles
     assert [mg.layout.pop[i].bits for i in range(3)] == [pg.layout.pop[i].bits for i in range(3)]
     _same_results(got, want, len(jobs), len(wins))
     _same_results(got_more, want_more, 1, len(wins))
     assert n_sites < 100 or int(want.u.sum()) > 0
+
+
+@pytest.mark.parametrize("kind", ["incompressible", "all_hom_ref", "sparse"])
+def test_int8_pipeline_zt_wire_extremes(kind, engine):
+    """The packers' zt records at the extremes: tiles that do not compress (stored raw, flagged in
+    the directory), an all-zero matrix (records without payload) and a realistic sparse spectrum
+    (wire bytes well under the dense tiles) -- results equal the dense-tile engine's."""
+    from sai_b200.encode import pack_populations
+    from sai_b200.scoring import make_job
+    from sai_b200.windows import split_genome
+
+    rng = np.random.default_rng(len(kind))
+    n_sites, n_ind = 40_000, [700, 500, 3]
+    if kind == "incompressible":
+        mats = [rng.integers(-1, 3, size=(n_sites, n)).astype(np.int8) for n in n_ind]
+    elif kind == "all_hom_ref":
+        mats = [np.zeros((n_sites, n), dtype=np.int8) for n in n_ind]
+    else:
+        f = rng.beta(0.15, 3.0, size=n_sites)
+        mats = [rng.binomial(2, f[:, None], size=(n_sites, n)).astype(np.int8) for n in n_ind]
+        mats[2][rng.random(n_sites) < 0.05] = 2
+    pos = np.cumsum(rng.integers(1, 60, size=n_sites)).astype(np.int32)
+    wins = split_genome([int(pos[0]), int(pos[-1])], 50_000, 10_000)
+    job = make_job(0, 1, [2], False, u=dict(w=0.3, x=0.2, y_list=[(">=", 0.5)]), q=dict(w=0.3, quantile=0.95, y_list=[(">=", 0.5)]))
+    pg = pack_populations(mats, [2, 2, 2], pos)
+    want = engine.score(pg, wins, [job])
+    got, _ = engine.score_matrices(mats, [2, 2, 2], pos, wins, [job])
+    _same_results(got, want, 1, len(wins))
+    wire_bytes = engine.i8_wire_bytes()
+    if kind == "incompressible":
+        assert pg.packed.nbytes <= wire_bytes <= pg.packed.nbytes + 72 * pg.n_tiles
+    elif kind == "all_hom_ref":
+        assert wire_bytes < 0.05 * pg.packed.nbytes
+    else:
+        assert wire_bytes < 0.5 * pg.packed.nbytes
 
 
 def test_int8_pipeline_widens_the_planes_when_the_data_needs_it(engine):
