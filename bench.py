@@ -588,9 +588,9 @@ def main():
     if Ke > 0:
         from sai_b200.encode import MatrixGenotypes, compress, pack_populations
 
-        # this rank's share of the host cores; with several ranks one core per rank is left to the thread
-        # that feeds the copy engine (the 8-GPU boxes of this pool have 4 vCPUs per GPU)
-        host_threads = max(1, (os.cpu_count() or 1) // world - (1 if world > 1 else 0))
+        # this rank's share of the host cores (the 8-GPU boxes of this pool have 4 vCPUs per GPU); the packers
+        # issue the copies and launches themselves and the calling thread sleeps in the C call, so no core is set aside
+        host_threads = max(1, (os.cpu_count() or 1) // world)
         host_threads = _env_int("SAI_BENCH_HOST_THREADS", host_threads) or host_threads  # tuning knob (tools/)
         t0 = time.perf_counter()
         h_i8 = device_unpack_i8(lay, d_packed, S)  # [S, 2504] int8, pageable (synthetic-data preparation, untimed)

@@ -27,6 +27,7 @@ struct sai_engine {
   int device = 0;
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   std::vector<cudaEvent_t> ev;
+  std::vector<cudaEvent_t> ev_dec;    // int8 pipeline, zt wire: slice decoded (its device ring slot is free again)
   int host_threads = 0;               // packer threads of the int8 pipeline (0: hardware concurrency)
   int i8_wire = 0;                    // wire format of the int8 pipeline: 0 = zt records, 1 = dense tiles
   void* ring = nullptr;               // pinned staging ring of the int8 pipeline
@@ -175,6 +176,7 @@ void sai_engine_destroy(sai_engine* e) {
   for (auto* b : {&e->packed, &e->pos, &e->win, &e->mask, &e->qval, &e->res, &e->cand, &e->counts, &e->sums, &e->hist, &e->neg, &e->dd, &e->zt, &e->ztoff})
     if (b->p) cudaFree(b->p);
   for (auto ev : e->ev) cudaEventDestroy(ev);
+  for (auto ev : e->ev_dec) cudaEventDestroy(ev);
   if (e->ring) cudaFreeHost(e->ring);
   if (e->h_ztoff) cudaFreeHost(e->h_ztoff);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
@@ -195,8 +197,9 @@ void sai_engine_destroy(sai_engine* e) {
 // (zt_simd.cpp) and streams the records of its block of tiles, back to back, to the block's fixed
 // region of the ring slot (region = where the dense tiles would have gone, so no packer waits for
 // another one's length).  A slice then goes out as ONE strided copy (rows = blocks, width = the
-// longest block) into a device stream buffer laid out the same way, followed by the slice's part
-// of the tile directory; k_zt_decode rebuilds the dense tiles in HBM in front of K1.
+// longest block) into a device ring laid out like the pinned one, followed by the slice's part of
+// the tile directory; k_zt_decode rebuilds the dense tiles in HBM in front of K1 and frees the
+// device slot.
 struct I8Source {
   const int8_t* const* gt;
   const int64_t* row_stride;
@@ -243,12 +246,23 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       e->h_ztoff_cap = need + need / 4;
     }
     h_off = static_cast<uint64_t*>(e->h_ztoff);
-    if (int k = grow(e->zt, (size_t)n_tiles * tile_bytes + 256)) return k;
+    // the records live in a device ring laid out like the pinned one: a slot is rewritten once its
+    // slice has been decoded (ev_dec)
+    if (int k = grow(e->zt, slot_bytes * kRing + 256)) return k;
     if (int k = grow(e->ztoff, need + 256)) return k;
+    while ((int64_t)e->ev_dec.size() < kRing) {
+      cudaEvent_t ev;
+      SAI_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->ev_dec.push_back(ev);
+    }
   }
   int n_threads = e->host_threads > 0 ? e->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   // packing tasks: blocks of tiles, in slice order
-  const int64_t block_tiles = std::max<int64_t>(1, std::min<int64_t>(32, (slice_tiles + 2 * n_threads - 1) / (2 * n_threads)));
+  int64_t block_cap = 32;
+#ifdef SAI_EXPERIMENTS
+  if (const char* v = getenv("SAI_I8_BLOCK_TILES")) block_cap = std::max(1, atoi(v));
+#endif
+  const int64_t block_tiles = std::max<int64_t>(1, std::min<int64_t>(block_cap, (slice_tiles + 2 * n_threads - 1) / (2 * n_threads)));
   const int64_t blocks_per_slice = (slice_tiles + block_tiles - 1) / block_tiles;
   auto blocks_of = [&](int64_t s) {
     const int64_t tiles = std::min(slice_tiles, n_tiles - s * slice_tiles);
@@ -317,9 +331,10 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
         const size_t pitch = (size_t)block_tiles * tile_bytes;
         size_t width = 0;
         for (int64_t b = 0; b < rows; ++b) width = std::max<size_t>(width, used[task0 + b]);
-        char* dst = static_cast<char*>(e->zt.p) + (size_t)t0 * tile_bytes;
+        char* dst = static_cast<char*>(e->zt.p) + (size_t)slot * slot_bytes;
         const uint8_t* srcp = ring + (size_t)slot * slot_bytes;
-        if (rows > 0 && width > 0)
+        if (s >= kRing) ce = cudaStreamWaitEvent(e->s_copy, e->ev_dec[slot], 0);  // the slot's previous slice is decoded
+        if (ce == cudaSuccess && rows > 0 && width > 0)
           ce = cudaMemcpy2DAsync(dst, pitch, srcp, pitch, width, (size_t)rows, cudaMemcpyHostToDevice, e->s_copy);
         if (ce == cudaSuccess && short_last && used[task0 + nb - 1] > 0)
           ce = cudaMemcpyAsync(dst + (size_t)rows * pitch, srcp + (size_t)rows * pitch, used[task0 + nb - 1],
@@ -339,12 +354,18 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       }
       ++next_issue;
       issued.store(next_issue, std::memory_order_release);
-      if (zt)
-        if (int k = sai_zt_decode(lay, e->zt.p, (uint64_t)n_tiles * tile_bytes, static_cast<const uint64_t*>(e->ztoff.p), t0,
-                                  t1 - t0, e->packed.p, e->s_comp)) {
+      if (zt) {
+        int k = sai_zt_decode(lay, e->zt.p, (uint64_t)slot_bytes * kRing, static_cast<const uint64_t*>(e->ztoff.p), t0, t1 - t0,
+                              e->packed.p, e->s_comp);
+        if (k == SAI_OK && cudaEventRecord(e->ev_dec[slot], e->s_comp) != cudaSuccess) {
+          set_error("int8 pipeline: cudaEventRecord failed");
+          k = SAI_E_CUDA;
+        }
+        if (k) {
           fail_locked(k);
           break;
         }
+      }
       if (int k = sai_site_flags(lay, e->packed.p, t0, t1 - t0, n_tiles, jobs, n_jobs, d_mask_u, d_mask_q, d_qval,
                                  stride, nullptr, nullptr, 0, 0, e->s_comp))
         fail_locked(k);
@@ -354,7 +375,7 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
   // written around the caches; returns the bytes written.  `tilebuf` (one dense tile) and `stage`
   // (one record + the < 64 bytes carried over from the previous one) stay in this core's L1/L2.
   auto pack_block_zt = [&](int64_t t0, int64_t t1, uint8_t* region, uint8_t* tilebuf, uint8_t* stage, uint8_t* tmp) {
-    const uint64_t dev_base = (uint64_t)t0 * tile_bytes;  // the device stream buffer is laid out like the dense tiles
+    const uint64_t dev_base = (uint64_t)(region - ring);  // the device ring is laid out like the pinned one
     size_t emitted = 0, carry = 0;                        // bytes streamed out / waiting at the head of `stage`
     bool bad_here = false;
     for (int64_t T = t0; T < t1; ++T) {

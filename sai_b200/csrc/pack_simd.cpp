@@ -348,6 +348,27 @@ flush_fn flush_fn_for(int isa) {
 
 inline void prefetch_row(const int8_t* row, int n) {
 #ifdef SAI_X86
+#ifdef SAI_EXPERIMENTS
+  static const int hint = [] { const char* e = getenv("SAI_PACK_HINT"); return e ? atoi(e) : 0; }();  // A/B knob
+  if (hint == 1) {
+    for (int i = 0; i < n; i += 64) _mm_prefetch(reinterpret_cast<const char*>(row + i), _MM_HINT_T1);
+    return;
+  }
+  if (hint == 2) {
+    for (int i = 0; i < n; i += 64) _mm_prefetch(reinterpret_cast<const char*>(row + i), _MM_HINT_T2);
+    return;
+  }
+  if (hint == 3) {
+    for (int i = 0; i < n; i += 64) _mm_prefetch(reinterpret_cast<const char*>(row + i), _MM_HINT_NTA);
+    return;
+  }
+  if (hint == 4) {  // first line of every 4 KB page only: leave the rest to the hardware streamer
+    const uintptr_t a = reinterpret_cast<uintptr_t>(row), b = a + n;
+    _mm_prefetch(reinterpret_cast<const char*>(row), _MM_HINT_T0);
+    for (uintptr_t pg = (a | 4095) + 1; pg < b; pg += 4096) _mm_prefetch(reinterpret_cast<const char*>(pg), _MM_HINT_T0);
+    return;
+  }
+#endif
   for (int i = 0; i < n; i += 64) _mm_prefetch(reinterpret_cast<const char*>(row + i), _MM_HINT_T0);
 #else
   (void)row, (void)n;
@@ -382,15 +403,12 @@ bool pack_tiles_i8_all(const sai_layout& lay, const int8_t* const* gt, const int
   const int col_words = 2 * pps;  // words of one site's whole column (zero pad words included)
   constexpr int kBatch = 8;       // sites per output cache line
   // +16: the vector row packers and the line writer move whole 64-byte vectors
-  // +16: the vector row packers and the line writer move whole 64-byte vectors
   uint32_t stack_words[kBatch * 512 + 16];
   const int wstride = col_words + 2;
   uint32_t* wbuf = wstride <= 512 ? stack_words : new uint32_t[(size_t)kBatch * wstride + 16];
 #ifdef SAI_EXPERIMENTS
-  static const int kAhead = [] {  // tools/ A/B knob: prefetch distance in sites
-    const char* e = getenv("SAI_PACK_AHEAD");
-    return e ? atoi(e) : 4;
-  }();
+  const char* ahead_env = getenv("SAI_PACK_AHEAD");  // tools/ A/B knob (read per call: one process can sweep it)
+  const int kAhead = ahead_env ? atoi(ahead_env) : 4;
 #else
   constexpr int kAhead = 4;  // sites
 #endif
