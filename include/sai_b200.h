@@ -404,9 +404,11 @@ int sai_engine_score_host_zt(sai_engine* e, const sai_layout* lay, const uint8_t
  * (gt[p][site * row_stride[p] + individual], negative = missing; what reshape_genotypes leaves
  * in memory, sai/utils/utils.py:405-410, narrowed to int8), ordinary pageable host memory.
  * A pool of host threads (sai_engine_set_host_threads; default: all cores) packs 32 MB slices
- * of tiles into a ring of pinned staging buffers with the CPU's vector unit (sai_pack_isa); each
- * finished slice is copied to the GPU and flagged while the following slices are being packed,
- * so the call costs about max(pack, copy) instead of pack + copy.  Returns SAI_E_DOMAIN when a
+ * of tiles into a ring of pinned staging buffers with the CPU's vector unit (sai_pack_isa) --
+ * by default as zt records encoded while a tile is still in the packer's L1 (sai_zt_isa,
+ * sai_engine_set_i8_wire); each finished slice is copied to the GPU, expanded and flagged while
+ * the following slices are being packed, so the call costs about max(pack, copy) instead of
+ * pack + copy.  Returns SAI_E_DOMAIN when a
  * value does not fit the layout's bit-planes (retry with a wider layout). */
 int sai_engine_score_host_i8(sai_engine* e, const sai_layout* lay, const int8_t* const* gt,
                              const int64_t* row_stride, const int32_t* pos, int64_t n_sites,
