@@ -644,9 +644,9 @@ def main():
         Ki = max(2, min(Ke, 5))
         r2, same_i8, t_i8 = run_wire(mg, Ki)  # default wire: zt records built by the packers
         i8_wire_bytes = eng.i8_wire_bytes()
-        eng.set_i8_wire(dense=True)
+        eng.set_i8_wire("dense")
         _, same_i8_dense, t_i8_dense = run_wire(mg, Ki)
-        eng.set_i8_wire(dense=False)
+        eng.set_i8_wire("auto")
         _, same_zt, t_zt = run_wire(zt, Ke)
         _, same_dense, t_dense = run_wire(pg, Ke)
         small = pos.nbytes + ws.nbytes + we.nbytes
@@ -667,7 +667,7 @@ def main():
                      f"({_cabi.load().sai_zt_isa().decode()} record encoder), records streamed into pinned 32 MB ring slots, "
                      "pipelined with the copy, the device-side decode and K1",
             "host_threads": host_threads,
-            "wire": "zt records built by the packers", "wire_ratio": packed_bytes / max(1, i8_wire_bytes),
+            "wire": "zt records built by the packers" if i8_wire_bytes < packed_bytes else "dense tiles (no vector record encoder on this CPU)", "wire_ratio": packed_bytes / max(1, i8_wire_bytes),
             "int8_gbps": h_i8.nbytes / t_i8 / 1e9,
             "pack_alone_ms": 1e3 * t_pack, "pack_alone_gbps_int8": h_i8.nbytes / t_pack / 1e9, "pack_reproduces_device_tiles": pack_matches,
             "pack_alone_note": "dense packer alone (int8 -> dense tiles in a pinned buffer, no GPU work)",
@@ -677,7 +677,7 @@ def main():
                 "value": world * W / t_i8_dense, "unit": "windows/s", "ms_per_step": 1e3 * t_i8_dense,
                 "h2d_bytes_per_step": int(packed_bytes + small), "matches_device_path": same_i8_dense,
                 "pipeline_vs_slowest_stage": t_i8_dense / max(t_pack, t_dense),
-                "note": "same call with sai_engine_set_i8_wire(1): dense tiles through the ring (data without a hom-ref majority)",
+                "note": "same call with sai_engine_set_i8_wire(e, 1): dense tiles through the ring (data without a hom-ref majority)",
             },
             "prepacked_zt": {
                 "value": world * W / t_zt, "unit": "windows/s", "h2d_bytes_per_step": int(zt.stream.nbytes + zt.tile_off.nbytes + small),

@@ -414,11 +414,13 @@ int sai_engine_score_host_i8(sai_engine* e, const sai_layout* lay, const int8_t*
                              const int64_t* row_stride, const int32_t* pos, int64_t n_sites,
                              const int64_t* win_start, const int64_t* win_end, int64_t n_windows,
                              const sai_job* jobs, int32_t n_jobs, sai_host_results* out);
-/* Wire format of the int8 pipeline.  0 (default): every packer turns the tile it has just packed
- * into a zt record while it is still in its L1 and only the records cross host memory and PCIe
- * (k_zt_decode rebuilds the dense tiles in HBM) -- the packers are bound by the host's memory
- * system, so the bytes not written and not read back by the copy engine are throughput.
- * 1: dense tiles (data known not to compress: no hom-ref majority).  Results are identical.
+/* Wire format of the int8 pipeline.  2 = zt records: every packer turns the tile it has just
+ * packed into a zt record while it is still in its L1 and only the records cross host memory and
+ * PCIe (k_zt_decode rebuilds the dense tiles in HBM) -- the packers are bound by the host's
+ * memory system, so the bytes not written and not read back by the copy engine are throughput.
+ * 1 = dense tiles (data known not to compress: no hom-ref majority).  0 (default) = auto: zt
+ * when this CPU has the vector record encoder (sai_zt_isa() != "portable"), else dense.
+ * Results are identical.
  * sai_engine_i8_wire_bytes: tile bytes the last sai_engine_score_host_i8 call copied. */
 int sai_engine_set_i8_wire(sai_engine* e, int32_t mode);
 uint64_t sai_engine_i8_wire_bytes(const sai_engine* e);

@@ -7,6 +7,7 @@
 // batch of device->host copies.  Device buffers are grow-only and reused across
 // calls (one engine per GPU / per worker process).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <atomic>
@@ -29,7 +30,7 @@ struct sai_engine {
   std::vector<cudaEvent_t> ev;
   std::vector<cudaEvent_t> ev_dec;    // int8 pipeline, zt wire: slice decoded (its device ring slot is free again)
   int host_threads = 0;               // packer threads of the int8 pipeline (0: hardware concurrency)
-  int i8_wire = 0;                    // wire format of the int8 pipeline: 0 = zt records, 1 = dense tiles
+  int i8_wire = 0;                    // wire format of the int8 pipeline: 0 = auto, 1 = dense tiles, 2 = zt records
   void* ring = nullptr;               // pinned staging ring of the int8 pipeline
   size_t ring_cap = 0;
   void* h_ztoff = nullptr;            // pinned tile directory of the int8 pipeline's zt records
@@ -231,7 +232,8 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
     SAI_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     e->ev.push_back(ev);
   }
-  const bool zt = e->i8_wire == 0;
+  // auto: zt records when this CPU has the vector record encoder (the portable one would be the bottleneck)
+  const bool zt = e->i8_wire == 2 || (e->i8_wire == 0 && strcmp(zt_isa(), "portable") != 0);
   const int P = lay->pairs_per_site;
   std::vector<uint64_t> padc(P);
   uint64_t* h_off = nullptr;
@@ -610,7 +612,7 @@ int sai_engine_score_host_i8(sai_engine* e, const sai_layout* lay, const int8_t*
 
 int sai_engine_set_i8_wire(sai_engine* e, int32_t mode) {
   SAI_REQUIRE(e, "NULL engine");
-  SAI_REQUIRE(mode == 0 || mode == 1, "wire format: 0 = zt records, 1 = dense tiles");
+  SAI_REQUIRE(mode >= 0 && mode <= 2, "wire format: 0 = auto, 1 = dense tiles, 2 = zt records");
   e->i8_wire = mode;
   return SAI_OK;
 }

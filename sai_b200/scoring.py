@@ -160,10 +160,11 @@ class HostEngine:
         """Host threads of the int8 pipeline (``score_matrices``); <= 0: all cores."""
         _cabi.check(_cabi.load().sai_engine_set_host_threads(self._handle(), int(n_threads)))
 
-    def set_i8_wire(self, dense: bool) -> None:
-        """Wire format of the int8 pipeline: zt records built by the packers (default) or dense
-        tiles (``dense=True``: data without a hom-ref majority).  Same results either way."""
-        _cabi.check(_cabi.load().sai_engine_set_i8_wire(self._handle(), 1 if dense else 0))
+    def set_i8_wire(self, mode: str = "auto") -> None:
+        """Wire format of the int8 pipeline: ``"zt"`` records built by the packers, ``"dense"`` tiles
+        (data without a hom-ref majority) or ``"auto"`` (default: zt when the CPU has the vector
+        record encoder).  Same results either way."""
+        _cabi.check(_cabi.load().sai_engine_set_i8_wire(self._handle(), {"auto": 0, "dense": 1, "zt": 2}[mode]))
 
     def i8_wire_bytes(self) -> int:
         """Tile bytes the last int8 call copied to the GPU."""

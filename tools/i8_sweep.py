@@ -77,7 +77,7 @@ def main():
         env = dict(base)
         env.update({k: v for k, v in cfg.items() if k.startswith("SAI_")})
         os.environ.update(env)
-        eng.set_i8_wire(dense=cfg["wire"] == "dense")
+        eng.set_i8_wire(cfg["wire"])
         eng.set_host_threads(cfg.get("threads", 0))
         arr = g
         note = {}
