@@ -1,13 +1,14 @@
 #!/bin/bash
-# 8-GPU box: the end-to-end leg with the packers' zt wire (host threads = all of a rank's cores), N = 8 only.
+# Multi-GPU box: the end-to-end leg with the packers' zt wire (host threads = all of a rank's cores); NS="8" (default), "4", "2".
 O=gpurun_out; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-for N in 8; do
+for N in ${NS:-8}; do
   timeout 500 $TR --nproc-per-node $N --master-port $((29900+N)) bench.py --gpus $N --steps 10 --warmup 3 --e2e-steps 3 --no-strong > $O/bench_zt_n$N.log 2> $O/bench_zt_n$N.err; echo "bench N=$N exit $?" >> $O/bench_zt_n$N.err
 done
 python - <<'PY'
 import json
-for n in (8,):
+import os
+for n in [int(x) for x in os.environ.get('NS', '8').split()]:
     try:
         d = json.loads(open(f'gpurun_out/bench_zt_n{n}.log').read().strip().splitlines()[-1])
         e = d['e2e'] or {}
@@ -17,4 +18,4 @@ for n in (8,):
     except Exception as ex:
         print(n, 'parse failed', ex)
 PY
-tail -3 $O/bench_zt_n8.err
+tail -3 $O/bench_zt_n*.err
