@@ -353,6 +353,15 @@ int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_si
 const char* sai_zt_isa(void);
 int64_t sai_zt_encode_isa(const sai_layout* lay, const uint8_t* packed, int64_t n_sites, uint8_t* out,
                           uint64_t out_cap, uint64_t* tile_off, int32_t n_threads, int32_t isa);
+/* Host: int8 matrices (arguments as sai_pack_i8_all) -> the same stream and directory as
+ * sai_zt_encode(sai_pack_i8_all(...)), byte for byte, without the dense tiles ever leaving the
+ * packers' L1 caches (the int8 pipeline's encoder; also the fast way to build a compressed
+ * on-disk cache).  Returns the stream length or a negative SAI_E_* code (SAI_E_DOMAIN: a value
+ * does not fit the layout's bit-planes; SAI_E_CAPACITY: out_cap too small -- sai_zt_bound is
+ * always enough). */
+int64_t sai_zt_pack_i8(const sai_layout* lay, const int8_t* const* gt, const int64_t* row_stride,
+                       int64_t n_sites, uint8_t* out, uint64_t out_cap, uint64_t* tile_off,
+                       int32_t n_threads);
 /* Host decoder (tests, tools). */
 int sai_zt_decode_host(const sai_layout* lay, const uint8_t* stream, const uint64_t* tile_off,
                        int64_t n_sites, uint8_t* packed);

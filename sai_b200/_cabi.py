@@ -156,6 +156,7 @@ SYMBOLS = {
     "sai_zt_encode": (_I64, [_LAY, _P, _I64, _P, _U64, _P, _I32]),
     "sai_zt_encode_isa": (_I64, [_LAY, _P, _I64, _P, _U64, _P, _I32, _I32]),
     "sai_zt_isa": (C.c_char_p, []),
+    "sai_zt_pack_i8": (_I64, [_LAY, _P, _P, _I64, _P, _U64, _P, _I32]),
     "sai_zt_decode_host": (C.c_int, [_LAY, _P, _P, _I64, _P]),
     "sai_zt_decode": (C.c_int, [_LAY, _P, _U64, _P, _I64, _I64, _P, _P]),
     "sai_synth_fill": (C.c_int, [_LAY, _P, _I64, _I64, _I64, _P, _U64, C.c_double, _P]),

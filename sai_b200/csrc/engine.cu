@@ -373,54 +373,10 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
         fail_locked(k);
     }
   };
-  // zt: the records of tiles [t0, t1) -> the block's region of the ring slot, as whole 64-byte lines
-  // written around the caches; returns the bytes written.  `tilebuf` (one dense tile) and `stage`
-  // (one record + the < 64 bytes carried over from the previous one) stay in this core's L1/L2.
-  auto pack_block_zt = [&](int64_t t0, int64_t t1, uint8_t* region, uint8_t* tilebuf, uint8_t* stage, uint8_t* tmp) {
-    const uint64_t dev_base = (uint64_t)(region - ring);  // the device ring is laid out like the pinned one
-    size_t emitted = 0, carry = 0;                        // bytes streamed out / waiting at the head of `stage`
-    bool bad_here = false;
-    for (int64_t T = t0; T < t1; ++T) {
-      bad_here |= pack_tiles_i8_all(*lay, src.gt, src.row_stride, n_sites, T, T + 1, T, tilebuf, 0, false);
-      uint8_t* rec = stage + carry;
-      const size_t unpadded = zt_encode_tile(reinterpret_cast<const uint64_t*>(tilebuf), P, padc.data(), rec, tmp, 0);
-      size_t len = (unpadded + 7) & ~size_t(7);
-      uint64_t flag = 0;
-      if (len >= tile_bytes) {  // not smaller than the tile itself: raw
-        memcpy(rec, tilebuf, tile_bytes);
-        len = tile_bytes;
-        flag = 1ull << 63;
-      } else {
-        memset(rec + unpadded, 0, len - unpadded);
-      }
-      h_off[T] = (dev_base + emitted + carry) | flag;
-      const size_t total = carry + len, lines = total / 64;
-      stream_lines(region + emitted, stage, lines);
-      emitted += lines * 64;
-      carry = total - lines * 64;
-      if (carry) memmove(stage, stage + lines * 64, carry);
-    }
-    if (carry) {
-      memset(stage + carry, 0, 64 - carry);
-      stream_lines(region + emitted, stage, 1);
-      emitted += 64;
-    }
-    stream_fence();
-    if (bad_here) bad.store(1);
-    return emitted;
-  };
   const int device = e->device;
   auto worker = [&]() {
     cudaSetDevice(device);  // a fresh thread starts on device 0
-    std::unique_ptr<uint8_t[]> scratch;
-    uint8_t *tilebuf = nullptr, *stage = nullptr, *tmp = nullptr;
-    if (zt) {
-      const size_t stage_bytes = (64 + std::max(zt_record_cap(P), tile_bytes) + 63) & ~size_t(63);
-      scratch.reset(new uint8_t[64 + tile_bytes + stage_bytes + zt_tmp_cap(P)]);
-      tilebuf = scratch.get() + ((64 - reinterpret_cast<uintptr_t>(scratch.get()) % 64) % 64);
-      stage = tilebuf + tile_bytes;
-      tmp = stage + stage_bytes;
-    }
+    std::unique_ptr<ZtBlockScratch> scratch(zt ? new ZtBlockScratch(P) : nullptr);
     for (;;) {
       const int64_t i = next_task.fetch_add(1);
       if (i >= n_tasks) break;
@@ -432,7 +388,13 @@ static int stream_tiles_from_i8(sai_engine* e, const sai_layout* lay, const I8So
       const int64_t t1 = std::min(std::min(n_tiles, (s + 1) * slice_tiles), t0 + block_tiles);
       uint8_t* slot = ring + (size_t)(s % kRing) * slot_bytes;
       if (zt) {
-        used[i] = (uint32_t)pack_block_zt(t0, t1, slot + (size_t)(t0 - s * slice_tiles) * tile_bytes, tilebuf, stage, tmp);
+        // the block's records -> its region of the ring slot (= where its dense tiles would go); the device
+        // ring is laid out like the pinned one, so a record's device offset is its offset in the ring
+        uint8_t* region = slot + (size_t)(t0 - s * slice_tiles) * tile_bytes;
+        bool bad_here = false;
+        used[i] = (uint32_t)zt_pack_block_i8(*lay, src.gt, src.row_stride, n_sites, t0, t1, padc.data(), region,
+                                             (uint64_t)(region - ring), h_off, *scratch, true, &bad_here);
+        if (bad_here) bad.store(1);
       } else if (pack_tiles_i8_all(*lay, src.gt, src.row_stride, n_sites, t0, t1, s * slice_tiles, slot, 0)) {
         bad.store(1);
       }

@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <functional>
 #include <thread>
 #include <vector>
@@ -223,6 +224,69 @@ int64_t sai_zt_encode(const sai_layout* lay, const uint8_t* packed, int64_t n_si
 }
 
 const char* sai_zt_isa(void) { return zt_isa(); }
+
+int64_t sai_zt_pack_i8(const sai_layout* lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
+                       uint8_t* out, uint64_t out_cap, uint64_t* tile_off, int32_t n_threads) {
+  if (int rc = validate_layout(lay)) return rc;
+  SAI_REQUIRE(gt && row_stride && tile_off && n_sites >= 0, "NULL argument");
+  for (int p = 0; p < lay->n_pops; ++p) {
+    SAI_REQUIRE(n_sites == 0 || gt[p], "NULL genotype matrix of population %d", p);
+    SAI_REQUIRE(row_stride[p] >= lay->pop[p].n_samples, "row_stride of population %d smaller than n_samples", p);
+  }
+  const int64_t n_tiles = sai_num_tiles(n_sites);
+  tile_off[0] = 0;
+  if (n_tiles == 0) return 0;
+  SAI_REQUIRE(out, "NULL argument");
+  const int P = lay->pairs_per_site;
+  const size_t tile_bytes = (size_t)P * kTile * 8;
+  std::vector<uint64_t> padc(P);
+  for (int r = 0; r < P; ++r) padc[r] = pad_constant(*lay, r);
+  // blocks of tiles are encoded into private buffers (their lengths are not known in advance),
+  // then laid end to end in `out`
+  const int64_t block = 32, n_blocks = (n_tiles + block - 1) / block;
+  std::vector<std::vector<uint8_t>> recs(n_blocks);
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<int64_t>(n_threads, n_blocks);
+  std::atomic<int64_t> next{0};
+  std::atomic<int> domain_err{0};
+  auto encode = [&]() {
+    ZtBlockScratch sc(P);
+    std::vector<uint8_t> region((size_t)block * tile_bytes + 64);
+    uint8_t* reg = region.data() + ((64 - reinterpret_cast<uintptr_t>(region.data()) % 64) % 64);
+    bool bad = false;
+    for (int64_t b = next.fetch_add(1); b < n_blocks; b = next.fetch_add(1)) {
+      const int64_t t0 = b * block, t1 = std::min(n_tiles, t0 + block);
+      const size_t used = zt_pack_block_i8(*lay, gt, row_stride, n_sites, t0, t1, padc.data(), reg, 0, tile_off, sc, false, &bad);
+      recs[b].assign(reg, reg + used);
+    }
+    if (bad) domain_err.store(1, std::memory_order_relaxed);
+  };
+  {
+    std::vector<std::thread> th;
+    for (int i = 1; i < n_threads; ++i) th.emplace_back(encode);
+    encode();
+    for (auto& t : th) t.join();
+  }
+  if (domain_err.load()) {
+    set_error("a genotype value does not fit the bit-planes of its population");
+    return SAI_E_DOMAIN;
+  }
+  std::vector<uint64_t> base(n_blocks + 1, 0);
+  for (int64_t b = 0; b < n_blocks; ++b) base[b + 1] = base[b] + recs[b].size();
+  const uint64_t total = base[n_blocks];
+  if (total > out_cap) {
+    set_error("zt stream needs %llu bytes, buffer has %llu", (unsigned long long)total, (unsigned long long)out_cap);
+    return SAI_E_CAPACITY;
+  }
+  run_parallel(n_blocks, n_threads, [&](int64_t b0, int64_t b1) {
+    for (int64_t b = b0; b < b1; ++b) {
+      memcpy(out + base[b], recs[b].data(), recs[b].size());
+      for (int64_t T = b * block; T < std::min(n_tiles, (b + 1) * block); ++T) tile_off[T] += base[b];  // raw flag: bit 63 untouched
+    }
+  });
+  tile_off[n_tiles] = total;
+  return (int64_t)total;
+}
 
 int sai_zt_decode_host(const sai_layout* lay, const uint8_t* stream, const uint64_t* tile_off, int64_t n_sites,
                        uint8_t* packed) {

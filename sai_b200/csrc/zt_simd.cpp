@@ -13,6 +13,10 @@
 
 #include "zt_simd.h"
 
+#include <algorithm>
+
+#include "host_pack.h"
+
 #if defined(__x86_64__) || defined(_M_X64)
 #include <immintrin.h>
 #define SAI_X86 1
@@ -158,6 +162,57 @@ size_t zt_encode_tile(const uint64_t* tile, int P, const uint64_t* padc, uint8_t
   if (use_vector(isa)) return encode_avx512(tile, P, padc, rec, tmp);
 #endif
   return encode_portable(tile, P, padc, rec, tmp);
+}
+
+ZtBlockScratch::ZtBlockScratch(int P) {
+  const size_t tile_bytes = (size_t)P * kTileSites * 8;
+  const size_t stage_bytes = (64 + std::max(zt_record_cap(P), tile_bytes) + 63) & ~size_t(63);
+  mem = new uint8_t[64 + tile_bytes + stage_bytes + zt_tmp_cap(P)];
+  tilebuf = mem + ((64 - reinterpret_cast<uintptr_t>(mem) % 64) % 64);
+  stage = tilebuf + tile_bytes;
+  tmp = stage + stage_bytes;
+}
+
+ZtBlockScratch::~ZtBlockScratch() { delete[] mem; }
+
+size_t zt_pack_block_i8(const sai_layout& lay, const int8_t* const* gt, const int64_t* row_stride, int64_t n_sites,
+                        int64_t t0, int64_t t1, const uint64_t* padc, uint8_t* region, uint64_t base_off,
+                        uint64_t* tile_off, ZtBlockScratch& sc, bool nontemporal, bool* bad) {
+  const int P = lay.pairs_per_site;
+  const size_t tile_bytes = (size_t)P * kTileSites * 8;
+  size_t emitted = 0, carry = 0;  // bytes written to the region / waiting at the head of the stage
+  for (int64_t T = t0; T < t1; ++T) {
+    if (pack_tiles_i8_all(lay, gt, row_stride, n_sites, T, T + 1, T, sc.tilebuf, 0, false)) *bad = true;
+    uint8_t* rec = sc.stage + carry;
+    const size_t unpadded = zt_encode_tile(reinterpret_cast<const uint64_t*>(sc.tilebuf), P, padc, rec, sc.tmp, 0);
+    size_t len = (unpadded + 7) & ~size_t(7);
+    uint64_t flag = 0;
+    if (len >= tile_bytes) {  // not smaller than the tile itself: raw
+      memcpy(rec, sc.tilebuf, tile_bytes);
+      len = tile_bytes;
+      flag = 1ull << 63;
+    } else {
+      memset(rec + unpadded, 0, len - unpadded);
+    }
+    tile_off[T] = (base_off + emitted + carry) | flag;
+    if (!nontemporal) {
+      memcpy(region + emitted, rec, len);
+      emitted += len;
+      continue;
+    }
+    const size_t total = carry + len, lines = total / 64;
+    stream_lines(region + emitted, sc.stage, lines);
+    emitted += lines * 64;
+    carry = total - lines * 64;
+    if (carry) memmove(sc.stage, sc.stage + lines * 64, carry);
+  }
+  if (carry) {
+    memset(sc.stage + carry, 0, 64 - carry);
+    stream_lines(region + emitted, sc.stage, 1);
+    emitted += 64;
+  }
+  if (nontemporal) stream_fence();
+  return emitted;
 }
 
 }  // namespace sai

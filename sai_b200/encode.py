@@ -234,6 +234,32 @@ def compress(pg: PackedGenotypes, n_threads: int = 0, out: Optional[np.ndarray] 
                        pg.neg_off, pg.neg_site, pg.neg_ind, pg.neg_val)
 
 
+def compress_matrices(mg: MatrixGenotypes, n_threads: int = 0, out: Optional[np.ndarray] = None) -> ZtGenotypes:
+    """int8 matrices -> zt stream in one pass (``sai_zt_pack_i8``): every tile is packed and
+    encoded while it sits in a packer thread's L1, the dense tiles never reach memory.  Same
+    bytes as ``compress(pack_populations(...))``.  Raises ``ValueError`` when a value does not
+    fit ``mg.layout``'s bit-planes."""
+    lib = _cabi.load()
+    n_pops = mg.layout.n_pops
+    mats = [_as_i8(m) for m in mg.mats]
+    if len(mats) != n_pops or any(m.shape[0] != mg.n_sites for m in mats):
+        raise ValueError("one (n_sites x individuals) matrix per population of the layout")
+    n_tiles = (mg.n_sites + _cabi.TILE_SITES - 1) // _cabi.TILE_SITES
+    tile_off = np.zeros(n_tiles + 1, dtype=np.uint64)
+    bound = int(lib.sai_zt_bound(C.byref(mg.layout), mg.n_sites))
+    buf = np.empty(max(bound, 8), dtype=np.uint8) if out is None else out
+    if buf.dtype != np.uint8 or not buf.flags.c_contiguous:
+        raise ValueError("out must be a contiguous uint8 buffer")
+    ptrs = (C.c_void_p * n_pops)(*[m.ctypes.data for m in mats])
+    strides = (C.c_int64 * n_pops)(*[m.strides[0] if m.shape[0] > 1 else max(m.shape[1], 1) for m in mats])
+    n = lib.sai_zt_pack_i8(C.byref(mg.layout), ptrs, strides, mg.n_sites, buf.ctypes.data, buf.nbytes, tile_off.ctypes.data, n_threads)
+    if n < 0:
+        _cabi.check(int(n))  # E_DOMAIN -> ValueError
+    stream = buf[: int(n)] if out is not None else buf[: int(n)].copy()
+    return ZtGenotypes(mg.layout, mg.n_sites, mg.pos, stream, tile_off, list(mg.pop_names),
+                       mg.neg_off, mg.neg_site, mg.neg_ind, mg.neg_val)
+
+
 def decompress(zt: ZtGenotypes) -> PackedGenotypes:
     """Host decoder (tests / tools): zt stream -> packed tiles."""
     lib = _cabi.load()

@@ -143,6 +143,65 @@ def test_zt_encoder_vector_path_is_identical():
         assert np.array_equal(back, pg.packed)
 
 
+@pytest.mark.parametrize("kind", ["sparse", "incompressible", "mixed_bits", "one_site", "empty", "views"])
+def test_zt_pack_i8_equals_pack_then_encode(kind):
+    """`sai_zt_pack_i8` (the int8 pipeline's block encoder: pack a tile, encode it in cache, append
+    the record) writes the stream and directory of `sai_zt_encode(sai_pack_i8_all(...))` byte for
+    byte -- sparse and incompressible (raw-tile) data, odd plane counts, row-strided views, several
+    blocks of 32 tiles, any thread count -- and reports a value that does not fit the planes."""
+    from sai_b200.encode import MatrixGenotypes, compress, compress_matrices, decompress, pack_populations
+
+    rng = np.random.default_rng(len(kind))
+    ploidy = [2, 2, 2]
+    if kind == "sparse":
+        n, sizes = 2500, (300, 90, 4)
+        f = rng.beta(0.2, 2.0, size=n)
+        mats = [rng.binomial(2, f[:, None], size=(n, k)).astype(np.int8) for k in sizes]
+        mats[1][rng.random(mats[1].shape) < 0.002] = -1
+        mats[0][rng.random(mats[0].shape) < 0.001] = -2
+    elif kind == "incompressible":
+        n, sizes = 1100, (64, 96, 32)
+        mats = [rng.integers(-1, 3, size=(n, k)).astype(np.int8) for k in sizes]
+    elif kind == "mixed_bits":
+        n, ploidy, sizes = 1300, [4, 3, 1, 8], (45, 32, 7, 70)
+        f = rng.beta(0.3, 3.0, size=n)
+        mats = [rng.binomial(p, f[:, None], size=(n, k)).astype(np.int8) for k, p in zip(sizes, ploidy)]
+        mats[3][rng.random(mats[3].shape) < 0.01] = -2
+    elif kind == "one_site":
+        n, sizes = 1, (3, 2, 1)
+        mats = [np.ones((1, k), np.int8) for k in sizes]
+    elif kind == "empty":
+        n, sizes = 0, (5, 3, 1)
+        mats = [np.zeros((0, k), np.int8) for k in sizes]
+    else:  # column blocks of one parsed matrix
+        n = 2100
+        f = rng.beta(0.2, 2.0, size=n)
+        whole = rng.binomial(2, f[:, None], size=(n, 160)).astype(np.int8)
+        whole[rng.random(whole.shape) < 0.01] = -1
+        mats = [whole[:, :100], whole[:, 100:157], whole[:, 157:]]
+    pos = np.arange(1, n + 1)
+    pg = pack_populations(mats, ploidy, pos)
+    want = compress(pg, n_threads=2)
+    mg = MatrixGenotypes(pg.layout, n, pos, mats)
+    for threads in (1, 3, 0):
+        got = compress_matrices(mg, n_threads=threads)
+        assert np.array_equal(got.tile_off, want.tile_off), (kind, threads)
+        assert np.array_equal(got.stream, want.stream), (kind, threads)
+    assert np.array_equal(decompress(got).packed, pg.packed)
+    if kind == "incompressible":
+        assert (got.tile_off[:-1] >> np.uint64(63)).all()
+    if n > 1:
+        from sai_b200 import _cabi
+
+        with pytest.raises(_cabi.SaiError):
+            compress_matrices(mg, out=np.empty(16, dtype=np.uint8))
+        bad = [m.copy() for m in mats]
+        bad[0][n // 2, 0] = 100
+        if pg.layout.pop[0].bits < 7:
+            with pytest.raises(ValueError, match="does not fit"):
+                compress_matrices(MatrixGenotypes(pg.layout, n, pos, bad))
+
+
 @pytest.mark.parametrize("shape", ["sparse", "dense", "mixed_bits", "tiny", "empty"])
 def test_zt_roundtrip_host(shape):
     """encode -> host decode is the identity on the packed tiles (sparse data, dense data that
