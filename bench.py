@@ -619,6 +619,17 @@ def main():
         t0 = time.perf_counter()
         zt = compress(pg, n_threads=host_threads, out=h_zt.numpy())
         t_encode = time.perf_counter() - t0
+        # int8 -> zt records in one pass, host only (sai_zt_pack_i8: the block encoder the pipeline's packers run):
+        # must reproduce pack + encode byte for byte; its time is the zt pipeline's host stage running alone
+        from sai_b200.encode import compress_matrices
+        h_zt2 = torch.empty(h_zt.numel(), dtype=torch.uint8, pin_memory=True)
+        t_pack_zt = 1e9
+        for _ in range(2):
+            t0 = time.perf_counter()
+            zt2 = compress_matrices(mg, n_threads=host_threads, out=h_zt2.numpy())
+            t_pack_zt = min(t_pack_zt, time.perf_counter() - t0)
+        pack_zt_matches = bool(np.array_equal(zt2.stream, zt.stream) and np.array_equal(zt2.tile_off, zt.tile_off))
+        del zt2, h_zt2
         h_off = torch.empty(zt.tile_off.shape[0], dtype=torch.int64, pin_memory=True)
         h_off.numpy()[:] = zt.tile_off.view(np.int64)
         zt.tile_off = h_off.numpy().view(np.uint64)
@@ -653,10 +664,10 @@ def main():
         d2h = int(r2.nsnps.nbytes + r2.u.nbytes + r2.q.nbytes + r2.q_cnt.nbytes + r2.u_start.nbytes + r2.q_start.nbytes
                   + r2.totals.nbytes + 4 * int(r2.totals.sum()))
         eng.close()
-        tp = torch.tensor([t_pack], dtype=torch.float64, device="cuda")
+        tp = torch.tensor([t_pack, t_pack_zt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-        t_pack = float(tp.item())
+        t_pack, t_pack_zt = float(tp[0].item()), float(tp[1].item())
         e2e = {
             "value": world * W / t_i8, "unit": "windows/s",
             "h2d_bytes_per_step": int(i8_wire_bytes + small), "d2h_bytes_per_step": d2h, "steps": Ki, "ms_per_step": 1e3 * t_i8,
@@ -671,8 +682,10 @@ def main():
             "int8_gbps": h_i8.nbytes / t_i8 / 1e9,
             "pack_alone_ms": 1e3 * t_pack, "pack_alone_gbps_int8": h_i8.nbytes / t_pack / 1e9, "pack_reproduces_device_tiles": pack_matches,
             "pack_alone_note": "dense packer alone (int8 -> dense tiles in a pinned buffer, no GPU work)",
+            "pack_zt_alone_ms": 1e3 * t_pack_zt, "pack_zt_reproduces_encode": pack_zt_matches,
+            "pack_zt_alone_note": "int8 -> zt records alone (sai_zt_pack_i8 into a pinned buffer, incl. its final gather copy; no GPU work)",
             "wire_alone_ms": 1e3 * t_dense,
-            "pipeline_vs_slowest_stage": t_i8 / max(t_pack, t_zt),
+            "pipeline_vs_slowest_stage": t_i8 / max(min(t_pack, t_pack_zt), t_zt),
             "dense_wire": {
                 "value": world * W / t_i8_dense, "unit": "windows/s", "ms_per_step": 1e3 * t_i8_dense,
                 "h2d_bytes_per_step": int(packed_bytes + small), "matches_device_path": same_i8_dense,

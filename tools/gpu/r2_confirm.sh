@@ -12,7 +12,7 @@ import json
 d=json.loads(open('gpurun_out/bench_confirm.log').read().strip().splitlines()[-1])
 e=d['e2e']; r=d['roofline']
 print('value', round(d['value']), 'ms', round(d['ms_per_step'],4), 'k1', round(r['k1_ms'],4), 'frac', round(r['frac'],4), 'traffic', r['traffic'])
-print('e2e', round(e['value']), round(e['ms_per_step'],1), 'pack', round(e['pack_alone_ms'],1), 'wire', round(e['wire_alone_ms'],1), 'ratio', round(e['pipeline_vs_slowest_stage'],3), 'zt', round(e['prepacked_zt']['value']), 'dense', round(e['prepacked_dense']['value']))
+print('e2e', round(e['value']), round(e['ms_per_step'],1), 'pack', round(e['pack_alone_ms'],1), 'pack_zt', round(e.get('pack_zt_alone_ms',0),1), e.get('pack_zt_reproduces_encode'), 'wire', round(e['wire_alone_ms'],1), 'ratio', round(e['pipeline_vs_slowest_stage'],3), 'zt', round(e['prepacked_zt']['value']), 'dense', round(e['prepacked_dense']['value']))
 print('cpu', d['cpu_baseline']['value'], d['cpu_baseline']['kind'], d['cpu_baseline']['gpu_vs_cpu_arm'])
 print('strong', d['strong']['ms'], d['strong']['threshold_ms'], d['clocks'], d['gpu_launches'])
 PY
