@@ -39,6 +39,7 @@ def hugepage_array(shape):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sites", type=int, default=bench.WORKLOAD["n_sites"])
+    ap.add_argument("--quick", action="store_true", help="only zt / dense / zt with the default knobs")
     a = ap.parse_args()
     wl = dict(bench.WORKLOAD)
     S, n_ind = a.sites, list(wl["n_ind"])
@@ -71,6 +72,8 @@ def main():
             dict(wire="zt", SAI_I8_BLOCK_TILES="8"), dict(wire="zt", SAI_I8_BLOCK_TILES="128"), dict(wire="zt", SAI_I8_RING="8"),
             dict(wire="zt", threads=cpus // 2), dict(wire="zt", threads=cpus // 4), dict(wire="zt", threads=1 if cpus < 3 else 3),
             dict(wire="zt", huge=True), dict(wire="dense", huge=True), dict(wire="zt")]
+    if a.quick:
+        cfgs = [dict(wire="zt"), dict(wire="dense"), dict(wire="zt"), dict(wire="zt")]
     huge = None
     ref = None
     for cfg in cfgs:
