@@ -143,7 +143,7 @@ def test_zt_encoder_vector_path_is_identical():
         assert np.array_equal(back, pg.packed)
 
 
-@pytest.mark.parametrize("kind", ["sparse", "incompressible", "mixed_bits", "one_site", "empty", "views"])
+@pytest.mark.parametrize("kind", ["sparse", "incompressible", "mixed_bits", "one_site", "empty", "views", "many_blocks"])
 def test_zt_pack_i8_equals_pack_then_encode(kind):
     """`sai_zt_pack_i8` (the int8 pipeline's block encoder: pack a tile, encode it in cache, append
     the record) writes the stream and directory of `sai_zt_encode(sai_pack_i8_all(...))` byte for
@@ -167,6 +167,9 @@ def test_zt_pack_i8_equals_pack_then_encode(kind):
         f = rng.beta(0.3, 3.0, size=n)
         mats = [rng.binomial(p, f[:, None], size=(n, k)).astype(np.int8) for k, p in zip(sizes, ploidy)]
         mats[3][rng.random(mats[3].shape) < 0.01] = -2
+    elif kind == "many_blocks":  # 39 blocks of raw tiles, 655 KB each: a thread's 16 MB arena chunk rolls over
+        n, sizes = 40_000, (1500, 1000, 4)
+        mats = [rng.integers(0, 3, size=(n, k), dtype=np.int8) for k in sizes]
     elif kind == "one_site":
         n, sizes = 1, (3, 2, 1)
         mats = [np.ones((1, k), np.int8) for k in sizes]
@@ -188,9 +191,9 @@ def test_zt_pack_i8_equals_pack_then_encode(kind):
         assert np.array_equal(got.tile_off, want.tile_off), (kind, threads)
         assert np.array_equal(got.stream, want.stream), (kind, threads)
     assert np.array_equal(decompress(got).packed, pg.packed)
-    if kind == "incompressible":
+    if kind in ("incompressible", "many_blocks"):
         assert (got.tile_off[:-1] >> np.uint64(63)).all()
-    if n > 1:
+    if n > 1 and kind != "many_blocks":
         from sai_b200 import _cabi
 
         with pytest.raises(_cabi.SaiError):
