@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -115,12 +116,136 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
       return SAI_E_ARG;
     }
 
-  // ---- pass 1 (parallel over byte segments cut at line starts): complete lines, record
-  //      filter, flip decision ----
+  // Diploid requests over runs of consecutive sample columns (a population's individuals usually sit
+  // next to each other in the file): a regular record then needs the allele sums of all its fields
+  // (one vector sweep, vcf_simd.cpp) and one block copy per run.
+  struct Run {
+    int col0, out0, len;
+  };
+  std::vector<Run> runs;
+  bool all_diploid = true;
+  for (int o = 0; o < n_out; ++o) {
+    if (sample_ploidy[o] != 2) all_diploid = false;
+    if (!runs.empty() && sample_column[o] == runs.back().col0 + runs.back().len && o == runs.back().out0 + runs.back().len)
+      ++runs.back().len;
+    else
+      runs.push_back(Run{sample_column[o], o, 1});
+  }
+  const bool by_runs = all_diploid && (int64_t)runs.size() * 8 <= n_out;
+
+  // One record -> one output row.  `a0`, `a1`, `sum2`: per-thread scratch for regular records.
+  struct Scratch {
+    std::vector<int8_t> a0, a1, sum2;
+  };
+  auto parse_record = [&](const KeptLine& K, const char* lend, int8_t* row, Scratch& sc) {
+    // Regular diploid record (every field `x|y` / `x/y`): all fields are converted 16 at a time,
+    // then the requested columns are picked with their own ploidy -- cut / padded with missing
+    // alleles and flipped exactly like gt_sum does field by field.
+    if (K.gt_index == 0) {
+      const int64_t max_fields = (lend - K.samples + 1) / 4 + 1;
+      if ((int64_t)sc.sum2.size() < max_fields) {
+        sc.a0.resize(max_fields);
+        sc.a1.resize(max_fields);
+        sc.sum2.resize(max_fields);
+      }
+      int64_t nf = 0;
+      if (all_diploid) {
+        if (vcf_regular_diploid_sum(K.samples, lend, K.flip, sc.sum2.data(), (int64_t)sc.sum2.size(), &nf)) {
+          const int8_t* s2 = sc.sum2.data();
+          if (by_runs) {
+            for (const Run& r : runs) {
+              const int64_t have = std::max<int64_t>(0, std::min<int64_t>(r.len, nf - r.col0));
+              if (have > 0) memcpy(row + r.out0, s2 + r.col0, (size_t)have);
+              if (have < r.len) memset(row + r.out0 + have, -2, (size_t)(r.len - have));  // column absent: both alleles missing
+            }
+          } else {
+            for (int o = 0; o < n_out; ++o) {
+              const int col = sample_column[o];
+              row[o] = col < nf ? s2[col] : (int8_t)-2;
+            }
+          }
+          return;
+        }
+      } else if (vcf_regular_diploid(K.samples, lend, sc.a0.data(), sc.a1.data(), (int64_t)sc.a0.size(), &nf)) {
+        const int8_t *p0 = sc.a0.data(), *p1 = sc.a1.data();
+        for (int o = 0; o < n_out; ++o) {
+          const int col = sample_column[o], ploidy = sample_ploidy[o];
+          if (col >= nf) {
+            row[o] = (int8_t)(-ploidy);  // column absent: all alleles missing
+            continue;
+          }
+          int x0 = p0[col], x1 = ploidy >= 2 ? p1[col] : 0;
+          int rest = ploidy > 2 ? ploidy - 2 : 0;  // alleles beyond the field: missing (-1)
+          if (K.flip) {
+            x0 = x0 > 0 ? x0 - 1 : 1 - x0;
+            if (ploidy >= 2) x1 = x1 > 0 ? x1 - 1 : 1 - x1;
+            rest *= -2;
+          }
+          const int sum = x0 + x1 - rest;
+          row[o] = (int8_t)(sum < -128 ? -128 : (sum > 127 ? 127 : sum));
+        }
+        return;
+      }
+    }
+    const char* f = K.samples;  // start of sample column `col`
+    const char* fe = nullptr;   // end of the field at f (its tab or lend) when already known
+    int col = 0;
+    bool have = f < lend;  // a field exists at f
+    for (int oi = 0; oi < n_out; ++oi) {
+      const int o = order[oi];
+      const int want = sample_column[o];
+      while (col < want && have) {
+        if (fe) {
+          f = fe;
+          fe = nullptr;
+        }
+        while (f < lend && *f != '\t') ++f;
+        if (f < lend) {
+          ++f;
+          ++col;
+        } else {
+          have = false;
+        }
+      }
+      if (col != want || !have) {
+        row[o] = (int8_t)(-sample_ploidy[o]);  // column absent: all alleles missing
+        continue;
+      }
+      // fast paths for the overwhelmingly common fields "a|b" / "a/b" (diploid) and "a"
+      // (haploid) with single-character alleles and GT first in FORMAT
+      const int ploidy = sample_ploidy[o];
+      if (K.gt_index == 0 && ploidy <= 2) {
+        const int len = ploidy == 2 ? 3 : 1;
+        if (f + len <= lend) {
+          const char e = f + len < lend ? f[len] : '\t';
+          const int a0 = allele_of(f[0]);
+          const int a1 = ploidy == 2 ? allele_of(f[2]) : 0;
+          const bool sep = ploidy == 1 || f[1] == '|' || f[1] == '/';
+          if (sep && a0 != kBadAllele && a1 != kBadAllele && (e == '\t' || e == ':')) {
+            int x0 = a0, x1 = a1;
+            if (K.flip) {
+              x0 = x0 > 0 ? x0 - 1 : 1 - x0;
+              x1 = x1 > 0 ? x1 - 1 : 1 - x1;
+            }
+            row[o] = (int8_t)(ploidy == 2 ? x0 + x1 : x0);
+            if (e == '\t') fe = f + len;  // the field ends right here
+            continue;
+          }
+        }
+      }
+      fe = gt_sum(f, lend, K.gt_index, ploidy, K.flip, &row[o]);  // f stays: a column may be requested twice
+    }
+  };
+
+  // ---- one pass, parallel over byte segments cut at line starts: complete lines, record filter,
+  //      flip decision, and -- while the line is still in this core's cache -- its output row,
+  //      into a per-segment buffer (how many rows the earlier segments keep is not known yet) ----
   const void* last_nl = len > 0 ? memrchr(text, '\n', (size_t)len) : nullptr;
   const char* const complete_end = last_nl ? static_cast<const char*>(last_nl) + 1 : text;  // incomplete last line: next call
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-  const int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, (complete_end - text) / (1 << 20)));
+  // a few segments per thread: lines are kept unevenly (region filter, other chromosomes)
+  const int64_t seg_bytes = 1 << 20;
+  const int n_seg = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_threads * 4, (complete_end - text) / seg_bytes));
   std::vector<const char*> seg(n_seg + 1);
   seg[0] = text;
   seg[n_seg] = complete_end;
@@ -130,9 +255,14 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
     const void* nl = guess < complete_end ? memchr(guess, '\n', (size_t)(complete_end - guess)) : nullptr;
     seg[i] = nl ? static_cast<const char*>(nl) + 1 : complete_end;
   }
-  std::vector<std::vector<KeptLine>> seg_kept(n_seg);
-  auto scan = [&](int si) {
-    std::vector<KeptLine>& kept = seg_kept[si];
+  struct SegOut {
+    std::vector<KeptLine> kept;
+    std::vector<int8_t> rows;  // kept.size() rows of n_out values
+  };
+  std::vector<SegOut> seg_out(n_seg);
+  auto scan = [&](int si, Scratch& sc) {
+    std::vector<KeptLine>& kept = seg_out[si].kept;
+    std::vector<int8_t>& rows = seg_out[si].rows;
     const char* p = seg[si];
     const char* const send = seg[si + 1];
     while (p < send) {
@@ -177,164 +307,73 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
       {
         int k = 0;
         const char* q = fmt;
-        bool found = false;
         while (q < t8) {
           const void* c = memchr(q, ':', (size_t)(t8 - q));
           const char* ke = c ? static_cast<const char*>(c) : t8;
           if (ke - q == 2 && q[0] == 'G' && q[1] == 'T') {
             gi = k;
-            found = true;
             break;
           }
           q = ke + 1;
           ++k;
         }
-        if (!found) gi = 0;
       }
       if (t8 >= lend) continue;  // no sample columns
-      kept.push_back(KeptLine{t8 + 1, line, gi, (int32_t)pos, flip});
+      const KeptLine K{t8 + 1, line, gi, (int32_t)pos, flip};
+      if (kept.empty()) {  // first kept line of the segment: room for a segment of lines like this one
+        const size_t est = (size_t)((send - line) / std::max<int64_t>(1, p - line) + 2);
+        kept.reserve(est);
+        rows.reserve(est * (size_t)n_out);
+      }
+      kept.push_back(K);
+      rows.resize(rows.size() + (size_t)n_out);
+      parse_record(K, lend, rows.data() + rows.size() - (size_t)n_out, sc);
     }
   };
-  if (n_seg == 1) {
-    scan(0);
-  } else {
+  {
+    std::atomic<int> next_seg{0};
+    auto worker = [&]() {
+      Scratch sc;
+      for (int si = next_seg.fetch_add(1); si < n_seg; si = next_seg.fetch_add(1)) scan(si, sc);
+    };
+    const int nt = std::min(n_threads, n_seg);
     std::vector<std::thread> th;
-    for (int i = 0; i < n_seg; ++i) th.emplace_back(scan, i);
+    for (int i = 1; i < nt; ++i) th.emplace_back(worker);
+    worker();
     for (auto& t : th) t.join();
   }
-  std::vector<KeptLine> kept;
-  {
-    size_t total = 0;
-    for (auto& v : seg_kept) total += v.size();
-    kept.reserve(total);
-    for (auto& v : seg_kept) kept.insert(kept.end(), v.begin(), v.end());
+  // rows of segment si start at row first[si]; a full output buffer stops in front of the first
+  // record that does not fit (the next call starts there)
+  std::vector<int64_t> first(n_seg + 1, 0);
+  for (int si = 0; si < n_seg; ++si) first[si + 1] = first[si] + (int64_t)seg_out[si].kept.size();
+  const int64_t n_rows = std::min<int64_t>(first[n_seg], rows_cap);
+  const char* consumed_to = complete_end;
+  if (first[n_seg] > rows_cap) {
+    int si = 0;
+    while (first[si + 1] <= rows_cap) ++si;
+    consumed_to = seg_out[si].kept[rows_cap - first[si]].line;
   }
-  const char* p = complete_end;
-  if ((int64_t)kept.size() > rows_cap) {  // output full: stop in front of the first record that does not fit
-    p = kept[rows_cap].line;
-    kept.resize(rows_cap);
-  }
-  *bytes_consumed = (int64_t)(p - text);
-  const int64_t n_rows = (int64_t)kept.size();
+  *bytes_consumed = (int64_t)(consumed_to - text);
   if (n_rows == 0) return 0;
-
-  // ---- pass 2 (parallel over records): walk the sample columns ----
-  auto work = [&](int64_t r0, int64_t r1) {
-    std::vector<int8_t> a0, a1, sum2;  // alleles (and diploid sums) of every field of a regular record (vcf_simd.cpp)
-    for (int64_t r = r0; r < r1; ++r) {
-      const KeptLine& K = kept[r];
-      out_pos[r] = K.pos;
-      int8_t* row = out_gt + r * row_stride;
-      const void* nl = memchr(K.samples, '\n', (size_t)(tend - K.samples));
-      const char* lend = nl ? static_cast<const char*>(nl) : tend;
-      if (lend > K.samples && lend[-1] == '\r') --lend;
-      // Regular diploid record (every field `x|y` / `x/y`): all fields are converted 16 at a time,
-      // then the requested columns are picked with their own ploidy -- cut / padded with missing
-      // alleles and flipped exactly like gt_sum does field by field.
-      if (K.gt_index == 0) {
-        const int64_t max_fields = (lend - K.samples + 1) / 4 + 1;
-        if ((int64_t)a0.size() < max_fields) {
-          a0.resize(max_fields);
-          a1.resize(max_fields);
-          sum2.resize(max_fields);
-        }
-        int64_t nf = 0;
-        if (vcf_regular_diploid(K.samples, lend, a0.data(), a1.data(), (int64_t)a0.size(), &nf)) {
-          // diploid requests (the common case): the sums of all fields in one vectorisable sweep,
-          // then one byte move per requested column
-          int8_t* s2 = sum2.data();
-          const int8_t *p0 = a0.data(), *p1 = a1.data();
-          if (K.flip) {  // |a - 1| on every allele (utils.py:555)
-            for (int64_t i = 0; i < nf; ++i) {
-              const int x0 = p0[i], x1 = p1[i];
-              s2[i] = (int8_t)((x0 > 0 ? x0 - 1 : 1 - x0) + (x1 > 0 ? x1 - 1 : 1 - x1));
-            }
-          } else {
-            for (int64_t i = 0; i < nf; ++i) s2[i] = (int8_t)(p0[i] + p1[i]);
-          }
-          for (int o = 0; o < n_out; ++o) {
-            const int col = sample_column[o], ploidy = sample_ploidy[o];
-            if (col >= nf) {
-              row[o] = (int8_t)(-ploidy);  // column absent: all alleles missing
-              continue;
-            }
-            if (ploidy == 2) {
-              row[o] = s2[col];
-              continue;
-            }
-            int x0 = p0[col], x1 = ploidy >= 2 ? p1[col] : 0;
-            int rest = ploidy > 2 ? ploidy - 2 : 0;  // alleles beyond the field: missing (-1)
-            if (K.flip) {
-              x0 = x0 > 0 ? x0 - 1 : 1 - x0;
-              if (ploidy >= 2) x1 = x1 > 0 ? x1 - 1 : 1 - x1;
-              rest *= -2;
-            }
-            const int sum = x0 + x1 - rest;
-            row[o] = (int8_t)(sum < -128 ? -128 : (sum > 127 ? 127 : sum));
-          }
-          continue;
+  {
+    std::atomic<int> next_seg{0};
+    auto gather = [&]() {
+      for (int si = next_seg.fetch_add(1); si < n_seg; si = next_seg.fetch_add(1)) {
+        const SegOut& so = seg_out[si];
+        const int64_t take = std::min<int64_t>((int64_t)so.kept.size(), n_rows - first[si]);
+        if (take <= 0) continue;
+        for (int64_t r = 0; r < take; ++r) out_pos[first[si] + r] = so.kept[r].pos;
+        if (row_stride == n_out) {
+          memcpy(out_gt + first[si] * row_stride, so.rows.data(), (size_t)take * n_out);
+        } else {
+          for (int64_t r = 0; r < take; ++r) memcpy(out_gt + (first[si] + r) * row_stride, so.rows.data() + r * n_out, (size_t)n_out);
         }
       }
-      const char* f = K.samples;  // start of sample column `col`
-      const char* fe = nullptr;   // end of the field at f (its tab or lend) when already known
-      int col = 0;
-      bool have = f < lend;  // a field exists at f
-      for (int oi = 0; oi < n_out; ++oi) {
-        const int o = order[oi];
-        const int want = sample_column[o];
-        while (col < want && have) {
-          if (fe) {
-            f = fe;
-            fe = nullptr;
-          }
-          while (f < lend && *f != '\t') ++f;
-          if (f < lend) {
-            ++f;
-            ++col;
-          } else {
-            have = false;
-          }
-        }
-        if (col != want || !have) {
-          row[o] = (int8_t)(-sample_ploidy[o]);  // column absent: all alleles missing
-          continue;
-        }
-        // fast paths for the overwhelmingly common fields "a|b" / "a/b" (diploid) and "a"
-        // (haploid) with single-character alleles and GT first in FORMAT
-        const int ploidy = sample_ploidy[o];
-        if (K.gt_index == 0 && ploidy <= 2) {
-          const int len = ploidy == 2 ? 3 : 1;
-          if (f + len <= lend) {
-            const char e = f + len < lend ? f[len] : '\t';
-            const int a0 = allele_of(f[0]);
-            const int a1 = ploidy == 2 ? allele_of(f[2]) : 0;
-            const bool sep = ploidy == 1 || f[1] == '|' || f[1] == '/';
-            if (sep && a0 != kBadAllele && a1 != kBadAllele && (e == '\t' || e == ':')) {
-              int x0 = a0, x1 = a1;
-              if (K.flip) {
-                x0 = x0 > 0 ? x0 - 1 : 1 - x0;
-                x1 = x1 > 0 ? x1 - 1 : 1 - x1;
-              }
-              row[o] = (int8_t)(ploidy == 2 ? x0 + x1 : x0);
-              if (e == '\t') fe = f + len;  // the field ends right here
-              continue;
-            }
-          }
-        }
-        fe = gt_sum(f, lend, K.gt_index, ploidy, K.flip, &row[o]);  // f stays: a column may be requested twice
-      }
-    }
-  };
-  n_threads = (int)std::min<int64_t>(n_threads, n_rows);
-  if (n_threads <= 1) {
-    work(0, n_rows);
-  } else {
+    };
+    const int nt = std::min(n_threads, n_seg);
     std::vector<std::thread> th;
-    const int64_t per = (n_rows + n_threads - 1) / n_threads;
-    for (int i = 0; i < n_threads; ++i) {
-      const int64_t a = i * per, b = std::min(n_rows, a + per);
-      if (a < b) th.emplace_back(work, a, b);
-    }
+    for (int i = 1; i < nt; ++i) th.emplace_back(gather);
+    gather();
     for (auto& t : th) t.join();
   }
   return n_rows;

@@ -40,6 +40,48 @@ bool regular_portable(const char* s, int64_t n, int8_t* a0, int8_t* a1) {
   return true;
 }
 
+inline int8_t flipped(int8_t a) { return (int8_t)(a > 0 ? a - 1 : 1 - a); }  // |a - 1| (utils.py:555)
+
+bool regular_sum_portable(const char* s, int64_t n, bool flip, int8_t* sum2) {
+  for (int64_t i = 0; i + 1 < n; ++i) {
+    uint32_t w;
+    memcpy(&w, s + 4 * i, 4);
+    int8_t a0, a1;
+    if (!field_alleles(w, true, a0, a1)) return false;
+    sum2[i] = flip ? (int8_t)(flipped(a0) + flipped(a1)) : (int8_t)(a0 + a1);
+  }
+  return true;
+}
+
+#ifdef SAI_X86
+#pragma GCC push_options
+#pragma GCC target("avx512f,avx512bw")
+bool regular_sum_avx512(const char* s, int64_t n, bool flip, int8_t* sum2) {
+  const __m512i zero = _mm512_set1_epi8('0'), dot = _mm512_set1_epi8('.'), bar = _mm512_set1_epi8('|'),
+                slash = _mm512_set1_epi8('/'), tab = _mm512_set1_epi8('\t'), ten = _mm512_set1_epi8(10),
+                minus1 = _mm512_set1_epi8(-1), one = _mm512_set1_epi8(1);
+  int64_t i = 0;
+  for (; i + 16 < n; i += 16) {
+    const __m512i v = _mm512_loadu_si512(s + 4 * i);
+    const __m512i d = _mm512_sub_epi8(v, zero);
+    const __mmask64 is_digit = _mm512_cmplt_epu8_mask(d, ten);
+    const __mmask64 is_dot = _mm512_cmpeq_epi8_mask(v, dot);
+    const __mmask64 is_sep = _mm512_cmpeq_epi8_mask(v, bar) | _mm512_cmpeq_epi8_mask(v, slash);
+    const __mmask64 is_tab = _mm512_cmpeq_epi8_mask(v, tab);
+    const __mmask64 allele_ok = is_digit | is_dot;
+    if ((allele_ok & 0x5555555555555555ull) != 0x5555555555555555ull || (is_sep & 0x2222222222222222ull) != 0x2222222222222222ull ||
+        (is_tab & 0x8888888888888888ull) != 0x8888888888888888ull)
+      return false;
+    __m512i val = _mm512_mask_mov_epi8(d, is_dot, minus1);  // bytes 0 and 2 of every field: allele, or -1 for "."
+    if (flip) val = _mm512_abs_epi8(_mm512_sub_epi8(val, one));
+    const __m512i sum = _mm512_add_epi8(val, _mm512_srli_epi32(val, 16));  // byte 0 of every field: a0 + a1
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(sum2 + i), _mm512_cvtepi32_epi8(sum));
+  }
+  return regular_sum_portable(s + 4 * i, n - i, flip, sum2 + i);
+}
+#pragma GCC pop_options
+#endif
+
 #ifdef SAI_X86
 #pragma GCC push_options
 #pragma GCC target("avx512f,avx512bw")
@@ -94,6 +136,31 @@ bool vcf_regular_diploid(const char* s, const char* lend, int8_t* a0, int8_t* a1
   uint32_t w = 0;
   memcpy(&w, s + 4 * (n - 1), 3);
   if (!field_alleles(w, false, a0[n - 1], a1[n - 1])) return false;
+  *n_fields = n;
+  return true;
+}
+
+bool vcf_regular_diploid_sum(const char* s, const char* lend, bool flip, int8_t* sum2, int64_t cap, int64_t* n_fields) {
+  const int64_t len = lend - s;
+  if (len < 3 || ((len + 1) & 3) != 0) return false;
+  const int64_t n = (len + 1) >> 2;
+  if (n > cap) return false;
+  bool ok;
+#ifdef SAI_X86
+  static const bool has512 = [] {
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f");
+  }();
+  ok = has512 ? regular_sum_avx512(s, n, flip, sum2) : regular_sum_portable(s, n, flip, sum2);
+#else
+  ok = regular_sum_portable(s, n, flip, sum2);
+#endif
+  if (!ok) return false;
+  uint32_t w = 0;
+  memcpy(&w, s + 4 * (n - 1), 3);  // the last field: three characters, then the line end
+  int8_t a0, a1;
+  if (!field_alleles(w, false, a0, a1)) return false;
+  sum2[n - 1] = flip ? (int8_t)(flipped(a0) + flipped(a1)) : (int8_t)(a0 + a1);
   *n_fields = n;
   return true;
 }

@@ -936,6 +936,105 @@ def test_shard_genome_follows_split_windows_ranges():
     assert shard_genome([[]], 3) == [[], [], []]
 
 
+@pytest.mark.parametrize("layout", ["contiguous", "scattered"])
+def test_all_diploid_requests_match_python_reader(tmp_path, layout):
+    """When every request is diploid the native parser takes the allele SUMS of a regular record in
+    one vector sweep (flipped records: |a - 1| per allele inside the sweep) and moves them either
+    as one block per run of neighbouring sample columns ("contiguous") or column by column
+    ("scattered": permuted and duplicated columns).  Both == the pure-Python reader, with
+    and without the ancestral-allele table, whole file and region, "." and multi-allelic alleles,
+    irregular records in between (field walker)."""
+    from sai_b200.configs import PloidyConfig
+    from sai_b200.vcf import read_data
+
+    rng = np.random.default_rng(len(layout))
+    n_samples, n_sites = 203, 700
+    lines = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n_samples))]
+    pos = np.cumsum(rng.integers(1, 50, size=n_sites))
+    bases = "ACGT"
+    recs = []
+    for p in pos:
+        ref = bases[rng.integers(4)]
+        alt = bases[(bases.index(ref) + 1 + rng.integers(3)) % 4]
+        toks = []
+        for _ in range(n_samples):
+            a = [("." if rng.random() < 0.05 else str(int(rng.integers(0, 10 if rng.random() < 0.03 else 2)))) for _ in range(2)]
+            toks.append(a[0] + ("|" if rng.random() < 0.7 else "/") + a[1])
+        kind = rng.random()
+        if kind < 0.05:
+            toks[int(rng.integers(n_samples))] = "1"  # haploid field: the record leaves the fast path
+        lines.append("\t".join(["7", str(p), ".", ref, alt, ".", "PASS", ".", "GT"] + toks))
+        recs.append((int(p), ref, alt))
+    vcf = tmp_path / "d.vcf"
+    vcf.write_text("\n".join(lines) + "\n")
+    anc = tmp_path / "anc.bed"
+    with open(anc, "w") as f:
+        for p, ref, alt in recs:
+            r = rng.random()
+            if r >= 0.1:
+                f.write(f"7\t{p - 1}\t{p}\t{ref if r < 0.5 else (alt if r < 0.92 else 'N')}\n")
+    if layout == "contiguous":
+        groups = {"ref": list(range(0, 120)), "tgt": list(range(120, 200)), "src": [200, 201, 202]}
+    else:
+        perm = rng.permutation(n_samples)
+        groups = {"ref": [int(x) for x in perm[:90]], "tgt": [int(x) for x in perm[60:140]], "src": [int(perm[0]), 202, 0]}
+    for g, idx in groups.items():
+        (tmp_path / f"{g}.list").write_text("".join(f"{g.upper()}\ts{i}\n" for i in idx))
+    pc = PloidyConfig({"ref": {"REF": 2}, "tgt": {"TGT": 2}, "src": {"SRC": 2}})
+    lists = [str(tmp_path / f"{g}.list") for g in ("ref", "tgt", "src")]
+    for anc_file in (None, str(anc)):
+        for region in ((None, None), (int(pos[40]), int(pos[600]))):
+            a = read_data(str(vcf), "7", pc, *lists, None, anc_file, start=region[0], end=region[1], native=True)
+            b = read_data(str(vcf), "7", pc, *lists, None, anc_file, start=region[0], end=region[1], native=False)
+            for g in ("ref", "tgt", "src"):
+                assert list(a[g][0]) == list(b[g][0])
+                for p in a[g][0]:
+                    assert np.array_equal(a[g][0][p].POS, b[g][0][p].POS), (g, p)
+                    assert np.array_equal(a[g][0][p].GT, b[g][0][p].GT), (g, p, anc_file, region)
+                    assert a[g][0][p].POS.size > 300
+
+
+def test_native_parser_absent_columns_and_runs():
+    """A record with fewer sample fields than the header promises: the missing columns read as all
+    alleles missing (-ploidy), in the block-copy path (runs of neighbouring columns, all diploid), the
+    column-by-column path and the mixed-ploidy path alike; and the three paths agree on every value."""
+    import ctypes as C
+
+    from sai_b200 import _cabi
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(3)
+    n_smp, n_rec = 90, 40
+    tok = np.array(["0|0", "0|1", "1/1", ".|1", "2|0"])
+    lines = ["#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n_smp))]
+    n_fields = []
+    for i in range(n_rec):
+        nf = n_smp if i % 3 else int(rng.integers(1, n_smp))
+        n_fields.append(nf)
+        lines.append(f"1\t{10 * i + 5}\t.\tA\tG\t.\t.\t.\tGT\t" + "\t".join(tok[rng.integers(0, len(tok), size=nf)]))
+    text = ("\n".join(lines) + "\n").encode()
+
+    def parse(cols, ploidy):
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        pl = np.ascontiguousarray(ploidy, dtype=np.int32)
+        out_pos = np.empty(n_rec, dtype=np.int32)
+        out_gt = np.full((n_rec, cols.size + 3), 99, dtype=np.int8)  # row stride > n_out
+        consumed = C.c_int64(0)
+        n = lib.sai_vcf_parse_gt(C.c_char_p(text), len(text), b"1", 1, 0, cols.ctypes.data, pl.ctypes.data, cols.size, None, None, 0,
+                                 out_pos.ctypes.data, out_gt.ctypes.data, out_gt.shape[1], n_rec, C.byref(consumed), 2)
+        assert n == n_rec and consumed.value == len(text) and (out_gt[:, cols.size:] == 99).all()
+        return out_gt[:, : cols.size].copy()
+
+    everything = np.arange(n_smp)
+    blocks = parse(everything, [2] * n_smp)  # one run of 90 columns: block copies
+    for i, nf in enumerate(n_fields):
+        assert (blocks[i, nf:] == -2).all() and (blocks[i, :nf] >= -2).all() and (blocks[i, :nf] != -2).any()
+    perm = rng.permutation(n_smp)
+    assert np.array_equal(parse(perm, [2] * n_smp), blocks[:, perm])  # column by column
+    mixed = parse(np.concatenate([everything, [0]]), [2] * n_smp + [1])  # one haploid request: the a0 / a1 path
+    assert np.array_equal(mixed[:, :n_smp], blocks)
+
+
 @pytest.mark.parametrize("crlf, final_newline", [(False, True), (True, True), (False, False)])
 def test_regular_record_fast_path_matches_python_reader(tmp_path, crlf, final_newline):
     """Records whose sample fields are all `x|y` / `x/y` take the vector fast path of the native
