@@ -713,7 +713,9 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
                 _cabi.check(int(n))
             if n:
                 pos_parts.append(out_pos[:n].copy())
-                gt_parts.append(out_gt[:n] if n * 4 >= cap * 3 else out_gt[:n].copy())
+                # rows beyond n were never touched (np.empty commits no pages): keeping the view costs address
+                # space only, while a copy of a chromosome-sized matrix costs tens of milliseconds
+                gt_parts.append(out_gt[:n] if n * 16 >= cap else out_gt[:n].copy())
             if consumed.value == 0:
                 break
             at += consumed.value
