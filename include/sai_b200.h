@@ -195,6 +195,12 @@ int64_t sai_bgzf_scan(const uint8_t* data, int64_t len, int64_t max_blocks, int6
                       int64_t* block_off, int64_t* out_off, int64_t* consumed);
 int sai_bgzf_inflate(const uint8_t* data, const int64_t* block_off, const int64_t* out_off,
                      int64_t n_blocks, uint8_t* out, int32_t n_threads);
+/* The block decoder and checksum sai_bgzf_inflate uses (tests, tools): raw deflate stream
+ * (RFC 1951) of known inflated size -> 1 on success, 0 on anything unexpected (sai_bgzf_inflate
+ * then repeats the block with zlib); CRC-32 == zlib's crc32(0, data, len) (isa: 0 = PCLMULQDQ
+ * when the CPU has it, 1 = slicing tables). */
+int32_t sai_inflate_raw(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_len);
+uint32_t sai_crc32(const uint8_t* data, int64_t len, int32_t isa);
 
 /* ---- K1: site counts (replaces calc_freq's passes, stat_utils.py:45-49) --- */
 /* For tiles [tile0, tile0+n_tiles): per population p and site s

@@ -891,6 +891,107 @@ def test_all_populations_packer_matches_per_population_packer(n_ind, bits):
         assert lib.sai_pack_i8_all(C.byref(lay), ptrs, strides, n_sites, got.ctypes.data, 2) == _cabi.E_DOMAIN
 
 
+# ---------------------------------------------------------------- BGZF block decoder + CRC-32 (N2)
+def test_crc32_matches_zlib():
+    """`sai_crc32` (PCLMULQDQ folding where the CPU has it, slicing tables otherwise) == zlib.crc32
+    for every length class of the vector path (below 64 bytes, whole 64-byte groups, 16-byte
+    groups, ragged tails)."""
+    import zlib
+
+    from sai_b200 import _cabi
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(0)
+    for n in list(range(1, 200)) + [255, 256, 257, 1000, 4096, 65279, 65280, 100003]:
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        for isa in (0, 1):
+            assert lib.sai_crc32(d, n, isa) == zlib.crc32(d), (n, isa)
+
+
+def _deflate_raw(data, level, strategy=None):
+    import zlib
+
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, zlib.Z_DEFAULT_STRATEGY if strategy is None else strategy)
+    return co.compress(data) + co.flush()
+
+
+def test_inflate_raw_matches_zlib():
+    """The in-house raw-deflate decoder of the BGZF reader reproduces zlib's output on dynamic,
+    fixed (Z_FIXED) and stored (level 0, incompressible data) blocks, multi-block streams
+    (Z_FULL_FLUSH: empty stored blocks in between), VCF-like text, runs with match distances
+    1, 2, 3, 4, 8 and long distances, every small size, and never writes past the output."""
+    import zlib
+
+    from sai_b200 import _cabi
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(1)
+    tok = np.array([b"0|0", b"0|1", b"1|0", b"1|1", b".|."])
+    vcf_like = b"\n".join(b"1\t%d\t.\tA\tT\t.\tPASS\t.\tGT\t" % (100 + 37 * i) + b"\t".join(tok[(rng.random(400) < 0.05) * rng.integers(1, 5, 400)])
+                          for i in range(60))
+
+    def check(data, comp):
+        out = np.full(len(data) + 16, 0xCD, dtype=np.uint8)
+        assert lib.sai_inflate_raw(comp, len(comp), out.ctypes.data, len(data)) == 1, len(data)
+        assert out[: len(data)].tobytes() == data and (out[len(data):] == 0xCD).all()
+        # a wrong size is refused, not overrun
+        if len(data) > 1:
+            assert lib.sai_inflate_raw(comp, len(comp), out.ctypes.data, len(data) - 1) == 0
+        assert lib.sai_inflate_raw(comp, len(comp), out.ctypes.data, len(data) + 1) == 0
+        assert (out[len(data) + 1:] == 0xCD).all()
+
+    samples = [vcf_like, vcf_like[:65280], bytes(70000), b"ab" * 30000, b"abc" * 20000, b"0|0\t" * 16000, b"abcdefgh" * 8000,
+               rng.integers(0, 256, 65280, dtype=np.uint8).tobytes(), rng.integers(0, 4, 50000, dtype=np.uint8).tobytes(),
+               (rng.integers(0, 256, 3000, dtype=np.uint8).tobytes() + bytes(29000)) * 2]
+    samples += [vcf_like[:n] for n in range(0, 40)] + [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (1, 2, 3, 7, 8, 9, 300)]
+    for data in samples:
+        for level in (0, 1, 6, 9):
+            check(data, _deflate_raw(data, level))
+        check(data, _deflate_raw(data, 6, zlib.Z_FIXED))
+        check(data, _deflate_raw(data, 6, zlib.Z_HUFFMAN_ONLY))
+        check(data, _deflate_raw(data, 6, zlib.Z_RLE))
+    # several blocks in one stream, with flush markers (empty stored blocks) between them
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    parts = [vcf_like[:20000], rng.integers(0, 256, 5000, dtype=np.uint8).tobytes(), bytes(10000), vcf_like[20000:]]
+    comp = b"".join(co.compress(p) + co.flush(zlib.Z_FULL_FLUSH if i % 2 else zlib.Z_SYNC_FLUSH) for i, p in enumerate(parts)) + co.flush()
+    check(b"".join(parts), comp)
+
+
+def test_inflate_raw_rejects_corrupt_streams_safely():
+    """Bit flips, truncations and random tails: the decoder either refuses the stream or produces
+    output that differs from the original (which the block's CRC-32 then catches) -- and in no case
+    writes outside the output buffer.  sai_bgzf_inflate reports a corrupt block."""
+    import zlib
+
+    from sai_b200 import _cabi
+    from sai_b200.vcf import write_bgzf
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(2)
+    tok = np.array([b"0|0", b"0|1", b"1|1"])
+    good = b"\n".join(b"\t".join(tok[(rng.random(500) < 0.1) * rng.integers(1, 3, 500)]) for _ in range(30))
+    comp = _deflate_raw(good, 6)
+    refused = 0
+    for it in range(1500):
+        bad = bytearray(comp)
+        kind = it % 3
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            bad = bad[: int(rng.integers(0, len(bad)))]
+        else:
+            at = int(rng.integers(0, len(bad)))
+            bad[at:] = rng.integers(0, 256, int(rng.integers(1, 60)), dtype=np.uint8).tobytes()
+        out = np.full(len(good) + 32, 0xCD, dtype=np.uint8)
+        ok = lib.sai_inflate_raw(bytes(bad), len(bad), out.ctypes.data, len(good))
+        assert (out[len(good):] == 0xCD).all()
+        if ok and out[: len(good)].tobytes() != good:
+            assert lib.sai_crc32(out.ctypes.data, len(good), 0) != zlib.crc32(good)
+        refused += not ok
+    assert refused > 1000
+
+
 # ---------------------------------------------------------------- whole-genome sharding (host logic)
 def test_shard_genome_follows_split_windows_ranges():
     """`shard_genome` cuts the flattened (chromosome, window) list like
