@@ -48,10 +48,19 @@ const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97,
 const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 const uint8_t kCodeLenOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-inline uint32_t reverse_bits(uint32_t code, int len) {
-  uint32_t r = 0;
-  for (int i = 0; i < len; ++i) r |= ((code >> i) & 1u) << (len - 1 - i);
-  return r;
+struct ByteReverse {
+  uint8_t r[256];
+  ByteReverse() {
+    for (int i = 0; i < 256; ++i) {
+      int v = 0;
+      for (int b = 0; b < 8; ++b) v |= ((i >> b) & 1) << (7 - b);
+      r[i] = (uint8_t)v;
+    }
+  }
+};
+inline uint32_t reverse_bits(uint32_t code, int len) {  // len <= 15
+  static const ByteReverse R;
+  return (((uint32_t)R.r[code & 0xffu] << 8) | R.r[(code >> 8) & 0xffu]) >> (16 - len);
 }
 
 struct Tables {
@@ -77,7 +86,17 @@ bool build_table(const uint8_t* lens, int n, int primary_bits, int sub_bits, uin
     next_code[len] = code;
   }
   const size_t primary = (size_t)1 << primary_bits;
-  for (size_t i = 0; i < primary; ++i) table[i] = 0;
+  // A complete code writes every primary slot, so the table (reused from block to block) is not
+  // cleared as a whole -- only the slots that will hold subtable links, because a link is
+  // recognised by reading its slot: left-aligned, the codes of up to primary_bits bits occupy the
+  // prefixes [0, short_slots) and the longer codes share the prefixes above.
+  if (left != 0) {
+    for (size_t i = 0; i < primary; ++i) table[i] = 0;
+  } else {
+    size_t short_slots = 0;
+    for (int len = 1; len <= primary_bits; ++len) short_slots += (size_t)count[len] << (primary_bits - len);
+    for (size_t v = short_slots; v < primary; ++v) table[reverse_bits((uint32_t)v, primary_bits)] = 0;
+  }
   size_t used = primary;
   for (int sym = 0; sym < n; ++sym) {
     const int len = lens[sym];
@@ -167,7 +186,7 @@ bool read_dynamic_tables(BitReader& br, Tables& T) {
   uint8_t lens[kNumLit + kNumDist] = {0};
   int i = 0;
   while (i < hlit + hdist) {
-    br.refill();
+    if (br.bits < 14) br.refill();  // a code of <= 7 bits and <= 7 extra bits
     const uint32_t e = cl_table[br.peek(7)];
     if (e_kind(e) != kLiteral) return false;
     br.drop((int)e_len(e));
@@ -210,65 +229,86 @@ bool build_fixed_tables(Tables& T) {
          build_table(dlens, kNumDist, kDistBits, kDistSub, T.dist, sizeof(T.dist) / 4, dist_entry);
 }
 
-// One Huffman-coded block.  false = invalid data or output overflow.
-bool inflate_block(BitReader& br, const Tables& T, uint8_t* const out_begin, uint8_t*& out, uint8_t* const out_end) {
+// One Huffman-coded block.  false = invalid data or output overflow.  The table entry of the NEXT
+// symbol is loaded before a match is copied, so that the load overlaps the copy.
+bool inflate_block(BitReader& br, const Tables& T, uint8_t* const out_begin, uint8_t*& out_ref, uint8_t* const out_end) {
+  uint8_t* out = out_ref;
+  br.refill();
+  uint32_t e = T.lit[br.peek(kLitBits)];
   for (;;) {
-    br.refill();
-    uint32_t e = T.lit[br.peek(kLitBits)];
+    // here: e = primary entry at the current position, >= 15 valid bits in the buffer
     if (e_kind(e) == kSubtable) e = T.lit[e_value(e) + ((br.buf >> kLitBits) & ((1u << kLitSub) - 1))];
     br.drop((int)e_len(e));
-    if (e_kind(e) == kLiteral) {
+    const uint32_t kind = e_kind(e);
+    if (kind == kLiteral) {
       if (out >= out_end) return false;
       *out++ = (uint8_t)e_value(e);
-      // a second literal from the same refill (56 bits cover two 15-bit codes)
+      if (br.bits < 32) br.refill();
       e = T.lit[br.peek(kLitBits)];
-      if (e_kind(e) != kLiteral) continue;
-      if (out >= out_end) return false;
-      br.drop((int)e_len(e));
-      *out++ = (uint8_t)e_value(e);
       continue;
     }
-    if (e_kind(e) == kEndOfBlock) return !br.past_end();
-    if (e_kind(e) != kLength) return false;
-    // <= 15 + 5 bits used so far; the distance code and its extra bits need <= 15 + 13 more
-    const uint32_t length = e_value(e) + br.take((int)e_extra(e));
-    uint32_t d = T.dist[br.peek(kDistBits)];
-    if (e_kind(d) == kSubtable) d = T.dist[e_value(d) + ((br.buf >> kDistBits) & ((1u << kDistSub) - 1))];
-    if (e_kind(d) != kDistance) return false;
-    br.drop((int)e_len(d));
-    const uint32_t distance = e_value(d) + br.take((int)e_extra(d));
-    if (br.past_end()) return false;
-    if (distance > (size_t)(out - out_begin) || length > (size_t)(out_end - out)) return false;
-    const uint8_t* src = out - distance;
-    uint8_t* dst = out;
-    out += length;
-    if ((size_t)(out_end - dst) >= (size_t)length + 8) {  // room to finish the last word past the match
-      if (distance >= 8) {
-        for (uint32_t k = 0; k < length; k += 8) {
-          uint64_t w;
-          memcpy(&w, src + k, 8);
-          memcpy(dst + k, &w, 8);
+    if (kind == kLength) {
+      if (br.bits < 5 + kMaxCodeLen + 13) br.refill();  // length extra bits, distance code, distance extra bits
+      const uint32_t length = e_value(e) + br.take((int)e_extra(e));
+      uint32_t d = T.dist[br.peek(kDistBits)];
+      if (e_kind(d) == kSubtable) d = T.dist[e_value(d) + ((br.buf >> kDistBits) & ((1u << kDistSub) - 1))];
+      if (e_kind(d) != kDistance) return false;
+      br.drop((int)e_len(d));
+      const uint32_t distance = e_value(d) + br.take((int)e_extra(d));
+      if (br.past_end()) return false;
+      if (distance > (size_t)(out - out_begin) || length > (size_t)(out_end - out)) return false;
+      br.refill();
+      e = T.lit[br.peek(kLitBits)];  // the next symbol's entry, in flight during the copy
+      const uint8_t* src = out - distance;
+      uint8_t* dst = out;
+      out += length;
+      const size_t room = (size_t)(out_end - dst);
+      if (distance >= 16 && room >= (size_t)length + 64) {  // the usual match: the same columns one line up
+        // 64 bytes unconditionally (most matches are shorter: no loop-exit misprediction), 16 at a
+        // time so that an overlap at distance >= 16 still reads what was just written
+        for (int k = 0; k < 64; k += 16) {
+          uint64_t w[2];
+          memcpy(w, src + k, 16);
+          memcpy(dst + k, w, 16);
+        }
+        for (uint32_t k = 64; k < length; k += 16) {
+          uint64_t w[2];
+          memcpy(w, src + k, 16);
+          memcpy(dst + k, w, 16);
         }
         continue;
       }
-      if (distance == 1 || distance == 2 || distance == 4) {  // a period that divides 8: one repeated word
-        uint64_t w = 0;
-        if (distance == 1) {
-          w = 0x0101010101010101ull * src[0];
-        } else if (distance == 2) {
-          uint16_t h;
-          memcpy(&h, src, 2);
-          w = 0x0001000100010001ull * h;
-        } else {
-          uint32_t q;
-          memcpy(&q, src, 4);
-          w = 0x0000000100000001ull * q;
+      if (room >= (size_t)length + 8) {  // room to finish the last word past the match
+        if (distance >= 8) {
+          for (uint32_t k = 0; k < length; k += 8) {
+            uint64_t w;
+            memcpy(&w, src + k, 8);
+            memcpy(dst + k, &w, 8);
+          }
+          continue;
         }
-        for (uint32_t k = 0; k < length; k += 8) memcpy(dst + k, &w, 8);
-        continue;
+        if (distance == 1 || distance == 2 || distance == 4) {  // a period that divides 8: one repeated word
+          uint64_t w = 0;
+          if (distance == 1) {
+            w = 0x0101010101010101ull * src[0];
+          } else if (distance == 2) {
+            uint16_t h;
+            memcpy(&h, src, 2);
+            w = 0x0001000100010001ull * h;
+          } else {
+            uint32_t q;
+            memcpy(&q, src, 4);
+            w = 0x0000000100000001ull * q;
+          }
+          for (uint32_t k = 0; k < length; k += 8) memcpy(dst + k, &w, 8);
+          continue;
+        }
       }
+      for (uint32_t k = 0; k < length; ++k) dst[k] = src[k];
+      continue;
     }
-    for (uint32_t k = 0; k < length; ++k) dst[k] = src[k];
+    out_ref = out;
+    return kind == kEndOfBlock && !br.past_end();
   }
 }
 
