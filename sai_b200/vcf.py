@@ -241,12 +241,14 @@ def load_population_group(
     return data, samples
 
 
-def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20, batch_bytes=256 << 20):
+def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20, batch_bytes=256 << 20, on_size_hint=None):
     """Feeds the text of a VCF (plain, bgzip or gzip) to ``on_lines(addr, length) -> bytes consumed``
     in large buffers of whole-or-partial lines (an incomplete last line is carried to the next
     buffer), after calling ``on_header(line)`` once with the ``#CHROM`` line.  Plain text is
     mapped read-only and handed over in place; bgzip blocks are inflated in parallel by the
-    native library; plain gzip streams through Python's reader."""
+    native library; plain gzip streams through Python's reader.  ``on_size_hint(total_text_bytes)``
+    is called first when the total is known without reading the text (plain: the file size;
+    bgzip: the sum of the blocks' ISIZE fields), so that the consumer can size its output once."""
     import ctypes as C
 
     from . import _cabi
@@ -263,6 +265,8 @@ def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20,
             h = mm.find(b"#CHROM")
             he = mm.find(b"\n", h) if h >= 0 else -1
             if h >= 0 and he >= 0:
+                if on_size_hint is not None:
+                    on_size_hint(len(mm) - he)
                 on_header(mm[h:he])
                 view = np.frombuffer(mm, dtype=np.uint8)
                 try:
@@ -286,6 +290,17 @@ def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20,
                 block_off = np.empty(max_blocks, dtype=np.int64)
                 out_off = np.empty(max_blocks + 1, dtype=np.int64)
                 at, carry = 0, b""
+                if on_size_hint is not None:  # the block headers alone give the size of the text
+                    text_total, p = 0, 0
+                    while p < total:
+                        n = int(lib.sai_bgzf_scan(base + p, total - p, max_blocks, 1 << 62, block_off.ctypes.data,
+                                                  out_off.ctypes.data, C.byref(consumed)))
+                        if n <= 0 or consumed.value == 0:
+                            break
+                        text_total += int(out_off[n])
+                        p += consumed.value
+                    on_size_hint(text_total)
+                buf = np.empty(0, dtype=np.uint8)  # reused from batch to batch: its pages are faulted in once
                 while True:
                     n = int(lib.sai_bgzf_scan(base + at, total - at, max_blocks, batch_bytes, block_off.ctypes.data,
                                               out_off.ctypes.data, C.byref(consumed))) if at < total else 0
@@ -293,7 +308,8 @@ def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20,
                         _cabi.check(n)
                     last = n == 0 or at + consumed.value >= total
                     text_len = int(out_off[n]) if n else 0
-                    buf = np.empty(len(carry) + text_len + 1, dtype=np.uint8)
+                    if buf.size < len(carry) + text_len + 1:
+                        buf = np.empty(max(len(carry) + text_len + 1, min(batch_bytes, total * 64) + (1 << 20)), dtype=np.uint8)
                     buf[: len(carry)] = np.frombuffer(carry, dtype=np.uint8)
                     if n:
                         _cabi.check(lib.sai_bgzf_inflate(base + at, block_off.ctypes.data, out_off.ctypes.data, n,
@@ -302,9 +318,14 @@ def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20,
                     length = len(carry) + text_len
                     start_at = 0
                     if not seen_header:
-                        head = buf[:length].tobytes() if length < (64 << 20) else bytes(buf[: 64 << 20])
-                        h = head.find(b"#CHROM")
-                        he = head.find(b"\n", h) if h >= 0 else -1
+                        probe = 1 << 20  # the header is at the top of the file: do not copy a whole batch to find it
+                        while True:
+                            head = buf[: min(length, probe)].tobytes()
+                            h = head.find(b"#CHROM")
+                            he = head.find(b"\n", h) if h >= 0 else -1
+                            if (h >= 0 and he >= 0) or probe >= length:
+                                break
+                            probe *= 16
                         if h < 0 or he < 0:
                             if last:
                                 break
@@ -685,11 +706,36 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
         anc_pos = np.ascontiguousarray(anc.pos, dtype=np.int32)
         anc_buf = np.ascontiguousarray(table.astype("S8")).tobytes()
         n_anc = len(anc)
-    pos_parts, gt_parts = [], []
     cols = ploidies = None
     n_out = len(requests)
     consumed = C.c_int64(0)
     region = (start, end) if (start is not None and end is not None) else (1, 0)
+    # ONE output matrix for the whole file, sized from the text size when that is known up front
+    # (np.empty commits no pages: an over-estimate costs address space only) and doubled otherwise:
+    # no per-batch parts to concatenate at the end (a chromosome-sized copy)
+    out = {"pos": np.empty(0, dtype=np.int32), "gt": np.empty((0, n_out), dtype=np.int8), "rows": 0}
+    row_bytes = max(64, 2 * n_out)  # a record is never shorter: >= 2 characters per requested column
+
+    def reserve(cap: int) -> None:
+        if cap <= out["pos"].shape[0]:
+            return
+        try:
+            pos_new, gt_new = np.empty(cap, dtype=np.int32), np.empty((cap, n_out), dtype=np.int8)
+        except MemoryError:
+            if out["rows"] == 0:
+                raise
+            cap = out["pos"].shape[0] + max(1024, out["pos"].shape[0] // 2)
+            pos_new, gt_new = np.empty(cap, dtype=np.int32), np.empty((cap, n_out), dtype=np.int8)
+        n = out["rows"]
+        pos_new[:n] = out["pos"][:n]
+        gt_new[:n] = out["gt"][:n]
+        out["pos"], out["gt"] = pos_new, gt_new
+
+    def on_size_hint(text_bytes: int) -> None:
+        try:
+            reserve(min(1 << 31, text_bytes // row_bytes + 1024))
+        except MemoryError:
+            pass  # grow on demand instead
     def header_columns(line: bytes):
         names = line.decode().rstrip("\r").split("\t")[9:]
         index = {n: i for i, n in enumerate(names)}
@@ -700,22 +746,20 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
         """Parses complete lines of ``length`` bytes at ``addr``; returns the bytes consumed."""
         at = 0
         while at < length:
-            cap = max(1024, min(1 << 20, (length - at) // max(64, 2 * n_out) + 16))
-            out_pos = np.empty(cap, dtype=np.int32)
-            out_gt = np.empty((cap, n_out), dtype=np.int8)
+            rows = out["rows"]
+            want = (length - at) // row_bytes + 16  # upper bound of the records in the rest of this buffer
+            if rows + want > out["pos"].shape[0]:
+                reserve(max(rows + want, 2 * out["pos"].shape[0]))
+            cap = out["pos"].shape[0] - rows
             n = lib.sai_vcf_parse_gt(
                 addr + at, length - at, chr_name.encode(), region[0], region[1],
                 cols.ctypes.data, ploidies.ctypes.data, n_out,
                 anc_pos.ctypes.data if n_anc else None, anc_buf if n_anc else None, n_anc,
-                out_pos.ctypes.data, out_gt.ctypes.data, n_out, cap, C.byref(consumed), n_threads,
+                out["pos"].ctypes.data + 4 * rows, out["gt"].ctypes.data + rows * n_out, n_out, cap, C.byref(consumed), n_threads,
             )
             if n < 0:
                 _cabi.check(int(n))
-            if n:
-                pos_parts.append(out_pos[:n].copy())
-                # rows beyond n were never touched (np.empty commits no pages): keeping the view costs address
-                # space only, while a copy of a chromosome-sized matrix costs tens of milliseconds
-                gt_parts.append(out_gt[:n] if n * 16 >= cap else out_gt[:n].copy())
+            out["rows"] = rows + int(n)
             if consumed.value == 0:
                 break
             at += consumed.value
@@ -729,14 +773,16 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
     if start is not None and end is not None:
         handled = _scan_sorted_region(vcf_file, chr_name, int(start), int(end), on_header, parse_buffer, n_threads, batch_bytes)
     if not handled:
-        _scan_text(vcf_file, on_header, parse_buffer, n_threads, chunk_bytes, batch_bytes)
+        _scan_text(vcf_file, on_header, parse_buffer, n_threads, chunk_bytes, batch_bytes, on_size_hint)
     if cols is None:
         return None
-    if not pos_parts:
+    n, cap = out["rows"], out["pos"].shape[0]
+    if n == 0:
         return np.empty(0, dtype=np.int32), np.empty((0, n_out), dtype=np.int8)
-    if len(pos_parts) == 1:  # the usual case (one mapped text file / one batch): no second copy of the matrix
-        return pos_parts[0], gt_parts[0]
-    return np.concatenate(pos_parts), np.concatenate(gt_parts)
+    # rows beyond n were never touched: keeping the views costs address space only, unless the estimate was far off
+    if n * 16 >= cap:
+        return out["pos"][:n], out["gt"][:n]
+    return out["pos"][:n].copy(), out["gt"][:n].copy()
 
 
 def _is_bgzf(path: str) -> bool:
