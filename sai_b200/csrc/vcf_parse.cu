@@ -21,17 +21,11 @@
 #include <vector>
 
 #include "common.cuh"
+#include "vcf_parse.h"
 #include "vcf_simd.h"
 
 namespace sai {
 
-struct KeptLine {
-  const char* samples;  // first character after the FORMAT column
-  const char* line;     // start of the record
-  int32_t gt_index;     // position of GT among the ':'-separated FORMAT keys
-  int32_t pos;
-  bool flip;
-};
 
 static inline const char* next_tab(const char* p, const char* end) {
   const void* t = memchr(p, '\t', (size_t)(end - p));
@@ -88,6 +82,255 @@ static inline int allele_of(char c) {
   return c == '.' ? -1 : kBadAllele;
 }
 
+// ---------------------------------------------------------------------------------------------
+// GtParser (vcf_parse.h): everything one parse call needs to know, the per-record work and the
+// final gather -- shared by the text entry point below and the fused bgzip one (bgzf.cu).
+
+bool GtParser::init(const char* chrom_, int64_t start_, int64_t end_, const int32_t* sample_column_,
+                    const int32_t* sample_ploidy_, int32_t n_out_, const int32_t* anc_pos_, const char* anc_allele_,
+                    int64_t n_anc_) {
+  chrom = chrom_;
+  chrom_len = strlen(chrom_);
+  start = start_;
+  end = end_;
+  region = start_ <= end_;
+  sample_column = sample_column_;
+  sample_ploidy = sample_ploidy_;
+  n_out = n_out_;
+  anc_pos = anc_pos_;
+  anc_allele = anc_allele_;
+  n_anc = n_anc_;
+  // columns sorted so that every line is walked once, left to right
+  order.resize(n_out);
+  for (int i = 0; i < n_out; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return sample_column[a] < sample_column[b]; });
+  for (int i = 0; i < n_out; ++i)
+    if (sample_column[i] < 0 || sample_ploidy[i] < 1 || sample_ploidy[i] > 16) return false;
+  // Diploid requests over runs of consecutive sample columns (a population's individuals usually sit
+  // next to each other in the file): a regular record then needs the allele sums of all its fields
+  // (one vector sweep, vcf_simd.cpp) and one block copy per run.
+  runs.clear();
+  all_diploid = true;
+  for (int o = 0; o < n_out; ++o) {
+    if (sample_ploidy[o] != 2) all_diploid = false;
+    if (!runs.empty() && sample_column[o] == runs.back().col0 + runs.back().len && o == runs.back().out0 + runs.back().len)
+      ++runs.back().len;
+    else
+      runs.push_back(Run{sample_column[o], o, 1});
+  }
+  by_runs = all_diploid && (int64_t)runs.size() * 8 <= n_out;
+  return true;
+}
+
+// One record -> one output row.
+void GtParser::parse_record(const KeptLine& K, const char* lend, int8_t* row, Scratch& sc) const {
+  // Regular diploid record (every field `x|y` / `x/y`): all fields are converted 16 at a time,
+  // then the requested columns are picked with their own ploidy -- cut / padded with missing
+  // alleles and flipped exactly like gt_sum does field by field.
+  if (K.gt_index == 0) {
+    const int64_t max_fields = (lend - K.samples + 1) / 4 + 1;
+    if ((int64_t)sc.sum2.size() < max_fields) {
+      sc.a0.resize(max_fields);
+      sc.a1.resize(max_fields);
+      sc.sum2.resize(max_fields);
+    }
+    int64_t nf = 0;
+    if (all_diploid) {
+      if (vcf_regular_diploid_sum(K.samples, lend, K.flip, sc.sum2.data(), (int64_t)sc.sum2.size(), &nf)) {
+        const int8_t* s2 = sc.sum2.data();
+        if (by_runs) {
+          for (const Run& r : runs) {
+            const int64_t have = std::max<int64_t>(0, std::min<int64_t>(r.len, nf - r.col0));
+            if (have > 0) memcpy(row + r.out0, s2 + r.col0, (size_t)have);
+            if (have < r.len) memset(row + r.out0 + have, -2, (size_t)(r.len - have));  // column absent: both alleles missing
+          }
+        } else {
+          for (int o = 0; o < n_out; ++o) {
+            const int col = sample_column[o];
+            row[o] = col < nf ? s2[col] : (int8_t)-2;
+          }
+        }
+        return;
+      }
+    } else if (vcf_regular_diploid(K.samples, lend, sc.a0.data(), sc.a1.data(), (int64_t)sc.a0.size(), &nf)) {
+      const int8_t *p0 = sc.a0.data(), *p1 = sc.a1.data();
+      for (int o = 0; o < n_out; ++o) {
+        const int col = sample_column[o], ploidy = sample_ploidy[o];
+        if (col >= nf) {
+          row[o] = (int8_t)(-ploidy);  // column absent: all alleles missing
+          continue;
+        }
+        int x0 = p0[col], x1 = ploidy >= 2 ? p1[col] : 0;
+        int rest = ploidy > 2 ? ploidy - 2 : 0;  // alleles beyond the field: missing (-1)
+        if (K.flip) {
+          x0 = x0 > 0 ? x0 - 1 : 1 - x0;
+          if (ploidy >= 2) x1 = x1 > 0 ? x1 - 1 : 1 - x1;
+          rest *= -2;
+        }
+        const int sum = x0 + x1 - rest;
+        row[o] = (int8_t)(sum < -128 ? -128 : (sum > 127 ? 127 : sum));
+      }
+      return;
+    }
+  }
+  const char* f = K.samples;  // start of sample column `col`
+  const char* fe = nullptr;   // end of the field at f (its tab or lend) when already known
+  int col = 0;
+  bool have = f < lend;  // a field exists at f
+  for (int oi = 0; oi < n_out; ++oi) {
+    const int o = order[oi];
+    const int want = sample_column[o];
+    while (col < want && have) {
+      if (fe) {
+        f = fe;
+        fe = nullptr;
+      }
+      while (f < lend && *f != '\t') ++f;
+      if (f < lend) {
+        ++f;
+        ++col;
+      } else {
+        have = false;
+      }
+    }
+    if (col != want || !have) {
+      row[o] = (int8_t)(-sample_ploidy[o]);  // column absent: all alleles missing
+      continue;
+    }
+    // fast paths for the overwhelmingly common fields "a|b" / "a/b" (diploid) and "a"
+    // (haploid) with single-character alleles and GT first in FORMAT
+    const int ploidy = sample_ploidy[o];
+    if (K.gt_index == 0 && ploidy <= 2) {
+      const int len = ploidy == 2 ? 3 : 1;
+      if (f + len <= lend) {
+        const char e = f + len < lend ? f[len] : '\t';
+        const int a0 = allele_of(f[0]);
+        const int a1 = ploidy == 2 ? allele_of(f[2]) : 0;
+        const bool sep = ploidy == 1 || f[1] == '|' || f[1] == '/';
+        if (sep && a0 != kBadAllele && a1 != kBadAllele && (e == '\t' || e == ':')) {
+          int x0 = a0, x1 = a1;
+          if (K.flip) {
+            x0 = x0 > 0 ? x0 - 1 : 1 - x0;
+            x1 = x1 > 0 ? x1 - 1 : 1 - x1;
+          }
+          row[o] = (int8_t)(ploidy == 2 ? x0 + x1 : x0);
+          if (e == '\t') fe = f + len;  // the field ends right here
+          continue;
+        }
+      }
+    }
+    fe = gt_sum(f, lend, K.gt_index, ploidy, K.flip, &row[o]);  // f stays: a column may be requested twice
+  }
+}
+
+// Complete lines of [p, send): record filter, flip decision and -- while the line is still in this
+// core's cache -- its output row, appended to `so`.
+void GtParser::scan(const char* p, const char* send, SegOut& so, Scratch& sc) const {
+  std::vector<KeptLine>& kept = so.kept;
+  std::vector<int8_t>& rows = so.rows;
+  while (p < send) {
+    const void* nl = memchr(p, '\n', (size_t)(send - p));
+    if (!nl) break;
+    const char* lend = static_cast<const char*>(nl);
+    const char* line = p;
+    p = lend + 1;
+    if (lend > line && lend[-1] == '\r') --lend;
+    if (line == lend || *line == '#') continue;
+    const char* t0 = next_tab(line, lend);  // CHROM
+    if ((size_t)(t0 - line) != chrom_len || memcmp(line, chrom, chrom_len) != 0) continue;
+    const char* f = t0 + 1;
+    const char* t1 = next_tab(f, lend);  // POS
+    int64_t pos = 0;
+    for (const char* q = f; q < t1; ++q) pos = pos * 10 + (*q - '0');
+    if (region && (pos < start || pos > end)) continue;
+    const char* t2 = next_tab(t1 + 1, lend);  // ID
+    const char* ref = t2 + 1;
+    const char* t3 = next_tab(ref, lend);  // REF
+    const char* alt = t3 + 1;
+    const char* t4 = next_tab(alt, lend);  // ALT
+    const void* comma = memchr(alt, ',', (size_t)(t4 - alt));
+    const char* alt_end = comma ? static_cast<const char*>(comma) : t4;  // alt_number=1: first ALT
+    bool flip = false;
+    if (n_anc > 0) {
+      const int32_t* it = std::lower_bound(anc_pos, anc_pos + n_anc, (int32_t)pos);
+      if (it == anc_pos + n_anc || *it != (int32_t)pos) continue;  // no ancestral allele: dropped
+      const char* a = anc_allele + 8 * (it - anc_pos);
+      const size_t alen = strnlen(a, 8);
+      const bool is_ref = (size_t)(t3 - ref) == alen && memcmp(a, ref, alen) == 0;
+      const bool is_alt = (size_t)(alt_end - alt) == alen && memcmp(a, alt, alen) == 0;
+      if (!is_ref && !is_alt) continue;
+      flip = is_alt;  // utils.py:523-524
+    }
+    const char* t5 = next_tab(t4 + 1, lend);   // QUAL
+    const char* t6 = next_tab(t5 + 1, lend);   // FILTER
+    const char* t7 = next_tab(t6 + 1, lend);   // INFO
+    const char* fmt = t7 + 1;
+    const char* t8 = next_tab(fmt, lend);      // FORMAT
+    int gi = 0;
+    {
+      int k = 0;
+      const char* q = fmt;
+      while (q < t8) {
+        const void* c = memchr(q, ':', (size_t)(t8 - q));
+        const char* ke = c ? static_cast<const char*>(c) : t8;
+        if (ke - q == 2 && q[0] == 'G' && q[1] == 'T') {
+          gi = k;
+          break;
+        }
+        q = ke + 1;
+        ++k;
+      }
+    }
+    if (t8 >= lend) continue;  // no sample columns
+    const KeptLine K{t8 + 1, line, gi, (int32_t)pos, flip};
+    if (kept.empty()) {  // first kept line of the segment: room for a segment of lines like this one
+      const size_t est = (size_t)((send - line) / std::max<int64_t>(1, p - line) + 2);
+      kept.reserve(est);
+      rows.reserve(est * (size_t)n_out);
+    }
+    kept.push_back(K);
+    rows.resize(rows.size() + (size_t)n_out);
+    parse_record(K, lend, rows.data() + rows.size() - (size_t)n_out, sc);
+  }
+}
+
+// Rows of the segments, in order, into the caller's arrays (at most rows_cap; *first_dropped = the
+// record in front of which a full output stopped, else NULL).  Returns the number of rows.
+int64_t GtParser::gather(const std::vector<SegOut>& seg_out, int32_t* out_pos, int8_t* out_gt, int64_t row_stride,
+                         int64_t rows_cap, int n_threads, const KeptLine** first_dropped) const {
+  const int n_seg = (int)seg_out.size();
+  std::vector<int64_t> first(n_seg + 1, 0);
+  for (int si = 0; si < n_seg; ++si) first[si + 1] = first[si] + (int64_t)seg_out[si].kept.size();
+  const int64_t n_rows = std::min<int64_t>(first[n_seg], rows_cap);
+  *first_dropped = nullptr;
+  if (first[n_seg] > rows_cap) {
+    int si = 0;
+    while (first[si + 1] <= rows_cap) ++si;
+    *first_dropped = &seg_out[si].kept[rows_cap - first[si]];
+  }
+  if (n_rows == 0) return 0;
+  std::atomic<int> next_seg{0};
+  auto work = [&]() {
+    for (int si = next_seg.fetch_add(1); si < n_seg; si = next_seg.fetch_add(1)) {
+      const SegOut& so = seg_out[si];
+      const int64_t take = std::min<int64_t>((int64_t)so.kept.size(), n_rows - first[si]);
+      if (take <= 0) continue;
+      for (int64_t r = 0; r < take; ++r) out_pos[first[si] + r] = so.kept[r].pos;
+      if (row_stride == n_out) {
+        memcpy(out_gt + first[si] * row_stride, so.rows.data(), (size_t)take * n_out);
+      } else {
+        for (int64_t r = 0; r < take; ++r) memcpy(out_gt + (first[si] + r) * row_stride, so.rows.data() + r * n_out, (size_t)n_out);
+      }
+    }
+  };
+  const int nt = std::max(1, std::min(n_threads, n_seg));
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; ++i) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  return n_rows;
+}
+
 }  // namespace sai
 
 using namespace sai;
@@ -103,143 +346,13 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
     set_error("sai_vcf_parse_gt: bad argument");
     return SAI_E_ARG;
   }
-  const size_t chrom_len = strlen(chrom);
-  const bool region = start <= end;
-  const char* const tend = text + len;
-  // columns sorted so that every line is walked once, left to right
-  std::vector<int> order(n_out);
-  for (int i = 0; i < n_out; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return sample_column[a] < sample_column[b]; });
-  for (int i = 0; i < n_out; ++i)
-    if (sample_column[i] < 0 || sample_ploidy[i] < 1 || sample_ploidy[i] > 16) {
-      set_error("sai_vcf_parse_gt: bad sample column / ploidy");
-      return SAI_E_ARG;
-    }
-
-  // Diploid requests over runs of consecutive sample columns (a population's individuals usually sit
-  // next to each other in the file): a regular record then needs the allele sums of all its fields
-  // (one vector sweep, vcf_simd.cpp) and one block copy per run.
-  struct Run {
-    int col0, out0, len;
-  };
-  std::vector<Run> runs;
-  bool all_diploid = true;
-  for (int o = 0; o < n_out; ++o) {
-    if (sample_ploidy[o] != 2) all_diploid = false;
-    if (!runs.empty() && sample_column[o] == runs.back().col0 + runs.back().len && o == runs.back().out0 + runs.back().len)
-      ++runs.back().len;
-    else
-      runs.push_back(Run{sample_column[o], o, 1});
+  GtParser P;
+  if (!P.init(chrom, start, end, sample_column, sample_ploidy, n_out, anc_pos, anc_allele, n_anc)) {
+    set_error("sai_vcf_parse_gt: bad sample column / ploidy");
+    return SAI_E_ARG;
   }
-  const bool by_runs = all_diploid && (int64_t)runs.size() * 8 <= n_out;
-
-  // One record -> one output row.  `a0`, `a1`, `sum2`: per-thread scratch for regular records.
-  struct Scratch {
-    std::vector<int8_t> a0, a1, sum2;
-  };
-  auto parse_record = [&](const KeptLine& K, const char* lend, int8_t* row, Scratch& sc) {
-    // Regular diploid record (every field `x|y` / `x/y`): all fields are converted 16 at a time,
-    // then the requested columns are picked with their own ploidy -- cut / padded with missing
-    // alleles and flipped exactly like gt_sum does field by field.
-    if (K.gt_index == 0) {
-      const int64_t max_fields = (lend - K.samples + 1) / 4 + 1;
-      if ((int64_t)sc.sum2.size() < max_fields) {
-        sc.a0.resize(max_fields);
-        sc.a1.resize(max_fields);
-        sc.sum2.resize(max_fields);
-      }
-      int64_t nf = 0;
-      if (all_diploid) {
-        if (vcf_regular_diploid_sum(K.samples, lend, K.flip, sc.sum2.data(), (int64_t)sc.sum2.size(), &nf)) {
-          const int8_t* s2 = sc.sum2.data();
-          if (by_runs) {
-            for (const Run& r : runs) {
-              const int64_t have = std::max<int64_t>(0, std::min<int64_t>(r.len, nf - r.col0));
-              if (have > 0) memcpy(row + r.out0, s2 + r.col0, (size_t)have);
-              if (have < r.len) memset(row + r.out0 + have, -2, (size_t)(r.len - have));  // column absent: both alleles missing
-            }
-          } else {
-            for (int o = 0; o < n_out; ++o) {
-              const int col = sample_column[o];
-              row[o] = col < nf ? s2[col] : (int8_t)-2;
-            }
-          }
-          return;
-        }
-      } else if (vcf_regular_diploid(K.samples, lend, sc.a0.data(), sc.a1.data(), (int64_t)sc.a0.size(), &nf)) {
-        const int8_t *p0 = sc.a0.data(), *p1 = sc.a1.data();
-        for (int o = 0; o < n_out; ++o) {
-          const int col = sample_column[o], ploidy = sample_ploidy[o];
-          if (col >= nf) {
-            row[o] = (int8_t)(-ploidy);  // column absent: all alleles missing
-            continue;
-          }
-          int x0 = p0[col], x1 = ploidy >= 2 ? p1[col] : 0;
-          int rest = ploidy > 2 ? ploidy - 2 : 0;  // alleles beyond the field: missing (-1)
-          if (K.flip) {
-            x0 = x0 > 0 ? x0 - 1 : 1 - x0;
-            if (ploidy >= 2) x1 = x1 > 0 ? x1 - 1 : 1 - x1;
-            rest *= -2;
-          }
-          const int sum = x0 + x1 - rest;
-          row[o] = (int8_t)(sum < -128 ? -128 : (sum > 127 ? 127 : sum));
-        }
-        return;
-      }
-    }
-    const char* f = K.samples;  // start of sample column `col`
-    const char* fe = nullptr;   // end of the field at f (its tab or lend) when already known
-    int col = 0;
-    bool have = f < lend;  // a field exists at f
-    for (int oi = 0; oi < n_out; ++oi) {
-      const int o = order[oi];
-      const int want = sample_column[o];
-      while (col < want && have) {
-        if (fe) {
-          f = fe;
-          fe = nullptr;
-        }
-        while (f < lend && *f != '\t') ++f;
-        if (f < lend) {
-          ++f;
-          ++col;
-        } else {
-          have = false;
-        }
-      }
-      if (col != want || !have) {
-        row[o] = (int8_t)(-sample_ploidy[o]);  // column absent: all alleles missing
-        continue;
-      }
-      // fast paths for the overwhelmingly common fields "a|b" / "a/b" (diploid) and "a"
-      // (haploid) with single-character alleles and GT first in FORMAT
-      const int ploidy = sample_ploidy[o];
-      if (K.gt_index == 0 && ploidy <= 2) {
-        const int len = ploidy == 2 ? 3 : 1;
-        if (f + len <= lend) {
-          const char e = f + len < lend ? f[len] : '\t';
-          const int a0 = allele_of(f[0]);
-          const int a1 = ploidy == 2 ? allele_of(f[2]) : 0;
-          const bool sep = ploidy == 1 || f[1] == '|' || f[1] == '/';
-          if (sep && a0 != kBadAllele && a1 != kBadAllele && (e == '\t' || e == ':')) {
-            int x0 = a0, x1 = a1;
-            if (K.flip) {
-              x0 = x0 > 0 ? x0 - 1 : 1 - x0;
-              x1 = x1 > 0 ? x1 - 1 : 1 - x1;
-            }
-            row[o] = (int8_t)(ploidy == 2 ? x0 + x1 : x0);
-            if (e == '\t') fe = f + len;  // the field ends right here
-            continue;
-          }
-        }
-      }
-      fe = gt_sum(f, lend, K.gt_index, ploidy, K.flip, &row[o]);  // f stays: a column may be requested twice
-    }
-  };
-
-  // ---- one pass, parallel over byte segments cut at line starts: complete lines, record filter,
-  //      flip decision, and -- while the line is still in this core's cache -- its output row,
-  //      into a per-segment buffer (how many rows the earlier segments keep is not known yet) ----
+  // ---- one pass, parallel over byte segments cut at line starts; the rows go to per-segment
+  //      buffers first (how many rows the earlier segments keep is not known yet) ----
   const void* last_nl = len > 0 ? memrchr(text, '\n', (size_t)len) : nullptr;
   const char* const complete_end = last_nl ? static_cast<const char*>(last_nl) + 1 : text;  // incomplete last line: next call
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -255,86 +368,12 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
     const void* nl = guess < complete_end ? memchr(guess, '\n', (size_t)(complete_end - guess)) : nullptr;
     seg[i] = nl ? static_cast<const char*>(nl) + 1 : complete_end;
   }
-  struct SegOut {
-    std::vector<KeptLine> kept;
-    std::vector<int8_t> rows;  // kept.size() rows of n_out values
-  };
-  std::vector<SegOut> seg_out(n_seg);
-  auto scan = [&](int si, Scratch& sc) {
-    std::vector<KeptLine>& kept = seg_out[si].kept;
-    std::vector<int8_t>& rows = seg_out[si].rows;
-    const char* p = seg[si];
-    const char* const send = seg[si + 1];
-    while (p < send) {
-      const void* nl = memchr(p, '\n', (size_t)(send - p));
-      if (!nl) break;
-      const char* lend = static_cast<const char*>(nl);
-      const char* line = p;
-      p = lend + 1;
-      if (lend > line && lend[-1] == '\r') --lend;
-      if (line == lend || *line == '#') continue;
-      const char* t0 = next_tab(line, lend);  // CHROM
-      if ((size_t)(t0 - line) != chrom_len || memcmp(line, chrom, chrom_len) != 0) continue;
-      const char* f = t0 + 1;
-      const char* t1 = next_tab(f, lend);  // POS
-      int64_t pos = 0;
-      for (const char* q = f; q < t1; ++q) pos = pos * 10 + (*q - '0');
-      if (region && (pos < start || pos > end)) continue;
-      const char* t2 = next_tab(t1 + 1, lend);  // ID
-      const char* ref = t2 + 1;
-      const char* t3 = next_tab(ref, lend);  // REF
-      const char* alt = t3 + 1;
-      const char* t4 = next_tab(alt, lend);  // ALT
-      const void* comma = memchr(alt, ',', (size_t)(t4 - alt));
-      const char* alt_end = comma ? static_cast<const char*>(comma) : t4;  // alt_number=1: first ALT
-      bool flip = false;
-      if (n_anc > 0) {
-        const int32_t* it = std::lower_bound(anc_pos, anc_pos + n_anc, (int32_t)pos);
-        if (it == anc_pos + n_anc || *it != (int32_t)pos) continue;  // no ancestral allele: dropped
-        const char* a = anc_allele + 8 * (it - anc_pos);
-        const size_t alen = strnlen(a, 8);
-        const bool is_ref = (size_t)(t3 - ref) == alen && memcmp(a, ref, alen) == 0;
-        const bool is_alt = (size_t)(alt_end - alt) == alen && memcmp(a, alt, alen) == 0;
-        if (!is_ref && !is_alt) continue;
-        flip = is_alt;  // utils.py:523-524
-      }
-      const char* t5 = next_tab(t4 + 1, lend);   // QUAL
-      const char* t6 = next_tab(t5 + 1, lend);   // FILTER
-      const char* t7 = next_tab(t6 + 1, lend);   // INFO
-      const char* fmt = t7 + 1;
-      const char* t8 = next_tab(fmt, lend);      // FORMAT
-      int gi = 0;
-      {
-        int k = 0;
-        const char* q = fmt;
-        while (q < t8) {
-          const void* c = memchr(q, ':', (size_t)(t8 - q));
-          const char* ke = c ? static_cast<const char*>(c) : t8;
-          if (ke - q == 2 && q[0] == 'G' && q[1] == 'T') {
-            gi = k;
-            break;
-          }
-          q = ke + 1;
-          ++k;
-        }
-      }
-      if (t8 >= lend) continue;  // no sample columns
-      const KeptLine K{t8 + 1, line, gi, (int32_t)pos, flip};
-      if (kept.empty()) {  // first kept line of the segment: room for a segment of lines like this one
-        const size_t est = (size_t)((send - line) / std::max<int64_t>(1, p - line) + 2);
-        kept.reserve(est);
-        rows.reserve(est * (size_t)n_out);
-      }
-      kept.push_back(K);
-      rows.resize(rows.size() + (size_t)n_out);
-      parse_record(K, lend, rows.data() + rows.size() - (size_t)n_out, sc);
-    }
-  };
+  std::vector<GtParser::SegOut> seg_out(n_seg);
   {
     std::atomic<int> next_seg{0};
     auto worker = [&]() {
-      Scratch sc;
-      for (int si = next_seg.fetch_add(1); si < n_seg; si = next_seg.fetch_add(1)) scan(si, sc);
+      GtParser::Scratch sc;
+      for (int si = next_seg.fetch_add(1); si < n_seg; si = next_seg.fetch_add(1)) P.scan(seg[si], seg[si + 1], seg_out[si], sc);
     };
     const int nt = std::min(n_threads, n_seg);
     std::vector<std::thread> th;
@@ -342,40 +381,9 @@ extern "C" int64_t sai_vcf_parse_gt(const char* text, int64_t len, const char* c
     worker();
     for (auto& t : th) t.join();
   }
-  // rows of segment si start at row first[si]; a full output buffer stops in front of the first
-  // record that does not fit (the next call starts there)
-  std::vector<int64_t> first(n_seg + 1, 0);
-  for (int si = 0; si < n_seg; ++si) first[si + 1] = first[si] + (int64_t)seg_out[si].kept.size();
-  const int64_t n_rows = std::min<int64_t>(first[n_seg], rows_cap);
-  const char* consumed_to = complete_end;
-  if (first[n_seg] > rows_cap) {
-    int si = 0;
-    while (first[si + 1] <= rows_cap) ++si;
-    consumed_to = seg_out[si].kept[rows_cap - first[si]].line;
-  }
-  *bytes_consumed = (int64_t)(consumed_to - text);
-  if (n_rows == 0) return 0;
-  {
-    std::atomic<int> next_seg{0};
-    auto gather = [&]() {
-      for (int si = next_seg.fetch_add(1); si < n_seg; si = next_seg.fetch_add(1)) {
-        const SegOut& so = seg_out[si];
-        const int64_t take = std::min<int64_t>((int64_t)so.kept.size(), n_rows - first[si]);
-        if (take <= 0) continue;
-        for (int64_t r = 0; r < take; ++r) out_pos[first[si] + r] = so.kept[r].pos;
-        if (row_stride == n_out) {
-          memcpy(out_gt + first[si] * row_stride, so.rows.data(), (size_t)take * n_out);
-        } else {
-          for (int64_t r = 0; r < take; ++r) memcpy(out_gt + (first[si] + r) * row_stride, so.rows.data() + r * n_out, (size_t)n_out);
-        }
-      }
-    };
-    const int nt = std::min(n_threads, n_seg);
-    std::vector<std::thread> th;
-    for (int i = 1; i < nt; ++i) th.emplace_back(gather);
-    gather();
-    for (auto& t : th) t.join();
-  }
+  const KeptLine* dropped = nullptr;
+  const int64_t n_rows = P.gather(seg_out, out_pos, out_gt, row_stride, rows_cap, n_threads, &dropped);
+  *bytes_consumed = (int64_t)((dropped ? dropped->line : complete_end) - text);
   return n_rows;
 }
 
