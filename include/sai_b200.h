@@ -195,6 +195,20 @@ int64_t sai_bgzf_scan(const uint8_t* data, int64_t len, int64_t max_blocks, int6
                       int64_t* block_off, int64_t* out_off, int64_t* consumed);
 int sai_bgzf_inflate(const uint8_t* data, const int64_t* block_off, const int64_t* out_off,
                      int64_t n_blocks, uint8_t* out, int32_t n_threads);
+/* Fused bgzip read: blocks [0, n_blocks) as indexed by sai_bgzf_scan over the WHOLE rest of the
+ * file, inflated in groups and parsed by the thread that inflated them while the text is still
+ * in its cache -- the text never exists in memory as a whole.  `skip` = text offset of the first
+ * record (the byte behind the "#CHROM" line); the other arguments and the rows written are those
+ * of sai_vcf_parse_gt over the same text (a last line without a newline is complete).  Returns
+ * the number of rows, SAI_E_CAPACITY when rows_cap is too small (nothing is resumable: size the
+ * output from the text size, out_off[n_blocks] / (2 * n_out) rows are always enough), or another
+ * negative SAI_E_* code.  group_blocks <= 0: 16 blocks (~1 MB of text) per group. */
+int64_t sai_bgzf_parse_gt(const uint8_t* data, const int64_t* block_off, const int64_t* out_off,
+                          int64_t n_blocks, int64_t skip, const char* chrom, int64_t start,
+                          int64_t end, const int32_t* sample_column, const int32_t* sample_ploidy,
+                          int32_t n_out, const int32_t* anc_pos, const char* anc_allele,
+                          int64_t n_anc, int32_t* out_pos, int8_t* out_gt, int64_t row_stride,
+                          int64_t rows_cap, int32_t group_blocks, int32_t n_threads);
 /* The block decoder and checksum sai_bgzf_inflate uses (tests, tools): raw deflate stream
  * (RFC 1951) of known inflated size -> 1 on success, 0 on anything unexpected (sai_bgzf_inflate
  * then repeats the block with zlib); CRC-32 == zlib's crc32(0, data, len) (isa: 0 = PCLMULQDQ

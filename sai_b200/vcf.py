@@ -241,14 +241,18 @@ def load_population_group(
     return data, samples
 
 
-def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20, batch_bytes=256 << 20, on_size_hint=None):
+def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20, batch_bytes=256 << 20, on_size_hint=None,
+               on_bgzf=None):
     """Feeds the text of a VCF (plain, bgzip or gzip) to ``on_lines(addr, length) -> bytes consumed``
     in large buffers of whole-or-partial lines (an incomplete last line is carried to the next
     buffer), after calling ``on_header(line)`` once with the ``#CHROM`` line.  Plain text is
     mapped read-only and handed over in place; bgzip blocks are inflated in parallel by the
     native library; plain gzip streams through Python's reader.  ``on_size_hint(total_text_bytes)``
     is called first when the total is known without reading the text (plain: the file size;
-    bgzip: the sum of the blocks' ISIZE fields), so that the consumer can size its output once."""
+    bgzip: the sum of the blocks' ISIZE fields), so that the consumer can size its output once.
+    ``on_bgzf(base_addr, block_off, out_off, n_blocks, skip)``, when given, receives a bgzip file
+    as its block index instead of text (``skip`` = text offset of the first record): the fused
+    inflate + parse of ``sai_bgzf_parse_gt``."""
     import ctypes as C
 
     from . import _cabi
@@ -289,6 +293,42 @@ def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20,
                 max_blocks = 1 << 14
                 block_off = np.empty(max_blocks, dtype=np.int64)
                 out_off = np.empty(max_blocks + 1, dtype=np.int64)
+                if on_bgzf is not None:
+                    # index every block (18 header bytes each), find the #CHROM line in the first few, hand the rest over
+                    offs, outs, p, text_total = [], [], 0, 0
+                    while p < total:
+                        n = int(lib.sai_bgzf_scan(base + p, total - p, max_blocks, 1 << 62, block_off.ctypes.data,
+                                                  out_off.ctypes.data, C.byref(consumed)))
+                        if n < 0:
+                            _cabi.check(n)
+                        if n == 0 or consumed.value == 0:
+                            break
+                        offs.append(block_off[:n] + p)
+                        outs.append(out_off[1 : n + 1] + text_total)
+                        text_total += int(out_off[n])
+                        p += consumed.value
+                    if not offs:
+                        return
+                    all_boff = np.ascontiguousarray(np.concatenate(offs))
+                    all_ooff = np.ascontiguousarray(np.concatenate([np.zeros(1, dtype=np.int64)] + outs))
+                    n_all, k, h, he = int(all_boff.shape[0]), 16, -1, -1
+                    while True:
+                        k = min(k, n_all)
+                        head_buf = np.empty(int(all_ooff[k]) + 1, dtype=np.uint8)
+                        _cabi.check(lib.sai_bgzf_inflate(base, all_boff.ctypes.data, all_ooff.ctypes.data, k, head_buf.ctypes.data, n_threads))
+                        head = head_buf[: int(all_ooff[k])].tobytes()
+                        h = head.find(b"#CHROM")
+                        he = head.find(b"\n", h) if h >= 0 else -1
+                        if (h >= 0 and he >= 0) or k == n_all:
+                            break
+                        k *= 8
+                    if h < 0 or he < 0:
+                        return
+                    on_header(head[h:he])
+                    if on_size_hint is not None:
+                        on_size_hint(text_total - he)
+                    on_bgzf(base, all_boff, all_ooff, n_all, he + 1)
+                    return
                 at, carry = 0, b""
                 if on_size_hint is not None:  # the block headers alone give the size of the text
                     text_total, p = 0, 0
@@ -685,7 +725,7 @@ def chromosome_span(vcf_file: str, chr_name: str, n_threads: int = 0):
 
 
 def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chunk_bytes=64 << 20,
-                 batch_bytes=256 << 20):
+                 batch_bytes=256 << 20, fused_bgzf=True, group_blocks=0):
     """One pass of the native parser (``sai_vcf_parse_gt``) over the file.
     ``requests`` = list of (sample_name, ploidy); returns ``(pos, gt)`` with one
     int8 column per request, or ``None`` for the sample names line missing."""
@@ -765,6 +805,19 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
             at += consumed.value
         return at
 
+    def parse_bgzf(base: int, block_off, out_off, n_blocks: int, skip: int) -> None:
+        """Whole bgzip file: groups of blocks inflated and parsed by the same thread (no text buffer)."""
+        reserve((int(out_off[n_blocks]) - skip) // row_bytes + 1024)
+        n = lib.sai_bgzf_parse_gt(
+            base, block_off.ctypes.data, out_off.ctypes.data, n_blocks, skip, chr_name.encode(), region[0], region[1],
+            cols.ctypes.data, ploidies.ctypes.data, n_out,
+            anc_pos.ctypes.data if n_anc else None, anc_buf if n_anc else None, n_anc,
+            out["pos"].ctypes.data, out["gt"].ctypes.data, n_out, out["pos"].shape[0], group_blocks, n_threads,
+        )
+        if n < 0:
+            _cabi.check(int(n))
+        out["rows"] = int(n)
+
     def on_header(line: bytes):
         nonlocal cols, ploidies
         cols, ploidies = header_columns(line)
@@ -773,7 +826,8 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
     if start is not None and end is not None:
         handled = _scan_sorted_region(vcf_file, chr_name, int(start), int(end), on_header, parse_buffer, n_threads, batch_bytes)
     if not handled:
-        _scan_text(vcf_file, on_header, parse_buffer, n_threads, chunk_bytes, batch_bytes, on_size_hint)
+        _scan_text(vcf_file, on_header, parse_buffer, n_threads, chunk_bytes, batch_bytes, on_size_hint,
+                   parse_bgzf if fused_bgzf else None)
     if cols is None:
         return None
     n, cap = out["rows"], out["pos"].shape[0]

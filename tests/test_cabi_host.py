@@ -522,7 +522,8 @@ def test_bgzf_parallel_inflate_and_reader(tmp_path):
     req = [(f"s{i}", 2) for i in rng.permutation(n_smp)[:40]]
     p0, g0 = _native_read(str(plain), "1", None, None, req, None)
     assert p0.shape[0] == n_rec
-    for path, kw in ((gz, {}), (bgz, {}), (bgz, dict(batch_bytes=10_000)), (bgz, dict(batch_bytes=1))):
+    for path, kw in ((gz, {}), (bgz, {}), (bgz, dict(group_blocks=1)), (bgz, dict(fused_bgzf=False)),
+                     (bgz, dict(fused_bgzf=False, batch_bytes=10_000)), (bgz, dict(fused_bgzf=False, batch_bytes=1))):
         p1, g1 = _native_read(str(path), "1", None, None, req, None, **kw)
         assert np.array_equal(p0, p1) and np.array_equal(g0, g1), (path, kw)
     # no trailing newline + region filter
@@ -889,6 +890,50 @@ def test_all_populations_packer_matches_per_population_packer(n_ind, bits):
     if bits < 8:
         whole[n_sites // 2, 1] = vmax + 1
         assert lib.sai_pack_i8_all(C.byref(lay), ptrs, strides, n_sites, got.ctypes.data, 2) == _cabi.E_DOMAIN
+
+
+@pytest.mark.parametrize("block, final_newline", [(64, True), (300, False), (5000, True)])
+def test_fused_bgzf_read_matches_text_read(tmp_path, block, final_newline):
+    """`sai_bgzf_parse_gt` (groups of bgzip blocks inflated and parsed by the same thread) returns
+    the rows of the plain-text parse for every group size and thread count -- with blocks much
+    shorter than a line (a line spans many blocks and several groups; some groups contain no line
+    start at all), a header longer than a group, a last line without a newline, records of other
+    chromosomes, the ancestral-allele filter / flip and a region filter."""
+    from sai_b200.vcf import _native_read, write_bgzf
+
+    rng = np.random.default_rng(block)
+    n_smp, n_rec = 60, 400
+    tok = np.array(["0|0", "0|1", "1|1", ".|.", "1/0", "2|1"])
+    pos = np.cumsum(rng.integers(1, 40, size=n_rec))
+    lines = ["##fileformat=VCFv4.1", "##a long meta line " + "x" * 700,
+             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"sample_with_a_long_name_{i}" for i in range(n_smp))]
+    anc = {}
+    for i in range(n_rec):
+        chrom = "9" if i % 11 == 3 else "4"
+        n_here = n_smp if i % 7 else n_smp  # regular records
+        g = rng.choice(len(tok), size=n_here, p=[.7, .1, .08, .04, .04, .04])
+        fields = list(tok[g])
+        if i % 13 == 0:
+            fields[int(rng.integers(n_smp))] = "0|1:35"  # leaves the fast path
+        info = "." if i % 5 else "NS=3;DP=14;AF=0.5;" + "k" * int(rng.integers(0, 900))  # lines of very different lengths
+        lines.append(f"{chrom}\t{pos[i]}\t.\tA\tG\t.\t.\t{info}\t{'GT:DP' if i % 13 == 0 else 'GT'}\t" + "\t".join(fields))
+        if chrom == "4" and rng.random() < 0.8:
+            anc[int(pos[i])] = "A" if rng.random() < 0.6 else "G"
+    text = ("\n".join(lines) + ("\n" if final_newline else "")).encode()
+    plain, bgz = tmp_path / "f.vcf", tmp_path / "f.vcf.gz"
+    plain.write_bytes(text)
+    write_bgzf(str(bgz), text, block=block)
+    req = [(f"sample_with_a_long_name_{i}", int(p)) for i, p in zip(rng.permutation(n_smp)[:25], rng.choice([1, 2, 2, 2, 3], size=25))]
+    req2 = [(f"sample_with_a_long_name_{i}", 2) for i in range(10, 50)]  # all diploid, one run
+    for requests in (req, req2):
+        for anc_table in (None, anc):
+            for region in ((None, None), (int(pos[30]), int(pos[300]))):
+                p0, g0 = _native_read(str(plain), "4", region[0], region[1], requests, anc_table)
+                assert p0.shape[0] > 50
+                for kw in (dict(group_blocks=1, n_threads=1), dict(group_blocks=2, n_threads=3), dict(group_blocks=7, n_threads=2), dict(),
+                           dict(fused_bgzf=False)):
+                    p1, g1 = _native_read(str(bgz), "4", region[0], region[1], requests, anc_table, **kw)
+                    assert np.array_equal(p0, p1) and np.array_equal(g0, g1), (block, kw, region, anc_table is not None)
 
 
 # ---------------------------------------------------------------- BGZF block decoder + CRC-32 (N2)
