@@ -269,9 +269,9 @@ def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20,
             h = mm.find(b"#CHROM")
             he = mm.find(b"\n", h) if h >= 0 else -1
             if h >= 0 and he >= 0:
+                on_header(mm[h:he])
                 if on_size_hint is not None:
                     on_size_hint(len(mm) - he)
-                on_header(mm[h:he])
                 view = np.frombuffer(mm, dtype=np.uint8)
                 try:
                     body, length = he + 1, len(mm)
@@ -807,20 +807,30 @@ def _native_read(vcf_file, chr_name, start, end, requests, anc, n_threads=0, chu
 
     def parse_bgzf(base: int, block_off, out_off, n_blocks: int, skip: int) -> None:
         """Whole bgzip file: groups of blocks inflated and parsed by the same thread (no text buffer)."""
-        reserve((int(out_off[n_blocks]) - skip) // row_bytes + 1024)
-        n = lib.sai_bgzf_parse_gt(
-            base, block_off.ctypes.data, out_off.ctypes.data, n_blocks, skip, chr_name.encode(), region[0], region[1],
-            cols.ctypes.data, ploidies.ctypes.data, n_out,
-            anc_pos.ctypes.data if n_anc else None, anc_buf if n_anc else None, n_anc,
-            out["pos"].ctypes.data, out["gt"].ctypes.data, n_out, out["pos"].shape[0], group_blocks, n_threads,
-        )
+        text_bytes = int(out_off[n_blocks]) - skip
+        reserve(text_bytes // row_bytes + 1024)
+        while True:
+            n = lib.sai_bgzf_parse_gt(
+                base, block_off.ctypes.data, out_off.ctypes.data, n_blocks, skip, chr_name.encode(), region[0], region[1],
+                cols.ctypes.data, ploidies.ctypes.data, n_out,
+                anc_pos.ctypes.data if n_anc else None, anc_buf if n_anc else None, n_anc,
+                out["pos"].ctypes.data, out["gt"].ctypes.data, n_out, out["pos"].shape[0], group_blocks, n_threads,
+            )
+            # records shorter than the header promises (truncated lines) can outnumber the estimate: the fused
+            # read is not resumable, so repeat it with more room (a record is at least ~20 bytes of fixed columns)
+            if n == _cabi.E_CAPACITY and out["pos"].shape[0] < text_bytes // 20 + 1024:
+                reserve(min(text_bytes // 20 + 1024, 4 * out["pos"].shape[0]))
+                continue
+            break
         if n < 0:
             _cabi.check(int(n))
         out["rows"] = int(n)
 
     def on_header(line: bytes):
-        nonlocal cols, ploidies
+        nonlocal cols, ploidies, row_bytes
         cols, ploidies = header_columns(line)
+        # a record holds every sample of the file, not just the requested ones: >= 2 characters per sample column
+        row_bytes = max(row_bytes, 2 * (line.count(b"\t") - 8) + 18)
 
     handled = False
     if start is not None and end is not None:

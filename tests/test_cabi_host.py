@@ -936,6 +936,27 @@ def test_fused_bgzf_read_matches_text_read(tmp_path, block, final_newline):
                     assert np.array_equal(p0, p1) and np.array_equal(g0, g1), (block, kw, region, anc_table is not None)
 
 
+def test_fused_bgzf_read_with_truncated_records(tmp_path):
+    """Records with far fewer sample fields than the header promises outnumber the row estimate
+    (text size / minimum record size): the fused bgzip read reports that, the reader repeats it with
+    more room, and the rows equal the plain-text parse (absent columns = all alleles missing)."""
+    from sai_b200.vcf import _native_read, write_bgzf
+
+    n_smp, n_rec = 400, 3000
+    lines = ["#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n_smp))]
+    for i in range(n_rec):
+        lines.append(f"1\t{i + 1}\t.\tA\tG\t.\t.\t.\tGT\t" + "\t".join(["0|1"] * (3 if i % 50 else n_smp)))
+    text = ("\n".join(lines) + "\n").encode()
+    plain, bgz = tmp_path / "t.vcf", tmp_path / "t.vcf.gz"
+    plain.write_bytes(text)
+    write_bgzf(str(bgz), text, block=2000)
+    req = [(f"s{i}", 2) for i in (0, 2, 3, 399)]
+    p0, g0 = _native_read(str(plain), "1", None, None, req, None)
+    p1, g1 = _native_read(str(bgz), "1", None, None, req, None)
+    assert p0.shape[0] == n_rec and np.array_equal(p0, p1) and np.array_equal(g0, g1)
+    assert (g1[1] == [1, 1, -2, -2]).all() and (g1[0] == 1).all()
+
+
 # ---------------------------------------------------------------- BGZF block decoder + CRC-32 (N2)
 def test_crc32_matches_zlib():
     """`sai_crc32` (PCLMULQDQ folding where the CPU has it, slicing tables otherwise) == zlib.crc32
