@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -171,6 +172,11 @@ int64_t sai_bgzf_parse_gt(const uint8_t* data, const int64_t* block_off, const i
     return SAI_E_ARG;
   }
   if (n_blocks == 0) return 0;
+  for (int64_t b = 0; b < n_blocks; ++b)  // SAM spec 4.1: a block holds at most 64 KB of text
+    if (out_off[b + 1] < out_off[b] || out_off[b + 1] - out_off[b] > (1 << 16)) {
+      set_error("BGZF block %lld claims %lld bytes of text", (long long)b, (long long)(out_off[b + 1] - out_off[b]));
+      return SAI_E_ARG;
+    }
   const int64_t G = group_blocks > 0 ? group_blocks : 16;  // ~1 MB of text: stays in the core's L2
   const int64_t n_groups = (n_blocks + G - 1) / G;
   if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -178,6 +184,7 @@ int64_t sai_bgzf_parse_gt(const uint8_t* data, const int64_t* block_off, const i
   std::vector<GtParser::SegOut> seg_out(n_groups);
   std::atomic<int64_t> next{0};
   std::atomic<int64_t> bad{-1};
+  std::atomic<int> oom{0};
   auto work = [&]() {
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
@@ -187,6 +194,7 @@ int64_t sai_bgzf_parse_gt(const uint8_t* data, const int64_t* block_off, const i
     }
     GtParser::Scratch sc;
     std::vector<uint8_t> text;
+    try {
     for (;;) {
       const int64_t g = next.fetch_add(1);
       if (g >= n_groups || bad.load(std::memory_order_relaxed) >= 0) break;
@@ -243,6 +251,10 @@ int64_t sai_bgzf_parse_gt(const uint8_t* data, const int64_t* block_off, const i
       // the records point into `text`, which the next group overwrites: only pos and the rows survive
       for (auto& k : seg_out[g].kept) k.samples = k.line = nullptr;
     }
+    } catch (const std::bad_alloc&) {
+      oom.store(1);
+      bad.store(0);  // stops the other threads
+    }
     inflateEnd(&zs);
   };
   if (n_threads <= 1) {
@@ -251,6 +263,10 @@ int64_t sai_bgzf_parse_gt(const uint8_t* data, const int64_t* block_off, const i
     std::vector<std::thread> th;
     for (int i = 0; i < n_threads; ++i) th.emplace_back(work);
     for (auto& t : th) t.join();
+  }
+  if (oom.load()) {
+    set_error("sai_bgzf_parse_gt: out of host memory");
+    return SAI_E_NOMEM;
   }
   if (bad.load() >= 0) {
     set_error("BGZF block %lld is corrupt", (long long)bad.load());

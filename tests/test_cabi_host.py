@@ -955,6 +955,22 @@ def test_fused_bgzf_read_with_truncated_records(tmp_path):
     p1, g1 = _native_read(str(bgz), "1", None, None, req, None)
     assert p0.shape[0] == n_rec and np.array_equal(p0, p1) and np.array_equal(g0, g1)
     assert (g1[1] == [1, 1, -2, -2]).all() and (g1[0] == 1).all()
+    # a corrupt block is reported by the fused read as well (payload damaged -> CRC / decoder; ISIZE damaged -> refused)
+    import struct
+
+    raw = bytearray(bgz.read_bytes())
+    bsize = struct.unpack_from("<H", raw, 16)[0] + 1
+    damaged = bytearray(raw)
+    damaged[bsize + 40] ^= 0x5A  # inside the second block's deflate data
+    (tmp_path / "bad1.vcf.gz").write_bytes(bytes(damaged))
+    with pytest.raises(ValueError, match="corrupt"):
+        _native_read(str(tmp_path / "bad1.vcf.gz"), "1", None, None, req, None)
+    damaged = bytearray(raw)
+    bsize2 = struct.unpack_from("<H", raw, bsize + 16)[0] + 1
+    struct.pack_into("<I", damaged, bsize + bsize2 - 4, 0x7FFFFFF0)  # ISIZE of the second block
+    (tmp_path / "bad2.vcf.gz").write_bytes(bytes(damaged))
+    with pytest.raises((ValueError, MemoryError)):
+        _native_read(str(tmp_path / "bad2.vcf.gz"), "1", None, None, req, None)
 
 
 # ---------------------------------------------------------------- BGZF block decoder + CRC-32 (N2)
