@@ -94,6 +94,10 @@ int64_t sai_bgzf_scan(const uint8_t* data, int64_t len, int64_t max_blocks, int6
     }
     if (bs == 0) break;  // incomplete block: the caller supplies more bytes
     const int64_t isize = le32(data + at + bs - 4);
+    if (isize > (1 << 16)) {  // SAM spec 4.1: at most 64 KB of text per block
+      set_error("BGZF block at offset %lld claims %lld bytes of text", (long long)at, (long long)isize);
+      return SAI_E_ARG;
+    }
     if (n > 0 && out + isize > max_out_bytes) break;
     block_off[n] = at;
     out += isize;
