@@ -209,6 +209,11 @@ int64_t sai_bgzf_parse_gt(const uint8_t* data, const int64_t* block_off, const i
                           int32_t n_out, const int32_t* anc_pos, const char* anc_allele,
                           int64_t n_anc, int32_t* out_pos, int8_t* out_gt, int64_t row_stride,
                           int64_t rows_cap, int32_t group_blocks, int32_t n_threads);
+/* A plain single-member gzip file (not bgzip) into `out` in one call with the same decoder:
+ * returns the text length (= the trailer's ISIZE), SAI_E_CAPACITY when out_cap is smaller,
+ * SAI_E_DOMAIN when the file is not what the fast path handles -- several members, more than
+ * 4 GB of text, or corrupt: read it with a streaming gzip reader instead -- or SAI_E_ARG. */
+int64_t sai_gzip_inflate(const uint8_t* data, int64_t len, uint8_t* out, int64_t out_cap);
 /* The block decoder and checksum sai_bgzf_inflate uses (tests, tools): raw deflate stream
  * (RFC 1951) of known inflated size -> 1 on success, 0 on anything unexpected (sai_bgzf_inflate
  * then repeats the block with zlib); CRC-32 == zlib's crc32(0, data, len) (isa: 0 = PCLMULQDQ

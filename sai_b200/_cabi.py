@@ -107,6 +107,7 @@ SYMBOLS = {
     "sai_bgzf_scan": (_I64, [_P, _I64, _I64, _I64, _P, _P, C.POINTER(_I64)]),
     "sai_bgzf_inflate": (C.c_int, [_P, _P, _P, _I64, _P, _I32]),
     "sai_bgzf_parse_gt": (_I64, [_P, _P, _P, _I64, _I64, C.c_char_p, _I64, _I64, _P, _P, _I32, _P, _P, _I64, _P, _P, _I64, _I64, _I32, _I32]),
+    "sai_gzip_inflate": (_I64, [_P, _I64, _P, _I64]),
     "sai_inflate_raw": (_I32, [_P, _I64, _P, _I64]),
     "sai_crc32": (C.c_uint32, [_P, _I64, _I32]),
     "sai_site_counts": (C.c_int, [_LAY, _P, _I64, _I64, _P, _P, _I64, _I32, _P]),

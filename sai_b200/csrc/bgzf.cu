@@ -285,6 +285,47 @@ int64_t sai_bgzf_parse_gt(const uint8_t* data, const int64_t* block_off, const i
   return n_rows;
 }
 
+// A plain (single-member) gzip file in one go: RFC 1952 header, raw deflate stream, CRC-32 + ISIZE.
+int64_t sai_gzip_inflate(const uint8_t* data, int64_t len, uint8_t* out, int64_t out_cap) {
+  if (!data || len < 18 || out_cap < 0 || (out_cap > 0 && !out)) {
+    set_error("sai_gzip_inflate: bad argument");
+    return SAI_E_ARG;
+  }
+  if (data[0] != 31 || data[1] != 139 || data[2] != 8 || (data[3] & 0xe0)) {
+    set_error("not a gzip file");
+    return SAI_E_ARG;
+  }
+  const int flg = data[3];
+  int64_t at = 10;
+  if (flg & 4) {  // FEXTRA
+    if (at + 2 > len) return SAI_E_ARG;
+    at += 2 + (int64_t)le16(data + at);
+  }
+  for (int bit : {8, 16})  // FNAME, FCOMMENT: zero-terminated
+    if (flg & bit) {
+      const void* z = at < len ? memchr(data + at, 0, (size_t)(len - at)) : nullptr;
+      if (!z) return SAI_E_ARG;
+      at = static_cast<const uint8_t*>(z) - data + 1;
+    }
+  if (flg & 2) at += 2;  // FHCRC
+  if (at + 8 > len) {
+    set_error("truncated gzip file");
+    return SAI_E_ARG;
+  }
+  const int64_t isize = le32(data + len - 4);  // of a single-member file below 4 GB of text
+  if (isize > out_cap) {
+    set_error("gzip file holds %lld bytes, buffer has %lld", (long long)isize, (long long)out_cap);
+    return SAI_E_CAPACITY;
+  }
+  size_t used = 0;
+  if (!inflate_raw(data + at, (size_t)(len - at - 8), out, (size_t)isize, &used) || (int64_t)used != len - at - 8 ||
+      crc32_fast(out, (size_t)isize, 0) != le32(data + len - 8)) {
+    set_error("not a single-member gzip file the fast decoder handles (several members, > 4 GB, or corrupt)");
+    return SAI_E_DOMAIN;
+  }
+  return isize;
+}
+
 int32_t sai_inflate_raw(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_len) {
   if (!in || in_len < 0 || out_len < 0 || (out_len > 0 && !out)) return 0;
   return inflate_raw(in, (size_t)in_len, out, (size_t)out_len) ? 1 : 0;

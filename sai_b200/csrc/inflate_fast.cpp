@@ -315,7 +315,7 @@ bool inflate_block(BitReader& br, const Tables& T, uint8_t* const out_begin, uin
 }  // namespace
 
 // Inflates the raw deflate stream [in, in + in_len) into exactly out_len bytes at out.
-bool inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) {
+bool inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len, size_t* consumed) {
   static const Tables* const fixed = [] {
     Tables* t = new Tables;
     return build_fixed_tables(*t) ? t : nullptr;
@@ -353,7 +353,12 @@ bool inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len)
     }
     if (last) break;
   }
-  return out == out_end && !br.past_end();
+  if (out != out_end || br.past_end()) return false;
+  if (consumed) {  // whole bytes still in the bit buffer (minus the padding shifted in at the end) were not used
+    const int64_t unused = (int64_t)(br.bits >> 3) - br.overrun;
+    *consumed = (size_t)((br.in - in) - (unused > 0 ? unused : 0));
+  }
+  return true;
 }
 
 // ---------------------------------------------------------------------------------- CRC-32

@@ -384,6 +384,47 @@ def _scan_text(vcf_file, on_header, on_lines, n_threads=0, chunk_bytes=64 << 20,
             finally:
                 del view
     else:
+        # a plain gzip file of moderate size: the whole text in one native call (sai_gzip_inflate: the
+        # bgzip block decoder on a single-member file, ~8x Python's gzip reader); several members, very
+        # large files or anything unexpected take the streaming reader below
+        import mmap
+        import struct
+
+        size = os.path.getsize(vcf_file)
+        if 18 <= size <= (1 << 30):
+            with open(vcf_file, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+                isize = struct.unpack("<I", mm[size - 4 : size])[0]
+                text = None
+                if isize <= (3 << 30) and isize >= size // 2:  # (a wrapped ISIZE of a > 4 GB text would be implausibly small)
+                    view = np.frombuffer(mm, dtype=np.uint8)
+                    try:
+                        text = np.empty(isize + 1, dtype=np.uint8)
+                        if int(lib.sai_gzip_inflate(view.ctypes.data, size, text.ctypes.data, isize)) != isize:
+                            text = None
+                    except MemoryError:
+                        text = None
+                    finally:
+                        del view
+            if text is not None:
+                head = text[: min(isize, 1 << 20)].tobytes()
+                h = head.find(b"#CHROM")
+                he = head.find(b"\n", h) if h >= 0 else -1
+                if h < 0 or he < 0:  # an unusually long header: look through everything
+                    head = text[:isize].tobytes()
+                    h = head.find(b"#CHROM")
+                    he = head.find(b"\n", h) if h >= 0 else -1
+                if h < 0 or he < 0:
+                    return
+                on_header(head[h:he])
+                if on_size_hint is not None:
+                    on_size_hint(isize - he)
+                length = isize
+                if length > he + 1 and text[length - 1] != 10:
+                    text[length] = 10  # last line without a newline
+                    length += 1
+                if length > he + 1:
+                    on_lines(text.ctypes.data + he + 1, length - he - 1)
+                return
         with gzip.open(vcf_file, "rb") as f:
             carry = b""
             while True:

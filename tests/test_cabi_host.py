@@ -1074,6 +1074,50 @@ def test_inflate_raw_rejects_corrupt_streams_safely():
     assert refused > 1000
 
 
+def test_plain_gzip_fast_path(tmp_path):
+    """`sai_gzip_inflate` (a single-member gzip file in one native call) returns gzip's text for
+    headers with and without a file name, refuses files with several members or a damaged payload
+    (SAI_E_DOMAIN: the reader then streams through Python's gzip module), and `_native_read` gives
+    the same rows for a plain file, its one-member gzip and a two-member gzip."""
+    import gzip
+
+    from sai_b200 import _cabi
+    from sai_b200.vcf import _native_read
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(4)
+    n_smp, n_rec = 30, 500
+    tok = np.array(["0|0", "0|1", "1|1", ".|1"])
+    lines = ["##x", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n_smp))]
+    for i in range(n_rec):
+        lines.append(f"5\t{3 * i + 1}\t.\tC\tT\t.\t.\t.\tGT\t" + "\t".join(tok[rng.integers(0, 4, n_smp)]))
+    text = ("\n".join(lines) + "\n").encode()
+    plain, one, named, two = tmp_path / "p.vcf", tmp_path / "one.vcf.gz", tmp_path / "named.vcf.gz", tmp_path / "two.vcf.gz"
+    plain.write_bytes(text)
+    one.write_bytes(gzip.compress(text, 6))
+    with gzip.GzipFile(filename="inner_name.vcf", mode="wb", fileobj=open(named, "wb")) as f:
+        f.write(text)
+    half = text.index(b"\n", len(text) // 2) + 1
+    two.write_bytes(gzip.compress(text[:half]) + gzip.compress(text[half:]))
+    for path, want in ((one, len(text)), (named, len(text)), (two, _cabi.E_DOMAIN)):
+        raw = np.frombuffer(path.read_bytes(), dtype=np.uint8)
+        out = np.full(len(text) + 8, 0xCD, dtype=np.uint8)
+        got = lib.sai_gzip_inflate(raw.ctypes.data, raw.size, out.ctypes.data, len(text))
+        assert got == want, path
+        if want > 0:
+            assert out[: len(text)].tobytes() == text and (out[len(text):] == 0xCD).all()
+            assert lib.sai_gzip_inflate(raw.ctypes.data, raw.size, out.ctypes.data, len(text) - 1) == _cabi.E_CAPACITY
+            bad = raw.copy()
+            bad[raw.size // 2] ^= 0x10
+            assert lib.sai_gzip_inflate(bad.ctypes.data, bad.size, out.ctypes.data, len(text)) == _cabi.E_DOMAIN
+    req = [(f"s{i}", 2) for i in (3, 4, 5, 29, 0)]
+    p0, g0 = _native_read(str(plain), "5", None, None, req, None)
+    assert p0.shape[0] == n_rec
+    for path in (one, named, two):
+        p1, g1 = _native_read(str(path), "5", None, None, req, None)
+        assert np.array_equal(p0, p1) and np.array_equal(g0, g1), path
+
+
 # ---------------------------------------------------------------- whole-genome sharding (host logic)
 def test_shard_genome_follows_split_windows_ranges():
     """`shard_genome` cuts the flattened (chromosome, window) list like
